@@ -1,0 +1,188 @@
+/* mcrt.h -- C ABI of libmcrt.so: the B200-native (sm_100a) replacement for the per-frame
+ * simulation hot path of thepochynsons/MCRay-Tracing.
+ *
+ * The reference exports no plugin/FFI interface: it is one executable (`mattausch <scene>`,
+ * src/main.cpp:42-50) whose frame loop (src/main.cpp:92-152) calls
+ *     scene::cast_rays<S,E>(transducer&)            src/scene.h:29-30, src/scene.cpp:50-183
+ *     the echo accumulation loop                     src/main.cpp:106-144
+ *     rf_image::{clear,add_echo,convolve,envelope,postprocess}   src/rfimage.h:33-140,161-164
+ * on objects built once by scene::scene(json, transducer&) (src/scene.cpp:16-31),
+ * transducer<N>::transducer (src/transducer.h:24-62), psf<...>::psf (src/psf.h:34-58) and
+ * volume<...>::volume (src/volume.h:19-35).  This header is that in-process seam as a C ABI:
+ * plain pointers and sizes, no C++/torch types, negative return codes instead of exceptions
+ * (the reference reports errors as exceptions caught at src/main.cpp:154-159).
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * All compute runs in hand-written CUDA kernels; there is NO CPU fallback: every entry point
+ * that needs the GPU fails with MCRT_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef MCRT_H
+#define MCRT_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCRT_OK 0
+#define MCRT_ERR_INVALID (-1)   /* bad argument */
+#define MCRT_ERR_SCENE (-2)     /* "Error while loading scene: ..." (src/scene.cpp:23-26) */
+#define MCRT_ERR_CUDA (-3)      /* CUDA runtime / no usable device */
+#define MCRT_ERR_NOMEM (-4)
+
+typedef struct mcrt_ctx mcrt_ctx; /* opaque; owns the device BVH, scatterer volume, streams, graphs */
+
+/* probe pose: replaces transducer::setPosition / the const `angles` (src/transducer.h:120-137) */
+typedef struct mcrt_pose {
+    float pos[3];        /* "transducerPosition", world cm (src/main.cpp:65,72) */
+    float angles_deg[3]; /* "transducerAngles" x,y,z degrees (src/main.cpp:68-69) */
+} mcrt_pose;
+
+/* Acquisition parameters: the constexpr block of src/main.cpp:23-37,54 made runtime.
+ * mcrt_default_params() fills in the reference's values. */
+typedef struct mcrt_params {
+    int32_t elements;        /* transducer_elements 512          main.cpp:26 */
+    int32_t samples;         /* samples_te 5                     main.cpp:27 */
+    int32_t max_depth;       /* ray::max_depth 10 (<= 16)        ray.h:23    */
+    float frequency_mhz;     /* transducer_frequency 4.5f        main.cpp:24 */
+    double radius_cm;        /* transducer_radius 3              main.cpp:29 */
+    double fov_deg;          /* transducer_amplitude 60          main.cpp:28 */
+    double depth_cm;         /* ultrasound_depth 15              main.cpp:30 */
+    uint32_t speed_of_sound; /* 1500                             main.cpp:23 */
+    uint32_t resolution_um;  /* 145: psf / scatterer-volume grid main.cpp:33 */
+    int32_t psf_axial;       /* 7  (odd)                         main.cpp:34 */
+    int32_t psf_lateral;     /* 13 (odd)                         main.cpp:34 */
+    float psf_var_x;         /* 0.05f                            main.cpp:54 */
+    float psf_var_y;         /* 0.2f                             main.cpp:54 */
+    int32_t deterministic;   /* 1: roughness off (cos theta' = 1, thickness q = 0); DESIGN.md "Deterministic mode" */
+    int32_t scan_rows;       /* 400                              rfimage.h:26 */
+    int32_t scan_cols;       /* 500                              rfimage.h:26 */
+    float axial_scale;       /* 1.0f; >1 refines the axial sampling grid (extension) */
+    int32_t rf_layout;       /* 0: rf_out[pose][element][row] (scanline-major, native);
+                                1: rf_out[pose][row][element] = cv::Mat(max_rows, columns), rfimage.h:24 */
+} mcrt_params;
+
+/* A ray segment (ray_physics::segment, src/ray.h:28-36) plus parity-debug fields. */
+typedef struct mcrt_segment {
+    float from[3];
+    float to[3];
+    float dir[3];
+    float reflected_intensity;
+    float initial_intensity;
+    float attenuation;
+    double distance_traveled; /* mm, from the transducer to the start of the segment */
+    int32_t media_id;         /* index into the scene's material array */
+    int32_t tri_id;           /* global triangle id hit at the end of the segment, -1 = miss */
+    int32_t mesh_id;          /* -1 = miss */
+    float hit_fraction;       /* closest-hit fraction along [from+0.1*dir, to]; 1 on a miss */
+} mcrt_segment;
+
+/* In-memory scene description (what scene::parse_config + load_mesh_from_obj produce,
+ * src/scene.cpp:185-247, src/objloader.h:154-161) for callers that do not go through files. */
+typedef struct mcrt_scene_arrays {
+    int32_t n_materials;
+    const float* materials8;              /* n_materials x {impedance, attenuation, mu0, mu1, sigma,
+                                             specularity, shininess, thickness}  (src/mesh.h:7-10) */
+    int32_t starting_material;
+    int32_t n_meshes;
+    const int32_t* mesh_material_inside;  /* src/mesh.h:18 */
+    const int32_t* mesh_material_outside; /* src/mesh.h:19 */
+    const int32_t* mesh_vascular;         /* src/mesh.h:15 */
+    const float* mesh_deltas;             /* n_meshes x 3, src/mesh.h:16 */
+    const int64_t* tri_offsets;           /* n_meshes + 1 */
+    const float* tri_vertices;            /* 9 floats per triangle, OBJ space, objloader.h order */
+    float scaling;                        /* "scaling" */
+    float origin[3];                      /* "origin"  */
+    float spacing[3];                     /* "spacing" */
+} mcrt_scene_arrays;
+
+typedef struct mcrt_info {
+    int32_t rows;             /* RF samples per scanline: rfimage.h:180 (465 by default) */
+    int32_t cols;             /* = elements */
+    int32_t scan_rows, scan_cols;
+    int32_t n_materials, n_meshes;
+    int64_t n_triangles;
+    int64_t n_bvh_nodes;
+    int32_t device;
+    int32_t sm_count;
+    float start_pose[6];      /* the scene file's transducerPosition / transducerAngles */
+    double axial_resolution_mm, time_step_us, row_period_us, max_travel_time_us;
+} mcrt_info;
+
+typedef struct mcrt_stats {   /* of the most recent mcrt_simulate call */
+    int64_t poses;
+    int64_t segments;         /* closest-hit queries = the reference's `tests` counter (scene.cpp:118) */
+    int64_t march_steps;      /* scatterer-volume samples (main.cpp:124-136) */
+    int64_t kernel_launches;  /* kernels launched by this library inside the call */
+    float ms_total;           /* device time of the call, CUDA events on the library's stream */
+    float ms_trace, ms_accumulate, ms_post; /* only filled when profiling stages (mcrt_set_option) */
+} mcrt_stats;
+
+int mcrt_default_params(mcrt_params* p);
+
+/* replaces: main.cpp:52-81 (volume, psf, rf_image, json, transducer, scene construction).
+ * Accepts the reference's scene files unchanged.  Extensions: missing "shininess"/"thickness"
+ * default to 1e6 / 0; a non-existent "workingDirectory" falls back to the scene file's directory. */
+int mcrt_create(const char* scene_json_path, const mcrt_params* params, int device, mcrt_ctx** out);
+int mcrt_create_from_arrays(const mcrt_scene_arrays* scene, const mcrt_params* params, int device, mcrt_ctx** out);
+void mcrt_destroy(mcrt_ctx* ctx);
+const char* mcrt_last_error(void); /* thread-local, never NULL */
+
+int mcrt_get_info(const mcrt_ctx* ctx, mcrt_info* info);
+int mcrt_get_stats(const mcrt_ctx* ctx, mcrt_stats* stats);
+/* options: "profile_stages"=0/1 (per-stage events, disables the CUDA graph), "use_graph"=0/1,
+ * "max_batch_poses"=N */
+int mcrt_set_option(mcrt_ctx* ctx, const char* name, int64_t value);
+
+/* replaces one iteration of main.cpp:92-152 per pose: rf_image.clear(); scene.cast_rays();
+ * echo accumulation; rf_image.convolve(psf); rf_image.envelope(); rf_image.postprocess().
+ * Pose i is simulated as frame (first_frame + i) of the Philox stream `seed`.
+ * rf_out:   n_poses x elements x rows float32 (layout per params.rf_layout), host OR device pointer.
+ * scan_out: n_poses x scan_rows x scan_cols float32 (cv::remap of rfimage.h:139), host or device, nullable. */
+int mcrt_simulate(mcrt_ctx* ctx, const mcrt_pose* poses, int32_t n_poses, uint64_t seed, uint64_t first_frame,
+                  float* rf_out, float* scan_out);
+
+/* Same, but rf_out/scan_out must be DEVICE pointers and nothing is synchronised: the work is
+ * enqueued on `cuda_stream` (a cudaStream_t passed as void*; NULL = the library's own stream)
+ * so a caller can overlap it or follow it with a collective. */
+int mcrt_simulate_async(mcrt_ctx* ctx, const mcrt_pose* poses, int32_t n_poses, uint64_t seed, uint64_t first_frame,
+                        float* rf_out_dev, float* scan_out_dev, void* cuda_stream);
+
+/* parity hook for scene::cast_rays (scene.cpp:50-183): segments[elements][samples][max_depth],
+ * n_segments[elements][samples]; host pointers. */
+int mcrt_trace_debug(mcrt_ctx* ctx, const mcrt_pose* pose, uint64_t seed, uint64_t frame, mcrt_segment* segments,
+                     int32_t* n_segments);
+
+/* ---- stage-level entry points (each one is the CUDA kernel of that stage; used by the parity
+ * tests and by callers that want only part of the chain).  Host pointers unless noted. ---- */
+
+/* btCollisionWorld::rayTest + ClosestRayResultCallback (scene.cpp:115-126) for n segments
+ * [from,to]: tri_id (-1 miss), mesh_id, fraction, hit point and origin-facing unit normal. */
+int mcrt_closest_hit(mcrt_ctx* ctx, int64_t n, const float* from3, const float* to3, int32_t* tri_id, int32_t* mesh_id,
+                     float* fraction, float* point3, float* normal3);
+/* transducer<N>::element(i) for a pose (transducer.h:24-67) */
+int mcrt_transducer_elements(mcrt_ctx* ctx, const mcrt_pose* pose, float* pos3, float* dir3);
+/* main.cpp:106-144 on caller-supplied segments -> raw (un-convolved) RF, scanline-major [elements][rows] */
+int mcrt_accumulate(mcrt_ctx* ctx, const mcrt_segment* segments, const int32_t* n_segments, float* rf_out);
+/* rf_image::convolve + rf_image::envelope (rfimage.h:93-123, 54-91) on a [cols][rows]
+ * scanline-major image; flags bit0 = convolve, bit1 = envelope.  Any rows/cols/tap counts. */
+int mcrt_postprocess(mcrt_ctx* ctx, const float* rf_in, int32_t cols, int32_t rows, const float* axial, int32_t n_axial,
+                     const float* lateral, int32_t n_lateral, int32_t flags, float* rf_out);
+/* rf_image::create_mapping + cv::remap (rfimage.h:183-215, 139) on the ctx's geometry */
+int mcrt_scan_convert(mcrt_ctx* ctx, const float* rf_in /* [cols][rows] */, float* scan_out);
+int mcrt_get_psf_taps(const mcrt_ctx* ctx, float* axial, float* lateral);
+/* scene as loaded (for loader parity): local-frame vertices (v_obj*scaling) 9 floats/triangle in
+ * objloader order, mesh id per triangle, body origin per mesh (scene.cpp:313-324) */
+int mcrt_get_scene(const mcrt_ctx* ctx, float* tri_local9, int32_t* tri_mesh, float* mesh_origin3, float* materials8);
+/* scatterer volume as uploaded: 256^3 x {texture_noise, scattering_probability} (volume.h:19-35) */
+int mcrt_get_volume(const mcrt_ctx* ctx, float* out);
+
+/* numerics contract self-test: evaluates the shared transcendentals ON THE DEVICE.
+ * op 0 expf, 1 logf, 2 powf(a,b), 3 sin (double), 4 cos (double), 5 philox (a=counter as float bits) */
+int mcrt_numerics_probe(int device, int32_t op, int64_t n, const double* a, const double* b, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCRT_H */

@@ -1,0 +1,296 @@
+"""ctypes binding of libmcrt.so (include/mcrt.h) -- the thin Python mirror used by the parity
+tests, bench.py and the torch.distributed sweep driver.  All compute happens inside the library's
+CUDA kernels; this module only marshals pointers.  It fails loudly if the library is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libmcrt.so"
+
+MCRT_OK = 0
+MCRT_ERR_INVALID, MCRT_ERR_SCENE, MCRT_ERR_CUDA, MCRT_ERR_NOMEM = -1, -2, -3, -4
+
+
+class McrtError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[mcrt {code}] {message}")
+        self.code = code
+        self.message = message
+
+
+class Params(C.Structure):
+    """mcrt_params (main.cpp:23-37,54 made runtime)."""
+    _fields_ = [("elements", C.c_int32), ("samples", C.c_int32), ("max_depth", C.c_int32), ("frequency_mhz", C.c_float),
+                ("radius_cm", C.c_double), ("fov_deg", C.c_double), ("depth_cm", C.c_double), ("speed_of_sound", C.c_uint32),
+                ("resolution_um", C.c_uint32), ("psf_axial", C.c_int32), ("psf_lateral", C.c_int32), ("psf_var_x", C.c_float),
+                ("psf_var_y", C.c_float), ("deterministic", C.c_int32), ("scan_rows", C.c_int32), ("scan_cols", C.c_int32),
+                ("axial_scale", C.c_float), ("rf_layout", C.c_int32)]
+
+
+class Pose(C.Structure):
+    _fields_ = [("pos", C.c_float * 3), ("angles_deg", C.c_float * 3)]
+
+
+class SceneArrays(C.Structure):
+    _fields_ = [("n_materials", C.c_int32), ("materials8", C.c_void_p), ("starting_material", C.c_int32), ("n_meshes", C.c_int32),
+                ("mesh_material_inside", C.c_void_p), ("mesh_material_outside", C.c_void_p), ("mesh_vascular", C.c_void_p),
+                ("mesh_deltas", C.c_void_p), ("tri_offsets", C.c_void_p), ("tri_vertices", C.c_void_p), ("scaling", C.c_float),
+                ("origin", C.c_float * 3), ("spacing", C.c_float * 3)]
+
+
+class Info(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("scan_rows", C.c_int32), ("scan_cols", C.c_int32), ("n_materials", C.c_int32),
+                ("n_meshes", C.c_int32), ("n_triangles", C.c_int64), ("n_bvh_nodes", C.c_int64), ("device", C.c_int32),
+                ("sm_count", C.c_int32), ("start_pose", C.c_float * 6), ("axial_resolution_mm", C.c_double), ("time_step_us", C.c_double),
+                ("row_period_us", C.c_double), ("max_travel_time_us", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("poses", C.c_int64), ("segments", C.c_int64), ("march_steps", C.c_int64), ("kernel_launches", C.c_int64),
+                ("ms_total", C.c_float), ("ms_trace", C.c_float), ("ms_accumulate", C.c_float), ("ms_post", C.c_float)]
+
+
+SEGMENT_DTYPE = np.dtype([("from", np.float32, 3), ("to", np.float32, 3), ("dir", np.float32, 3),
+                          ("reflected_intensity", np.float32), ("initial_intensity", np.float32), ("attenuation", np.float32),
+                          ("distance_traveled", np.float64), ("media_id", np.int32), ("tri_id", np.int32), ("mesh_id", np.int32),
+                          ("hit_fraction", np.float32)], align=True)
+assert SEGMENT_DTYPE.itemsize == 72
+
+EXPORTS = ["mcrt_default_params", "mcrt_create", "mcrt_create_from_arrays", "mcrt_destroy", "mcrt_last_error", "mcrt_get_info",
+           "mcrt_get_stats", "mcrt_set_option", "mcrt_simulate", "mcrt_simulate_async", "mcrt_trace_debug", "mcrt_closest_hit",
+           "mcrt_transducer_elements", "mcrt_accumulate", "mcrt_postprocess", "mcrt_scan_convert", "mcrt_get_psf_taps",
+           "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe"]
+
+
+def build_library(force: bool = False, verbose: bool = False) -> Path:
+    """Compile libmcrt.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    csrc = PKG_DIR / "csrc"
+    cmd = ["make", "-C", str(csrc), "all"] + (["-B"] if force else [])
+    subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not LIB_PATH.exists():
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(str(LIB_PATH))
+        L.mcrt_last_error.restype = C.c_char_p
+        vp = C.c_void_p
+        L.mcrt_default_params.argtypes = [vp]
+        L.mcrt_create.argtypes = [C.c_char_p, vp, C.c_int, vp]
+        L.mcrt_create_from_arrays.argtypes = [vp, vp, C.c_int, vp]
+        L.mcrt_destroy.argtypes = [vp]
+        L.mcrt_destroy.restype = None
+        L.mcrt_get_info.argtypes = [vp, vp]
+        L.mcrt_get_stats.argtypes = [vp, vp]
+        L.mcrt_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+        L.mcrt_simulate.argtypes = [vp, vp, C.c_int32, C.c_uint64, C.c_uint64, vp, vp]
+        L.mcrt_simulate_async.argtypes = [vp, vp, C.c_int32, C.c_uint64, C.c_uint64, vp, vp, vp]
+        L.mcrt_trace_debug.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, vp]
+        L.mcrt_closest_hit.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
+        L.mcrt_transducer_elements.argtypes = [vp, vp, vp, vp]
+        L.mcrt_accumulate.argtypes = [vp, vp, vp, vp]
+        L.mcrt_postprocess.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, C.c_int32, vp, C.c_int32, C.c_int32, vp]
+        L.mcrt_scan_convert.argtypes = [vp, vp, vp]
+        L.mcrt_get_psf_taps.argtypes = [vp, vp, vp]
+        L.mcrt_get_scene.argtypes = [vp, vp, vp, vp, vp]
+        L.mcrt_get_volume.argtypes = [vp, vp]
+        L.mcrt_numerics_probe.argtypes = [C.c_int, C.c_int32, C.c_int64, vp, vp, vp]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc: int):
+    if rc != MCRT_OK:
+        raise McrtError(rc, lib().mcrt_last_error().decode("utf-8", "replace"))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    _check(lib().mcrt_default_params(C.byref(p)))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def make_poses(poses) -> np.ndarray:
+    """float32 [n, 6] = (pos xyz, angles xyz deg): the memory layout of mcrt_pose[n]."""
+    a = np.ascontiguousarray(np.asarray(poses, dtype=np.float32).reshape(-1, 6))
+    return a
+
+
+class Simulator:
+    """One scene + acquisition geometry on one GPU: the objects main.cpp:52-81 builds
+    (volume, psf, rf_image, transducer, scene) behind one handle."""
+
+    def __init__(self, scene, params: Params | None = None, device: int = 0):
+        L = lib()
+        self.params = params if params is not None else default_params()
+        h = C.c_void_p()
+        if isinstance(scene, (str, os.PathLike)):
+            rc = L.mcrt_create(str(scene).encode(), C.byref(self.params), int(device), C.byref(h))
+        else:
+            self._keep = {k: np.ascontiguousarray(scene[k]) for k in ("materials", "mesh_material_inside", "mesh_material_outside",
+                                                                        "mesh_vascular", "mesh_deltas", "tri_offsets", "tri_vertices")}
+            k = self._keep
+            sa = SceneArrays()
+            sa.n_materials = len(k["materials"]); sa.materials8 = _p(k["materials"].astype(np.float32, copy=False))
+            sa.starting_material = int(scene["starting_material"]); sa.n_meshes = len(k["mesh_material_inside"])
+            sa.mesh_material_inside = _p(k["mesh_material_inside"]); sa.mesh_material_outside = _p(k["mesh_material_outside"])
+            sa.mesh_vascular = _p(k["mesh_vascular"]); sa.mesh_deltas = _p(k["mesh_deltas"]); sa.tri_offsets = _p(k["tri_offsets"])
+            sa.tri_vertices = _p(k["tri_vertices"]); sa.scaling = float(scene["scaling"])
+            for i in range(3):
+                sa.origin[i] = float(scene["origin"][i]); sa.spacing[i] = float(scene["spacing"][i])
+            rc = L.mcrt_create_from_arrays(C.byref(sa), C.byref(self.params), int(device), C.byref(h))
+        _check(rc)
+        self.h = h
+        self.info = Info()
+        _check(L.mcrt_get_info(self.h, C.byref(self.info)))
+        self.rows, self.cols = self.info.rows, self.info.cols
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mcrt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def start_pose(self) -> np.ndarray:
+        return np.array(list(self.info.start_pose), dtype=np.float32)
+
+    def set_option(self, name: str, value: int):
+        _check(lib().mcrt_set_option(self.h, name.encode(), int(value)))
+
+    def stats(self) -> Stats:
+        s = Stats()
+        _check(lib().mcrt_get_stats(self.h, C.byref(s)))
+        return s
+
+    # -- the frame loop body (main.cpp:102-148) --------------------------------------------------
+    def rf_shape(self, n_poses: int):
+        return (n_poses, self.rows, self.cols) if self.params.rf_layout == 1 else (n_poses, self.cols, self.rows)
+
+    def simulate(self, poses, seed: int = 0, first_frame: int = 0, scan: bool = False, rf_out: np.ndarray | None = None,
+                 scan_out: np.ndarray | None = None):
+        """Host-buffer call: poses -> RF (+ scan-converted image).  Copies are inside the call."""
+        P = make_poses(poses)
+        n = len(P)
+        rf = rf_out if rf_out is not None else np.empty(self.rf_shape(n), np.float32)
+        sc = scan_out if scan_out is not None else (np.empty((n, self.info.scan_rows, self.info.scan_cols), np.float32) if scan else None)
+        _check(lib().mcrt_simulate(self.h, _p(P), n, int(seed), int(first_frame), _p(rf), _p(sc)))
+        return (rf, sc) if (scan or scan_out is not None) else rf
+
+    def simulate_device(self, poses, rf_ptr: int, seed: int = 0, first_frame: int = 0, scan_ptr: int | None = None,
+                        stream: int | None = None, sync: bool = True):
+        """Device-buffer call: rf_ptr / scan_ptr are raw device addresses (e.g. torch.Tensor.data_ptr())."""
+        P = make_poses(poses)
+        n = len(P)
+        if sync and stream is None:
+            _check(lib().mcrt_simulate(self.h, _p(P), n, int(seed), int(first_frame), C.c_void_p(rf_ptr),
+                                       C.c_void_p(scan_ptr) if scan_ptr else None))
+        else:
+            _check(lib().mcrt_simulate_async(self.h, _p(P), n, int(seed), int(first_frame), C.c_void_p(rf_ptr),
+                                             C.c_void_p(scan_ptr) if scan_ptr else None, C.c_void_p(stream) if stream else None))
+
+    # -- parity hooks ----------------------------------------------------------------------------
+    def cast_rays(self, pose, seed: int = 0, frame: int = 0):
+        """scene::cast_rays (scene.cpp:50-183): segments[E][S][D], n_segments[E][S]."""
+        P = make_poses(pose)
+        E, S, D = self.params.elements, self.params.samples, self.params.max_depth
+        segs = np.zeros((E, S, D), dtype=SEGMENT_DTYPE)
+        nseg = np.zeros((E, S), dtype=np.int32)
+        _check(lib().mcrt_trace_debug(self.h, _p(P), int(seed), int(frame), _p(segs), _p(nseg)))
+        return segs, nseg
+
+    def closest_hit(self, frm, to):
+        f = np.ascontiguousarray(np.asarray(frm, np.float32).reshape(-1, 3))
+        t = np.ascontiguousarray(np.asarray(to, np.float32).reshape(-1, 3))
+        n = len(f)
+        tri = np.empty(n, np.int32); mesh = np.empty(n, np.int32); frac = np.empty(n, np.float32)
+        pt = np.empty((n, 3), np.float32); nr = np.empty((n, 3), np.float32)
+        _check(lib().mcrt_closest_hit(self.h, n, _p(f), _p(t), _p(tri), _p(mesh), _p(frac), _p(pt), _p(nr)))
+        return tri, mesh, frac, pt, nr
+
+    def transducer_elements(self, pose):
+        P = make_poses(pose)
+        pos = np.empty((self.params.elements, 3), np.float32); d = np.empty((self.params.elements, 3), np.float32)
+        _check(lib().mcrt_transducer_elements(self.h, _p(P), _p(pos), _p(d)))
+        return pos, d
+
+    def accumulate(self, segs, nseg):
+        """main.cpp:106-144 -> raw RF, scanline-major [cols][rows]."""
+        segs = np.ascontiguousarray(segs); nseg = np.ascontiguousarray(nseg, np.int32)
+        rf = np.empty((self.cols, self.rows), np.float32)
+        _check(lib().mcrt_accumulate(self.h, _p(segs), _p(nseg), _p(rf)))
+        return rf
+
+    def postprocess(self, rf_cols_rows, axial=None, lateral=None, convolve=True, envelope=True):
+        rf = np.ascontiguousarray(rf_cols_rows, np.float32)
+        cols, rows = rf.shape
+        if axial is None or lateral is None:
+            axial, lateral = self.psf_taps()
+        ax = np.ascontiguousarray(axial, np.float32); lat = np.ascontiguousarray(lateral, np.float32)
+        out = np.empty_like(rf)
+        _check(lib().mcrt_postprocess(self.h, _p(rf), cols, rows, _p(ax), len(ax), _p(lat), len(lat), (1 if convolve else 0) | (2 if envelope else 0), _p(out)))
+        return out
+
+    def scan_convert(self, rf_cols_rows):
+        rf = np.ascontiguousarray(rf_cols_rows, np.float32)
+        out = np.empty((self.info.scan_rows, self.info.scan_cols), np.float32)
+        _check(lib().mcrt_scan_convert(self.h, _p(rf), _p(out)))
+        return out
+
+    def psf_taps(self):
+        ax = np.empty(self.params.psf_axial, np.float32); lat = np.empty(self.params.psf_lateral, np.float32)
+        _check(lib().mcrt_get_psf_taps(self.h, _p(ax), _p(lat)))
+        return ax, lat
+
+    def scene_arrays(self):
+        n = int(self.info.n_triangles)
+        tri = np.empty((n, 9), np.float32); tm = np.empty(n, np.int32)
+        org = np.empty((self.info.n_meshes, 3), np.float32); mats = np.empty((self.info.n_materials, 8), np.float32)
+        _check(lib().mcrt_get_scene(self.h, _p(tri), _p(tm), _p(org), _p(mats)))
+        return tri, tm, org, mats
+
+    def volume(self):
+        v = np.empty((256, 256, 256, 2), np.float32)
+        _check(lib().mcrt_get_volume(self.h, _p(v)))
+        return v
+
+
+def numerics_probe(op: int, a, b=None, device: int = 0) -> np.ndarray:
+    a = np.ascontiguousarray(a, np.float64)
+    b = np.ascontiguousarray(b if b is not None else np.zeros_like(a), np.float64)
+    out = np.empty_like(a)
+    _check(lib().mcrt_numerics_probe(int(device), int(op), a.size, _p(a), _p(b), _p(out)))
+    return out

@@ -1,0 +1,781 @@
+// mcrt_abi.cu -- the C ABI of include/mcrt.h: context ownership, per-frame pipeline orchestration
+// (upload poses -> wavefront trace -> accumulate -> PSF -> envelope -> scan conversion), CUDA-graph
+// capture of that pipeline, and the stage-level entry points the parity tests call.
+// No CPU fallback anywhere: every compute entry point launches the kernels of csrc/kernels/.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/mcrt.h"
+#include "../host/mcrt_host.h"
+#include "../kernels/mcrt_launch.h"
+
+using namespace mcrt;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+struct CudaError : std::runtime_error {
+    explicit CudaError(const std::string& m) : std::runtime_error(m) {}
+};
+
+#define CUDA_TRY(expr)                                                                                            \
+    do {                                                                                                          \
+        cudaError_t e__ = (expr);                                                                                 \
+        if (e__ != cudaSuccess) {                                                                                 \
+            (void)cudaGetLastError();                                                                             \
+            throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(e__));                                 \
+        }                                                                                                         \
+    } while (0)
+
+// process-wide, per-device copy of the 128 MiB scatterer volume (volume.h: `static const volume_`)
+std::mutex g_volume_mutex;
+std::map<int, float2*> g_volume_dev;
+
+float2* device_volume(int device, cudaStream_t stream)
+{
+    std::lock_guard<std::mutex> lock(g_volume_mutex);
+    auto it = g_volume_dev.find(device);
+    if (it != g_volume_dev.end()) return it->second;
+    const std::vector<float>& h = scatterer_volume();
+    float2* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, h.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    g_volume_dev[device] = d;
+    return d;
+}
+
+template <typename T>
+void dev_alloc(T*& p, size_t n)
+{
+    p = nullptr;
+    if (n == 0) return;
+    CUDA_TRY(cudaMalloc(&p, n * sizeof(T)));
+}
+
+template <typename T>
+void dev_free(T*& p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+bool is_device_pointer(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+struct mcrt_ctx {
+    int device = 0;
+    int sm_count = 148;
+    mcrt_params params;
+    Derived dv;
+    HostScene scene;
+    AcqDev aq;
+    SceneDev sc;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+
+    DevMesh* d_meshes = nullptr;
+    DevMaterial* d_materials = nullptr;
+    LbvhResult bvh{};
+    float2* d_volume = nullptr;        // owned by the process-wide cache
+    float2* d_elem_sincos = nullptr;
+    float* d_axial = nullptr;
+    float* d_lateral = nullptr;
+    float* d_map_x = nullptr;
+    float* d_map_y = nullptr;
+    std::vector<float> h_axial, h_lateral;
+
+    // per-batch workspace
+    int cap_poses = 0;
+    TraceBuffers tb{};
+    PoseTrigDev* d_poses = nullptr;
+    unsigned long long* d_seed_frame = nullptr;
+    unsigned long long* d_steps = nullptr;
+    float* d_rf_acc = nullptr;
+    float* d_rf_tmp0 = nullptr;
+    float* d_rf_tmp1 = nullptr;
+    float* d_rf_final = nullptr;
+    float* d_rf_t = nullptr;           // transposed copy when rf_layout == 1
+    float* d_scan = nullptr;
+    float* d_columns = nullptr;        // HBM accumulate columns (long scanlines only)
+    size_t columns_bytes = 0;
+    PoseTrig* h_poses = nullptr;       // pinned staging
+    unsigned long long* h_seed_frame = nullptr;
+    int* h_counters = nullptr;         // pinned, [MAX_BATCHES][32]
+    unsigned long long* h_steps = nullptr;
+
+    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;   // (n_poses in batch, want_scan) -> exec
+    bool use_graph = true;
+    bool profile_stages = false;
+    int max_batch_poses = 256;
+    mcrt_stats stats{};
+    bool stats_pending = false;
+    int pending_batches = 0;
+    int pending_launches = 0;
+};
+
+namespace {
+
+const int kMaxBatchesPerCall = 4096;
+
+void free_workspace(mcrt_ctx* c)
+{
+    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    c->graphs.clear();
+    dev_free(c->tb.paths.origin_intensity); dev_free(c->tb.paths.dir_state); dev_free(c->tb.paths.distance);
+    dev_free(c->tb.segments); dev_free(c->tb.n_segments); dev_free(c->tb.hit_fraction); dev_free(c->tb.hit_mesh);
+    dev_free(c->tb.queue_a); dev_free(c->tb.queue_b); dev_free(c->tb.counters);
+    dev_free(c->d_poses); dev_free(c->d_rf_acc); dev_free(c->d_rf_tmp0); dev_free(c->d_rf_tmp1); dev_free(c->d_rf_final);
+    dev_free(c->d_rf_t); dev_free(c->d_scan); dev_free(c->d_columns);
+    if (c->h_poses) cudaFreeHost(c->h_poses);
+    c->h_poses = nullptr;
+    c->cap_poses = 0;
+}
+
+void ensure_workspace(mcrt_ctx* c, int n_poses)
+{
+    if (n_poses <= c->cap_poses) return;
+    free_workspace(c);
+    const size_t n_paths = (size_t)n_poses * c->aq.elements * c->aq.samples;
+    const size_t n_px = (size_t)n_poses * c->aq.elements * c->aq.rows;
+    if (n_paths * c->aq.max_depth > 0x7fffffffULL) throw std::invalid_argument("batch too large: reduce max_batch_poses");
+    dev_alloc(c->tb.paths.origin_intensity, n_paths);
+    dev_alloc(c->tb.paths.dir_state, n_paths);
+    dev_alloc(c->tb.paths.distance, n_paths);
+    dev_alloc(c->tb.segments, n_paths * c->aq.max_depth);
+    dev_alloc(c->tb.n_segments, n_paths);
+    dev_alloc(c->tb.queue_a, n_paths);
+    dev_alloc(c->tb.queue_b, n_paths);
+    dev_alloc(c->tb.counters, (size_t)c->aq.max_depth + 1);
+    dev_alloc(c->d_poses, (size_t)n_poses);
+    dev_alloc(c->d_rf_acc, n_px);
+    dev_alloc(c->d_rf_tmp0, n_px);
+    dev_alloc(c->d_rf_tmp1, n_px);
+    dev_alloc(c->d_rf_final, n_px);
+    if (c->params.rf_layout == 1) dev_alloc(c->d_rf_t, n_px);
+    dev_alloc(c->d_scan, (size_t)n_poses * c->params.scan_rows * c->params.scan_cols);
+    c->columns_bytes = accumulate_columns_bytes(c->aq, n_poses);
+    if (c->columns_bytes) dev_alloc(c->d_columns, c->columns_bytes / sizeof(float));
+    CUDA_TRY(cudaMallocHost(&c->h_poses, sizeof(PoseTrig) * (size_t)n_poses));
+    c->cap_poses = n_poses;
+}
+
+// enqueue the whole per-frame chain for `n` poses already uploaded to d_poses / d_seed_frame
+void enqueue_pipeline(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches, bool stage_events)
+{
+    FrameDev fr;
+    fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = n; fr.pad = 0;
+    if (stage_events) CUDA_TRY(cudaEventRecord(c->ev_a, s));
+    launch_trace(c->sc, c->aq, fr, c->tb, c->sm_count, s, launches);
+    if (stage_events) CUDA_TRY(cudaEventRecord(c->ev_b, s));
+    CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, sizeof(unsigned long long), s));
+    CUDA_TRY(launch_accumulate(c->sc, c->aq, c->d_volume, c->tb.segments, c->tb.n_segments, n, c->d_rf_acc, c->d_steps, c->d_columns, s,
+                               launches));
+    if (stage_events) CUDA_TRY(cudaEventRecord(c->ev_c, s));
+    launch_post(c->d_rf_acc, n, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
+                c->d_rf_tmp0, c->d_rf_tmp1, c->d_rf_final, s, launches);
+    if (c->params.rf_layout == 1) launch_transpose(c->d_rf_final, n, c->aq.elements, c->aq.rows, c->d_rf_t, s, launches);
+    if (want_scan)
+        launch_scan_convert(c->d_rf_final, n, c->aq.elements, c->aq.rows, c->d_map_x, c->d_map_y, c->params.scan_rows, c->params.scan_cols,
+                            c->d_scan, s, launches);
+    CUDA_TRY(cudaGetLastError());
+}
+
+int count_pipeline_launches(const mcrt_ctx* c, bool want_scan)
+{
+    return c->aq.max_depth + 1 + 3 + (c->params.rf_layout == 1 ? 1 : 0) + (want_scan ? 1 : 0);
+}
+
+void run_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches)
+{
+    const bool graph_ok = c->use_graph && !c->profile_stages;
+    if (!graph_ok) {
+        enqueue_pipeline(c, n, want_scan, s, launches, c->profile_stages);
+        return;
+    }
+    const auto key = std::make_pair(n, want_scan ? 1 : 0);
+    auto it = c->graphs.find(key);
+    if (it == c->graphs.end()) {
+        // capture on the library's own stream (the caller's stream may be the legacy default stream)
+        cudaGraph_t graph = nullptr;
+        int dummy = 0;
+        CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        try {
+            enqueue_pipeline(c, n, want_scan, c->stream, &dummy, false);
+        } catch (...) {
+            cudaStreamEndCapture(c->stream, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+        }
+        CUDA_TRY(cudaStreamEndCapture(c->stream, &graph));
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) throw CudaError(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        it = c->graphs.emplace(key, exec).first;
+    }
+    CUDA_TRY(cudaGraphLaunch(it->second, s));
+    if (launches) *launches += count_pipeline_launches(c, want_scan);
+}
+
+int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t seed, uint64_t first_frame, float* rf_out,
+                  float* scan_out, cudaStream_t user_stream, bool async)
+{
+    if (!c || !poses || n_poses < 0 || !rf_out) return fail(MCRT_ERR_INVALID, "mcrt_simulate: null argument");
+    if (n_poses == 0) return MCRT_OK;
+    try {
+        CUDA_TRY(cudaSetDevice(c->device));
+        const bool rf_dev = async ? true : is_device_pointer(rf_out);
+        const bool scan_dev = scan_out ? (async ? true : is_device_pointer(scan_out)) : true;
+        cudaStream_t s = (async && user_stream) ? user_stream : c->stream;
+        const int batch_cap = c->max_batch_poses < 1 ? 1 : c->max_batch_poses;
+        const int n_batches = (n_poses + batch_cap - 1) / batch_cap;
+        if (n_batches > kMaxBatchesPerCall) return fail(MCRT_ERR_INVALID, "mcrt_simulate: too many batches; raise max_batch_poses");
+        ensure_workspace(c, n_poses < batch_cap ? n_poses : batch_cap);
+        const size_t px_per_pose = (size_t)c->aq.elements * c->aq.rows;
+        const size_t scan_per_pose = (size_t)c->params.scan_rows * c->params.scan_cols;
+        int launches = 0;
+        CUDA_TRY(cudaEventRecord(c->ev0, s));
+        for (int b = 0; b < n_batches; b++) {
+            const int p0 = b * batch_cap;
+            const int n = (n_poses - p0) < batch_cap ? (n_poses - p0) : batch_cap;
+            if (b > 0) CUDA_TRY(cudaStreamSynchronize(s));      // pinned staging is reused
+            for (int i = 0; i < n; i++) c->h_poses[i] = pose_trig(poses[p0 + i]);
+            c->h_seed_frame[0] = seed;
+            c->h_seed_frame[1] = first_frame + (uint64_t)p0;
+            CUDA_TRY(cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig) * (size_t)n, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(c->d_seed_frame, c->h_seed_frame, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+            run_batch(c, n, scan_out != nullptr, s, &launches);
+            const float* rf_src = c->params.rf_layout == 1 ? c->d_rf_t : c->d_rf_final;
+            CUDA_TRY(cudaMemcpyAsync(rf_out + (size_t)p0 * px_per_pose, rf_src, sizeof(float) * px_per_pose * n,
+                                     rf_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+            if (scan_out)
+                CUDA_TRY(cudaMemcpyAsync(scan_out + (size_t)p0 * scan_per_pose, c->d_scan, sizeof(float) * scan_per_pose * n,
+                                         scan_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(c->h_counters + 32 * b, c->tb.counters, sizeof(int) * (size_t)(c->aq.max_depth + 1),
+                                     cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(c->h_steps + b, c->d_steps, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        }
+        CUDA_TRY(cudaEventRecord(c->ev1, s));
+        c->stats_pending = true;
+        c->pending_batches = n_batches;
+        c->pending_launches = launches;
+        c->stats = mcrt_stats{};
+        c->stats.poses = n_poses;
+        if (!async) CUDA_TRY(cudaStreamSynchronize(s));
+    } catch (const CudaError& e) {
+        return fail(MCRT_ERR_CUDA, e.what());
+    } catch (const std::exception& e) {
+        return fail(MCRT_ERR_INVALID, e.what());
+    }
+    return MCRT_OK;
+}
+
+void finalize_stats(mcrt_ctx* c)
+{
+    if (!c->stats_pending) return;
+    if (cudaEventSynchronize(c->ev1) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->stats.ms_total = ms;
+    const int64_t paths_per_pose = (int64_t)c->aq.elements * c->aq.samples;
+    int64_t segs = c->stats.poses * paths_per_pose;      // bounce 0 traces every path
+    int64_t steps = 0;
+    for (int b = 0; b < c->pending_batches; b++) {
+        for (int d = 1; d < c->aq.max_depth; d++) segs += c->h_counters[32 * b + d];
+        steps += (int64_t)c->h_steps[b];
+    }
+    c->stats.segments = segs;
+    c->stats.march_steps = steps;
+    c->stats.kernel_launches = c->pending_launches;
+    if (c->profile_stages && c->pending_batches == 1) {
+        cudaEventElapsedTime(&c->stats.ms_trace, c->ev_a, c->ev_b);
+        cudaEventElapsedTime(&c->stats.ms_accumulate, c->ev_b, c->ev_c);
+        cudaEventElapsedTime(&c->stats.ms_post, c->ev_c, c->ev1);
+    }
+    c->stats_pending = false;
+}
+
+int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_ctx** out)
+{
+    std::unique_ptr<mcrt_ctx> c(new mcrt_ctx());
+    c->params = *params;
+    validate_params(c->params);
+    c->dv = derive(c->params);
+    c->scene = std::move(scene);
+    if ((int)c->scene.meshes.size() > MCRT_MAX_SMEM_MESHES) throw std::invalid_argument("more than 64 meshes are not supported");
+    if ((int)c->scene.materials.size() > MCRT_MAX_SMEM_MATERIALS) throw std::invalid_argument("more than 64 materials are not supported");
+    c->device = device;
+    int n_dev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) throw CudaError("no CUDA device " + std::to_string(device) + " (libmcrt has no CPU fallback)");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) throw CudaError(std::string("device '") + prop.name + "' is not sm_100 (B200); libmcrt only carries sm_100a code");
+    c->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&c->ev0)); CUDA_TRY(cudaEventCreate(&c->ev1));
+    CUDA_TRY(cudaEventCreate(&c->ev_a)); CUDA_TRY(cudaEventCreate(&c->ev_b)); CUDA_TRY(cudaEventCreate(&c->ev_c));
+
+    // acquisition constants
+    AcqDev& aq = c->aq;
+    memset(&aq, 0, sizeof(aq));
+    aq.elements = c->params.elements; aq.samples = c->params.samples; aq.max_depth = c->params.max_depth; aq.rows = c->dv.rows;
+    aq.frequency = c->params.frequency_mhz; aq.axres_f = c->dv.axial_resolution_f;
+    aq.radius_f = (float)c->params.radius_cm;                         // radius.to<float>(), transducer.h:51
+    aq.vol_resolution = c->params.resolution_um / 1000.0f;            // volume.h:49
+    aq.axres_mm = c->dv.axial_resolution_mm; aq.time_step_us = c->dv.time_step_us; aq.row_period_us = c->dv.row_period_us;
+    aq.inv_row_period = 1.0 / c->dv.row_period_us; aq.max_travel_time_us = c->dv.max_travel_time_us;
+    aq.speed = (double)c->params.speed_of_sound; aq.deterministic = c->params.deterministic;
+
+    // scene tables
+    const HostScene& hs = c->scene;
+    std::vector<DevMesh> meshes(hs.meshes.size());
+    for (size_t m = 0; m < hs.meshes.size(); m++) {
+        DevMesh& d = meshes[m];
+        d.ox = hs.meshes[m].origin[0]; d.oy = hs.meshes[m].origin[1]; d.oz = hs.meshes[m].origin[2];
+        d.mat_in = hs.meshes[m].material_inside; d.mat_out = hs.meshes[m].material_outside; d.vascular = hs.meshes[m].is_vascular ? 1 : 0;
+        d.pad0 = d.pad1 = 0;
+    }
+    dev_alloc(c->d_meshes, meshes.size() ? meshes.size() : 1);
+    if (!meshes.empty()) CUDA_TRY(cudaMemcpy(c->d_meshes, meshes.data(), sizeof(DevMesh) * meshes.size(), cudaMemcpyHostToDevice));
+    dev_alloc(c->d_materials, hs.materials.size());
+    CUDA_TRY(cudaMemcpy(c->d_materials, hs.materials.data(), sizeof(DevMaterial) * hs.materials.size(), cudaMemcpyHostToDevice));
+    const cudaError_t be = build_lbvh(hs.tri_local.data(), hs.tri_mesh.data(), (int)hs.tri_mesh.size(), c->d_meshes, c->stream, &c->bvh);
+    if (be != cudaSuccess) throw CudaError(std::string("build_lbvh: ") + cudaGetErrorString(be));
+    if (c->bvh.max_depth > MCRT_TRAVERSAL_STACK) throw std::invalid_argument("BVH deeper than the traversal stack (degenerate mesh?)");
+    SceneDev& sc = c->sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.nodes = c->bvh.nodes; sc.tris = c->bvh.tris; sc.meshes = c->d_meshes; sc.materials = c->d_materials;
+    sc.n_tri = c->bvh.n_tri; sc.n_mesh = (int)hs.meshes.size(); sc.n_mat = (int)hs.materials.size();
+    sc.starting_material = hs.starting_material;
+    for (int a = 0; a < 3; a++) sc.spacing[a] = hs.spacing[a];
+    sc.max_abs = c->bvh.max_abs;
+
+    // transducer table, psf taps, scan maps, scatterer volume
+    std::vector<float> sincos;
+    element_angle_table(c->params, c->dv, sincos);
+    dev_alloc(c->d_elem_sincos, (size_t)c->params.elements);
+    CUDA_TRY(cudaMemcpy(c->d_elem_sincos, sincos.data(), sizeof(float) * sincos.size(), cudaMemcpyHostToDevice));
+    psf_taps(c->params, c->h_axial, c->h_lateral);
+    dev_alloc(c->d_axial, c->h_axial.size());
+    dev_alloc(c->d_lateral, c->h_lateral.size());
+    CUDA_TRY(cudaMemcpy(c->d_axial, c->h_axial.data(), sizeof(float) * c->h_axial.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->d_lateral, c->h_lateral.data(), sizeof(float) * c->h_lateral.size(), cudaMemcpyHostToDevice));
+    std::vector<float> mx, my;
+    scan_mapping(c->params, c->dv, mx, my);
+    dev_alloc(c->d_map_x, mx.size());
+    dev_alloc(c->d_map_y, my.size());
+    CUDA_TRY(cudaMemcpy(c->d_map_x, mx.data(), sizeof(float) * mx.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->d_map_y, my.data(), sizeof(float) * my.size(), cudaMemcpyHostToDevice));
+    c->d_volume = device_volume(device, c->stream);
+    CUDA_TRY(init_image_kernels());
+
+    dev_alloc(c->d_seed_frame, 2);
+    dev_alloc(c->d_steps, 1);
+    CUDA_TRY(cudaMallocHost(&c->h_seed_frame, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMallocHost(&c->h_counters, sizeof(int) * 32 * kMaxBatchesPerCall));
+    CUDA_TRY(cudaMallocHost(&c->h_steps, sizeof(unsigned long long) * kMaxBatchesPerCall));
+    memset(c->h_counters, 0, sizeof(int) * 32 * kMaxBatchesPerCall);
+    memset(c->h_steps, 0, sizeof(unsigned long long) * kMaxBatchesPerCall);
+    *out = c.release();
+    return MCRT_OK;
+}
+
+void destroy_impl(mcrt_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_workspace(c);
+    dev_free(c->d_meshes); dev_free(c->d_materials); dev_free(c->bvh.nodes); dev_free(c->bvh.tris);
+    dev_free(c->d_elem_sincos); dev_free(c->d_axial); dev_free(c->d_lateral); dev_free(c->d_map_x); dev_free(c->d_map_y);
+    dev_free(c->d_seed_frame); dev_free(c->d_steps);
+    if (c->h_seed_frame) cudaFreeHost(c->h_seed_frame);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->h_steps) cudaFreeHost(c->h_steps);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_b) cudaEventDestroy(c->ev_b);
+    if (c->ev_c) cudaEventDestroy(c->ev_c);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    (void)cudaGetLastError();
+    delete c;
+}
+
+template <typename F>
+int guarded(const char* what, F&& f)
+{
+    try {
+        return f();
+    } catch (const CudaError& e) {
+        return fail(MCRT_ERR_CUDA, std::string(what) + ": " + e.what());
+    } catch (const std::bad_alloc&) {
+        return fail(MCRT_ERR_NOMEM, std::string(what) + ": out of host memory");
+    } catch (const std::invalid_argument& e) {
+        return fail(MCRT_ERR_INVALID, std::string(what) + ": " + e.what());
+    } catch (const std::exception& e) {
+        return fail(MCRT_ERR_SCENE, e.what());
+    }
+}
+
+DevSegment to_dev_segment(const mcrt_segment& s)
+{
+    DevSegment d;
+    d.s0 = make_float4(s.from[0], s.from[1], s.from[2], s.reflected_intensity);
+    d.s1 = make_float4(s.dir[0], s.dir[1], s.dir[2], s.initial_intensity);
+    d.s2 = make_float4(s.to[0], s.to[1], s.to[2], s.attenuation);
+    unsigned long long bits;
+    memcpy(&bits, &s.distance_traveled, 8);
+    d.s3 = make_int4((int)(bits & 0xffffffffu), (int)(bits >> 32), s.media_id, s.tri_id);
+    return d;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* mcrt_last_error(void) { return g_last_error.c_str(); }
+
+int mcrt_default_params(mcrt_params* p)
+{
+    if (!p) return fail(MCRT_ERR_INVALID, "mcrt_default_params: null");
+    memset(p, 0, sizeof(*p));
+    p->elements = 512; p->samples = 5; p->max_depth = 10; p->frequency_mhz = 4.5f; p->radius_cm = 3; p->fov_deg = 60; p->depth_cm = 15;
+    p->speed_of_sound = 1500; p->resolution_um = 145; p->psf_axial = 7; p->psf_lateral = 13; p->psf_var_x = 0.05f; p->psf_var_y = 0.2f;
+    p->deterministic = 0; p->scan_rows = 400; p->scan_cols = 500; p->axial_scale = 1.0f; p->rf_layout = 0;
+    return MCRT_OK;
+}
+
+int mcrt_create(const char* scene_json_path, const mcrt_params* params, int device, mcrt_ctx** out)
+{
+    if (!scene_json_path || !out) return fail(MCRT_ERR_INVALID, "mcrt_create: null argument");
+    *out = nullptr;
+    mcrt_params defaults;
+    mcrt_default_params(&defaults);
+    const mcrt_params* p = params ? params : &defaults;
+    return guarded("mcrt_create", [&]() { return create_impl(load_scene_file(scene_json_path), p, device, out); });
+}
+
+int mcrt_create_from_arrays(const mcrt_scene_arrays* scene, const mcrt_params* params, int device, mcrt_ctx** out)
+{
+    if (!scene || !out) return fail(MCRT_ERR_INVALID, "mcrt_create_from_arrays: null argument");
+    *out = nullptr;
+    mcrt_params defaults;
+    mcrt_default_params(&defaults);
+    const mcrt_params* p = params ? params : &defaults;
+    return guarded("mcrt_create_from_arrays", [&]() { return create_impl(scene_from_arrays(*scene), p, device, out); });
+}
+
+void mcrt_destroy(mcrt_ctx* ctx) { destroy_impl(ctx); }
+
+int mcrt_get_info(const mcrt_ctx* c, mcrt_info* info)
+{
+    if (!c || !info) return fail(MCRT_ERR_INVALID, "mcrt_get_info: null argument");
+    memset(info, 0, sizeof(*info));
+    info->rows = c->dv.rows; info->cols = c->dv.cols; info->scan_rows = c->params.scan_rows; info->scan_cols = c->params.scan_cols;
+    info->n_materials = (int)c->scene.materials.size(); info->n_meshes = (int)c->scene.meshes.size();
+    info->n_triangles = (int64_t)c->scene.tri_mesh.size(); info->n_bvh_nodes = c->bvh.n_nodes; info->device = c->device;
+    info->sm_count = c->sm_count;
+    for (int i = 0; i < 6; i++) info->start_pose[i] = c->scene.start_pose[i];
+    info->axial_resolution_mm = c->dv.axial_resolution_mm; info->time_step_us = c->dv.time_step_us;
+    info->row_period_us = c->dv.row_period_us; info->max_travel_time_us = c->dv.max_travel_time_us;
+    return MCRT_OK;
+}
+
+int mcrt_get_stats(const mcrt_ctx* c, mcrt_stats* stats)
+{
+    if (!c || !stats) return fail(MCRT_ERR_INVALID, "mcrt_get_stats: null argument");
+    finalize_stats(const_cast<mcrt_ctx*>(c));
+    *stats = c->stats;
+    return MCRT_OK;
+}
+
+int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
+{
+    if (!c || !name) return fail(MCRT_ERR_INVALID, "mcrt_set_option: null argument");
+    const std::string n(name);
+    if (n == "profile_stages") c->profile_stages = value != 0;
+    else if (n == "use_graph") c->use_graph = value != 0;
+    else if (n == "max_batch_poses") { if (value < 1) return fail(MCRT_ERR_INVALID, "max_batch_poses must be >= 1"); c->max_batch_poses = (int)value; }
+    else return fail(MCRT_ERR_INVALID, "unknown option '" + n + "'");
+    return MCRT_OK;
+}
+
+int mcrt_simulate(mcrt_ctx* ctx, const mcrt_pose* poses, int32_t n_poses, uint64_t seed, uint64_t first_frame, float* rf_out,
+                  float* scan_out)
+{
+    return simulate_impl(ctx, poses, n_poses, seed, first_frame, rf_out, scan_out, nullptr, false);
+}
+
+int mcrt_simulate_async(mcrt_ctx* ctx, const mcrt_pose* poses, int32_t n_poses, uint64_t seed, uint64_t first_frame, float* rf_out_dev,
+                        float* scan_out_dev, void* cuda_stream)
+{
+    return simulate_impl(ctx, poses, n_poses, seed, first_frame, rf_out_dev, scan_out_dev, (cudaStream_t)cuda_stream, true);
+}
+
+int mcrt_trace_debug(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, uint64_t frame, mcrt_segment* segments, int32_t* n_segments)
+{
+    if (!c || !pose || !segments || !n_segments) return fail(MCRT_ERR_INVALID, "mcrt_trace_debug: null argument");
+    return guarded("mcrt_trace_debug", [&]() {
+        CUDA_TRY(cudaSetDevice(c->device));
+        ensure_workspace(c, 1);
+        const size_t n_paths = (size_t)c->aq.elements * c->aq.samples;
+        const size_t n_seg = n_paths * c->aq.max_depth;
+        if (!c->tb.hit_fraction) { dev_alloc(c->tb.hit_fraction, (size_t)c->cap_poses * n_seg); dev_alloc(c->tb.hit_mesh, (size_t)c->cap_poses * n_seg); }
+        c->h_poses[0] = pose_trig(*pose);
+        c->h_seed_frame[0] = seed; c->h_seed_frame[1] = frame;
+        CUDA_TRY(cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->d_seed_frame, c->h_seed_frame, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+        FrameDev fr;
+        fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = 1; fr.pad = 0;
+        int launches = 0;
+        launch_trace(c->sc, c->aq, fr, c->tb, c->sm_count, c->stream, &launches);
+        CUDA_TRY(cudaGetLastError());
+        std::vector<DevSegment> hs(n_seg);
+        std::vector<float> hf(n_seg);
+        std::vector<int32_t> hm(n_seg);
+        CUDA_TRY(cudaMemcpyAsync(hs.data(), c->tb.segments, sizeof(DevSegment) * n_seg, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(hf.data(), c->tb.hit_fraction, sizeof(float) * n_seg, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(hm.data(), c->tb.hit_mesh, sizeof(int32_t) * n_seg, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(n_segments, c->tb.n_segments, sizeof(int32_t) * n_paths, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        // the debug arrays make later graph captures carry two extra stores per segment: drop them again
+        dev_free(c->tb.hit_fraction); dev_free(c->tb.hit_mesh);
+        memset(segments, 0, sizeof(mcrt_segment) * n_seg);
+        for (size_t p = 0; p < n_paths; p++)
+            for (int k = 0; k < n_segments[p]; k++) {
+                const size_t i = p * c->aq.max_depth + k;
+                const DevSegment& d = hs[i];
+                mcrt_segment& o = segments[i];
+                o.from[0] = d.s0.x; o.from[1] = d.s0.y; o.from[2] = d.s0.z; o.reflected_intensity = d.s0.w;
+                o.dir[0] = d.s1.x; o.dir[1] = d.s1.y; o.dir[2] = d.s1.z; o.initial_intensity = d.s1.w;
+                o.to[0] = d.s2.x; o.to[1] = d.s2.y; o.to[2] = d.s2.z; o.attenuation = d.s2.w;
+                const unsigned long long bits = (unsigned long long)(unsigned int)d.s3.x | ((unsigned long long)(unsigned int)d.s3.y << 32);
+                memcpy(&o.distance_traveled, &bits, 8);
+                o.media_id = d.s3.z; o.tri_id = d.s3.w; o.mesh_id = hm[i]; o.hit_fraction = hf[i];
+            }
+        return MCRT_OK;
+    });
+}
+
+int mcrt_closest_hit(mcrt_ctx* c, int64_t n, const float* from3, const float* to3, int32_t* tri_id, int32_t* mesh_id, float* fraction,
+                     float* point3, float* normal3)
+{
+    if (!c || n < 0 || !from3 || !to3 || !tri_id || !mesh_id || !fraction || !point3 || !normal3)
+        return fail(MCRT_ERR_INVALID, "mcrt_closest_hit: null argument");
+    if (n == 0) return MCRT_OK;
+    return guarded("mcrt_closest_hit", [&]() {
+        CUDA_TRY(cudaSetDevice(c->device));
+        float *d_from = nullptr, *d_to = nullptr, *d_frac = nullptr, *d_pt = nullptr, *d_nr = nullptr;
+        int32_t *d_tri = nullptr, *d_mesh = nullptr;
+        int rc = MCRT_OK;
+        try {
+            dev_alloc(d_from, (size_t)n * 3); dev_alloc(d_to, (size_t)n * 3); dev_alloc(d_frac, (size_t)n); dev_alloc(d_pt, (size_t)n * 3);
+            dev_alloc(d_nr, (size_t)n * 3); dev_alloc(d_tri, (size_t)n); dev_alloc(d_mesh, (size_t)n);
+            CUDA_TRY(cudaMemcpyAsync(d_from, from3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(d_to, to3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+            launch_closest_hit(c->sc, n, d_from, d_to, d_tri, d_mesh, d_frac, d_pt, d_nr, c->stream);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(tri_id, d_tri, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(mesh_id, d_mesh, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(fraction, d_frac, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(point3, d_pt, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(normal3, d_nr, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+        } catch (...) {
+            dev_free(d_from); dev_free(d_to); dev_free(d_frac); dev_free(d_pt); dev_free(d_nr); dev_free(d_tri); dev_free(d_mesh);
+            throw;
+        }
+        dev_free(d_from); dev_free(d_to); dev_free(d_frac); dev_free(d_pt); dev_free(d_nr); dev_free(d_tri); dev_free(d_mesh);
+        return rc;
+    });
+}
+
+int mcrt_transducer_elements(mcrt_ctx* c, const mcrt_pose* pose, float* pos3, float* dir3)
+{
+    if (!c || !pose || !pos3 || !dir3) return fail(MCRT_ERR_INVALID, "mcrt_transducer_elements: null argument");
+    return guarded("mcrt_transducer_elements", [&]() {
+        CUDA_TRY(cudaSetDevice(c->device));
+        ensure_workspace(c, 1);
+        float *d_pos = nullptr, *d_dir = nullptr;
+        const size_t n = (size_t)c->aq.elements * 3;
+        dev_alloc(d_pos, n); dev_alloc(d_dir, n);
+        c->h_poses[0] = pose_trig(*pose);
+        cudaError_t e = cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig), cudaMemcpyHostToDevice, c->stream);
+        FrameDev fr;
+        fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = 1; fr.pad = 0;
+        if (e == cudaSuccess) { launch_elements(c->aq, fr, d_pos, d_dir, c->stream); e = cudaGetLastError(); }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pos3, d_pos, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dir3, d_dir, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        dev_free(d_pos); dev_free(d_dir);
+        CUDA_TRY(e);
+        return MCRT_OK;
+    });
+}
+
+int mcrt_accumulate(mcrt_ctx* c, const mcrt_segment* segments, const int32_t* n_segments, float* rf_out)
+{
+    if (!c || !segments || !n_segments || !rf_out) return fail(MCRT_ERR_INVALID, "mcrt_accumulate: null argument");
+    return guarded("mcrt_accumulate", [&]() {
+        CUDA_TRY(cudaSetDevice(c->device));
+        ensure_workspace(c, 1);
+        const size_t n_paths = (size_t)c->aq.elements * c->aq.samples;
+        const size_t n_seg = n_paths * c->aq.max_depth;
+        for (size_t p = 0; p < n_paths; p++)
+            if (n_segments[p] < 0 || n_segments[p] > c->aq.max_depth) throw std::invalid_argument("n_segments out of range");
+        std::vector<DevSegment> hs(n_seg);
+        for (size_t i = 0; i < n_seg; i++) {
+            if (segments[i].media_id < 0 || segments[i].media_id >= c->sc.n_mat) {
+                if (n_segments[i / c->aq.max_depth] > (int)(i % c->aq.max_depth)) throw std::invalid_argument("segment media_id out of range");
+                hs[i] = DevSegment{};
+                continue;
+            }
+            hs[i] = to_dev_segment(segments[i]);
+        }
+        CUDA_TRY(cudaMemcpyAsync(c->tb.segments, hs.data(), sizeof(DevSegment) * n_seg, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->tb.n_segments, n_segments, sizeof(int32_t) * n_paths, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, sizeof(unsigned long long), c->stream));
+        int launches = 0;
+        CUDA_TRY(launch_accumulate(c->sc, c->aq, c->d_volume, c->tb.segments, c->tb.n_segments, 1, c->d_rf_acc, c->d_steps, c->d_columns,
+                                   c->stream, &launches));
+        CUDA_TRY(cudaMemcpyAsync(rf_out, c->d_rf_acc, sizeof(float) * (size_t)c->aq.elements * c->aq.rows, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->h_steps, c->d_steps, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->stats = mcrt_stats{};
+        c->stats.march_steps = (int64_t)c->h_steps[0];
+        c->stats.kernel_launches = launches;
+        c->stats_pending = false;
+        return MCRT_OK;
+    });
+}
+
+int mcrt_postprocess(mcrt_ctx* c, const float* rf_in, int32_t cols, int32_t rows, const float* axial, int32_t n_axial, const float* lateral,
+                     int32_t n_lateral, int32_t flags, float* rf_out)
+{
+    if (!c || !rf_in || !rf_out || cols < 1 || rows < 2) return fail(MCRT_ERR_INVALID, "mcrt_postprocess: bad argument");
+    if ((flags & 1) && (!axial || !lateral || n_axial < 1 || n_lateral < 1 || n_axial > 255 || n_lateral > 255))
+        return fail(MCRT_ERR_INVALID, "mcrt_postprocess: bad taps");
+    if (rows > 32768) return fail(MCRT_ERR_INVALID, "mcrt_postprocess: rows > 32768");
+    return guarded("mcrt_postprocess", [&]() {
+        CUDA_TRY(cudaSetDevice(c->device));
+        const size_t n = (size_t)cols * rows;
+        float *d_in = nullptr, *d_t0 = nullptr, *d_t1 = nullptr, *d_out = nullptr, *d_ax = nullptr, *d_lat = nullptr;
+        cudaError_t e = cudaSuccess;
+        try {
+            dev_alloc(d_in, n); dev_alloc(d_t0, n); dev_alloc(d_t1, n); dev_alloc(d_out, n);
+            dev_alloc(d_ax, (size_t)(n_axial > 0 ? n_axial : 1)); dev_alloc(d_lat, (size_t)(n_lateral > 0 ? n_lateral : 1));
+            CUDA_TRY(cudaMemcpyAsync(d_in, rf_in, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+            if (flags & 1) {
+                CUDA_TRY(cudaMemcpyAsync(d_ax, axial, sizeof(float) * n_axial, cudaMemcpyHostToDevice, c->stream));
+                CUDA_TRY(cudaMemcpyAsync(d_lat, lateral, sizeof(float) * n_lateral, cudaMemcpyHostToDevice, c->stream));
+            }
+            int launches = 0;
+            launch_post(d_in, 1, cols, rows, d_ax, n_axial, d_lat, n_lateral, flags, d_t0, d_t1, d_out, c->stream, &launches);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(rf_out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+        } catch (...) {
+            dev_free(d_in); dev_free(d_t0); dev_free(d_t1); dev_free(d_out); dev_free(d_ax); dev_free(d_lat);
+            throw;
+        }
+        dev_free(d_in); dev_free(d_t0); dev_free(d_t1); dev_free(d_out); dev_free(d_ax); dev_free(d_lat);
+        (void)e;
+        return MCRT_OK;
+    });
+}
+
+int mcrt_scan_convert(mcrt_ctx* c, const float* rf_in, float* scan_out)
+{
+    if (!c || !rf_in || !scan_out) return fail(MCRT_ERR_INVALID, "mcrt_scan_convert: null argument");
+    return guarded("mcrt_scan_convert", [&]() {
+        CUDA_TRY(cudaSetDevice(c->device));
+        ensure_workspace(c, 1);
+        const size_t n = (size_t)c->aq.elements * c->aq.rows;
+        const size_t ns = (size_t)c->params.scan_rows * c->params.scan_cols;
+        CUDA_TRY(cudaMemcpyAsync(c->d_rf_final, rf_in, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+        int launches = 0;
+        launch_scan_convert(c->d_rf_final, 1, c->aq.elements, c->aq.rows, c->d_map_x, c->d_map_y, c->params.scan_rows, c->params.scan_cols,
+                            c->d_scan, c->stream, &launches);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(scan_out, c->d_scan, sizeof(float) * ns, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return MCRT_OK;
+    });
+}
+
+int mcrt_get_psf_taps(const mcrt_ctx* c, float* axial, float* lateral)
+{
+    if (!c || !axial || !lateral) return fail(MCRT_ERR_INVALID, "mcrt_get_psf_taps: null argument");
+    memcpy(axial, c->h_axial.data(), sizeof(float) * c->h_axial.size());
+    memcpy(lateral, c->h_lateral.data(), sizeof(float) * c->h_lateral.size());
+    return MCRT_OK;
+}
+
+int mcrt_get_scene(const mcrt_ctx* c, float* tri_local9, int32_t* tri_mesh, float* mesh_origin3, float* materials8)
+{
+    if (!c) return fail(MCRT_ERR_INVALID, "mcrt_get_scene: null argument");
+    if (tri_local9) memcpy(tri_local9, c->scene.tri_local.data(), sizeof(float) * c->scene.tri_local.size());
+    if (tri_mesh) memcpy(tri_mesh, c->scene.tri_mesh.data(), sizeof(int32_t) * c->scene.tri_mesh.size());
+    if (mesh_origin3)
+        for (size_t m = 0; m < c->scene.meshes.size(); m++)
+            for (int a = 0; a < 3; a++) mesh_origin3[3 * m + a] = c->scene.meshes[m].origin[a];
+    if (materials8) memcpy(materials8, c->scene.materials.data(), sizeof(HostMaterial) * c->scene.materials.size());
+    return MCRT_OK;
+}
+
+int mcrt_get_volume(const mcrt_ctx* c, float* out)
+{
+    if (!c || !out) return fail(MCRT_ERR_INVALID, "mcrt_get_volume: null argument");
+    return guarded("mcrt_get_volume", [&]() {
+        CUDA_TRY(cudaSetDevice(c->device));
+        CUDA_TRY(cudaMemcpy(out, c->d_volume, sizeof(float) * 2 * (size_t)256 * 256 * 256, cudaMemcpyDeviceToHost));
+        return MCRT_OK;
+    });
+}
+
+int mcrt_numerics_probe(int device, int32_t op, int64_t n, const double* a, const double* b, double* out)
+{
+    if (n < 0 || !a || !b || !out) return fail(MCRT_ERR_INVALID, "mcrt_numerics_probe: bad argument");
+    if (n == 0) return MCRT_OK;
+    return guarded("mcrt_numerics_probe", [&]() {
+        CUDA_TRY(cudaSetDevice(device));
+        double *d_a = nullptr, *d_b = nullptr, *d_o = nullptr;
+        cudaError_t e = cudaSuccess;
+        dev_alloc(d_a, (size_t)n); dev_alloc(d_b, (size_t)n); dev_alloc(d_o, (size_t)n);
+        e = cudaMemcpy(d_a, a, sizeof(double) * n, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_b, b, sizeof(double) * n, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) { launch_numerics_probe(op, n, d_a, d_b, d_o, 0); e = cudaGetLastError(); }
+        if (e == cudaSuccess) e = cudaMemcpy(out, d_o, sizeof(double) * n, cudaMemcpyDeviceToHost);
+        dev_free(d_a); dev_free(d_b); dev_free(d_o);
+        CUDA_TRY(e);
+        return MCRT_OK;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,385 @@
+// image.cu -- image-formation kernels: echo accumulation with scatterer-volume sampling
+// (main.cpp:106-144, volume.h:46-61, rfimage.h:33-40), separable PSF convolution
+// (rfimage.h:93-123), envelope detection (rfimage.h:54-91) and scan conversion (rfimage.h:139,
+// 183-215).  RF images live in HBM scanline-major: rf[image][element][row], one scanline contiguous.
+#include "mcrt_device.cuh"
+#include "mcrt_launch.h"
+
+namespace mcrt {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// volume.h:46-61
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t voxel_index(float coord, float resolution)
+{
+    // static_cast<unsigned>(negative float) is UB in the reference; x86-64/GCC converts through a
+    // 64-bit integer and keeps the low 32 bits.  `% 256` of that is `& 255`.
+    const float q = coord / resolution;
+    return (uint32_t)__float2ll_rz(q) & 255u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Echo accumulation.  One thread marches one Monte-Carlo path (its segments in order, each a
+// sequential fp32 position chain that must be reproduced exactly); every thread owns a private
+// RF column in shared memory so there are no atomics and the summation order is fixed.  The
+// columns of the samples of a scanline are then reduced in sample order and written coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_accumulate(const SceneDev sc, const AcqDev aq, const float2* __restrict__ volume,
+                                                   const DevSegment* __restrict__ segments, const int32_t* __restrict__ nseg,
+                                                   const int n_scanlines, const int spc /*scanlines per CTA*/,
+                                                   const int tps /*threads per scanline*/, float* __restrict__ rf,
+                                                   unsigned long long* __restrict__ steps_total, float* g_columns)
+{
+    extern __shared__ float s_dyn[];                      // [rows][blockDim.x + 1] private columns ...
+    __shared__ DevMaterial s_mat[MCRT_MAX_SMEM_MATERIALS];
+    const int NT = blockDim.x;
+    const int stride = NT + 1;
+    const int rows = aq.rows;
+    const int tid = threadIdx.x;
+    // ... or, when a scanline is too long for shared memory (BASELINE config 5), the same layout in HBM
+    float* s_acc = g_columns ? g_columns + (size_t)blockIdx.x * rows * stride : s_dyn;
+    for (int i = tid; i < sc.n_mat && i < MCRT_MAX_SMEM_MATERIALS; i += NT) s_mat[i] = sc.materials[i];
+    for (int i = tid; i < rows * stride; i += NT) s_acc[i] = 0.0f;       // rf_image.clear(), main.cpp:102
+    __syncthreads();
+
+    const int sl_local = tid / tps;
+    const int j = tid - sl_local * tps;
+    const int scanline = blockIdx.x * spc + sl_local;
+    unsigned long long my_steps = 0;
+    if (sl_local < spc && scanline < n_scanlines) {
+        float* col = s_acc + tid;
+        const float axres_f = aq.axres_f;
+        const double time_step = aq.time_step_us;
+        const double max_travel_time = aq.max_travel_time_us;
+        const double row_period = aq.row_period_us, inv_row_period = aq.inv_row_period;
+        const float samples_f = (float)(size_t)aq.samples;
+        auto add_echo = [&](float echo, double micros) {                  // rfimage.h:33-40
+            // row = micros / (axial_resolution_/speed_of_sound_), truncated.  The product with the
+            // reciprocal decides the row unless it lands within 1e-9 of an integer, where the exact
+            // IEEE quotient is taken instead.
+            double rowd = micros * inv_row_period;
+            const double fl = floor(rowd);
+            const double fr_ = rowd - fl;
+            if (fr_ < 1e-9 || fr_ > 1.0 - 1e-9) rowd = micros / row_period;
+            if (rowd < (double)(unsigned)rows) col[(int)rowd * stride] += echo;
+        };
+        for (int s = j; s < aq.samples; s += tps) {
+            const int p = scanline * aq.samples + s;
+            const int ns = nseg[p];
+            for (int k = 0; k < ns; k++) {
+                const DevSegment* sg = segments + (size_t)p * aq.max_depth + k;
+                const float4 s0 = __ldg(&sg->s0), s1 = __ldg(&sg->s1), s2 = __ldg(&sg->s2);
+                const int4 s3 = __ldg(&sg->s3);
+                const DevMaterial media = s_mat[s3.z];
+                const double distance_traveled = __hiloint2double(s3.y, s3.x);
+                const double starting_micros = ((distance_traveled * 1000) / 1) / aq.speed;      // main.cpp:114
+                const float3 from = make_float3(s0.x, s0.y, s0.z), to = make_float3(s2.x, s2.y, s2.z);
+                const double distance = (double)(v_length(v_sub(to, from)) * 10.0f);               // scene.cpp:342-346
+                const double steps_d = distance / aq.axres_mm;                                      // main.cpp:116
+                unsigned long long steps64;                                                         // B-14
+                if (!(steps_d >= 0.0)) steps64 = 0;
+                else if (steps_d >= 9.0e18) steps64 = 9000000000000000000ULL;
+                else steps64 = (unsigned long long)steps_d;
+                const uint32_t steps32 = (uint32_t)steps64;
+                const float3 delta_step = v_scl(make_float3(s1.x, s1.y, s1.z), axres_f);            // main.cpp:117
+                float3 point = from;
+                double time_elapsed = starting_micros;
+                float intensity = s1.w;
+                const float decay = mc_expf(-s2.w * axres_f * 0.01f * aq.frequency * 1.0f);         // main.cpp:135
+                for (unsigned long long step = 0; step < steps64 && time_elapsed < max_travel_time; step++) {
+                    const uint32_t xi = voxel_index(point.x, aq.vol_resolution);
+                    const uint32_t yi = voxel_index(point.y, aq.vol_resolution);
+                    const uint32_t zi = voxel_index(point.z, aq.vol_resolution);
+                    const float2 vox = __ldg(&volume[((size_t)xi * 256 + yi) * 256 + zi]);          // (noise, probability)
+                    // get_scattering(mu1, mu0, sigma, ...): density = mu1, mu = mu0 (main.cpp:126 vs volume.h:46)
+                    const float scattering = vox.y >= media.mu1 ? vox.x * media.sigma + media.mu0 : 0.0f;
+                    add_echo(intensity * scattering, time_elapsed);
+                    point = v_add(point, delta_step);
+                    time_elapsed = time_elapsed + time_step;
+                    intensity *= decay;
+                    my_steps++;
+                }
+                // main.cpp:139
+                add_echo(s0.w / samples_f, starting_micros + time_step * (double)(uint32_t)(steps32 - 1u));
+            }
+        }
+    }
+    __syncthreads();
+    // ordered reduction over the threads of each scanline, coalesced store
+    for (int o = tid; o < spc * rows; o += NT) {
+        const int sl = o / rows, r = o - sl * rows;
+        const int gl = blockIdx.x * spc + sl;
+        if (gl >= n_scanlines) break;
+        const float* src = s_acc + r * stride + sl * tps;
+        float sum = src[0];
+        for (int t = 1; t < tps; t++) sum += src[t];
+        rf[(size_t)gl * rows + r] = sum;
+    }
+    if (steps_total) {
+        for (int off = 16; off > 0; off >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, off);
+        if ((tid & 31) == 0 && my_steps) atomicAdd(steps_total, my_steps);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rf_image::convolve (rfimage.h:93-123).  Pass 1 (axial, along a scanline) and pass 2 (lateral,
+// across scanlines) keep the reference's forward-looking taps, its sequential fp32 sum order and
+// its untouched borders (B-9): rows [0,Ka) and [rows-Ka,rows), columns [0,Kl/2) and [cols-Kl,cols)
+// keep the raw samples.
+// ------------------------------------------------------------------------------------------------
+#define MCRT_MAX_TAPS 256
+
+__global__ void __launch_bounds__(256) k_psf_axial(const float* __restrict__ in, const int64_t n_scanlines, const int rows,
+                                                  const float* __restrict__ taps, const int ka, float* __restrict__ out)
+{
+    __shared__ float s_taps[MCRT_MAX_TAPS];
+    for (int i = threadIdx.x; i < ka; i += blockDim.x) s_taps[i] = taps[i];
+    __syncthreads();
+    const int64_t total = n_scanlines * rows;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(i % rows);
+        if (row < ka || row >= rows - ka) continue;                      // conv_axial_buffer is never read there
+        const float* src = in + i;
+        float convolution = 0;
+        for (int k = 0; k < ka; k++) convolution += src[k] * s_taps[k];
+        out[i] = convolution;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_psf_lateral(const float* __restrict__ raw, const float* __restrict__ axial_buf, const int n_images,
+                                                    const int cols, const int rows, const float* __restrict__ taps, const int ka,
+                                                    const int kl, float* __restrict__ out)
+{
+    __shared__ float s_taps[MCRT_MAX_TAPS];
+    for (int i = threadIdx.x; i < kl; i += blockDim.x) s_taps[i] = taps[i];
+    __syncthreads();
+    const int64_t total = (int64_t)n_images * cols * rows;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(i % rows);
+        const int col = (int)((i / rows) % cols);
+        float v;
+        if (row >= ka && row < rows - ka && col >= kl / 2 && col < cols - kl) {
+            const float* src = axial_buf + i;
+            float convolution = 0;
+            for (int k = 0; k < kl; k++) convolution += src[(size_t)k * rows] * s_taps[k];
+            v = convolution;
+        } else {
+            v = raw[i];
+        }
+        out[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rf_image::envelope (rfimage.h:54-91): one warp per scanline.  A sample i in [1, rows-2] is a peak
+// iff I[i-1] < I[i] and not I[i] < I[i+1] (the sequential `ascending` flag reduces to this because
+// peak detection only ever reads samples that have not been rewritten yet).  Between consecutive
+// peaks p < q the output is lerp(last, |I[q]|) with last = I[0] (signed) for the virtual first peak
+// and |I[p]| otherwise; samples from the last peak on keep their raw value.
+// ------------------------------------------------------------------------------------------------
+#define MCRT_ENV_WARPS 4
+#define MCRT_ENV_MAX_CHUNKS 1024      // rows <= 32768
+
+__device__ __forceinline__ unsigned peak_mask(const float* __restrict__ I, int rows, int c, int lane)
+{
+    const int i = (c << 5) + lane;
+    const float v = i < rows ? I[i] : 0.0f;
+    const float vm = (i >= 1 && i < rows) ? I[i - 1] : 0.0f;
+    const float vp = (i + 1 < rows) ? I[i + 1] : 0.0f;
+    const bool peak = (i >= 1) && (i + 1 < rows) && (vm < v) && !(v < vp);
+    return __ballot_sync(0xffffffffu, peak);
+}
+
+__global__ void __launch_bounds__(32 * MCRT_ENV_WARPS) k_envelope(const float* __restrict__ in, const int64_t n_scanlines, const int rows,
+                                                                float* __restrict__ out)
+{
+    __shared__ unsigned s_mask[MCRT_ENV_WARPS][MCRT_ENV_MAX_CHUNKS];
+    __shared__ int s_next[MCRT_ENV_WARPS][MCRT_ENV_MAX_CHUNKS];
+    const int lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * MCRT_ENV_WARPS + w;
+    const int64_t n_warps = (int64_t)gridDim.x * MCRT_ENV_WARPS;
+    const int n_chunks = (rows + 31) >> 5;
+    for (int64_t sl = warp; sl < n_scanlines; sl += n_warps) {
+        const float* I = in + sl * rows;
+        float* O = out + sl * rows;
+        // pass A (backward): peak mask of every 32-row chunk and the first peak after each chunk
+        int next = rows;                               // "no peak"
+        for (int c = n_chunks - 1; c >= 0; c--) {
+            const unsigned m = peak_mask(I, rows, c, lane);
+            if (lane == 0) { s_mask[w][c] = m; s_next[w][c] = next; }
+            if (m) next = (c << 5) + (__ffs(m) - 1);
+        }
+        __syncwarp();
+        // pass B (forward): lerp between the enclosing peaks
+        int last_peak = 0;                             // the virtual first peak (0, I[0]) of rfimage.h:63-64
+        for (int c = 0; c < n_chunks; c++) {
+            const unsigned mask = s_mask[w][c];
+            const int i = (c << 5) + lane;
+            const unsigned le = mask & (0xffffffffu >> (31 - lane));
+            const int p = le ? (c << 5) + (31 - __clz(le)) : last_peak;
+            const unsigned gt = lane == 31 ? 0u : (mask & (0xffffffffu << (lane + 1)));
+            const int q = gt ? (c << 5) + (__ffs(gt) - 1) : s_next[w][c];
+            if (i < rows) {
+                float r = I[i];
+                if (q < rows) {
+                    const float last = (p == 0) ? I[0] : fabsf(I[p]);
+                    const float new_peak = fabsf(I[q]);
+                    const float alpha = ((float)i - (float)p) / ((float)q - (float)p);
+                    r = last * (1 - alpha) + new_peak * alpha;
+                }
+                O[i] = r;
+            }
+            if (mask) last_peak = (c << 5) + (31 - __clz(mask));
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_copy(const float* __restrict__ in, const int64_t n, float* __restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+// [n][cols][rows] -> [n][rows][cols] through a padded shared-memory tile
+__global__ void k_transpose(const float* __restrict__ in, const int cols, const int rows, float* __restrict__ out)
+{
+    __shared__ float tile[32][33];
+    const size_t img = (size_t)blockIdx.z * cols * rows;
+    int r = blockIdx.x * 32 + threadIdx.x, c = blockIdx.y * 32 + threadIdx.y;
+    for (int k = 0; k < 32; k += 8)
+        if (r < rows && c + k < cols) tile[threadIdx.y + k][threadIdx.x] = in[img + (size_t)(c + k) * rows + r];
+    __syncthreads();
+    c = blockIdx.y * 32 + threadIdx.x; r = blockIdx.x * 32 + threadIdx.y;
+    for (int k = 0; k < 32; k += 8)
+        if (c < cols && r + k < rows) out[img + (size_t)(r + k) * cols + c] = tile[threadIdx.x][threadIdx.y + k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// cv::remap(intensities, scan_converted, map1 = map_y (x = source column), map2 = map_x (y = source
+// row), INTER_LINEAR, BORDER_CONSTANT 0) (rfimage.h:139) as OpenCV evaluates it for CV_32FC1 maps:
+// coordinates rounded to 1/32 pixel, four taps weighted by a float table, out-of-image taps = 0.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int remap_fix(float v)
+{
+    const double t = (double)v * 32.0;
+    if (!(t == t)) return INT32_MIN;
+    if (t <= -2147483648.0) return INT32_MIN;
+    if (t >= 2147483647.0) return INT32_MAX;
+    return __double2int_rn(t);           // cvRound: round half to even
+}
+
+__global__ void __launch_bounds__(256) k_scan_convert(const float* __restrict__ rf, const int n_images, const int cols, const int rows,
+                                                     const float* __restrict__ map_x, const float* __restrict__ map_y, const int scan_rows,
+                                                     const int scan_cols, float* __restrict__ out)
+{
+    const int64_t per = (int64_t)scan_rows * scan_cols;
+    const int64_t total = per * n_images;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t img = i / per, px = i - img * per;
+        const float* S = rf + img * (int64_t)cols * rows;
+        const float x = __ldg(&map_y[px]), y = __ldg(&map_x[px]);
+        const int sx = remap_fix(x), sy = remap_fix(y);
+        const int ix = sx >> 5, iy = sy >> 5;
+        const int fx = sx & 31, fy = sy & 31;
+        const float ax = fx * (1.0f / 32), ay = fy * (1.0f / 32);
+        const float w0 = (1.0f - ay) * (1.0f - ax), w1 = (1.0f - ay) * ax, w2 = ay * (1.0f - ax), w3 = ay * ax;
+        // source pixel (row r, column c) lives at S[c * rows + r] (scanline-major)
+        auto pix = [&](int r, int c) -> float { return (r >= 0 && r < rows && c >= 0 && c < cols) ? S[(size_t)c * rows + r] : 0.0f; };
+        float v;
+        if (ix >= cols || ix + 1 < 0 || iy >= rows || iy + 1 < 0) v = 0.0f;
+        else v = pix(iy, ix) * w0 + pix(iy, ix + 1) * w1 + pix(iy + 1, ix) * w2 + pix(iy + 1, ix + 1) * w3;
+        out[i] = v;
+    }
+}
+
+int grid1d(int64_t n, int block)
+{
+    int64_t g = (n + block - 1) / block;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace
+
+cudaError_t init_image_kernels()
+{
+    // per-device function attribute; must not be issued inside a stream capture
+    return cudaFuncSetAttribute(k_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize, MCRT_ACC_SMEM_LIMIT);
+}
+
+size_t accumulate_columns_bytes(const AcqDev& aq, int n_poses)
+{
+    const int block = 32;
+    if (sizeof(float) * (size_t)aq.rows * (block + 1) <= MCRT_ACC_SMEM_LIMIT) return 0;
+    const int tps = aq.samples < 32 ? aq.samples : 32;
+    int spc = 32 / tps;
+    if (spc < 1) spc = 1;
+    const size_t grid = ((size_t)n_poses * aq.elements + spc - 1) / spc;
+    return grid * aq.rows * (block + 1) * sizeof(float);
+}
+
+cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2* d_volume, const DevSegment* d_segments,
+                              const int32_t* d_nseg, int n_poses, float* d_rf, unsigned long long* d_steps, float* d_columns,
+                              cudaStream_t stream, int* launches)
+{
+    const int n_scanlines = n_poses * aq.elements;
+    // threads per scanline: all samples in parallel when they fit a warp, else a warp striding over them
+    const int tps = aq.samples < 32 ? aq.samples : 32;
+    int spc = 32 / tps;
+    if (spc < 1) spc = 1;
+    const int block = 32;
+    size_t smem = sizeof(float) * (size_t)aq.rows * (block + 1);
+    if (smem > MCRT_ACC_SMEM_LIMIT) {
+        if (!d_columns) return cudaErrorInvalidConfiguration;      // caller must supply accumulate_columns_bytes() of HBM
+        smem = 0;
+    } else d_columns = nullptr;
+    const int grid = (n_scanlines + spc - 1) / spc;
+    k_accumulate<<<grid, block, smem, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_scanlines, spc, tps, d_rf, d_steps, d_columns);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+void launch_post(const float* d_in, int n_images, int cols, int rows, const float* d_axial, int n_axial, const float* d_lateral,
+                 int n_lateral, int flags, float* d_tmp0, float* d_tmp1, float* d_out, cudaStream_t stream, int* launches)
+{
+    const int64_t n_scanlines = (int64_t)n_images * cols;
+    const int64_t total = n_scanlines * rows;
+    const float* cur = d_in;
+    if (flags & 1) {
+        k_psf_axial<<<grid1d(total, 256), 256, 0, stream>>>(cur, n_scanlines, rows, d_axial, n_axial, d_tmp0);
+        float* dst = (flags & 2) ? d_tmp1 : d_out;
+        k_psf_lateral<<<grid1d(total, 256), 256, 0, stream>>>(cur, d_tmp0, n_images, cols, rows, d_lateral, n_axial, n_lateral, dst);
+        cur = dst;
+        if (launches) (*launches) += 2;
+    }
+    if (flags & 2) {
+        int64_t g = (n_scanlines + MCRT_ENV_WARPS - 1) / MCRT_ENV_WARPS;
+        if (g > 148 * 16) g = 148 * 16;
+        k_envelope<<<(int)g, 32 * MCRT_ENV_WARPS, 0, stream>>>(cur, n_scanlines, rows, d_out);
+        if (launches) (*launches)++;
+    } else if (!(flags & 1)) {
+        k_copy<<<grid1d(total, 256), 256, 0, stream>>>(cur, total, d_out);
+        if (launches) (*launches)++;
+    }
+}
+
+void launch_transpose(const float* d_in, int n_images, int cols, int rows, float* d_out, cudaStream_t stream, int* launches)
+{
+    dim3 block(32, 8, 1), grid((rows + 31) / 32, (cols + 31) / 32, n_images);
+    k_transpose<<<grid, block, 0, stream>>>(d_in, cols, rows, d_out);
+    if (launches) (*launches)++;
+}
+
+void launch_scan_convert(const float* d_rf, int n_images, int cols, int rows, const float* d_map_x, const float* d_map_y, int scan_rows,
+                         int scan_cols, float* d_out, cudaStream_t stream, int* launches)
+{
+    const int64_t total = (int64_t)n_images * scan_rows * scan_cols;
+    k_scan_convert<<<grid1d(total, 256), 256, 0, stream>>>(d_rf, n_images, cols, rows, d_map_x, d_map_y, scan_rows, scan_cols, d_out);
+    if (launches) (*launches)++;
+}
+
+}  // namespace mcrt

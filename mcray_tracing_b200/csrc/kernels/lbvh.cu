@@ -1,0 +1,281 @@
+// lbvh.cu -- device-side BVH construction: replaces Bullet's btBvhTriangleMeshShape /
+// btQuantizedBvh build per OBJ (scene.cpp:300-334, `new btBvhTriangleMeshShape(tiva, true)`) and
+// the btDbvtBroadphase over the bodies (scene.cpp:249-262) with ONE world-space LBVH over all
+// triangles of all meshes.
+//
+// Pipeline (all on the GPU): world boxes + centroids -> 63-bit Morton keys -> radix sort
+// (cub::DeviceRadixSort, the CUDA toolkit's primitive; start-up only) -> Karras 2012 radix-tree
+// hierarchy -> bottom-up refit with arrival counters -> 64-byte traversal nodes + Morton-ordered
+// 48-byte triangle slots.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "mcrt_device.cuh"
+#include "mcrt_launch.h"
+
+namespace mcrt {
+
+namespace {
+
+__device__ __forceinline__ int f2ord(float f)       // order-preserving float -> int
+{
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__host__ __device__ __forceinline__ float ord2f(int i)
+{
+    const int j = i >= 0 ? i : i ^ 0x7fffffff;
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(j);
+#else
+    float f; memcpy(&f, &j, 4); return f;
+#endif
+}
+
+// world-space box of a triangle: fl(v_local + body origin) per vertex
+__global__ void k_tri_bounds(const float* __restrict__ tri_local, const int32_t* __restrict__ tri_mesh, const DevMesh* __restrict__ meshes,
+                             int n, float4* __restrict__ box_lo, float4* __restrict__ box_hi, int* __restrict__ scene_bounds)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const DevMesh m = meshes[tri_mesh[t]];
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int k = 0; k < 3; k++) {
+        const float w[3] = {tri_local[9 * (size_t)t + 3 * k] + m.ox, tri_local[9 * (size_t)t + 3 * k + 1] + m.oy,
+                            tri_local[9 * (size_t)t + 3 * k + 2] + m.oz};
+        for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], w[a]); hi[a] = fmaxf(hi[a], w[a]); }
+    }
+    box_lo[t] = make_float4(lo[0], lo[1], lo[2], 0.f);
+    box_hi[t] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    for (int a = 0; a < 3; a++) {
+        atomicMin(&scene_bounds[a], f2ord(lo[a]));
+        atomicMax(&scene_bounds[3 + a], f2ord(hi[a]));
+    }
+}
+
+__device__ __forceinline__ unsigned long long expand21(unsigned long long v)
+{
+    v &= 0x1fffffULL;
+    v = (v | (v << 32)) & 0x1f00000000ffffULL;
+    v = (v | (v << 16)) & 0x1f0000ff0000ffULL;
+    v = (v | (v << 8)) & 0x100f00f00f00f00fULL;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ULL;
+    v = (v | (v << 2)) & 0x1249249249249249ULL;
+    return v;
+}
+
+__global__ void k_morton(const float4* __restrict__ box_lo, const float4* __restrict__ box_hi, const int* __restrict__ scene_bounds, int n,
+                         unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    float q[3];
+    const float lo[3] = {box_lo[t].x, box_lo[t].y, box_lo[t].z}, hi[3] = {box_hi[t].x, box_hi[t].y, box_hi[t].z};
+    for (int a = 0; a < 3; a++) {
+        const float slo = ord2f(scene_bounds[a]), shi = ord2f(scene_bounds[3 + a]);
+        const float c = 0.5f * (lo[a] + hi[a]);
+        const float ext = fmaxf(shi - slo, 1e-30f);
+        q[a] = fminf(fmaxf((c - slo) / ext, 0.0f), 1.0f);
+    }
+    const unsigned long long x = (unsigned long long)fminf(q[0] * 2097152.0f, 2097151.0f);
+    const unsigned long long y = (unsigned long long)fminf(q[1] * 2097152.0f, 2097151.0f);
+    const unsigned long long z = (unsigned long long)fminf(q[2] * 2097152.0f, 2097151.0f);
+    keys[t] = (expand21(x) << 2) | (expand21(y) << 1) | expand21(z);
+    vals[t] = (unsigned int)t;
+}
+
+// Karras 2012: delta(i,j) = length of the common prefix of keys i and j (key ties broken by index)
+__device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    const unsigned long long a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz(i ^ j);
+    return __clzll((long long)(a ^ b));
+}
+
+__global__ void k_karras(const unsigned long long* __restrict__ keys, int n, int* __restrict__ left, int* __restrict__ right,
+                         int* __restrict__ parent_internal, int* __restrict__ parent_leaf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    // child encoding: >= 0 internal, < 0 leaf (~sorted position)
+    const int lc = (lo == gamma) ? ~gamma : gamma;
+    const int rc = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    left[i] = lc;
+    right[i] = rc;
+    if (lc >= 0) parent_internal[lc] = i; else parent_leaf[~lc] = i;
+    if (rc >= 0) parent_internal[rc] = i; else parent_leaf[~rc] = i;
+    if (i == 0) parent_internal[0] = -1;
+}
+
+// bottom-up refit: the second thread to arrive at a node owns it
+__global__ void k_refit(const unsigned int* __restrict__ vals, const float4* __restrict__ box_lo, const float4* __restrict__ box_hi, int n,
+                        const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parent_internal,
+                        const int* __restrict__ parent_leaf, int* __restrict__ arrivals, float4* __restrict__ node_lo,
+                        float4* __restrict__ node_hi, int* __restrict__ max_depth)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int node = parent_leaf[k];
+    int depth = 1;
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(&arrivals[node], 1) == 0) return;      // first arrival: sibling subtree not ready
+        __threadfence();
+        const int lc = left[node], rc = right[node];
+        float4 llo, lhi, rlo, rhi;
+        if (lc >= 0) { llo = node_lo[lc]; lhi = node_hi[lc]; } else { const unsigned int t = vals[~lc]; llo = box_lo[t]; lhi = box_hi[t]; }
+        if (rc >= 0) { rlo = node_lo[rc]; rhi = node_hi[rc]; } else { const unsigned int t = vals[~rc]; rlo = box_lo[t]; rhi = box_hi[t]; }
+        node_lo[node] = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.f);
+        node_hi[node] = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f);
+        depth++;
+        node = parent_internal[node];
+    }
+    atomicMax(max_depth, depth);   // only the thread that completes the root gets here
+}
+
+// exact depth of the tree (longest leaf-to-root chain): the traversal stack bound
+__global__ void k_leaf_depth(int n, const int* __restrict__ parent_internal, const int* __restrict__ parent_leaf, int* __restrict__ max_depth)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int depth = 0;
+    for (int node = parent_leaf[k]; node >= 0; node = parent_internal[node]) depth++;
+    atomicMax(max_depth, depth);
+}
+
+__global__ void k_emit_nodes(const unsigned int* __restrict__ vals, const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
+                             int n, const int* __restrict__ left, const int* __restrict__ right, const float4* __restrict__ node_lo,
+                             const float4* __restrict__ node_hi, BvhNode* __restrict__ nodes)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int lc = left[i], rc = right[i];
+    float4 llo, lhi, rlo, rhi;
+    if (lc >= 0) { llo = node_lo[lc]; lhi = node_hi[lc]; } else { const unsigned int t = vals[~lc]; llo = box_lo[t]; lhi = box_hi[t]; }
+    if (rc >= 0) { rlo = node_lo[rc]; rhi = node_hi[rc]; } else { const unsigned int t = vals[~rc]; rlo = box_lo[t]; rhi = box_hi[t]; }
+    BvhNode nd;
+    nd.a = make_float4(llo.x, llo.y, llo.z, lhi.x);
+    nd.b = make_float4(lhi.y, lhi.z, rlo.x, rlo.y);
+    nd.c = make_float4(rlo.z, rhi.x, rhi.y, rhi.z);
+    nd.d = make_int4(lc, rc, 0, 0);
+    nodes[i] = nd;
+}
+
+__global__ void k_emit_tris(const unsigned int* __restrict__ vals, const float* __restrict__ tri_local, const int32_t* __restrict__ tri_mesh,
+                            int n, TriSlot* __restrict__ slots)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const unsigned int t = vals[k];
+    const float* p = tri_local + 9 * (size_t)t;
+    TriSlot s;
+    s.v0 = make_float4(p[0], p[1], p[2], __int_as_float(tri_mesh[t]));
+    s.v1 = make_float4(p[3], p[4], p[5], __int_as_float((int)t));
+    s.v2 = make_float4(p[6], p[7], p[8], 0.f);
+    slots[k] = s;
+}
+
+}  // namespace
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = e_; goto done; } } while (0)
+
+cudaError_t build_lbvh(const float* h_tri_local, const int32_t* h_tri_mesh, int n_tri, const DevMesh* d_meshes, cudaStream_t stream,
+                       LbvhResult* out)
+{
+    cudaError_t err = cudaSuccess;
+    memset(out, 0, sizeof(*out));
+    float* d_tri_local = nullptr; int32_t* d_tri_mesh = nullptr;
+    float4 *d_lo = nullptr, *d_hi = nullptr, *d_nlo = nullptr, *d_nhi = nullptr;
+    int *d_bounds = nullptr, *d_left = nullptr, *d_right = nullptr, *d_pi = nullptr, *d_pl = nullptr, *d_arr = nullptr, *d_depth = nullptr;
+    unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
+    unsigned int *d_vals = nullptr, *d_vals2 = nullptr;
+    void* d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    const int n = n_tri;
+    const int B = 256, G = (n + B - 1) / B;
+    int h_bounds[6];
+    int h_depth[2] = {0, 0};
+    if (n <= 0) return cudaSuccess;
+
+    CK(cudaMalloc(&d_tri_local, sizeof(float) * 9 * (size_t)n));
+    CK(cudaMalloc(&d_tri_mesh, sizeof(int32_t) * (size_t)n));
+    CK(cudaMemcpyAsync(d_tri_local, h_tri_local, sizeof(float) * 9 * (size_t)n, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_tri_mesh, h_tri_mesh, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, stream));
+    CK(cudaMalloc(&d_lo, sizeof(float4) * (size_t)n));
+    CK(cudaMalloc(&d_hi, sizeof(float4) * (size_t)n));
+    CK(cudaMalloc(&d_bounds, sizeof(int) * 6));
+    for (int a = 0; a < 3; a++) { h_bounds[a] = 0x7f7fffff; h_bounds[3 + a] = (int)0x80800000 /* ord(-FLT_MAX) */; }
+    h_bounds[3] = h_bounds[4] = h_bounds[5] = (int)(0xff7fffffu ^ 0x7fffffffu);
+    CK(cudaMemcpyAsync(d_bounds, h_bounds, sizeof(h_bounds), cudaMemcpyHostToDevice, stream));
+    k_tri_bounds<<<G, B, 0, stream>>>(d_tri_local, d_tri_mesh, d_meshes, n, d_lo, d_hi, d_bounds);
+    CK(cudaGetLastError());
+    CK(cudaMalloc(&out->tris, sizeof(TriSlot) * (size_t)n));
+    CK(cudaMalloc(&d_vals, sizeof(unsigned int) * (size_t)n));
+    if (n >= 2) {
+        CK(cudaMalloc(&d_keys, sizeof(unsigned long long) * (size_t)n));
+        CK(cudaMalloc(&d_keys2, sizeof(unsigned long long) * (size_t)n));
+        CK(cudaMalloc(&d_vals2, sizeof(unsigned int) * (size_t)n));
+        k_morton<<<G, B, 0, stream>>>(d_lo, d_hi, d_bounds, n, d_keys2, d_vals2);
+        CK(cudaGetLastError());
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys2, d_keys, d_vals2, d_vals, n, 0, 63, stream));
+        CK(cudaMalloc(&d_tmp, tmp_bytes));
+        CK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys2, d_keys, d_vals2, d_vals, n, 0, 63, stream));
+        CK(cudaMalloc(&d_left, sizeof(int) * (size_t)(n - 1)));
+        CK(cudaMalloc(&d_right, sizeof(int) * (size_t)(n - 1)));
+        CK(cudaMalloc(&d_pi, sizeof(int) * (size_t)(n - 1)));
+        CK(cudaMalloc(&d_pl, sizeof(int) * (size_t)n));
+        CK(cudaMalloc(&d_arr, sizeof(int) * (size_t)(n - 1)));
+        CK(cudaMalloc(&d_depth, sizeof(int) * 2));
+        CK(cudaMalloc(&d_nlo, sizeof(float4) * (size_t)(n - 1)));
+        CK(cudaMalloc(&d_nhi, sizeof(float4) * (size_t)(n - 1)));
+        CK(cudaMemsetAsync(d_arr, 0, sizeof(int) * (size_t)(n - 1), stream));
+        CK(cudaMemsetAsync(d_depth, 0, sizeof(int) * 2, stream));
+        k_karras<<<G, B, 0, stream>>>(d_keys, n, d_left, d_right, d_pi, d_pl);
+        CK(cudaGetLastError());
+        k_refit<<<G, B, 0, stream>>>(d_vals, d_lo, d_hi, n, d_left, d_right, d_pi, d_pl, d_arr, d_nlo, d_nhi, d_depth);
+        CK(cudaGetLastError());
+        k_leaf_depth<<<G, B, 0, stream>>>(n, d_pi, d_pl, d_depth + 1);
+        CK(cudaGetLastError());
+        CK(cudaMalloc(&out->nodes, sizeof(BvhNode) * (size_t)(n - 1)));
+        k_emit_nodes<<<G, B, 0, stream>>>(d_vals, d_lo, d_hi, n, d_left, d_right, d_nlo, d_nhi, out->nodes);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h_depth, d_depth, sizeof(h_depth), cudaMemcpyDeviceToHost, stream));
+    } else {
+        const unsigned int zero = 0;
+        CK(cudaMemcpyAsync(d_vals, &zero, sizeof(zero), cudaMemcpyHostToDevice, stream));
+    }
+    k_emit_tris<<<G, B, 0, stream>>>(d_vals, d_tri_local, d_tri_mesh, n, out->tris);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_bounds, d_bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    out->n_tri = n;
+    out->n_nodes = n >= 2 ? n - 1 : 0;
+    out->max_depth = h_depth[1];
+    out->max_abs = 0.0f;
+    for (int a = 0; a < 6; a++) { const float f = fabsf(ord2f(h_bounds[a])); if (f > out->max_abs) out->max_abs = f; }
+done:
+    cudaFree(d_tri_local); cudaFree(d_tri_mesh); cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_nlo); cudaFree(d_nhi);
+    cudaFree(d_bounds); cudaFree(d_left); cudaFree(d_right); cudaFree(d_pi); cudaFree(d_pl); cudaFree(d_arr); cudaFree(d_depth);
+    cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_tmp);
+    if (err != cudaSuccess) { cudaFree(out->nodes); cudaFree(out->tris); memset(out, 0, sizeof(*out)); }
+    return err;
+}
+
+}  // namespace mcrt

@@ -1,0 +1,328 @@
+// mcrt_device.cuh -- device-side data layout and the ray-physics device functions shared by the
+// trace kernels.  Arithmetic follows the reference's evaluation order in fp32/fp64 (citations to
+// thepochynsons/MCRay-Tracing); this translation unit family is compiled with -fmad=false so no
+// multiply-add is ever contracted, and all transcendentals come from mcrt_numerics.h.
+#ifndef MCRT_DEVICE_CUH
+#define MCRT_DEVICE_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../common/mcrt_numerics.h"
+
+namespace mcrt {
+
+// ------------------------------------------------------------------------------------------------
+// HBM layout
+// ------------------------------------------------------------------------------------------------
+struct DevMaterial { float impedance, attenuation, mu0, mu1, sigma, specularity, shininess, thickness; };   // 32 B
+struct DevMesh { float ox, oy, oz; int mat_in; int mat_out; int vascular; int pad0, pad1; };                // 32 B
+
+// BVH2 node, 64 B = one half cache line pair, fetched as 4 x LDG.128.
+//   a = (c0.lo.x, c0.lo.y, c0.lo.z, c0.hi.x)   b = (c0.hi.y, c0.hi.z, c1.lo.x, c1.lo.y)
+//   c = (c1.lo.z, c1.hi.x, c1.hi.y, c1.hi.z)   d = (child0, child1, -, -)
+// child >= 0: internal node index; child < 0: leaf, ~child = triangle slot.
+struct __align__(16) BvhNode { float4 a, b, c; int4 d; };
+
+// Triangle slot (48 B, Morton order): local-frame vertices v_obj*scaling; v0.w = mesh id bits,
+// v1.w = original (objloader-order) triangle id bits.
+struct __align__(16) TriSlot { float4 v0, v1, v2; };
+
+// One emitted segment, 64 B (ray.h:28-36 minus the dangling media reference, B-1).
+//   s0 = (from.xyz, reflected_intensity)  s1 = (dir.xyz, initial_intensity)
+//   s2 = (to.xyz, attenuation)            s3 = (distance_traveled lo, hi [double bits], media_id, tri_id)
+struct __align__(16) DevSegment { float4 s0, s1, s2; int4 s3; };
+
+#define MCRT_MAX_SMEM_MESHES 64
+#define MCRT_MAX_SMEM_MATERIALS 64
+
+struct SceneDev {
+    const BvhNode* nodes;
+    const TriSlot* tris;
+    const DevMesh* meshes;
+    const DevMaterial* materials;
+    int n_tri, n_mesh, n_mat;
+    int starting_material;
+    float spacing[3];
+    float max_abs;          // largest |coordinate| of any world-space triangle box
+};
+
+struct AcqDev {
+    int elements, samples, max_depth, rows;
+    float frequency;
+    float axres_f;          // axial_resolution.to<float>()
+    float radius_f;         // transducer_radius.to<float>() [cm]
+    float vol_resolution;   // resolution_um / 1000.0f
+    double axres_mm;
+    double time_step_us;
+    double row_period_us;
+    double inv_row_period;
+    double max_travel_time_us;
+    double speed;           // (double)speed_of_sound
+    int deterministic;
+    int pad;
+};
+
+struct PoseTrigDev { float px, py, pz, cz, sz, cx, sx, cy, sy, pad0, pad1, pad2; };   // = mcrt::PoseTrig, 48 B
+
+// Path state between bounces (ray.h:13-26), SoA.
+struct PathState {
+    float4* origin_intensity;   // (from.xyz, intensity)
+    float4* dir_state;          // (dir.xyz, packed: media | (outside+2)<<8 | depth<<16)
+    double* distance;           // distance_traveled [mm]
+};
+
+#define MCRT_OUTSIDE_NULL (-1)
+#define MCRT_OUTSIDE_SELF (-2)
+#define MCRT_INTENSITY_EPSILON 1e-10f     // ray.h:24
+
+// ------------------------------------------------------------------------------------------------
+// btVector3, scalar path
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 v_add(float3 a, float3 b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 v_sub(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 v_neg(float3 a) { return make_float3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float3 v_scl(float3 a, float s) { return make_float3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float v_dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 v_cross(float3 a, float3 b)
+{
+    return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float v_length(float3 a) { return sqrtf(v_dot(a, a)); }
+__device__ __forceinline__ float3 v_normalized(float3 a) { return v_scl(a, 1.0f / v_length(a)); }
+__device__ __forceinline__ float3 v_interpolate3(float3 v0, float3 v1, float rt)     // btVector3::setInterpolate3
+{
+    const float s = 1.0f - rt;
+    return make_float3(s * v0.x + rt * v1.x, s * v0.y + rt * v1.y, s * v0.z + rt * v1.z);
+}
+// btVector3::rotate with the host-supplied cos/sin of the angle
+__device__ __forceinline__ float3 v_rotate(float3 v, float3 axis, float c, float s)
+{
+    const float3 o = v_scl(axis, v_dot(axis, v));
+    const float3 x_ = v_sub(v, o);
+    const float3 y_ = v_cross(axis, v);
+    return v_add(v_add(o, v_scl(x_, c)), v_scl(y_, s));
+}
+
+// ------------------------------------------------------------------------------------------------
+// ray_physics (ray.cpp)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rp_max_ray_length(float attenuation, float intensity, float frequency)   // ray.cpp:110-113
+{
+    return 10.f * mc_logf(MCRT_INTENSITY_EPSILON / intensity) / -attenuation * frequency;
+}
+
+__device__ __forceinline__ float3 rp_snells_law(float3 l, float3 n, float c, float refraction_angle, float r)   // ray.cpp:115-124
+{
+    return v_add(v_scl(l, r), v_scl(n, r * c - refraction_angle));
+}
+
+__device__ __forceinline__ float rp_reflection_intensity(float intensity_in, float media_1, float incidence_angle, float media_2,
+                                                         float refracted_angle)                                    // ray.cpp:126-132
+{
+    const float num = media_1 * incidence_angle - media_2 * refracted_angle;
+    const float denom = media_1 * incidence_angle + media_2 * refracted_angle;
+    const double q = (double)(num / denom);
+    return (float)((double)intensity_in * (q * q));
+}
+
+__device__ __forceinline__ float rp_reflected_intensity_eq8(float3 d, float3 refr, float3 refl, float specularity)  // ray.cpp:154-164
+{
+    const float refraction_angle = v_dot(d, refr);
+    float refraction_factor = mc_powf(refraction_angle, specularity);
+    const float reflection_angle = v_dot(d, refl);
+    float reflection_factor = mc_powf(reflection_angle, specularity);
+    if (refraction_factor != refraction_factor) refraction_factor = 0.0f;      // B-5
+    if (reflection_factor != reflection_factor) reflection_factor = 0.0f;
+    return fmaxf(refraction_factor, 0.0f) + fmaxf(reflection_factor, 0.0f);
+}
+
+__device__ __forceinline__ float rp_power_cosine_variate(int v, double number)    // ray.cpp:213-224 (int v: B-8)
+{
+    const int indice = v + 1;
+    const float exponente = (float)((double)1.0 / indice);
+    return (float)mc_pow(number, (double)exponente);
+}
+
+// ray.cpp:167-211, one disk-sampling attempt
+__device__ __forceinline__ bool rp_random_unit_vector_attempt(float3 v, float cos_theta, double u_az, double u_rad, float3& out)
+{
+    const double a = u_az * 2 * MC_PI_D;
+    const double r = 0.5 * sqrt(u_rad);
+    double sn, cs;
+    mc_sincos(a, &sn, &cs);
+    float px = (float)(r * cs);
+    float py = (float)(r * sn);
+    const float p = px * px + py * py;
+    if (!(p <= 0.25f)) return false;
+    bool flag = false;
+    float vx = v.x, vy = v.y;
+    const float vz = v.z;
+    if (fabsf(vx) > fabsf(vy)) { vx = vy; vy = v.x; flag = true; }
+    const float b = 1 - vx * vx;
+    float radicando = 1 - cos_theta * cos_theta;
+    radicando = radicando / (p * b);
+    const float c = sqrtf(radicando);
+    px = px * c;
+    py = py * c;
+    const float d = cos_theta - vx * px;
+    float wx = vx * cos_theta - b * px;
+    float wy = vy * d + vz * py;
+    const float wz = vz * d - vy * py;
+    if (flag) { const float aux = wy; wy = wx; wx = aux; }
+    out = make_float3(wx, wy, wz);
+    return true;
+}
+
+// scene.cpp:281-290
+__device__ __forceinline__ double rp_distance_in_mm(const float* spacing, float3 v1, float3 v2)
+{
+    const float x_dist = fabsf(v1.x - v2.x) * spacing[0];
+    const float y_dist = fabsf(v1.y - v2.y) * spacing[1];
+    const float z_dist = fabsf(v1.z - v2.z) * spacing[2];
+    const double xd = x_dist, yd = y_dist, zd = z_dist;
+    return sqrt(xd * xd + yd * yd + zd * zd) * 10;
+}
+
+// ------------------------------------------------------------------------------------------------
+// closest hit: device BVH traversal + Bullet's triangle ray-cast (btTriangleRaycastCallback)
+// ------------------------------------------------------------------------------------------------
+struct HitRec {
+    float fraction;     // m_closestHitFraction (1.0f = no hit)
+    int tri_id;         // original triangle id, -1 = none
+    int mesh;
+    float3 n_raw;       // un-normalised triangle normal of the best hit
+    float dist_a;       // signed plane distance of the ray origin (normal flip rule)
+};
+
+__device__ __forceinline__ void tri_test(const TriSlot* __restrict__ tris, int slot, const float4* __restrict__ s_mesh, float3 from_w,
+                                         float3 to_w, HitRec& best)
+{
+    const float4 q0 = __ldg(&tris[slot].v0);
+    const float4 q1 = __ldg(&tris[slot].v1);
+    const float4 q2 = __ldg(&tris[slot].v2);
+    const int mesh = __float_as_int(q0.w);
+    const int tri = __float_as_int(q1.w);
+    const float4 mo = s_mesh[mesh];
+    // worldTocollisionObject * p with an identity basis = p - body origin
+    const float3 from_l = make_float3(from_w.x - mo.x, from_w.y - mo.y, from_w.z - mo.z);
+    const float3 to_l = make_float3(to_w.x - mo.x, to_w.y - mo.y, to_w.z - mo.z);
+    const float3 vert0 = make_float3(q0.x, q0.y, q0.z), vert1 = make_float3(q1.x, q1.y, q1.z), vert2 = make_float3(q2.x, q2.y, q2.z);
+    const float3 v10 = v_sub(vert1, vert0);
+    const float3 v20 = v_sub(vert2, vert0);
+    const float3 n = v_cross(v10, v20);
+    const float dist = v_dot(vert0, n);
+    float dist_a = v_dot(n, from_l);
+    dist_a -= dist;
+    float dist_b = v_dot(n, to_l);
+    dist_b -= dist;
+    if (dist_a * dist_b >= 0.0f) return;
+    const float proj_length = dist_a - dist_b;
+    const float distance = dist_a / proj_length;
+    if (!(distance < best.fraction || (distance == best.fraction && tri < best.tri_id))) return;
+    float edge_tolerance = v_dot(n, n);
+    edge_tolerance *= -0.0001f;
+    const float3 point = v_interpolate3(from_l, to_l, distance);
+    const float3 v0p = v_sub(vert0, point);
+    const float3 v1p = v_sub(vert1, point);
+    const float3 cp0 = v_cross(v0p, v1p);
+    if (v_dot(cp0, n) >= edge_tolerance) {
+        const float3 v2p = v_sub(vert2, point);
+        const float3 cp1 = v_cross(v1p, v2p);
+        if (v_dot(cp1, n) >= edge_tolerance) {
+            const float3 cp2 = v_cross(v2p, v0p);
+            if (v_dot(cp2, n) >= edge_tolerance) {
+                best.fraction = distance;
+                best.tri_id = tri;
+                best.mesh = mesh;
+                best.n_raw = n;
+                best.dist_a = dist_a;
+            }
+        }
+    }
+}
+
+// Conservative slab test of one child box against the segment (see DESIGN.md "Traversal"): the
+// ray origin is widened by +-e per axis (o_near / o_far) and the interval compare carries a
+// relative slack, so the BVH can never cull a triangle the exact per-triangle arithmetic accepts.
+struct RayBox {
+    float onx, ony, onz;   // origin for the near plane (o + e where inv >= 0 else o - e)
+    float ofx, ofy, ofz;   // origin for the far plane
+    float ix, iy, iz;      // 1 / (to - from)
+    bool px, py, pz;       // inv >= 0
+};
+
+__device__ __forceinline__ RayBox make_raybox(float3 from_w, float3 to_w, float scene_max_abs)
+{
+    RayBox r;
+    const float dx = to_w.x - from_w.x, dy = to_w.y - from_w.y, dz = to_w.z - from_w.z;
+    r.ix = 1.0f / dx; r.iy = 1.0f / dy; r.iz = 1.0f / dz;
+    r.px = r.ix >= 0.0f; r.py = r.iy >= 0.0f; r.pz = r.iz >= 0.0f;
+    const float mo = fmaxf(fabsf(from_w.x), fmaxf(fabsf(from_w.y), fabsf(from_w.z)));
+    const float e = 4e-6f * (scene_max_abs + mo) + 1e-7f;
+    r.onx = r.px ? from_w.x + e : from_w.x - e; r.ofx = r.px ? from_w.x - e : from_w.x + e;
+    r.ony = r.py ? from_w.y + e : from_w.y - e; r.ofy = r.py ? from_w.y - e : from_w.y + e;
+    r.onz = r.pz ? from_w.z + e : from_w.z - e; r.ofz = r.pz ? from_w.z - e : from_w.z + e;
+    return r;
+}
+
+__device__ __forceinline__ bool box_test(const RayBox& r, float lox, float loy, float loz, float hix, float hiy, float hiz, float tbest,
+                                         float& tnear)
+{
+    const float nx = r.px ? lox : hix, fx = r.px ? hix : lox;
+    const float ny = r.py ? loy : hiy, fy = r.py ? hiy : loy;
+    const float nz = r.pz ? loz : hiz, fz = r.pz ? hiz : loz;
+    const float t0x = (nx - r.onx) * r.ix, t1x = (fx - r.ofx) * r.ix;
+    const float t0y = (ny - r.ony) * r.iy, t1y = (fy - r.ofy) * r.iy;
+    const float t0z = (nz - r.onz) * r.iz, t1z = (fz - r.ofz) * r.iz;
+    // fmaxf / fminf drop NaN operands (0 * inf when the origin sits exactly on a slab plane)
+    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tbest));
+    tnear = tn;
+    return tn <= tf * 1.000002f + 1e-37f;
+}
+
+__device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __restrict__ s_mesh, float3 from_w, float3 to_w, HitRec& best)
+{
+    best.fraction = 1.0f; best.tri_id = -1; best.mesh = -1; best.n_raw = make_float3(0.f, 0.f, 0.f); best.dist_a = 0.0f;
+    if (sc.n_tri <= 0) return;
+    if (sc.n_tri == 1) { tri_test(sc.tris, 0, s_mesh, from_w, to_w, best); return; }
+    const RayBox rb = make_raybox(from_w, to_w, sc.max_abs);
+    int stack[64];
+    int sp = 0;
+    int node = 0;   // root
+    while (true) {
+        if (node >= 0) {
+            const BvhNode* nd = sc.nodes + node;
+            const float4 a = __ldg(&nd->a), b = __ldg(&nd->b), c = __ldg(&nd->c);
+            const int4 d = __ldg(&nd->d);
+            const float tb = best.fraction * 1.000002f;
+            float t0, t1;
+            const bool h0 = box_test(rb, a.x, a.y, a.z, a.w, b.x, b.y, tb, t0);
+            const bool h1 = box_test(rb, b.z, b.w, c.x, c.y, c.z, c.w, tb, t1);
+            if (h0 && h1) {
+                const bool swap = t1 < t0;
+                const int nearc = swap ? d.y : d.x, farc = swap ? d.x : d.y;
+                if (sp < 64) stack[sp++] = farc;
+                node = nearc;
+                continue;
+            }
+            if (h0) { node = d.x; continue; }
+            if (h1) { node = d.y; continue; }
+        } else {
+            tri_test(sc.tris, ~node, s_mesh, from_w, to_w, best);
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+}
+
+// final normal of the best hit: normalise, face the ray origin (btTriangleRaycastCallback)
+__device__ __forceinline__ float3 hit_normal(const HitRec& h)
+{
+    const float3 n = v_normalized(h.n_raw);
+    return (h.dist_a <= 0.0f) ? v_neg(n) : n;
+}
+
+}  // namespace mcrt
+#endif

@@ -1,0 +1,73 @@
+// mcrt_launch.h -- host-callable launchers of the sm_100a kernels (lbvh.cu, trace.cu, image.cu).
+#ifndef MCRT_LAUNCH_H
+#define MCRT_LAUNCH_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mcrt_device.cuh"
+
+namespace mcrt {
+
+struct LbvhResult {
+    BvhNode* nodes;
+    TriSlot* tris;
+    int n_tri, n_nodes;
+    int max_depth;      // longest leaf-to-root chain = traversal stack bound
+    float max_abs;
+};
+#define MCRT_TRAVERSAL_STACK 64
+
+// builds the device BVH from host triangle data; d_meshes must already be on the device
+cudaError_t build_lbvh(const float* h_tri_local, const int32_t* h_tri_mesh, int n_tri, const DevMesh* d_meshes, cudaStream_t stream,
+                       LbvhResult* out);
+
+struct FrameDev {
+    const PoseTrigDev* poses;            // [n_poses]
+    const float2* elem_sincos;           // [elements] (sin a_t, cos a_t)
+    const unsigned long long* seed_frame;   // device: {Philox seed, first frame}; kept in HBM so a captured graph stays valid
+    int n_poses;
+    int pad;
+};
+
+struct TraceBuffers {
+    PathState paths;               // [n_paths]
+    DevSegment* segments;          // [n_paths][max_depth]
+    int32_t* n_segments;           // [n_paths]
+    float* hit_fraction;           // [n_paths][max_depth] or nullptr
+    int32_t* hit_mesh;             // [n_paths][max_depth] or nullptr
+    int* queue_a;                  // [n_paths]
+    int* queue_b;                  // [n_paths]
+    int* counters;                 // [max_depth + 1]: counters[b] = live paths entering bounce b
+};
+
+// generate + max_depth x (intersect, shade, compact): scene::cast_rays (scene.cpp:50-183)
+void launch_trace(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, const TraceBuffers& tb, int sm_count, cudaStream_t stream,
+                  int* launches);
+void launch_closest_hit(const SceneDev& sc, int64_t n, const float* d_from, const float* d_to, int32_t* d_tri, int32_t* d_mesh,
+                        float* d_frac, float* d_point, float* d_normal, cudaStream_t stream);
+void launch_elements(const AcqDev& aq, const FrameDev& fr, float* d_pos, float* d_dir, cudaStream_t stream);
+
+// main.cpp:106-144: segments -> raw RF, scanline-major [n_poses*elements][rows]
+// d_columns: nullptr, or accumulate_columns_bytes() bytes of HBM when that is non-zero (scanlines too
+// long for per-thread shared-memory columns).
+#define MCRT_ACC_SMEM_LIMIT (200 * 1024)
+cudaError_t init_image_kernels();      // once per device, outside any stream capture
+size_t accumulate_columns_bytes(const AcqDev& aq, int n_poses);
+cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2* d_volume, const DevSegment* d_segments,
+                              const int32_t* d_nseg, int n_poses, float* d_rf, unsigned long long* d_steps, float* d_columns,
+                              cudaStream_t stream, int* launches);
+
+// rf_image::convolve + envelope (rfimage.h:93-123, 54-91) on [n_images][cols][rows]; flags bit0 convolve, bit1 envelope.
+// d_tmp0/d_tmp1: scratch of the same size as the image batch.  Result always lands in d_out.
+void launch_post(const float* d_in, int n_images, int cols, int rows, const float* d_axial, int n_axial, const float* d_lateral,
+                 int n_lateral, int flags, float* d_tmp0, float* d_tmp1, float* d_out, cudaStream_t stream, int* launches);
+// [n][cols][rows] -> [n][rows][cols]
+void launch_transpose(const float* d_in, int n_images, int cols, int rows, float* d_out, cudaStream_t stream, int* launches);
+// cv::remap (rfimage.h:139) with the precomputed maps; input scanline-major [n][cols][rows]
+void launch_scan_convert(const float* d_rf, int n_images, int cols, int rows, const float* d_map_x, const float* d_map_y, int scan_rows,
+                         int scan_cols, float* d_out, cudaStream_t stream, int* launches);
+void launch_numerics_probe(int op, int64_t n, const double* d_a, const double* d_b, double* d_out, cudaStream_t stream);
+
+}  // namespace mcrt
+#endif

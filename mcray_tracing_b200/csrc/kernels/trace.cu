@@ -1,0 +1,330 @@
+// trace.cu -- the Monte-Carlo path loop of scene::cast_rays<S,E> (scene.cpp:50-183) as a wavefront:
+// one launch per bounce; each launch does generate (bounce 0) / intersect (device BVH instead of
+// btCollisionWorld::rayTest) / shade (ray_physics::hit_boundary, ray.cpp:11-97) / compact (warp-
+// aggregated append of the surviving path ids into the next bounce's queue).  This fork of the
+// reference keeps exactly one of {reflection, refraction} per hit (ray.cpp:84-94), so the wavefront
+// never grows: compaction only.
+#include "mcrt_device.cuh"
+#include "mcrt_launch.h"
+
+namespace mcrt {
+
+namespace {
+
+struct SharedScene {
+    float4 mesh_origin[MCRT_MAX_SMEM_MESHES];
+    int4 mesh_info[MCRT_MAX_SMEM_MESHES];      // (mat_in, mat_out, vascular, -)
+    DevMaterial materials[MCRT_MAX_SMEM_MATERIALS];
+};
+
+__device__ __forceinline__ void load_shared_scene(const SceneDev& sc, SharedScene& sh)
+{
+    for (int i = threadIdx.x; i < sc.n_mesh && i < MCRT_MAX_SMEM_MESHES; i += blockDim.x) {
+        const DevMesh m = sc.meshes[i];
+        sh.mesh_origin[i] = make_float4(m.ox, m.oy, m.oz, 0.f);
+        sh.mesh_info[i] = make_int4(m.mat_in, m.mat_out, m.vascular, 0);
+    }
+    for (int i = threadIdx.x; i < sc.n_mat && i < MCRT_MAX_SMEM_MATERIALS; i += blockDim.x) sh.materials[i] = sc.materials[i];
+    __syncthreads();
+}
+
+// transducer<N>::transducer (transducer.h:45-59): element direction and position for one pose.
+__device__ __forceinline__ void element_pose(const AcqDev& aq, const PoseTrigDev& pt, float2 sc_t, float3& pos, float3& dir)
+{
+    float3 d = make_float3(sc_t.x, sc_t.y, 0.0f);                       // (sin a, cos a, 0)
+    d = v_rotate(d, make_float3(0.f, 0.f, 1.f), pt.cz, pt.sz);
+    d = v_rotate(d, make_float3(1.f, 0.f, 0.f), pt.cx, pt.sx);
+    d = v_rotate(d, make_float3(0.f, 1.f, 0.f), pt.cy, pt.sy);
+    dir = d;
+    pos = v_add(make_float3(pt.px, pt.py, pt.pz), v_scl(d, aq.radius_f));
+}
+
+__device__ __forceinline__ unsigned pack_state(int media, int outside, int depth)
+{
+    return (unsigned)(media & 0xff) | ((unsigned)((outside + 2) & 0xff) << 8) | ((unsigned)(depth & 0xff) << 16);
+}
+
+// One bounce of one path.  Returns true if the path survives into the next bounce.
+template <bool FIRST>
+__device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, const TraceBuffers& tb,
+                                            const SharedScene& sh, int p, int bounce)
+{
+    const int ES = aq.elements * aq.samples;
+    const int pose = p / ES;
+    const int rem = p - pose * ES;
+    const int element = rem / aq.samples;
+    const int sample = rem - element * aq.samples;
+    const uint64_t seed = __ldg(&fr.seed_frame[0]);
+    const uint32_t frame = (uint32_t)(__ldg(&fr.seed_frame[1]) + (uint64_t)pose);
+
+    float3 from, dir;
+    float intensity;
+    double distance_traveled;
+    int media, outside;
+    if (FIRST) {                                                          // scene.cpp:84-100
+        element_pose(aq, fr.poses[pose], __ldg(&fr.elem_sincos[element]), from, dir);
+        intensity = 1.0f / (float)(unsigned)aq.samples;
+        distance_traveled = 0.0;
+        media = sc.starting_material;
+        outside = MCRT_OUTSIDE_NULL;
+    } else {
+        const float4 oi = tb.paths.origin_intensity[p];
+        const float4 ds = tb.paths.dir_state[p];
+        from = make_float3(oi.x, oi.y, oi.z); intensity = oi.w;
+        dir = make_float3(ds.x, ds.y, ds.z);
+        const unsigned st = __float_as_uint(ds.w);
+        media = (int)(st & 0xff); outside = (int)((st >> 8) & 0xff) - 2;
+        distance_traveled = tb.paths.distance[p];
+    }
+    const float frequency = aq.frequency;
+    const DevMaterial med = sh.materials[media];
+
+    // scene.cpp:112-117
+    const float r_length = rp_max_ray_length(med.attenuation, intensity, frequency);
+    const float3 to = v_add(from, v_scl(make_float3(sc.spacing[0] * dir.x, sc.spacing[1] * dir.y, sc.spacing[2] * dir.z), r_length / 100.0f));
+    const float3 from_test = v_add(from, v_scl(dir, 0.1f));
+    HitRec h;
+    closest_hit(sc, sh.mesh_origin, from_test, to, h);
+
+    DevSegment seg;
+    bool alive = false;
+    const size_t seg_idx = (size_t)p * aq.max_depth + bounce;
+    if (h.tri_id >= 0) {
+        const double distance_before_hit = distance_traveled;
+        const float intensity_before_hit = intensity;
+        const int4 organ = sh.mesh_info[h.mesh];
+        const float3 hit_point = v_interpolate3(from_test, to, h.fraction);      // m_hitPointWorld
+        const float3 normal = hit_normal(h);
+        const mc_u32x4 b0 = mc_rng_block(seed, frame, (uint32_t)element, (uint32_t)sample, (uint32_t)bounce, 0);
+        // scene.cpp:132-139: penetration q = |N(0, thickness_inside)| (Box-Muller on block 0 words 0,1)
+        float q = 0.0f;
+        const float thickness = sh.materials[organ.x].thickness;
+        if (!aq.deterministic && thickness != 0.0f) {
+            const double u1 = mc_u01d(b0.v[0]), u2 = mc_u01d(b0.v[1]);
+            double sn, cs;
+            mc_sincos(2 * MC_PI_D * u2, &sn, &cs);
+            const double z = sqrt(-2.0 * mc_log(u1)) * cs;
+            q = (float)fabs(z * (double)thickness);
+        }
+        const float3 inside_point = v_add(v_scl(dir, q), hit_point);
+        // ray_physics::travel (ray.cpp:99-103)
+        const double mm = rp_distance_in_mm(sc.spacing, from, inside_point);
+        distance_traveled = distance_traveled + mm;
+        intensity = intensity * mc_expf(-med.attenuation * ((float)mm * 0.01f) * frequency);
+        // medium state machine, ray.cpp:14-47 as it behaves
+        int mac, mav;
+        if (outside != MCRT_OUTSIDE_NULL) {
+            if (organ.z) { mav = MCRT_OUTSIDE_NULL; mac = (outside == MCRT_OUTSIDE_SELF) ? media : outside; }
+            else { mav = (outside == organ.x) ? organ.y : organ.x; mac = media; }
+        } else {
+            if (organ.z) { mav = MCRT_OUTSIDE_SELF; mac = organ.x; }
+            else { mav = MCRT_OUTSIDE_NULL; mac = organ.x; }
+        }
+        const DevMaterial after = sh.materials[mac];
+        // ray.cpp:49-50: power-cosine jitter of the normal
+        float random_angle = 1.0f;
+        float3 random_normal = normal;
+        if (!aq.deterministic) {
+            random_angle = rp_power_cosine_variate((int)after.shininess, mc_u01d(b0.v[2]));
+            bool ok = false;
+            for (uint32_t attempt = 0; attempt < MC_RNG_BLOCKS_PER_BOUNCE - 1 && !ok; attempt++) {
+                const mc_u32x4 b = mc_rng_block(seed, frame, (uint32_t)element, (uint32_t)sample, (uint32_t)bounce, 1 + attempt);
+                ok = rp_random_unit_vector_attempt(normal, random_angle, mc_u01d(b.v[0]), mc_u01d(b.v[1]), random_normal);
+            }
+            if (!ok) random_normal = normal;
+        }
+        // ray.cpp:53-82
+        float incidence_angle = v_dot(dir, v_neg(random_normal));
+        if (incidence_angle < 0) incidence_angle = v_dot(dir, random_normal);
+        const float refr_ratio = med.impedance / after.impedance;
+        float refraction_angle = 1 - refr_ratio * refr_ratio * (1 - incidence_angle * incidence_angle);
+        const bool total_internal_reflection = refraction_angle < 0;
+        refraction_angle = sqrtf(refraction_angle);
+        float3 refraction_direction = rp_snells_law(dir, random_normal, incidence_angle, refraction_angle, refr_ratio);
+        refraction_direction = v_normalized(refraction_direction);
+        float3 reflection_direction = v_add(dir, v_scl(random_normal, 2 * incidence_angle));
+        reflection_direction = v_normalized(reflection_direction);
+        const float intensity_refl = total_internal_reflection
+                                         ? intensity
+                                         : rp_reflection_intensity(intensity, med.impedance, incidence_angle, after.impedance, refraction_angle);
+        const float intensity_refr = intensity - intensity_refl;
+        const float back = rp_reflected_intensity_eq8(dir, refraction_direction, reflection_direction, after.specularity) * random_angle;
+        // ray.cpp:84-94: keep exactly one branch
+        const float x = mc_u01f(b0.v[3]);
+        const float reflection_probability = intensity_refl / intensity;
+        float3 ndir;
+        float nint;
+        int nmedia, noutside;
+        if (reflection_probability > x) {
+            ndir = reflection_direction; nmedia = media; noutside = outside;
+            nint = intensity_refl > MCRT_INTENSITY_EPSILON ? intensity_refl : 0.0f;
+        } else {
+            ndir = refraction_direction; nmedia = mac; noutside = mav;
+            nint = intensity_refr > MCRT_INTENSITY_EPSILON ? intensity_refr : 0.0f;
+        }
+        // scene.cpp:148
+        seg.s0 = make_float4(from.x, from.y, from.z, back);
+        seg.s1 = make_float4(dir.x, dir.y, dir.z, intensity_before_hit);
+        seg.s2 = make_float4(inside_point.x, inside_point.y, inside_point.z, med.attenuation);
+        seg.s3 = make_int4(__double2loint(distance_before_hit), __double2hiint(distance_before_hit), media, h.tri_id);
+        // scene.cpp:151-157
+        alive = nint > MCRT_INTENSITY_EPSILON;
+        if (alive && bounce + 1 < aq.max_depth) {
+            tb.paths.origin_intensity[p] = make_float4(hit_point.x, hit_point.y, hit_point.z, nint);
+            tb.paths.dir_state[p] = make_float4(ndir.x, ndir.y, ndir.z, __uint_as_float(pack_state(nmedia, noutside, bounce + 1)));
+            tb.paths.distance[p] = distance_traveled;
+        }
+    } else {
+        // scene.cpp:163-164
+        seg.s0 = make_float4(from.x, from.y, from.z, 0.0f);
+        seg.s1 = make_float4(dir.x, dir.y, dir.z, intensity);
+        seg.s2 = make_float4(to.x, to.y, to.z, med.attenuation);
+        seg.s3 = make_int4(__double2loint(distance_traveled), __double2hiint(distance_traveled), media, -1);
+    }
+    tb.segments[seg_idx] = seg;
+    tb.n_segments[p] = bounce + 1;
+    if (tb.hit_fraction) tb.hit_fraction[seg_idx] = h.fraction;
+    if (tb.hit_mesh) tb.hit_mesh[seg_idx] = h.mesh;
+    return alive;
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(128) k_bounce(const SceneDev sc, const AcqDev aq, const FrameDev fr, const TraceBuffers tb, const int bounce)
+{
+    __shared__ SharedScene sh;
+    load_shared_scene(sc, sh);
+    const int* __restrict__ qin = (bounce & 1) ? tb.queue_b : tb.queue_a;
+    int* __restrict__ qout = (bounce & 1) ? tb.queue_a : tb.queue_b;
+    const int n_in = FIRST ? fr.n_poses * aq.elements * aq.samples : tb.counters[bounce];
+    const int n_round = (n_in + 31) & ~31;
+    const unsigned lane = threadIdx.x & 31;
+    const bool last = bounce + 1 >= aq.max_depth;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += gridDim.x * blockDim.x) {
+        int p = -1;
+        bool alive = false;
+        if (idx < n_in) {
+            p = FIRST ? idx : qin[idx];
+            alive = bounce_path<FIRST>(sc, aq, fr, tb, sh, p, bounce);
+        }
+        if (!last) {
+            // compact: warp-aggregated queue append (one atomic per warp)
+            const unsigned m = __ballot_sync(0xffffffffu, alive);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                int base = 0;
+                if ((int)lane == leader) base = atomicAdd(&tb.counters[bounce + 1], __popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (alive) qout[base + __popc(m & ((1u << lane) - 1u))] = p;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_closest_hit(const SceneDev sc, const int64_t n, const float* __restrict__ from3,
+                                                    const float* __restrict__ to3, int32_t* __restrict__ tri, int32_t* __restrict__ mesh,
+                                                    float* __restrict__ frac, float* __restrict__ point3, float* __restrict__ normal3)
+{
+    __shared__ SharedScene sh;
+    load_shared_scene(sc, sh);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float3 f = make_float3(from3[3 * i], from3[3 * i + 1], from3[3 * i + 2]);
+        const float3 t = make_float3(to3[3 * i], to3[3 * i + 1], to3[3 * i + 2]);
+        HitRec h;
+        closest_hit(sc, sh.mesh_origin, f, t, h);
+        tri[i] = h.tri_id;
+        mesh[i] = h.mesh;
+        frac[i] = h.fraction;
+        const float3 pt = v_interpolate3(f, t, h.fraction);
+        float3 nr = make_float3(0.f, 0.f, 0.f);
+        if (h.tri_id >= 0) nr = hit_normal(h);
+        point3[3 * i] = pt.x; point3[3 * i + 1] = pt.y; point3[3 * i + 2] = pt.z;
+        normal3[3 * i] = nr.x; normal3[3 * i + 1] = nr.y; normal3[3 * i + 2] = nr.z;
+    }
+}
+
+__global__ void k_elements(const AcqDev aq, const FrameDev fr, float* __restrict__ pos3, float* __restrict__ dir3)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= fr.n_poses * aq.elements) return;
+    const int pose = i / aq.elements, e = i - pose * aq.elements;
+    float3 pos, dir;
+    element_pose(aq, fr.poses[pose], fr.elem_sincos[e], pos, dir);
+    pos3[3 * i] = pos.x; pos3[3 * i + 1] = pos.y; pos3[3 * i + 2] = pos.z;
+    dir3[3 * i] = dir.x; dir3[3 * i + 1] = dir.y; dir3[3 * i + 2] = dir.z;
+}
+
+__global__ void k_numerics_probe(const int op, const int64_t n, const double* __restrict__ a, const double* __restrict__ b,
+                                 double* __restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r = 0.0;
+    switch (op) {
+        case 0: r = (double)mc_expf((float)a[i]); break;
+        case 1: r = (double)mc_logf((float)a[i]); break;
+        case 2: r = (double)mc_powf((float)a[i], (float)b[i]); break;
+        case 3: { double s, c; mc_sincos(a[i], &s, &c); r = s; break; }
+        case 4: { double s, c; mc_sincos(a[i], &s, &c); r = c; break; }
+        case 5: {
+            const mc_u32x4 w = mc_rng_block(0x0123456789abcdefULL, (uint32_t)a[i], (uint32_t)b[i], 3u, 2u, 1u);
+            r = (double)w.v[0] + 4294967296.0 * (double)(w.v[3] & 0xfffffu);
+            break;
+        }
+        case 6: r = mc_pow(a[i], b[i]); break;
+        case 7: r = mc_exp(a[i]); break;
+        case 8: r = mc_log(a[i]); break;
+        default: break;
+    }
+    out[i] = r;
+}
+
+}  // namespace
+
+static int grid_for(int64_t n_threads, int block, int sm_count, int ctas_per_sm)
+{
+    int64_t g = (n_threads + block - 1) / block;
+    const int64_t cap = (int64_t)sm_count * ctas_per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+void launch_trace(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, const TraceBuffers& tb, int sm_count, cudaStream_t stream,
+                  int* launches)
+{
+    const int64_t n_paths = (int64_t)fr.n_poses * aq.elements * aq.samples;
+    // counters[0] is informational; counters[1..] are the compaction cursors
+    cudaMemsetAsync(tb.counters, 0, sizeof(int) * (size_t)(aq.max_depth + 1), stream);
+    const int block = 128;
+    // persistent-style grid: a multiple of the SM count, grid-stride loop inside
+    const int grid = grid_for(n_paths, block, sm_count, 8);
+    for (int b = 0; b < aq.max_depth; b++) {
+        if (b == 0) k_bounce<true><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
+        else k_bounce<false><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
+        if (launches) (*launches)++;
+    }
+}
+
+void launch_closest_hit(const SceneDev& sc, int64_t n, const float* d_from, const float* d_to, int32_t* d_tri, int32_t* d_mesh,
+                        float* d_frac, float* d_point, float* d_normal, cudaStream_t stream)
+{
+    if (n <= 0) return;
+    const int block = 128;
+    int64_t g = (n + block - 1) / block;
+    if (g > 148 * 8) g = 148 * 8;
+    k_closest_hit<<<(int)g, block, 0, stream>>>(sc, n, d_from, d_to, d_tri, d_mesh, d_frac, d_point, d_normal);
+}
+
+void launch_elements(const AcqDev& aq, const FrameDev& fr, float* d_pos, float* d_dir, cudaStream_t stream)
+{
+    const int n = fr.n_poses * aq.elements;
+    k_elements<<<(n + 127) / 128, 128, 0, stream>>>(aq, fr, d_pos, d_dir);
+}
+
+void launch_numerics_probe(int op, int64_t n, const double* d_a, const double* d_b, double* d_out, cudaStream_t stream)
+{
+    if (n <= 0) return;
+    k_numerics_probe<<<(int)((n + 255) / 256), 256, 0, stream>>>(op, n, d_a, d_b, d_out);
+}
+
+}  // namespace mcrt

@@ -938,6 +938,31 @@ void orc_scan_convert(const float* rf, int32_t rows, int32_t cols, const float* 
         }
 }
 
+// host evaluation of the shared numerics contract (same op codes as mcrt_numerics_probe)
+void orc_numerics(int32_t op, int64_t n, const double* a, const double* b, double* out)
+{
+    for (int64_t i = 0; i < n; i++) {
+        double r = 0.0;
+        switch (op) {
+            case 0: r = (double)mc_expf((float)a[i]); break;
+            case 1: r = (double)mc_logf((float)a[i]); break;
+            case 2: r = (double)mc_powf((float)a[i], (float)b[i]); break;
+            case 3: { double sn, cs; mc_sincos(a[i], &sn, &cs); r = sn; break; }
+            case 4: { double sn, cs; mc_sincos(a[i], &sn, &cs); r = cs; break; }
+            case 5: {
+                const mc_u32x4 w = mc_rng_block(0x0123456789abcdefULL, (uint32_t)a[i], (uint32_t)b[i], 3u, 2u, 1u);
+                r = (double)w.v[0] + 4294967296.0 * (double)(w.v[3] & 0xfffffu);
+                break;
+            }
+            case 6: r = mc_pow(a[i], b[i]); break;
+            case 7: r = mc_exp(a[i]); break;
+            case 8: r = mc_log(a[i]); break;
+            default: break;
+        }
+        out[i] = r;
+    }
+}
+
 int64_t orc_simulate_frame(const orc_scene* s, const orc_params* p, const float* pos3, const float* angles_deg3, uint64_t seed,
                            uint32_t frame, float* rf, float* scan_out, double* stage_seconds4, int64_t* steps_out)
 {

@@ -154,6 +154,9 @@ int64_t orc_simulate_frame(const orc_scene* s, const orc_params* p, const float*
                            uint64_t seed, uint32_t frame, float* rf, float* scan_out, double* stage_seconds4,
                            int64_t* steps_out);
 
+/* the shared numerics contract evaluated on the host; op codes as mcrt_numerics_probe (include/mcrt.h) */
+void orc_numerics(int32_t op, int64_t n, const double* a, const double* b, double* out);
+
 /* number of OpenMP threads used over elements (1 = the reference's single thread, scene.cpp:74) */
 void orc_set_threads(int32_t n);
 int32_t orc_get_max_threads(void);

@@ -107,6 +107,7 @@ def oracle():
         L.orc_transducer_elements.argtypes = [C.c_void_p] * 5
         L.orc_psf_taps.argtypes = [C.c_void_p] * 3
         L.orc_get_max_threads.restype = C.c_int32
+        L.orc_numerics.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         _ORACLE = L
     return _ORACLE
 
@@ -333,3 +334,11 @@ def volume_raw() -> np.ndarray:
     L = oracle()
     ptr = L.orc_volume_raw(C.c_void_p(L.orc_volume_get()))
     return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(256, 256, 256, 2))
+
+
+def numerics(op: int, a, b=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, np.float64)
+    b = np.ascontiguousarray(b if b is not None else np.zeros_like(a), np.float64)
+    out = np.empty_like(a)
+    oracle().orc_numerics(int(op), a.size, _p(a), _p(b), _p(out))
+    return out

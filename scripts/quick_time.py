@@ -1,0 +1,26 @@
+"""Quick timing probe (development aid): ircad11 256x16, latency mode and batched."""
+import sys, time
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import numpy as np
+from mcray_tracing_b200 import api, assets
+
+d = assets.ensure_all()
+scene = d["ircad11"] / "santi-liver.scene"
+t0 = time.time()
+sim = api.Simulator(scene, api.default_params(elements=256, samples=16))
+print("create s", time.time() - t0, "tris", sim.info.n_triangles, "nodes", sim.info.n_bvh_nodes)
+pose = sim.start_pose[None, :]
+for nb in (1, 8, 64, 256):
+    poses = np.repeat(pose, nb, axis=0)
+    for it in range(3):
+        rf = sim.simulate(poses, seed=1, first_frame=it * nb)
+    st = sim.stats()
+    print(f"batch {nb}: ms_total {st.ms_total:.3f}  per-frame {st.ms_total/nb*1000:.1f} us  fps {nb/st.ms_total*1000:.0f}  segs {st.segments} steps {st.march_steps} launches {st.kernel_launches}")
+sim.set_option("profile_stages", 1)
+for nb in (1, 64):
+    poses = np.repeat(pose, nb, axis=0)
+    for it in range(2):
+        sim.simulate(poses, seed=1, first_frame=0)
+    st = sim.stats()
+    print(f"stages batch {nb}: trace {st.ms_trace:.3f} acc {st.ms_accumulate:.3f} post {st.ms_post:.3f} total {st.ms_total:.3f}")

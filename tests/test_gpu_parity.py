@@ -1,0 +1,296 @@
+"""GPU parity tests: every stage of the CUDA path, called through the C ABI (libmcrt.so), against
+the CPU oracle on the same seeded inputs.  Bars: bit-exact for hit ids / bounce counts / every
+segment field / PSF / envelope / scan conversion; RF after accumulation within
+|gpu - oracle| <= 1e-4 * max(|oracle|, 1e-3 * max|oracle image|)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _tol(ref):
+    return 1e-4 * np.maximum(np.abs(ref), 1e-3 * np.abs(ref).max())
+
+
+def _assert_segments_equal(gs, gn, os_, on):
+    assert np.array_equal(gn, on), "bounce counts differ"
+    D = gs.shape[-1]
+    valid = np.arange(D)[None, None, :] < on[:, :, None]
+    for name in gs.dtype.names:
+        a, b = gs[name][valid], os_[name][valid]
+        same = (a == b) | (np.isnan(a) & np.isnan(b)) if a.dtype.kind == "f" else (a == b)
+        assert np.all(same), f"segment field {name!r} differs in {np.count_nonzero(~same)} of {same.size} entries"
+
+
+@pytest.fixture(scope="module")
+def O(built):
+    from oracle import oracle_py
+    return oracle_py
+
+
+@pytest.fixture(scope="module")
+def api(built):
+    from mcray_tracing_b200 import api as a
+    return a
+
+
+@pytest.fixture(scope="module")
+def sphere(api, O, assets_dirs):
+    path = assets_dirs["sphere"] / "sphere.scene"
+    A = O.load_scene_py(path)
+    return path, A, O.OracleScene(A)
+
+
+@pytest.fixture(scope="module")
+def ircad(api, O, assets_dirs):
+    path = assets_dirs["ircad11"] / "santi-liver.scene"
+    A = O.load_scene_py(path)
+    return path, A, O.OracleScene(A)
+
+
+@pytest.fixture(scope="module")
+def ircad_rough(api, O, assets_dirs):
+    path = assets_dirs["ircad11"] / "santi-liver-rough.scene"
+    A = O.load_scene_py(path)
+    return path, A, O.OracleScene(A)
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_numerics_contract_device_equals_host(api, O):
+    """The shared transcendentals / Philox must be bit-identical on the device and on the host."""
+    rng = np.random.default_rng(1)
+    n = 200000
+    cases = [
+        (0, rng.uniform(-40, 10, n), None),
+        (1, np.exp(rng.uniform(-25, 5, n)), None),
+        (2, rng.uniform(-1, 1, n), rng.choice([0.001, 0.2, 0.5, 1.0, 2.0, 3.0], n)),
+        (3, rng.uniform(0, 2 * np.pi, n), None),
+        (4, rng.uniform(0, 2 * np.pi, n), None),
+        (5, rng.integers(0, 2**31, n).astype(np.float64), rng.integers(0, 2**20, n).astype(np.float64)),
+        (6, rng.uniform(1e-12, 1, n), rng.uniform(1e-9, 1, n)),
+        (7, rng.uniform(-700, 700, n), None),
+        (8, np.exp(rng.uniform(-700, 700, n)), None),
+    ]
+    for op, a, b in cases:
+        dev = api.numerics_probe(op, a, b)
+        host = O.numerics(op, a, b)
+        same = (dev == host) | (np.isnan(dev) & np.isnan(host))
+        assert np.all(same), f"op {op}: {np.count_nonzero(~same)} mismatches"
+
+
+def test_scene_loader_matches_python_loader(api, O, ircad, sphere):
+    for path, A, osc in (sphere, ircad):
+        with api.Simulator(path, api.default_params(elements=64, samples=1)) as sim:
+            tri, tm, org, mats = sim.scene_arrays()
+        L = O.oracle()
+        ref_tri = np.empty((osc.n_tri, 9), np.float32)
+        ref_org = np.empty((len(A["mesh_deltas"]), 3), np.float32)
+        L.orc_scene_get_local_vertices(osc.h, ref_tri.ctypes.data)
+        L.orc_scene_get_mesh_origins(osc.h, ref_org.ctypes.data)
+        assert np.array_equal(tri, ref_tri)
+        assert np.array_equal(org, ref_org)
+        assert np.array_equal(mats, A["materials"])
+        assert np.array_equal(tm, np.repeat(np.arange(len(A["mesh_deltas"])), np.diff(A["tri_offsets"])).astype(np.int32))
+
+
+def test_volume_upload_is_the_reference_volume(api, O, sphere):
+    with api.Simulator(sphere[0], api.default_params(elements=64, samples=1)) as sim:
+        v = sim.volume()
+    assert np.array_equal(v, O.volume_raw())
+
+
+@pytest.mark.parametrize("pose", [(-13.5, 0, 0, 0, 0, -90), (-17.5, 1, 5, 120, 0, -90), (-16, 3, 14, 45, 45, -90), (1.25, -4.5, 7.75, 33.3, -71.2, 190.0)])
+def test_transducer_elements_bit_exact(api, O, sphere, pose):
+    for E in (512, 256):
+        with api.Simulator(sphere[0], api.default_params(elements=E, samples=1)) as sim:
+            pos, d = sim.transducer_elements(pose)
+        op, od = O.transducer_elements(O.default_params(elements=E, samples=1), pose[:3], pose[3:])
+        assert np.array_equal(pos, op) and np.array_equal(d, od)
+
+
+def _random_rays(rng, n, center, radius, length):
+    o = center + rng.normal(size=(n, 3)) * radius
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return o.astype(np.float32), (o + d * length).astype(np.float32)
+
+
+def test_closest_hit_vs_brute_force_sphere(api, O, sphere):
+    """Device LBVH traversal vs the oracle's brute force over all 20 492 triangles."""
+    path, A, osc = sphere
+    rng = np.random.default_rng(3)
+    f, t = _random_rays(rng, 3000, np.zeros(3), 6.0, 40.0)
+    # plus astronomically long rays (GEL: `to` ~ 1e9 world units)
+    f2, t2 = _random_rays(rng, 500, np.array([-13.5, 0, 0]), 0.5, 1.0e9)
+    f, t = np.concatenate([f, f2]), np.concatenate([t, t2])
+    with api.Simulator(path, api.default_params(elements=64, samples=1)) as sim:
+        tri, mesh, frac, pt, nr = sim.closest_hit(f, t)
+    for i in range(len(f)):
+        otri, omesh, o7 = osc.closest_hit(f[i], t[i], use_bvh=False)
+        assert tri[i] == otri and mesh[i] == omesh, f"ray {i}: gpu tri {tri[i]} oracle {otri}"
+        assert frac[i] == o7[0]
+        assert np.array_equal(pt[i], o7[1:4])
+        if otri >= 0:
+            assert np.array_equal(nr[i], o7[4:7])
+    assert np.count_nonzero(tri >= 0) > 1000
+
+
+def test_closest_hit_vs_oracle_bvh_ircad(api, O, ircad):
+    path, A, osc = ircad
+    rng = np.random.default_rng(4)
+    f, t = _random_rays(rng, 20000, np.array([-2.0, -1.0, 7.0]), 8.0, 60.0)
+    with api.Simulator(path, api.default_params(elements=64, samples=1)) as sim:
+        tri, mesh, frac, pt, nr = sim.closest_hit(f, t)
+    # the oracle BVH is itself validated against its brute force on a subset
+    for i in range(0, 200):
+        a = osc.closest_hit(f[i], t[i], use_bvh=False)
+        b = osc.closest_hit(f[i], t[i], use_bvh=True)
+        assert a[0] == b[0] and np.array_equal(a[2], b[2])
+    bad = 0
+    for i in range(len(f)):
+        otri, omesh, o7 = osc.closest_hit(f[i], t[i], use_bvh=True)
+        if not (tri[i] == otri and frac[i] == o7[0] and np.array_equal(pt[i], o7[1:4])):
+            bad += 1
+    assert bad == 0
+    assert np.count_nonzero(tri >= 0) > 10000
+
+
+def test_cast_rays_deterministic_sphere_c1(api, O, sphere):
+    """BASELINE config 1: sphere scene, default transducer, deterministic mode: hit triangle ids,
+    bounce counts and every segment field bit-exact (oracle closest hit = brute force)."""
+    path, A, osc = sphere
+    gp = api.default_params(samples=1, deterministic=1)
+    op = O.default_params(samples=1, deterministic=1)
+    with api.Simulator(path, gp) as sim:
+        pose = sim.start_pose
+        gs, gn = sim.cast_rays(pose, seed=11, frame=0)
+    os_, on, tests = osc.cast_rays(op, pose[:3], pose[3:], seed=11, frame=0, use_bvh=False)
+    _assert_segments_equal(gs, gn, os_, on)
+    assert gn.sum() == tests and gn.max() >= 4
+
+
+@pytest.mark.parametrize("scene_name,det", [("ircad", 1), ("ircad", 0), ("ircad_rough", 0)])
+def test_cast_rays_ircad_path_for_path(api, O, request, scene_name, det):
+    """ircad11 256 x 16: with the shared Philox keying the GPU wavefront is path-for-path identical to
+    the oracle in deterministic AND stochastic mode (the stronger check of SURVEY.md section 8d)."""
+    path, A, osc = request.getfixturevalue(scene_name)
+    S = 1 if det else 16
+    gp = api.default_params(elements=256, samples=S, deterministic=det)
+    op = O.default_params(elements=256, samples=S, deterministic=det)
+    with api.Simulator(path, gp) as sim:
+        pose = sim.start_pose
+        for frame in (0, 5):
+            gs, gn = sim.cast_rays(pose, seed=1234, frame=frame)
+            os_, on, _ = osc.cast_rays(op, pose[:3], pose[3:], seed=1234, frame=frame, use_bvh=True)
+            _assert_segments_equal(gs, gn, os_, on)
+    assert on.max() >= 5
+
+
+def test_accumulate_matches_oracle(api, O, ircad_rough):
+    path, A, osc = ircad_rough
+    op = O.default_params(elements=256, samples=16)
+    pose = np.concatenate([A["transducer_position"], A["transducer_angles"]])
+    os_, on, _ = osc.cast_rays(op, pose[:3], pose[3:], seed=5, frame=1)
+    ref, steps = osc.accumulate(op, os_, on)
+    with api.Simulator(path, api.default_params(elements=256, samples=16)) as sim:
+        rf = sim.accumulate(os_, on)
+        assert sim.stats().march_steps == steps
+    ref = ref.T
+    assert np.all(np.abs(rf - ref) <= _tol(ref)), f"max abs err {np.abs(rf - ref).max()}"
+    assert np.count_nonzero(ref) > 10000
+
+
+@pytest.mark.parametrize("cols,rows,ka,kl", [(512, 465, 7, 13), (256, 465, 7, 13), (40, 64, 7, 13), (64, 300, 31, 15), (33, 31, 3, 5)])
+def test_convolve_and_envelope_bit_exact(api, O, sphere, cols, rows, ka, kl):
+    rng = np.random.default_rng(cols * 1000 + rows)
+    img = rng.normal(size=(rows, cols)).astype(np.float32)          # oracle layout [rows][cols]
+    img[rng.random(img.shape) < 0.3] = 0.0                          # plateaus / exact ties
+    ax = rng.normal(size=ka).astype(np.float32)
+    lat = rng.random(kl).astype(np.float32)
+    with api.Simulator(sphere[0], api.default_params(elements=64, samples=1)) as sim:
+        g_conv = sim.postprocess(img.T, ax, lat, convolve=True, envelope=False)
+        g_env = sim.postprocess(img.T, ax, lat, convolve=False, envelope=True)
+        g_both = sim.postprocess(img.T, ax, lat, convolve=True, envelope=True)
+    o_conv = O.convolve(img, ax, lat)
+    assert np.array_equal(g_conv.T, o_conv)
+    assert np.array_equal(g_env.T, O.envelope(img))
+    assert np.array_equal(g_both.T, O.envelope(o_conv))
+
+
+def test_scan_convert_bit_exact(api, O, sphere):
+    rng = np.random.default_rng(9)
+    with api.Simulator(sphere[0], api.default_params(elements=512, samples=1)) as sim:
+        img = rng.random((sim.rows, sim.cols)).astype(np.float32)
+        g = sim.scan_convert(img.T)
+    mx, my = O.create_mapping(O.default_params(samples=1))
+    assert np.array_equal(g, O.scan_convert(img, mx, my))
+
+
+@pytest.mark.parametrize("scene_name,E,S,det", [("sphere", 512, 1, 1), ("sphere", 512, 5, 0), ("ircad", 256, 16, 0), ("ircad_rough", 256, 16, 0)])
+def test_full_frame_rf_within_tolerance(api, O, request, scene_name, E, S, det):
+    path, A, osc = request.getfixturevalue(scene_name)
+    gp = api.default_params(elements=E, samples=S, deterministic=det)
+    op = O.default_params(elements=E, samples=S, deterministic=det)
+    with api.Simulator(path, gp) as sim:
+        pose = sim.start_pose
+        rf, scan = sim.simulate(pose[None, :], seed=77, first_frame=3, scan=True)
+        st = sim.stats()
+    o = osc.simulate_frame(op, pose[:3], pose[3:], seed=77, frame=3, scan=True)
+    ref = o["rf"].T
+    assert st.segments == o["tests"] and st.march_steps == o["steps"]
+    assert np.all(np.abs(rf[0] - ref) <= _tol(ref)), f"max abs err {np.abs(rf[0] - ref).max()} (max |ref| {np.abs(ref).max()})"
+    sref = o["scan"]
+    assert np.all(np.abs(scan[0] - sref) <= 1e-4 * np.maximum(np.abs(sref), 1e-3 * np.abs(sref).max()) + 1e-7)
+
+
+def test_batched_poses_equal_single_pose_calls(api, ircad, O):
+    """Sharding invariance: frames are pure functions of (scene, pose, seed, frame index), so any
+    batching / split of a sweep is bit-identical (what makes N-GPU == 1-GPU)."""
+    from mcray_tracing_b200 import assets
+    path, A, osc = ircad
+    poses = assets.sweep_poses(12)
+    with api.Simulator(path, api.default_params(elements=128, samples=4)) as sim:
+        all_rf = sim.simulate(poses, seed=9, first_frame=100)
+        sim.set_option("max_batch_poses", 5)
+        chunked = sim.simulate(poses, seed=9, first_frame=100)
+        singles = np.stack([sim.simulate(poses[i:i + 1], seed=9, first_frame=100 + i)[0] for i in range(len(poses))])
+        tail = sim.simulate(poses[7:], seed=9, first_frame=107)
+        sim.set_option("use_graph", 0)
+        nograph = sim.simulate(poses, seed=9, first_frame=100)
+    assert np.array_equal(all_rf, chunked)
+    assert np.array_equal(all_rf, singles)
+    assert np.array_equal(all_rf[7:], tail)
+    assert np.array_equal(all_rf, nograph)
+    assert len({all_rf[i].tobytes() for i in range(len(poses))}) == len(poses)
+
+
+def test_rf_layout_cv_mat(api, sphere):
+    gp0 = api.default_params(elements=128, samples=2)
+    gp1 = api.default_params(elements=128, samples=2, rf_layout=1)
+    with api.Simulator(sphere[0], gp0) as s0, api.Simulator(sphere[0], gp1) as s1:
+        a = s0.simulate(s0.start_pose[None, :], seed=1)
+        b = s1.simulate(s1.start_pose[None, :], seed=1)
+    assert b.shape == (1, s1.rows, s1.cols)
+    assert np.array_equal(a[0].T, b[0])
+
+
+def test_ircad11_scene_without_shininess_loads(api, assets_dirs):
+    """examples/ircad11/ircad11.scene lacks shininess/thickness and fails in the reference
+    (scene.cpp:217-218); the drop-in defaults them (documented extension)."""
+    with api.Simulator(assets_dirs["ircad11"] / "ircad11.scene", api.default_params(elements=64, samples=2)) as sim:
+        rf = sim.simulate(sim.start_pose[None, :], seed=2)
+    assert np.isfinite(rf).all() and np.abs(rf).max() > 0
+
+
+def test_errors_are_codes_not_crashes(api, assets_dirs, tmp_path):
+    with pytest.raises(api.McrtError) as e:
+        api.Simulator(tmp_path / "missing.scene")
+    assert e.value.code == api.MCRT_ERR_SCENE and "Error while loading scene" in e.value.message
+    bad = tmp_path / "bad.scene"
+    bad.write_text('{"materials": 3}')
+    with pytest.raises(api.McrtError) as e:
+        api.Simulator(bad)
+    assert e.value.code == api.MCRT_ERR_SCENE
+    with pytest.raises(api.McrtError) as e:
+        api.Simulator(assets_dirs["sphere"] / "sphere.scene", api.default_params(psf_axial=8))
+    assert e.value.code == api.MCRT_ERR_INVALID
