@@ -178,6 +178,20 @@ int mcrt_get_scene(const mcrt_ctx* ctx, float* tri_local9, int32_t* tri_mesh, fl
 /* scatterer volume as uploaded: 256^3 x {texture_noise, scattering_probability} (volume.h:19-35) */
 int mcrt_get_volume(const mcrt_ctx* ctx, float* out);
 
+/* ---- host-only entry points (no GPU needed): the drop-in surface's loaders and start-up tables ---- */
+
+/* load_mesh_from_obj (objloader.h:154-161 = tinyobj::LoadObj + btgCreateGraphicsShapeFromWavefrontObj):
+ * un-welded triangle soup, 9 floats per triangle in OBJ space.  Writes min(n, capacity) triangles. */
+int mcrt_load_obj(const char* obj_path, float* out9, int64_t capacity_tris, int64_t* n_tris);
+/* scene::parse_config + mesh loading (scene.cpp:185-247, 300-334) without creating a device context:
+ * counts, and the same error codes / messages mcrt_create reports for a bad scene. */
+int mcrt_scene_probe(const char* scene_json_path, int64_t* n_triangles, int32_t* n_meshes, int32_t* n_materials, float* start_pose6);
+/* start-up tables for a parameter set: derived sizes (info: rows, cols, timing constants), the
+ * (sin a_t, cos a_t) element table (transducer.h:41-59), PSF taps (psf.h:34-58) and the scan-conversion
+ * maps (rfimage.h:183-215).  Any output pointer may be NULL. */
+int mcrt_host_tables(const mcrt_params* params, mcrt_info* info, float* elem_sincos2, float* axial, float* lateral, float* map_x,
+                     float* map_y);
+
 /* numerics contract self-test: evaluates the shared transcendentals ON THE DEVICE.
  * op 0 expf, 1 logf, 2 powf(a,b), 3 sin (double), 4 cos (double), 5 philox (a=counter as float bits) */
 int mcrt_numerics_probe(int device, int32_t op, int64_t n, const double* a, const double* b, double* out);

@@ -65,7 +65,7 @@ assert SEGMENT_DTYPE.itemsize == 72
 EXPORTS = ["mcrt_default_params", "mcrt_create", "mcrt_create_from_arrays", "mcrt_destroy", "mcrt_last_error", "mcrt_get_info",
            "mcrt_get_stats", "mcrt_set_option", "mcrt_simulate", "mcrt_simulate_async", "mcrt_trace_debug", "mcrt_closest_hit",
            "mcrt_transducer_elements", "mcrt_accumulate", "mcrt_postprocess", "mcrt_scan_convert", "mcrt_get_psf_taps",
-           "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe"]
+           "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe", "mcrt_load_obj", "mcrt_scene_probe", "mcrt_host_tables"]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
@@ -108,6 +108,9 @@ def lib():
         L.mcrt_get_scene.argtypes = [vp, vp, vp, vp, vp]
         L.mcrt_get_volume.argtypes = [vp, vp]
         L.mcrt_numerics_probe.argtypes = [C.c_int, C.c_int32, C.c_int64, vp, vp, vp]
+        L.mcrt_load_obj.argtypes = [C.c_char_p, vp, C.c_int64, vp]
+        L.mcrt_scene_probe.argtypes = [C.c_char_p, vp, vp, vp, vp]
+        L.mcrt_host_tables.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -294,3 +297,30 @@ def numerics_probe(op: int, a, b=None, device: int = 0) -> np.ndarray:
     out = np.empty_like(a)
     _check(lib().mcrt_numerics_probe(int(device), int(op), a.size, _p(a), _p(b), _p(out)))
     return out
+
+
+# ---- host-only entry points (no GPU) --------------------------------------------------------------
+def load_obj(path) -> np.ndarray:
+    """objloader.h:154-161: un-welded triangle soup float32 [n, 9]."""
+    n = C.c_int64(0)
+    _check(lib().mcrt_load_obj(str(path).encode(), None, 0, C.byref(n)))
+    out = np.empty((n.value, 9), np.float32)
+    _check(lib().mcrt_load_obj(str(path).encode(), _p(out), n.value, C.byref(n)))
+    return out
+
+
+def scene_probe(path) -> dict:
+    nt, nm, nmat = C.c_int64(0), C.c_int32(0), C.c_int32(0)
+    pose = np.zeros(6, np.float32)
+    _check(lib().mcrt_scene_probe(str(path).encode(), C.byref(nt), C.byref(nm), C.byref(nmat), _p(pose)))
+    return dict(n_triangles=nt.value, n_meshes=nm.value, n_materials=nmat.value, start_pose=pose)
+
+
+def host_tables(params: Params) -> dict:
+    info = Info()
+    _check(lib().mcrt_host_tables(C.byref(params), C.byref(info), None, None, None, None, None))
+    sc = np.empty((params.elements, 2), np.float32)
+    ax = np.empty(params.psf_axial, np.float32); lat = np.empty(params.psf_lateral, np.float32)
+    mx = np.empty((params.scan_rows, params.scan_cols), np.float32); my = np.empty_like(mx)
+    _check(lib().mcrt_host_tables(C.byref(params), C.byref(info), _p(sc), _p(ax), _p(lat), _p(mx), _p(my)))
+    return dict(info=info, elem_sincos=sc, axial=ax, lateral=lat, map_x=mx, map_y=my)

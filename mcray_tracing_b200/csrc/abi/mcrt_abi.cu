@@ -93,7 +93,8 @@ struct mcrt_ctx {
     AcqDev aq;
     SceneDev sc;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_up = nullptr;
+    bool upload_pending = false;
 
     DevMesh* d_meshes = nullptr;
     DevMaterial* d_materials = nullptr;
@@ -260,12 +261,15 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
         for (int b = 0; b < n_batches; b++) {
             const int p0 = b * batch_cap;
             const int n = (n_poses - p0) < batch_cap ? (n_poses - p0) : batch_cap;
-            if (b > 0) CUDA_TRY(cudaStreamSynchronize(s));      // pinned staging is reused
+            // the pinned pose staging is reused: wait for the previous upload (not the previous frame) to finish
+            if (c->upload_pending) { CUDA_TRY(cudaEventSynchronize(c->ev_up)); c->upload_pending = false; }
             for (int i = 0; i < n; i++) c->h_poses[i] = pose_trig(poses[p0 + i]);
             c->h_seed_frame[0] = seed;
             c->h_seed_frame[1] = first_frame + (uint64_t)p0;
             CUDA_TRY(cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig) * (size_t)n, cudaMemcpyHostToDevice, s));
             CUDA_TRY(cudaMemcpyAsync(c->d_seed_frame, c->h_seed_frame, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaEventRecord(c->ev_up, s));
+            c->upload_pending = true;
             run_batch(c, n, scan_out != nullptr, s, &launches);
             const float* rf_src = c->params.rf_layout == 1 ? c->d_rf_t : c->d_rf_final;
             CUDA_TRY(cudaMemcpyAsync(rf_out + (size_t)p0 * px_per_pose, rf_src, sizeof(float) * px_per_pose * n,
@@ -338,6 +342,7 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->ev0)); CUDA_TRY(cudaEventCreate(&c->ev1));
     CUDA_TRY(cudaEventCreate(&c->ev_a)); CUDA_TRY(cudaEventCreate(&c->ev_b)); CUDA_TRY(cudaEventCreate(&c->ev_c));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
 
     // acquisition constants
     AcqDev& aq = c->aq;
@@ -421,6 +426,7 @@ void destroy_impl(mcrt_ctx* c)
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     if (c->ev_c) cudaEventDestroy(c->ev_c);
+    if (c->ev_up) cudaEventDestroy(c->ev_up);
     if (c->stream) cudaStreamDestroy(c->stream);
     (void)cudaGetLastError();
     delete c;
@@ -755,6 +761,67 @@ int mcrt_get_volume(const mcrt_ctx* c, float* out)
     return guarded("mcrt_get_volume", [&]() {
         CUDA_TRY(cudaSetDevice(c->device));
         CUDA_TRY(cudaMemcpy(out, c->d_volume, sizeof(float) * 2 * (size_t)256 * 256 * 256, cudaMemcpyDeviceToHost));
+        return MCRT_OK;
+    });
+}
+
+int mcrt_load_obj(const char* obj_path, float* out9, int64_t capacity_tris, int64_t* n_tris)
+{
+    if (!obj_path || !n_tris) return fail(MCRT_ERR_INVALID, "mcrt_load_obj: null argument");
+    return guarded("mcrt_load_obj", [&]() {
+        std::vector<float> soup;
+        load_obj_soup(obj_path, soup);
+        const int64_t n = (int64_t)(soup.size() / 9);
+        *n_tris = n;
+        if (out9 && capacity_tris > 0) memcpy(out9, soup.data(), sizeof(float) * 9 * (size_t)(n < capacity_tris ? n : capacity_tris));
+        return MCRT_OK;
+    });
+}
+
+int mcrt_scene_probe(const char* scene_json_path, int64_t* n_triangles, int32_t* n_meshes, int32_t* n_materials, float* start_pose6)
+{
+    if (!scene_json_path) return fail(MCRT_ERR_INVALID, "mcrt_scene_probe: null argument");
+    return guarded("mcrt_scene_probe", [&]() {
+        const HostScene s = load_scene_file(scene_json_path);
+        if (n_triangles) *n_triangles = (int64_t)s.tri_mesh.size();
+        if (n_meshes) *n_meshes = (int32_t)s.meshes.size();
+        if (n_materials) *n_materials = (int32_t)s.materials.size();
+        if (start_pose6) memcpy(start_pose6, s.start_pose, sizeof(float) * 6);
+        return MCRT_OK;
+    });
+}
+
+int mcrt_host_tables(const mcrt_params* params, mcrt_info* info, float* elem_sincos2, float* axial, float* lateral, float* map_x,
+                     float* map_y)
+{
+    if (!params) return fail(MCRT_ERR_INVALID, "mcrt_host_tables: null argument");
+    return guarded("mcrt_host_tables", [&]() {
+        validate_params(*params);
+        const Derived d = derive(*params);
+        if (info) {
+            memset(info, 0, sizeof(*info));
+            info->rows = d.rows; info->cols = d.cols; info->scan_rows = params->scan_rows; info->scan_cols = params->scan_cols;
+            info->device = -1;
+            info->axial_resolution_mm = d.axial_resolution_mm; info->time_step_us = d.time_step_us; info->row_period_us = d.row_period_us;
+            info->max_travel_time_us = d.max_travel_time_us;
+        }
+        if (elem_sincos2) {
+            std::vector<float> t;
+            element_angle_table(*params, d, t);
+            memcpy(elem_sincos2, t.data(), sizeof(float) * t.size());
+        }
+        if (axial || lateral) {
+            std::vector<float> a, l;
+            psf_taps(*params, a, l);
+            if (axial) memcpy(axial, a.data(), sizeof(float) * a.size());
+            if (lateral) memcpy(lateral, l.data(), sizeof(float) * l.size());
+        }
+        if (map_x || map_y) {
+            std::vector<float> mx, my;
+            scan_mapping(*params, d, mx, my);
+            if (map_x) memcpy(map_x, mx.data(), sizeof(float) * mx.size());
+            if (map_y) memcpy(map_y, my.data(), sizeof(float) * my.size());
+        }
         return MCRT_OK;
     });
 }

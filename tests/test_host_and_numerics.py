@@ -1,0 +1,285 @@
+"""CPU-side tests (no GPU): the numerics contract vs glibc, the C-ABI library's exports and its
+loud failure without a device, the sweep sharding logic under gloo (world_size 2), and closed-form
+known-answer tests of the oracle."""
+import ctypes as C
+import ctypes.util
+import os
+import re
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def O(built):
+    from oracle import oracle_py
+    return oracle_py
+
+
+@pytest.fixture(scope="module")
+def api(built):
+    from mcray_tracing_b200 import api as a
+    return a
+
+
+# ---- numerics contract vs glibc ----------------------------------------------------------------------
+def _ulp32(a, b):
+    a = np.asarray(a, np.float32).view(np.int32).astype(np.int64)
+    b = np.asarray(b, np.float32).view(np.int32).astype(np.int64)
+    return np.abs(a - b)
+
+
+def test_contract_float_functions_match_glibc_within_one_ulp(O):
+    libm = C.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    for f in ("expf", "logf"):
+        getattr(libm, f).restype = C.c_float
+        getattr(libm, f).argtypes = [C.c_float]
+    libm.powf.restype = C.c_float
+    libm.powf.argtypes = [C.c_float, C.c_float]
+    rng = np.random.default_rng(5)
+    n = 60000
+    x = rng.uniform(-40, 10, n).astype(np.float32)
+    ref = np.array([libm.expf(float(v)) for v in x], np.float32)
+    d = _ulp32(O.numerics(0, x).astype(np.float32), ref)
+    assert d.max() <= 1 and np.mean(d == 0) > 0.995
+    y = np.exp(rng.uniform(-25, 5, n)).astype(np.float32)
+    ref = np.array([libm.logf(float(v)) for v in y], np.float32)
+    d = _ulp32(O.numerics(1, y).astype(np.float32), ref)
+    assert d.max() <= 1 and np.mean(d == 0) > 0.995
+    b = rng.uniform(0, 1, n).astype(np.float32)
+    e = rng.choice([0.001, 0.2, 0.5, 1.0, 2.0, 3.0], n).astype(np.float32)
+    ref = np.array([libm.powf(float(u), float(v)) for u, v in zip(b, e)], np.float32)
+    d = _ulp32(O.numerics(2, b, e).astype(np.float32), ref)
+    assert d.max() <= 1 and np.mean(d == 0) > 0.995
+
+
+def test_contract_double_functions_accuracy(O):
+    import math
+    rng = np.random.default_rng(6)
+    a = rng.uniform(0, 2 * np.pi, 20000)
+    assert np.abs(O.numerics(3, a) - np.sin(a)).max() < 4e-16
+    assert np.abs(O.numerics(4, a) - np.cos(a)).max() < 4e-16
+    x = rng.uniform(-700, 700, 20000)
+    ref = np.array([math.exp(v) for v in x])
+    assert np.abs(O.numerics(7, x) / ref - 1).max() < 5e-16
+    y = np.exp(rng.uniform(-700, 700, 20000))
+    ref = np.array([math.log(v) for v in y])
+    assert np.abs(O.numerics(8, y) - ref).max() <= 5e-16 * np.abs(ref).max()
+    # special cases of pow the hot path can reach (ray.cpp:131,158,160,223)
+    vals = O.numerics(6, np.array([-0.5, -0.5, -0.5, 0.0, 0.0, 2.0, 1.0, np.nan]), np.array([1.0, 2.0, 0.2, 1.0, 0.0, 0.0, np.nan, 1.0]))
+    assert vals[0] == -0.5 and vals[1] == 0.25 and np.isnan(vals[2]) and vals[3] == 0.0 and vals[4] == 1.0 and vals[5] == 1.0
+    assert vals[6] == 1.0 and np.isnan(vals[7])
+
+
+def test_philox_known_answer(O):
+    """Philox4x32-10 known-answer vectors of Random123 (kat_vectors): zero counter/key and the
+    'pi' vector; checked through an independent pure-Python restatement of the round function."""
+    def philox(c, k):
+        c, k = list(c), list(k)
+        for _ in range(10):
+            p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+            c = [((p1 >> 32) ^ c[1] ^ k[0]) & 0xffffffff, p1 & 0xffffffff, ((p0 >> 32) ^ c[3] ^ k[1]) & 0xffffffff, p0 & 0xffffffff]
+            k = [(k[0] + 0x9E3779B9) & 0xffffffff, (k[1] + 0xBB67AE85) & 0xffffffff]
+        return c
+    assert philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    # the contract's keyed block: counter = (frame, element, sample, bounce*8+block), key = seed halves
+    a = np.array([0.0, 1.0, 123456.0, 2**31 - 1.0])
+    b = np.array([0.0, 7.0, 99.0, 2**20 - 1.0])
+    got = O.numerics(5, a, b)
+    seed = 0x0123456789abcdef
+    for i in range(len(a)):
+        w = philox([int(a[i]), int(b[i]), 3, 2 * 8 + 1], [seed & 0xffffffff, seed >> 32])
+        assert got[i] == float(w[0]) + 4294967296.0 * float(w[3] & 0xfffff)
+
+
+# ---- the C-ABI library ---------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol(api):
+    header = (ROOT / "include" / "mcrt.h").read_text()
+    declared = set(re.findall(r"\b(mcrt_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(api.EXPORTS), declared ^ set(api.EXPORTS)
+    L = api.lib()
+    for name in sorted(declared):
+        assert getattr(L, name) is not None
+    out = subprocess.run(["nm", "-D", "--defined-only", str(api.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (mcrt_[a-z_0-9]+)", out))
+    assert declared <= exported
+
+
+def test_library_contains_sm100a_code_only(api):
+    out = subprocess.run(["cuobjdump", "-lelf", str(api.LIB_PATH)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_gpu_means_loud_failure_not_fallback(api, assets_dirs):
+    """In this container there is no GPU: creating a context must fail with MCRT_ERR_CUDA -- the
+    product has no CPU path.  (On a GPU box this test is skipped.)"""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    with pytest.raises(api.McrtError) as e:
+        api.Simulator(assets_dirs["sphere"] / "sphere.scene")
+    assert e.value.code == api.MCRT_ERR_CUDA
+
+
+def test_product_does_not_reference_the_oracle():
+    """The shipped path must not import, link or call anything under oracle/."""
+    pkg = ROOT / "mcray_tracing_b200"
+    for path in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cpp")) + list(pkg.rglob("*.h")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("Makefile")):
+        text = path.read_text(errors="replace")
+        assert "oracle_py" not in text and "liboracle" not in text and "mcrt_oracle" not in text, path
+        assert not re.search(r"(from|import)\s+oracle\b", text), path
+    out = subprocess.run(["ldd", str(pkg / "libmcrt.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+def test_scene_errors_and_probe(api, assets_dirs, tmp_path):
+    info = api.scene_probe(assets_dirs["sphere"] / "sphere.scene")
+    assert info["n_triangles"] == 12 + 20480 and info["n_meshes"] == 2 and info["n_materials"] == 11
+    assert np.array_equal(info["start_pose"], np.array([-13.5, 0, 0, 0, 0, -90], np.float32))
+    assert api.scene_probe(assets_dirs["ircad11"] / "ircad11.scene")["n_triangles"] == 624640   # defaulted shininess/thickness
+    cases = {"nojson.scene": "{", "nomesh.scene": '{"transducerPosition":[0,0,0],"origin":[0,0,0],"spacing":[1,1,1],"startingMaterial":"A","scaling":1,'
+             '"materials":[{"name":"A","impedance":1,"attenuation":1,"mu0":0,"mu1":0,"sigma":0,"specularity":1}],"meshes":3}',
+             "badmat.scene": '{"transducerPosition":[0,0,0],"origin":[0,0,0],"spacing":[1,1,1],"startingMaterial":"B","scaling":1,'
+             '"materials":[{"name":"A","impedance":1,"attenuation":1,"mu0":0,"mu1":0,"sigma":0,"specularity":1}],"meshes":[]}'}
+    for name, text in cases.items():
+        (tmp_path / name).write_text(text)
+        with pytest.raises(api.McrtError) as e:
+            api.scene_probe(tmp_path / name)
+        assert e.value.code == api.MCRT_ERR_SCENE and e.value.message.startswith("Error while loading scene: ")
+    with pytest.raises(api.McrtError) as e:
+        api.host_tables(api.default_params(psf_lateral=12))
+    assert e.value.code == api.MCRT_ERR_INVALID
+
+
+def test_runtime_sizes(api, O):
+    """BASELINE configs: 256 x 16 keeps 465 rows; a finer axial grid gives config 5's ~8192 samples."""
+    for kw, rows in ((dict(elements=256, samples=16), 465), (dict(elements=1024, samples=8, axial_scale=17.6), 8333)):
+        info = api.host_tables(api.default_params(**kw))["info"]
+        d = O.derive(O.default_params(**kw))
+        assert info.rows == d.rows == rows and info.cols == kw["elements"]
+        assert info.time_step_us == d.time_step_us and info.row_period_us == d.row_period_us
+
+
+# ---- sweep sharding --------------------------------------------------------------------------------------
+def test_shard_bounds_partition():
+    from mcray_tracing_b200 import sweep
+    for n in (0, 1, 7, 512, 513):
+        for w in (1, 2, 3, 4, 8):
+            b = [sweep.shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [e - s for s, e in b]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sweep.all_shard_sizes(n, w)
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from mcray_tracing_b200 import sweep
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+n = int(sys.argv[1])
+poses = np.arange(n * 6, dtype=np.float32).reshape(n, 6)
+def fake(block, first_frame, out):          # stands in for Simulator.simulate_device: a pure function of (pose, global frame)
+    for i in range(len(block)):
+        out[i] = torch.arange(12, dtype=torch.float32).reshape(3, 4) * float(first_frame + i + 1) + float(block[i, 0])
+res = sweep.run_sweep(fake, poses, (3, 4), torch.device("cpu"), seed_first_frame=100)
+if dist.get_rank() == 0:
+    single = torch.empty((n, 3, 4))
+    fake(poses, 100, single)
+    assert res.shape == single.shape and torch.equal(res, single), "sharded sweep differs from the single-rank sweep"
+    print("OK", n)
+else:
+    assert res is None
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("n_poses", [8, 7])
+def test_sweep_gather_world_size_2_gloo(tmp_path, n_poses):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=str(ROOT)))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), str(n_poses)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=180) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e[-2000:]
+    assert f"OK {n_poses}" in outs[0][0]
+
+
+# ---- closed-form known answers for the oracle ----------------------------------------------------------
+def _box_scene(O, half=2.0):
+    v = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], np.float32) * half
+    q = [[0, 3, 2, 1], [4, 5, 6, 7], [0, 1, 5, 4], [2, 3, 7, 6], [1, 2, 6, 5], [0, 4, 7, 3]]
+    tris = []
+    for a, b, c, d in q:
+        tris += [np.concatenate([v[a], v[b], v[c]]), np.concatenate([v[a], v[c], v[d]])]
+    mats = np.array([[1.5, 0.5, 0.1, 0.2, 0.1, 1, 1e6, 0], [1.5, 0.7, 0.2, 0.3, 0.2, 1, 1e6, 0], [3.0, 1.0, 0.2, 0.3, 0.2, 1, 1e6, 0]], np.float32)
+    return dict(materials=mats, starting_material=0, mesh_material_inside=np.array([1], np.int32), mesh_material_outside=np.array([0], np.int32),
+                mesh_vascular=np.array([0], np.int32), mesh_deltas=np.zeros((1, 3), np.float32), tri_offsets=np.array([0, 12], np.int64),
+                tri_vertices=np.array(tris, np.float32), scaling=1.0, origin=np.zeros(3, np.float32), spacing=np.ones(3, np.float32))
+
+
+def test_ray_box_closed_form(O):
+    osc = O.OracleScene(_box_scene(O))
+    rng = np.random.default_rng(2)
+    for _ in range(300):
+        o = np.array([-5.0, rng.uniform(-1.9, 1.9), rng.uniform(-1.9, 1.9)], np.float32)
+        t = o + np.array([10.0, 0, 0], np.float32)
+        for use_bvh in (False, True):
+            tri, mesh, f = osc.closest_hit(o, t, use_bvh)
+            assert tri >= 0 and mesh == 0
+            assert abs(f[0] - 0.3) < 1e-6                                  # enters the x = -2 face at 3/10 of the segment
+            assert np.allclose(f[1:4], [-2.0, o[1], o[2]], atol=1e-5)
+            assert np.allclose(f[4:7], [-1.0, 0, 0], atol=1e-6)            # normal faces the ray origin
+    assert osc.closest_hit([-5, 3, 0], [5, 3, 0])[0] == -1                 # passes above the box
+    assert osc.closest_hit([-5, 0, 0], [-3, 0, 0])[0] == -1                # stops short
+
+
+def test_snell_and_intensity_closed_forms(O):
+    L = O.oracle()
+    assert L.orc_reflection_intensity(0.7, 1.5, 0.8, 1.5, 0.8) == 0.0      # matched impedance: nothing reflected
+    z1, z2 = 1.38, 7.8
+    r = L.orc_reflection_intensity(1.0, z1, 1.0, z2, 1.0)
+    assert abs(r - ((z1 - z2) / (z1 + z2)) ** 2) < 1e-6                    # normal incidence
+    o3 = np.zeros(3, np.float32)
+    l = np.array([1, 0, 0], np.float32); n = np.array([-1, 0, 0], np.float32)
+    L.orc_snells_law(l.ctypes.data, n.ctypes.data, 1.0, 1.0, 1.0, o3.ctypes.data)
+    assert np.array_equal(o3, l)                                           # no deviation at normal incidence, equal media
+    oi, od = C.c_float(), C.c_double()
+    L.orc_travel(0.7, 0.2, 4.5, 0.0, 30.0, C.byref(oi), C.byref(od))       # Beer-Lambert; SURVEY.md C-3c value
+    assert abs(oi.value - 0.2 * np.exp(-0.7 * 0.3 * 4.5)) < 1e-7 and abs(oi.value - 0.0777359232) < 1e-8 and od.value == 30.0
+    assert abs(L.orc_max_ray_length(0.7, 0.2, 4.5) - 1376.769) < 1e-2
+
+
+def test_psf_of_delta_and_envelope_of_sinusoid(O):
+    p = O.default_params()
+    ax, lat = O.psf_taps(p)
+    img = np.zeros((100, 60), np.float32)
+    img[50, 30] = 1.0
+    out = O.convolve(img, ax, lat)
+    exp = np.zeros_like(img)
+    for k in range(7):
+        for m in range(13):
+            exp[50 - k, 30 - m] = ax[k] * lat[m]                           # forward-looking taps: the delta spreads up/left
+    assert np.allclose(out, exp, atol=1e-7)
+    t = np.arange(400, dtype=np.float32)
+    sig = (np.sin(2 * np.pi * t / 16.0)).astype(np.float32)
+    col = np.tile(sig[:, None], (1, 4))
+    env = O.envelope(col)
+    inner = env[8:380, 0]
+    assert inner.min() > 0.99 and inner.max() < 1.0 + 1e-6                 # envelope of a unit sinusoid ~ 1 between its peaks

@@ -1,0 +1,286 @@
+"""Pins the CPU oracle (and the product's host-side loaders / tables) to the REFERENCE: every golden
+vector under tests/golden/reference_kat.npz was produced by the reference's own code (make_golden.py
+through oracle/_ref).  Bit-exact unless a tolerance is written next to the assert.  No GPU needed."""
+import ctypes as C
+import hashlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def G():
+    return dict(np.load(GOLD / "reference_kat.npz"))
+
+
+@pytest.fixture(scope="module")
+def O(built):
+    from oracle import oracle_py
+    return oracle_py
+
+
+@pytest.fixture(scope="module")
+def api(built):
+    from mcray_tracing_b200 import api as a
+    return a
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def gold_sha(G, key):
+    return bytes(G[key]).hex()
+
+
+def ulp_diff(a, b):
+    a = np.asarray(a, np.float32).view(np.int32).astype(np.int64)
+    b = np.asarray(b, np.float32).view(np.int32).astype(np.int64)
+    return np.abs(a - b)
+
+
+# ---- constants, psf, transducer, volume ---------------------------------------------------------------
+def test_derived_constants(G, O, api):
+    c = G["constants"]
+    d = O.derive(O.default_params())
+    assert d.axial_resolution_mm == c[0] and d.max_travel_time_us == c[1] and d.max_travel_time_u == c[2]
+    assert d.rf_axial_um == c[3] and d.rows == c[4] == 465 and d.cols == c[5] == 512
+    assert d.element_separation_mm == c[6] and d.time_step_us == c[7] and d.axial_resolution_f == np.float32(c[13])
+    info = api.host_tables(api.default_params())["info"]            # the product's own derivation
+    assert info.rows == 465 and info.cols == 512
+    assert info.axial_resolution_mm == c[0] and info.time_step_us == c[7] and info.max_travel_time_us == c[1]
+    assert info.row_period_us == 322.0 / 1500.0
+
+
+def test_psf_taps(G, O, api):
+    ax, lat = O.psf_taps(O.default_params())
+    assert np.array_equal(ax, G["psf_axial"]) and np.array_equal(lat, G["psf_lateral"])
+    t = api.host_tables(api.default_params())
+    assert np.array_equal(t["axial"], G["psf_axial"]) and np.array_equal(t["lateral"], G["psf_lateral"])
+    # SURVEY.md Appendix C-2 literal values
+    assert abs(float(ax[2]) - 0.617545009) < 1e-8 and abs(float(lat[6]) - 0.986945331) < 1e-8
+
+
+def test_transducer_elements(G, O):
+    p = O.default_params()
+    for i, q in enumerate(G["tr_poses"]):
+        pos, d = O.transducer_elements(p, q[:3], q[3:])
+        assert np.array_equal(pos, G["tr_pos"][i]) and np.array_equal(d, G["tr_dir"][i])
+
+
+def test_product_element_table_reproduces_reference_directions(G, api):
+    """The product keeps sin/cos on the host (table + per-pose trig) and rotates on the device; with a
+    zero-angle pose the rotations are exact identities, so the table must equal the reference's
+    un-rotated directions: use pose angles (0,0,0)... which the golden set does not contain, so
+    instead check the table against the closed form in the same float pipeline."""
+    t = api.host_tables(api.default_params())["elem_sincos"]
+    assert t.shape == (512, 2)
+    assert np.allclose(t[:, 0] ** 2 + t[:, 1] ** 2, 1.0, atol=1e-6)
+    assert np.all(np.diff(t[:, 0]) > 0)                      # angles increase monotonically across the fan
+    assert abs(float(t[0, 0]) + float(t[511, 0])) < 1e-6     # symmetric fan
+
+
+def test_volume(G, O):
+    v = O.volume_raw()
+    assert sha(v) == gold_sha(G, "volume_sha256")
+    assert np.array_equal(v.reshape(-1)[:16], G["volume_first"])
+    assert np.array_equal(v.reshape(-1)[::65521][:512], G["volume_strided"])
+    # SURVEY.md Appendix C-3 literal values
+    assert abs(float(v[0, 0, 0, 0]) + 0.121965781) < 1e-8 and abs(float(v[255, 255, 255, 0]) + 0.459138662) < 1e-8
+    L = O.oracle()
+    out = np.array([L.orc_volume_get_scattering(C.c_void_p(L.orc_volume_get()), *map(float, G["scat_prm"][i]), *map(float, G["scat_pts"][i]))
+                    for i in range(len(G["scat_pts"]))], np.float32)
+    assert np.array_equal(out, G["scat_out"])                # includes negative coordinates (B-4)
+
+
+# ---- ray.cpp ---------------------------------------------------------------------------------------------
+def test_max_ray_length_and_travel(G, O):
+    """logf / expf come from the shared numerics contract instead of glibc: equal to the reference
+    within 1 ulp, and bit-equal in > 99.5 % of the cases (DESIGN.md "Numerics contract")."""
+    L = O.oracle()
+    got = np.array([L.orc_max_ray_length(float(a), float(i), 4.5) for a, i in G["mrl_in"]], np.float32)
+    d = ulp_diff(got, G["mrl_out"])
+    assert d.max() <= 1 and np.mean(d == 0) > 0.995
+    oi, od = C.c_float(), C.c_double()
+    ti, td = [], []
+    for (a, i), (d0, mm) in zip(G["mrl_in"], G["travel_in"]):
+        L.orc_travel(float(a), float(i), 4.5, float(d0), float(mm), C.byref(oi), C.byref(od))
+        ti.append(oi.value); td.append(od.value)
+    assert np.array_equal(np.array(td), G["travel_d"])       # double accumulation: exact
+    # relative 2e-7 on the intensity (a float may underflow towards 0 where ulps are meaningless)
+    assert np.allclose(np.array(ti, np.float32), G["travel_i"], rtol=2.5e-7, atol=1e-44)
+    assert np.mean(np.array(ti, np.float32) == G["travel_i"]) > 0.99
+
+
+def test_reflection_intensity_snell_eq8(G, O):
+    L = O.oracle()
+    got = np.array([L.orc_reflection_intensity(*map(float, r)) for r in G["ri_in"]], np.float32)
+    assert np.array_equal(got, G["ri_out"])
+    o3 = np.zeros(3, np.float32)
+    for i in range(len(G["snell_in"])):
+        l, n = np.ascontiguousarray(G["eq8_dirs"][i, 0]), np.ascontiguousarray(G["eq8_dirs"][i, 1])
+        c1, c2, r = map(float, G["snell_in"][i])
+        L.orc_snells_law(l.ctypes.data, n.ctypes.data, c1, c2, r, o3.ctypes.data)
+        assert np.array_equal(o3, G["snell_out"][i])
+    got = np.array([L.orc_reflected_intensity_eq8(np.ascontiguousarray(d[0]).ctypes.data, np.ascontiguousarray(d[1]).ctypes.data,
+                                                  np.ascontiguousarray(d[2]).ctypes.data, float(s))
+                    for d, s in zip(G["eq8_dirs"], G["eq8_spec"])], np.float32)
+    dd = ulp_diff(got, G["eq8_out"])                          # powf from the numerics contract
+    assert dd.max() <= 1 and np.mean(dd == 0) > 0.995
+
+
+def test_random_unit_vector_identity_at_cos_one(G, O):
+    assert G["ruv_identity_ok"][0] == G["ruv_identity_ok"][1]
+    L = O.oracle()
+    rng = np.random.default_rng(0)
+    o3 = np.zeros(3, np.float32)
+    for i in range(300):
+        v = np.ascontiguousarray(G["eq8_dirs"][i, 0])
+        L.orc_random_unit_vector(v.ctypes.data, 1.0, float(rng.uniform(1e-9, 1)), float(rng.uniform(1e-9, 1)), o3.ctypes.data)
+        assert np.array_equal(o3, v)
+
+
+def test_random_unit_vector_distribution(G, O):
+    """For cos(theta') < 1 the reference draws from std::random_device, so ray.cpp:167-211 can only be
+    pinned statistically: the first and second moments of the returned vector over 20000 draws per
+    (v, cos theta') case agree with the reference's within 5 standard errors.  (The reference's
+    construction does not return unit vectors -- |w| spans ~[0.1, 1.4] -- and the oracle keeps that.)"""
+    L = O.oracle()
+    rng = np.random.default_rng(1)
+    o3 = np.zeros(3, np.float32)
+    nd = int(G["ruv_draws"][0])
+    for cse, st in zip(G["ruv_cases"], G["ruv_stats"]):
+        v = np.ascontiguousarray(cse[:3])
+        acc = np.zeros((nd, 3), np.float64)
+        for i in range(nd):
+            L.orc_random_unit_vector(v.ctypes.data, float(cse[3]), float(rng.uniform(0, 1)), float(rng.uniform(0, 1)), o3.ctypes.data)
+            acc[i] = o3
+        se = 5.0 * np.sqrt(2.0) * np.maximum(st[1], 1e-6) / np.sqrt(nd)
+        assert np.all(np.abs(acc.mean(0) - st[0]) <= se), (acc.mean(0), st[0])
+        assert np.all(np.abs(acc.std(0) - st[1]) <= 0.05 * st[1] + 1e-6), (acc.std(0), st[1])
+        dots = acc @ v.astype(np.float64)
+        assert abs(dots.mean() - st[2, 0]) <= 5.0 * np.sqrt(2.0) * st[2, 1] / np.sqrt(nd) + 1e-6
+        nrm = np.linalg.norm(acc, axis=1)
+        assert abs(nrm.mean() - st[2, 2]) <= 5.0 * np.sqrt(2.0) * st[3, 0] / np.sqrt(nd) + 1e-6
+
+
+def test_hit_boundary_state_machine_and_physics(G, O):
+    """Replays every reference hit_boundary call (ray.cpp:11-97, reflect/refract branch as the reference
+    drew it): returned direction / intensity / back-scatter and the medium state machine, incl. the
+    `media_outside = &r.media` aliasing (B-2).  Floats: <= 1 ulp (powf contract), mostly bit-equal."""
+    arr = {k: np.ascontiguousarray(G[k]) for k in ("hb_mats", "hb_mesh_in", "hb_mesh_out", "hb_mesh_vasc")}
+    n_mesh = len(arr["hb_mesh_in"])
+    scene = dict(materials=arr["hb_mats"], starting_material=0, mesh_material_inside=arr["hb_mesh_in"], mesh_material_outside=arr["hb_mesh_out"],
+                 mesh_vascular=arr["hb_mesh_vasc"], mesh_deltas=np.zeros((n_mesh, 3), np.float32), tri_offsets=np.arange(n_mesh + 1, dtype=np.int64),
+                 tri_vertices=np.tile(np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32), (n_mesh, 1)), scaling=1.0,
+                 origin=np.zeros(3, np.float32), spacing=np.ones(3, np.float32))
+    osc = O.OracleScene(scene)
+    L = O.oracle()
+    recs = G["hb_records"]
+    assert len(recs) > 1000
+    exact = 0
+    branches = set()
+    for r in recs:
+        media, outside, depth, mesh = int(r[2]), int(r[3]), int(r[4]), int(r[5])
+        frm, d, I0, hp, nrm = r[6:9].astype(np.float32), r[9:12].astype(np.float32), float(np.float32(r[12])), r[13:16].astype(np.float32), r[16:19].astype(np.float32)
+        ref_f, ref_i = r[19:27].astype(np.float32), r[27:30].astype(np.int32)
+        st = np.array([media, outside, depth], np.int32)
+        u = np.zeros(4, np.float64)
+        ok = False
+        for force in (0, 1):
+            of, oi, br = np.zeros(8, np.float32), np.zeros(3, np.int32), C.c_int32(0)
+            L.orc_hit_boundary(osc.h, frm.ctypes.data, d.ctypes.data, I0, st.ctypes.data, hp.ctypes.data, nrm.ctypes.data, mesh, 1,
+                               u.ctypes.data, force, of.ctypes.data, oi.ctypes.data, C.byref(br))
+            if np.array_equal(oi, ref_i) and np.all(ulp_diff(of[np.isfinite(ref_f)], ref_f[np.isfinite(ref_f)]) <= 1) and \
+                    np.array_equal(np.isnan(of[4:8]), np.isnan(ref_f[4:8])):
+                ok = True
+                exact += int(np.array_equal(of[np.isfinite(ref_f)], ref_f[np.isfinite(ref_f)]))
+                branches.add((force, media != int(ref_i[1]), outside, int(ref_i[2])))
+                break
+        # B-5: where the reference returns NaN back-scatter (non-integer specularity with a negative
+        # base) the oracle deliberately returns a finite value; everything else must still match
+        if not ok and np.isnan(ref_f[0]):
+            for force in (0, 1):
+                of, oi, br = np.zeros(8, np.float32), np.zeros(3, np.int32), C.c_int32(0)
+                L.orc_hit_boundary(osc.h, frm.ctypes.data, d.ctypes.data, I0, st.ctypes.data, hp.ctypes.data, nrm.ctypes.data, mesh, 1,
+                                   u.ctypes.data, force, of.ctypes.data, oi.ctypes.data, C.byref(br))
+                if np.array_equal(oi, ref_i) and np.isfinite(of[0]) and np.all(ulp_diff(of[1:8][np.isfinite(ref_f[1:8])], ref_f[1:8][np.isfinite(ref_f[1:8])]) <= 1):
+                    ok = True
+                    break
+        assert ok, f"hit_boundary record {r[:6]} not reproduced"
+    assert exact > 0.98 * len(recs)
+    assert len({b[2:] for b in branches}) >= 5               # null/SELF/material transitions all exercised
+
+
+# ---- rfimage.h -------------------------------------------------------------------------------------------
+def test_add_echo_row_mapping(G, O):
+    """rf_image::add_echo (rfimage.h:33-40) row = t / (322 um / 1500 m/s), truncated, dropped if >= 465:
+    the oracle's accumulate uses the same expression; replay through orc_accumulate with one-step segments."""
+    d = O.derive(O.default_params())
+    rows = (G["echo_times"] / d.row_period_us)
+    mine = np.where(rows < 465, rows.astype(np.int64), -1)
+    assert np.array_equal(mine, G["echo_row_of_time"])
+    assert np.array_equal(np.unique(mine[mine >= 0]).astype(np.int32), G["echo_nonzero_rows"])
+
+
+def _img(G):
+    seed = int(G["img_seed"][0])
+    src = np.random.default_rng(seed).standard_normal((465, 512)).astype(np.float32)
+    src[np.random.default_rng(seed + 1).random(src.shape) < 0.3] = 0.0
+    return src
+
+
+def test_convolve_envelope(G, O):
+    src = _img(G)
+    ax, lat = O.psf_taps(O.default_params())
+    conv = O.convolve(src, ax, lat)
+    assert np.array_equal(conv[::7, ::11], G["conv_sample"]) and sha(conv) == gold_sha(G, "conv_sha256")
+    env = O.envelope(src)
+    assert np.array_equal(env[::7, ::11], G["env_sample"]) and sha(env) == gold_sha(G, "env_sha256")
+    both = O.envelope(conv)
+    assert np.array_equal(both[::7, ::11], G["conv_env_sample"]) and sha(both) == gold_sha(G, "conv_env_sha256")
+    # B-9: borders keep the raw samples
+    assert np.array_equal(conv[:7], src[:7]) and np.array_equal(conv[-7:], src[-7:])
+    assert np.array_equal(conv[:, :6], src[:, :6]) and np.array_equal(conv[:, -13:], src[:, -13:])
+
+
+def test_scan_mapping_and_remap(G, O, api):
+    mx, my = O.create_mapping(O.default_params())
+    assert np.array_equal(mx[::9, ::13], G["map_x_sample"]) and sha(mx) == gold_sha(G, "map_x_sha256")
+    assert np.array_equal(my[::9, ::13], G["map_y_sample"]) and sha(my) == gold_sha(G, "map_y_sha256")
+    t = api.host_tables(api.default_params())                 # the product's maps
+    assert np.array_equal(t["map_x"], mx) and np.array_equal(t["map_y"], my)
+    img = np.abs(_img(G)) + 0.1
+    out = O.scan_convert(img, mx, my)
+    ref = G["remap_sample"]
+    got = out[::3, ::3]
+    assert int(np.count_nonzero(out)) == int(G["remap_nonzero"][0])
+    # cv2.remap evaluates the 4 taps with SIMD FMAs in a different order: tolerance 2e-6 relative
+    assert np.allclose(got, ref, rtol=2e-6, atol=1e-7), np.abs(got - ref).max()
+
+
+# ---- OBJ loading -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["quad_fan.obj", "negative.obj", "forms_groups.obj", "crlf_ws.obj"])
+def test_obj_loader_matches_tinyobj(G, O, api, name):
+    ref = G["obj_" + name]
+    assert len(ref) > 0
+    assert np.array_equal(O.load_obj_py(GOLD / name), ref)    # the tests' own Python loader
+    assert np.array_equal(api.load_obj(GOLD / name), ref)     # the product's C++ loader
+
+
+def test_live_reference_probe_when_available(G, O):
+    """Where the reference tree is mounted, re-derive a few vectors live from the reference's code."""
+    R = O.ref_probe()
+    if R is None:
+        pytest.skip("reference tree not mounted (golden vectors cover this)")
+    ax = np.zeros(7, np.float32); lat = np.zeros(13, np.float32)
+    R.ref_psf_taps(ax.ctypes.data, lat.ctypes.data)
+    assert np.array_equal(ax, G["psf_axial"]) and np.array_equal(lat, G["psf_lateral"])
+    pos = np.zeros((512, 3), np.float32); d = np.zeros((512, 3), np.float32)
+    q = np.array([3.5, -2.25, 9.0, 17.0, 250.0, -45.5], np.float32)
+    R.ref_transducer_elements(np.ascontiguousarray(q[:3]).ctypes.data, np.ascontiguousarray(q[3:]).ctypes.data, pos.ctypes.data, d.ctypes.data)
+    op, od = O.transducer_elements(O.default_params(), q[:3], q[3:])
+    assert np.array_equal(op, pos) and np.array_equal(od, d)
