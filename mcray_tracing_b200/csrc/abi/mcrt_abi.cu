@@ -205,7 +205,7 @@ void enqueue_pipeline(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* l
 
 int count_pipeline_launches(const mcrt_ctx* c, bool want_scan)
 {
-    return c->aq.max_depth + 1 + 3 + (c->params.rf_layout == 1 ? 1 : 0) + (want_scan ? 1 : 0);
+    return c->aq.max_depth + 2 + 3 + (c->params.rf_layout == 1 ? 1 : 0) + (want_scan ? 1 : 0);
 }
 
 void run_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches)
@@ -396,7 +396,6 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     CUDA_TRY(cudaMemcpy(c->d_map_x, mx.data(), sizeof(float) * mx.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(c->d_map_y, my.data(), sizeof(float) * my.size(), cudaMemcpyHostToDevice));
     c->d_volume = device_volume(device, c->stream);
-    CUDA_TRY(init_image_kernels());
 
     dev_alloc(c->d_seed_frame, 2);
     dev_alloc(c->d_steps, 1);

@@ -12,114 +12,180 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // volume.h:46-61
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t voxel_index(float coord, float resolution)
+// static_cast<unsigned>(negative float) is UB in the reference; x86-64/GCC converts through a 64-bit
+// integer and keeps the low 32 bits.  `% 256` of that is `& 255`.
+__device__ __forceinline__ uint32_t voxel_index_exact(float coord, float resolution)
 {
-    // static_cast<unsigned>(negative float) is UB in the reference; x86-64/GCC converts through a
-    // 64-bit integer and keeps the low 32 bits.  `% 256` of that is `& 255`.
     const float q = coord / resolution;
     return (uint32_t)__float2ll_rz(q) & 255u;
 }
 
+// Same result without the IEEE division on the hot path: q~ = coord * (1/resolution) is within
+// 2 ulp of fl(coord/resolution), so both truncate to the same integer unless q~ lies within a
+// (much wider) guard band of an integer -- only then is the exact quotient evaluated.
+__device__ __forceinline__ uint32_t voxel_index(float coord, float resolution, float inv_resolution)
+{
+    const float q = coord * inv_resolution;
+    const float tq = truncf(q);
+    const float fr = fabsf(q - tq);
+    const float eps = fabsf(q) * 1e-6f + 1e-30f;
+    if (fr < eps || fr > 1.0f - eps || !(fabsf(q) < 2.0e9f)) return voxel_index_exact(coord, resolution);
+    return (uint32_t)__float2int_rz(tq) & 255u;
+}
+
 // ------------------------------------------------------------------------------------------------
-// Echo accumulation.  One thread marches one Monte-Carlo path (its segments in order, each a
-// sequential fp32 position chain that must be reproduced exactly); every thread owns a private
-// RF column in shared memory so there are no atomics and the summation order is fixed.  The
-// columns of the samples of a scanline are then reduced in sample order and written coalesced.
+// Echo accumulation (main.cpp:106-144 + rf_image::add_echo, rfimage.h:33-40), no atomics.
+//
+// k_accumulate: one thread marches one Monte-Carlo path -- its segments in order, each a sequential
+// fp32 position chain / fp64 time chain that is reproduced exactly.  The RF row a step lands in
+// grows (almost always) monotonically along a path, so the thread keeps the running sum of the
+// current row in a register and writes every row of its private column exactly once, in order,
+// to HBM: columns[scanline][row][sample] (samples of a scanline adjacent -> the 16 lanes that march
+// a scanline in lock-step store one 64-byte line).  A row that is revisited (time going backwards,
+// possible only with spacing != 1) falls back to a read-modify-write of the thread's own column.
+// Scatterer-volume gathers are issued MCRT_ACC_UNROLL steps ahead of their use.
+//
+// k_reduce_samples: rf[scanline][row] = sum over samples in sample order (fixed order -> results
+// do not depend on scheduling; N-GPU sharding is bit-identical to 1 GPU).
 // ------------------------------------------------------------------------------------------------
+#define MCRT_ACC_UNROLL 4
+
 __global__ void __launch_bounds__(128) k_accumulate(const SceneDev sc, const AcqDev aq, const float2* __restrict__ volume,
                                                    const DevSegment* __restrict__ segments, const int32_t* __restrict__ nseg,
-                                                   const int n_scanlines, const int spc /*scanlines per CTA*/,
-                                                   const int tps /*threads per scanline*/, float* __restrict__ rf,
-                                                   unsigned long long* __restrict__ steps_total, float* g_columns)
+                                                   const int n_paths, float* __restrict__ columns,
+                                                   unsigned long long* __restrict__ steps_total)
 {
-    extern __shared__ float s_dyn[];                      // [rows][blockDim.x + 1] private columns ...
     __shared__ DevMaterial s_mat[MCRT_MAX_SMEM_MATERIALS];
-    const int NT = blockDim.x;
-    const int stride = NT + 1;
-    const int rows = aq.rows;
-    const int tid = threadIdx.x;
-    // ... or, when a scanline is too long for shared memory (BASELINE config 5), the same layout in HBM
-    float* s_acc = g_columns ? g_columns + (size_t)blockIdx.x * rows * stride : s_dyn;
-    for (int i = tid; i < sc.n_mat && i < MCRT_MAX_SMEM_MATERIALS; i += NT) s_mat[i] = sc.materials[i];
-    for (int i = tid; i < rows * stride; i += NT) s_acc[i] = 0.0f;       // rf_image.clear(), main.cpp:102
+    for (int i = threadIdx.x; i < sc.n_mat && i < MCRT_MAX_SMEM_MATERIALS; i += blockDim.x) s_mat[i] = sc.materials[i];
     __syncthreads();
-
-    const int sl_local = tid / tps;
-    const int j = tid - sl_local * tps;
-    const int scanline = blockIdx.x * spc + sl_local;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long my_steps = 0;
-    if (sl_local < spc && scanline < n_scanlines) {
-        float* col = s_acc + tid;
+    if (p < n_paths) {
+        const int S = aq.samples;
+        const int rows = aq.rows;
+        const int scanline = p / S;
+        const int s = p - scanline * S;
+        float* const col = columns + (size_t)scanline * rows * S + s;      // row r lives at col[r * S]
+        int written = 0;          // rows [0, written) of this column have been stored
+        int cur_row = -1;         // row being accumulated in cur_acc
+        float cur_acc = 0.0f;
         const float axres_f = aq.axres_f;
         const double time_step = aq.time_step_us;
         const double max_travel_time = aq.max_travel_time_us;
         const double row_period = aq.row_period_us, inv_row_period = aq.inv_row_period;
-        const float samples_f = (float)(size_t)aq.samples;
-        auto add_echo = [&](float echo, double micros) {                  // rfimage.h:33-40
+        const float samples_f = (float)(size_t)S;
+        const float vres = aq.vol_resolution, inv_vres = 1.0f / aq.vol_resolution;
+
+        auto flush = [&]() {
+            if (cur_row < 0) return;
+            if (cur_row >= written) {
+                for (int r = written; r < cur_row; r++) col[(size_t)r * S] = 0.0f;      // rows nothing landed in
+                col[(size_t)cur_row * S] = cur_acc;
+                written = cur_row + 1;
+            } else {
+                col[(size_t)cur_row * S] += cur_acc;                                     // revisited row (own data)
+            }
+        };
+        auto add_echo = [&](float echo, double micros) {                                  // rfimage.h:33-40
             // row = micros / (axial_resolution_/speed_of_sound_), truncated.  The product with the
             // reciprocal decides the row unless it lands within 1e-9 of an integer, where the exact
             // IEEE quotient is taken instead.
             double rowd = micros * inv_row_period;
-            const double fl = floor(rowd);
-            const double fr_ = rowd - fl;
-            if (fr_ < 1e-9 || fr_ > 1.0 - 1e-9) rowd = micros / row_period;
-            if (rowd < (double)(unsigned)rows) col[(int)rowd * stride] += echo;
+            const double fr_ = rowd - floor(rowd);
+            if (!(fr_ >= 1e-9 && fr_ <= 1.0 - 1e-9)) rowd = micros / row_period;
+            if (!(rowd < (double)(unsigned)rows)) return;
+            const int row = (int)rowd;
+            if (row == cur_row) { cur_acc += echo; return; }
+            flush();
+            cur_row = row;
+            cur_acc = echo;                                                               // 0 + echo
         };
-        for (int s = j; s < aq.samples; s += tps) {
-            const int p = scanline * aq.samples + s;
-            const int ns = nseg[p];
-            for (int k = 0; k < ns; k++) {
-                const DevSegment* sg = segments + (size_t)p * aq.max_depth + k;
-                const float4 s0 = __ldg(&sg->s0), s1 = __ldg(&sg->s1), s2 = __ldg(&sg->s2);
-                const int4 s3 = __ldg(&sg->s3);
-                const DevMaterial media = s_mat[s3.z];
-                const double distance_traveled = __hiloint2double(s3.y, s3.x);
-                const double starting_micros = ((distance_traveled * 1000) / 1) / aq.speed;      // main.cpp:114
-                const float3 from = make_float3(s0.x, s0.y, s0.z), to = make_float3(s2.x, s2.y, s2.z);
-                const double distance = (double)(v_length(v_sub(to, from)) * 10.0f);               // scene.cpp:342-346
-                const double steps_d = distance / aq.axres_mm;                                      // main.cpp:116
-                unsigned long long steps64;                                                         // B-14
-                if (!(steps_d >= 0.0)) steps64 = 0;
-                else if (steps_d >= 9.0e18) steps64 = 9000000000000000000ULL;
-                else steps64 = (unsigned long long)steps_d;
-                const uint32_t steps32 = (uint32_t)steps64;
-                const float3 delta_step = v_scl(make_float3(s1.x, s1.y, s1.z), axres_f);            // main.cpp:117
-                float3 point = from;
-                double time_elapsed = starting_micros;
-                float intensity = s1.w;
-                const float decay = mc_expf(-s2.w * axres_f * 0.01f * aq.frequency * 1.0f);         // main.cpp:135
-                for (unsigned long long step = 0; step < steps64 && time_elapsed < max_travel_time; step++) {
-                    const uint32_t xi = voxel_index(point.x, aq.vol_resolution);
-                    const uint32_t yi = voxel_index(point.y, aq.vol_resolution);
-                    const uint32_t zi = voxel_index(point.z, aq.vol_resolution);
-                    const float2 vox = __ldg(&volume[((size_t)xi * 256 + yi) * 256 + zi]);          // (noise, probability)
-                    // get_scattering(mu1, mu0, sigma, ...): density = mu1, mu = mu0 (main.cpp:126 vs volume.h:46)
-                    const float scattering = vox.y >= media.mu1 ? vox.x * media.sigma + media.mu0 : 0.0f;
-                    add_echo(intensity * scattering, time_elapsed);
-                    point = v_add(point, delta_step);
-                    time_elapsed = time_elapsed + time_step;
-                    intensity *= decay;
-                    my_steps++;
+
+        const int ns = nseg[p];
+        for (int k = 0; k < ns; k++) {
+            const DevSegment* sg = segments + (size_t)p * aq.max_depth + k;
+            const float4 s0 = __ldg(&sg->s0), s1 = __ldg(&sg->s1), s2 = __ldg(&sg->s2);
+            const int4 s3 = __ldg(&sg->s3);
+            const DevMaterial media = s_mat[s3.z];
+            const double distance_traveled = __hiloint2double(s3.y, s3.x);
+            const double starting_micros = ((distance_traveled * 1000) / 1) / aq.speed;      // main.cpp:114
+            const float3 from = make_float3(s0.x, s0.y, s0.z), to = make_float3(s2.x, s2.y, s2.z);
+            const double distance = (double)(v_length(v_sub(to, from)) * 10.0f);               // scene.cpp:342-346
+            const double steps_d = distance / aq.axres_mm;                                      // main.cpp:116
+            unsigned long long steps64;                                                         // B-14
+            if (!(steps_d >= 0.0)) steps64 = 0;
+            else if (steps_d >= 9.0e18) steps64 = 9000000000000000000ULL;
+            else steps64 = (unsigned long long)steps_d;
+            const uint32_t steps32 = (uint32_t)steps64;
+            const float3 delta_step = v_scl(make_float3(s1.x, s1.y, s1.z), axres_f);            // main.cpp:117
+            float3 point = from;
+            double time_elapsed = starting_micros;
+            float intensity = s1.w;
+            const float decay = mc_expf(-s2.w * axres_f * 0.01f * aq.frequency * 1.0f);         // main.cpp:135
+            unsigned long long step = 0;
+            while (step < steps64 && time_elapsed < max_travel_time) {                          // main.cpp:124
+                // issue up to MCRT_ACC_UNROLL gathers, then consume them in order
+                float2 vox[MCRT_ACC_UNROLL];
+                float inten[MCRT_ACC_UNROLL];
+                double tt[MCRT_ACC_UNROLL];
+                int nv = 0;
+#pragma unroll
+                for (int u = 0; u < MCRT_ACC_UNROLL; u++) {
+                    if (step + u < steps64 && time_elapsed < max_travel_time) {
+                        const uint32_t xi = voxel_index(point.x, vres, inv_vres);
+                        const uint32_t yi = voxel_index(point.y, vres, inv_vres);
+                        const uint32_t zi = voxel_index(point.z, vres, inv_vres);
+                        vox[u] = __ldg(&volume[(xi << 16) | (yi << 8) | zi]);                  // (noise, probability)
+                        inten[u] = intensity;
+                        tt[u] = time_elapsed;
+                        point = v_add(point, delta_step);                                       // main.cpp:131
+                        time_elapsed = time_elapsed + time_step;
+                        intensity *= decay;
+                        nv = u + 1;
+                    }
                 }
-                // main.cpp:139
-                add_echo(s0.w / samples_f, starting_micros + time_step * (double)(uint32_t)(steps32 - 1u));
+#pragma unroll
+                for (int u = 0; u < MCRT_ACC_UNROLL; u++) {
+                    if (u < nv) {
+                        // get_scattering(mu1, mu0, sigma, ...): density = mu1, mu = mu0 (main.cpp:126 vs volume.h:46)
+                        const float scattering = vox[u].y >= media.mu1 ? vox[u].x * media.sigma + media.mu0 : 0.0f;
+                        add_echo(inten[u] * scattering, tt[u]);
+                    }
+                }
+                step += (unsigned long long)nv;
+                my_steps += (unsigned long long)nv;
             }
+            // main.cpp:139
+            add_echo(s0.w / samples_f, starting_micros + time_step * (double)(uint32_t)(steps32 - 1u));
         }
-    }
-    __syncthreads();
-    // ordered reduction over the threads of each scanline, coalesced store
-    for (int o = tid; o < spc * rows; o += NT) {
-        const int sl = o / rows, r = o - sl * rows;
-        const int gl = blockIdx.x * spc + sl;
-        if (gl >= n_scanlines) break;
-        const float* src = s_acc + r * stride + sl * tps;
-        float sum = src[0];
-        for (int t = 1; t < tps; t++) sum += src[t];
-        rf[(size_t)gl * rows + r] = sum;
+        flush();
+        for (int r = written; r < rows; r++) col[(size_t)r * S] = 0.0f;                          // rf_image.clear(), main.cpp:102
     }
     if (steps_total) {
         for (int off = 16; off > 0; off >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, off);
-        if ((tid & 31) == 0 && my_steps) atomicAdd(steps_total, my_steps);
+        if ((threadIdx.x & 31) == 0 && my_steps) atomicAdd(steps_total, my_steps);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_reduce_samples(const float* __restrict__ columns, const int64_t n_pixels, const int samples,
+                                                       float* __restrict__ rf)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += (int64_t)gridDim.x * blockDim.x) {
+        const float* src = columns + i * samples;
+        float sum;
+        if ((samples & 3) == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4 v = __ldg(&s4[0]);
+            sum = v.x; sum += v.y; sum += v.z; sum += v.w;
+            for (int t = 1; t < (samples >> 2); t++) {
+                v = __ldg(&s4[t]);
+                sum += v.x; sum += v.y; sum += v.z; sum += v.w;
+            }
+        } else {
+            sum = __ldg(&src[0]);
+            for (int t = 1; t < samples; t++) sum += __ldg(&src[t]);
+        }
+        rf[i] = sum;
     }
 }
 
@@ -305,41 +371,22 @@ int grid1d(int64_t n, int block)
 
 }  // namespace
 
-cudaError_t init_image_kernels()
-{
-    // per-device function attribute; must not be issued inside a stream capture
-    return cudaFuncSetAttribute(k_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize, MCRT_ACC_SMEM_LIMIT);
-}
-
 size_t accumulate_columns_bytes(const AcqDev& aq, int n_poses)
 {
-    const int block = 32;
-    if (sizeof(float) * (size_t)aq.rows * (block + 1) <= MCRT_ACC_SMEM_LIMIT) return 0;
-    const int tps = aq.samples < 32 ? aq.samples : 32;
-    int spc = 32 / tps;
-    if (spc < 1) spc = 1;
-    const size_t grid = ((size_t)n_poses * aq.elements + spc - 1) / spc;
-    return grid * aq.rows * (block + 1) * sizeof(float);
+    return sizeof(float) * (size_t)n_poses * aq.elements * aq.samples * aq.rows;
 }
 
 cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2* d_volume, const DevSegment* d_segments,
                               const int32_t* d_nseg, int n_poses, float* d_rf, unsigned long long* d_steps, float* d_columns,
                               cudaStream_t stream, int* launches)
 {
-    const int n_scanlines = n_poses * aq.elements;
-    // threads per scanline: all samples in parallel when they fit a warp, else a warp striding over them
-    const int tps = aq.samples < 32 ? aq.samples : 32;
-    int spc = 32 / tps;
-    if (spc < 1) spc = 1;
-    const int block = 32;
-    size_t smem = sizeof(float) * (size_t)aq.rows * (block + 1);
-    if (smem > MCRT_ACC_SMEM_LIMIT) {
-        if (!d_columns) return cudaErrorInvalidConfiguration;      // caller must supply accumulate_columns_bytes() of HBM
-        smem = 0;
-    } else d_columns = nullptr;
-    const int grid = (n_scanlines + spc - 1) / spc;
-    k_accumulate<<<grid, block, smem, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_scanlines, spc, tps, d_rf, d_steps, d_columns);
-    if (launches) (*launches)++;
+    if (!d_columns) return cudaErrorInvalidValue;
+    const int n_paths = n_poses * aq.elements * aq.samples;
+    const int block = 128;
+    k_accumulate<<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_paths, d_columns, d_steps);
+    const int64_t n_pixels = (int64_t)n_poses * aq.elements * aq.rows;
+    k_reduce_samples<<<grid1d(n_pixels, 256), 256, 0, stream>>>(d_columns, n_pixels, aq.samples, d_rf);
+    if (launches) (*launches) += 2;
     return cudaGetLastError();
 }
 

@@ -49,10 +49,8 @@ void launch_closest_hit(const SceneDev& sc, int64_t n, const float* d_from, cons
 void launch_elements(const AcqDev& aq, const FrameDev& fr, float* d_pos, float* d_dir, cudaStream_t stream);
 
 // main.cpp:106-144: segments -> raw RF, scanline-major [n_poses*elements][rows]
-// d_columns: nullptr, or accumulate_columns_bytes() bytes of HBM when that is non-zero (scanlines too
-// long for per-thread shared-memory columns).
-#define MCRT_ACC_SMEM_LIMIT (200 * 1024)
-cudaError_t init_image_kernels();      // once per device, outside any stream capture
+// d_columns: accumulate_columns_bytes() bytes of HBM scratch: one private RF column per path,
+// columns[scanline][row][sample].
 size_t accumulate_columns_bytes(const AcqDev& aq, int n_poses);
 cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2* d_volume, const DevSegment* d_segments,
                               const int32_t* d_nseg, int n_poses, float* d_rf, unsigned long long* d_steps, float* d_columns,
