@@ -117,6 +117,8 @@ typedef struct mcrt_stats {   /* of the most recent mcrt_simulate call */
     int64_t kernel_launches;  /* kernels launched by this library inside the call */
     float ms_total;           /* device time of the call, CUDA events on the library's stream */
     float ms_trace, ms_accumulate, ms_post; /* only filled when profiling stages (mcrt_set_option) */
+    int64_t bvh_node_visits;  /* only with option "count_traversal": BVH nodes fetched / triangles tested */
+    int64_t bvh_triangle_tests;
 } mcrt_stats;
 
 int mcrt_default_params(mcrt_params* p);
@@ -132,7 +134,7 @@ const char* mcrt_last_error(void); /* thread-local, never NULL */
 int mcrt_get_info(const mcrt_ctx* ctx, mcrt_info* info);
 int mcrt_get_stats(const mcrt_ctx* ctx, mcrt_stats* stats);
 /* options: "profile_stages"=0/1 (per-stage events, disables the CUDA graph), "use_graph"=0/1,
- * "max_batch_poses"=N */
+ * "max_batch_poses"=N, "count_traversal"=0/1 (BVH work counters in mcrt_stats) */
 int mcrt_set_option(mcrt_ctx* ctx, const char* name, int64_t value);
 
 /* replaces one iteration of main.cpp:92-152 per pose: rf_image.clear(); scene.cast_rays();

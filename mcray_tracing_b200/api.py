@@ -11,7 +11,7 @@ from pathlib import Path
 import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libmcrt.so"
+LIB_PATH = Path(os.environ.get("MCRT_LIB_PATH", PKG_DIR / "libmcrt.so"))   # override: A/B builds during development
 
 MCRT_OK = 0
 MCRT_ERR_INVALID, MCRT_ERR_SCENE, MCRT_ERR_CUDA, MCRT_ERR_NOMEM = -1, -2, -3, -4
@@ -53,7 +53,8 @@ class Info(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("poses", C.c_int64), ("segments", C.c_int64), ("march_steps", C.c_int64), ("kernel_launches", C.c_int64),
-                ("ms_total", C.c_float), ("ms_trace", C.c_float), ("ms_accumulate", C.c_float), ("ms_post", C.c_float)]
+                ("ms_total", C.c_float), ("ms_trace", C.c_float), ("ms_accumulate", C.c_float), ("ms_post", C.c_float),
+                ("bvh_node_visits", C.c_int64), ("bvh_triangle_tests", C.c_int64)]
 
 
 SEGMENT_DTYPE = np.dtype([("from", np.float32, 3), ("to", np.float32, 3), ("dir", np.float32, 3),

@@ -113,6 +113,8 @@ struct mcrt_ctx {
     PoseTrigDev* d_poses = nullptr;
     unsigned long long* d_seed_frame = nullptr;
     unsigned long long* d_steps = nullptr;
+    unsigned long long* d_trav = nullptr;      // {node visits, triangle tests}, only when count_traversal
+    bool count_traversal = false;
     float* d_rf_acc = nullptr;
     float* d_rf_tmp0 = nullptr;
     float* d_rf_tmp1 = nullptr;
@@ -125,6 +127,7 @@ struct mcrt_ctx {
     unsigned long long* h_seed_frame = nullptr;
     int* h_counters = nullptr;         // pinned, [MAX_BATCHES][32]
     unsigned long long* h_steps = nullptr;
+    unsigned long long* h_trav = nullptr;
 
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;   // (n_poses in batch, want_scan) -> exec
     bool use_graph = true;
@@ -179,6 +182,7 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
     c->columns_bytes = accumulate_columns_bytes(c->aq, n_poses);
     if (c->columns_bytes) dev_alloc(c->d_columns, c->columns_bytes / sizeof(float));
     CUDA_TRY(cudaMallocHost(&c->h_poses, sizeof(PoseTrig) * (size_t)n_poses));
+    c->tb.trav_counters = c->count_traversal ? c->d_trav : nullptr;
     c->cap_poses = n_poses;
 }
 
@@ -258,6 +262,7 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
         const size_t scan_per_pose = (size_t)c->params.scan_rows * c->params.scan_cols;
         int launches = 0;
         CUDA_TRY(cudaEventRecord(c->ev0, s));
+        if (c->count_traversal) CUDA_TRY(cudaMemsetAsync(c->d_trav, 0, 2 * sizeof(unsigned long long), s));
         for (int b = 0; b < n_batches; b++) {
             const int p0 = b * batch_cap;
             const int n = (n_poses - p0) < batch_cap ? (n_poses - p0) : batch_cap;
@@ -281,6 +286,7 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
                                      cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaMemcpyAsync(c->h_steps + b, c->d_steps, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         }
+        if (c->count_traversal) CUDA_TRY(cudaMemcpyAsync(c->h_trav, c->d_trav, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaEventRecord(c->ev1, s));
         c->stats_pending = true;
         c->pending_batches = n_batches;
@@ -313,6 +319,7 @@ void finalize_stats(mcrt_ctx* c)
     c->stats.segments = segs;
     c->stats.march_steps = steps;
     c->stats.kernel_launches = c->pending_launches;
+    if (c->count_traversal) { c->stats.bvh_node_visits = (int64_t)c->h_trav[0]; c->stats.bvh_triangle_tests = (int64_t)c->h_trav[1]; }
     if (c->profile_stages && c->pending_batches == 1) {
         cudaEventElapsedTime(&c->stats.ms_trace, c->ev_a, c->ev_b);
         cudaEventElapsedTime(&c->stats.ms_accumulate, c->ev_b, c->ev_c);
@@ -398,10 +405,13 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     c->d_volume = device_volume(device, c->stream);
 
     dev_alloc(c->d_seed_frame, 2);
+    dev_alloc(c->d_trav, 2);
     dev_alloc(c->d_steps, 1);
     CUDA_TRY(cudaMallocHost(&c->h_seed_frame, 2 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMallocHost(&c->h_counters, sizeof(int) * 32 * kMaxBatchesPerCall));
     CUDA_TRY(cudaMallocHost(&c->h_steps, sizeof(unsigned long long) * kMaxBatchesPerCall));
+    CUDA_TRY(cudaMallocHost(&c->h_trav, 2 * sizeof(unsigned long long)));
+    c->h_trav[0] = c->h_trav[1] = 0;
     memset(c->h_counters, 0, sizeof(int) * 32 * kMaxBatchesPerCall);
     memset(c->h_steps, 0, sizeof(unsigned long long) * kMaxBatchesPerCall);
     *out = c.release();
@@ -416,10 +426,11 @@ void destroy_impl(mcrt_ctx* c)
     free_workspace(c);
     dev_free(c->d_meshes); dev_free(c->d_materials); dev_free(c->bvh.nodes); dev_free(c->bvh.tris);
     dev_free(c->d_elem_sincos); dev_free(c->d_axial); dev_free(c->d_lateral); dev_free(c->d_map_x); dev_free(c->d_map_y);
-    dev_free(c->d_seed_frame); dev_free(c->d_steps);
+    dev_free(c->d_seed_frame); dev_free(c->d_steps); dev_free(c->d_trav);
     if (c->h_seed_frame) cudaFreeHost(c->h_seed_frame);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_steps) cudaFreeHost(c->h_steps);
+    if (c->h_trav) cudaFreeHost(c->h_trav);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
@@ -526,6 +537,13 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
     const std::string n(name);
     if (n == "profile_stages") c->profile_stages = value != 0;
     else if (n == "use_graph") c->use_graph = value != 0;
+    else if (n == "count_traversal") {
+        // changes the kernel arguments baked into captured graphs: drop them
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear();
+        c->count_traversal = value != 0;
+        c->tb.trav_counters = c->count_traversal ? c->d_trav : nullptr;
+    }
     else if (n == "max_batch_poses") { if (value < 1) return fail(MCRT_ERR_INVALID, "max_batch_poses must be >= 1"); c->max_batch_poses = (int)value; }
     else return fail(MCRT_ERR_INVALID, "unknown option '" + n + "'");
     return MCRT_OK;

@@ -14,23 +14,27 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // static_cast<unsigned>(negative float) is UB in the reference; x86-64/GCC converts through a 64-bit
 // integer and keeps the low 32 bits.  `% 256` of that is `& 255`.
-__device__ __forceinline__ uint32_t voxel_index_exact(float coord, float resolution)
+__device__ __noinline__ uint32_t voxel_linear_exact(float x, float y, float z, float resolution)
 {
-    const float q = coord / resolution;
-    return (uint32_t)__float2ll_rz(q) & 255u;
+    const uint32_t xi = (uint32_t)__float2ll_rz(x / resolution) & 255u;
+    const uint32_t yi = (uint32_t)__float2ll_rz(y / resolution) & 255u;
+    const uint32_t zi = (uint32_t)__float2ll_rz(z / resolution) & 255u;
+    return (xi << 16) | (yi << 8) | zi;
 }
 
-// Same result without the IEEE division on the hot path: q~ = coord * (1/resolution) is within
-// 2 ulp of fl(coord/resolution), so both truncate to the same integer unless q~ lies within a
-// (much wider) guard band of an integer -- only then is the exact quotient evaluated.
-__device__ __forceinline__ uint32_t voxel_index(float coord, float resolution, float inv_resolution)
+// Same result without three IEEE divisions on the hot path: q~ = coord * (1/resolution) is within
+// 2 ulp of fl(coord/resolution), so both truncate to the same integer unless q~ lies within a (much
+// wider, 1e-6 relative) guard band of an integer -- only then are the exact quotients evaluated.
+__device__ __forceinline__ uint32_t voxel_linear(float3 p, float resolution, float inv_resolution)
 {
-    const float q = coord * inv_resolution;
-    const float tq = truncf(q);
-    const float fr = fabsf(q - tq);
-    const float eps = fabsf(q) * 1e-6f + 1e-30f;
-    if (fr < eps || fr > 1.0f - eps || !(fabsf(q) < 2.0e9f)) return voxel_index_exact(coord, resolution);
-    return (uint32_t)__float2int_rz(tq) & 255u;
+    const float qx = p.x * inv_resolution, qy = p.y * inv_resolution, qz = p.z * inv_resolution;
+    const int ix = __float2int_rz(qx), iy = __float2int_rz(qy), iz = __float2int_rz(qz);
+    const float ax = fabsf(qx - (float)ix), ay = fabsf(qy - (float)iy), az = fabsf(qz - (float)iz);   // [0,1) unless saturated
+    const float amin = fminf(fminf(ax, ay), az), amax = fmaxf(fmaxf(ax, ay), az);
+    const float qmax = fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
+    const float eps = qmax * 1e-6f + 1e-30f;
+    if (!(amin >= eps && amax <= 1.0f - eps && qmax < 2.0e9f)) return voxel_linear_exact(p.x, p.y, p.z, resolution);
+    return ((uint32_t)(ix & 255) << 16) | ((uint32_t)(iy & 255) << 8) | (uint32_t)(iz & 255);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -38,10 +42,10 @@ __device__ __forceinline__ uint32_t voxel_index(float coord, float resolution, f
 //
 // k_accumulate: one thread marches one Monte-Carlo path -- its segments in order, each a sequential
 // fp32 position chain / fp64 time chain that is reproduced exactly.  The RF row a step lands in
-// grows (almost always) monotonically along a path, so the thread keeps the running sum of the
-// current row in a register and writes every row of its private column exactly once, in order,
-// to HBM: columns[scanline][row][sample] (samples of a scanline adjacent -> the 16 lanes that march
-// a scanline in lock-step store one 64-byte line).  A row that is revisited (time going backwards,
+// grows (almost always) by one per step, so the thread keeps the running sum of the current row in
+// a register and writes every row of its private column exactly once, in order, to HBM:
+// columns[scanline][row][sample] (samples of a scanline adjacent -> the 16 lanes that march a
+// scanline in lock-step store one 64-byte line).  A row that is revisited (time going backwards,
 // possible only with spacing != 1) falls back to a read-modify-write of the thread's own column.
 // Scatterer-volume gathers are issued MCRT_ACC_UNROLL steps ahead of their use.
 //
@@ -49,6 +53,57 @@ __device__ __forceinline__ uint32_t voxel_index(float coord, float resolution, f
 // do not depend on scheduling; N-GPU sharding is bit-identical to 1 GPU).
 // ------------------------------------------------------------------------------------------------
 #define MCRT_ACC_UNROLL 4
+
+// Slow path of the column writer: the row being closed is not the next unwritten one.  Returns the
+// new `written` watermark.  Kept out of line so the hot loop stays small.
+__device__ __noinline__ int column_flush_slow(float* col, int S, int written, int cur_row, float cur_acc)
+{
+    if (cur_row < 0) return written;
+    if (cur_row >= written) {
+        for (int r = written; r < cur_row; r++) col[(size_t)r * S] = 0.0f;              // rows nothing landed in
+        col[(size_t)cur_row * S] = cur_acc;
+        return cur_row + 1;
+    }
+    col[(size_t)cur_row * S] += cur_acc;                                                 // revisited row (own data)
+    return written;
+}
+
+// Per-thread writer of one private RF column; all members live in registers (everything inlines).
+struct ColumnWriter {
+    float* col;          // row r lives at col[r * S]
+    int S, rows;
+    int written;         // rows [0, written) have been stored
+    int cur_row;         // row being accumulated in cur_acc (-1: none yet)
+    float cur_acc;
+    double row_period, inv_row_period;
+
+    // rf_image::add_echo (rfimage.h:33-40): row = micros / (axial_resolution_/speed_of_sound_), truncated;
+    // dropped when row >= max_rows.  The product with the reciprocal decides the row unless it lands
+    // within 1e-9 of an integer, where the exact IEEE quotient is taken instead.
+    __device__ __forceinline__ void add_echo(float echo, double micros)
+    {
+        double rowd = micros * inv_row_period;
+        int row = __double2int_rd(rowd);
+        const double fr = rowd - (double)row;
+        if (!(fr >= 1e-9 && fr <= 1.0 - 1e-9)) {
+            rowd = micros / row_period;
+            if (!(rowd < (double)(unsigned)rows)) return;
+            row = (int)rowd;
+        } else if (row >= rows) {
+            return;
+        }
+        if (row == cur_row) { cur_acc += echo; return; }
+        if (cur_row == written) { col[(size_t)cur_row * S] = cur_acc; written = cur_row + 1; }   // the common case: next row
+        else written = column_flush_slow(col, S, written, cur_row, cur_acc);
+        cur_row = row;
+        cur_acc = echo;                                                                   // 0 + echo
+    }
+    __device__ __forceinline__ void finish()
+    {
+        written = column_flush_slow(col, S, written, cur_row, cur_acc);
+        for (int r = written; r < rows; r++) col[(size_t)r * S] = 0.0f;                  // rf_image.clear(), main.cpp:102
+    }
+};
 
 __global__ void __launch_bounds__(128) k_accumulate(const SceneDev sc, const AcqDev aq, const float2* __restrict__ volume,
                                                    const DevSegment* __restrict__ segments, const int32_t* __restrict__ nseg,
@@ -62,44 +117,18 @@ __global__ void __launch_bounds__(128) k_accumulate(const SceneDev sc, const Acq
     unsigned long long my_steps = 0;
     if (p < n_paths) {
         const int S = aq.samples;
-        const int rows = aq.rows;
         const int scanline = p / S;
-        const int s = p - scanline * S;
-        float* const col = columns + (size_t)scanline * rows * S + s;      // row r lives at col[r * S]
-        int written = 0;          // rows [0, written) of this column have been stored
-        int cur_row = -1;         // row being accumulated in cur_acc
-        float cur_acc = 0.0f;
+        ColumnWriter w;
+        w.S = S; w.rows = aq.rows;
+        w.col = columns + (size_t)scanline * aq.rows * S + (p - scanline * S);
+        w.written = 0; w.cur_row = -1; w.cur_acc = 0.0f;
+        w.row_period = aq.row_period_us; w.inv_row_period = aq.inv_row_period;
         const float axres_f = aq.axres_f;
         const double time_step = aq.time_step_us;
+        const double inv_time_step = 1.0 / aq.time_step_us;
         const double max_travel_time = aq.max_travel_time_us;
-        const double row_period = aq.row_period_us, inv_row_period = aq.inv_row_period;
         const float samples_f = (float)(size_t)S;
         const float vres = aq.vol_resolution, inv_vres = 1.0f / aq.vol_resolution;
-
-        auto flush = [&]() {
-            if (cur_row < 0) return;
-            if (cur_row >= written) {
-                for (int r = written; r < cur_row; r++) col[(size_t)r * S] = 0.0f;      // rows nothing landed in
-                col[(size_t)cur_row * S] = cur_acc;
-                written = cur_row + 1;
-            } else {
-                col[(size_t)cur_row * S] += cur_acc;                                     // revisited row (own data)
-            }
-        };
-        auto add_echo = [&](float echo, double micros) {                                  // rfimage.h:33-40
-            // row = micros / (axial_resolution_/speed_of_sound_), truncated.  The product with the
-            // reciprocal decides the row unless it lands within 1e-9 of an integer, where the exact
-            // IEEE quotient is taken instead.
-            double rowd = micros * inv_row_period;
-            const double fr_ = rowd - floor(rowd);
-            if (!(fr_ >= 1e-9 && fr_ <= 1.0 - 1e-9)) rowd = micros / row_period;
-            if (!(rowd < (double)(unsigned)rows)) return;
-            const int row = (int)rowd;
-            if (row == cur_row) { cur_acc += echo; return; }
-            flush();
-            cur_row = row;
-            cur_acc = echo;                                                               // 0 + echo
-        };
 
         const int ns = nseg[p];
         for (int k = 0; k < ns; k++) {
@@ -122,44 +151,50 @@ __global__ void __launch_bounds__(128) k_accumulate(const SceneDev sc, const Acq
             double time_elapsed = starting_micros;
             float intensity = s1.w;
             const float decay = mc_expf(-s2.w * axres_f * 0.01f * aq.frequency * 1.0f);         // main.cpp:135
-            unsigned long long step = 0;
-            while (step < steps64 && time_elapsed < max_travel_time) {                          // main.cpp:124
-                // issue up to MCRT_ACC_UNROLL gathers, then consume them in order
+            // The loop of main.cpp:124 runs while (step < steps && time_elapsed < max_travel_time); the time
+            // bound caps it far below 2^31 iterations, so the step budget fits an int.
+            int remaining = steps64 > 0x7fffffffULL ? 0x7fffffff : (int)steps64;
+            // steps that certainly satisfy the time bound (2 steps of slack against the rounding of the
+            // iterated fp64 sum) run in unrolled blocks without per-step checks
+            const double safe_d = (max_travel_time - time_elapsed) * inv_time_step - 2.0;
+            int n_safe = safe_d > 0.0 ? (safe_d < 2.0e9 ? (int)safe_d : 2000000000) : 0;
+            if (n_safe > remaining) n_safe = remaining;
+            const int n_blocks = n_safe / MCRT_ACC_UNROLL;
+            for (int b = 0; b < n_blocks; b++) {
+                uint32_t idx[MCRT_ACC_UNROLL];
+#pragma unroll
+                for (int u = 0; u < MCRT_ACC_UNROLL; u++) {
+                    idx[u] = voxel_linear(point, vres, inv_vres);
+                    point = v_add(point, delta_step);                                           // main.cpp:131
+                }
                 float2 vox[MCRT_ACC_UNROLL];
-                float inten[MCRT_ACC_UNROLL];
-                double tt[MCRT_ACC_UNROLL];
-                int nv = 0;
+#pragma unroll
+                for (int u = 0; u < MCRT_ACC_UNROLL; u++) vox[u] = __ldg(&volume[idx[u]]);      // (noise, probability)
 #pragma unroll
                 for (int u = 0; u < MCRT_ACC_UNROLL; u++) {
-                    if (step + u < steps64 && time_elapsed < max_travel_time) {
-                        const uint32_t xi = voxel_index(point.x, vres, inv_vres);
-                        const uint32_t yi = voxel_index(point.y, vres, inv_vres);
-                        const uint32_t zi = voxel_index(point.z, vres, inv_vres);
-                        vox[u] = __ldg(&volume[(xi << 16) | (yi << 8) | zi]);                  // (noise, probability)
-                        inten[u] = intensity;
-                        tt[u] = time_elapsed;
-                        point = v_add(point, delta_step);                                       // main.cpp:131
-                        time_elapsed = time_elapsed + time_step;
-                        intensity *= decay;
-                        nv = u + 1;
-                    }
+                    // get_scattering(mu1, mu0, sigma, ...): density = mu1, mu = mu0 (main.cpp:126 vs volume.h:46)
+                    const float scattering = vox[u].y >= media.mu1 ? vox[u].x * media.sigma + media.mu0 : 0.0f;
+                    w.add_echo(intensity * scattering, time_elapsed);
+                    time_elapsed = time_elapsed + time_step;
+                    intensity *= decay;
                 }
-#pragma unroll
-                for (int u = 0; u < MCRT_ACC_UNROLL; u++) {
-                    if (u < nv) {
-                        // get_scattering(mu1, mu0, sigma, ...): density = mu1, mu = mu0 (main.cpp:126 vs volume.h:46)
-                        const float scattering = vox[u].y >= media.mu1 ? vox[u].x * media.sigma + media.mu0 : 0.0f;
-                        add_echo(inten[u] * scattering, tt[u]);
-                    }
-                }
-                step += (unsigned long long)nv;
-                my_steps += (unsigned long long)nv;
+            }
+            remaining -= n_blocks * MCRT_ACC_UNROLL;
+            my_steps += (unsigned long long)(n_blocks * MCRT_ACC_UNROLL);
+            while (remaining > 0 && time_elapsed < max_travel_time) {                           // checked tail
+                const float2 vox = __ldg(&volume[voxel_linear(point, vres, inv_vres)]);
+                const float scattering = vox.y >= media.mu1 ? vox.x * media.sigma + media.mu0 : 0.0f;
+                w.add_echo(intensity * scattering, time_elapsed);
+                point = v_add(point, delta_step);
+                time_elapsed = time_elapsed + time_step;
+                intensity *= decay;
+                remaining--;
+                my_steps++;
             }
             // main.cpp:139
-            add_echo(s0.w / samples_f, starting_micros + time_step * (double)(uint32_t)(steps32 - 1u));
+            w.add_echo(s0.w / samples_f, starting_micros + time_step * (double)(uint32_t)(steps32 - 1u));
         }
-        flush();
-        for (int r = written; r < rows; r++) col[(size_t)r * S] = 0.0f;                          // rf_image.clear(), main.cpp:102
+        w.finish();
     }
     if (steps_total) {
         for (int off = 16; off > 0; off >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, off);

@@ -93,7 +93,7 @@ __device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys
 }
 
 __global__ void k_karras(const unsigned long long* __restrict__ keys, int n, int* __restrict__ left, int* __restrict__ right,
-                         int* __restrict__ parent_internal, int* __restrict__ parent_leaf)
+                         int* __restrict__ parent_internal, int* __restrict__ parent_leaf, int2* __restrict__ range)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
@@ -119,6 +119,7 @@ __global__ void k_karras(const unsigned long long* __restrict__ keys, int n, int
     const int rc = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
     left[i] = lc;
     right[i] = rc;
+    range[i] = make_int2(lo, hi);      // sorted-position range covered by this node
     if (lc >= 0) parent_internal[lc] = i; else parent_leaf[~lc] = i;
     if (rc >= 0) parent_internal[rc] = i; else parent_leaf[~rc] = i;
     if (i == 0) parent_internal[0] = -1;
@@ -140,8 +141,8 @@ __global__ void k_refit(const unsigned int* __restrict__ vals, const float4* __r
         __threadfence();
         const int lc = left[node], rc = right[node];
         float4 llo, lhi, rlo, rhi;
-        if (lc >= 0) { llo = node_lo[lc]; lhi = node_hi[lc]; } else { const unsigned int t = vals[~lc]; llo = box_lo[t]; lhi = box_hi[t]; }
-        if (rc >= 0) { rlo = node_lo[rc]; rhi = node_hi[rc]; } else { const unsigned int t = vals[~rc]; rlo = box_lo[t]; rhi = box_hi[t]; }
+        if (lc >= 0) { llo = __ldcg(&node_lo[lc]); lhi = __ldcg(&node_hi[lc]); } else { const unsigned int t = vals[~lc]; llo = box_lo[t]; lhi = box_hi[t]; }
+        if (rc >= 0) { rlo = __ldcg(&node_lo[rc]); rhi = __ldcg(&node_hi[rc]); } else { const unsigned int t = vals[~rc]; rlo = box_lo[t]; rhi = box_hi[t]; }
         node_lo[node] = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.f);
         node_hi[node] = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f);
         depth++;
@@ -160,9 +161,21 @@ __global__ void k_leaf_depth(int n, const int* __restrict__ parent_internal, con
     atomicMax(max_depth, depth);
 }
 
+// Child reference of the traversal layout: >= 0 internal node; < 0 a leaf holding `count` (1..MCRT_LEAF_MAX)
+// consecutive Morton-ordered triangle slots starting at `first`: -(1 + first * 4 + (count - 1)).  Radix-tree
+// subtrees of at most MCRT_LEAF_MAX triangles are collapsed into one leaf (their inner nodes are never visited).
+__device__ __forceinline__ int encode_child(int child, const int2* __restrict__ range)
+{
+    if (child < 0) return -(1 + (~child) * 4);
+    const int2 r = range[child];
+    const int count = r.y - r.x + 1;
+    if (count <= MCRT_LEAF_MAX) return -(1 + r.x * 4 + (count - 1));
+    return child;
+}
+
 __global__ void k_emit_nodes(const unsigned int* __restrict__ vals, const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
                              int n, const int* __restrict__ left, const int* __restrict__ right, const float4* __restrict__ node_lo,
-                             const float4* __restrict__ node_hi, BvhNode* __restrict__ nodes)
+                             const float4* __restrict__ node_hi, const int2* __restrict__ range, BvhNode* __restrict__ nodes)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
@@ -174,7 +187,7 @@ __global__ void k_emit_nodes(const unsigned int* __restrict__ vals, const float4
     nd.a = make_float4(llo.x, llo.y, llo.z, lhi.x);
     nd.b = make_float4(lhi.y, lhi.z, rlo.x, rlo.y);
     nd.c = make_float4(rlo.z, rhi.x, rhi.y, rhi.z);
-    nd.d = make_int4(lc, rc, 0, 0);
+    nd.d = make_int4(encode_child(lc, range), encode_child(rc, range), 0, 0);
     nodes[i] = nd;
 }
 
@@ -203,6 +216,7 @@ cudaError_t build_lbvh(const float* h_tri_local, const int32_t* h_tri_mesh, int 
     memset(out, 0, sizeof(*out));
     float* d_tri_local = nullptr; int32_t* d_tri_mesh = nullptr;
     float4 *d_lo = nullptr, *d_hi = nullptr, *d_nlo = nullptr, *d_nhi = nullptr;
+    int2* d_range = nullptr;
     int *d_bounds = nullptr, *d_left = nullptr, *d_right = nullptr, *d_pi = nullptr, *d_pl = nullptr, *d_arr = nullptr, *d_depth = nullptr;
     unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
     unsigned int *d_vals = nullptr, *d_vals2 = nullptr;
@@ -241,20 +255,21 @@ cudaError_t build_lbvh(const float* h_tri_local, const int32_t* h_tri_mesh, int 
         CK(cudaMalloc(&d_right, sizeof(int) * (size_t)(n - 1)));
         CK(cudaMalloc(&d_pi, sizeof(int) * (size_t)(n - 1)));
         CK(cudaMalloc(&d_pl, sizeof(int) * (size_t)n));
+        CK(cudaMalloc(&d_range, sizeof(int2) * (size_t)(n - 1)));
         CK(cudaMalloc(&d_arr, sizeof(int) * (size_t)(n - 1)));
         CK(cudaMalloc(&d_depth, sizeof(int) * 2));
         CK(cudaMalloc(&d_nlo, sizeof(float4) * (size_t)(n - 1)));
         CK(cudaMalloc(&d_nhi, sizeof(float4) * (size_t)(n - 1)));
         CK(cudaMemsetAsync(d_arr, 0, sizeof(int) * (size_t)(n - 1), stream));
         CK(cudaMemsetAsync(d_depth, 0, sizeof(int) * 2, stream));
-        k_karras<<<G, B, 0, stream>>>(d_keys, n, d_left, d_right, d_pi, d_pl);
+        k_karras<<<G, B, 0, stream>>>(d_keys, n, d_left, d_right, d_pi, d_pl, d_range);
         CK(cudaGetLastError());
         k_refit<<<G, B, 0, stream>>>(d_vals, d_lo, d_hi, n, d_left, d_right, d_pi, d_pl, d_arr, d_nlo, d_nhi, d_depth);
         CK(cudaGetLastError());
         k_leaf_depth<<<G, B, 0, stream>>>(n, d_pi, d_pl, d_depth + 1);
         CK(cudaGetLastError());
         CK(cudaMalloc(&out->nodes, sizeof(BvhNode) * (size_t)(n - 1)));
-        k_emit_nodes<<<G, B, 0, stream>>>(d_vals, d_lo, d_hi, n, d_left, d_right, d_nlo, d_nhi, out->nodes);
+        k_emit_nodes<<<G, B, 0, stream>>>(d_vals, d_lo, d_hi, n, d_left, d_right, d_nlo, d_nhi, d_range, out->nodes);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h_depth, d_depth, sizeof(h_depth), cudaMemcpyDeviceToHost, stream));
     } else {
@@ -273,7 +288,7 @@ cudaError_t build_lbvh(const float* h_tri_local, const int32_t* h_tri_mesh, int 
 done:
     cudaFree(d_tri_local); cudaFree(d_tri_mesh); cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_nlo); cudaFree(d_nhi);
     cudaFree(d_bounds); cudaFree(d_left); cudaFree(d_right); cudaFree(d_pi); cudaFree(d_pl); cudaFree(d_arr); cudaFree(d_depth);
-    cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_tmp);
+    cudaFree(d_range); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_tmp);
     if (err != cudaSuccess) { cudaFree(out->nodes); cudaFree(out->tris); memset(out, 0, sizeof(*out)); }
     return err;
 }

@@ -21,7 +21,14 @@ struct DevMesh { float ox, oy, oz; int mat_in; int mat_out; int vascular; int pa
 // BVH2 node, 64 B = one half cache line pair, fetched as 4 x LDG.128.
 //   a = (c0.lo.x, c0.lo.y, c0.lo.z, c0.hi.x)   b = (c0.hi.y, c0.hi.z, c1.lo.x, c1.lo.y)
 //   c = (c1.lo.z, c1.hi.x, c1.hi.y, c1.hi.z)   d = (child0, child1, -, -)
-// child >= 0: internal node index; child < 0: leaf, ~child = triangle slot.
+// child >= 0: internal node index; child < 0: leaf of 1..MCRT_LEAF_MAX consecutive triangle slots,
+// encoded -(1 + first * 4 + (count - 1)).
+#ifndef MCRT_LEAF_MAX
+#define MCRT_LEAF_MAX 1       // measured on ircad11 (profiles/r01_traversal_ab.txt): 1 beats 2 and 4
+#endif
+#ifndef MCRT_STACK_CULL
+#define MCRT_STACK_CULL 0     // measured: storing the entry parameter on the stack costs more than it saves
+#endif
 struct __align__(16) BvhNode { float4 a, b, c; int4 d; };
 
 // Triangle slot (48 B, Morton order): local-frame vertices v_obj*scaling; v0.w = mesh id bits,
@@ -75,6 +82,7 @@ struct PathState {
 #define MCRT_OUTSIDE_NULL (-1)
 #define MCRT_OUTSIDE_SELF (-2)
 #define MCRT_INTENSITY_EPSILON 1e-10f     // ray.h:24
+#define MCRT_STACK_DEPTH 64                // >= depth of the BVH (checked at build time)
 
 // ------------------------------------------------------------------------------------------------
 // btVector3, scalar path
@@ -282,17 +290,24 @@ __device__ __forceinline__ bool box_test(const RayBox& r, float lox, float loy, 
     return tn <= tf * 1.000002f + 1e-37f;
 }
 
-__device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __restrict__ s_mesh, float3 from_w, float3 to_w, HitRec& best)
+// Stack-based closest-hit traversal, near child first.  `node_visits` / `tri_tests` are per-thread work
+// counters (two integer adds per iteration; reported through mcrt_stats when "count_traversal" is on).
+__device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __restrict__ s_mesh, float3 from_w, float3 to_w, HitRec& best,
+                                            int& node_visits, int& tri_tests)
 {
     best.fraction = 1.0f; best.tri_id = -1; best.mesh = -1; best.n_raw = make_float3(0.f, 0.f, 0.f); best.dist_a = 0.0f;
     if (sc.n_tri <= 0) return;
-    if (sc.n_tri == 1) { tri_test(sc.tris, 0, s_mesh, from_w, to_w, best); return; }
+    if (sc.n_tri == 1) { tri_test(sc.tris, 0, s_mesh, from_w, to_w, best); tri_tests++; return; }
     const RayBox rb = make_raybox(from_w, to_w, sc.max_abs);
-    int stack[64];
+    int stack[MCRT_STACK_DEPTH];
+#if MCRT_STACK_CULL
+    float stack_t[MCRT_STACK_DEPTH];     // entry parameter of the pushed subtree: lets a pop be culled without a fetch
+#endif
     int sp = 0;
     int node = 0;   // root
     while (true) {
         if (node >= 0) {
+            node_visits++;
             const BvhNode* nd = sc.nodes + node;
             const float4 a = __ldg(&nd->a), b = __ldg(&nd->b), c = __ldg(&nd->c);
             const int4 d = __ldg(&nd->d);
@@ -302,18 +317,34 @@ __device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __
             const bool h1 = box_test(rb, b.z, b.w, c.x, c.y, c.z, c.w, tb, t1);
             if (h0 && h1) {
                 const bool swap = t1 < t0;
-                const int nearc = swap ? d.y : d.x, farc = swap ? d.x : d.y;
-                if (sp < 64) stack[sp++] = farc;
-                node = nearc;
+                node = swap ? d.y : d.x;
+                stack[sp] = swap ? d.x : d.y;
+#if MCRT_STACK_CULL
+                stack_t[sp] = swap ? t0 : t1;
+#endif
+                sp++;
                 continue;
             }
             if (h0) { node = d.x; continue; }
             if (h1) { node = d.y; continue; }
         } else {
-            tri_test(sc.tris, ~node, s_mesh, from_w, to_w, best);
+            const int code = -node - 1;
+            const int first = code >> 2, count = (code & 3) + 1;
+            tri_tests += count;
+            for (int k = 0; k < count; k++) tri_test(sc.tris, first + k, s_mesh, from_w, to_w, best);
         }
+#if MCRT_STACK_CULL
+        // pop, skipping subtrees that start beyond the current closest hit (with the same slack)
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            if (stack_t[sp] <= best.fraction * 1.000002f) { node = stack[sp]; found = true; break; }
+        }
+        if (!found) break;
+#else
         if (sp == 0) break;
         node = stack[--sp];
+#endif
     }
 }
 

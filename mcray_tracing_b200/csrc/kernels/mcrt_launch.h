@@ -39,6 +39,7 @@ struct TraceBuffers {
     int* queue_a;                  // [n_paths]
     int* queue_b;                  // [n_paths]
     int* counters;                 // [max_depth + 1]: counters[b] = live paths entering bounce b
+    unsigned long long* trav_counters;   // nullptr, or {BVH node visits, triangle tests} accumulated over the call
 };
 
 // generate + max_depth x (intersect, shade, compact): scene::cast_rays (scene.cpp:50-183)

@@ -47,7 +47,7 @@ __device__ __forceinline__ unsigned pack_state(int media, int outside, int depth
 // One bounce of one path.  Returns true if the path survives into the next bounce.
 template <bool FIRST>
 __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, const TraceBuffers& tb,
-                                            const SharedScene& sh, int p, int bounce)
+                                            const SharedScene& sh, int p, int bounce, int& node_visits, int& tri_tests)
 {
     const int ES = aq.elements * aq.samples;
     const int pose = p / ES;
@@ -84,7 +84,7 @@ __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq
     const float3 to = v_add(from, v_scl(make_float3(sc.spacing[0] * dir.x, sc.spacing[1] * dir.y, sc.spacing[2] * dir.z), r_length / 100.0f));
     const float3 from_test = v_add(from, v_scl(dir, 0.1f));
     HitRec h;
-    closest_hit(sc, sh.mesh_origin, from_test, to, h);
+    closest_hit(sc, sh.mesh_origin, from_test, to, h, node_visits, tri_tests);
 
     DevSegment seg;
     bool alive = false;
@@ -199,12 +199,13 @@ __global__ void __launch_bounds__(128) k_bounce(const SceneDev sc, const AcqDev 
     const int n_round = (n_in + 31) & ~31;
     const unsigned lane = threadIdx.x & 31;
     const bool last = bounce + 1 >= aq.max_depth;
+    int node_visits = 0, tri_tests = 0;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += gridDim.x * blockDim.x) {
         int p = -1;
         bool alive = false;
         if (idx < n_in) {
             p = FIRST ? idx : qin[idx];
-            alive = bounce_path<FIRST>(sc, aq, fr, tb, sh, p, bounce);
+            alive = bounce_path<FIRST>(sc, aq, fr, tb, sh, p, bounce, node_visits, tri_tests);
         }
         if (!last) {
             // compact: warp-aggregated queue append (one atomic per warp)
@@ -216,6 +217,16 @@ __global__ void __launch_bounds__(128) k_bounce(const SceneDev sc, const AcqDev 
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (alive) qout[base + __popc(m & ((1u << lane) - 1u))] = p;
             }
+        }
+    }
+    if (tb.trav_counters) {      // optional work counters (mcrt_set_option "count_traversal")
+        for (int off = 16; off > 0; off >>= 1) {
+            node_visits += __shfl_xor_sync(0xffffffffu, node_visits, off);
+            tri_tests += __shfl_xor_sync(0xffffffffu, tri_tests, off);
+        }
+        if (lane == 0) {
+            atomicAdd(&tb.trav_counters[0], (unsigned long long)node_visits);
+            atomicAdd(&tb.trav_counters[1], (unsigned long long)tri_tests);
         }
     }
 }
@@ -230,7 +241,8 @@ __global__ void __launch_bounds__(128) k_closest_hit(const SceneDev sc, const in
         const float3 f = make_float3(from3[3 * i], from3[3 * i + 1], from3[3 * i + 2]);
         const float3 t = make_float3(to3[3 * i], to3[3 * i + 1], to3[3 * i + 2]);
         HitRec h;
-        closest_hit(sc, sh.mesh_origin, f, t, h);
+        int nv = 0, nt = 0;
+        closest_hit(sc, sh.mesh_origin, f, t, h, nv, nt);
         tri[i] = h.tri_id;
         mesh[i] = h.mesh;
         frac[i] = h.fraction;

@@ -24,3 +24,9 @@ for nb in (1, 64):
         sim.simulate(poses, seed=1, first_frame=0)
     st = sim.stats()
     print(f"stages batch {nb}: trace {st.ms_trace:.3f} acc {st.ms_accumulate:.3f} post {st.ms_post:.3f} total {st.ms_total:.3f}")
+sim.set_option("profile_stages", 0)
+sim.set_option("count_traversal", 1)
+poses = np.repeat(pose, 64, axis=0)
+sim.simulate(poses, seed=1, first_frame=0)
+st = sim.stats()
+print(f"traversal: segs {st.segments} node visits/seg {st.bvh_node_visits/st.segments:.1f} tri tests/seg {st.bvh_triangle_tests/st.segments:.1f}")
