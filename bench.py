@@ -93,6 +93,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads() -> int:
+    """Host cores this process may use (torchrun exports OMP_NUM_THREADS=1, so ask the scheduler, not OpenMP)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def measured_hbm_peak() -> tuple[float, str]:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -131,7 +139,7 @@ def run_reference(args, rank: int, world: int):
     d = assets.ensure_all()
     scene = d[SCENE_REL[0]] / SCENE_REL[1]
     pose = np.array([-17.5, 1.0, 5.0, 120.0, 0.0, -90.0], np.float32)
-    threads = max(1, O.oracle().orc_get_max_threads())
+    threads = host_threads()
     frames_per_sample = 4
     A = O.load_scene_py(scene)
     osc = O.OracleScene(A)
@@ -289,6 +297,20 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             sim.simulate_device(one, out1.data_ptr(), seed=seed, first_frame=50 + k)
             lat.append(sim.stats().ms_total)
         extra["latency_mode"] = {"frames_per_call": 1, "ms_per_frame_device": float(np.median(lat)), "frames_per_s": 1e3 / float(np.median(lat))}
+        if world == 1:
+            # the N > 1 runs simulate a freehand sweep (BASELINE configs[2]); its per-frame cost differs from
+            # the single pose, so the 1-GPU figure on the SAME sweep poses is reported for a like-for-like
+            # scaling comparison
+            sw = assets.sweep_poses(F * 8)[:F]
+            ms = []
+            for k in range(3 + 8):
+                flush.fill_(0.0)
+                torch.cuda.synchronize(dev)
+                sim.simulate_device(sw, out.data_ptr(), seed=seed, first_frame=k * F)
+                if k >= 3:
+                    ms.append(sim.stats().ms_total)
+            extra["sweep_workload_1gpu"] = {"frames_per_step": F, "poses": "first rank's block of an 8-rank sweep", "ms_per_step": float(np.mean(ms)),
+                                            "frames_per_s": F / (float(np.mean(ms)) * 1e-3)}
         # per-stage device times: separate pass, stage events between the kernels (no CUDA graph)
         sim.set_option("profile_stages", 1)
         tr, ac, po, tot, msteps = [], [], [], [], []
@@ -317,7 +339,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                     "stage_ms": {"trace": float(np.mean(tr)), "accumulate": ms_acc, "post": float(np.mean(po)), "total": float(np.mean(tot))}}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle_py as O
-            threads = max(1, O.oracle().orc_get_max_threads())
+            threads = host_threads()
             n = args.cpu_frames
             fps1, sps1, _, _ = oracle_frames_per_s(n, 1, scene, sim.start_pose)
             fpsN, spsN = (fps1, sps1) if threads == 1 else oracle_frames_per_s(n, threads, scene, sim.start_pose)[:2]

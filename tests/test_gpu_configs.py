@@ -1,0 +1,139 @@
+"""GPU parity at the other BASELINE configurations (parity cases, not bench lines) and edge cases:
+config 4 (2 097 152-triangle nested tissue mesh, rough surfaces, 10 bounces), config 5 (long
+scanlines / large PSF), degenerate scenes (no mesh, one triangle, two triangles)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _tol(ref):
+    return 1e-4 * np.maximum(np.abs(ref), 1e-3 * np.abs(ref).max())
+
+
+@pytest.fixture(scope="module")
+def O(built):
+    from oracle import oracle_py
+    return oracle_py
+
+
+@pytest.fixture(scope="module")
+def api(built):
+    from mcray_tracing_b200 import api as a
+    return a
+
+
+def _segments_equal(gs, gn, os_, on):
+    assert np.array_equal(gn, on)
+    valid = np.arange(gs.shape[-1])[None, None, :] < on[:, :, None]
+    for name in gs.dtype.names:
+        a, b = gs[name][valid], os_[name][valid]
+        same = (a == b) | (np.isnan(a) & np.isnan(b)) if a.dtype.kind == "f" else (a == b)
+        assert np.all(same), f"{name}: {np.count_nonzero(~same)} of {same.size} differ"
+
+
+def _tiny_scene(tris):
+    tris = np.asarray(tris, np.float32).reshape(-1, 9)
+    mats = np.array([[1.5, 0.5, 0.1, 0.2, 0.1, 1, 1e6, 0], [1.6, 0.7, 0.2, 0.3, 0.2, 1, 1e6, 0]], np.float32)
+    n_mesh = 1 if len(tris) else 0
+    return dict(materials=mats, starting_material=0, mesh_material_inside=np.array([1] * n_mesh, np.int32),
+                mesh_material_outside=np.array([0] * n_mesh, np.int32), mesh_vascular=np.array([0] * n_mesh, np.int32),
+                mesh_deltas=np.zeros((n_mesh, 3), np.float32), tri_offsets=np.array([0, len(tris)][: n_mesh + 1], np.int64),
+                tri_vertices=tris, scaling=1.0, origin=np.zeros(3, np.float32), spacing=np.ones(3, np.float32))
+
+
+@pytest.mark.parametrize("tris", [
+    [],                                                                                   # no mesh at all: every ray misses
+    [[-10.0, -5, -5, -10.0, 5, -5, -10.0, 0, 6]],                                         # one triangle (BVH without inner nodes)
+    [[-10.0, -5, -5, -10.0, 5, -5, -10.0, 0, 6], [-8.0, -5, -5, -8.0, 5, -5, -8.0, 0, 6]],  # two triangles (single inner node)
+])
+def test_degenerate_scenes(api, O, tris):
+    A = _tiny_scene(tris)
+    pose = np.array([-13.5, 0, 0, 0, 0, -90], np.float32)
+    gp = api.default_params(elements=64, samples=2, deterministic=1)
+    op = O.default_params(elements=64, samples=2, deterministic=1)
+    osc = O.OracleScene(A)
+    with api.Simulator(A, gp) as sim:
+        gs, gn = sim.cast_rays(pose, seed=3)
+        rf = sim.simulate(pose[None, :], seed=3)[0]
+    os_, on, _ = osc.cast_rays(op, pose[:3], pose[3:], seed=3, use_bvh=False)
+    _segments_equal(gs, gn, os_, on)
+    ref = osc.simulate_frame(op, pose[:3], pose[3:], seed=3)["rf"].T
+    assert np.all(np.abs(rf - ref) <= _tol(ref) + 1e-12)
+    if len(tris) == 0:
+        assert np.all(gn == 1) and np.all(gs["tri_id"][:, :, 0] == -1)
+    else:
+        assert (gs["tri_id"] >= 0).any()
+
+
+def test_config4_small_rough_nested_shells_path_for_path(api, O):
+    """Config 4 in miniature (8 nested shells, 32 768 triangles, shininess 2, thickness 0.5, vascular
+    shells): 10-bounce stochastic paths identical to the oracle's brute-force closest hit."""
+    from mcray_tracing_b200 import assets
+    A = assets.stress_scene_arrays(shells=8, nu=64, nv=32)
+    pose = np.concatenate([A["transducer_position"], A["transducer_angles"]])
+    gp = api.default_params(elements=64, samples=8)
+    op = O.default_params(elements=64, samples=8)
+    osc = O.OracleScene(A)
+    with api.Simulator(A, gp) as sim:
+        gs, gn = sim.cast_rays(pose, seed=99, frame=2)
+        rf = sim.simulate(pose[None, :], seed=99, first_frame=2)[0]
+    os_, on, _ = osc.cast_rays(op, pose[:3], pose[3:], seed=99, frame=2, use_bvh=False)
+    _segments_equal(gs, gn, os_, on)
+    assert on.max() == 10 and on.mean() > 4                       # paths really survive many bounces
+    assert len(np.unique(gs["media_id"][gs["tri_id"] >= 0])) >= 3
+    ref = osc.simulate_frame(op, pose[:3], pose[3:], seed=99, frame=2)["rf"].T
+    assert np.all(np.abs(rf - ref) <= _tol(ref))
+
+
+def test_config4_full_size_2m_triangles(api, O):
+    """Config 4 at full size (2 097 152 triangles): closest hits and whole paths against the oracle's
+    own BVH (validated against brute force on the small variant and on a subset here)."""
+    from mcray_tracing_b200 import assets
+    A = assets.stress_scene_arrays()
+    assert len(A["tri_vertices"]) == 2097152
+    pose = np.concatenate([A["transducer_position"], A["transducer_angles"]])
+    osc = O.OracleScene(A)
+    rng = np.random.default_rng(8)
+    o = rng.normal(size=(3000, 3)) * 5.0
+    d = rng.normal(size=(3000, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    f, t = o.astype(np.float32), (o + d * 40.0).astype(np.float32)
+    gp = api.default_params(elements=64, samples=8)
+    op = O.default_params(elements=64, samples=8)
+    with api.Simulator(A, gp) as sim:
+        assert sim.info.n_triangles == 2097152
+        tri, mesh, frac, pt, nr = sim.closest_hit(f, t)
+        gs, gn = sim.cast_rays(pose, seed=99, frame=0)
+    for i in range(len(f)):
+        otri, omesh, o7 = osc.closest_hit(f[i], t[i], use_bvh=True)
+        assert tri[i] == otri and frac[i] == o7[0], i
+    for i in range(40):
+        a = osc.closest_hit(f[i], t[i], use_bvh=False)
+        assert a[0] == tri[i]
+    os_, on, _ = osc.cast_rays(op, pose[:3], pose[3:], seed=99, frame=0, use_bvh=True)
+    _segments_equal(gs, gn, os_, on)
+    assert on.max() == 10
+
+
+def test_config5_long_scanlines_and_large_psf(api, O, assets_dirs):
+    """Config 5: a 17.6x finer axial grid (8333 RF samples per scanline; private accumulate columns of
+    33 KB per path) and a 63 x 31 PSF: full frame within tolerance, PSF/envelope bit-exact."""
+    path = assets_dirs["ircad11"] / "santi-liver.scene"
+    A = O.load_scene_py(path)
+    osc = O.OracleScene(A)
+    kw = dict(elements=64, samples=8, axial_scale=17.6, psf_axial=63, psf_lateral=31)
+    gp, op = api.default_params(**kw), O.default_params(**kw)
+    with api.Simulator(path, gp) as sim:
+        assert sim.rows == 8333
+        pose = sim.start_pose
+        rf = sim.simulate(pose[None, :], seed=7, first_frame=1)[0]
+        st = sim.stats()
+        rng = np.random.default_rng(5)
+        img = rng.normal(size=(8192, 256)).astype(np.float32)        # [rows][cols], oracle layout
+        ax = rng.normal(size=63).astype(np.float32); lat = rng.random(31).astype(np.float32)
+        g = sim.postprocess(img.T, ax, lat)
+    o = osc.simulate_frame(op, pose[:3], pose[3:], seed=7, frame=1)
+    assert st.march_steps == o["steps"] and st.segments == o["tests"]
+    ref = o["rf"].T
+    assert np.all(np.abs(rf - ref) <= _tol(ref)), np.abs(rf - ref).max()
+    assert np.array_equal(g.T, O.envelope(O.convolve(img, ax, lat)))
