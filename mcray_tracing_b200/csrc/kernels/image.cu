@@ -71,6 +71,7 @@ __device__ __noinline__ int column_flush_slow(float* col, int S, int written, in
 // Per-thread writer of one private RF column; all members live in registers (everything inlines).
 struct ColumnWriter {
     float* col;          // row r lives at col[r * S]
+    float* wptr;         // = col + written * S: where the next in-order row goes
     int S, rows;
     int written;         // rows [0, written) have been stored
     int cur_row;         // row being accumulated in cur_acc (-1: none yet)
@@ -92,9 +93,14 @@ struct ColumnWriter {
         } else if (row >= rows) {
             return;
         }
+        add_row(echo, row);
+    }
+    // the echo lands in RF row `row` (0 <= row < rows already established)
+    __device__ __forceinline__ void add_row(float echo, int row)
+    {
         if (row == cur_row) { cur_acc += echo; return; }
-        if (cur_row == written) { col[(size_t)cur_row * S] = cur_acc; written = cur_row + 1; }   // the common case: next row
-        else written = column_flush_slow(col, S, written, cur_row, cur_acc);
+        if (cur_row == written) { *wptr = cur_acc; wptr += S; written++; }                        // the common case: next row
+        else { written = column_flush_slow(col, S, written, cur_row, cur_acc); wptr = col + (size_t)written * S; }
         cur_row = row;
         cur_acc = echo;                                                                   // 0 + echo
     }
@@ -121,7 +127,7 @@ __global__ void __launch_bounds__(128) k_accumulate(const SceneDev sc, const Acq
         ColumnWriter w;
         w.S = S; w.rows = aq.rows;
         w.col = columns + (size_t)scanline * aq.rows * S + (p - scanline * S);
-        w.written = 0; w.cur_row = -1; w.cur_acc = 0.0f;
+        w.wptr = w.col; w.written = 0; w.cur_row = -1; w.cur_acc = 0.0f;
         w.row_period = aq.row_period_us; w.inv_row_period = aq.inv_row_period;
         const float axres_f = aq.axres_f;
         const double time_step = aq.time_step_us;
@@ -129,6 +135,14 @@ __global__ void __launch_bounds__(128) k_accumulate(const SceneDev sc, const Acq
         const double max_travel_time = aq.max_travel_time_us;
         const float samples_f = (float)(size_t)S;
         const float vres = aq.vol_resolution, inv_vres = 1.0f / aq.vol_resolution;
+        // One march step advances the RF row by `ratio` = time_step / row_period (1.00069 for the reference's
+        // 322.22 um step on a 322 um row grid).  When 1 <= ratio < 1.2 the rows of an unrolled block are
+        // row0, row0+1, ... as long as the fractional row position of its first step stays below
+        // block_safe_hi; then no per-step fp64 row computation is needed (guard 1e-6 >> the ~1e-12 rounding
+        // of the iterated fp64 time chain and of the product with the reciprocal).
+        const double row_delta = aq.time_step_us * aq.inv_row_period - 1.0;
+        const bool fast_rows = row_delta >= 0.0 && row_delta < 0.2;
+        const double block_safe_hi = 1.0 - 1e-6 - (double)(MCRT_ACC_UNROLL - 1) * row_delta;
 
         const int ns = nseg[p];
         for (int k = 0; k < ns; k++) {
@@ -159,6 +173,12 @@ __global__ void __launch_bounds__(128) k_accumulate(const SceneDev sc, const Acq
             const double safe_d = (max_travel_time - time_elapsed) * inv_time_step - 2.0;
             int n_safe = safe_d > 0.0 ? (safe_d < 2.0e9 ? (int)safe_d : 2000000000) : 0;
             if (n_safe > remaining) n_safe = remaining;
+            // a medium with sigma == 0 and mu0 == 0 (coupling gel) scatters exactly +0 at every voxel: adding +0
+            // never changes a row, so only the time chain (which bounds the step count) is advanced
+            if (media.sigma == 0.0f && media.mu0 == 0.0f) {
+                while (remaining > 0 && time_elapsed < max_travel_time) { time_elapsed = time_elapsed + time_step; remaining--; my_steps++; }
+                n_safe = 0;
+            }
             const int n_blocks = n_safe / MCRT_ACC_UNROLL;
             for (int b = 0; b < n_blocks; b++) {
                 uint32_t idx[MCRT_ACC_UNROLL];
@@ -170,13 +190,26 @@ __global__ void __launch_bounds__(128) k_accumulate(const SceneDev sc, const Acq
                 float2 vox[MCRT_ACC_UNROLL];
 #pragma unroll
                 for (int u = 0; u < MCRT_ACC_UNROLL; u++) vox[u] = __ldg(&volume[idx[u]]);      // (noise, probability)
+                const double rowd0 = time_elapsed * w.inv_row_period;
+                const int row0 = __double2int_rd(rowd0);
+                const double f0 = rowd0 - (double)row0;
+                if (fast_rows && f0 >= 1e-6 && f0 <= block_safe_hi && row0 + MCRT_ACC_UNROLL <= w.rows) {
 #pragma unroll
-                for (int u = 0; u < MCRT_ACC_UNROLL; u++) {
-                    // get_scattering(mu1, mu0, sigma, ...): density = mu1, mu = mu0 (main.cpp:126 vs volume.h:46)
-                    const float scattering = vox[u].y >= media.mu1 ? vox[u].x * media.sigma + media.mu0 : 0.0f;
-                    w.add_echo(intensity * scattering, time_elapsed);
-                    time_elapsed = time_elapsed + time_step;
-                    intensity *= decay;
+                    for (int u = 0; u < MCRT_ACC_UNROLL; u++) {
+                        // get_scattering(mu1, mu0, sigma, ...): density = mu1, mu = mu0 (main.cpp:126 vs volume.h:46)
+                        const float scattering = vox[u].y >= media.mu1 ? vox[u].x * media.sigma + media.mu0 : 0.0f;
+                        w.add_row(intensity * scattering, row0 + u);
+                        time_elapsed = time_elapsed + time_step;
+                        intensity *= decay;
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < MCRT_ACC_UNROLL; u++) {
+                        const float scattering = vox[u].y >= media.mu1 ? vox[u].x * media.sigma + media.mu0 : 0.0f;
+                        w.add_echo(intensity * scattering, time_elapsed);
+                        time_elapsed = time_elapsed + time_step;
+                        intensity *= decay;
+                    }
                 }
             }
             remaining -= n_blocks * MCRT_ACC_UNROLL;

@@ -189,7 +189,10 @@ __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq
 }
 
 template <bool FIRST>
-__global__ void __launch_bounds__(128) k_bounce(const SceneDev sc, const AcqDev aq, const FrameDev fr, const TraceBuffers tb, const int bounce)
+#ifndef MCRT_BOUNCE_MIN_CTAS
+#define MCRT_BOUNCE_MIN_CTAS 6      // 80 registers, 24 warps/SM: measured best of 4/5/6/8 (profiles/r01_traversal_ab.txt)
+#endif
+__global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const SceneDev sc, const AcqDev aq, const FrameDev fr, const TraceBuffers tb, const int bounce)
 {
     __shared__ SharedScene sh;
     load_shared_scene(sc, sh);
