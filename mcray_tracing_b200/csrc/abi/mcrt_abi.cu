@@ -209,7 +209,8 @@ void enqueue_pipeline(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* l
 
 int count_pipeline_launches(const mcrt_ctx* c, bool want_scan)
 {
-    return c->aq.max_depth + 2 + 3 + (c->params.rf_layout == 1 ? 1 : 0) + (want_scan ? 1 : 0);
+    return c->aq.max_depth + 2 + post_launch_count(c->aq.elements, c->aq.rows, c->params.psf_lateral, 3, 1) + (c->params.rf_layout == 1 ? 1 : 0) +
+           (want_scan ? 1 : 0);
 }
 
 void run_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches)
@@ -403,6 +404,7 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     CUDA_TRY(cudaMemcpy(c->d_map_x, mx.data(), sizeof(float) * mx.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(c->d_map_y, my.data(), sizeof(float) * my.size(), cudaMemcpyHostToDevice));
     c->d_volume = device_volume(device, c->stream);
+    CUDA_TRY(init_image_kernels());
 
     dev_alloc(c->d_seed_frame, 2);
     dev_alloc(c->d_trav, 2);

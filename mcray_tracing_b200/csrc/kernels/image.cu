@@ -25,6 +25,19 @@ __device__ __noinline__ uint32_t voxel_linear_exact(float x, float y, float z, f
 // Same result without three IEEE divisions on the hot path: q~ = coord * (1/resolution) is within
 // 2 ulp of fl(coord/resolution), so both truncate to the same integer unless q~ lies within a (much
 // wider, 1e-6 relative) guard band of an integer -- only then are the exact quotients evaluated.
+// `risky` is OR-ed with "the fast result may be wrong"; the caller then re-evaluates with voxel_linear_exact.
+__device__ __forceinline__ uint32_t voxel_linear_fast(float3 p, float inv_resolution, bool& risky)
+{
+    const float qx = p.x * inv_resolution, qy = p.y * inv_resolution, qz = p.z * inv_resolution;
+    const int ix = __float2int_rz(qx), iy = __float2int_rz(qy), iz = __float2int_rz(qz);
+    const float ax = fabsf(qx - (float)ix), ay = fabsf(qy - (float)iy), az = fabsf(qz - (float)iz);   // [0,1) unless saturated
+    const float amin = fminf(fminf(ax, ay), az), amax = fmaxf(fmaxf(ax, ay), az);
+    const float qmax = fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
+    const float eps = qmax * 1e-6f + 1e-30f;
+    risky = risky || !(amin >= eps && amax <= 1.0f - eps && qmax < 2.0e9f);
+    return ((uint32_t)(ix & 255) << 16) | ((uint32_t)(iy & 255) << 8) | (uint32_t)(iz & 255);
+}
+
 __device__ __forceinline__ uint32_t voxel_linear(float3 p, float resolution, float inv_resolution)
 {
     const float qx = p.x * inv_resolution, qy = p.y * inv_resolution, qz = p.z * inv_resolution;
@@ -111,7 +124,10 @@ struct ColumnWriter {
     }
 };
 
-__global__ void __launch_bounds__(128) k_accumulate(const SceneDev sc, const AcqDev aq, const float2* __restrict__ volume,
+#ifndef MCRT_ACC_MIN_CTAS
+#define MCRT_ACC_MIN_CTAS 8      // 64 registers, 32 warps/SM: measured 9 % faster than 6 (78 registers)
+#endif
+__global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate(const SceneDev sc, const AcqDev aq, const float2* __restrict__ volume,
                                                    const DevSegment* __restrict__ segments, const int32_t* __restrict__ nseg,
                                                    const int n_paths, float* __restrict__ columns,
                                                    unsigned long long* __restrict__ steps_total)
@@ -182,10 +198,17 @@ __global__ void __launch_bounds__(128) k_accumulate(const SceneDev sc, const Acq
             const int n_blocks = n_safe / MCRT_ACC_UNROLL;
             for (int b = 0; b < n_blocks; b++) {
                 uint32_t idx[MCRT_ACC_UNROLL];
+                float3 pts[MCRT_ACC_UNROLL];
+                bool risky = false;                 // one guard branch per block instead of one per step
 #pragma unroll
                 for (int u = 0; u < MCRT_ACC_UNROLL; u++) {
-                    idx[u] = voxel_linear(point, vres, inv_vres);
+                    pts[u] = point;
+                    idx[u] = voxel_linear_fast(point, inv_vres, risky);
                     point = v_add(point, delta_step);                                           // main.cpp:131
+                }
+                if (risky) {
+#pragma unroll
+                    for (int u = 0; u < MCRT_ACC_UNROLL; u++) idx[u] = voxel_linear_exact(pts[u].x, pts[u].y, pts[u].z, vres);
                 }
                 float2 vox[MCRT_ACC_UNROLL];
 #pragma unroll
@@ -372,6 +395,126 @@ __global__ void __launch_bounds__(32 * MCRT_ENV_WARPS) k_envelope(const float* _
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused post-processing for scanlines that fit shared memory (the reference's 465-row images):
+// one CTA stages TC output scanlines plus the Kl-1 halo scanlines to their right (whole columns, so
+// the forward-looking axial taps need no row halo), runs the axial pass and the lateral pass out of
+// shared memory and finishes with the envelope, one warp per scanline -- the image is read from HBM
+// once and written once (8 B/pixel) instead of three round trips.  Same arithmetic, same order, same
+// untouched borders as k_psf_axial / k_psf_lateral / k_envelope (bit-identical results).
+// ------------------------------------------------------------------------------------------------
+#define MCRT_FUSED_THREADS 256
+#define MCRT_FUSED_MAX_CHUNKS 64     // rows <= 2048 on this path
+
+__device__ __forceinline__ unsigned peak_mask_smem(const float* I, int rows, int c, int lane)
+{
+    const int i = (c << 5) + lane;
+    const float v = i < rows ? I[i] : 0.0f;
+    const float vm = (i >= 1 && i < rows) ? I[i - 1] : 0.0f;
+    const float vp = (i + 1 < rows) ? I[i + 1] : 0.0f;
+    const bool peak = (i >= 1) && (i + 1 < rows) && (vm < v) && !(v < vp);
+    return __ballot_sync(0xffffffffu, peak);
+}
+
+__global__ void __launch_bounds__(MCRT_FUSED_THREADS) k_post_fused(const float* __restrict__ in, const int cols, const int rows,
+                                                                  const float* __restrict__ ax_taps, const int ka,
+                                                                  const float* __restrict__ lat_taps, const int kl, const int flags,
+                                                                  const int TC, float* __restrict__ out)
+{
+    extern __shared__ float sm[];
+    __shared__ float s_taps_a[MCRT_MAX_TAPS], s_taps_l[MCRT_MAX_TAPS];
+    __shared__ unsigned s_mask[MCRT_FUSED_THREADS / 32][MCRT_FUSED_MAX_CHUNKS];
+    __shared__ int s_next[MCRT_FUSED_THREADS / 32][MCRT_FUSED_MAX_CHUNKS];
+    const bool conv = (flags & 1) != 0, env = (flags & 2) != 0;
+    const int W = conv ? TC + kl - 1 : TC;                 // staged scanlines
+    float* s_in = sm;                                      // [W][rows]
+    float* s_ax = s_in + (size_t)W * rows;                 // [W][rows]   (only with conv)
+    float* s_out = conv ? s_ax + (size_t)W * rows : s_in;  // [TC][rows]
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int c0 = blockIdx.x * TC;
+    const size_t img = (size_t)blockIdx.y * cols * rows;
+    if (conv) {
+        for (int i = tid; i < ka; i += NT) s_taps_a[i] = ax_taps[i];
+        for (int i = tid; i < kl; i += NT) s_taps_l[i] = lat_taps[i];
+    }
+    // stage: consecutive threads read consecutive rows of a scanline (coalesced 128 B per warp)
+    for (int i = tid; i < W * rows; i += NT) {
+        const int c = i / rows, r = i - c * rows;
+        const int gc = c0 + c;
+        s_in[i] = gc < cols ? __ldg(&in[img + (size_t)gc * rows + r]) : 0.0f;
+    }
+    __syncthreads();
+    if (conv) {
+        // axial pass (rfimage.h:97-108): forward-looking taps, sequential fp32 sum
+        for (int i = tid; i < W * rows; i += NT) {
+            const int c = i / rows, r = i - c * rows;
+            if (r < ka || r >= rows - ka) continue;
+            const float* src = s_in + i;
+            float convolution = 0;
+            for (int k = 0; k < ka; k++) convolution += src[k] * s_taps_a[k];
+            s_ax[i] = convolution;
+        }
+        __syncthreads();
+        // lateral pass (rfimage.h:111-122) + untouched borders (B-9)
+        for (int i = tid; i < TC * rows; i += NT) {
+            const int c = i / rows, r = i - c * rows;
+            const int gc = c0 + c;
+            float v = s_in[i];
+            if (r >= ka && r < rows - ka && gc >= kl / 2 && gc < cols - kl) {
+                const float* src = s_ax + i;
+                float convolution = 0;
+                for (int k = 0; k < kl; k++) convolution += src[(size_t)k * rows] * s_taps_l[k];
+                v = convolution;
+            }
+            s_out[i] = v;
+        }
+        __syncthreads();
+    }
+    if (!env) {
+        for (int i = tid; i < TC * rows; i += NT) {
+            const int c = i / rows, r = i - c * rows;
+            if (c0 + c < cols) out[img + (size_t)(c0 + c) * rows + r] = s_out[i];
+        }
+        return;
+    }
+    // envelope (rfimage.h:54-91): one warp per scanline, see k_envelope
+    const int lane = tid & 31, w = tid >> 5;
+    const int n_chunks = (rows + 31) >> 5;
+    for (int c = w; c < TC; c += NT / 32) {
+        if (c0 + c >= cols) continue;                      // warp-uniform
+        const float* I = s_out + (size_t)c * rows;
+        float* O = out + img + (size_t)(c0 + c) * rows;
+        int next = rows;
+        for (int ch = n_chunks - 1; ch >= 0; ch--) {
+            const unsigned m = peak_mask_smem(I, rows, ch, lane);
+            if (lane == 0) { s_mask[w][ch] = m; s_next[w][ch] = next; }
+            if (m) next = (ch << 5) + (__ffs(m) - 1);
+        }
+        __syncwarp();
+        int last_peak = 0;
+        for (int ch = 0; ch < n_chunks; ch++) {
+            const unsigned mask = s_mask[w][ch];
+            const int i = (ch << 5) + lane;
+            const unsigned le = mask & (0xffffffffu >> (31 - lane));
+            const int p = le ? (ch << 5) + (31 - __clz(le)) : last_peak;
+            const unsigned gt = lane == 31 ? 0u : (mask & (0xffffffffu << (lane + 1)));
+            const int q = gt ? (ch << 5) + (__ffs(gt) - 1) : s_next[w][ch];
+            if (i < rows) {
+                float r = I[i];
+                if (q < rows) {
+                    const float last = (p == 0) ? I[0] : fabsf(I[p]);
+                    const float new_peak = fabsf(I[q]);
+                    const float alpha = ((float)i - (float)p) / ((float)q - (float)p);
+                    r = last * (1 - alpha) + new_peak * alpha;
+                }
+                O[i] = r;
+            }
+            if (mask) last_peak = (ch << 5) + (31 - __clz(mask));
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(256) k_copy(const float* __restrict__ in, const int64_t n, float* __restrict__ out)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i];
@@ -458,11 +601,53 @@ cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2
     return cudaGetLastError();
 }
 
+// shared-memory budget of the fused path and its tile width: the widest TC in {32,16,8,4} whose staging fits
+#define MCRT_FUSED_SMEM_LIMIT (200 * 1024)
+static int fused_tile_cols(int rows, int kl, int flags, size_t* smem)
+{
+    if (rows > 32 * MCRT_FUSED_MAX_CHUNKS) return 0;
+    for (int tc = 32; tc >= 4; tc >>= 1) {
+        const size_t w = (flags & 1) ? (size_t)(tc + kl - 1) : (size_t)tc;
+        const size_t bytes = sizeof(float) * rows * ((flags & 1) ? (2 * w + tc) : w);
+        if (bytes <= MCRT_FUSED_SMEM_LIMIT) { *smem = bytes; return tc; }
+    }
+    return 0;
+}
+
+cudaError_t init_image_kernels()
+{
+    // per-device function attribute; must not be issued inside a stream capture
+    return cudaFuncSetAttribute(k_post_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, MCRT_FUSED_SMEM_LIMIT);
+}
+
+int post_launch_count(int cols, int rows, int n_lateral, int flags, int n_images)
+{
+    size_t smem = 0;
+    (void)cols;
+    if ((flags & 3) && fused_tile_cols(rows, n_lateral, flags, &smem) > 0 && n_images <= 65535) return 1;
+    return ((flags & 1) ? 2 : 0) + (((flags & 2) || !(flags & 1)) ? 1 : 0);
+}
+
 void launch_post(const float* d_in, int n_images, int cols, int rows, const float* d_axial, int n_axial, const float* d_lateral,
                  int n_lateral, int flags, float* d_tmp0, float* d_tmp1, float* d_out, cudaStream_t stream, int* launches)
 {
     const int64_t n_scanlines = (int64_t)n_images * cols;
     const int64_t total = n_scanlines * rows;
+    size_t smem = 0;
+    int tc = (flags & 3) ? fused_tile_cols(rows, n_lateral, flags, &smem) : 0;
+    // few images (latency mode): narrower tiles so the grid still covers the 148 SMs
+    while (tc > 4 && (int64_t)((cols + tc - 1) / tc) * n_images < 2 * 148) {
+        tc >>= 1;
+        const size_t w = (flags & 1) ? (size_t)(tc + n_lateral - 1) : (size_t)tc;
+        smem = sizeof(float) * rows * ((flags & 1) ? (2 * w + tc) : w);
+    }
+    if (tc > 0 && n_images <= 65535) {
+        // whole scanlines fit shared memory: one pass over HBM
+        dim3 grid((cols + tc - 1) / tc, n_images, 1);
+        k_post_fused<<<grid, MCRT_FUSED_THREADS, smem, stream>>>(d_in, cols, rows, d_axial, n_axial, d_lateral, n_lateral, flags, tc, d_out);
+        if (launches) (*launches)++;
+        return;
+    }
     const float* cur = d_in;
     if (flags & 1) {
         k_psf_axial<<<grid1d(total, 256), 256, 0, stream>>>(cur, n_scanlines, rows, d_axial, n_axial, d_tmp0);

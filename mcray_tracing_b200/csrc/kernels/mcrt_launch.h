@@ -52,7 +52,10 @@ void launch_elements(const AcqDev& aq, const FrameDev& fr, float* d_pos, float* 
 // main.cpp:106-144: segments -> raw RF, scanline-major [n_poses*elements][rows]
 // d_columns: accumulate_columns_bytes() bytes of HBM scratch: one private RF column per path,
 // columns[scanline][row][sample].
+cudaError_t init_image_kernels();      // once per device, outside any stream capture
 size_t accumulate_columns_bytes(const AcqDev& aq, int n_poses);
+// kernels launch_post will issue for this geometry (1 = fused shared-memory path, 3 = axial + lateral + envelope)
+int post_launch_count(int cols, int rows, int n_lateral, int flags, int n_images);
 cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2* d_volume, const DevSegment* d_segments,
                               const int32_t* d_nseg, int n_poses, float* d_rf, unsigned long long* d_steps, float* d_columns,
                               cudaStream_t stream, int* launches);
