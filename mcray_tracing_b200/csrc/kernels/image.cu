@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(32 * MCRT_ENV_WARPS) k_envelope(const float* _
 // once and written once (8 B/pixel) instead of three round trips.  Same arithmetic, same order, same
 // untouched borders as k_psf_axial / k_psf_lateral / k_envelope (bit-identical results).
 // ------------------------------------------------------------------------------------------------
-#define MCRT_FUSED_THREADS 256
+#define MCRT_FUSED_THREADS 512
 #define MCRT_FUSED_MAX_CHUNKS 64     // rows <= 2048 on this path
 
 __device__ __forceinline__ unsigned peak_mask_smem(const float* I, int rows, int c, int lane)
@@ -426,64 +426,73 @@ __global__ void __launch_bounds__(MCRT_FUSED_THREADS) k_post_fused(const float* 
     __shared__ unsigned s_mask[MCRT_FUSED_THREADS / 32][MCRT_FUSED_MAX_CHUNKS];
     __shared__ int s_next[MCRT_FUSED_THREADS / 32][MCRT_FUSED_MAX_CHUNKS];
     const bool conv = (flags & 1) != 0, env = (flags & 2) != 0;
-    const int W = conv ? TC + kl - 1 : TC;                 // staged scanlines
-    float* s_in = sm;                                      // [W][rows]
-    float* s_ax = s_in + (size_t)W * rows;                 // [W][rows]   (only with conv)
-    float* s_out = conv ? s_ax + (size_t)W * rows : s_in;  // [TC][rows]
-    const int tid = threadIdx.x, NT = blockDim.x;
+    const int W = conv ? TC + kl - 1 : TC;                 // staged scanlines (tile + right halo)
+    float* s_in = sm;                                      // [W][rows]   raw scanlines; the first TC are overwritten
+    float* s_ax = sm + (size_t)W * rows;                   // [W][rows]   axial pass result (conv only)
+    float* s_out = s_in;                                   //             in place by the lateral pass
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, NW = blockDim.x >> 5;
     const int c0 = blockIdx.x * TC;
-    const size_t img = (size_t)blockIdx.y * cols * rows;
+    const float* img_in = in + (size_t)blockIdx.y * cols * rows;
+    float* img_out = out + (size_t)blockIdx.y * cols * rows;
     if (conv) {
-        for (int i = tid; i < ka; i += NT) s_taps_a[i] = ax_taps[i];
-        for (int i = tid; i < kl; i += NT) s_taps_l[i] = lat_taps[i];
+        for (int i = tid; i < ka; i += blockDim.x) s_taps_a[i] = ax_taps[i];
+        for (int i = tid; i < kl; i += blockDim.x) s_taps_l[i] = lat_taps[i];
     }
-    // stage: consecutive threads read consecutive rows of a scanline (coalesced 128 B per warp)
-    for (int i = tid; i < W * rows; i += NT) {
-        const int c = i / rows, r = i - c * rows;
+    // stage: a warp walks one scanline, lanes on consecutive rows (coalesced); all loads are independent,
+    // so the L2 latency is paid once per warp, not once per tap
+    for (int c = w; c < W; c += NW) {
         const int gc = c0 + c;
-        s_in[i] = gc < cols ? __ldg(&in[img + (size_t)gc * rows + r]) : 0.0f;
+        float* dst = s_in + (size_t)c * rows;
+        if (gc < cols) {
+            const float* src = img_in + (size_t)gc * rows;
+            for (int r = lane; r < rows; r += 32) dst[r] = __ldg(&src[r]);
+        }
     }
     __syncthreads();
     if (conv) {
         // axial pass (rfimage.h:97-108): forward-looking taps, sequential fp32 sum
-        for (int i = tid; i < W * rows; i += NT) {
-            const int c = i / rows, r = i - c * rows;
-            if (r < ka || r >= rows - ka) continue;
-            const float* src = s_in + i;
-            float convolution = 0;
-            for (int k = 0; k < ka; k++) convolution += src[k] * s_taps_a[k];
-            s_ax[i] = convolution;
+        for (int c = w; c < W; c += NW) {
+            if (c0 + c >= cols) continue;
+            const float* src = s_in + (size_t)c * rows;
+            float* dst = s_ax + (size_t)c * rows;
+            for (int r = ka + lane; r < rows - ka; r += 32) {
+                float convolution = 0;
+#pragma unroll 4
+                for (int k = 0; k < ka; k++) convolution += src[r + k] * s_taps_a[k];
+                dst[r] = convolution;
+            }
         }
         __syncthreads();
-        // lateral pass (rfimage.h:111-122) + untouched borders (B-9)
-        for (int i = tid; i < TC * rows; i += NT) {
-            const int c = i / rows, r = i - c * rows;
+        // lateral pass (rfimage.h:111-122), in place over the raw tile; borders keep the raw samples (B-9)
+        for (int c = w; c < TC; c += NW) {
             const int gc = c0 + c;
-            float v = s_in[i];
-            if (r >= ka && r < rows - ka && gc >= kl / 2 && gc < cols - kl) {
-                const float* src = s_ax + i;
+            if (gc >= cols || !(gc >= kl / 2 && gc < cols - kl)) continue;
+            float* dst = s_out + (size_t)c * rows;
+            for (int r = ka + lane; r < rows - ka; r += 32) {
+                const float* src = s_ax + (size_t)c * rows + r;
                 float convolution = 0;
+#pragma unroll 4
                 for (int k = 0; k < kl; k++) convolution += src[(size_t)k * rows] * s_taps_l[k];
-                v = convolution;
+                dst[r] = convolution;
             }
-            s_out[i] = v;
         }
         __syncthreads();
     }
     if (!env) {
-        for (int i = tid; i < TC * rows; i += NT) {
-            const int c = i / rows, r = i - c * rows;
-            if (c0 + c < cols) out[img + (size_t)(c0 + c) * rows + r] = s_out[i];
+        for (int c = w; c < TC; c += NW) {
+            const int gc = c0 + c;
+            if (gc >= cols) continue;
+            const float* src = s_out + (size_t)c * rows;
+            for (int r = lane; r < rows; r += 32) img_out[(size_t)gc * rows + r] = src[r];
         }
         return;
     }
     // envelope (rfimage.h:54-91): one warp per scanline, see k_envelope
-    const int lane = tid & 31, w = tid >> 5;
     const int n_chunks = (rows + 31) >> 5;
-    for (int c = w; c < TC; c += NT / 32) {
+    for (int c = w; c < TC; c += NW) {
         if (c0 + c >= cols) continue;                      // warp-uniform
         const float* I = s_out + (size_t)c * rows;
-        float* O = out + img + (size_t)(c0 + c) * rows;
+        float* O = img_out + (size_t)(c0 + c) * rows;
         int next = rows;
         for (int ch = n_chunks - 1; ch >= 0; ch--) {
             const unsigned m = peak_mask_smem(I, rows, ch, lane);
@@ -601,14 +610,18 @@ cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2
     return cudaGetLastError();
 }
 
-// shared-memory budget of the fused path and its tile width: the widest TC in {32,16,8,4} whose staging fits
-#define MCRT_FUSED_SMEM_LIMIT (200 * 1024)
+// shared-memory budget of the fused path
+#define MCRT_FUSED_SMEM_LIMIT (100 * 1024)     // + ~12 KB static: two CTAs of 512 threads per SM
+static size_t fused_smem_bytes(int rows, int kl, int flags, int tc)
+{
+    return sizeof(float) * (size_t)rows * ((flags & 1) ? (size_t)(2 * (tc + kl - 1)) : (size_t)tc);
+}
+// widest tile (<= 32 scanlines, >= 4) whose staging fits; 0 = use the unfused kernels
 static int fused_tile_cols(int rows, int kl, int flags, size_t* smem)
 {
     if (rows > 32 * MCRT_FUSED_MAX_CHUNKS) return 0;
-    for (int tc = 32; tc >= 4; tc >>= 1) {
-        const size_t w = (flags & 1) ? (size_t)(tc + kl - 1) : (size_t)tc;
-        const size_t bytes = sizeof(float) * rows * ((flags & 1) ? (2 * w + tc) : w);
+    for (int tc = 32; tc >= 4; tc--) {
+        const size_t bytes = fused_smem_bytes(rows, kl, flags, tc);
         if (bytes <= MCRT_FUSED_SMEM_LIMIT) { *smem = bytes; return tc; }
     }
     return 0;
@@ -637,9 +650,8 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
     int tc = (flags & 3) ? fused_tile_cols(rows, n_lateral, flags, &smem) : 0;
     // few images (latency mode): narrower tiles so the grid still covers the 148 SMs
     while (tc > 4 && (int64_t)((cols + tc - 1) / tc) * n_images < 2 * 148) {
-        tc >>= 1;
-        const size_t w = (flags & 1) ? (size_t)(tc + n_lateral - 1) : (size_t)tc;
-        smem = sizeof(float) * rows * ((flags & 1) ? (2 * w + tc) : w);
+        tc = tc > 8 ? tc / 2 : 4;
+        smem = fused_smem_bytes(rows, n_lateral, flags, tc);
     }
     if (tc > 0 && n_images <= 65535) {
         // whole scanlines fit shared memory: one pass over HBM
