@@ -26,7 +26,7 @@ __device__ __noinline__ uint32_t voxel_linear_exact(float x, float y, float z, f
 // 2 ulp of fl(coord/resolution), so both truncate to the same integer unless q~ lies within a (much
 // wider, 1e-6 relative) guard band of an integer -- only then are the exact quotients evaluated.
 // `risky` is OR-ed with "the fast result may be wrong"; the caller then re-evaluates with voxel_linear_exact.
-__device__ __forceinline__ uint32_t voxel_linear_fast(float3 p, float inv_resolution, bool& risky)
+__device__ __forceinline__ uint32_t voxel_linear_fast(float3 p, float inv_resolution, int& risky)
 {
     const float qx = p.x * inv_resolution, qy = p.y * inv_resolution, qz = p.z * inv_resolution;
     const int ix = __float2int_rz(qx), iy = __float2int_rz(qy), iz = __float2int_rz(qz);
@@ -34,7 +34,8 @@ __device__ __forceinline__ uint32_t voxel_linear_fast(float3 p, float inv_resolu
     const float amin = fminf(fminf(ax, ay), az), amax = fmaxf(fmaxf(ax, ay), az);
     const float qmax = fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
     const float eps = qmax * 1e-6f + 1e-30f;
-    risky = risky || !(amin >= eps && amax <= 1.0f - eps && qmax < 2.0e9f);
+    // branch-free: the three conditions are evaluated as predicates and OR-ed into the flag
+    risky |= (int)(!(amin >= eps)) | (int)(!(amax <= 1.0f - eps)) | (int)(!(qmax < 2.0e9f));
     return ((uint32_t)(ix & 255) << 16) | ((uint32_t)(iy & 255) << 8) | (uint32_t)(iz & 255);
 }
 
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate(const Sce
             for (int b = 0; b < n_blocks; b++) {
                 uint32_t idx[MCRT_ACC_UNROLL];
                 float3 pts[MCRT_ACC_UNROLL];
-                bool risky = false;                 // one guard branch per block instead of one per step
+                int risky = 0;                      // one guard branch per block instead of one per step
 #pragma unroll
                 for (int u = 0; u < MCRT_ACC_UNROLL; u++) {
                     pts[u] = point;
@@ -217,13 +218,30 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate(const Sce
                 const int row0 = __double2int_rd(rowd0);
                 const double f0 = rowd0 - (double)row0;
                 if (fast_rows && f0 >= 1e-6 && f0 <= block_safe_hi && row0 + MCRT_ACC_UNROLL <= w.rows) {
+                    float echo[MCRT_ACC_UNROLL];
 #pragma unroll
                     for (int u = 0; u < MCRT_ACC_UNROLL; u++) {
                         // get_scattering(mu1, mu0, sigma, ...): density = mu1, mu = mu0 (main.cpp:126 vs volume.h:46)
                         const float scattering = vox[u].y >= media.mu1 ? vox[u].x * media.sigma + media.mu0 : 0.0f;
-                        w.add_row(intensity * scattering, row0 + u);
+                        echo[u] = intensity * scattering;
                         time_elapsed = time_elapsed + time_step;
                         intensity *= decay;
+                    }
+                    w.add_row(echo[0], row0);
+                    if (w.written == row0) {
+                        // in-order streaming: rows row0 .. row0+U-1 receive exactly one echo each from this
+                        // block; every closed row goes straight to the column, the last one stays in the register
+#pragma unroll
+                        for (int u = 1; u < MCRT_ACC_UNROLL; u++) {
+                            *w.wptr = w.cur_acc;
+                            w.wptr += w.S;
+                            w.cur_acc = echo[u];
+                        }
+                        w.written = row0 + MCRT_ACC_UNROLL - 1;
+                        w.cur_row = row0 + MCRT_ACC_UNROLL - 1;
+                    } else {
+#pragma unroll
+                        for (int u = 1; u < MCRT_ACC_UNROLL; u++) w.add_row(echo[u], row0 + u);
                     }
                 } else {
 #pragma unroll
