@@ -374,7 +374,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=64)
+    ap.add_argument("--frames-per-step", type=int, default=256)
     ap.add_argument("--cpu-frames", type=int, default=60, help="frames per CPU-baseline variant (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -134,7 +134,9 @@ const char* mcrt_last_error(void); /* thread-local, never NULL */
 int mcrt_get_info(const mcrt_ctx* ctx, mcrt_info* info);
 int mcrt_get_stats(const mcrt_ctx* ctx, mcrt_stats* stats);
 /* options: "profile_stages"=0/1 (per-stage events, disables the CUDA graph), "use_graph"=0/1,
- * "max_batch_poses"=N, "count_traversal"=0/1 (BVH work counters in mcrt_stats) */
+ * "max_batch_poses"=N, "overlap"=0/1 (two-stream software pipelining of pose sub-batches inside the graph; measured slower than one stream, default 0),
+ * "count_traversal"=0/1 (BVH work counters in mcrt_stats), "bvh_builder"=0 device LBVH
+ * (default) / 1 host binned-SAH tree (rebuilds the acceleration structure in place) */
 int mcrt_set_option(mcrt_ctx* ctx, const char* name, int64_t value);
 
 /* replaces one iteration of main.cpp:92-152 per pose: rf_image.clear(); scene.cast_rays();

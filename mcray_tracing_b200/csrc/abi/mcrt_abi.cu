@@ -15,6 +15,7 @@
 
 #include "../../../include/mcrt.h"
 #include "../host/mcrt_host.h"
+#include "../host/sah_builder.h"
 #include "../kernels/mcrt_launch.h"
 
 using namespace mcrt;
@@ -93,6 +94,9 @@ struct mcrt_ctx {
     AcqDev aq;
     SceneDev sc;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;        // second branch of the captured two-stream pipeline
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sub[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool overlap = false;                  // software-pipeline sub-batches inside the graph (measured slower: off)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_up = nullptr;
     bool upload_pending = false;
 
@@ -142,6 +146,9 @@ struct mcrt_ctx {
 namespace {
 
 const int kMaxBatchesPerCall = 4096;
+const int kMaxSub = 4;               // sub-batches of the two-stream pipeline
+const int kMinPosesPerSub = 8;
+const int kCounterSlot = 128;        // ints reserved per batch in the pinned counters mirror
 
 void free_workspace(mcrt_ctx* c)
 {
@@ -171,7 +178,7 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
     dev_alloc(c->tb.n_segments, n_paths);
     dev_alloc(c->tb.queue_a, n_paths);
     dev_alloc(c->tb.queue_b, n_paths);
-    dev_alloc(c->tb.counters, (size_t)c->aq.max_depth + 1);
+    dev_alloc(c->tb.counters, (size_t)kMaxSub * (c->aq.max_depth + 1));
     dev_alloc(c->d_poses, (size_t)n_poses);
     dev_alloc(c->d_rf_acc, n_px);
     dev_alloc(c->d_rf_tmp0, n_px);
@@ -186,31 +193,96 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
     c->cap_poses = n_poses;
 }
 
-// enqueue the whole per-frame chain for `n` poses already uploaded to d_poses / d_seed_frame
+// wavefront trace of poses [pose0, pose0 + n) of the uploaded batch; `slot` selects its compaction counters
+void enqueue_trace(mcrt_ctx* c, int pose0, int n, int slot, cudaStream_t s, int* launches)
+{
+    const size_t p0 = (size_t)pose0 * c->aq.elements * c->aq.samples;
+    FrameDev fr;
+    fr.poses = c->d_poses + pose0; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = n; fr.frame_offset = pose0;
+    TraceBuffers tb = c->tb;
+    tb.paths.origin_intensity += p0; tb.paths.dir_state += p0; tb.paths.distance += p0;
+    tb.segments += p0 * c->aq.max_depth; tb.n_segments += p0;
+    if (tb.hit_fraction) tb.hit_fraction += p0 * c->aq.max_depth;
+    if (tb.hit_mesh) tb.hit_mesh += p0 * c->aq.max_depth;
+    tb.queue_a += p0; tb.queue_b += p0;
+    tb.counters += (size_t)slot * (c->aq.max_depth + 1);
+    launch_trace(c->sc, c->aq, fr, tb, c->sm_count, s, launches);
+}
+
+// accumulate -> PSF -> envelope (-> transpose, scan conversion) of poses [pose0, pose0 + n)
+void enqueue_image(mcrt_ctx* c, int pose0, int n, bool want_scan, cudaStream_t s, int* launches)
+{
+    const size_t p0 = (size_t)pose0 * c->aq.elements * c->aq.samples;
+    const size_t px0 = (size_t)pose0 * c->aq.elements * c->aq.rows;
+    CUDA_TRY(launch_accumulate(c->sc, c->aq, c->d_volume, c->tb.segments + p0 * c->aq.max_depth, c->tb.n_segments + p0, n, c->d_rf_acc + px0,
+                               c->d_steps, c->d_columns + p0 * c->aq.rows, s, launches));
+    launch_post(c->d_rf_acc + px0, n, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
+                c->d_rf_tmp0 + px0, c->d_rf_tmp1 + px0, c->d_rf_final + px0, s, launches);
+    if (c->params.rf_layout == 1) launch_transpose(c->d_rf_final + px0, n, c->aq.elements, c->aq.rows, c->d_rf_t + px0, s, launches);
+    if (want_scan)
+        launch_scan_convert(c->d_rf_final + px0, n, c->aq.elements, c->aq.rows, c->d_map_x, c->d_map_y, c->params.scan_rows, c->params.scan_cols,
+                            c->d_scan + (size_t)pose0 * c->params.scan_rows * c->params.scan_cols, s, launches);
+}
+
+// enqueue the whole per-frame chain for `n` poses already uploaded to d_poses / d_seed_frame, one stream
 void enqueue_pipeline(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches, bool stage_events)
 {
-    FrameDev fr;
-    fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = n; fr.pad = 0;
-    if (stage_events) CUDA_TRY(cudaEventRecord(c->ev_a, s));
-    launch_trace(c->sc, c->aq, fr, c->tb, c->sm_count, s, launches);
-    if (stage_events) CUDA_TRY(cudaEventRecord(c->ev_b, s));
+    CUDA_TRY(cudaMemsetAsync(c->tb.counters, 0, sizeof(int) * (size_t)kMaxSub * (c->aq.max_depth + 1), s));
     CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, sizeof(unsigned long long), s));
-    CUDA_TRY(launch_accumulate(c->sc, c->aq, c->d_volume, c->tb.segments, c->tb.n_segments, n, c->d_rf_acc, c->d_steps, c->d_columns, s,
-                               launches));
-    if (stage_events) CUDA_TRY(cudaEventRecord(c->ev_c, s));
-    launch_post(c->d_rf_acc, n, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
-                c->d_rf_tmp0, c->d_rf_tmp1, c->d_rf_final, s, launches);
-    if (c->params.rf_layout == 1) launch_transpose(c->d_rf_final, n, c->aq.elements, c->aq.rows, c->d_rf_t, s, launches);
-    if (want_scan)
-        launch_scan_convert(c->d_rf_final, n, c->aq.elements, c->aq.rows, c->d_map_x, c->d_map_y, c->params.scan_rows, c->params.scan_cols,
-                            c->d_scan, s, launches);
+    if (stage_events) CUDA_TRY(cudaEventRecord(c->ev_a, s));
+    enqueue_trace(c, 0, n, 0, s, launches);
+    if (stage_events) CUDA_TRY(cudaEventRecord(c->ev_b, s));
+    // stage split for the profile: accumulate (+ sample reduction) | PSF + envelope (+ transpose, scan)
+    const size_t dummy = 0; (void)dummy;
+    if (stage_events) {
+        CUDA_TRY(launch_accumulate(c->sc, c->aq, c->d_volume, c->tb.segments, c->tb.n_segments, n, c->d_rf_acc, c->d_steps, c->d_columns, s,
+                                   launches));
+        CUDA_TRY(cudaEventRecord(c->ev_c, s));
+        launch_post(c->d_rf_acc, n, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
+                    c->d_rf_tmp0, c->d_rf_tmp1, c->d_rf_final, s, launches);
+        if (c->params.rf_layout == 1) launch_transpose(c->d_rf_final, n, c->aq.elements, c->aq.rows, c->d_rf_t, s, launches);
+        if (want_scan)
+            launch_scan_convert(c->d_rf_final, n, c->aq.elements, c->aq.rows, c->d_map_x, c->d_map_y, c->params.scan_rows,
+                                c->params.scan_cols, c->d_scan, s, launches);
+    } else {
+        enqueue_image(c, 0, n, want_scan, s, launches);
+    }
     CUDA_TRY(cudaGetLastError());
 }
 
-int count_pipeline_launches(const mcrt_ctx* c, bool want_scan)
+// The same chain software-pipelined over `nsub` pose sub-batches on two streams (only ever captured into a
+// CUDA graph): stream s1 traces sub-batch k+1 while stream s2 accumulates / post-processes sub-batch k.
+// The trace kernels are latency-bound and the accumulate kernel issue-bound, so they fill each other's
+// idle issue slots.  Results are bit-identical to the single-stream chain (every write is keyed by path).
+void enqueue_pipeline_overlapped(mcrt_ctx* c, int n, int nsub, bool want_scan, cudaStream_t s1, cudaStream_t s2, int* launches)
 {
-    return c->aq.max_depth + 2 + post_launch_count(c->aq.elements, c->aq.rows, c->params.psf_lateral, 3, 1) + (c->params.rf_layout == 1 ? 1 : 0) +
-           (want_scan ? 1 : 0);
+    CUDA_TRY(cudaMemsetAsync(c->tb.counters, 0, sizeof(int) * (size_t)kMaxSub * (c->aq.max_depth + 1), s1));
+    CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, sizeof(unsigned long long), s1));
+    CUDA_TRY(cudaEventRecord(c->ev_fork, s1));
+    CUDA_TRY(cudaStreamWaitEvent(s2, c->ev_fork, 0));
+    for (int k = 0; k < nsub; k++) {
+        const int pose0 = (int)((long long)n * k / nsub), pose1 = (int)((long long)n * (k + 1) / nsub);
+        enqueue_trace(c, pose0, pose1 - pose0, k, s1, launches);
+        CUDA_TRY(cudaEventRecord(c->ev_sub[k], s1));
+        CUDA_TRY(cudaStreamWaitEvent(s2, c->ev_sub[k], 0));
+        enqueue_image(c, pose0, pose1 - pose0, want_scan, s2, launches);
+    }
+    CUDA_TRY(cudaEventRecord(c->ev_join, s2));
+    CUDA_TRY(cudaStreamWaitEvent(s1, c->ev_join, 0));
+    CUDA_TRY(cudaGetLastError());
+}
+
+int pipeline_sub_batches(const mcrt_ctx* c, int n)
+{
+    if (!c->overlap || n < 2 * kMinPosesPerSub) return 1;
+    int nsub = n / kMinPosesPerSub;
+    return nsub > kMaxSub ? kMaxSub : nsub;
+}
+
+int count_pipeline_launches(const mcrt_ctx* c, bool want_scan, int nsub)
+{
+    return nsub * (c->aq.max_depth + 2 + post_launch_count(c->aq.elements, c->aq.rows, c->params.psf_lateral, 3, 1) + (c->params.rf_layout == 1 ? 1 : 0) +
+                   (want_scan ? 1 : 0));
 }
 
 void run_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches)
@@ -221,6 +293,7 @@ void run_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches
         return;
     }
     const auto key = std::make_pair(n, want_scan ? 1 : 0);
+    const int nsub = pipeline_sub_batches(c, n);
     auto it = c->graphs.find(key);
     if (it == c->graphs.end()) {
         // capture on the library's own stream (the caller's stream may be the legacy default stream)
@@ -228,7 +301,8 @@ void run_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches
         int dummy = 0;
         CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         try {
-            enqueue_pipeline(c, n, want_scan, c->stream, &dummy, false);
+            if (nsub > 1) enqueue_pipeline_overlapped(c, n, nsub, want_scan, c->stream, c->stream2, &dummy);
+            else enqueue_pipeline(c, n, want_scan, c->stream, &dummy, false);
         } catch (...) {
             cudaStreamEndCapture(c->stream, &graph);
             if (graph) cudaGraphDestroy(graph);
@@ -242,7 +316,7 @@ void run_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches
         it = c->graphs.emplace(key, exec).first;
     }
     CUDA_TRY(cudaGraphLaunch(it->second, s));
-    if (launches) *launches += count_pipeline_launches(c, want_scan);
+    if (launches) *launches += count_pipeline_launches(c, want_scan, nsub);
 }
 
 int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t seed, uint64_t first_frame, float* rf_out,
@@ -283,7 +357,7 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
             if (scan_out)
                 CUDA_TRY(cudaMemcpyAsync(scan_out + (size_t)p0 * scan_per_pose, c->d_scan, sizeof(float) * scan_per_pose * n,
                                          scan_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(cudaMemcpyAsync(c->h_counters + 32 * b, c->tb.counters, sizeof(int) * (size_t)(c->aq.max_depth + 1),
+            CUDA_TRY(cudaMemcpyAsync(c->h_counters + kCounterSlot * b, c->tb.counters, sizeof(int) * (size_t)kMaxSub * (c->aq.max_depth + 1),
                                      cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaMemcpyAsync(c->h_steps + b, c->d_steps, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         }
@@ -314,7 +388,8 @@ void finalize_stats(mcrt_ctx* c)
     int64_t segs = c->stats.poses * paths_per_pose;      // bounce 0 traces every path
     int64_t steps = 0;
     for (int b = 0; b < c->pending_batches; b++) {
-        for (int d = 1; d < c->aq.max_depth; d++) segs += c->h_counters[32 * b + d];
+        for (int k = 0; k < kMaxSub; k++)
+            for (int d = 1; d < c->aq.max_depth; d++) segs += c->h_counters[kCounterSlot * b + k * (c->aq.max_depth + 1) + d];
         steps += (int64_t)c->h_steps[b];
     }
     c->stats.segments = segs;
@@ -348,6 +423,10 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     if (prop.major != 10) throw CudaError(std::string("device '") + prop.name + "' is not sm_100 (B200); libmcrt only carries sm_100a code");
     c->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    for (int k = 0; k < 4; k++) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_sub[k], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreate(&c->ev0)); CUDA_TRY(cudaEventCreate(&c->ev1));
     CUDA_TRY(cudaEventCreate(&c->ev_a)); CUDA_TRY(cudaEventCreate(&c->ev_b)); CUDA_TRY(cudaEventCreate(&c->ev_c));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
@@ -410,11 +489,11 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     dev_alloc(c->d_trav, 2);
     dev_alloc(c->d_steps, 1);
     CUDA_TRY(cudaMallocHost(&c->h_seed_frame, 2 * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMallocHost(&c->h_counters, sizeof(int) * 32 * kMaxBatchesPerCall));
+    CUDA_TRY(cudaMallocHost(&c->h_counters, sizeof(int) * kCounterSlot * kMaxBatchesPerCall));
     CUDA_TRY(cudaMallocHost(&c->h_steps, sizeof(unsigned long long) * kMaxBatchesPerCall));
     CUDA_TRY(cudaMallocHost(&c->h_trav, 2 * sizeof(unsigned long long)));
     c->h_trav[0] = c->h_trav[1] = 0;
-    memset(c->h_counters, 0, sizeof(int) * 32 * kMaxBatchesPerCall);
+    memset(c->h_counters, 0, sizeof(int) * kCounterSlot * kMaxBatchesPerCall);
     memset(c->h_steps, 0, sizeof(unsigned long long) * kMaxBatchesPerCall);
     *out = c.release();
     return MCRT_OK;
@@ -439,6 +518,10 @@ void destroy_impl(mcrt_ctx* c)
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     if (c->ev_c) cudaEventDestroy(c->ev_c);
     if (c->ev_up) cudaEventDestroy(c->ev_up);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    for (int k = 0; k < 4; k++) if (c->ev_sub[k]) cudaEventDestroy(c->ev_sub[k]);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     (void)cudaGetLastError();
     delete c;
@@ -539,6 +622,55 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
     const std::string n(name);
     if (n == "profile_stages") c->profile_stages = value != 0;
     else if (n == "use_graph") c->use_graph = value != 0;
+    else if (n == "overlap") {
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear();
+        c->overlap = value != 0;
+    }
+    else if (n == "bvh_builder") {
+        // 0: device LBVH (default, lbvh.cu); 1: host binned-SAH tree (sah_builder.cpp).  Rebuilds in place.
+        return guarded("mcrt_set_option", [&]() {
+            CUDA_TRY(cudaSetDevice(c->device));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+            c->graphs.clear();
+            const HostScene& hs = c->scene;
+            LbvhResult nb{};
+            if (value == 0) {
+                const cudaError_t be = build_lbvh(hs.tri_local.data(), hs.tri_mesh.data(), (int)hs.tri_mesh.size(), c->d_meshes, c->stream, &nb);
+                if (be != cudaSuccess) throw CudaError(std::string("build_lbvh: ") + cudaGetErrorString(be));
+            } else {
+                std::vector<float> origins(hs.meshes.size() * 3 + 3);
+                for (size_t m = 0; m < hs.meshes.size(); m++)
+                    for (int a = 0; a < 3; a++) origins[3 * m + a] = hs.meshes[m].origin[a];
+                HostBvh hb;
+                build_sah_bvh(hs.tri_local.data(), hs.tri_mesh.data(), (int)hs.tri_mesh.size(), origins.data(), &hb);
+                const size_t n = hb.slots.size();
+                std::vector<TriSlot> slots(n);
+                for (size_t k = 0; k < n; k++) {
+                    const HostTriSlot& t = hb.slots[k];
+                    int mbits = t.mesh, tbits = t.tri;
+                    float mf, tf;
+                    memcpy(&mf, &mbits, 4); memcpy(&tf, &tbits, 4);
+                    slots[k].v0 = make_float4(t.v[0], t.v[1], t.v[2], mf);
+                    slots[k].v1 = make_float4(t.v[3], t.v[4], t.v[5], tf);
+                    slots[k].v2 = make_float4(t.v[6], t.v[7], t.v[8], 0.f);
+                }
+                static_assert(sizeof(HostBvhNode) == sizeof(BvhNode), "node layouts must match");
+                if (n) { dev_alloc(nb.tris, n); CUDA_TRY(cudaMemcpy(nb.tris, slots.data(), sizeof(TriSlot) * n, cudaMemcpyHostToDevice)); }
+                if (!hb.nodes.empty()) {
+                    dev_alloc(nb.nodes, hb.nodes.size());
+                    CUDA_TRY(cudaMemcpy(nb.nodes, hb.nodes.data(), sizeof(BvhNode) * hb.nodes.size(), cudaMemcpyHostToDevice));
+                }
+                nb.n_tri = (int)n; nb.n_nodes = (int)hb.nodes.size(); nb.max_depth = hb.max_depth; nb.max_abs = hb.max_abs;
+            }
+            if (nb.max_depth > MCRT_TRAVERSAL_STACK) { cudaFree(nb.nodes); cudaFree(nb.tris); throw std::invalid_argument("BVH deeper than the traversal stack"); }
+            dev_free(c->bvh.nodes); dev_free(c->bvh.tris);
+            c->bvh = nb;
+            c->sc.nodes = nb.nodes; c->sc.tris = nb.tris; c->sc.n_tri = nb.n_tri; c->sc.max_abs = nb.max_abs;
+            return MCRT_OK;
+        });
+    }
     else if (n == "count_traversal") {
         // changes the kernel arguments baked into captured graphs: drop them
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
@@ -577,7 +709,7 @@ int mcrt_trace_debug(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, uint64_t
         CUDA_TRY(cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaMemcpyAsync(c->d_seed_frame, c->h_seed_frame, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
         FrameDev fr;
-        fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = 1; fr.pad = 0;
+        fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = 1; fr.frame_offset = 0;
         int launches = 0;
         launch_trace(c->sc, c->aq, fr, c->tb, c->sm_count, c->stream, &launches);
         CUDA_TRY(cudaGetLastError());
@@ -653,7 +785,7 @@ int mcrt_transducer_elements(mcrt_ctx* c, const mcrt_pose* pose, float* pos3, fl
         c->h_poses[0] = pose_trig(*pose);
         cudaError_t e = cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig), cudaMemcpyHostToDevice, c->stream);
         FrameDev fr;
-        fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = 1; fr.pad = 0;
+        fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = 1; fr.frame_offset = 0;
         if (e == cudaSuccess) { launch_elements(c->aq, fr, d_pos, d_dir, c->stream); e = cudaGetLastError(); }
         if (e == cudaSuccess) e = cudaMemcpyAsync(pos3, d_pos, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(dir3, d_dir, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream);

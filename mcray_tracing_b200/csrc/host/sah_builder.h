@@ -1,0 +1,23 @@
+// sah_builder.h -- optional host-side SAH BVH builder (see sah_builder.cpp).
+#ifndef MCRT_SAH_BUILDER_H
+#define MCRT_SAH_BUILDER_H
+#include <cstdint>
+#include <vector>
+
+namespace mcrt {
+
+struct HostBvhNode { float f[12]; int32_t child[4]; };          // bit-compatible with kernels' BvhNode (64 B)
+struct HostTriSlot { float v[9]; int32_t mesh; int32_t tri; };
+
+struct HostBvh {
+    std::vector<HostBvhNode> nodes;      // n_tri - 1 nodes, root = 0, pre-order
+    std::vector<HostTriSlot> slots;      // triangles in leaf order
+    int max_depth = 0;
+    float max_abs = 0.0f;
+};
+
+// tri_local: 9 floats/triangle (v_obj * scaling); mesh_origin3: body origin per mesh
+void build_sah_bvh(const float* tri_local, const int32_t* tri_mesh, int n_tri, const float* mesh_origin3, HostBvh* out);
+
+}  // namespace mcrt
+#endif

@@ -27,7 +27,7 @@ struct FrameDev {
     const float2* elem_sincos;           // [elements] (sin a_t, cos a_t)
     const unsigned long long* seed_frame;   // device: {Philox seed, first frame}; kept in HBM so a captured graph stays valid
     int n_poses;
-    int pad;
+    int frame_offset;                    // added to the first frame: index of poses[0] within the call's batch
 };
 
 struct TraceBuffers {

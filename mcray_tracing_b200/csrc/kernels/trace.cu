@@ -55,7 +55,7 @@ __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq
     const int element = rem / aq.samples;
     const int sample = rem - element * aq.samples;
     const uint64_t seed = __ldg(&fr.seed_frame[0]);
-    const uint32_t frame = (uint32_t)(__ldg(&fr.seed_frame[1]) + (uint64_t)pose);
+    const uint32_t frame = (uint32_t)(__ldg(&fr.seed_frame[1]) + (uint64_t)fr.frame_offset + (uint64_t)pose);
 
     float3 from, dir;
     float intensity;
@@ -189,6 +189,9 @@ __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq
 }
 
 template <bool FIRST>
+#ifndef MCRT_BOUNCE_GRID_CTAS_PER_SM
+#define MCRT_BOUNCE_GRID_CTAS_PER_SM 64   // measured: an (effectively) uncapped grid beats a persistent 8-CTA/SM grid by 15 % at 256 frames
+#endif
 #ifndef MCRT_BOUNCE_MIN_CTAS
 #define MCRT_BOUNCE_MIN_CTAS 6      // 80 registers, 24 warps/SM: measured best of 4/5/6/8 (profiles/r01_traversal_ab.txt)
 #endif
@@ -312,7 +315,7 @@ void launch_trace(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, cons
     cudaMemsetAsync(tb.counters, 0, sizeof(int) * (size_t)(aq.max_depth + 1), stream);
     const int block = 128;
     // persistent-style grid: a multiple of the SM count, grid-stride loop inside
-    const int grid = grid_for(n_paths, block, sm_count, 8);
+    const int grid = grid_for(n_paths, block, sm_count, MCRT_BOUNCE_GRID_CTAS_PER_SM);
     for (int b = 0; b < aq.max_depth; b++) {
         if (b == 0) k_bounce<true><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
         else k_bounce<false><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);

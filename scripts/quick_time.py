@@ -30,3 +30,15 @@ poses = np.repeat(pose, 64, axis=0)
 sim.simulate(poses, seed=1, first_frame=0)
 st = sim.stats()
 print(f"traversal: segs {st.segments} node visits/seg {st.bvh_node_visits/st.segments:.1f} tri tests/seg {st.bvh_triangle_tests/st.segments:.1f}")
+# SAH tree experiment
+import time as _t
+t0 = _t.time(); sim.set_option("bvh_builder", 1); print("sah build s", _t.time() - t0)
+sim.simulate(poses, seed=1, first_frame=0)
+st = sim.stats()
+print(f"SAH traversal: segs {st.segments} node visits/seg {st.bvh_node_visits/st.segments:.1f} tri tests/seg {st.bvh_triangle_tests/st.segments:.1f}")
+sim.set_option("count_traversal", 0)
+sim.set_option("profile_stages", 1)
+for it in range(2):
+    sim.simulate(poses, seed=1, first_frame=0)
+st = sim.stats()
+print(f"SAH stages batch 64: trace {st.ms_trace:.3f} acc {st.ms_accumulate:.3f} post {st.ms_post:.3f} total {st.ms_total:.3f}")
