@@ -434,6 +434,8 @@ __device__ __forceinline__ unsigned peak_mask_smem(const float* I, int rows, int
     return __ballot_sync(0xffffffffu, peak);
 }
 
+// KA / KL > 0: compile-time tap counts (taps held in registers, loops fully unrolled); 0: run-time sizes.
+template <int KA, int KL>
 __global__ void __launch_bounds__(MCRT_FUSED_THREADS) k_post_fused(const float* __restrict__ in, const int cols, const int rows,
                                                                   const float* __restrict__ ax_taps, const int ka,
                                                                   const float* __restrict__ lat_taps, const int kl, const int flags,
@@ -473,11 +475,23 @@ __global__ void __launch_bounds__(MCRT_FUSED_THREADS) k_post_fused(const float* 
             if (c0 + c >= cols) continue;
             const float* src = s_in + (size_t)c * rows;
             float* dst = s_ax + (size_t)c * rows;
-            for (int r = ka + lane; r < rows - ka; r += 32) {
-                float convolution = 0;
+            if (KA > 0) {
+                float ta[KA > 0 ? KA : 1];
+#pragma unroll
+                for (int k = 0; k < KA; k++) ta[k] = s_taps_a[k];
+                for (int r = KA + lane; r < rows - KA; r += 32) {
+                    float convolution = 0;
+#pragma unroll
+                    for (int k = 0; k < KA; k++) convolution += src[r + k] * ta[k];
+                    dst[r] = convolution;
+                }
+            } else {
+                for (int r = ka + lane; r < rows - ka; r += 32) {
+                    float convolution = 0;
 #pragma unroll 4
-                for (int k = 0; k < ka; k++) convolution += src[r + k] * s_taps_a[k];
-                dst[r] = convolution;
+                    for (int k = 0; k < ka; k++) convolution += src[r + k] * s_taps_a[k];
+                    dst[r] = convolution;
+                }
             }
         }
         __syncthreads();
@@ -486,12 +500,25 @@ __global__ void __launch_bounds__(MCRT_FUSED_THREADS) k_post_fused(const float* 
             const int gc = c0 + c;
             if (gc >= cols || !(gc >= kl / 2 && gc < cols - kl)) continue;
             float* dst = s_out + (size_t)c * rows;
-            for (int r = ka + lane; r < rows - ka; r += 32) {
-                const float* src = s_ax + (size_t)c * rows + r;
-                float convolution = 0;
+            if (KL > 0) {
+                float tl[KL > 0 ? KL : 1];
+#pragma unroll
+                for (int k = 0; k < KL; k++) tl[k] = s_taps_l[k];
+                for (int r = ka + lane; r < rows - ka; r += 32) {
+                    const float* src = s_ax + (size_t)c * rows + r;
+                    float convolution = 0;
+#pragma unroll
+                    for (int k = 0; k < KL; k++) convolution += src[(size_t)k * rows] * tl[k];
+                    dst[r] = convolution;
+                }
+            } else {
+                for (int r = ka + lane; r < rows - ka; r += 32) {
+                    const float* src = s_ax + (size_t)c * rows + r;
+                    float convolution = 0;
 #pragma unroll 4
-                for (int k = 0; k < kl; k++) convolution += src[(size_t)k * rows] * s_taps_l[k];
-                dst[r] = convolution;
+                    for (int k = 0; k < kl; k++) convolution += src[(size_t)k * rows] * s_taps_l[k];
+                    dst[r] = convolution;
+                }
             }
         }
         __syncthreads();
@@ -648,7 +675,9 @@ static int fused_tile_cols(int rows, int kl, int flags, size_t* smem)
 cudaError_t init_image_kernels()
 {
     // per-device function attribute; must not be issued inside a stream capture
-    return cudaFuncSetAttribute(k_post_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, MCRT_FUSED_SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(k_post_fused<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MCRT_FUSED_SMEM_LIMIT);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_post_fused<7, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, MCRT_FUSED_SMEM_LIMIT);
 }
 
 int post_launch_count(int cols, int rows, int n_lateral, int flags, int n_images)
@@ -674,7 +703,10 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
     if (tc > 0 && n_images <= 65535) {
         // whole scanlines fit shared memory: one pass over HBM
         dim3 grid((cols + tc - 1) / tc, n_images, 1);
-        k_post_fused<<<grid, MCRT_FUSED_THREADS, smem, stream>>>(d_in, cols, rows, d_axial, n_axial, d_lateral, n_lateral, flags, tc, d_out);
+        if (n_axial == 7 && n_lateral == 13)      // the reference's psf<7,13,...> (main.cpp:34)
+            k_post_fused<7, 13><<<grid, MCRT_FUSED_THREADS, smem, stream>>>(d_in, cols, rows, d_axial, 7, d_lateral, 13, flags, tc, d_out);
+        else
+            k_post_fused<0, 0><<<grid, MCRT_FUSED_THREADS, smem, stream>>>(d_in, cols, rows, d_axial, n_axial, d_lateral, n_lateral, flags, tc, d_out);
         if (launches) (*launches)++;
         return;
     }
