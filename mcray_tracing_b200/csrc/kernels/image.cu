@@ -306,110 +306,171 @@ __global__ void __launch_bounds__(256) k_reduce_samples(const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 #define MCRT_MAX_TAPS 256
 
-__global__ void __launch_bounds__(256) k_psf_axial(const float* __restrict__ in, const int64_t n_scanlines, const int rows,
-                                                  const float* __restrict__ taps, const int ka, float* __restrict__ out)
+// ---- long-scanline path (rows that do not fit the fused kernel's shared memory, BASELINE config 5) ----
+// Register-blocked so each loaded sample feeds MCRT_PSF_R outputs: 2 + ~1/R instructions per tap and
+// output instead of a load + multiply + add + loop overhead per tap.
+#define MCRT_PSF_R 8                  // consecutive outputs per thread
+#define MCRT_PSF_CHUNK (256 * MCRT_PSF_R)   // output rows per CTA of k_psf_axial
+
+// logical row index within the staged chunk -> shared-memory word: one pad word per MCRT_PSF_R words, so
+// the lanes of a warp (whose windows start MCRT_PSF_R apart) hit distinct banks
+__host__ __device__ __forceinline__ int psf_pad(int i) { return i + (i >> 3); }
+
+// Axial pass (rfimage.h:97-108).  CTA = one MCRT_PSF_CHUNK-row piece of one scanline, staged through shared
+// memory (coalesced 128 B loads); thread t owns outputs [8t, 8t+8) and slides an 8-sample register window
+// along the taps.  For every output the taps are applied in order k = 0.. with separate multiply and add
+// (the reference's sequential fp32 sum).  Rows outside [ka, rows-ka) are never read downstream.
+__global__ void __launch_bounds__(256) k_psf_axial(const float* __restrict__ in, const int rows, const float* __restrict__ taps, const int ka,
+                                                  float* __restrict__ out)
 {
+    extern __shared__ float s_row[];                       // psf_pad(MCRT_PSF_CHUNK + ka + MCRT_PSF_R) words
     __shared__ float s_taps[MCRT_MAX_TAPS];
-    for (int i = threadIdx.x; i < ka; i += blockDim.x) s_taps[i] = taps[i];
+    const int tid = threadIdx.x;
+    const int chunk0 = blockIdx.x * MCRT_PSF_CHUNK;        // first output row of this CTA
+    const float* src = in + (size_t)blockIdx.y * rows;
+    float* dst = out + (size_t)blockIdx.y * rows;
+    for (int i = tid; i < ka; i += blockDim.x) s_taps[i] = taps[i];
+    const int n_stage = MCRT_PSF_CHUNK + ka + MCRT_PSF_R;
+    for (int i = tid; i < n_stage; i += blockDim.x) {
+        const int r = chunk0 + i;
+        s_row[psf_pad(i)] = r < rows ? __ldg(&src[r]) : 0.0f;
+    }
     __syncthreads();
-    const int64_t total = n_scanlines * rows;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int row = (int)(i % rows);
-        if (row < ka || row >= rows - ka) continue;                      // conv_axial_buffer is never read there
-        const float* src = in + i;
-        float convolution = 0;
-        for (int k = 0; k < ka; k++) convolution += src[k] * s_taps[k];
-        out[i] = convolution;
+    const int l0 = tid * MCRT_PSF_R;                       // first output row of this thread, chunk-local
+    const int r0 = chunk0 + l0;
+    if (r0 >= rows - ka || r0 + MCRT_PSF_R <= ka) return;
+    float acc[MCRT_PSF_R], win[MCRT_PSF_R];
+#pragma unroll
+    for (int j = 0; j < MCRT_PSF_R; j++) { acc[j] = 0.0f; win[j] = s_row[psf_pad(l0 + j)]; }
+    for (int k0 = 0; k0 < ka; k0 += MCRT_PSF_R) {
+#pragma unroll
+        for (int kk = 0; kk < MCRT_PSF_R; kk++) {
+            const int k = k0 + kk;
+            if (k < ka) {
+                const float t = s_taps[k];
+                // window invariant: win[(kk + j) & 7] == sample at row l0 + k + j
+#pragma unroll
+                for (int j = 0; j < MCRT_PSF_R; j++) acc[j] += win[(kk + j) & (MCRT_PSF_R - 1)] * t;
+                win[kk] = s_row[psf_pad(l0 + k + MCRT_PSF_R)];   // slot kk held row l0+k, now row l0+k+8
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < MCRT_PSF_R; j++) {
+        const int r = r0 + j;
+        if (r >= ka && r < rows - ka) dst[r] = acc[j];
     }
 }
 
-__global__ void __launch_bounds__(256) k_psf_lateral(const float* __restrict__ raw, const float* __restrict__ axial_buf, const int n_images,
-                                                    const int cols, const int rows, const float* __restrict__ taps, const int ka,
-                                                    const int kl, float* __restrict__ out)
+// Lateral pass (rfimage.h:111-122) + untouched borders (B-9).  Thread = one row, MCRT_PSF_R consecutive
+// scanlines; lanes walk consecutive rows, so every load/store is coalesced and no shared memory is needed.
+__global__ void __launch_bounds__(256) k_psf_lateral(const float* __restrict__ raw, const float* __restrict__ axial_buf, const int cols,
+                                                    const int rows, const float* __restrict__ taps, const int ka, const int kl,
+                                                    float* __restrict__ out)
 {
     __shared__ float s_taps[MCRT_MAX_TAPS];
     for (int i = threadIdx.x; i < kl; i += blockDim.x) s_taps[i] = taps[i];
     __syncthreads();
-    const int64_t total = (int64_t)n_images * cols * rows;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int row = (int)(i % rows);
-        const int col = (int)((i / rows) % cols);
-        float v;
-        if (row >= ka && row < rows - ka && col >= kl / 2 && col < cols - kl) {
-            const float* src = axial_buf + i;
-            float convolution = 0;
-            for (int k = 0; k < kl; k++) convolution += src[(size_t)k * rows] * s_taps[k];
-            v = convolution;
-        } else {
-            v = raw[i];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int c0 = blockIdx.y * MCRT_PSF_R;
+    const size_t img = (size_t)blockIdx.z * cols * rows;
+    const float* ax = axial_buf + img;
+    const bool row_ok = r >= ka && r < rows - ka;
+    // does any of the 8 scanlines get convolved at all?
+    const bool any = row_ok && (c0 + MCRT_PSF_R > kl / 2) && (c0 < cols - kl);
+    float acc[MCRT_PSF_R], win[MCRT_PSF_R];
+    if (any) {
+        auto ld = [&](int c) -> float { return c < cols ? __ldg(&ax[(size_t)c * rows + r]) : 0.0f; };
+#pragma unroll
+        for (int j = 0; j < MCRT_PSF_R; j++) { acc[j] = 0.0f; win[j] = ld(c0 + j); }
+        for (int k0 = 0; k0 < kl; k0 += MCRT_PSF_R) {
+#pragma unroll
+            for (int kk = 0; kk < MCRT_PSF_R; kk++) {
+                const int k = k0 + kk;
+                if (k < kl) {
+                    const float t = s_taps[k];
+#pragma unroll
+                    for (int j = 0; j < MCRT_PSF_R; j++) acc[j] += win[(kk + j) & (MCRT_PSF_R - 1)] * t;
+                    win[kk] = ld(c0 + k + MCRT_PSF_R);
+                }
+            }
         }
-        out[i] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < MCRT_PSF_R; j++) {
+        const int c = c0 + j;
+        if (c >= cols) break;
+        const size_t o = img + (size_t)c * rows + r;
+        out[o] = (any && c >= kl / 2 && c < cols - kl) ? acc[j] : __ldg(&raw[o]);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// rf_image::envelope (rfimage.h:54-91): one warp per scanline.  A sample i in [1, rows-2] is a peak
-// iff I[i-1] < I[i] and not I[i] < I[i+1] (the sequential `ascending` flag reduces to this because
-// peak detection only ever reads samples that have not been rewritten yet).  Between consecutive
-// peaks p < q the output is lerp(last, |I[q]|) with last = I[0] (signed) for the virtual first peak
-// and |I[p]| otherwise; samples from the last peak on keep their raw value.
+// rf_image::envelope (rfimage.h:54-91).  A sample i in [1, rows-2] is a peak iff I[i-1] < I[i] and not
+// I[i] < I[i+1] (the sequential `ascending` flag reduces to this because peak detection only ever reads
+// samples that have not been rewritten yet).  Between consecutive peaks p < q the output is
+// lerp(last, |I[q]|) with last = I[0] (signed) for the virtual first peak and |I[p]| otherwise; samples
+// from the last peak on keep their raw value.
+// Long-scanline version: k_peak_masks writes one 32-row peak bit mask per word, then k_envelope_lerp
+// is fully parallel -- each sample finds its enclosing peaks by scanning mask words (peaks are a few
+// samples apart in RF data, so the scan almost always ends in the sample's own word).
 // ------------------------------------------------------------------------------------------------
-#define MCRT_ENV_WARPS 4
-#define MCRT_ENV_MAX_CHUNKS 1024      // rows <= 32768
-
-__device__ __forceinline__ unsigned peak_mask(const float* __restrict__ I, int rows, int c, int lane)
+__global__ void __launch_bounds__(256) k_peak_masks(const float* __restrict__ in, const int64_t n_scanlines, const int rows, const int words,
+                                                   unsigned* __restrict__ masks)
 {
-    const int i = (c << 5) + lane;
-    const float v = i < rows ? I[i] : 0.0f;
-    const float vm = (i >= 1 && i < rows) ? I[i - 1] : 0.0f;
-    const float vp = (i + 1 < rows) ? I[i + 1] : 0.0f;
-    const bool peak = (i >= 1) && (i + 1 < rows) && (vm < v) && !(v < vp);
-    return __ballot_sync(0xffffffffu, peak);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t total = n_scanlines * words;
+    for (int64_t wdx = warp; wdx < total; wdx += n_warps) {
+        const int64_t sl = wdx / words;
+        const int c = (int)(wdx - sl * words);
+        const float* I = in + sl * rows;
+        const int i = (c << 5) + lane;
+        const float v = i < rows ? __ldg(&I[i]) : 0.0f;
+        const float vm = (i >= 1 && i < rows) ? __ldg(&I[i - 1]) : 0.0f;
+        const float vp = (i + 1 < rows) ? __ldg(&I[i + 1]) : 0.0f;
+        const bool peak = (i >= 1) && (i + 1 < rows) && (vm < v) && !(v < vp);
+        const unsigned m = __ballot_sync(0xffffffffu, peak);
+        if (lane == 0) masks[wdx] = m;
+    }
 }
 
-__global__ void __launch_bounds__(32 * MCRT_ENV_WARPS) k_envelope(const float* __restrict__ in, const int64_t n_scanlines, const int rows,
-                                                                float* __restrict__ out)
+__global__ void __launch_bounds__(256) k_envelope_lerp(const float* __restrict__ in, const unsigned* __restrict__ masks, const int64_t n_scanlines,
+                                                      const int rows, const int words, float* __restrict__ out)
 {
-    __shared__ unsigned s_mask[MCRT_ENV_WARPS][MCRT_ENV_MAX_CHUNKS];
-    __shared__ int s_next[MCRT_ENV_WARPS][MCRT_ENV_MAX_CHUNKS];
-    const int lane = threadIdx.x & 31;
-    const int w = threadIdx.x >> 5;
-    const int64_t warp = (int64_t)blockIdx.x * MCRT_ENV_WARPS + w;
-    const int64_t n_warps = (int64_t)gridDim.x * MCRT_ENV_WARPS;
-    const int n_chunks = (rows + 31) >> 5;
-    for (int64_t sl = warp; sl < n_scanlines; sl += n_warps) {
+    const int64_t total = n_scanlines * rows;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t sl = idx / rows;
+        const int i = (int)(idx - sl * rows);
         const float* I = in + sl * rows;
-        float* O = out + sl * rows;
-        // pass A (backward): peak mask of every 32-row chunk and the first peak after each chunk
-        int next = rows;                               // "no peak"
-        for (int c = n_chunks - 1; c >= 0; c--) {
-            const unsigned m = peak_mask(I, rows, c, lane);
-            if (lane == 0) { s_mask[w][c] = m; s_next[w][c] = next; }
-            if (m) next = (c << 5) + (__ffs(m) - 1);
+        const unsigned* M = masks + sl * words;
+        const int w0 = i >> 5, b = i & 31;
+        // last peak at or before i (0 = the virtual first peak (0, I[0]) of rfimage.h:63-64)
+        int p = 0;
+        {
+            unsigned m = __ldg(&M[w0]) & (0xffffffffu >> (31 - b));
+            int w = w0;
+            while (m == 0u && w > 0) m = __ldg(&M[--w]);
+            if (m) p = (w << 5) + (31 - __clz(m));
         }
-        __syncwarp();
-        // pass B (forward): lerp between the enclosing peaks
-        int last_peak = 0;                             // the virtual first peak (0, I[0]) of rfimage.h:63-64
-        for (int c = 0; c < n_chunks; c++) {
-            const unsigned mask = s_mask[w][c];
-            const int i = (c << 5) + lane;
-            const unsigned le = mask & (0xffffffffu >> (31 - lane));
-            const int p = le ? (c << 5) + (31 - __clz(le)) : last_peak;
-            const unsigned gt = lane == 31 ? 0u : (mask & (0xffffffffu << (lane + 1)));
-            const int q = gt ? (c << 5) + (__ffs(gt) - 1) : s_next[w][c];
-            if (i < rows) {
-                float r = I[i];
-                if (q < rows) {
-                    const float last = (p == 0) ? I[0] : fabsf(I[p]);
-                    const float new_peak = fabsf(I[q]);
-                    const float alpha = ((float)i - (float)p) / ((float)q - (float)p);
-                    r = last * (1 - alpha) + new_peak * alpha;
-                }
-                O[i] = r;
-            }
-            if (mask) last_peak = (c << 5) + (31 - __clz(mask));
+        // first peak strictly after i (rows = none)
+        int q = rows;
+        {
+            unsigned m = b == 31 ? 0u : (__ldg(&M[w0]) & (0xffffffffu << (b + 1)));
+            int w = w0;
+            while (m == 0u && w + 1 < words) m = __ldg(&M[++w]);
+            if (m) q = (w << 5) + (__ffs(m) - 1);
         }
-        __syncwarp();
+        float r = __ldg(&I[i]);
+        if (q < rows) {
+            const float last = (p == 0) ? __ldg(&I[0]) : fabsf(__ldg(&I[p]));
+            const float new_peak = fabsf(__ldg(&I[q]));
+            const float alpha = ((float)i - (float)p) / ((float)q - (float)p);
+            r = last * (1 - alpha) + new_peak * alpha;
+        }
+        out[idx] = r;
     }
 }
 
@@ -685,7 +746,8 @@ int post_launch_count(int cols, int rows, int n_lateral, int flags, int n_images
     size_t smem = 0;
     (void)cols;
     if ((flags & 3) && fused_tile_cols(rows, n_lateral, flags, &smem) > 0 && n_images <= 65535) return 1;
-    return ((flags & 1) ? 2 : 0) + (((flags & 2) || !(flags & 1)) ? 1 : 0);
+    const int64_t n_scanlines = (int64_t)n_images * cols;
+    return ((flags & 1) ? (int)((n_scanlines + 65534) / 65535) + 1 : 0) + ((flags & 2) ? 2 : ((flags & 1) ? 0 : 1));
 }
 
 void launch_post(const float* d_in, int n_images, int cols, int rows, const float* d_axial, int n_axial, const float* d_lateral,
@@ -710,19 +772,31 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
         if (launches) (*launches)++;
         return;
     }
+    // long scanlines: register-blocked axial / lateral passes, mask-based parallel envelope
     const float* cur = d_in;
     if (flags & 1) {
-        k_psf_axial<<<grid1d(total, 256), 256, 0, stream>>>(cur, n_scanlines, rows, d_axial, n_axial, d_tmp0);
+        const size_t smem_ax = sizeof(float) * (size_t)(psf_pad(MCRT_PSF_CHUNK + n_axial + MCRT_PSF_R) + 1);
+        dim3 ga((rows + MCRT_PSF_CHUNK - 1) / MCRT_PSF_CHUNK, (unsigned)n_scanlines, 1);
+        if (n_scanlines > 65535) ga = dim3(ga.x, 65535, 1);   // guarded below
+        for (int64_t s0 = 0; s0 < n_scanlines; s0 += 65535) {
+            const int64_t ns = n_scanlines - s0 < 65535 ? n_scanlines - s0 : 65535;
+            ga.y = (unsigned)ns;
+            k_psf_axial<<<ga, 256, smem_ax, stream>>>(cur + s0 * rows, rows, d_axial, n_axial, d_tmp0 + s0 * rows);
+            if (launches) (*launches)++;
+        }
         float* dst = (flags & 2) ? d_tmp1 : d_out;
-        k_psf_lateral<<<grid1d(total, 256), 256, 0, stream>>>(cur, d_tmp0, n_images, cols, rows, d_lateral, n_axial, n_lateral, dst);
+        dim3 gl((rows + 255) / 256, (cols + MCRT_PSF_R - 1) / MCRT_PSF_R, n_images);
+        k_psf_lateral<<<gl, 256, 0, stream>>>(cur, d_tmp0, cols, rows, d_lateral, n_axial, n_lateral, dst);
         cur = dst;
-        if (launches) (*launches) += 2;
+        if (launches) (*launches)++;
     }
     if (flags & 2) {
-        int64_t g = (n_scanlines + MCRT_ENV_WARPS - 1) / MCRT_ENV_WARPS;
-        if (g > 148 * 16) g = 148 * 16;
-        k_envelope<<<(int)g, 32 * MCRT_ENV_WARPS, 0, stream>>>(cur, n_scanlines, rows, d_out);
-        if (launches) (*launches)++;
+        // the peak masks live in the (now free) axial scratch buffer: rows/32 words per scanline
+        const int words = (rows + 31) >> 5;
+        unsigned* masks = reinterpret_cast<unsigned*>((flags & 1) ? d_tmp0 : d_tmp1);
+        k_peak_masks<<<grid1d(n_scanlines * words * 32, 256), 256, 0, stream>>>(cur, n_scanlines, rows, words, masks);
+        k_envelope_lerp<<<grid1d(total, 256), 256, 0, stream>>>(cur, masks, n_scanlines, rows, words, d_out);
+        if (launches) (*launches) += 2;
     } else if (!(flags & 1)) {
         k_copy<<<grid1d(total, 256), 256, 0, stream>>>(cur, total, d_out);
         if (launches) (*launches)++;

@@ -91,14 +91,15 @@ def c5():
         p = api.default_params(elements=1024, samples=16, axial_scale=17.6, psf_axial=ka, psf_lateral=kl)
         sim = api.Simulator(d["ircad11"] / "santi-liver.scene", p)
         pose = sim.start_pose[None, :]
-        poses = np.repeat(pose, 2, axis=0)
-        out = torch.empty((2, sim.cols, sim.rows), dtype=torch.float32, device="cuda")
+        NF = 8
+        poses = np.repeat(pose, NF, axis=0)
+        out = torch.empty((NF, sim.cols, sim.rows), dtype=torch.float32, device="cuda")
         ms, st = timed(sim, poses, out, reps=3, warm=1)
         stg = stages(sim, poses, out)
-        px = 2 * sim.cols * sim.rows
+        px = NF * sim.cols * sim.rows
         steps = st.march_steps
         acc_alg = 8.0 * steps + 4.0 * px
-        res.append(dict(psf=f"{ka}x{kl}", rows=sim.rows, cols=sim.cols, frames_per_call=2, ms_per_call=ms, stage_ms=stg, march_steps=int(steps),
+        res.append(dict(psf=f"{ka}x{kl}", rows=sim.rows, cols=sim.cols, frames_per_call=NF, ms_per_call=ms, stage_ms=stg, march_steps=int(steps),
                         accumulate_algorithmic_GBps=acc_alg / stg["accumulate"] / 1e6, accumulate_frac_of_measured_hbm=acc_alg / stg["accumulate"] / 1e6 / peak,
                         post_pixels=px, post_algorithmic_bytes=3 * 8.0 * px, post_GBps=3 * 8.0 * px / stg["post"] / 1e6,
                         post_frac_of_measured_hbm=3 * 8.0 * px / stg["post"] / 1e6 / peak,

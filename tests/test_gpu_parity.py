@@ -200,7 +200,9 @@ def test_accumulate_matches_oracle(api, O, ircad_rough):
     assert np.count_nonzero(ref) > 10000
 
 
-@pytest.mark.parametrize("cols,rows,ka,kl", [(512, 465, 7, 13), (256, 465, 7, 13), (40, 64, 7, 13), (64, 300, 31, 15), (33, 31, 3, 5)])
+@pytest.mark.parametrize("cols,rows,ka,kl", [(512, 465, 7, 13), (256, 465, 7, 13), (40, 64, 7, 13), (64, 300, 31, 15), (33, 31, 3, 5),
+                                              # rows > 2048: the long-scanline kernels (register-blocked PSF, mask-based envelope)
+                                              (40, 2500, 7, 13), (9, 2100, 3, 5), (70, 4099, 63, 31), (17, 2049, 9, 1)])
 def test_convolve_and_envelope_bit_exact(api, O, sphere, cols, rows, ka, kl):
     rng = np.random.default_rng(cols * 1000 + rows)
     img = rng.normal(size=(rows, cols)).astype(np.float32)          # oracle layout [rows][cols]
