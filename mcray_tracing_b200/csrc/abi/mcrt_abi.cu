@@ -34,6 +34,7 @@ struct CudaError : std::runtime_error {
     explicit CudaError(const std::string& m) : std::runtime_error(m) {}
 };
 
+#define CUDA_TRY_NOTHROW(expr) do { (void)(expr); (void)cudaGetLastError(); } while (0)
 #define CUDA_TRY(expr)                                                                                            \
     do {                                                                                                          \
         cudaError_t e__ = (expr);                                                                                 \
@@ -119,6 +120,7 @@ struct mcrt_ctx {
     unsigned long long* d_steps = nullptr;
     unsigned long long* d_trav = nullptr;      // {node visits, triangle tests}, only when count_traversal
     bool count_traversal = false;
+    bool coherence_sort = false;           // radix-sort surviving paths between bounces (rough scenes)
     float* d_rf_acc = nullptr;
     float* d_rf_tmp0 = nullptr;
     float* d_rf_tmp1 = nullptr;
@@ -157,6 +159,9 @@ void free_workspace(mcrt_ctx* c)
     dev_free(c->tb.paths.origin_intensity); dev_free(c->tb.paths.dir_state); dev_free(c->tb.paths.distance);
     dev_free(c->tb.segments); dev_free(c->tb.n_segments); dev_free(c->tb.hit_fraction); dev_free(c->tb.hit_mesh);
     dev_free(c->tb.queue_a); dev_free(c->tb.queue_b); dev_free(c->tb.counters);
+    dev_free(c->tb.sort_keys); dev_free(c->tb.sort_keys_tmp); dev_free(c->tb.sort_queue_tmp);
+    if (c->tb.sort_tmp) cudaFree(c->tb.sort_tmp);
+    c->tb.sort_tmp = nullptr; c->tb.sort_tmp_bytes = 0;
     dev_free(c->d_poses); dev_free(c->d_rf_acc); dev_free(c->d_rf_tmp0); dev_free(c->d_rf_tmp1); dev_free(c->d_rf_final);
     dev_free(c->d_rf_t); dev_free(c->d_scan); dev_free(c->d_columns);
     if (c->h_poses) cudaFreeHost(c->h_poses);
@@ -190,6 +195,11 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
     if (c->columns_bytes) dev_alloc(c->d_columns, c->columns_bytes / sizeof(float));
     CUDA_TRY(cudaMallocHost(&c->h_poses, sizeof(PoseTrig) * (size_t)n_poses));
     c->tb.trav_counters = c->count_traversal ? c->d_trav : nullptr;
+    if (c->coherence_sort) {
+        dev_alloc(c->tb.sort_keys, n_paths); dev_alloc(c->tb.sort_keys_tmp, n_paths); dev_alloc(c->tb.sort_queue_tmp, n_paths);
+        c->tb.sort_tmp_bytes = trace_sort_tmp_bytes((int64_t)n_paths);
+        CUDA_TRY(cudaMalloc(&c->tb.sort_tmp, c->tb.sort_tmp_bytes ? c->tb.sort_tmp_bytes : 16));
+    }
     c->cap_poses = n_poses;
 }
 
@@ -205,6 +215,7 @@ void enqueue_trace(mcrt_ctx* c, int pose0, int n, int slot, cudaStream_t s, int*
     if (tb.hit_fraction) tb.hit_fraction += p0 * c->aq.max_depth;
     if (tb.hit_mesh) tb.hit_mesh += p0 * c->aq.max_depth;
     tb.queue_a += p0; tb.queue_b += p0;
+    if (tb.sort_keys) { tb.sort_keys += p0; tb.sort_keys_tmp += p0; tb.sort_queue_tmp += p0; }
     tb.counters += (size_t)slot * (c->aq.max_depth + 1);
     launch_trace(c->sc, c->aq, fr, tb, c->sm_count, s, launches);
 }
@@ -465,6 +476,20 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     sc.starting_material = hs.starting_material;
     for (int a = 0; a < 3; a++) sc.spacing[a] = hs.spacing[a];
     sc.max_abs = c->bvh.max_abs;
+    {
+        float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+        for (size_t t = 0; t < hs.tri_mesh.size(); t++)
+            for (int k = 0; k < 3; k++)
+                for (int a = 0; a < 3; a++) {
+                    const float w = hs.tri_local[9 * t + 3 * k + a] + hs.meshes[hs.tri_mesh[t]].origin[a];
+                    lo[a] = w < lo[a] ? w : lo[a]; hi[a] = w > hi[a] ? w : hi[a];
+                }
+        for (int a = 0; a < 3; a++) {
+            const float ext = hi[a] - lo[a];
+            sc.bounds_lo[a] = hs.tri_mesh.empty() ? 0.0f : lo[a];
+            sc.bounds_inv[a] = (!hs.tri_mesh.empty() && ext > 0.0f) ? 1.0f / ext : 0.0f;
+        }
+    }
 
     // transducer table, psf taps, scan maps, scatterer volume
     std::vector<float> sincos;
@@ -670,6 +695,12 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
             c->sc.nodes = nb.nodes; c->sc.tris = nb.tris; c->sc.n_tri = nb.n_tri; c->sc.max_abs = nb.max_abs;
             return MCRT_OK;
         });
+    }
+    else if (n == "coherence_sort") {
+        // changes the workspace and the captured graphs: drop both, they are rebuilt on the next call
+        CUDA_TRY_NOTHROW(cudaStreamSynchronize(c->stream));
+        free_workspace(c);
+        c->coherence_sort = value != 0;
     }
     else if (n == "count_traversal") {
         // changes the kernel arguments baked into captured graphs: drop them

@@ -52,6 +52,8 @@ struct SceneDev {
     int starting_material;
     float spacing[3];
     float max_abs;          // largest |coordinate| of any world-space triangle box
+    float bounds_lo[3];     // world-space bounding box of the scene and 1/extent (coherence sort keys)
+    float bounds_inv[3];
 };
 
 struct AcqDev {

@@ -40,11 +40,19 @@ struct TraceBuffers {
     int* queue_b;                  // [n_paths]
     int* counters;                 // [max_depth + 1]: counters[b] = live paths entering bounce b
     unsigned long long* trav_counters;   // nullptr, or {BVH node visits, triangle tests} accumulated over the call
+    // optional coherence sort of the surviving paths between bounces (nullptr = off): Morton key of the next
+    // ray's origin + direction octant, radix-sorted so neighbouring lanes traverse neighbouring rays
+    unsigned* sort_keys;           // [n_paths]
+    unsigned* sort_keys_tmp;       // [n_paths]
+    int* sort_queue_tmp;           // [n_paths]
+    void* sort_tmp;                // cub temporary storage
+    size_t sort_tmp_bytes;
 };
 
 // generate + max_depth x (intersect, shade, compact): scene::cast_rays (scene.cpp:50-183)
 void launch_trace(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, const TraceBuffers& tb, int sm_count, cudaStream_t stream,
                   int* launches);
+size_t trace_sort_tmp_bytes(int64_t n_paths);
 void launch_closest_hit(const SceneDev& sc, int64_t n, const float* d_from, const float* d_to, int32_t* d_tri, int32_t* d_mesh,
                         float* d_frac, float* d_point, float* d_normal, cudaStream_t stream);
 void launch_elements(const AcqDev& aq, const FrameDev& fr, float* d_pos, float* d_dir, cudaStream_t stream);

@@ -79,6 +79,13 @@ def c4():
              segments_per_s=st.segments / ms * 1e3, trace_segments_per_s=st.segments / stg["trace"] * 1e3, stage_ms=stg,
              mean_segments_per_path=st.segments / (8 * 512 * 16), bvh_node_visits_per_segment=sc.bvh_node_visits / sc.segments,
              triangle_tests_per_segment=sc.bvh_triangle_tests / sc.segments)
+    # the same with the wavefront radix-sorted by origin Morton code + direction octant between bounces
+    sim.set_option("count_traversal", 0)
+    sim.set_option("coherence_sort", 1)
+    ms2, st2 = timed(sim, poses, out)
+    stg2 = stages(sim, poses, out)
+    r["coherence_sort"] = dict(ms_per_call=ms2, frames_per_s=8 / ms2 * 1e3, segments_per_s=st2.segments / ms2 * 1e3,
+                               trace_segments_per_s=st2.segments / stg2["trace"] * 1e3, stage_ms=stg2)
     sim.close()
     return r
 

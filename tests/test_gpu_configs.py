@@ -137,3 +137,24 @@ def test_config5_long_scanlines_and_large_psf(api, O, assets_dirs):
     ref = o["rf"].T
     assert np.all(np.abs(rf - ref) <= _tol(ref)), np.abs(rf - ref).max()
     assert np.array_equal(g.T, O.envelope(O.convolve(img, ax, lat)))
+
+
+def test_traversal_options_do_not_change_results(api, O):
+    """coherence_sort (radix-sorted wavefront), the host SAH tree and the two-stream pipeline only change
+    scheduling / the acceleration structure: RF frames and segments stay bit-identical."""
+    from mcray_tracing_b200 import assets
+    A = assets.stress_scene_arrays(shells=8, nu=64, nv=32)
+    pose = np.concatenate([A["transducer_position"], A["transducer_angles"]])
+    poses = np.repeat(pose[None, :], 20, axis=0)
+    with api.Simulator(A, api.default_params(elements=64, samples=8)) as sim:
+        base = sim.simulate(poses, seed=5, first_frame=7)
+        segs0, n0 = sim.cast_rays(pose, seed=5, frame=7)
+        for opt, val in (("coherence_sort", 1), ("bvh_builder", 1), ("overlap", 1)):
+            sim.set_option(opt, val)
+            assert np.array_equal(sim.simulate(poses, seed=5, first_frame=7), base), opt
+            segs, n = sim.cast_rays(pose, seed=5, frame=7)
+            assert np.array_equal(n, n0) and np.array_equal(segs["tri_id"], segs0["tri_id"]), opt
+        sim.set_option("count_traversal", 1)
+        sim.simulate(poses, seed=5, first_frame=7)
+        st = sim.stats()
+        assert st.bvh_node_visits > st.segments and st.bvh_triangle_tests > 0
