@@ -120,6 +120,8 @@ struct mcrt_ctx {
     unsigned long long* d_steps = nullptr;
     unsigned long long* d_trav = nullptr;      // {node visits, triangle tests}, only when count_traversal
     bool count_traversal = false;
+    bool log_compress = false;             // rfimage.h:127-136, commented out in the reference
+    int* d_max_bits = nullptr;             // [cap_poses] per-image maximum (ordered-int encoding)
     bool coherence_sort = false;           // radix-sort surviving paths between bounces (rough scenes)
     float* d_rf_acc = nullptr;
     float* d_rf_tmp0 = nullptr;
@@ -163,7 +165,7 @@ void free_workspace(mcrt_ctx* c)
     if (c->tb.sort_tmp) cudaFree(c->tb.sort_tmp);
     c->tb.sort_tmp = nullptr; c->tb.sort_tmp_bytes = 0;
     dev_free(c->d_poses); dev_free(c->d_rf_acc); dev_free(c->d_rf_tmp0); dev_free(c->d_rf_tmp1); dev_free(c->d_rf_final);
-    dev_free(c->d_rf_t); dev_free(c->d_scan); dev_free(c->d_columns);
+    dev_free(c->d_rf_t); dev_free(c->d_scan); dev_free(c->d_columns); dev_free(c->d_max_bits);
     if (c->h_poses) cudaFreeHost(c->h_poses);
     c->h_poses = nullptr;
     c->cap_poses = 0;
@@ -191,6 +193,7 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
     dev_alloc(c->d_rf_final, n_px);
     if (c->params.rf_layout == 1) dev_alloc(c->d_rf_t, n_px);
     dev_alloc(c->d_scan, (size_t)n_poses * c->params.scan_rows * c->params.scan_cols);
+    dev_alloc(c->d_max_bits, (size_t)n_poses);
     c->columns_bytes = accumulate_columns_bytes(c->aq, n_poses);
     if (c->columns_bytes) dev_alloc(c->d_columns, c->columns_bytes / sizeof(float));
     CUDA_TRY(cudaMallocHost(&c->h_poses, sizeof(PoseTrig) * (size_t)n_poses));
@@ -229,6 +232,7 @@ void enqueue_image(mcrt_ctx* c, int pose0, int n, bool want_scan, cudaStream_t s
                                c->d_steps, c->d_columns + p0 * c->aq.rows, s, launches));
     launch_post(c->d_rf_acc + px0, n, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
                 c->d_rf_tmp0 + px0, c->d_rf_tmp1 + px0, c->d_rf_final + px0, s, launches);
+    if (c->log_compress) launch_log_compress(c->d_rf_final + px0, n, (int64_t)c->aq.elements * c->aq.rows, c->d_max_bits + pose0, s, launches);
     if (c->params.rf_layout == 1) launch_transpose(c->d_rf_final + px0, n, c->aq.elements, c->aq.rows, c->d_rf_t + px0, s, launches);
     if (want_scan)
         launch_scan_convert(c->d_rf_final + px0, n, c->aq.elements, c->aq.rows, c->d_map_x, c->d_map_y, c->params.scan_rows, c->params.scan_cols,
@@ -251,6 +255,7 @@ void enqueue_pipeline(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* l
         CUDA_TRY(cudaEventRecord(c->ev_c, s));
         launch_post(c->d_rf_acc, n, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
                     c->d_rf_tmp0, c->d_rf_tmp1, c->d_rf_final, s, launches);
+        if (c->log_compress) launch_log_compress(c->d_rf_final, n, (int64_t)c->aq.elements * c->aq.rows, c->d_max_bits, s, launches);
         if (c->params.rf_layout == 1) launch_transpose(c->d_rf_final, n, c->aq.elements, c->aq.rows, c->d_rf_t, s, launches);
         if (want_scan)
             launch_scan_convert(c->d_rf_final, n, c->aq.elements, c->aq.rows, c->d_map_x, c->d_map_y, c->params.scan_rows,
@@ -293,7 +298,7 @@ int pipeline_sub_batches(const mcrt_ctx* c, int n)
 int count_pipeline_launches(const mcrt_ctx* c, bool want_scan, int nsub)
 {
     return nsub * (c->aq.max_depth + 2 + post_launch_count(c->aq.elements, c->aq.rows, c->params.psf_lateral, 3, 1) + (c->params.rf_layout == 1 ? 1 : 0) +
-                   (want_scan ? 1 : 0));
+                   (c->log_compress ? 2 : 0) + (want_scan ? 1 : 0));
 }
 
 void run_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches)
@@ -695,6 +700,11 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
             c->sc.nodes = nb.nodes; c->sc.tris = nb.tris; c->sc.n_tri = nb.n_tri; c->sc.max_abs = nb.max_abs;
             return MCRT_OK;
         });
+    }
+    else if (n == "log_compress") {
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear();
+        c->log_compress = value != 0;
     }
     else if (n == "coherence_sort") {
         // changes the workspace and the captured graphs: drop both, they are rebuilt on the next call

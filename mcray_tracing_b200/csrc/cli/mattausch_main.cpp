@@ -3,7 +3,7 @@
 // the RF image (raw little-endian float32) and the scan-converted B-mode image (8-bit PGM, the
 // x255 conversion of rf_image::save, rfimage.h:142-148) instead of opening an imshow window.
 // Extensions (all optional, reference defaults otherwise):
-//   --frames N  --seed S  --elements E  --samples S  --deterministic  --out DIR  --device D
+//   --frames N  --seed S  --elements E  --samples S  --deterministic  --out DIR  --device D  --log-compress
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -39,7 +39,7 @@ int main(int argc, char** argv)
     }
     mcrt_params p;
     mcrt_default_params(&p);
-    int frames = 1, device = 0;
+    int frames = 1, device = 0, log_compress = 0;
     unsigned long long seed = 0;
     std::string out_dir = ".";
     for (int i = 2; i < argc; i++) {
@@ -52,6 +52,7 @@ int main(int argc, char** argv)
         else if (a == "--deterministic") p.deterministic = 1;
         else if (a == "--out") out_dir = next();
         else if (a == "--device") device = atoi(next());
+        else if (a == "--log-compress") log_compress = 1;        // rfimage.h:131-136 (commented out in the reference)
         else { printf("Incorrect argument list.\n"); return 0; }
     }
     mcrt_ctx* ctx = nullptr;
@@ -60,6 +61,7 @@ int main(int argc, char** argv)
         printf("The program found an error and will terminate.\nReason:\n%s\n", mcrt_last_error());
         return 0;
     }
+    if (log_compress) mcrt_set_option(ctx, "log_compress", 1);
     mcrt_info info;
     mcrt_get_info(ctx, &info);
     printf("%g us\n", info.max_travel_time_us);                      // main.cpp:76

@@ -630,6 +630,41 @@ __global__ void __launch_bounds__(MCRT_FUSED_THREADS) k_post_fused(const float* 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Log compression: the block the reference keeps commented out in rf_image::postprocess
+// (rfimage.h:127-136): max = minMaxLoc(intensities); I = log10(I + 1) / log10(max + 1), applied to the
+// envelope image before scan conversion.  Optional (mcrt_set_option "log_compress").
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int f2ord_img(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f_img(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void __launch_bounds__(256) k_image_max(const float* __restrict__ img, const int64_t px_per_image, int* __restrict__ max_bits)
+{
+    const float* I = img + (size_t)blockIdx.y * px_per_image;
+    float m = -3.0e38f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < px_per_image; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, __ldg(&I[i]));
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    __shared__ float s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, s[w]);
+        atomicMax(&max_bits[blockIdx.y], f2ord_img(m));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_log_compress(float* __restrict__ img, const int64_t px_per_image, const int* __restrict__ max_bits)
+{
+    const double ln10 = 2.30258509299404568402;
+    const double maxv = (double)ord2f_img(max_bits[blockIdx.y]);
+    const double den = mc_log(maxv + 1) / ln10;                               // std::log10(max + 1), double
+    float* I = img + (size_t)blockIdx.y * px_per_image;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < px_per_image; i += (int64_t)gridDim.x * blockDim.x) {
+        const float num = (float)(mc_log((double)(I[i] + 1)) / ln10);         // std::log10(float)
+        I[i] = (float)((double)num / den);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_copy(const float* __restrict__ in, const int64_t n, float* __restrict__ out)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i];
@@ -800,6 +835,22 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
     } else if (!(flags & 1)) {
         k_copy<<<grid1d(total, 256), 256, 0, stream>>>(cur, total, d_out);
         if (launches) (*launches)++;
+    }
+}
+
+void launch_log_compress(float* d_img, int n_images, int64_t px_per_image, int* d_max_bits, cudaStream_t stream, int* launches)
+{
+    // ordered-int encoding of -FLT_MAX-ish: any finite sample is larger
+    cudaMemsetAsync(d_max_bits, 0x80, sizeof(int) * (size_t)n_images, stream);
+    int gx = (int)((px_per_image + 256 * 8 - 1) / (256 * 8));
+    if (gx < 1) gx = 1;
+    if (gx > 1024) gx = 1024;
+    for (int i0 = 0; i0 < n_images; i0 += 65535) {
+        const int ni = n_images - i0 < 65535 ? n_images - i0 : 65535;
+        dim3 grid(gx, ni, 1);
+        k_image_max<<<grid, 256, 0, stream>>>(d_img + (size_t)i0 * px_per_image, px_per_image, d_max_bits + i0);
+        k_log_compress<<<grid, 256, 0, stream>>>(d_img + (size_t)i0 * px_per_image, px_per_image, d_max_bits + i0);
+        if (launches) (*launches) += 2;
     }
 }
 

@@ -879,6 +879,20 @@ void orc_envelope(float* rf, int32_t rows, int32_t cols)
     }
 }
 
+// rfimage.h:127-136 (commented out in the reference): max = minMaxLoc; I = log10(I + 1) / log10(max + 1)
+void orc_log_compress(float* rf, int32_t rows, int32_t cols)
+{
+    const double ln10 = 2.30258509299404568402;
+    float mx = -3.0e38f;
+    const size_t n = (size_t)rows * cols;
+    for (size_t i = 0; i < n; i++) mx = rf[i] > mx ? rf[i] : mx;           // NaN samples never win, like fmaxf
+    const double den = mc_log((double)mx + 1) / ln10;
+    for (size_t i = 0; i < n; i++) {
+        const float num = (float)(mc_log((double)(rf[i] + 1)) / ln10);
+        rf[i] = (float)((double)num / den);
+    }
+}
+
 // rfimage.h:183-215
 void orc_create_mapping(const orc_params* p, float* map_x, float* map_y)
 {

@@ -142,6 +142,8 @@ int64_t orc_accumulate(const orc_scene* s, const orc_params* p, const orc_volume
 /* rfimage.h:93-123 / :54-91 on a rows x cols row-major image, in place */
 void orc_convolve(float* rf, int32_t rows, int32_t cols, const float* axial, int32_t n_axial, const float* lateral, int32_t n_lateral);
 void orc_envelope(float* rf, int32_t rows, int32_t cols);
+/* rfimage.h:127-136, the log compression the reference keeps commented out; in place */
+void orc_log_compress(float* rf, int32_t rows, int32_t cols);
 /* rfimage.h:183-215: map_x (source row), map_y (source column), each scan_rows x scan_cols */
 void orc_create_mapping(const orc_params* p, float* map_x, float* map_y);
 /* rfimage.h:139: cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) restated (OpenCV 5-bit fixed-point weights) */

@@ -96,6 +96,7 @@ def oracle():
         L.orc_accumulate.argtypes = [C.c_void_p] * 6
         L.orc_convolve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
         L.orc_envelope.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.orc_log_compress.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.orc_create_mapping.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_scan_convert.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.orc_simulate_frame.restype = C.c_int64
@@ -313,6 +314,12 @@ def convolve(rf, ax, lat):
 def envelope(rf):
     out = np.ascontiguousarray(rf, np.float32).copy()
     oracle().orc_envelope(_p(out), out.shape[0], out.shape[1])
+    return out
+
+
+def log_compress(rf):
+    out = np.ascontiguousarray(rf, np.float32).copy()
+    oracle().orc_log_compress(_p(out), out.shape[0], out.shape[1])
     return out
 
 

@@ -158,3 +158,23 @@ def test_traversal_options_do_not_change_results(api, O):
         sim.simulate(poses, seed=5, first_frame=7)
         st = sim.stats()
         assert st.bvh_node_visits > st.segments and st.bvh_triangle_tests > 0
+
+
+def test_log_compression_option(api, O, assets_dirs):
+    """The log compression the reference keeps commented out (rfimage.h:127-136), as an option: applied to
+    the envelope image, so both rf_out and the scan-converted image change; bit-exact to the oracle."""
+    path = assets_dirs["sphere"] / "sphere.scene"
+    with api.Simulator(path, api.default_params(elements=512, samples=2)) as sim:
+        poses = np.repeat(sim.start_pose[None, :], 3, axis=0)
+        lin = sim.simulate(poses, seed=4, first_frame=0)
+        sim.set_option("log_compress", 1)
+        rf, scan = sim.simulate(poses, seed=4, first_frame=0, scan=True)
+        sim.set_option("log_compress", 0)
+        assert np.array_equal(sim.simulate(poses, seed=4, first_frame=0), lin)
+    mx, my = O.create_mapping(O.default_params(samples=2))
+    for i in range(len(poses)):
+        ref = O.log_compress(lin[i].T)                       # oracle layout [rows][cols]
+        assert np.array_equal(rf[i].T, ref, equal_nan=True)
+        assert np.array_equal(scan[i], O.scan_convert(ref, mx, my), equal_nan=True)
+    finite = rf[np.isfinite(rf)]
+    assert finite.max() == 1.0 and np.isfinite(rf).mean() > 0.99
