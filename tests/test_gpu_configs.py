@@ -178,3 +178,19 @@ def test_log_compression_option(api, O, assets_dirs):
         assert np.array_equal(scan[i], O.scan_convert(ref, mx, my), equal_nan=True)
     finite = rf[np.isfinite(rf)]
     assert finite.max() == 1.0 and np.isfinite(rf).mean() > 0.99
+
+
+def test_streaming_driver_matches_batched_call(api, assets_dirs):
+    """stream.FrameStreamer (pose stream in, frames out through pinned double buffers on one CUDA
+    stream) returns exactly the frames of one batched mcrt_simulate call, in order."""
+    from mcray_tracing_b200 import assets, stream
+    path = assets_dirs["ircad11"] / "santi-liver.scene"
+    poses = assets.sweep_poses(14)
+    with api.Simulator(path, api.default_params(elements=128, samples=4)) as sim:
+        ref, ref_scan = sim.simulate(poses, seed=3, first_frame=0, scan=True)
+        got, got_scan, tickets = [], [], []
+        fs = stream.FrameStreamer(sim, depth=3, frames_per_submit=2, scan=True, seed=3)
+        fs.run(stream.sweep_pose_stream(poses, 2), lambda t, rf, sc: (tickets.append(t), got.append(rf.copy()), got_scan.append(sc.copy())))
+    assert tickets == list(range(1, 8))
+    assert np.array_equal(np.concatenate(got), ref)
+    assert np.array_equal(np.concatenate(got_scan), ref_scan)
