@@ -2,9 +2,10 @@
 replacing the reference's interactive loop (inputmanager.cpp:61-122 moves the probe, main.cpp:92-152
 re-simulates and rf_image::show() displays -- SURVEY.md section 8f item 1).
 
-Frames are enqueued on a dedicated CUDA stream through mcrt_simulate_async and their results are
-copied into a ring of PINNED host buffers on the same stream, so frame k+1 is being traced while
-frame k is still travelling to the host; `get()` only waits for the event of the frame it returns.
+Frames are enqueued on a dedicated compute stream through mcrt_simulate_async; their results are
+copied into a ring of PINNED host buffers on a second (copy) stream that waits on the frame's event, so
+frame k+1 is being traced while frame k is still travelling over PCIe; `get()` only waits for the event
+of the frame it returns.
 The pipeline depth bounds the latency: a frame is at most `depth` submissions behind.
 """
 from __future__ import annotations
@@ -28,13 +29,14 @@ class FrameStreamer:
         self.seed = int(seed)
         self.dev = torch.device("cuda", sim.info.device if device is None else device)
         self.stream = torch.cuda.Stream(device=self.dev)
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
         shape = sim.rf_shape(self.n)
         sshape = (self.n, sim.info.scan_rows, sim.info.scan_cols)
         self._slots = []
         for _ in range(depth):
             slot = dict(rf_dev=torch.empty(shape, dtype=torch.float32, device=self.dev),
                         rf_host=torch.empty(shape, dtype=torch.float32, pin_memory=True),
-                        done=torch.cuda.Event())
+                        computed=torch.cuda.Event(), done=torch.cuda.Event())
             if self.scan:
                 slot["scan_dev"] = torch.empty(sshape, dtype=torch.float32, device=self.dev)
                 slot["scan_host"] = torch.empty(sshape, dtype=torch.float32, pin_memory=True)
@@ -56,11 +58,13 @@ class FrameStreamer:
         slot = self._slots[s]
         self.sim.simulate_device(P, slot["rf_dev"].data_ptr(), seed=self.seed, first_frame=self._frame,
                                  scan_ptr=slot["scan_dev"].data_ptr() if self.scan else None, stream=self.stream.cuda_stream, sync=False)
-        with torch.cuda.stream(self.stream):
+        slot["computed"].record(self.stream)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(slot["computed"])
             slot["rf_host"].copy_(slot["rf_dev"], non_blocking=True)
             if self.scan:
                 slot["scan_host"].copy_(slot["scan_dev"], non_blocking=True)
-            slot["done"].record(self.stream)
+            slot["done"].record(self.copy_stream)
         self._frame += self.n
         self._ticket += 1
         self._inflight.append((self._ticket, s))
