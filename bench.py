@@ -40,7 +40,7 @@ SCENE_REL = ("ircad11", "santi-liver.scene")
 def workload_config(frames_per_step: int, n_gpus: int) -> dict:
     return {
         "workload": "ircad11 (synthetic organs, 624640 triangles) santi-liver pose, 256 scanlines x 16 MC samples/element, "
-                    "465 RF rows, stochastic mode" + ("" if n_gpus == 1 else "; freehand probe sweep, contiguous pose blocks per rank, one NCCL gather of RF lines per step"),
+                    "465 RF rows, stochastic mode" + ("" if n_gpus == 1 else "; freehand probe sweep, contiguous pose blocks per rank, one NCCL gather of RF lines per step (on its own stream: the gather of step k overlaps the simulation of step k+1, every gather inside a timed interval)"),
         "elements": ELEMENTS, "samples_per_element": SAMPLES, "max_depth": 10, "rf_rows": 465,
         "frames_per_step_per_gpu": frames_per_step,
         "parallelism": f"pose-sharded x{n_gpus}" if n_gpus > 1 else "single GPU",
@@ -214,17 +214,31 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     sizes = sweep.all_shard_sizes(F * world, world)
     seed = 1234
     st = torch.cuda.Stream(device=dev)
-    out = torch.empty((F, cols, rows), dtype=torch.float32, device=dev)
+    comm = torch.cuda.Stream(device=dev)
+    # two output buffers: the gather of step k (comm stream) overlaps the simulation of step k+1 (stream st)
+    outs = [torch.empty((F, cols, rows), dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
+    out = outs[0]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     frames_per_step_total = F * world
-    gathered = None
+    recv = torch.empty((world * F, cols, rows), dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
+    gather_done = [torch.cuda.Event() for _ in range(2)]
+    pending = [False, False]
 
-    def step(k: int):
-        nonlocal gathered
-        sim.simulate_device(poses, out.data_ptr(), seed=seed, first_frame=k * frames_per_step_total + my_first, stream=st.cuda_stream, sync=False)
-        if world > 1:
-            with torch.cuda.stream(st):
-                gathered = sweep.gather_lines(out, sizes, dst=0)
+    def compute(k: int, i: int):
+        """simulate this rank's pose block of step k into outs[i % 2] on stream st"""
+        b = i % len(outs)
+        if pending[b]:                                   # the gather that last read this buffer must be done
+            st.wait_event(gather_done[b]); pending[b] = False
+        sim.simulate_device(poses, outs[b].data_ptr(), seed=seed, first_frame=k * frames_per_step_total + my_first, stream=st.cuda_stream, sync=False)
+
+    def gather(i: int, after: "torch.cuda.Event"):
+        """ONE NCCL gather of the finished RF lines of outs[i % 2] to rank 0, on the comm stream, not before `after`"""
+        b = i % len(outs)
+        comm.wait_event(after)
+        with torch.cuda.stream(comm):
+            sweep.gather_lines(outs[b], sizes, dst=0, out=recv)
+            gather_done[b].record(comm)
+        pending[b] = True
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -232,24 +246,38 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    done_ev = torch.cuda.Event()
     for k in range(max(args.warmup, 3)):
-        step(k)
+        compute(k, k)
+        if world > 1:
+            done_ev.record(st)
+            gather(k, done_ev)
     sync_all()
+    pending[0] = pending[1] = False
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # Timed region.  Interval k = [start_k, end_k] on stream st, the L2 flush before start_k outside it.  N > 1: the
+    # gather of step k-1 is released only after start_k and end_k is recorded only after st has waited for it, so
+    # every gather lies entirely inside a timed interval (overlapped with the next step's simulation); the last
+    # step's gather gets an interval of its own (index K).
+    n_iv = args.steps + (1 if world > 1 else 0)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_iv)]
     seg_total = 0
     step_total = 0
     launches = 0
     t_wall0 = time.perf_counter()
-    for k in range(args.steps):
+    for k in range(n_iv):
         with torch.cuda.stream(st):
             flush.fill_(float(k))                                          # evict L2 (not timed)
             ev[k][0].record(st)
-        step(1000 + k)
+        if world > 1 and k > 0:
+            gather(k - 1, ev[k][0])
+        if k < args.steps:
+            compute(1000 + k, k)
+        if world > 1 and k > 0:
+            st.wait_event(gather_done[(k - 1) % 2]); pending[(k - 1) % 2] = False
         ev[k][1].record(st)
-        s = None
     sync_all()
     t_wall = time.perf_counter() - t_wall0
     ms_steps = [a.elapsed_time(b) for a, b in ev]

@@ -155,6 +155,13 @@ int mcrt_simulate(mcrt_ctx* ctx, const mcrt_pose* poses, int32_t n_poses, uint64
 int mcrt_simulate_async(mcrt_ctx* ctx, const mcrt_pose* poses, int32_t n_poses, uint64_t seed, uint64_t first_frame,
                         float* rf_out_dev, float* scan_out_dev, void* cuda_stream);
 
+/* One pose, only the scanline block [first_element, first_element + n_elements): the unit of the
+ * scanline-block partition of a single frame across GPUs.  The block's right-hand PSF halo (psf_lateral - 1
+ * scanlines) is re-traced locally, so the result equals the same scanlines of mcrt_simulate bit for bit.
+ * rf_out: n_elements x rows float32, scanline-major, host or device pointer. */
+int mcrt_simulate_scanlines(mcrt_ctx* ctx, const mcrt_pose* pose, uint64_t seed, uint64_t frame, int32_t first_element,
+                            int32_t n_elements, float* rf_out);
+
 /* parity hook for scene::cast_rays (scene.cpp:50-183): segments[elements][samples][max_depth],
  * n_segments[elements][samples]; host pointers. */
 int mcrt_trace_debug(mcrt_ctx* ctx, const mcrt_pose* pose, uint64_t seed, uint64_t frame, mcrt_segment* segments,

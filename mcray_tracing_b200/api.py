@@ -66,7 +66,7 @@ assert SEGMENT_DTYPE.itemsize == 72
 EXPORTS = ["mcrt_default_params", "mcrt_create", "mcrt_create_from_arrays", "mcrt_destroy", "mcrt_last_error", "mcrt_get_info",
            "mcrt_get_stats", "mcrt_set_option", "mcrt_simulate", "mcrt_simulate_async", "mcrt_trace_debug", "mcrt_closest_hit",
            "mcrt_transducer_elements", "mcrt_accumulate", "mcrt_postprocess", "mcrt_scan_convert", "mcrt_get_psf_taps",
-           "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe", "mcrt_load_obj", "mcrt_scene_probe", "mcrt_host_tables"]
+           "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe", "mcrt_load_obj", "mcrt_scene_probe", "mcrt_host_tables", "mcrt_simulate_scanlines"]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
@@ -100,6 +100,7 @@ def lib():
         L.mcrt_simulate.argtypes = [vp, vp, C.c_int32, C.c_uint64, C.c_uint64, vp, vp]
         L.mcrt_simulate_async.argtypes = [vp, vp, C.c_int32, C.c_uint64, C.c_uint64, vp, vp, vp]
         L.mcrt_trace_debug.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, vp]
+        L.mcrt_simulate_scanlines.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, vp]
         L.mcrt_closest_hit.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
         L.mcrt_transducer_elements.argtypes = [vp, vp, vp, vp]
         L.mcrt_accumulate.argtypes = [vp, vp, vp, vp]
@@ -225,6 +226,17 @@ class Simulator:
         else:
             _check(lib().mcrt_simulate_async(self.h, _p(P), n, int(seed), int(first_frame), C.c_void_p(rf_ptr),
                                              C.c_void_p(scan_ptr) if scan_ptr else None, C.c_void_p(stream) if stream else None))
+
+    def simulate_scanlines(self, pose, first_element: int, n_elements: int, seed: int = 0, frame: int = 0, rf_ptr: int | None = None):
+        """One pose, scanline block [first_element, first_element + n_elements) -> [n_elements, rows] (host array, or
+        written to the device address rf_ptr)."""
+        P = make_poses(pose)
+        if rf_ptr is not None:
+            _check(lib().mcrt_simulate_scanlines(self.h, _p(P), int(seed), int(frame), int(first_element), int(n_elements), C.c_void_p(rf_ptr)))
+            return None
+        out = np.empty((n_elements, self.rows), np.float32)
+        _check(lib().mcrt_simulate_scanlines(self.h, _p(P), int(seed), int(frame), int(first_element), int(n_elements), _p(out)))
+        return out
 
     # -- parity hooks ----------------------------------------------------------------------------
     def cast_rays(self, pose, seed: int = 0, frame: int = 0):

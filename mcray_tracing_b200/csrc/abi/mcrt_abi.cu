@@ -736,6 +736,51 @@ int mcrt_simulate_async(mcrt_ctx* ctx, const mcrt_pose* poses, int32_t n_poses, 
     return simulate_impl(ctx, poses, n_poses, seed, first_frame, rf_out_dev, scan_out_dev, (cudaStream_t)cuda_stream, true);
 }
 
+int mcrt_simulate_scanlines(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, uint64_t frame, int32_t first_element, int32_t n_elements,
+                            float* rf_out)
+{
+    if (!c || !pose || !rf_out) return fail(MCRT_ERR_INVALID, "mcrt_simulate_scanlines: null argument");
+    if (first_element < 0 || n_elements < 1 || first_element + n_elements > c->aq.elements)
+        return fail(MCRT_ERR_INVALID, "mcrt_simulate_scanlines: scanline block out of range");
+    if (c->log_compress) return fail(MCRT_ERR_INVALID, "mcrt_simulate_scanlines: log_compress needs the whole frame (its maximum)");
+    return guarded("mcrt_simulate_scanlines", [&]() {
+        CUDA_TRY(cudaSetDevice(c->device));
+        ensure_workspace(c, 1);
+        const int E = c->aq.elements, kl = c->params.psf_lateral;
+        // the forward-looking lateral taps of the block's last scanlines reach Kl-1 scanlines to the right:
+        // recompute that halo locally instead of exchanging it (Philox keys make it bit-identical)
+        const int e0 = first_element;
+        const int e1 = (e0 + n_elements + kl - 1 < E) ? e0 + n_elements + kl - 1 : E;
+        const int n_local = e1 - e0;
+        AcqDev aq = c->aq;
+        aq.elements = n_local;
+        aq.element_offset = e0;
+        c->h_poses[0] = pose_trig(*pose);
+        if (c->upload_pending) { CUDA_TRY(cudaEventSynchronize(c->ev_up)); c->upload_pending = false; }
+        c->h_seed_frame[0] = seed; c->h_seed_frame[1] = frame;
+        cudaStream_t s = c->stream;
+        CUDA_TRY(cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->d_seed_frame, c->h_seed_frame, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+        FrameDev fr;
+        fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos + e0; fr.seed_frame = c->d_seed_frame; fr.n_poses = 1; fr.frame_offset = 0;
+        int launches = 0;
+        CUDA_TRY(cudaMemsetAsync(c->tb.counters, 0, sizeof(int) * (size_t)kMaxSub * (c->aq.max_depth + 1), s));
+        CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, sizeof(unsigned long long), s));
+        launch_trace(c->sc, aq, fr, c->tb, c->sm_count, s, &launches);
+        CUDA_TRY(launch_accumulate(c->sc, aq, c->d_volume, c->tb.segments, c->tb.n_segments, 1, c->d_rf_acc, c->d_steps, c->d_columns, s, &launches));
+        launch_post(c->d_rf_acc, 1, n_local, aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, kl, 3, c->d_rf_tmp0, c->d_rf_tmp1,
+                    c->d_rf_final, s, &launches, e0, E);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(rf_out, c->d_rf_final, sizeof(float) * (size_t)n_elements * aq.rows,
+                                 is_device_pointer(rf_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        c->stats = mcrt_stats{};
+        c->stats.poses = 1; c->stats.kernel_launches = launches;
+        c->stats_pending = false;
+        return MCRT_OK;
+    });
+}
+
 int mcrt_trace_debug(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, uint64_t frame, mcrt_segment* segments, int32_t* n_segments)
 {
     if (!c || !pose || !segments || !n_segments) return fail(MCRT_ERR_INVALID, "mcrt_trace_debug: null argument");

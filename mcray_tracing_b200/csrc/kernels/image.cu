@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(256) k_psf_axial(const float* __restrict__ in,
 // scanlines; lanes walk consecutive rows, so every load/store is coalesced and no shared memory is needed.
 __global__ void __launch_bounds__(256) k_psf_lateral(const float* __restrict__ raw, const float* __restrict__ axial_buf, const int cols,
                                                     const int rows, const float* __restrict__ taps, const int ka, const int kl,
-                                                    float* __restrict__ out)
+                                                    const int col_offset, const int cols_total, float* __restrict__ out)
 {
     __shared__ float s_taps[MCRT_MAX_TAPS];
     for (int i = threadIdx.x; i < kl; i += blockDim.x) s_taps[i] = taps[i];
@@ -378,7 +378,8 @@ __global__ void __launch_bounds__(256) k_psf_lateral(const float* __restrict__ r
     const float* ax = axial_buf + img;
     const bool row_ok = r >= ka && r < rows - ka;
     // does any of the 8 scanlines get convolved at all?
-    const bool any = row_ok && (c0 + MCRT_PSF_R > kl / 2) && (c0 < cols - kl);
+    // border rule in GLOBAL scanline indices (a scanline-block run holds scanlines col_offset.. of cols_total)
+    const bool any = row_ok && (col_offset + c0 + MCRT_PSF_R > kl / 2) && (col_offset + c0 < cols_total - kl);
     float acc[MCRT_PSF_R], win[MCRT_PSF_R];
     if (any) {
         auto ld = [&](int c) -> float { return c < cols ? __ldg(&ax[(size_t)c * rows + r]) : 0.0f; };
@@ -402,7 +403,7 @@ __global__ void __launch_bounds__(256) k_psf_lateral(const float* __restrict__ r
         const int c = c0 + j;
         if (c >= cols) break;
         const size_t o = img + (size_t)c * rows + r;
-        out[o] = (any && c >= kl / 2 && c < cols - kl) ? acc[j] : __ldg(&raw[o]);
+        out[o] = (any && col_offset + c >= kl / 2 && col_offset + c < cols_total - kl) ? acc[j] : __ldg(&raw[o]);
     }
 }
 
@@ -500,7 +501,7 @@ template <int KA, int KL>
 __global__ void __launch_bounds__(MCRT_FUSED_THREADS) k_post_fused(const float* __restrict__ in, const int cols, const int rows,
                                                                   const float* __restrict__ ax_taps, const int ka,
                                                                   const float* __restrict__ lat_taps, const int kl, const int flags,
-                                                                  const int TC, float* __restrict__ out)
+                                                                  const int TC, const int col_offset, const int cols_total, float* __restrict__ out)
 {
     extern __shared__ float sm[];
     __shared__ float s_taps_a[MCRT_MAX_TAPS], s_taps_l[MCRT_MAX_TAPS];
@@ -559,7 +560,7 @@ __global__ void __launch_bounds__(MCRT_FUSED_THREADS) k_post_fused(const float* 
         // lateral pass (rfimage.h:111-122), in place over the raw tile; borders keep the raw samples (B-9)
         for (int c = w; c < TC; c += NW) {
             const int gc = c0 + c;
-            if (gc >= cols || !(gc >= kl / 2 && gc < cols - kl)) continue;
+            if (gc >= cols || !(col_offset + gc >= kl / 2 && col_offset + gc < cols_total - kl)) continue;   // global indices
             float* dst = s_out + (size_t)c * rows;
             if (KL > 0) {
                 float tl[KL > 0 ? KL : 1];
@@ -786,8 +787,10 @@ int post_launch_count(int cols, int rows, int n_lateral, int flags, int n_images
 }
 
 void launch_post(const float* d_in, int n_images, int cols, int rows, const float* d_axial, int n_axial, const float* d_lateral,
-                 int n_lateral, int flags, float* d_tmp0, float* d_tmp1, float* d_out, cudaStream_t stream, int* launches)
+                 int n_lateral, int flags, float* d_tmp0, float* d_tmp1, float* d_out, cudaStream_t stream, int* launches, int col_offset,
+                 int cols_total)
 {
+    if (cols_total <= 0) { col_offset = 0; cols_total = cols; }
     const int64_t n_scanlines = (int64_t)n_images * cols;
     const int64_t total = n_scanlines * rows;
     size_t smem = 0;
@@ -801,9 +804,9 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
         // whole scanlines fit shared memory: one pass over HBM
         dim3 grid((cols + tc - 1) / tc, n_images, 1);
         if (n_axial == 7 && n_lateral == 13)      // the reference's psf<7,13,...> (main.cpp:34)
-            k_post_fused<7, 13><<<grid, MCRT_FUSED_THREADS, smem, stream>>>(d_in, cols, rows, d_axial, 7, d_lateral, 13, flags, tc, d_out);
+            k_post_fused<7, 13><<<grid, MCRT_FUSED_THREADS, smem, stream>>>(d_in, cols, rows, d_axial, 7, d_lateral, 13, flags, tc, col_offset, cols_total, d_out);
         else
-            k_post_fused<0, 0><<<grid, MCRT_FUSED_THREADS, smem, stream>>>(d_in, cols, rows, d_axial, n_axial, d_lateral, n_lateral, flags, tc, d_out);
+            k_post_fused<0, 0><<<grid, MCRT_FUSED_THREADS, smem, stream>>>(d_in, cols, rows, d_axial, n_axial, d_lateral, n_lateral, flags, tc, col_offset, cols_total, d_out);
         if (launches) (*launches)++;
         return;
     }
@@ -821,7 +824,7 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
         }
         float* dst = (flags & 2) ? d_tmp1 : d_out;
         dim3 gl((rows + 255) / 256, (cols + MCRT_PSF_R - 1) / MCRT_PSF_R, n_images);
-        k_psf_lateral<<<gl, 256, 0, stream>>>(cur, d_tmp0, cols, rows, d_lateral, n_axial, n_lateral, dst);
+        k_psf_lateral<<<gl, 256, 0, stream>>>(cur, d_tmp0, cols, rows, d_lateral, n_axial, n_lateral, col_offset, cols_total, dst);
         cur = dst;
         if (launches) (*launches)++;
     }

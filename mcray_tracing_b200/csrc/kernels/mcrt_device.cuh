@@ -69,7 +69,7 @@ struct AcqDev {
     double max_travel_time_us;
     double speed;           // (double)speed_of_sound
     int deterministic;
-    int pad;
+    int element_offset;     // global index of local element 0 (scanline-block runs; 0 otherwise): RNG key, PSF borders
 };
 
 struct PoseTrigDev { float px, py, pz, cz, sz, cx, sx, cy, sy, pad0, pad1, pad2; };   // = mcrt::PoseTrig, 48 B

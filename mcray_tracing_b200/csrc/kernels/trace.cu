@@ -97,7 +97,7 @@ __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq
         const int4 organ = sh.mesh_info[h.mesh];
         const float3 hit_point = v_interpolate3(from_test, to, h.fraction);      // m_hitPointWorld
         const float3 normal = hit_normal(h);
-        const mc_u32x4 b0 = mc_rng_block(seed, frame, (uint32_t)element, (uint32_t)sample, (uint32_t)bounce, 0);
+        const mc_u32x4 b0 = mc_rng_block(seed, frame, (uint32_t)(element + aq.element_offset), (uint32_t)sample, (uint32_t)bounce, 0);
         // scene.cpp:132-139: penetration q = |N(0, thickness_inside)| (Box-Muller on block 0 words 0,1)
         float q = 0.0f;
         const float thickness = sh.materials[organ.x].thickness;
@@ -130,7 +130,7 @@ __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq
             random_angle = rp_power_cosine_variate((int)after.shininess, mc_u01d(b0.v[2]));
             bool ok = false;
             for (uint32_t attempt = 0; attempt < MC_RNG_BLOCKS_PER_BOUNCE - 1 && !ok; attempt++) {
-                const mc_u32x4 b = mc_rng_block(seed, frame, (uint32_t)element, (uint32_t)sample, (uint32_t)bounce, 1 + attempt);
+                const mc_u32x4 b = mc_rng_block(seed, frame, (uint32_t)(element + aq.element_offset), (uint32_t)sample, (uint32_t)bounce, 1 + attempt);
                 ok = rp_random_unit_vector_attempt(normal, random_angle, mc_u01d(b.v[0]), mc_u01d(b.v[1]), random_normal);
             }
             if (!ok) random_normal = normal;

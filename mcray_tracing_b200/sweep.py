@@ -28,9 +28,11 @@ def all_shard_sizes(n_items: int, world_size: int) -> list[int]:
     return [shard_bounds(n_items, world_size, r)[1] - shard_bounds(n_items, world_size, r)[0] for r in range(world_size)]
 
 
-def gather_lines(local: torch.Tensor, sizes: list[int], group=None, dst: int = 0) -> torch.Tensor | None:
+def gather_lines(local: torch.Tensor, sizes: list[int], group=None, dst: int = 0, out: torch.Tensor | None = None) -> torch.Tensor | None:
     """Gather per-rank blocks [sizes[r], ...] on `dst` into [sum(sizes), ...] with one collective.
-    Ragged blocks are padded to the largest block so a single dist.gather / all_gather suffices."""
+    Ragged blocks are padded to the largest block so a single dist.gather / all_gather suffices.
+    `out` (rank `dst` only): a preallocated [world * max(sizes), ...] receive buffer, so a steady-state loop
+    that runs the gather on its own stream allocates nothing."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     if world == 1:
@@ -43,7 +45,10 @@ def gather_lines(local: torch.Tensor, sizes: list[int], group=None, dst: int = 0
     else:
         padded = local.contiguous()
     if rank == dst:
-        out = local.new_empty((world * max_n,) + tail)
+        if out is None:
+            out = local.new_empty((world * max_n,) + tail)
+        elif tuple(out.shape) != (world * max_n,) + tail or not out.is_contiguous():
+            raise ValueError("gather_lines: out must be a contiguous [world * max(sizes), ...] tensor")
         dist.gather(padded, list(out.view((world, max_n) + tail).unbind(0)), dst=dst, group=group)
         if all(s == max_n for s in sizes):
             return out
@@ -68,3 +73,22 @@ def run_sweep(simulate_block: Callable[[np.ndarray, int, torch.Tensor], None], p
     if world == 1:
         return local
     return gather_lines(local, all_shard_sizes(n, world), group=group, dst=dst)
+
+
+def run_frame_scanline_blocks(simulate_block: Callable[[int, int, torch.Tensor], None], n_elements: int, rows: int,
+                              device: torch.device, group=None, dst: int = 0) -> torch.Tensor | None:
+    """ONE frame partitioned by scanline blocks (the single-pose latency partition): rank r simulates the
+    contiguous scanline block `shard_bounds(n_elements, world, r)`; `simulate_block(first_element, n, out)`
+    must fill `out` ([n, rows], on `device`) -- on a GPU that is
+    api.Simulator.simulate_scanlines(pose, first_element, n, rf_ptr=out.data_ptr()), which re-traces the
+    block's right-hand PSF halo locally (no halo exchange).  The same single gather as the pose sweep then
+    assembles [n_elements, rows] on rank `dst` (None elsewhere); bit-identical to the unpartitioned frame."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    b, e = shard_bounds(n_elements, world, rank)
+    local = torch.empty((e - b, rows), dtype=torch.float32, device=device)
+    if e > b:
+        simulate_block(b, e - b, local)
+    if world == 1:
+        return local
+    return gather_lines(local, all_shard_sizes(n_elements, world), group=group, dst=dst)

@@ -194,3 +194,29 @@ def test_streaming_driver_matches_batched_call(api, assets_dirs):
     assert tickets == list(range(1, 8))
     assert np.array_equal(np.concatenate(got), ref)
     assert np.array_equal(np.concatenate(got_scan), ref_scan)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(elements=96, samples=4),                                                     # fused PSF+envelope kernel (465 rows)
+    dict(elements=70, samples=2, axial_scale=5.0, psf_axial=15, psf_lateral=9),       # long-scanline kernels (2 k+ rows)
+], ids=["short-fused", "long-split"])
+def test_scanline_block_partition_equals_whole_frame(api, assets_dirs, kw):
+    """SURVEY 8(e) secondary partition: ONE frame split into scanline blocks (what each of G ranks would run,
+    mcrt_simulate_scanlines) and concatenated is bit-identical to mcrt_simulate of the whole frame, for every
+    G incl. ragged splits and blocks narrower than the PSF halo.  The halo is re-traced, never exchanged."""
+    from mcray_tracing_b200 import sweep
+    path = assets_dirs["ircad11"] / "santi-liver-rough.scene"
+    with api.Simulator(path, api.default_params(**kw)) as sim:
+        pose = sim.start_pose
+        whole = sim.simulate(pose[None, :], seed=11, first_frame=5)[0]
+        E = sim.cols
+        for world in (1, 2, 3, 8, 16):
+            parts = []
+            for r in range(world):
+                b, e = sweep.shard_bounds(E, world, r)
+                parts.append(sim.simulate_scanlines(pose, b, e - b, seed=11, frame=5))
+            assert np.array_equal(np.concatenate(parts), whole), f"world={world}"
+        # the batched entry point afterwards still gives the same frame (no state leaks from the block runs)
+        assert np.array_equal(sim.simulate(pose[None, :], seed=11, first_frame=5)[0], whole)
+        with pytest.raises(api.McrtError):
+            sim.simulate_scanlines(pose, E - 2, 3)

@@ -221,6 +221,51 @@ def test_sweep_gather_world_size_2_gloo(tmp_path, n_poses):
     assert f"OK {n_poses}" in outs[0][0]
 
 
+_WORKER_SCANLINES = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from mcray_tracing_b200 import sweep
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+E, rows, kl = int(sys.argv[1]), 5, 4
+raw = torch.arange(E * rows, dtype=torch.float32).reshape(E, rows) % 7.0        # what tracing scanline e yields: a pure function of e
+taps = torch.tensor([0.5, 0.25, 0.125, 0.0625])
+def lateral(block, first, total):                                                # forward-looking taps, raw borders (rfimage.h:111-122)
+    out = block.clone()
+    for c in range(block.shape[0]):
+        g = first + c
+        if g >= kl // 2 and g < total - kl and c + kl <= block.shape[0]:
+            out[c] = sum(block[c + k] * taps[k] for k in range(kl))
+    return out
+def fake(first, n, out):                  # stands in for Simulator.simulate_scanlines: re-traces its right-hand halo locally
+    e1 = min(first + n + kl - 1, E)
+    out[:] = lateral(raw[first:e1], first, E)[:n]
+res = sweep.run_frame_scanline_blocks(fake, E, rows, torch.device("cpu"))
+if dist.get_rank() == 0:
+    assert res.shape == (E, rows) and torch.equal(res, lateral(raw, 0, E)), "scanline-block frame differs from the whole frame"
+    print("OK", E)
+else:
+    assert res is None
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("n_elements", [16, 9])
+def test_frame_scanline_blocks_world_size_2_gloo(tmp_path, n_elements):
+    """SURVEY 8(e) secondary partition, host logic: contiguous scanline blocks + recomputed halo + one gather."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker_scanlines.py"
+    script.write_text(_WORKER_SCANLINES.format(root=str(ROOT)))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), str(n_elements)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=180) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e[-2000:]
+    assert f"OK {n_elements}" in outs[0][0]
+
+
 # ---- closed-form known answers for the oracle ----------------------------------------------------------
 def _box_scene(O, half=2.0):
     v = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], np.float32) * half
