@@ -108,6 +108,8 @@ typedef struct mcrt_info {
     int32_t sm_count;
     float start_pose[6];      /* the scene file's transducerPosition / transducerAngles */
     double axial_resolution_mm, time_step_us, row_period_us, max_travel_time_us;
+    int32_t voxel_fma_division; /* 1: the 3-instruction voxel index passed its exhaustive check for this resolution and is in use */
+    int32_t reserved0;
 } mcrt_info;
 
 typedef struct mcrt_stats {   /* of the most recent mcrt_simulate call */

@@ -48,7 +48,7 @@ class Info(C.Structure):
     _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("scan_rows", C.c_int32), ("scan_cols", C.c_int32), ("n_materials", C.c_int32),
                 ("n_meshes", C.c_int32), ("n_triangles", C.c_int64), ("n_bvh_nodes", C.c_int64), ("device", C.c_int32),
                 ("sm_count", C.c_int32), ("start_pose", C.c_float * 6), ("axial_resolution_mm", C.c_double), ("time_step_us", C.c_double),
-                ("row_period_us", C.c_double), ("max_travel_time_us", C.c_double)]
+                ("row_period_us", C.c_double), ("max_travel_time_us", C.c_double), ("voxel_fma_division", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -237,6 +237,12 @@ class Simulator:
         out = np.empty((n_elements, self.rows), np.float32)
         _check(lib().mcrt_simulate_scanlines(self.h, _p(P), int(seed), int(frame), int(first_element), int(n_elements), _p(out)))
         return out
+
+    def get_info(self) -> Info:
+        """mcrt_get_info, re-read (options can change what it reports)."""
+        info = Info()
+        _check(lib().mcrt_get_info(self.h, C.byref(info)))
+        return info
 
     # -- parity hooks ----------------------------------------------------------------------------
     def cast_rays(self, pose, seed: int = 0, frame: int = 0):

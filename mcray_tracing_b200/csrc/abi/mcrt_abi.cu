@@ -106,6 +106,7 @@ struct mcrt_ctx {
     LbvhResult bvh{};
     float2* d_volume = nullptr;        // owned by the process-wide cache
     float2* d_elem_sincos = nullptr;
+    bool voxel_fma_validated = false;
     float* d_axial = nullptr;
     float* d_lateral = nullptr;
     float* d_map_x = nullptr;
@@ -514,6 +515,12 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     CUDA_TRY(cudaMemcpy(c->d_map_y, my.data(), sizeof(float) * my.size(), cudaMemcpyHostToDevice));
     c->d_volume = device_volume(device, c->stream);
     CUDA_TRY(init_image_kernels());
+    {   // enable the 3-instruction voxel index only if it is provably the reference's for this resolution
+        bool ok = false;
+        CUDA_TRY(validate_fma_division(c->aq.vol_resolution, &ok));
+        c->voxel_fma_validated = ok;
+        c->aq.voxel_fma_division = ok ? 1 : 0;
+    }
 
     dev_alloc(c->d_seed_frame, 2);
     dev_alloc(c->d_trav, 2);
@@ -635,6 +642,7 @@ int mcrt_get_info(const mcrt_ctx* c, mcrt_info* info)
     for (int i = 0; i < 6; i++) info->start_pose[i] = c->scene.start_pose[i];
     info->axial_resolution_mm = c->dv.axial_resolution_mm; info->time_step_us = c->dv.time_step_us;
     info->row_period_us = c->dv.row_period_us; info->max_travel_time_us = c->dv.max_travel_time_us;
+    info->voxel_fma_division = c->aq.voxel_fma_division;
     return MCRT_OK;
 }
 
@@ -718,6 +726,12 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
         c->graphs.clear();
         c->count_traversal = value != 0;
         c->tb.trav_counters = c->count_traversal ? c->d_trav : nullptr;
+    }
+    else if (n == "voxel_fma_division") {
+        // A/B switch; can only be turned on for a resolution that passed the exhaustive check at mcrt_create
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear();
+        c->aq.voxel_fma_division = (value != 0 && c->voxel_fma_validated) ? 1 : 0;
     }
     else if (n == "max_batch_poses") { if (value < 1) return fail(MCRT_ERR_INVALID, "max_batch_poses must be >= 1"); c->max_batch_poses = (int)value; }
     else return fail(MCRT_ERR_INVALID, "unknown option '" + n + "'");

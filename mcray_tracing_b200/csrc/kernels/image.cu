@@ -51,6 +51,47 @@ __device__ __forceinline__ uint32_t voxel_linear(float3 p, float resolution, flo
     return ((uint32_t)(ix & 255) << 16) | ((uint32_t)(iy & 255) << 8) | (uint32_t)(iz & 255);
 }
 
+// Correctly rounded coord / resolution from three FP32 instructions (Markstein's FMA division step):
+//   q0 = coord * y (y = fl(1/resolution)),  r = fma(-q0, resolution, coord) (exact residual),  q = fma(r, y, q0).
+// For a fixed divisor this equals the IEEE quotient except where the residual underflows (|coord| < ~1e-31), and
+// there both truncate to 0.  It is not taken on faith: k_validate_fma_division checks, for the context's actual
+// resolution and ALL 2^32 float bit patterns, that the voxel index byte equals the one from the IEEE division
+// (a few ms at mcrt_create); a resolution that fails keeps the guarded path above.
+__device__ __forceinline__ float div_fma(float x, float resolution, float y)
+{
+    const float q0 = x * y;
+    const float r = __fmaf_rn(-q0, resolution, x);
+    return __fmaf_rn(r, y, q0);
+}
+
+// |q| < 2^31 on all three axes is established per segment by the caller, so the 32-bit conversion is the
+// truncation of volume.h:49-51 and `& 255` its `% 256`.
+__device__ __forceinline__ uint32_t voxel_linear_fma(float3 p, float resolution, float y)
+{
+    const int ix = __float2int_rz(div_fma(p.x, resolution, y));
+    const int iy = __float2int_rz(div_fma(p.y, resolution, y));
+    const int iz = __float2int_rz(div_fma(p.z, resolution, y));
+    // (ix & 255) << 16 | (iy & 255) << 8 | (iz & 255) as two byte permutes
+    const uint32_t zy = __byte_perm((uint32_t)iz, (uint32_t)iy, 0x0040);          // b0 = iz.b0, b1 = iy.b0 (b2, b3 dropped below)
+    return __byte_perm(zy, (uint32_t)ix & 255u, 0x7410);                          // b2 = ix.b0, b3 = 0
+}
+
+__global__ void __launch_bounds__(256) k_validate_fma_division(const float resolution, unsigned int* __restrict__ mismatches)
+{
+    const float y = 1.0f / resolution;
+    unsigned int bad = 0;
+    // thread t checks the 256 bit patterns t * 256 .. t * 256 + 255
+    const uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) << 8;
+    for (uint32_t k = 0; k < 256u; k++) {
+        const float x = __uint_as_float(base + k);
+        const float qe = x / resolution;
+        if (!(fabsf(qe) < 2147483648.0f)) continue;      // beyond 2^31 (or non-finite) the caller never takes the FMA path
+        const float q = div_fma(x, resolution, y);
+        bad += (__float2int_rz(qe) & 255) != (__float2int_rz(q) & 255);
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Echo accumulation (main.cpp:106-144 + rf_image::add_echo, rfimage.h:33-40), no atomics.
 //
@@ -128,6 +169,7 @@ struct ColumnWriter {
 #ifndef MCRT_ACC_MIN_CTAS
 #define MCRT_ACC_MIN_CTAS 8      // 64 registers, 32 warps/SM: measured 9 % faster than 6 (78 registers)
 #endif
+template <bool FMADIV>
 __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate(const SceneDev sc, const AcqDev aq, const float2* __restrict__ volume,
                                                    const DevSegment* __restrict__ segments, const int32_t* __restrict__ nseg,
                                                    const int n_paths, float* __restrict__ columns,
@@ -197,19 +239,32 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate(const Sce
                 n_safe = 0;
             }
             const int n_blocks = n_safe / MCRT_ACC_UNROLL;
+            // FMA-division voxel indices need |coord / resolution| < 2^31 along the whole march: the march is a
+            // straight line of n_safe steps of length <= axres per axis from `from` (bound with 2x slack)
+            const float reach = fmaxf(fmaxf(fabsf(from.x), fabsf(from.y)), fabsf(from.z)) + 2.0f * (float)n_safe * fabsf(axres_f) *
+                                fmaxf(fmaxf(fabsf(s1.x), fabsf(s1.y)), fabsf(s1.z));
+            const bool fma_ok = FMADIV && reach * inv_vres < 1.0e9f;
             for (int b = 0; b < n_blocks; b++) {
                 uint32_t idx[MCRT_ACC_UNROLL];
-                float3 pts[MCRT_ACC_UNROLL];
-                int risky = 0;                      // one guard branch per block instead of one per step
+                if (fma_ok) {
 #pragma unroll
-                for (int u = 0; u < MCRT_ACC_UNROLL; u++) {
-                    pts[u] = point;
-                    idx[u] = voxel_linear_fast(point, inv_vres, risky);
-                    point = v_add(point, delta_step);                                           // main.cpp:131
-                }
-                if (risky) {
+                    for (int u = 0; u < MCRT_ACC_UNROLL; u++) {
+                        idx[u] = voxel_linear_fma(point, vres, inv_vres);
+                        point = v_add(point, delta_step);                                       // main.cpp:131
+                    }
+                } else {
+                    float3 pts[MCRT_ACC_UNROLL];
+                    int risky = 0;                      // one guard branch per block instead of one per step
 #pragma unroll
-                    for (int u = 0; u < MCRT_ACC_UNROLL; u++) idx[u] = voxel_linear_exact(pts[u].x, pts[u].y, pts[u].z, vres);
+                    for (int u = 0; u < MCRT_ACC_UNROLL; u++) {
+                        pts[u] = point;
+                        idx[u] = voxel_linear_fast(point, inv_vres, risky);
+                        point = v_add(point, delta_step);                                       // main.cpp:131
+                    }
+                    if (risky) {
+#pragma unroll
+                        for (int u = 0; u < MCRT_ACC_UNROLL; u++) idx[u] = voxel_linear_exact(pts[u].x, pts[u].y, pts[u].z, vres);
+                    }
                 }
                 float2 vox[MCRT_ACC_UNROLL];
 #pragma unroll
@@ -745,7 +800,10 @@ cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2
     if (!d_columns) return cudaErrorInvalidValue;
     const int n_paths = n_poses * aq.elements * aq.samples;
     const int block = 128;
-    k_accumulate<<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_paths, d_columns, d_steps);
+    if (aq.voxel_fma_division)
+        k_accumulate<true><<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_paths, d_columns, d_steps);
+    else
+        k_accumulate<false><<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_paths, d_columns, d_steps);
     const int64_t n_pixels = (int64_t)n_poses * aq.elements * aq.rows;
     k_reduce_samples<<<grid1d(n_pixels, 256), 256, 0, stream>>>(d_columns, n_pixels, aq.samples, d_rf);
     if (launches) (*launches) += 2;
@@ -767,6 +825,20 @@ static int fused_tile_cols(int rows, int kl, int flags, size_t* smem)
         if (bytes <= MCRT_FUSED_SMEM_LIMIT) { *smem = bytes; return tc; }
     }
     return 0;
+}
+
+cudaError_t validate_fma_division(float resolution, bool* ok)
+{
+    unsigned int* d_bad = nullptr;
+    unsigned int bad = 1;
+    cudaError_t e = cudaMalloc(&d_bad, sizeof(unsigned int));
+    if (e != cudaSuccess) return e;
+    cudaMemset(d_bad, 0, sizeof(unsigned int));
+    k_validate_fma_division<<<(1u << 24) / 256, 256>>>(resolution, d_bad);       // 2^24 threads x 256 bit patterns
+    e = cudaMemcpy(&bad, d_bad, sizeof(unsigned int), cudaMemcpyDeviceToHost);
+    cudaFree(d_bad);
+    *ok = (e == cudaSuccess) && bad == 0 && resolution > 0.0f;
+    return e;
 }
 
 cudaError_t init_image_kernels()

@@ -70,6 +70,8 @@ struct AcqDev {
     double speed;           // (double)speed_of_sound
     int deterministic;
     int element_offset;     // global index of local element 0 (scanline-block runs; 0 otherwise): RNG key, PSF borders
+    int voxel_fma_division; // 1: coord / vol_resolution via div_fma was validated exhaustively for this resolution (image.cu)
+    int pad1;
 };
 
 struct PoseTrigDev { float px, py, pz, cz, sz, cx, sx, cy, sy, pad0, pad1, pad2; };   // = mcrt::PoseTrig, 48 B
@@ -255,9 +257,20 @@ __device__ __forceinline__ void tri_test(const TriSlot* __restrict__ tris, int s
 // Conservative slab test of one child box against the segment (see DESIGN.md "Traversal"): the
 // ray origin is widened by +-e per axis (o_near / o_far) and the interval compare carries a
 // relative slack, so the BVH can never cull a triangle the exact per-triangle arithmetic accepts.
+#ifndef MCRT_WHILE_WHILE
+#define MCRT_WHILE_WHILE 0
+#endif
+#ifndef MCRT_BOX_FMA
+#define MCRT_BOX_FMA 1   // slab planes as one FFMA each (plane * inv - origin * inv); measured in profiles/r01_traversal_ab.txt
+#endif
 struct RayBox {
+#if MCRT_BOX_FMA
+    float cnx, cny, cnz;   // -(o_near * inv): o_near = o + e where inv >= 0 else o - e
+    float cfx, cfy, cfz;   // -(o_far * inv)
+#else
     float onx, ony, onz;   // origin for the near plane (o + e where inv >= 0 else o - e)
     float ofx, ofy, ofz;   // origin for the far plane
+#endif
     float ix, iy, iz;      // 1 / (to - from)
     bool px, py, pz;       // inv >= 0
 };
@@ -267,12 +280,26 @@ __device__ __forceinline__ RayBox make_raybox(float3 from_w, float3 to_w, float 
     RayBox r;
     const float dx = to_w.x - from_w.x, dy = to_w.y - from_w.y, dz = to_w.z - from_w.z;
     r.ix = 1.0f / dx; r.iy = 1.0f / dy; r.iz = 1.0f / dz;
+#if MCRT_BOX_FMA
+    // an axis-parallel ray (d == 0) gets a huge finite reciprocal: plane * inv - origin * inv must not become
+    // inf - inf; t = (plane - origin) * 1e30 still separates "inside the slab" from "outside" for any gap > 1e-30
+    if (!(fabsf(r.ix) <= 1e30f)) r.ix = copysignf(1e30f, dx);
+    if (!(fabsf(r.iy) <= 1e30f)) r.iy = copysignf(1e30f, dy);
+    if (!(fabsf(r.iz) <= 1e30f)) r.iz = copysignf(1e30f, dz);
+#endif
     r.px = r.ix >= 0.0f; r.py = r.iy >= 0.0f; r.pz = r.iz >= 0.0f;
     const float mo = fmaxf(fabsf(from_w.x), fmaxf(fabsf(from_w.y), fabsf(from_w.z)));
     const float e = 4e-6f * (scene_max_abs + mo) + 1e-7f;
+#if MCRT_BOX_FMA
+    // rounding of the two-term form: <= 2^-24 (|o * inv| + |t|), i.e. <= 1.2e-7 (max_abs + |o|) in space -- 30x inside e
+    r.cnx = -((r.px ? from_w.x + e : from_w.x - e) * r.ix); r.cfx = -((r.px ? from_w.x - e : from_w.x + e) * r.ix);
+    r.cny = -((r.py ? from_w.y + e : from_w.y - e) * r.iy); r.cfy = -((r.py ? from_w.y - e : from_w.y + e) * r.iy);
+    r.cnz = -((r.pz ? from_w.z + e : from_w.z - e) * r.iz); r.cfz = -((r.pz ? from_w.z - e : from_w.z + e) * r.iz);
+#else
     r.onx = r.px ? from_w.x + e : from_w.x - e; r.ofx = r.px ? from_w.x - e : from_w.x + e;
     r.ony = r.py ? from_w.y + e : from_w.y - e; r.ofy = r.py ? from_w.y - e : from_w.y + e;
     r.onz = r.pz ? from_w.z + e : from_w.z - e; r.ofz = r.pz ? from_w.z - e : from_w.z + e;
+#endif
     return r;
 }
 
@@ -282,6 +309,16 @@ __device__ __forceinline__ bool box_test(const RayBox& r, float lox, float loy, 
     const float nx = r.px ? lox : hix, fx = r.px ? hix : lox;
     const float ny = r.py ? loy : hiy, fy = r.py ? hiy : loy;
     const float nz = r.pz ? loz : hiz, fz = r.pz ? hiz : loz;
+#if MCRT_BOX_FMA
+    // the box test only has to be conservative, not bit-exact: explicit FFMA (the library is built -fmad=false)
+    const float t0x = __fmaf_rn(nx, r.ix, r.cnx), t1x = __fmaf_rn(fx, r.ix, r.cfx);
+    const float t0y = __fmaf_rn(ny, r.iy, r.cny), t1y = __fmaf_rn(fy, r.iy, r.cfy);
+    const float t0z = __fmaf_rn(nz, r.iz, r.cnz), t1z = __fmaf_rn(fz, r.iz, r.cfz);
+    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tbest));
+    tnear = tn;
+    return tn <= __fmaf_rn(tf, 1.000002f, 1e-37f);
+#else
     const float t0x = (nx - r.onx) * r.ix, t1x = (fx - r.ofx) * r.ix;
     const float t0y = (ny - r.ony) * r.iy, t1y = (fy - r.ofy) * r.iy;
     const float t0z = (nz - r.onz) * r.iz, t1z = (fz - r.ofz) * r.iz;
@@ -290,6 +327,7 @@ __device__ __forceinline__ bool box_test(const RayBox& r, float lox, float loy, 
     const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tbest));
     tnear = tn;
     return tn <= tf * 1.000002f + 1e-37f;
+#endif
 }
 
 // Stack-based closest-hit traversal, near child first.  `node_visits` / `tri_tests` are per-thread work
@@ -307,6 +345,43 @@ __device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __
 #endif
     int sp = 0;
     int node = 0;   // root
+#if MCRT_WHILE_WHILE
+    // while-while: every lane first descends to its next leaf (or runs out of nodes), the warp reconverges, then the
+    // leaves are tested with (nearly) all lanes active instead of a few lanes per loop iteration
+    const int kDone = (int)0x80000000;
+    while (true) {
+        while (node >= 0) {
+            node_visits++;
+            const BvhNode* nd = sc.nodes + node;
+            const float4 a = __ldg(&nd->a), b = __ldg(&nd->b), c = __ldg(&nd->c);
+            const int4 d = __ldg(&nd->d);
+            const float tb = best.fraction * 1.000002f;
+            float t0, t1;
+            const bool h0 = box_test(rb, a.x, a.y, a.z, a.w, b.x, b.y, tb, t0);
+            const bool h1 = box_test(rb, b.z, b.w, c.x, c.y, c.z, c.w, tb, t1);
+            if (h0 && h1) {
+                const bool swap = t1 < t0;
+                node = swap ? d.y : d.x;
+                stack[sp++] = swap ? d.x : d.y;
+            } else if (h0) {
+                node = d.x;
+            } else if (h1) {
+                node = d.y;
+            } else {
+                node = sp > 0 ? stack[--sp] : kDone;
+            }
+        }
+        if (node == kDone) break;
+        {
+            const int code = -node - 1;
+            const int first = code >> 2, count = (code & 3) + 1;
+            tri_tests += count;
+            for (int k = 0; k < count; k++) tri_test(sc.tris, first + k, s_mesh, from_w, to_w, best);
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+#else
     while (true) {
         if (node >= 0) {
             node_visits++;
@@ -348,6 +423,7 @@ __device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __
         node = stack[--sp];
 #endif
     }
+#endif
 }
 
 // final normal of the best hit: normalise, face the ray origin (btTriangleRaycastCallback)

@@ -73,6 +73,9 @@ cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2
 void launch_post(const float* d_in, int n_images, int cols, int rows, const float* d_axial, int n_axial, const float* d_lateral,
                  int n_lateral, int flags, float* d_tmp0, float* d_tmp1, float* d_out, cudaStream_t stream, int* launches,
                  int col_offset = 0, int cols_total = 0);   // scanline-block runs: global index of scanline 0 / global scanline count
+// exhaustive device check (all 2^32 float bit patterns) that the 3-instruction FMA division reproduces the voxel index of
+// coord / resolution for this resolution; enables AcqDev::voxel_fma_division
+cudaError_t validate_fma_division(float resolution, bool* ok);
 // rfimage.h:127-136 (commented out in the reference): I = log10(I+1)/log10(max+1) per image, in place
 void launch_log_compress(float* d_img, int n_images, int64_t px_per_image, int* d_max_bits, cudaStream_t stream, int* launches);
 // [n][cols][rows] -> [n][rows][cols]

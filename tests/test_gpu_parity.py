@@ -296,3 +296,70 @@ def test_errors_are_codes_not_crashes(api, assets_dirs, tmp_path):
     with pytest.raises(api.McrtError) as e:
         api.Simulator(assets_dirs["sphere"] / "sphere.scene", api.default_params(psf_axial=8))
     assert e.value.code == api.MCRT_ERR_INVALID
+
+
+def test_stochastic_mode_statistics_over_independent_seeds(api, O, ircad_rough):
+    """North-star stochastic criterion, made independent of the shared Philox keying: the GPU simulates N = 256
+    frames with seeds 0..255, the oracle N frames with DIFFERENT seeds (independent draws), rough ircad11 scene
+    (thickness + shininess jitter active).  Per pixel with non-zero variance:
+      * means agree within 4 standard errors, |m_g - m_o| <= 4 sqrt((v_g + v_o)/N), for >= 99 % of pixels
+        (achieved oracle-vs-oracle on this scene: 100 %);
+      * the variance ratio lies in [0.7, 1.4] for >= 85 % and in [1/3, 3] for >= 94 % of pixels.  SURVEY 8(d)
+        asked for 99 % in [0.7, 1.4]; that is unreachable for ANY correct implementation because RF pixels are
+        heavy-tailed (rare specular paths): the oracle against itself with two seed sets reaches 88.9 % / 96.2 %.
+        So the bar that matters is the control: the GPU's fractions are within 2 points of the oracle-vs-oracle
+        fractions computed in this same test."""
+    path, A, osc = ircad_rough
+    N = 256
+    kw = dict(elements=32, samples=4)
+    op = O.default_params(**kw)
+    O.oracle().orc_set_threads(8)
+    with api.Simulator(path, api.default_params(**kw)) as sim:
+        pose = sim.start_pose
+        g = np.stack([sim.simulate(pose[None, :], seed=s, first_frame=0)[0] for s in range(N)])           # [N][cols][rows]
+    o_same = np.stack([osc.simulate_frame(op, pose[:3], pose[3:], seed=s, frame=0)["rf"].T for s in range(0, N, 32)])
+    o_b = np.stack([osc.simulate_frame(op, pose[:3], pose[3:], seed=100000 + s, frame=0)["rf"].T for s in range(N)])
+    o_c = np.stack([osc.simulate_frame(op, pose[:3], pose[3:], seed=200000 + s, frame=0)["rf"].T for s in range(N)])
+    O.oracle().orc_set_threads(1)
+    # same seeds: path-for-path (the stronger check, kept alongside)
+    for i, s in enumerate(range(0, N, 32)):
+        assert np.all(np.abs(g[s] - o_same[i]) <= _tol(o_same[i]))
+
+    def fractions(a, b):
+        m1, m2, v1, v2 = a.mean(0), b.mean(0), a.var(0, ddof=1), b.var(0, ddof=1)
+        nz = (v1 > 0) & (v2 > 0)
+        z = np.abs(m1 - m2)[nz] / np.sqrt((v1 + v2)[nz] / N)
+        r = v1[nz] / v2[nz]
+        return float((z <= 4).mean()), float(((r >= 0.7) & (r <= 1.4)).mean()), float(((r >= 1 / 3) & (r <= 3)).mean()), int(nz.sum())
+
+    gm, gv, gw, npx = fractions(g, o_b)
+    cm, cv, cw, _ = fractions(o_c, o_b)
+    print(f"stochastic statistics over {N} seeds, {npx} pixels: GPU-vs-oracle mean {gm:.4f} var[0.7,1.4] {gv:.4f} var[1/3,3] {gw:.4f}; "
+          f"oracle-vs-oracle control {cm:.4f} {cv:.4f} {cw:.4f}")
+    assert npx > 0.9 * g[0].size
+    assert gm >= 0.99 and gv >= 0.85 and gw >= 0.94
+    assert gm >= cm - 0.02 and gv >= cv - 0.02 and gw >= cw - 0.02
+
+
+@pytest.mark.parametrize("resolution_um", [145, 100, 333, 7])
+def test_voxel_index_fma_division_is_exact(api, O, ircad_rough, resolution_um):
+    """The accumulate kernel's 3-instruction voxel index (FMA division, image.cu) is enabled only after an exhaustive
+    device check over all 2^32 float bit patterns for the context's resolution.  With it on and off the RF frame is
+    bit-identical, and both match the oracle's IEEE divisions (volume.h:49-51), also for non-default resolutions."""
+    path, A, osc = ircad_rough
+    kw = dict(elements=64, samples=4, resolution_um=resolution_um)
+    op = O.default_params(**kw)
+    pose = np.concatenate([A["transducer_position"], A["transducer_angles"]])
+    os_, on, _ = osc.cast_rays(op, pose[:3], pose[3:], seed=5, frame=1)
+    ref, steps = osc.accumulate(op, os_, on)
+    with api.Simulator(path, api.default_params(**kw)) as sim:
+        validated = sim.get_info().voxel_fma_division
+        on_rf = sim.accumulate(os_, on)
+        assert sim.stats().march_steps == steps
+        sim.set_option("voxel_fma_division", 0)
+        assert sim.get_info().voxel_fma_division == 0
+        off_rf = sim.accumulate(os_, on)
+    if resolution_um == 145:
+        assert validated == 1            # the reference's resolution (main.cpp:33) must take the fast path
+    assert np.array_equal(on_rf, off_rf)
+    assert np.all(np.abs(on_rf - ref.T) <= _tol(ref.T))
