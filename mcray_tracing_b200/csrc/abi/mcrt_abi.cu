@@ -123,6 +123,7 @@ struct mcrt_ctx {
     bool count_traversal = false;
     bool log_compress = false;             // rfimage.h:127-136, commented out in the reference
     int* d_max_bits = nullptr;             // [cap_poses] per-image maximum (ordered-int encoding)
+    bool ordered_compaction = false;       // order-preserving compaction between bounces (TraceBuffers::chunk_prefix_a)
     bool coherence_sort = false;           // radix-sort surviving paths between bounces (rough scenes)
     float* d_rf_acc = nullptr;
     float* d_rf_tmp0 = nullptr;
@@ -163,6 +164,7 @@ void free_workspace(mcrt_ctx* c)
     dev_free(c->tb.segments); dev_free(c->tb.n_segments); dev_free(c->tb.hit_fraction); dev_free(c->tb.hit_mesh);
     dev_free(c->tb.queue_a); dev_free(c->tb.queue_b); dev_free(c->tb.counters);
     dev_free(c->tb.sort_keys); dev_free(c->tb.sort_keys_tmp); dev_free(c->tb.sort_queue_tmp);
+    dev_free(c->tb.chunk_prefix_a); dev_free(c->tb.chunk_prefix_b); dev_free(c->tb.n_chunks);
     if (c->tb.sort_tmp) cudaFree(c->tb.sort_tmp);
     c->tb.sort_tmp = nullptr; c->tb.sort_tmp_bytes = 0;
     dev_free(c->d_poses); dev_free(c->d_rf_acc); dev_free(c->d_rf_tmp0); dev_free(c->d_rf_tmp1); dev_free(c->d_rf_final);
@@ -199,6 +201,11 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
     if (c->columns_bytes) dev_alloc(c->d_columns, c->columns_bytes / sizeof(float));
     CUDA_TRY(cudaMallocHost(&c->h_poses, sizeof(PoseTrig) * (size_t)n_poses));
     c->tb.trav_counters = c->count_traversal ? c->d_trav : nullptr;
+    if (c->ordered_compaction) {
+        const size_t n_chunks = (n_paths + 127) / 128 + 2;
+        dev_alloc(c->tb.chunk_prefix_a, n_chunks); dev_alloc(c->tb.chunk_prefix_b, n_chunks);
+        dev_alloc(c->tb.n_chunks, (size_t)c->aq.max_depth + 1);
+    }
     if (c->coherence_sort) {
         dev_alloc(c->tb.sort_keys, n_paths); dev_alloc(c->tb.sort_keys_tmp, n_paths); dev_alloc(c->tb.sort_queue_tmp, n_paths);
         c->tb.sort_tmp_bytes = trace_sort_tmp_bytes((int64_t)n_paths);
@@ -219,6 +226,7 @@ void enqueue_trace(mcrt_ctx* c, int pose0, int n, int slot, cudaStream_t s, int*
     if (tb.hit_fraction) tb.hit_fraction += p0 * c->aq.max_depth;
     if (tb.hit_mesh) tb.hit_mesh += p0 * c->aq.max_depth;
     tb.queue_a += p0; tb.queue_b += p0;
+    if (pose0 != 0 || slot != 0) { tb.chunk_prefix_a = nullptr; tb.chunk_prefix_b = nullptr; tb.n_chunks = nullptr; }   // sub-batches: atomic compaction
     if (tb.sort_keys) { tb.sort_keys += p0; tb.sort_keys_tmp += p0; tb.sort_queue_tmp += p0; }
     tb.counters += (size_t)slot * (c->aq.max_depth + 1);
     launch_trace(c->sc, c->aq, fr, tb, c->sm_count, s, launches);
@@ -298,7 +306,8 @@ int pipeline_sub_batches(const mcrt_ctx* c, int n)
 
 int count_pipeline_launches(const mcrt_ctx* c, bool want_scan, int nsub)
 {
-    return nsub * (c->aq.max_depth + 2 + post_launch_count(c->aq.elements, c->aq.rows, c->params.psf_lateral, 3, 1) + (c->params.rf_layout == 1 ? 1 : 0) +
+    const int scans = (c->ordered_compaction && nsub == 1) ? c->aq.max_depth - 1 : 0;
+    return nsub * (c->aq.max_depth + scans + 2 + post_launch_count(c->aq.elements, c->aq.rows, c->params.psf_lateral, 3, 1) + (c->params.rf_layout == 1 ? 1 : 0) +
                    (c->log_compress ? 2 : 0) + (want_scan ? 1 : 0));
 }
 
@@ -714,6 +723,12 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
         c->graphs.clear();
         c->log_compress = value != 0;
     }
+    else if (n == "ordered_compaction") {
+        // changes the workspace and the captured graphs: drop both, they are rebuilt on the next call
+        CUDA_TRY_NOTHROW(cudaStreamSynchronize(c->stream));
+        free_workspace(c);
+        c->ordered_compaction = value != 0;
+    }
     else if (n == "coherence_sort") {
         // changes the workspace and the captured graphs: drop both, they are rebuilt on the next call
         CUDA_TRY_NOTHROW(cudaStreamSynchronize(c->stream));
@@ -856,7 +871,9 @@ int mcrt_closest_hit(mcrt_ctx* c, int64_t n, const float* from3, const float* to
             dev_alloc(d_nr, (size_t)n * 3); dev_alloc(d_tri, (size_t)n); dev_alloc(d_mesh, (size_t)n);
             CUDA_TRY(cudaMemcpyAsync(d_from, from3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
             CUDA_TRY(cudaMemcpyAsync(d_to, to3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
             launch_closest_hit(c->sc, n, d_from, d_to, d_tri, d_mesh, d_frac, d_pt, d_nr, c->stream);
+            CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaMemcpyAsync(tri_id, d_tri, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(cudaMemcpyAsync(mesh_id, d_mesh, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -864,6 +881,12 @@ int mcrt_closest_hit(mcrt_ctx* c, int64_t n, const float* from3, const float* to
             CUDA_TRY(cudaMemcpyAsync(point3, d_pt, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(cudaMemcpyAsync(normal3, d_nr, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));
+            // traversal micro-benchmark: device time of the closest-hit kernel alone
+            c->stats = mcrt_stats{};
+            c->stats.segments = n; c->stats.kernel_launches = 1;
+            CUDA_TRY(cudaEventElapsedTime(&c->stats.ms_total, c->ev0, c->ev1));
+            c->stats.ms_trace = c->stats.ms_total;
+            c->stats_pending = false;
         } catch (...) {
             dev_free(d_from); dev_free(d_to); dev_free(d_frac); dev_free(d_pt); dev_free(d_nr); dev_free(d_tri); dev_free(d_mesh);
             throw;

@@ -169,6 +169,7 @@ MCRT_HD double mc_pow(double x, double y)
     if (y == 0.0) return 1.0;
     if (x == 1.0) return 1.0;
     if (x != x || y != y) return MC_NAN_D;
+    if (y == 1.0) return x;            // exact in IEEE pow; every example material has specularity 1 (ray.cpp:154-164)
     const double ay = fabs(y);
     const bool y_is_int = (ay >= 9007199254740992.0) || (floor(y) == y);
     bool y_is_odd = false;

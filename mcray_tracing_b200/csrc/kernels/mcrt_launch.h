@@ -47,6 +47,13 @@ struct TraceBuffers {
     int* sort_queue_tmp;           // [n_paths]
     void* sort_tmp;                // cub temporary storage
     size_t sort_tmp_bytes;
+    // optional order-preserving compaction (nullptr = off): every 128-path chunk compacts its survivors into its own slot
+    // of queue_a/queue_b and records how many; k_scan_chunks turns the counts into an exclusive prefix and the next bounce
+    // finds path idx by a binary search over it.  Survivors stay sorted by (pose, element, sample), so the lanes of a warp
+    // keep tracing neighbouring rays instead of pieces of unrelated warps glued together by atomic order.
+    int* chunk_prefix_a;           // [ceil(n_paths / 128) + 1]
+    int* chunk_prefix_b;
+    int* n_chunks;                 // [max_depth + 1]: chunks written by bounce b - 1 = entries of the prefix bounce b reads
 };
 
 // generate + max_depth x (intersect, shade, compact): scene::cast_rays (scene.cpp:50-183)

@@ -200,21 +200,27 @@ __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq
     return alive;
 }
 
-template <bool FIRST>
 #ifndef MCRT_BOUNCE_GRID_CTAS_PER_SM
 #define MCRT_BOUNCE_GRID_CTAS_PER_SM 64   // measured: an (effectively) uncapped grid beats a persistent 8-CTA/SM grid by 15 % at 256 frames
 #endif
 #ifndef MCRT_BOUNCE_MIN_CTAS
 #define MCRT_BOUNCE_MIN_CTAS 6      // 80 registers, 24 warps/SM: measured best of 4/5/6/8 (profiles/r01_traversal_ab.txt)
 #endif
+// ORDERED: order-preserving compaction (see TraceBuffers::chunk_prefix_a); otherwise survivors are appended to the next
+// queue with one warp-aggregated atomicAdd per warp.
+template <bool FIRST, bool ORDERED>
 __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const SceneDev sc, const AcqDev aq, const FrameDev fr, const TraceBuffers tb, const int bounce)
 {
     __shared__ SharedScene sh;
+    __shared__ int s_wcount[4];
     load_shared_scene(sc, sh);
     const int* __restrict__ qin = (bounce & 1) ? tb.queue_b : tb.queue_a;
     int* __restrict__ qout = (bounce & 1) ? tb.queue_a : tb.queue_b;
+    const int* __restrict__ pin = (bounce & 1) ? tb.chunk_prefix_b : tb.chunk_prefix_a;     // ORDERED only
+    int* __restrict__ pout = (bounce & 1) ? tb.chunk_prefix_a : tb.chunk_prefix_b;
     const int n_in = FIRST ? fr.n_poses * aq.elements * aq.samples : tb.counters[bounce];
-    const int n_round = (n_in + 31) & ~31;
+    const int n_round = ORDERED ? (n_in + 127) & ~127 : (n_in + 31) & ~31;
+    const int n_chunks_in = (ORDERED && !FIRST) ? tb.n_chunks[bounce] : 0;
     const unsigned lane = threadIdx.x & 31;
     const bool last = bounce + 1 >= aq.max_depth;
     int node_visits = 0, tri_tests = 0;
@@ -223,22 +229,45 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const Scen
         bool alive = false;
         unsigned sort_key = 0u;
         if (idx < n_in) {
-            p = FIRST ? idx : qin[idx];
+            if (FIRST) {
+                p = idx;
+            } else if (ORDERED) {
+                // largest chunk c with prefix[c] <= idx (prefix[n_chunks_in] = n_in > idx)
+                int lo = 0, hi = n_chunks_in;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (__ldg(&pin[mid]) <= idx) lo = mid; else hi = mid;
+                }
+                p = qin[lo * 128 + (idx - __ldg(&pin[lo]))];
+            } else {
+                p = qin[idx];
+            }
             alive = bounce_path<FIRST>(sc, aq, fr, tb, sh, p, bounce, node_visits, tri_tests, sort_key);
         }
-        if (!last) {
+        if (last) continue;
+        const unsigned m = __ballot_sync(0xffffffffu, alive);
+        if (ORDERED) {
+            // the CTA's 128 paths of this iteration are one chunk: compact into the chunk's own slot, in order
+            const int warp = threadIdx.x >> 5;
+            if (lane == 0) s_wcount[warp] = __popc(m);
+            __syncthreads();
+            int base = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < 4; w++) { const int cw = s_wcount[w]; if (w < warp) base += cw; total += cw; }
+            const int chunk = idx >> 7;
+            if (alive) qout[chunk * 128 + base + __popc(m & ((1u << lane) - 1u))] = p;
+            if (threadIdx.x == 0) pout[chunk] = total;
+            __syncthreads();
+        } else if (m) {
             // compact: warp-aggregated queue append (one atomic per warp)
-            const unsigned m = __ballot_sync(0xffffffffu, alive);
-            if (m) {
-                const int leader = __ffs(m) - 1;
-                int base = 0;
-                if ((int)lane == leader) base = atomicAdd(&tb.counters[bounce + 1], __popc(m));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (alive) {
-                    const int pos = base + __popc(m & ((1u << lane) - 1u));
-                    qout[pos] = p;
-                    if (tb.sort_keys) tb.sort_keys[pos] = sort_key;
-                }
+            const int leader = __ffs(m) - 1;
+            int base = 0;
+            if ((int)lane == leader) base = atomicAdd(&tb.counters[bounce + 1], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (alive) {
+                const int pos = base + __popc(m & ((1u << lane) - 1u));
+                qout[pos] = p;
+                if (tb.sort_keys) tb.sort_keys[pos] = sort_key;
             }
         }
     }
@@ -254,7 +283,46 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const Scen
     }
 }
 
-__global__ void __launch_bounds__(128) k_closest_hit(const SceneDev sc, const int64_t n, const float* __restrict__ from3,
+// ORDERED compaction, between bounce b and b + 1: exclusive prefix of the per-chunk survivor counts bounce b wrote
+// (in place), counters[b + 1] = number of survivors, n_chunks[b + 1] = number of chunks.  One CTA; the arrays are small
+// (n_paths / 128 entries).
+__global__ void __launch_bounds__(1024) k_scan_chunks(int* __restrict__ counts, int* __restrict__ counters, int* __restrict__ n_chunks,
+                                                      const int bounce, const int n_paths_first)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int n_in = bounce == 0 ? n_paths_first : counters[bounce];
+    const int nch = (n_in + 127) >> 7;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nch; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < nch ? counts[i] : 0;
+        int x = v;                                               // inclusive warp scan
+        for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+            for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += y; }
+            s_warp[lane] = w;                                    // inclusive scan of the warp totals
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int excl = carry + (warp ? s_warp[warp - 1] : 0) + x - v;
+        if (i < nch) counts[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { counts[nch] = s_carry; counters[bounce + 1] = s_carry; n_chunks[bounce + 1] = nch; }
+}
+
+#ifndef MCRT_CH_MIN_CTAS
+#define MCRT_CH_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(128, MCRT_CH_MIN_CTAS) k_closest_hit(const SceneDev sc, const int64_t n, const float* __restrict__ from3,
                                                     const float* __restrict__ to3, int32_t* __restrict__ tri, int32_t* __restrict__ mesh,
                                                     float* __restrict__ frac, float* __restrict__ point3, float* __restrict__ normal3)
 {
@@ -334,11 +402,19 @@ void launch_trace(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, cons
     // persistent-style grid: a multiple of the SM count, grid-stride loop inside
     const int grid = grid_for(n_paths, block, sm_count, MCRT_BOUNCE_GRID_CTAS_PER_SM);
     for (int b = 0; b < aq.max_depth; b++) {
-        const bool sort = tb.sort_keys && b + 1 < aq.max_depth;
+        const bool sort = tb.sort_keys && !tb.chunk_prefix_a && b + 1 < aq.max_depth;
         // unused queue slots get the largest key so they sort behind the survivors
         if (sort) cudaMemsetAsync(tb.sort_keys, 0xff, sizeof(unsigned) * (size_t)n_paths, stream);
-        if (b == 0) k_bounce<true><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
-        else k_bounce<false><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
+        const bool ordered = tb.chunk_prefix_a != nullptr;
+        if (ordered) {
+            if (b == 0) k_bounce<true, true><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
+            else k_bounce<false, true><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
+            if (b + 1 < aq.max_depth) {
+                k_scan_chunks<<<1, 1024, 0, stream>>>((b & 1) ? tb.chunk_prefix_a : tb.chunk_prefix_b, tb.counters, tb.n_chunks, b, (int)n_paths);
+                if (launches) (*launches)++;
+            }
+        } else if (b == 0) k_bounce<true, false><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
+        else k_bounce<false, false><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
         if (launches) (*launches)++;
         if (sort) {
             int* qout = (b & 1) ? tb.queue_a : tb.queue_b;
@@ -363,7 +439,7 @@ void launch_closest_hit(const SceneDev& sc, int64_t n, const float* d_from, cons
     if (n <= 0) return;
     const int block = 128;
     int64_t g = (n + block - 1) / block;
-    if (g > 148 * 8) g = 148 * 8;
+    if (g > 148 * 64) g = 148 * 64;
     k_closest_hit<<<(int)g, block, 0, stream>>>(sc, n, d_from, d_to, d_tri, d_mesh, d_frac, d_point, d_normal);
 }
 
