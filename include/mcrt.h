@@ -121,6 +121,7 @@ typedef struct mcrt_stats {   /* of the most recent mcrt_simulate call */
     float ms_trace, ms_accumulate, ms_post; /* only filled when profiling stages (mcrt_set_option) */
     int64_t bvh_node_visits;  /* only with option "count_traversal": BVH nodes fetched / triangles tested */
     int64_t bvh_triangle_tests;
+    int64_t late_echoes;      /* windowed accumulate: echoes that arrived for an already finished row window (0 unless time runs backwards) */
 } mcrt_stats;
 
 int mcrt_default_params(mcrt_params* p);

@@ -54,7 +54,7 @@ class Info(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("poses", C.c_int64), ("segments", C.c_int64), ("march_steps", C.c_int64), ("kernel_launches", C.c_int64),
                 ("ms_total", C.c_float), ("ms_trace", C.c_float), ("ms_accumulate", C.c_float), ("ms_post", C.c_float),
-                ("bvh_node_visits", C.c_int64), ("bvh_triangle_tests", C.c_int64)]
+                ("bvh_node_visits", C.c_int64), ("bvh_triangle_tests", C.c_int64), ("late_echoes", C.c_int64)]
 
 
 SEGMENT_DTYPE = np.dtype([("from", np.float32, 3), ("to", np.float32, 3), ("dir", np.float32, 3),

@@ -197,7 +197,8 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
     if (c->params.rf_layout == 1) dev_alloc(c->d_rf_t, n_px);
     dev_alloc(c->d_scan, (size_t)n_poses * c->params.scan_rows * c->params.scan_cols);
     dev_alloc(c->d_max_bits, (size_t)n_poses);
-    c->columns_bytes = accumulate_columns_bytes(c->aq, n_poses);
+    // the windowed accumulate kernel keeps its columns in shared memory: no HBM columns at all
+    c->columns_bytes = c->aq.accumulate_windowed ? 0 : accumulate_columns_bytes(c->aq, n_poses);
     if (c->columns_bytes) dev_alloc(c->d_columns, c->columns_bytes / sizeof(float));
     CUDA_TRY(cudaMallocHost(&c->h_poses, sizeof(PoseTrig) * (size_t)n_poses));
     c->tb.trav_counters = c->count_traversal ? c->d_trav : nullptr;
@@ -252,7 +253,7 @@ void enqueue_image(mcrt_ctx* c, int pose0, int n, bool want_scan, cudaStream_t s
 void enqueue_pipeline(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches, bool stage_events)
 {
     CUDA_TRY(cudaMemsetAsync(c->tb.counters, 0, sizeof(int) * (size_t)kMaxSub * (c->aq.max_depth + 1), s));
-    CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, sizeof(unsigned long long), s));
+    CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, 2 * sizeof(unsigned long long), s));
     if (stage_events) CUDA_TRY(cudaEventRecord(c->ev_a, s));
     enqueue_trace(c, 0, n, 0, s, launches);
     if (stage_events) CUDA_TRY(cudaEventRecord(c->ev_b, s));
@@ -282,7 +283,7 @@ void enqueue_pipeline(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* l
 void enqueue_pipeline_overlapped(mcrt_ctx* c, int n, int nsub, bool want_scan, cudaStream_t s1, cudaStream_t s2, int* launches)
 {
     CUDA_TRY(cudaMemsetAsync(c->tb.counters, 0, sizeof(int) * (size_t)kMaxSub * (c->aq.max_depth + 1), s1));
-    CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, sizeof(unsigned long long), s1));
+    CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, 2 * sizeof(unsigned long long), s1));
     CUDA_TRY(cudaEventRecord(c->ev_fork, s1));
     CUDA_TRY(cudaStreamWaitEvent(s2, c->ev_fork, 0));
     for (int k = 0; k < nsub; k++) {
@@ -307,7 +308,8 @@ int pipeline_sub_batches(const mcrt_ctx* c, int n)
 int count_pipeline_launches(const mcrt_ctx* c, bool want_scan, int nsub)
 {
     const int scans = (c->ordered_compaction && nsub == 1) ? c->aq.max_depth - 1 : 0;
-    return nsub * (c->aq.max_depth + scans + 2 + post_launch_count(c->aq.elements, c->aq.rows, c->params.psf_lateral, 3, 1) + (c->params.rf_layout == 1 ? 1 : 0) +
+    const int acc = (c->aq.accumulate_windowed && accumulate_windowed_supported(c->sc, c->aq)) ? 1 : 2;   // accumulate (+ sample reduction)
+    return nsub * (c->aq.max_depth + scans + acc + post_launch_count(c->aq.elements, c->aq.rows, c->params.psf_lateral, 3, 1) + (c->params.rf_layout == 1 ? 1 : 0) +
                    (c->log_compress ? 2 : 0) + (want_scan ? 1 : 0));
 }
 
@@ -385,7 +387,7 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
                                          scan_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaMemcpyAsync(c->h_counters + kCounterSlot * b, c->tb.counters, sizeof(int) * (size_t)kMaxSub * (c->aq.max_depth + 1),
                                      cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(cudaMemcpyAsync(c->h_steps + b, c->d_steps, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(c->h_steps + 2 * b, c->d_steps, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         }
         if (c->count_traversal) CUDA_TRY(cudaMemcpyAsync(c->h_trav, c->d_trav, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaEventRecord(c->ev1, s));
@@ -412,14 +414,16 @@ void finalize_stats(mcrt_ctx* c)
     c->stats.ms_total = ms;
     const int64_t paths_per_pose = (int64_t)c->aq.elements * c->aq.samples;
     int64_t segs = c->stats.poses * paths_per_pose;      // bounce 0 traces every path
-    int64_t steps = 0;
+    int64_t steps = 0, late = 0;
     for (int b = 0; b < c->pending_batches; b++) {
         for (int k = 0; k < kMaxSub; k++)
             for (int d = 1; d < c->aq.max_depth; d++) segs += c->h_counters[kCounterSlot * b + k * (c->aq.max_depth + 1) + d];
-        steps += (int64_t)c->h_steps[b];
+        steps += (int64_t)c->h_steps[2 * b];
+        late += (int64_t)c->h_steps[2 * b + 1];
     }
     c->stats.segments = segs;
     c->stats.march_steps = steps;
+    c->stats.late_echoes = late;
     c->stats.kernel_launches = c->pending_launches;
     if (c->count_traversal) { c->stats.bvh_node_visits = (int64_t)c->h_trav[0]; c->stats.bvh_triangle_tests = (int64_t)c->h_trav[1]; }
     if (c->profile_stages && c->pending_batches == 1) {
@@ -490,6 +494,7 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     sc.n_tri = c->bvh.n_tri; sc.n_mesh = (int)hs.meshes.size(); sc.n_mat = (int)hs.materials.size();
     sc.starting_material = hs.starting_material;
     for (int a = 0; a < 3; a++) sc.spacing[a] = hs.spacing[a];
+    c->aq.accumulate_windowed = accumulate_windowed_supported(sc, c->aq) ? 1 : 0;
     sc.max_abs = c->bvh.max_abs;
     {
         float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
@@ -533,14 +538,14 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
 
     dev_alloc(c->d_seed_frame, 2);
     dev_alloc(c->d_trav, 2);
-    dev_alloc(c->d_steps, 1);
+    dev_alloc(c->d_steps, 2);
     CUDA_TRY(cudaMallocHost(&c->h_seed_frame, 2 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMallocHost(&c->h_counters, sizeof(int) * kCounterSlot * kMaxBatchesPerCall));
-    CUDA_TRY(cudaMallocHost(&c->h_steps, sizeof(unsigned long long) * kMaxBatchesPerCall));
+    CUDA_TRY(cudaMallocHost(&c->h_steps, sizeof(unsigned long long) * 2 * kMaxBatchesPerCall));
     CUDA_TRY(cudaMallocHost(&c->h_trav, 2 * sizeof(unsigned long long)));
     c->h_trav[0] = c->h_trav[1] = 0;
     memset(c->h_counters, 0, sizeof(int) * kCounterSlot * kMaxBatchesPerCall);
-    memset(c->h_steps, 0, sizeof(unsigned long long) * kMaxBatchesPerCall);
+    memset(c->h_steps, 0, sizeof(unsigned long long) * 2 * kMaxBatchesPerCall);
     *out = c.release();
     return MCRT_OK;
 }
@@ -742,6 +747,12 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
         c->count_traversal = value != 0;
         c->tb.trav_counters = c->count_traversal ? c->d_trav : nullptr;
     }
+    else if (n == "accumulate_windowed") {
+        // changes the workspace (HBM columns or not) and the captured graphs
+        CUDA_TRY_NOTHROW(cudaStreamSynchronize(c->stream));
+        free_workspace(c);
+        c->aq.accumulate_windowed = (value != 0 && accumulate_windowed_supported(c->sc, c->aq)) ? 1 : 0;
+    }
     else if (n == "voxel_fma_division") {
         // A/B switch; can only be turned on for a resolution that passed the exhaustive check at mcrt_create
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
@@ -794,7 +805,7 @@ int mcrt_simulate_scanlines(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, u
         fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos + e0; fr.seed_frame = c->d_seed_frame; fr.n_poses = 1; fr.frame_offset = 0;
         int launches = 0;
         CUDA_TRY(cudaMemsetAsync(c->tb.counters, 0, sizeof(int) * (size_t)kMaxSub * (c->aq.max_depth + 1), s));
-        CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, sizeof(unsigned long long), s));
+        CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, 2 * sizeof(unsigned long long), s));
         launch_trace(c->sc, aq, fr, c->tb, c->sm_count, s, &launches);
         CUDA_TRY(launch_accumulate(c->sc, aq, c->d_volume, c->tb.segments, c->tb.n_segments, 1, c->d_rf_acc, c->d_steps, c->d_columns, s, &launches));
         launch_post(c->d_rf_acc, 1, n_local, aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, kl, 3, c->d_rf_tmp0, c->d_rf_tmp1,
@@ -940,15 +951,16 @@ int mcrt_accumulate(mcrt_ctx* c, const mcrt_segment* segments, const int32_t* n_
         }
         CUDA_TRY(cudaMemcpyAsync(c->tb.segments, hs.data(), sizeof(DevSegment) * n_seg, cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaMemcpyAsync(c->tb.n_segments, n_segments, sizeof(int32_t) * n_paths, cudaMemcpyHostToDevice, c->stream));
-        CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, sizeof(unsigned long long), c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, 2 * sizeof(unsigned long long), c->stream));
         int launches = 0;
         CUDA_TRY(launch_accumulate(c->sc, c->aq, c->d_volume, c->tb.segments, c->tb.n_segments, 1, c->d_rf_acc, c->d_steps, c->d_columns,
                                    c->stream, &launches));
         CUDA_TRY(cudaMemcpyAsync(rf_out, c->d_rf_acc, sizeof(float) * (size_t)c->aq.elements * c->aq.rows, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(c->h_steps, c->d_steps, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->h_steps, c->d_steps, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->stats = mcrt_stats{};
         c->stats.march_steps = (int64_t)c->h_steps[0];
+        c->stats.late_echoes = (int64_t)c->h_steps[1];
         c->stats.kernel_launches = launches;
         c->stats_pending = false;
         return MCRT_OK;

@@ -333,6 +333,294 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate(const Sce
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Windowed echo accumulation: the same march as k_accumulate, but the private columns never reach HBM.
+//
+// A *group* of threads owns G whole scanlines (thread = one Monte-Carlo path, as before): a warp when S <= 32
+// (G = 32 / S; the group then synchronises with __syncwarp, which costs nothing -- the CTA-wide barrier of the first
+// version was its largest stall), the whole CTA for 32 < S <= 128 (G = 128 / S).  Time along a path is monotone
+// (spacing == 1: every segment starts where the previous one ended), so all paths of the group sweep the RF rows
+// together: the rows are processed in windows of MCRT_WIN_ROWS; inside a window every thread runs its march until
+// its next echo would land beyond the window, writing its private column of the window to shared memory (each row
+// once, in order: plain stores, no read-modify-write, no atomics).  Then the group sums the S columns of each
+// scanline in sample order -- the exact order of k_reduce_samples, so both paths give bit-identical images -- and
+// streams the finished rows to rf[scanline][row] with coalesced stores.  Compared with k_accumulate +
+// k_reduce_samples this removes the write and the re-read of the [scanline][row][sample] columns (2 x 1.95 GB per
+// 256 frames of 256 x 16 paths) and one launch.
+// The host only selects this kernel for spacing == (1,1,1) and S <= 128; an echo that nevertheless arrives for an
+// already finished window is added with atomicAdd and counted in `late_echoes` (tests hold the counter at 0).
+// ------------------------------------------------------------------------------------------------
+#ifndef MCRT_WIN_RING
+#define MCRT_WIN_RING 32           // rows of the shared-memory ring (power of two)
+#endif
+#ifndef MCRT_WIN_UNROLL
+#define MCRT_WIN_UNROLL 8          // steps per unrolled block
+#endif
+// A window finishes MCRT_WIN_ROWS rows; an unrolled block only has to START inside the window, its last rows may run
+// up to MCRT_WIN_UNROLL - 1 rows ahead into the ring's slack (they belong to the next window and stay in the ring).
+#define MCRT_WIN_ROWS (MCRT_WIN_RING - MCRT_WIN_UNROLL)
+#define MCRT_WIN_SLOT(row) ((row) & (MCRT_WIN_RING - 1))
+
+// ring row stride (floats) of a group with T active threads: a multiple of 4 (float4 reduce loads) whose quarter is odd
+// (conflict-free quarter-warp phases for consecutive rows)
+__host__ __device__ __forceinline__ int win_stride(int T) { const int q = (T + 3) / 4; return 4 * (q | 1); }
+
+template <bool FMADIV, bool WARP>
+__global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const SceneDev sc, const AcqDev aq, const float2* __restrict__ volume,
+                                                       const DevSegment* __restrict__ segments, const int32_t* __restrict__ nseg,
+                                                       const int n_scanlines, const int G, float* __restrict__ rf,
+                                                       unsigned long long* __restrict__ steps_total,
+                                                       unsigned long long* __restrict__ late_echoes)
+{
+    extern __shared__ float4 s_win4[];                     // per group: [MCRT_WIN_RING][stride]; row r lives in slot r % RING
+    __shared__ DevMaterial s_mat[MCRT_MAX_SMEM_MATERIALS];
+    for (int i = threadIdx.x; i < sc.n_mat && i < MCRT_MAX_SMEM_MATERIALS; i += blockDim.x) s_mat[i] = sc.materials[i];
+    const int S = aq.samples, rows = aq.rows;
+    const int T = G * S;                                   // active threads of a group
+    const int stride = win_stride(T);
+    const int group_size = WARP ? 32 : 128;
+    const int group = WARP ? (int)(blockIdx.x * 4 + (threadIdx.x >> 5)) : (int)blockIdx.x;
+    const int t = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;          // index within the group
+    float* const s_win = reinterpret_cast<float*>(s_win4) + (WARP ? (size_t)(threadIdx.x >> 5) * MCRT_WIN_RING * stride : 0);
+    auto group_sync = [&]() { if (WARP) __syncwarp(); else __syncthreads(); };
+    const int scanline0 = group * G;
+    const int my_scanline = scanline0 + t / S;
+    const bool active = t < T && my_scanline < n_scanlines;
+    const int p = my_scanline * S + (t - (t / S) * S);
+    __syncthreads();
+
+    const float axres_f = aq.axres_f;
+    const double time_step = aq.time_step_us;
+    const double inv_time_step = 1.0 / aq.time_step_us;
+    const double max_travel_time = aq.max_travel_time_us;
+    const double row_period = aq.row_period_us, inv_row_period = aq.inv_row_period;
+    const float samples_f = (float)(size_t)S;
+    const float vres = aq.vol_resolution, inv_vres = 1.0f / aq.vol_resolution;
+    const double row_delta = aq.time_step_us * aq.inv_row_period - 1.0;
+    const bool fast_rows = row_delta >= 0.0 && row_delta < 0.2;
+    const double block_safe_hi = 1.0 - 1e-6 - (double)(MCRT_WIN_UNROLL - 1) * row_delta;
+
+    // ---- per-path march state, kept in registers across windows ----
+    const int ns = active ? nseg[p] : 0;
+    int k = 0;                       // next segment to load
+    bool in_seg = false;             // a segment is loaded and not finished
+    bool fma_ok = false;
+    float3 point = make_float3(0.f, 0.f, 0.f), delta_step = point;
+    double time_elapsed = 0.0;
+    float intensity = 0.0f, decay = 0.0f;
+    float m_mu0 = 0.0f, m_mu1 = 0.0f, m_sigma = 0.0f;
+    int remaining = 0;               // steps left by the step budget (main.cpp:124 `step < steps`)
+    int n_safe = 0;                  // of those, steps that certainly satisfy the time bound
+    float end_echo = 0.0f;           // the segment's closing echo (main.cpp:139) ...
+    double end_micros = 0.0;         // ... and its time
+    unsigned long long my_steps = 0;
+    // column writer state: rows [.., written) of my column are stored; cur_row accumulates in cur_acc
+    int written = 0, cur_row = -1;
+    float cur_acc = 0.0f;
+    float* const my_col = s_win + t;
+
+    for (int base = 0; base < rows; base += MCRT_WIN_ROWS) {
+        const int wend = base + MCRT_WIN_ROWS < rows ? base + MCRT_WIN_ROWS : rows;
+        // put `echo` into RF row `row` of my column (base <= row < wend, row >= cur_row)
+        auto add_row = [&](float echo, int row) {
+            if (row == cur_row) { cur_acc += echo; return; }
+            if (cur_row >= base) {
+                for (int r = written > base ? written : base; r < cur_row; r++) my_col[MCRT_WIN_SLOT(r) * stride] = 0.0f;   // rows nothing landed in
+                my_col[MCRT_WIN_SLOT(cur_row) * stride] = cur_acc;
+                written = cur_row + 1;
+            }
+            cur_row = row;
+            cur_acc = echo;                                                                     // 0 + echo
+        };
+        // rf_image::add_echo (rfimage.h:33-40) with the exact-row guard of ColumnWriter::add_echo.  Returns false when
+        // the echo belongs to a later window (nothing consumed).
+        auto try_echo = [&](float echo, double micros) -> bool {
+            double rowd = micros * inv_row_period;
+            int row = __double2int_rd(rowd);
+            const double fr = rowd - (double)row;
+            if (!(fr >= 1e-9 && fr <= 1.0 - 1e-9)) {
+                rowd = micros / row_period;
+                if (!(rowd < (double)(unsigned)rows)) return true;                              // dropped (row >= max_rows)
+                row = (int)rowd;
+            } else if (row >= rows) {
+                return true;
+            }
+            if (row >= wend) return false;
+            if (row < base) {                                                                   // a finished window: see header
+                atomicAdd(&rf[(size_t)my_scanline * rows + row], echo);
+                atomicAdd(late_echoes, 1ULL);
+                return true;
+            }
+            if (row < cur_row) {                                                                // revisited row of my own column
+                for (int r = written > base ? written : base; r < cur_row; r++) my_col[MCRT_WIN_SLOT(r) * stride] = 0.0f;
+                written = cur_row;
+                my_col[MCRT_WIN_SLOT(row) * stride] += echo;
+                return true;
+            }
+            add_row(echo, row);
+            return true;
+        };
+
+        bool waiting = !active;                      // true: my next echo lies beyond this window (or the path is done)
+        while (!waiting) {
+            if (!in_seg) {
+                if (k >= ns) break;
+                const DevSegment* sg = segments + (size_t)p * aq.max_depth + k;
+                const float4 s0 = __ldg(&sg->s0), s1 = __ldg(&sg->s1), s2 = __ldg(&sg->s2);
+                const int4 s3 = __ldg(&sg->s3);
+                const DevMaterial media = s_mat[s3.z];
+                m_mu0 = media.mu0; m_mu1 = media.mu1; m_sigma = media.sigma;
+                const double distance_traveled = __hiloint2double(s3.y, s3.x);
+                const double starting_micros = ((distance_traveled * 1000) / 1) / aq.speed;      // main.cpp:114
+                const float3 from = make_float3(s0.x, s0.y, s0.z), to = make_float3(s2.x, s2.y, s2.z);
+                const double distance = (double)(v_length(v_sub(to, from)) * 10.0f);               // scene.cpp:342-346
+                const double steps_d = distance / aq.axres_mm;                                      // main.cpp:116
+                unsigned long long steps64;                                                         // B-14
+                if (!(steps_d >= 0.0)) steps64 = 0;
+                else if (steps_d >= 9.0e18) steps64 = 9000000000000000000ULL;
+                else steps64 = (unsigned long long)steps_d;
+                const uint32_t steps32 = (uint32_t)steps64;
+                delta_step = v_scl(make_float3(s1.x, s1.y, s1.z), axres_f);                      // main.cpp:117
+                point = from;
+                time_elapsed = starting_micros;
+                intensity = s1.w;
+                decay = mc_expf(-s2.w * axres_f * 0.01f * aq.frequency * 1.0f);                  // main.cpp:135
+                remaining = steps64 > 0x7fffffffULL ? 0x7fffffff : (int)steps64;
+                const double safe_d = (max_travel_time - time_elapsed) * inv_time_step - 2.0;
+                n_safe = safe_d > 0.0 ? (safe_d < 2.0e9 ? (int)safe_d : 2000000000) : 0;
+                if (n_safe > remaining) n_safe = remaining;
+                end_echo = s0.w / samples_f;
+                end_micros = starting_micros + time_step * (double)(uint32_t)(steps32 - 1u);
+                const float reach = fmaxf(fmaxf(fabsf(from.x), fabsf(from.y)), fabsf(from.z)) +
+                                    2.0f * (float)n_safe * fabsf(axres_f) * fmaxf(fmaxf(fabsf(s1.x), fabsf(s1.y)), fabsf(s1.z));
+                fma_ok = FMADIV && reach * inv_vres < 1.0e9f;
+                // coupling gel (sigma == mu0 == 0) scatters exactly +0 everywhere: only the time chain, which bounds the
+                // step count, is advanced -- in one go, it touches no row
+                if (m_sigma == 0.0f && m_mu0 == 0.0f) {
+                    while (remaining > 0 && time_elapsed < max_travel_time) { time_elapsed = time_elapsed + time_step; remaining--; my_steps++; }
+                    remaining = 0; n_safe = 0;
+                }
+                in_seg = true;
+                k++;
+            }
+            // ---- unrolled blocks: MCRT_WIN_UNROLL steps whose rows are row0 .. row0+U-1, all inside this window ----
+            while (n_safe >= MCRT_WIN_UNROLL) {
+                const double rowd0 = time_elapsed * inv_row_period;
+                const int row0 = __double2int_rd(rowd0);
+                const double f0 = rowd0 - (double)row0;
+                if (!(fast_rows && f0 >= 1e-6 && f0 <= block_safe_hi && row0 < wend && row0 + MCRT_WIN_UNROLL <= rows && row0 >= base && row0 >= cur_row)) break;
+                uint32_t idx[MCRT_WIN_UNROLL];
+                if (fma_ok) {
+#pragma unroll
+                    for (int u = 0; u < MCRT_WIN_UNROLL; u++) { idx[u] = voxel_linear_fma(point, vres, inv_vres); point = v_add(point, delta_step); }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < MCRT_WIN_UNROLL; u++) { idx[u] = voxel_linear(point, vres, inv_vres); point = v_add(point, delta_step); }
+                }
+                float2 vox[MCRT_WIN_UNROLL];
+#pragma unroll
+                for (int u = 0; u < MCRT_WIN_UNROLL; u++) vox[u] = __ldg(&volume[idx[u]]);      // (noise, probability)
+                float echo[MCRT_WIN_UNROLL];
+#pragma unroll
+                for (int u = 0; u < MCRT_WIN_UNROLL; u++) {
+                    // get_scattering(mu1, mu0, sigma, ...): density = mu1, mu = mu0 (main.cpp:126 vs volume.h:46)
+                    const float scattering = vox[u].y >= m_mu1 ? vox[u].x * m_sigma + m_mu0 : 0.0f;
+                    echo[u] = intensity * scattering;
+                    time_elapsed = time_elapsed + time_step;
+                    intensity *= decay;
+                }
+                add_row(echo[0], row0);
+                for (int r = written > base ? written : base; r < row0; r++) my_col[MCRT_WIN_SLOT(r) * stride] = 0.0f;   // gap (time jumped ahead)
+                // rows row0+1 .. row0+U-1 receive exactly one echo each: close every row straight into the column
+                const int slot0 = MCRT_WIN_SLOT(row0);
+                if (slot0 + MCRT_WIN_UNROLL <= MCRT_WIN_RING) {                                 // no wrap inside the block
+                    float* dst = my_col + slot0 * stride;
+#pragma unroll
+                    for (int u = 1; u < MCRT_WIN_UNROLL; u++) {
+                        *dst = cur_acc;
+                        dst += stride;
+                        cur_acc = echo[u];
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 1; u < MCRT_WIN_UNROLL; u++) {
+                        my_col[MCRT_WIN_SLOT(row0 + u - 1) * stride] = cur_acc;
+                        cur_acc = echo[u];
+                    }
+                }
+                written = row0 + MCRT_WIN_UNROLL - 1;
+                cur_row = row0 + MCRT_WIN_UNROLL - 1;
+                n_safe -= MCRT_WIN_UNROLL; remaining -= MCRT_WIN_UNROLL;
+                my_steps += MCRT_WIN_UNROLL;
+            }
+            // ---- single checked steps: window edges, guard bands, the tail of the segment ----
+            bool seg_done = false;
+            while (true) {
+                if (!(remaining > 0 && time_elapsed < max_travel_time)) { seg_done = true; break; }
+                if (n_safe >= MCRT_WIN_UNROLL) {
+                    // back to the block path as soon as a whole block fits this window again
+                    const int row_now = __double2int_rd(time_elapsed * inv_row_period);
+                    if (fast_rows && row_now < wend && row_now + MCRT_WIN_UNROLL <= rows && row_now >= base) {
+                        const double f0 = time_elapsed * inv_row_period - (double)row_now;
+                        if (fast_rows && f0 >= 1e-6 && f0 <= block_safe_hi && row_now >= cur_row) break;
+                    }
+                }
+                const float2 vox = __ldg(&volume[voxel_linear(point, vres, inv_vres)]);
+                const float scattering = vox.y >= m_mu1 ? vox.x * m_sigma + m_mu0 : 0.0f;
+                if (!try_echo(intensity * scattering, time_elapsed)) { waiting = true; break; }
+                point = v_add(point, delta_step);
+                time_elapsed = time_elapsed + time_step;
+                intensity *= decay;
+                remaining--;
+                if (n_safe > 0) n_safe--;
+                my_steps++;
+            }
+            if (seg_done) {
+                // main.cpp:139: the closing echo of the segment
+                if (!try_echo(end_echo, end_micros)) { waiting = true; remaining = 0; n_safe = 0; }
+                else in_seg = false;
+            }
+        }
+        // close my column of this window: pending row (if it lies in the window) and zeros up to the window end
+        if (t < T) {
+            if (cur_row >= base && cur_row < wend) {
+                for (int r = written; r < cur_row; r++) my_col[MCRT_WIN_SLOT(r) * stride] = 0.0f;
+                my_col[MCRT_WIN_SLOT(cur_row) * stride] = cur_acc;
+                written = cur_row + 1;
+                cur_row = -1; cur_acc = 0.0f;
+            }
+            if (written < base) written = base;
+            for (int r = written; r < wend; r++) my_col[MCRT_WIN_SLOT(r) * stride] = 0.0f;
+            if (written < wend) written = wend;
+        }
+        group_sync();
+        // sample reduction in sample order (= k_reduce_samples), coalesced row stores
+        const int wrows = wend - base;
+        for (int j = t; j < MCRT_WIN_ROWS * G; j += group_size) {
+            const int g = j / MCRT_WIN_ROWS, r = j - g * MCRT_WIN_ROWS;                    // constant divisor
+            if (r < wrows && scanline0 + g < n_scanlines) {
+                const float* src = s_win + MCRT_WIN_SLOT(base + r) * stride + g * S;
+                float sum;
+                if ((S & 3) == 0) {
+                    const float4* s4 = reinterpret_cast<const float4*>(src);
+                    float4 v = s4[0];
+                    sum = v.x; sum += v.y; sum += v.z; sum += v.w;
+                    for (int q = 1; q < (S >> 2); q++) { v = s4[q]; sum += v.x; sum += v.y; sum += v.z; sum += v.w; }
+                } else {
+                    sum = src[0];
+                    for (int s = 1; s < S; s++) sum += src[s];
+                }
+                rf[(size_t)(scanline0 + g) * rows + base + r] = sum;
+            }
+        }
+        group_sync();
+    }
+    if (steps_total) {
+        for (int off = 16; off > 0; off >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, off);
+        if ((threadIdx.x & 31) == 0 && my_steps) atomicAdd(steps_total, my_steps);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_reduce_samples(const float* __restrict__ columns, const int64_t n_pixels, const int samples,
                                                        float* __restrict__ rf)
 {
@@ -795,12 +1083,39 @@ size_t accumulate_columns_bytes(const AcqDev& aq, int n_poses)
     return sizeof(float) * (size_t)n_poses * aq.elements * aq.samples * aq.rows;
 }
 
+bool accumulate_windowed_supported(const SceneDev& sc, const AcqDev& aq)
+{
+    return aq.samples >= 1 && aq.samples <= 128 && sc.spacing[0] == 1.0f && sc.spacing[1] == 1.0f && sc.spacing[2] == 1.0f;
+}
+
 cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2* d_volume, const DevSegment* d_segments,
                               const int32_t* d_nseg, int n_poses, float* d_rf, unsigned long long* d_steps, float* d_columns,
                               cudaStream_t stream, int* launches)
 {
-    if (!d_columns) return cudaErrorInvalidValue;
     const int n_paths = n_poses * aq.elements * aq.samples;
+    if (aq.accumulate_windowed && accumulate_windowed_supported(sc, aq)) {
+        // row-window synchronous kernel: no columns in HBM, sample reduction inside (d_steps[1] counts late echoes)
+        const bool warp = aq.samples <= 32;                       // a warp owns whole scanlines: __syncwarp instead of a CTA barrier
+        const int G = (warp ? 32 : 128) / aq.samples;
+        const int n_scanlines = n_poses * aq.elements;
+        const int n_groups = (n_scanlines + G - 1) / G;
+        const size_t smem = sizeof(float) * MCRT_WIN_RING * (size_t)win_stride(G * aq.samples) * (warp ? 4 : 1);
+        const int grid = warp ? (n_groups + 3) / 4 : n_groups;
+        if (warp) {
+            if (aq.voxel_fma_division)
+                k_accumulate_win<true, true><<<grid, 128, smem, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_scanlines, G, d_rf, d_steps, d_steps + 1);
+            else
+                k_accumulate_win<false, true><<<grid, 128, smem, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_scanlines, G, d_rf, d_steps, d_steps + 1);
+        } else {
+            if (aq.voxel_fma_division)
+                k_accumulate_win<true, false><<<grid, 128, smem, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_scanlines, G, d_rf, d_steps, d_steps + 1);
+            else
+                k_accumulate_win<false, false><<<grid, 128, smem, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_scanlines, G, d_rf, d_steps, d_steps + 1);
+        }
+        if (launches) (*launches) += 1;
+        return cudaGetLastError();
+    }
+    if (!d_columns) return cudaErrorInvalidValue;
     const int block = 128;
     if (aq.voxel_fma_division)
         k_accumulate<true><<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_paths, d_columns, d_steps);

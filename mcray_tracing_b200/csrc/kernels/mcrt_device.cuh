@@ -71,7 +71,7 @@ struct AcqDev {
     int deterministic;
     int element_offset;     // global index of local element 0 (scanline-block runs; 0 otherwise): RNG key, PSF borders
     int voxel_fma_division; // 1: coord / vol_resolution via div_fma was validated exhaustively for this resolution (image.cu)
-    int pad1;
+    int accumulate_windowed;// 1: row-window synchronous accumulate (no columns in HBM) when the scene allows it (image.cu)
 };
 
 struct PoseTrigDev { float px, py, pz, cz, sz, cx, sx, cy, sy, pad0, pad1, pad2; };   // = mcrt::PoseTrig, 48 B

@@ -83,6 +83,8 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
 // exhaustive device check (all 2^32 float bit patterns) that the 3-instruction FMA division reproduces the voxel index of
 // coord / resolution for this resolution; enables AcqDev::voxel_fma_division
 cudaError_t validate_fma_division(float resolution, bool* ok);
+// can launch_accumulate use the windowed kernel for this scene / acquisition (then d_columns may be nullptr)?
+bool accumulate_windowed_supported(const SceneDev& sc, const AcqDev& aq);
 // rfimage.h:127-136 (commented out in the reference): I = log10(I+1)/log10(max+1) per image, in place
 void launch_log_compress(float* d_img, int n_images, int64_t px_per_image, int* d_max_bits, cudaStream_t stream, int* launches);
 // [n][cols][rows] -> [n][rows][cols]

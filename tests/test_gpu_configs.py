@@ -220,3 +220,28 @@ def test_scanline_block_partition_equals_whole_frame(api, assets_dirs, kw):
         assert np.array_equal(sim.simulate(pose[None, :], seed=11, first_frame=5)[0], whole)
         with pytest.raises(api.McrtError):
             sim.simulate_scanlines(pose, E - 2, 3)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(elements=256, samples=16), dict(elements=64, samples=5), dict(elements=40, samples=1), dict(elements=33, samples=3),
+    dict(elements=24, samples=128), dict(elements=32, samples=8, axial_scale=17.6, psf_axial=63, psf_lateral=31),
+], ids=["256x16", "64x5", "40x1", "33x3", "24x128", "long-scanlines"])
+def test_windowed_accumulate_equals_column_accumulate(api, assets_dirs, kw):
+    """The row-window synchronous accumulate kernel (columns in shared memory, in-kernel sample reduction, no HBM
+    columns) and the k_accumulate + k_reduce_samples pair give bit-identical frames and step counts; no echo ever
+    arrives for an already finished window (late_echoes == 0)."""
+    path = assets_dirs["ircad11"] / "santi-liver-rough.scene"
+    from mcray_tracing_b200 import assets
+    poses = assets.sweep_poses(5)
+    with api.Simulator(path, api.default_params(**kw)) as sim:
+        win = sim.simulate(poses, seed=17, first_frame=3)
+        st_w = sim.stats()
+        sim.set_option("accumulate_windowed", 0)
+        col = sim.simulate(poses, seed=17, first_frame=3)
+        st_c = sim.stats()
+        sim.set_option("accumulate_windowed", 1)
+        again = sim.simulate(poses, seed=17, first_frame=3)
+    assert st_w.kernel_launches == st_c.kernel_launches - 1          # really two different kernels
+    assert st_w.march_steps == st_c.march_steps and st_w.late_echoes == 0
+    assert np.array_equal(win, col) and np.array_equal(again, win)
+    assert np.count_nonzero(win) > 0.2 * win.size
