@@ -123,7 +123,8 @@ struct mcrt_ctx {
     bool count_traversal = false;
     bool log_compress = false;             // rfimage.h:127-136, commented out in the reference
     int* d_max_bits = nullptr;             // [cap_poses] per-image maximum (ordered-int encoding)
-    bool ordered_compaction = false;       // order-preserving compaction between bounces (TraceBuffers::chunk_prefix_a)
+    int first_hit_dedup = 1;               // bounce 0 traced once per element (TraceBuffers::first_hits) when samples >= 4: 0 off, 1 large calls, 2 always
+    int ordered_compaction = 1;            // order-preserving compaction between bounces (TraceBuffers::chunk_prefix_a): 0 off, 1 large calls, 2 always
     bool coherence_sort = false;           // radix-sort surviving paths between bounces (rough scenes)
     float* d_rf_acc = nullptr;
     float* d_rf_tmp0 = nullptr;
@@ -140,6 +141,7 @@ struct mcrt_ctx {
     unsigned long long* h_trav = nullptr;
 
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;   // (n_poses in batch, want_scan) -> exec
+    std::map<std::pair<int, int>, int> graph_launches;        // kernels in that graph, counted while capturing
     bool use_graph = true;
     bool profile_stages = false;
     int max_batch_poses = 256;
@@ -152,6 +154,8 @@ struct mcrt_ctx {
 namespace {
 
 const int kMaxBatchesPerCall = 4096;
+const int64_t kOrderedMinPaths = 262144;      // paths per call from which the order-preserving compaction is used
+const int64_t kFirstHitMinElements = 4096;   // (pose, element) pairs per call from which bounce 0 is traced once per element
 const int kMaxSub = 4;               // sub-batches of the two-stream pipeline
 const int kMinPosesPerSub = 8;
 const int kCounterSlot = 128;        // ints reserved per batch in the pinned counters mirror
@@ -164,7 +168,7 @@ void free_workspace(mcrt_ctx* c)
     dev_free(c->tb.segments); dev_free(c->tb.n_segments); dev_free(c->tb.hit_fraction); dev_free(c->tb.hit_mesh);
     dev_free(c->tb.queue_a); dev_free(c->tb.queue_b); dev_free(c->tb.counters);
     dev_free(c->tb.sort_keys); dev_free(c->tb.sort_keys_tmp); dev_free(c->tb.sort_queue_tmp);
-    dev_free(c->tb.chunk_prefix_a); dev_free(c->tb.chunk_prefix_b); dev_free(c->tb.n_chunks);
+    dev_free(c->tb.chunk_prefix_a); dev_free(c->tb.chunk_prefix_b); dev_free(c->tb.n_chunks); dev_free(c->tb.first_hits);
     if (c->tb.sort_tmp) cudaFree(c->tb.sort_tmp);
     c->tb.sort_tmp = nullptr; c->tb.sort_tmp_bytes = 0;
     dev_free(c->d_poses); dev_free(c->d_rf_acc); dev_free(c->d_rf_tmp0); dev_free(c->d_rf_tmp1); dev_free(c->d_rf_final);
@@ -202,6 +206,7 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
     if (c->columns_bytes) dev_alloc(c->d_columns, c->columns_bytes / sizeof(float));
     CUDA_TRY(cudaMallocHost(&c->h_poses, sizeof(PoseTrig) * (size_t)n_poses));
     c->tb.trav_counters = c->count_traversal ? c->d_trav : nullptr;
+    if (c->first_hit_dedup && c->aq.samples >= 4) dev_alloc(c->tb.first_hits, 2 * (size_t)n_poses * c->aq.elements);
     if (c->ordered_compaction) {
         const size_t n_chunks = (n_paths + 127) / 128 + 2;
         dev_alloc(c->tb.chunk_prefix_a, n_chunks); dev_alloc(c->tb.chunk_prefix_b, n_chunks);
@@ -227,7 +232,14 @@ void enqueue_trace(mcrt_ctx* c, int pose0, int n, int slot, cudaStream_t s, int*
     if (tb.hit_fraction) tb.hit_fraction += p0 * c->aq.max_depth;
     if (tb.hit_mesh) tb.hit_mesh += p0 * c->aq.max_depth;
     tb.queue_a += p0; tb.queue_b += p0;
-    if (pose0 != 0 || slot != 0) { tb.chunk_prefix_a = nullptr; tb.chunk_prefix_b = nullptr; tb.n_chunks = nullptr; }   // sub-batches: atomic compaction
+    // measured (profiles/r01u_ab_firsthit.txt): -3.6 % trace time at 256 frames per call, +2 % at one frame (one more dependent launch)
+    if (tb.first_hits && c->first_hit_dedup == 1 && (int64_t)n * c->aq.elements < kFirstHitMinElements) tb.first_hits = nullptr;
+    if (tb.first_hits) tb.first_hits += 2 * (size_t)pose0 * c->aq.elements;
+    // sub-batches keep the atomic compaction; small calls too (the 9 extra scan launches cost more than the order returns:
+    // +1.6 % frames/s at 256 frames per call, profiles/r01o_ab_ordered.txt)
+    if (pose0 != 0 || slot != 0 || c->coherence_sort || (c->ordered_compaction == 1 && (int64_t)n * c->aq.elements * c->aq.samples < kOrderedMinPaths)) {
+        tb.chunk_prefix_a = nullptr; tb.chunk_prefix_b = nullptr; tb.n_chunks = nullptr;
+    }
     if (tb.sort_keys) { tb.sort_keys += p0; tb.sort_keys_tmp += p0; tb.sort_queue_tmp += p0; }
     tb.counters += (size_t)slot * (c->aq.max_depth + 1);
     launch_trace(c->sc, c->aq, fr, tb, c->sm_count, s, launches);
@@ -305,14 +317,6 @@ int pipeline_sub_batches(const mcrt_ctx* c, int n)
     return nsub > kMaxSub ? kMaxSub : nsub;
 }
 
-int count_pipeline_launches(const mcrt_ctx* c, bool want_scan, int nsub)
-{
-    const int scans = (c->ordered_compaction && nsub == 1) ? c->aq.max_depth - 1 : 0;
-    const int acc = (c->aq.accumulate_windowed && accumulate_windowed_supported(c->sc, c->aq)) ? 1 : 2;   // accumulate (+ sample reduction)
-    return nsub * (c->aq.max_depth + scans + acc + post_launch_count(c->aq.elements, c->aq.rows, c->params.psf_lateral, 3, 1) + (c->params.rf_layout == 1 ? 1 : 0) +
-                   (c->log_compress ? 2 : 0) + (want_scan ? 1 : 0));
-}
-
 void run_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches)
 {
     const bool graph_ok = c->use_graph && !c->profile_stages;
@@ -342,9 +346,10 @@ void run_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) throw CudaError(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
         it = c->graphs.emplace(key, exec).first;
+        c->graph_launches[key] = dummy;
     }
     CUDA_TRY(cudaGraphLaunch(it->second, s));
-    if (launches) *launches += count_pipeline_launches(c, want_scan, nsub);
+    if (launches) *launches += c->graph_launches[key];
 }
 
 int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t seed, uint64_t first_frame, float* rf_out,
@@ -728,11 +733,16 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
         c->graphs.clear();
         c->log_compress = value != 0;
     }
+    else if (n == "first_hit_dedup") {
+        CUDA_TRY_NOTHROW(cudaStreamSynchronize(c->stream));
+        free_workspace(c);
+        c->first_hit_dedup = value < 0 ? 0 : (value > 2 ? 2 : (int)value);
+    }
     else if (n == "ordered_compaction") {
         // changes the workspace and the captured graphs: drop both, they are rebuilt on the next call
         CUDA_TRY_NOTHROW(cudaStreamSynchronize(c->stream));
         free_workspace(c);
-        c->ordered_compaction = value != 0;
+        c->ordered_compaction = value < 0 ? 0 : (value > 2 ? 2 : (int)value);
     }
     else if (n == "coherence_sort") {
         // changes the workspace and the captured graphs: drop both, they are rebuilt on the next call

@@ -54,6 +54,10 @@ struct TraceBuffers {
     int* chunk_prefix_a;           // [ceil(n_paths / 128) + 1]
     int* chunk_prefix_b;
     int* n_chunks;                 // [max_depth + 1]: chunks written by bounce b - 1 = entries of the prefix bounce b reads
+    // optional (nullptr = off): closest hit of bounce 0 per (pose, element).  All samples of an element leave the transducer
+    // on the same ray (scene.cpp:84-100), so k_first_hit traces it once and bounce 0 only shades: 2 float4 per element =
+    // (fraction, tri_id, mesh, dist_a), (n_raw.xyz, -)
+    float4* first_hits;
 };
 
 // generate + max_depth x (intersect, shade, compact): scene::cast_rays (scene.cpp:50-183)

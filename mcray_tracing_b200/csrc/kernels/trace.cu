@@ -86,7 +86,14 @@ __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq
     const float3 to = v_add(from, v_scl(make_float3(sc.spacing[0] * dir.x, sc.spacing[1] * dir.y, sc.spacing[2] * dir.z), r_length / 100.0f));
     const float3 from_test = v_add(from, v_scl(dir, 0.1f));
     HitRec h;
-    closest_hit(sc, sh.mesh_origin, from_test, to, h, node_visits, tri_tests);
+    if (FIRST && tb.first_hits) {
+        // traced once per element by k_first_hit (same ray for every sample)
+        const float4 a = __ldg(&tb.first_hits[2 * (size_t)(p / aq.samples)]), b = __ldg(&tb.first_hits[2 * (size_t)(p / aq.samples) + 1]);
+        h.fraction = a.x; h.tri_id = __float_as_int(a.y); h.mesh = __float_as_int(a.z); h.dist_a = a.w;
+        h.n_raw = make_float3(b.x, b.y, b.z);
+    } else {
+        closest_hit(sc, sh.mesh_origin, from_test, to, h, node_visits, tri_tests);
+    }
 
     DevSegment seg;
     bool alive = false;
@@ -283,6 +290,40 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const Scen
     }
 }
 
+// Bounce 0 for one (pose, element): every sample of the element starts on this ray with intensity 1 / samples in the
+// starting medium (scene.cpp:84-100), so its closest hit is found once here; k_bounce<true> then shades each sample.
+__global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_first_hit(const SceneDev sc, const AcqDev aq, const FrameDev fr, const TraceBuffers tb)
+{
+    __shared__ SharedScene sh;
+    load_shared_scene(sc, sh);
+    const int n = fr.n_poses * aq.elements;
+    int node_visits = 0, tri_tests = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int pose = i / aq.elements, element = i - pose * aq.elements;
+        float3 from, dir;
+        element_pose(aq, fr.poses[pose], __ldg(&fr.elem_sincos[element]), from, dir);
+        const float intensity = 1.0f / (float)(unsigned)aq.samples;
+        const DevMaterial med = sh.materials[sc.starting_material];
+        const float r_length = rp_max_ray_length(med.attenuation, intensity, aq.frequency);
+        const float3 to = v_add(from, v_scl(make_float3(sc.spacing[0] * dir.x, sc.spacing[1] * dir.y, sc.spacing[2] * dir.z), r_length / 100.0f));
+        const float3 from_test = v_add(from, v_scl(dir, 0.1f));
+        HitRec h;
+        closest_hit(sc, sh.mesh_origin, from_test, to, h, node_visits, tri_tests);
+        tb.first_hits[2 * (size_t)i] = make_float4(h.fraction, __int_as_float(h.tri_id), __int_as_float(h.mesh), h.dist_a);
+        tb.first_hits[2 * (size_t)i + 1] = make_float4(h.n_raw.x, h.n_raw.y, h.n_raw.z, 0.0f);
+    }
+    if (tb.trav_counters) {
+        for (int off = 16; off > 0; off >>= 1) {
+            node_visits += __shfl_xor_sync(0xffffffffu, node_visits, off);
+            tri_tests += __shfl_xor_sync(0xffffffffu, tri_tests, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&tb.trav_counters[0], (unsigned long long)node_visits);
+            atomicAdd(&tb.trav_counters[1], (unsigned long long)tri_tests);
+        }
+    }
+}
+
 // ORDERED compaction, between bounce b and b + 1: exclusive prefix of the per-chunk survivor counts bounce b wrote
 // (in place), counters[b + 1] = number of survivors, n_chunks[b + 1] = number of chunks.  One CTA; the arrays are small
 // (n_paths / 128 entries).
@@ -401,6 +442,11 @@ void launch_trace(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, cons
     const int block = 128;
     // persistent-style grid: a multiple of the SM count, grid-stride loop inside
     const int grid = grid_for(n_paths, block, sm_count, MCRT_BOUNCE_GRID_CTAS_PER_SM);
+    if (tb.first_hits) {
+        const int n_elem = fr.n_poses * aq.elements;
+        k_first_hit<<<grid_for(n_elem, block, sm_count, MCRT_BOUNCE_GRID_CTAS_PER_SM), block, 0, stream>>>(sc, aq, fr, tb);
+        if (launches) (*launches)++;
+    }
     for (int b = 0; b < aq.max_depth; b++) {
         const bool sort = tb.sort_keys && !tb.chunk_prefix_a && b + 1 < aq.max_depth;
         // unused queue slots get the largest key so they sort behind the survivors
