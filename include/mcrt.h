@@ -187,6 +187,20 @@ int mcrt_postprocess(mcrt_ctx* ctx, const float* rf_in, int32_t cols, int32_t ro
                      const float* lateral, int32_t n_lateral, int32_t flags, float* rf_out);
 /* rf_image::create_mapping + cv::remap (rfimage.h:183-215, 139) on the ctx's geometry */
 int mcrt_scan_convert(mcrt_ctx* ctx, const float* rf_in /* [cols][rows] */, float* scan_out);
+/* B-mode display chain on an envelope image (the reference stops at the envelope and keeps its
+ * log compression commented out, rfimage.h:127-136, then writes the scan-converted image x255 as 8 bit, rfimage.h:142-148):
+ *   v = |E| * 10^((gain_db + tgc_db_per_cm * depth_cm(row)) / 20),   y = clamp(1 + 20 log10(v / max v) / dynamic_range_db, 0, 1),
+ * then create_mapping + cv::remap and x255 -> uint8.  env_in: n x [cols][rows] (rf_out of mcrt_simulate, rf_layout 0), host
+ * or device.  compressed_out (nullable): n x [cols][rows] float in [0,1].  bmode8_out (nullable): n x scan_rows x scan_cols
+ * uint8.  Both outputs host or device. */
+typedef struct mcrt_bmode_params {
+    float gain_db;           /* overall gain */
+    float tgc_db_per_cm;     /* time-gain compensation slope; depth_cm(row) = row * depth_cm / rows */
+    float dynamic_range_db;  /* > 0, e.g. 60 */
+    float reserved0;
+} mcrt_bmode_params;
+int mcrt_bmode(mcrt_ctx* ctx, const float* env_in, int32_t n_images, const mcrt_bmode_params* bp, float* compressed_out,
+               uint8_t* bmode8_out);
 int mcrt_get_psf_taps(const mcrt_ctx* ctx, float* axial, float* lateral);
 /* scene as loaded (for loader parity): local-frame vertices (v_obj*scaling) 9 floats/triangle in
  * objloader order, mesh id per triangle, body origin per mesh (scene.cpp:313-324) */

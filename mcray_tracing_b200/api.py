@@ -51,6 +51,10 @@ class Info(C.Structure):
                 ("row_period_us", C.c_double), ("max_travel_time_us", C.c_double), ("voxel_fma_division", C.c_int32), ("reserved0", C.c_int32)]
 
 
+class BmodeParams(C.Structure):
+    _fields_ = [("gain_db", C.c_float), ("tgc_db_per_cm", C.c_float), ("dynamic_range_db", C.c_float), ("reserved0", C.c_float)]
+
+
 class Stats(C.Structure):
     _fields_ = [("poses", C.c_int64), ("segments", C.c_int64), ("march_steps", C.c_int64), ("kernel_launches", C.c_int64),
                 ("ms_total", C.c_float), ("ms_trace", C.c_float), ("ms_accumulate", C.c_float), ("ms_post", C.c_float),
@@ -66,7 +70,7 @@ assert SEGMENT_DTYPE.itemsize == 72
 EXPORTS = ["mcrt_default_params", "mcrt_create", "mcrt_create_from_arrays", "mcrt_destroy", "mcrt_last_error", "mcrt_get_info",
            "mcrt_get_stats", "mcrt_set_option", "mcrt_simulate", "mcrt_simulate_async", "mcrt_trace_debug", "mcrt_closest_hit",
            "mcrt_transducer_elements", "mcrt_accumulate", "mcrt_postprocess", "mcrt_scan_convert", "mcrt_get_psf_taps",
-           "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe", "mcrt_load_obj", "mcrt_scene_probe", "mcrt_host_tables", "mcrt_simulate_scanlines"]
+           "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe", "mcrt_load_obj", "mcrt_scene_probe", "mcrt_host_tables", "mcrt_simulate_scanlines", "mcrt_bmode"]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
@@ -101,6 +105,7 @@ def lib():
         L.mcrt_simulate_async.argtypes = [vp, vp, C.c_int32, C.c_uint64, C.c_uint64, vp, vp, vp]
         L.mcrt_trace_debug.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, vp]
         L.mcrt_simulate_scanlines.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, vp]
+        L.mcrt_bmode.argtypes = [vp, vp, C.c_int32, vp, vp, vp]
         L.mcrt_closest_hit.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
         L.mcrt_transducer_elements.argtypes = [vp, vp, vp, vp]
         L.mcrt_accumulate.argtypes = [vp, vp, vp, vp]
@@ -237,6 +242,19 @@ class Simulator:
         out = np.empty((n_elements, self.rows), np.float32)
         _check(lib().mcrt_simulate_scanlines(self.h, _p(P), int(seed), int(frame), int(first_element), int(n_elements), _p(out)))
         return out
+
+    def bmode(self, env, gain_db: float = 0.0, tgc_db_per_cm: float = 0.0, dynamic_range_db: float = 60.0):
+        """B-mode display chain (mcrt_bmode) on envelope images [n][cols][rows] (rf_layout 0):
+        returns (compressed float [n][cols][rows] in [0,1], 8-bit scan-converted [n][scan_rows][scan_cols])."""
+        e = np.ascontiguousarray(env, np.float32)
+        if e.ndim == 2:
+            e = e[None]
+        n = e.shape[0]
+        bp = BmodeParams(gain_db, tgc_db_per_cm, dynamic_range_db, 0.0)
+        cmp_ = np.empty_like(e)
+        img8 = np.empty((n, self.info.scan_rows, self.info.scan_cols), np.uint8)
+        _check(lib().mcrt_bmode(self.h, _p(e), n, C.byref(bp), _p(cmp_), _p(img8)))
+        return cmp_, img8
 
     def get_info(self) -> Info:
         """mcrt_get_info, re-read (options can change what it reports)."""

@@ -1031,6 +1031,56 @@ int mcrt_scan_convert(mcrt_ctx* c, const float* rf_in, float* scan_out)
     });
 }
 
+int mcrt_bmode(mcrt_ctx* c, const float* env_in, int32_t n_images, const mcrt_bmode_params* bp, float* compressed_out, uint8_t* bmode8_out)
+{
+    if (!c || !env_in || !bp || n_images < 1) return fail(MCRT_ERR_INVALID, "mcrt_bmode: null argument");
+    if (!(bp->dynamic_range_db > 0.0f)) return fail(MCRT_ERR_INVALID, "mcrt_bmode: dynamic_range_db must be > 0");
+    return guarded("mcrt_bmode", [&]() {
+        CUDA_TRY(cudaSetDevice(c->device));
+        const int rows = c->aq.rows, cols = c->aq.elements;
+        const size_t px = (size_t)rows * cols, ns = (size_t)c->params.scan_rows * c->params.scan_cols;
+        // gain table from the shared numerics (so the oracle reproduces it bit for bit): 10^(dB / 20) = exp(dB * ln10 / 20)
+        std::vector<float> gain(rows);
+        for (int r = 0; r < rows; r++) {
+            const double depth_cm = (double)r * c->params.depth_cm / (double)rows;
+            gain[r] = (float)mc_exp(((double)bp->gain_db + (double)bp->tgc_db_per_cm * depth_cm) * (2.30258509299404568402 / 20.0));
+        }
+        float *d_gain = nullptr, *d_env = nullptr, *d_cmp = nullptr, *d_scan = nullptr;
+        unsigned char* d_q = nullptr;
+        int* d_max = nullptr;
+        cudaStream_t s = c->stream;
+        auto cleanup = [&]() { dev_free(d_gain); dev_free(d_env); dev_free(d_cmp); dev_free(d_scan); dev_free(d_q); dev_free(d_max); };
+        try {
+            dev_alloc(d_gain, (size_t)rows); dev_alloc(d_cmp, px * n_images); dev_alloc(d_max, (size_t)n_images);
+            CUDA_TRY(cudaMemcpyAsync(d_gain, gain.data(), sizeof(float) * rows, cudaMemcpyHostToDevice, s));
+            const float* src = env_in;
+            if (!is_device_pointer(env_in)) {
+                dev_alloc(d_env, px * n_images);
+                CUDA_TRY(cudaMemcpyAsync(d_env, env_in, sizeof(float) * px * n_images, cudaMemcpyHostToDevice, s));
+                src = d_env;
+            }
+            int launches = 0;
+            launch_bmode(src, n_images, cols, rows, d_gain, bp->dynamic_range_db, d_cmp, d_max, s, &launches);
+            if (compressed_out)
+                CUDA_TRY(cudaMemcpyAsync(compressed_out, d_cmp, sizeof(float) * px * n_images,
+                                         is_device_pointer(compressed_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+            if (bmode8_out) {
+                dev_alloc(d_scan, ns * n_images); dev_alloc(d_q, ns * n_images);
+                launch_scan_convert(d_cmp, n_images, cols, rows, c->d_map_x, c->d_map_y, c->params.scan_rows, c->params.scan_cols, d_scan, s, &launches);
+                launch_quantize8(d_scan, (int64_t)(ns * n_images), d_q, s, &launches);
+                CUDA_TRY(cudaMemcpyAsync(bmode8_out, d_q, ns * n_images, is_device_pointer(bmode8_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+            }
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaStreamSynchronize(s));
+            c->stats = mcrt_stats{};
+            c->stats.poses = n_images; c->stats.kernel_launches = launches;
+            c->stats_pending = false;
+        } catch (...) { cleanup(); throw; }
+        cleanup();
+        return MCRT_OK;
+    });
+}
+
 int mcrt_get_psf_taps(const mcrt_ctx* c, float* axial, float* lateral)
 {
     if (!c || !axial || !lateral) return fail(MCRT_ERR_INVALID, "mcrt_get_psf_taps: null argument");

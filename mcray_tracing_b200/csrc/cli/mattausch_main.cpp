@@ -4,6 +4,9 @@
 // x255 conversion of rf_image::save, rfimage.h:142-148) instead of opening an imshow window.
 // Extensions (all optional, reference defaults otherwise):
 //   --frames N  --seed S  --elements E  --samples S  --deterministic  --out DIR  --device D  --log-compress
+//   --png                      also write the scan-converted image as 8-bit PNG (frame 0 under the reference's name,
+//                              prelog.png, rfimage.h:147)
+//   --bmode DR [--gain dB] [--tgc dB/cm]   B-mode display chain (mcrt_bmode): TGC, log compression to DR dB -> bmode_NNNN.png
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -31,6 +34,70 @@ static bool write_pgm(const std::string& path, const float* img, int rows, int c
     return true;
 }
 
+// Minimal 8-bit grayscale PNG: zlib stream of *stored* deflate blocks (no compression library needed).
+static unsigned crc32_update(unsigned crc, const unsigned char* p, size_t n)
+{
+    static unsigned table[256];
+    static bool init = false;
+    if (!init) {
+        for (unsigned i = 0; i < 256; i++) { unsigned c = i; for (int k = 0; k < 8; k++) c = (c & 1) ? 0xedb88320u ^ (c >> 1) : c >> 1; table[i] = c; }
+        init = true;
+    }
+    for (size_t i = 0; i < n; i++) crc = table[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
+    return crc;
+}
+static void put_be32(std::vector<unsigned char>& v, unsigned x) { for (int s = 24; s >= 0; s -= 8) v.push_back((unsigned char)(x >> s)); }
+static void png_chunk(FILE* f, const char* type, const std::vector<unsigned char>& data)
+{
+    std::vector<unsigned char> head; put_be32(head, (unsigned)data.size());
+    fwrite(head.data(), 1, 4, f);
+    std::vector<unsigned char> body(type, type + 4);
+    body.insert(body.end(), data.begin(), data.end());
+    fwrite(body.data(), 1, body.size(), f);
+    std::vector<unsigned char> tail; put_be32(tail, crc32_update(0xffffffffu, body.data(), body.size()) ^ 0xffffffffu);
+    fwrite(tail.data(), 1, 4, f);
+}
+static bool write_png8(const std::string& path, const unsigned char* img, int rows, int cols)
+{
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    const unsigned char sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+    fwrite(sig, 1, 8, f);
+    std::vector<unsigned char> ihdr; put_be32(ihdr, (unsigned)cols); put_be32(ihdr, (unsigned)rows);
+    const unsigned char rest[5] = {8, 0, 0, 0, 0};                 // 8 bit, grayscale, deflate, no filter, no interlace
+    ihdr.insert(ihdr.end(), rest, rest + 5);
+    png_chunk(f, "IHDR", ihdr);
+    std::vector<unsigned char> raw;                                // scanlines, each prefixed by filter type 0
+    raw.reserve((size_t)rows * (cols + 1));
+    for (int r = 0; r < rows; r++) { raw.push_back(0); raw.insert(raw.end(), img + (size_t)r * cols, img + (size_t)(r + 1) * cols); }
+    std::vector<unsigned char> z = {0x78, 0x01};
+    unsigned a = 1, b = 0;                                         // adler32
+    for (unsigned char c : raw) { a = (a + c) % 65521u; b = (b + a) % 65521u; }
+    for (size_t off = 0; off < raw.size() || off == 0; off += 65535) {
+        const size_t n = raw.size() - off < 65535 ? raw.size() - off : 65535;
+        z.push_back(off + n >= raw.size() ? 1 : 0);               // BFINAL, BTYPE = 00 (stored)
+        z.push_back((unsigned char)(n & 0xff)); z.push_back((unsigned char)(n >> 8));
+        z.push_back((unsigned char)(~n & 0xff)); z.push_back((unsigned char)((~n >> 8) & 0xff));
+        z.insert(z.end(), raw.begin() + off, raw.begin() + off + n);
+        if (raw.empty()) break;
+    }
+    put_be32(z, (b << 16) | a);
+    png_chunk(f, "IDAT", z);
+    png_chunk(f, "IEND", {});
+    fclose(f);
+    return true;
+}
+
+static void quantize8(const float* img, size_t n, std::vector<unsigned char>& out)
+{
+    out.resize(n);
+    for (size_t i = 0; i < n; i++) {
+        const float v = img[i] * 255.0f;                             // convertTo(CV_8U, 255.0): round + saturate
+        const long q = std::isnan(v) ? 0 : lrintf(v);
+        out[i] = (unsigned char)(q < 0 ? 0 : (q > 255 ? 255 : q));
+    }
+}
+
 int main(int argc, char** argv)
 {
     if (argc < 2 || argv[1][0] == '-') {
@@ -39,7 +106,8 @@ int main(int argc, char** argv)
     }
     mcrt_params p;
     mcrt_default_params(&p);
-    int frames = 1, device = 0, log_compress = 0;
+    int frames = 1, device = 0, log_compress = 0, png = 0, bmode = 0;
+    mcrt_bmode_params bp = {0.0f, 0.0f, 60.0f, 0.0f};
     unsigned long long seed = 0;
     std::string out_dir = ".";
     for (int i = 2; i < argc; i++) {
@@ -53,6 +121,10 @@ int main(int argc, char** argv)
         else if (a == "--out") out_dir = next();
         else if (a == "--device") device = atoi(next());
         else if (a == "--log-compress") log_compress = 1;        // rfimage.h:131-136 (commented out in the reference)
+        else if (a == "--png") png = 1;
+        else if (a == "--bmode") { bmode = 1; bp.dynamic_range_db = (float)atof(next()); }
+        else if (a == "--gain") bp.gain_db = (float)atof(next());
+        else if (a == "--tgc") bp.tgc_db_per_cm = (float)atof(next());
         else { printf("Incorrect argument list.\n"); return 0; }
     }
     mcrt_ctx* ctx = nullptr;
@@ -83,6 +155,22 @@ int main(int argc, char** argv)
         if (FILE* fh = fopen((out_dir + name).c_str(), "wb")) { fwrite(rf.data(), sizeof(float), rf.size(), fh); fclose(fh); }
         snprintf(name, sizeof(name), "/mattausch_%04d.pgm", f);
         write_pgm(out_dir + name, scan.data(), info.scan_rows, info.scan_cols);
+        std::vector<unsigned char> img8;
+        if (png) {
+            quantize8(scan.data(), scan.size(), img8);
+            if (f == 0) write_png8(out_dir + "/prelog.png", img8.data(), info.scan_rows, info.scan_cols);        // rfimage.h:147
+            snprintf(name, sizeof(name), "/mattausch_%04d.png", f);
+            write_png8(out_dir + name, img8.data(), info.scan_rows, info.scan_cols);
+        }
+        if (bmode) {
+            img8.resize(scan.size());
+            if (mcrt_bmode(ctx, rf.data(), 1, &bp, nullptr, img8.data()) != MCRT_OK) {
+                printf("The program found an error and will terminate.\nReason:\n%s\n", mcrt_last_error());
+                break;
+            }
+            snprintf(name, sizeof(name), "/bmode_%04d.png", f);
+            write_png8(out_dir + name, img8.data(), info.scan_rows, info.scan_cols);
+        }
     }
     mcrt_destroy(ctx);
     return 0;

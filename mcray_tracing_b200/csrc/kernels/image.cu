@@ -1246,6 +1246,83 @@ void launch_log_compress(float* d_img, int n_images, int64_t px_per_image, int* 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// B-mode display chain (the reference stops at the envelope and keeps its log compression
+// commented out, rfimage.h:127-136): time-gain compensation, log compression to a dynamic range, 8-bit output.
+//   v = |E[row]| * gain[row]          gain[row] = 10^((gain_db + tgc_db_per_cm * depth_cm(row)) / 20)   (host table)
+//   y = clamp(1 + (20 / DR) * log10(v / max_image(v)), 0, 1)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bmode_gain_max(const float* __restrict__ env, const int rows, const int64_t px_per_image,
+                                                       const float* __restrict__ gain, float* __restrict__ out, int* __restrict__ max_bits)
+{
+    const float* I = env + (size_t)blockIdx.y * px_per_image;
+    float* O = out + (size_t)blockIdx.y * px_per_image;
+    float m = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < px_per_image; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = fabsf(__ldg(&I[i])) * __ldg(&gain[(int)(i % rows)]);
+        O[i] = v;
+        m = fmaxf(m, v);                                                    // NaN samples never win
+    }
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    __shared__ float s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, s[w]);
+        atomicMax(&max_bits[blockIdx.y], __float_as_int(m));                // m >= 0: the bit pattern is ordered
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bmode_compress(float* __restrict__ img, const int64_t px_per_image, const int* __restrict__ max_bits,
+                                                       const float dynamic_range_db)
+{
+    const double ln10 = 2.30258509299404568402;
+    const double maxv = (double)__int_as_float(max_bits[blockIdx.y]);
+    const double scale = 20.0 / (double)dynamic_range_db;
+    float* I = img + (size_t)blockIdx.y * px_per_image;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < px_per_image; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = I[i];
+        float y = 0.0f;
+        if (maxv > 0.0 && v > 0.0f) {
+            y = (float)(1.0 + scale * (mc_log((double)v / maxv) / ln10));
+            y = y < 0.0f ? 0.0f : (y > 1.0f ? 1.0f : y);
+        }
+        I[i] = y;                                                            // NaN in -> 0
+    }
+}
+
+__global__ void __launch_bounds__(256) k_quantize8(const float* __restrict__ in, const int64_t n, unsigned char* __restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = in[i] * 255.0f;                                       // convertTo(CV_8U, 255.0): round to nearest even, saturate
+        const int q = (v != v) ? 0 : __float2int_rn(fminf(fmaxf(v, 0.0f), 255.0f));
+        out[i] = (unsigned char)q;
+    }
+}
+
+void launch_bmode(const float* d_env, int n_images, int cols, int rows, const float* d_gain, float dynamic_range_db, float* d_out,
+                  int* d_max_bits, cudaStream_t stream, int* launches)
+{
+    const int64_t px = (int64_t)cols * rows;
+    cudaMemsetAsync(d_max_bits, 0, sizeof(int) * (size_t)n_images, stream);
+    int gx = (int)((px + 256 * 8 - 1) / (256 * 8));
+    if (gx < 1) gx = 1;
+    if (gx > 1024) gx = 1024;
+    for (int i0 = 0; i0 < n_images; i0 += 65535) {
+        const int ni = n_images - i0 < 65535 ? n_images - i0 : 65535;
+        dim3 grid(gx, ni, 1);
+        k_bmode_gain_max<<<grid, 256, 0, stream>>>(d_env + (size_t)i0 * px, rows, px, d_gain, d_out + (size_t)i0 * px, d_max_bits + i0);
+        k_bmode_compress<<<grid, 256, 0, stream>>>(d_out + (size_t)i0 * px, px, d_max_bits + i0, dynamic_range_db);
+        if (launches) (*launches) += 2;
+    }
+}
+
+void launch_quantize8(const float* d_in, int64_t n, unsigned char* d_out, cudaStream_t stream, int* launches)
+{
+    k_quantize8<<<grid1d(n, 256), 256, 0, stream>>>(d_in, n, d_out);
+    if (launches) (*launches)++;
+}
+
 void launch_transpose(const float* d_in, int n_images, int cols, int rows, float* d_out, cudaStream_t stream, int* launches)
 {
     dim3 block(32, 8, 1), grid((rows + 31) / 32, (cols + 31) / 32, n_images);

@@ -91,6 +91,11 @@ cudaError_t validate_fma_division(float resolution, bool* ok);
 bool accumulate_windowed_supported(const SceneDev& sc, const AcqDev& aq);
 // rfimage.h:127-136 (commented out in the reference): I = log10(I+1)/log10(max+1) per image, in place
 void launch_log_compress(float* d_img, int n_images, int64_t px_per_image, int* d_max_bits, cudaStream_t stream, int* launches);
+// B-mode display chain on the envelope image [n][cols][rows]: TGC gain table (per row), log compression to a dynamic range;
+// d_out receives values in [0, 1].  launch_quantize8: x255, round, saturate -> uint8
+void launch_bmode(const float* d_env, int n_images, int cols, int rows, const float* d_gain, float dynamic_range_db, float* d_out,
+                  int* d_max_bits, cudaStream_t stream, int* launches);
+void launch_quantize8(const float* d_in, int64_t n, unsigned char* d_out, cudaStream_t stream, int* launches);
 // [n][cols][rows] -> [n][rows][cols]
 void launch_transpose(const float* d_in, int n_images, int cols, int rows, float* d_out, cudaStream_t stream, int* launches);
 // cv::remap (rfimage.h:139) with the precomputed maps; input scanline-major [n][cols][rows]

@@ -880,6 +880,34 @@ void orc_envelope(float* rf, int32_t rows, int32_t cols)
 }
 
 // rfimage.h:127-136 (commented out in the reference): max = minMaxLoc; I = log10(I + 1) / log10(max + 1)
+// B-mode display chain (new functionality on top of rfimage.h:127-148): TGC gain, log compression to a
+// dynamic range.  rf: [rows][cols] envelope image (oracle layout), in place -> [0, 1].
+void orc_bmode(float* rf, int32_t rows, int32_t cols, double depth_cm, float gain_db, float tgc_db_per_cm, float dynamic_range_db)
+{
+    const double ln10 = 2.30258509299404568402;
+    const size_t n = (size_t)rows * cols;
+    float mx = 0.0f;
+    for (int32_t r = 0; r < rows; r++) {
+        const double d = (double)r * depth_cm / (double)rows;
+        const float g = (float)mc_exp(((double)gain_db + (double)tgc_db_per_cm * d) * (ln10 / 20.0));
+        for (int32_t c = 0; c < cols; c++) {
+            const float v = std::fabs(rf[(size_t)r * cols + c]) * g;
+            rf[(size_t)r * cols + c] = v;
+            mx = v > mx ? v : mx;
+        }
+    }
+    const double scale = 20.0 / (double)dynamic_range_db;
+    for (size_t i = 0; i < n; i++) {
+        const float v = rf[i];
+        float y = 0.0f;
+        if ((double)mx > 0.0 && v > 0.0f) {
+            y = (float)(1.0 + scale * (mc_log((double)v / (double)mx) / ln10));
+            y = y < 0.0f ? 0.0f : (y > 1.0f ? 1.0f : y);
+        }
+        rf[i] = y;
+    }
+}
+
 void orc_log_compress(float* rf, int32_t rows, int32_t cols)
 {
     const double ln10 = 2.30258509299404568402;

@@ -144,6 +144,7 @@ void orc_convolve(float* rf, int32_t rows, int32_t cols, const float* axial, int
 void orc_envelope(float* rf, int32_t rows, int32_t cols);
 /* rfimage.h:127-136, the log compression the reference keeps commented out; in place */
 void orc_log_compress(float* rf, int32_t rows, int32_t cols);
+void orc_bmode(float* rf, int32_t rows, int32_t cols, double depth_cm, float gain_db, float tgc_db_per_cm, float dynamic_range_db);
 /* rfimage.h:183-215: map_x (source row), map_y (source column), each scan_rows x scan_cols */
 void orc_create_mapping(const orc_params* p, float* map_x, float* map_y);
 /* rfimage.h:139: cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) restated (OpenCV 5-bit fixed-point weights) */

@@ -97,6 +97,7 @@ def oracle():
         L.orc_convolve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
         L.orc_envelope.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.orc_log_compress.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.orc_bmode.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_float, C.c_float, C.c_float]
         L.orc_create_mapping.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_scan_convert.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.orc_simulate_frame.restype = C.c_int64
@@ -320,6 +321,13 @@ def envelope(rf):
 def log_compress(rf):
     out = np.ascontiguousarray(rf, np.float32).copy()
     oracle().orc_log_compress(_p(out), out.shape[0], out.shape[1])
+    return out
+
+
+def bmode(rf, depth_cm, gain_db, tgc_db_per_cm, dynamic_range_db):
+    """B-mode display chain on a [rows][cols] envelope image -> [0, 1] (the 8-bit image is np.rint(scan_convert(.) * 255))."""
+    out = np.ascontiguousarray(rf, np.float32).copy()
+    oracle().orc_bmode(_p(out), out.shape[0], out.shape[1], float(depth_cm), float(gain_db), float(tgc_db_per_cm), float(dynamic_range_db))
     return out
 
 

@@ -245,3 +245,58 @@ def test_windowed_accumulate_equals_column_accumulate(api, assets_dirs, kw):
     assert st_w.march_steps == st_c.march_steps and st_w.late_echoes == 0
     assert np.array_equal(win, col) and np.array_equal(again, win)
     assert np.count_nonzero(win) > 0.2 * win.size
+
+
+def _read_png8(path):
+    """Decode an 8-bit grayscale, non-interlaced, filter-0 PNG (what the CLI writes) with zlib; checks CRCs."""
+    import struct
+    import zlib
+    b = open(path, "rb").read()
+    assert b[:8] == b"\x89PNG\r\n\x1a\n"
+    off, idat, shape = 8, b"", None
+    while off < len(b):
+        n, typ = struct.unpack(">I4s", b[off:off + 8])
+        data = b[off + 8:off + 8 + n]
+        assert struct.unpack(">I", b[off + 8 + n:off + 12 + n])[0] == (zlib.crc32(typ + data) & 0xffffffff)
+        if typ == b"IHDR":
+            w, h, depth, ctype, comp, flt, inter = struct.unpack(">IIBBBBB", data)
+            assert (depth, ctype, comp, flt, inter) == (8, 0, 0, 0, 0)
+            shape = (h, w)
+        elif typ == b"IDAT":
+            idat += data
+        off += 12 + n
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(shape[0], shape[1] + 1)
+    assert np.all(raw[:, 0] == 0)
+    return raw[:, 1:]
+
+
+def test_bmode_display_chain_and_cli_png(api, O, assets_dirs, tmp_path):
+    """TGC + log compression to a dynamic range + scan conversion + 8-bit (mcrt_bmode), bit-exact to
+    the oracle restatement (shared numerics); the CLI writes the same image as PNG (and prelog.png like rfimage.h:147)."""
+    import subprocess
+    path = assets_dirs["sphere"] / "sphere.scene"
+    gp = api.default_params(elements=512, samples=2)
+    op = O.default_params(elements=512, samples=2)
+    mx, my = O.create_mapping(op)
+    with api.Simulator(path, gp) as sim:
+        poses = np.repeat(sim.start_pose[None, :], 2, axis=0)
+        env, scan = sim.simulate(poses, seed=0, first_frame=0, scan=True)
+        for gain, tgc, dr in ((0.0, 0.0, 60.0), (6.0, 0.7, 45.0), (-3.0, 2.0, 80.0)):
+            cmp_, img8 = sim.bmode(env, gain_db=gain, tgc_db_per_cm=tgc, dynamic_range_db=dr)
+            for i in range(len(poses)):
+                ref = O.bmode(env[i].T, gp.depth_cm, gain, tgc, dr)                  # oracle layout [rows][cols]
+                assert np.array_equal(cmp_[i].T, ref)
+                ref8 = np.clip(np.rint(O.scan_convert(ref, mx, my) * np.float32(255.0)), 0, 255).astype(np.uint8)
+                assert np.array_equal(img8[i], ref8)
+            assert img8.max() > 200 and 0.02 < (img8 > 0).mean() < 1.0
+        with pytest.raises(api.McrtError):
+            sim.bmode(env, dynamic_range_db=0.0)
+        _, img8 = sim.bmode(env[:1], gain_db=6.0, tgc_db_per_cm=0.7, dynamic_range_db=45.0)
+    from pathlib import Path
+    exe = Path(api.__file__).resolve().parent / "mattausch"
+    out = subprocess.run([str(exe), str(path), "--samples", "2", "--seed", "0", "--out", str(tmp_path), "--png", "--bmode", "45", "--gain", "6",
+                          "--tgc", "0.7"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "rf_image: 465, 512" in out.stdout, out.stdout + out.stderr
+    assert np.array_equal(_read_png8(tmp_path / "bmode_0000.png"), img8[0])
+    pre = _read_png8(tmp_path / "prelog.png")
+    assert np.array_equal(pre, np.clip(np.rint(scan[0] * np.float32(255.0)), 0, 255).astype(np.uint8))
