@@ -109,7 +109,7 @@ typedef struct mcrt_info {
     float start_pose[6];      /* the scene file's transducerPosition / transducerAngles */
     double axial_resolution_mm, time_step_us, row_period_us, max_travel_time_us;
     int32_t voxel_fma_division; /* 1: the 3-instruction voxel index passed its exhaustive check for this resolution and is in use */
-    int32_t reserved0;
+    int32_t bvh_cache_hit;      /* 1: the SAH tree (option bvh_builder=1) was loaded from $MCRT_BVH_CACHE instead of being built */
 } mcrt_info;
 
 typedef struct mcrt_stats {   /* of the most recent mcrt_simulate call */
@@ -187,6 +187,14 @@ int mcrt_postprocess(mcrt_ctx* ctx, const float* rf_in, int32_t cols, int32_t ro
                      const float* lateral, int32_t n_lateral, int32_t flags, float* rf_out);
 /* rf_image::create_mapping + cv::remap (rfimage.h:183-215, 139) on the ctx's geometry */
 int mcrt_scan_convert(mcrt_ctx* ctx, const float* rf_in /* [cols][rows] */, float* scan_out);
+/* Moving / deforming meshes (the reference's `rigid` flag, mesh.h:15, anticipates non-rigid organs but
+ * nothing ever moves, scene.cpp:318-333).  Updates are staged and applied by ONE acceleration-structure rebuild at the next
+ * compute call (the device LBVH build is ~0.3 ms of kernels for 624 640 triangles, cheaper and better than a refit).
+ * origin3: the body origin in world cm (= deltas * scaling, scene.cpp:320-324).  tri_local9: the mesh's triangles in its
+ * local frame (v_obj * scaling), 9 floats each, same count and order as loaded (mcrt_get_scene). */
+int mcrt_set_mesh_origin(mcrt_ctx* ctx, int32_t mesh, const float* origin3);
+int mcrt_set_mesh_vertices(mcrt_ctx* ctx, int32_t mesh, const float* tri_local9, int64_t n_triangles);
+
 /* B-mode display chain on an envelope image (the reference stops at the envelope and keeps its
  * log compression commented out, rfimage.h:127-136, then writes the scan-converted image x255 as 8 bit, rfimage.h:142-148):
  *   v = |E| * 10^((gain_db + tgc_db_per_cm * depth_cm(row)) / 20),   y = clamp(1 + 20 log10(v / max v) / dynamic_range_db, 0, 1),

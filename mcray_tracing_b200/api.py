@@ -48,7 +48,7 @@ class Info(C.Structure):
     _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("scan_rows", C.c_int32), ("scan_cols", C.c_int32), ("n_materials", C.c_int32),
                 ("n_meshes", C.c_int32), ("n_triangles", C.c_int64), ("n_bvh_nodes", C.c_int64), ("device", C.c_int32),
                 ("sm_count", C.c_int32), ("start_pose", C.c_float * 6), ("axial_resolution_mm", C.c_double), ("time_step_us", C.c_double),
-                ("row_period_us", C.c_double), ("max_travel_time_us", C.c_double), ("voxel_fma_division", C.c_int32), ("reserved0", C.c_int32)]
+                ("row_period_us", C.c_double), ("max_travel_time_us", C.c_double), ("voxel_fma_division", C.c_int32), ("bvh_cache_hit", C.c_int32)]
 
 
 class BmodeParams(C.Structure):
@@ -70,7 +70,7 @@ assert SEGMENT_DTYPE.itemsize == 72
 EXPORTS = ["mcrt_default_params", "mcrt_create", "mcrt_create_from_arrays", "mcrt_destroy", "mcrt_last_error", "mcrt_get_info",
            "mcrt_get_stats", "mcrt_set_option", "mcrt_simulate", "mcrt_simulate_async", "mcrt_trace_debug", "mcrt_closest_hit",
            "mcrt_transducer_elements", "mcrt_accumulate", "mcrt_postprocess", "mcrt_scan_convert", "mcrt_get_psf_taps",
-           "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe", "mcrt_load_obj", "mcrt_scene_probe", "mcrt_host_tables", "mcrt_simulate_scanlines", "mcrt_bmode"]
+           "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe", "mcrt_load_obj", "mcrt_scene_probe", "mcrt_host_tables", "mcrt_simulate_scanlines", "mcrt_bmode", "mcrt_set_mesh_origin", "mcrt_set_mesh_vertices"]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
@@ -106,6 +106,8 @@ def lib():
         L.mcrt_trace_debug.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, vp]
         L.mcrt_simulate_scanlines.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, vp]
         L.mcrt_bmode.argtypes = [vp, vp, C.c_int32, vp, vp, vp]
+        L.mcrt_set_mesh_origin.argtypes = [vp, C.c_int32, vp]
+        L.mcrt_set_mesh_vertices.argtypes = [vp, C.c_int32, vp, C.c_int64]
         L.mcrt_closest_hit.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
         L.mcrt_transducer_elements.argtypes = [vp, vp, vp, vp]
         L.mcrt_accumulate.argtypes = [vp, vp, vp, vp]
@@ -255,6 +257,16 @@ class Simulator:
         img8 = np.empty((n, self.info.scan_rows, self.info.scan_cols), np.uint8)
         _check(lib().mcrt_bmode(self.h, _p(e), n, C.byref(bp), _p(cmp_), _p(img8)))
         return cmp_, img8
+
+    def set_mesh_origin(self, mesh: int, origin3):
+        """Move a mesh: new body origin in world cm; applied (one BVH rebuild) at the next compute call."""
+        o = np.ascontiguousarray(origin3, np.float32).reshape(3)
+        _check(lib().mcrt_set_mesh_origin(self.h, int(mesh), _p(o)))
+
+    def set_mesh_vertices(self, mesh: int, tri_local9):
+        """Deform a mesh: its triangles in the local frame, [n][9], same count and order as loaded."""
+        v = np.ascontiguousarray(tri_local9, np.float32).reshape(-1, 9)
+        _check(lib().mcrt_set_mesh_vertices(self.h, int(mesh), _p(v), len(v)))
 
     def get_info(self) -> Info:
         """mcrt_get_info, re-read (options can change what it reports)."""

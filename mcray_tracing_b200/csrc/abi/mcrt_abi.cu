@@ -107,6 +107,9 @@ struct mcrt_ctx {
     float2* d_volume = nullptr;        // owned by the process-wide cache
     float2* d_elem_sincos = nullptr;
     bool voxel_fma_validated = false;
+    int bvh_builder = 0;               // 0 device LBVH, 1 host binned SAH (option "bvh_builder")
+    bool bvh_cache_hit = false;        // the last SAH build came from $MCRT_BVH_CACHE
+    bool scene_dirty = false;          // staged mesh updates wait for a rebuild
     float* d_axial = nullptr;
     float* d_lateral = nullptr;
     float* d_map_x = nullptr;
@@ -150,6 +153,12 @@ struct mcrt_ctx {
     int pending_batches = 0;
     int pending_launches = 0;
 };
+
+extern "C" {   // defined next to the entry points below
+static void update_scene_bounds(mcrt_ctx* c);
+static void ensure_scene_current(mcrt_ctx* c);
+static void rebuild_bvh(mcrt_ctx* c);
+}
 
 namespace {
 
@@ -365,6 +374,7 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
         const int batch_cap = c->max_batch_poses < 1 ? 1 : c->max_batch_poses;
         const int n_batches = (n_poses + batch_cap - 1) / batch_cap;
         if (n_batches > kMaxBatchesPerCall) return fail(MCRT_ERR_INVALID, "mcrt_simulate: too many batches; raise max_batch_poses");
+        ensure_scene_current(c);
         ensure_workspace(c, n_poses < batch_cap ? n_poses : batch_cap);
         const size_t px_per_pose = (size_t)c->aq.elements * c->aq.rows;
         const size_t scan_per_pose = (size_t)c->params.scan_rows * c->params.scan_cols;
@@ -501,20 +511,7 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     for (int a = 0; a < 3; a++) sc.spacing[a] = hs.spacing[a];
     c->aq.accumulate_windowed = accumulate_windowed_supported(sc, c->aq) ? 1 : 0;
     sc.max_abs = c->bvh.max_abs;
-    {
-        float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-        for (size_t t = 0; t < hs.tri_mesh.size(); t++)
-            for (int k = 0; k < 3; k++)
-                for (int a = 0; a < 3; a++) {
-                    const float w = hs.tri_local[9 * t + 3 * k + a] + hs.meshes[hs.tri_mesh[t]].origin[a];
-                    lo[a] = w < lo[a] ? w : lo[a]; hi[a] = w > hi[a] ? w : hi[a];
-                }
-        for (int a = 0; a < 3; a++) {
-            const float ext = hi[a] - lo[a];
-            sc.bounds_lo[a] = hs.tri_mesh.empty() ? 0.0f : lo[a];
-            sc.bounds_inv[a] = (!hs.tri_mesh.empty() && ext > 0.0f) ? 1.0f / ext : 0.0f;
-        }
-    }
+    update_scene_bounds(c.get());
 
     // transducer table, psf taps, scan maps, scatterer volume
     std::vector<float> sincos;
@@ -650,6 +647,172 @@ int mcrt_create_from_arrays(const mcrt_scene_arrays* scene, const mcrt_params* p
 
 void mcrt_destroy(mcrt_ctx* ctx) { destroy_impl(ctx); }
 
+// 64-bit FNV-1a over the data that determines the SAH tree (the cache key)
+static uint64_t fnv1a64(const void* data, size_t n, uint64_t h)
+{
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ULL; }
+    return h;
+}
+
+// SAH tree cache: $MCRT_BVH_CACHE/sah_<hash>.bvh = {magic, n_nodes, n_slots, max_depth, max_abs, nodes, slots}
+static std::string sah_cache_path(const HostScene& hs, const std::vector<float>& origins)
+{
+    const char* dir = getenv("MCRT_BVH_CACHE");
+    if (!dir || !*dir) return std::string();
+    uint64_t h = 1469598103934665603ULL;
+    h = fnv1a64(hs.tri_local.data(), sizeof(float) * hs.tri_local.size(), h);
+    h = fnv1a64(hs.tri_mesh.data(), sizeof(int32_t) * hs.tri_mesh.size(), h);
+    h = fnv1a64(origins.data(), sizeof(float) * origins.size(), h);
+    char name[64];
+    snprintf(name, sizeof(name), "/sah_%016llx.bvh", (unsigned long long)h);
+    return std::string(dir) + name;
+}
+static const uint64_t kSahCacheMagic = 0x3142564853544d43ULL;   // "CMTSHVB1"
+static bool sah_cache_load(const std::string& path, size_t n_tri, HostBvh* hb)
+{
+    FILE* f = path.empty() ? nullptr : fopen(path.c_str(), "rb");
+    if (!f) return false;
+    uint64_t head[4] = {0, 0, 0, 0};
+    bool ok = fread(head, sizeof(head), 1, f) == 1 && head[0] == kSahCacheMagic && head[2] == n_tri && head[1] + 1 == (n_tri ? n_tri : 1);
+    int32_t depth = 0; float max_abs = 0.0f;
+    ok = ok && fread(&depth, sizeof(depth), 1, f) == 1 && fread(&max_abs, sizeof(max_abs), 1, f) == 1;
+    if (ok) {
+        hb->nodes.resize(head[1]); hb->slots.resize(head[2]);
+        ok = (head[1] == 0 || fread(hb->nodes.data(), sizeof(HostBvhNode), head[1], f) == head[1]) &&
+             (head[2] == 0 || fread(hb->slots.data(), sizeof(HostTriSlot), head[2], f) == head[2]);
+        hb->max_depth = depth; hb->max_abs = max_abs;
+    }
+    fclose(f);
+    return ok;
+}
+static void sah_cache_store(const std::string& path, const HostBvh& hb)
+{
+    if (path.empty()) return;
+    const std::string tmp = path + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return;                                   // an unwritable cache directory is not an error
+    const uint64_t head[4] = {kSahCacheMagic, hb.nodes.size(), hb.slots.size(), 0};
+    const int32_t depth = hb.max_depth;
+    bool ok = fwrite(head, sizeof(head), 1, f) == 1 && fwrite(&depth, sizeof(depth), 1, f) == 1 && fwrite(&hb.max_abs, sizeof(float), 1, f) == 1;
+    ok = ok && (hb.nodes.empty() || fwrite(hb.nodes.data(), sizeof(HostBvhNode), hb.nodes.size(), f) == hb.nodes.size());
+    ok = ok && (hb.slots.empty() || fwrite(hb.slots.data(), sizeof(HostTriSlot), hb.slots.size(), f) == hb.slots.size());
+    fclose(f);
+    if (ok) rename(tmp.c_str(), path.c_str()); else remove(tmp.c_str());
+}
+
+// scene bounds for the coherence-sort keys
+static void update_scene_bounds(mcrt_ctx* c)
+{
+    const HostScene& hs = c->scene;
+    SceneDev& sc = c->sc;
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (size_t t = 0; t < hs.tri_mesh.size(); t++)
+        for (int k = 0; k < 3; k++)
+            for (int a = 0; a < 3; a++) {
+                const float w = hs.tri_local[9 * t + 3 * k + a] + hs.meshes[hs.tri_mesh[t]].origin[a];
+                lo[a] = w < lo[a] ? w : lo[a]; hi[a] = w > hi[a] ? w : hi[a];
+            }
+    for (int a = 0; a < 3; a++) {
+        const float ext = hi[a] - lo[a];
+        sc.bounds_lo[a] = hs.tri_mesh.empty() ? 0.0f : lo[a];
+        sc.bounds_inv[a] = (!hs.tri_mesh.empty() && ext > 0.0f) ? 1.0f / ext : 0.0f;
+    }
+}
+
+// (Re)build the acceleration structure from c->scene with the selected builder and swap it in.  Used by the bvh_builder
+// option and after mesh updates (mcrt_set_mesh_origin / mcrt_set_mesh_vertices): the device LBVH build is ~0.3 ms of
+// kernels for 624 640 triangles, so moving or deforming meshes are handled by rebuilding, not by refitting.
+static void rebuild_bvh(mcrt_ctx* c)
+{
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    c->graphs.clear();
+    const HostScene& hs = c->scene;
+    LbvhResult nb{};
+    if (c->bvh_builder == 0) {
+        const cudaError_t be = build_lbvh(hs.tri_local.data(), hs.tri_mesh.data(), (int)hs.tri_mesh.size(), c->d_meshes, c->stream, &nb);
+        if (be != cudaSuccess) throw CudaError(std::string("build_lbvh: ") + cudaGetErrorString(be));
+    } else {
+        std::vector<float> origins(hs.meshes.size() * 3 + 3);
+        for (size_t m = 0; m < hs.meshes.size(); m++)
+            for (int a = 0; a < 3; a++) origins[3 * m + a] = hs.meshes[m].origin[a];
+        HostBvh hb;
+        const std::string cache = sah_cache_path(hs, origins);
+        c->bvh_cache_hit = sah_cache_load(cache, hs.tri_mesh.size(), &hb);
+        if (!c->bvh_cache_hit) {
+            build_sah_bvh(hs.tri_local.data(), hs.tri_mesh.data(), (int)hs.tri_mesh.size(), origins.data(), &hb);
+            sah_cache_store(cache, hb);
+        }
+        const size_t n = hb.slots.size();
+        std::vector<TriSlot> slots(n);
+        for (size_t k = 0; k < n; k++) {
+            const HostTriSlot& t = hb.slots[k];
+            int mbits = t.mesh, tbits = t.tri;
+            float mf, tf;
+            memcpy(&mf, &mbits, 4); memcpy(&tf, &tbits, 4);
+            slots[k].v0 = make_float4(t.v[0], t.v[1], t.v[2], mf);
+            slots[k].v1 = make_float4(t.v[3], t.v[4], t.v[5], tf);
+            slots[k].v2 = make_float4(t.v[6], t.v[7], t.v[8], 0.f);
+        }
+        static_assert(sizeof(HostBvhNode) == sizeof(BvhNode), "node layouts must match");
+        if (n) { dev_alloc(nb.tris, n); CUDA_TRY(cudaMemcpy(nb.tris, slots.data(), sizeof(TriSlot) * n, cudaMemcpyHostToDevice)); }
+        if (!hb.nodes.empty()) {
+            dev_alloc(nb.nodes, hb.nodes.size());
+            CUDA_TRY(cudaMemcpy(nb.nodes, hb.nodes.data(), sizeof(BvhNode) * hb.nodes.size(), cudaMemcpyHostToDevice));
+        }
+        nb.n_tri = (int)n; nb.n_nodes = (int)hb.nodes.size(); nb.max_depth = hb.max_depth; nb.max_abs = hb.max_abs;
+    }
+    if (nb.max_depth > MCRT_TRAVERSAL_STACK) { cudaFree(nb.nodes); cudaFree(nb.tris); throw std::invalid_argument("BVH deeper than the traversal stack"); }
+    dev_free(c->bvh.nodes); dev_free(c->bvh.tris);
+    c->bvh = nb;
+    c->sc.nodes = nb.nodes; c->sc.tris = nb.tris; c->sc.n_tri = nb.n_tri; c->sc.max_abs = nb.max_abs;
+    update_scene_bounds(c);
+    c->scene_dirty = false;
+}
+
+// mesh updates are staged on the host and applied by ONE rebuild at the next compute call
+static void ensure_scene_current(mcrt_ctx* c)
+{
+    if (!c->scene_dirty) return;
+    const HostScene& hs = c->scene;
+    std::vector<DevMesh> meshes(hs.meshes.size());
+    for (size_t m = 0; m < hs.meshes.size(); m++) {
+        DevMesh& d = meshes[m];
+        d.ox = hs.meshes[m].origin[0]; d.oy = hs.meshes[m].origin[1]; d.oz = hs.meshes[m].origin[2];
+        d.mat_in = hs.meshes[m].material_inside; d.mat_out = hs.meshes[m].material_outside; d.vascular = hs.meshes[m].is_vascular ? 1 : 0;
+        d.pad0 = d.pad1 = 0;
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (!meshes.empty()) CUDA_TRY(cudaMemcpy(c->d_meshes, meshes.data(), sizeof(DevMesh) * meshes.size(), cudaMemcpyHostToDevice));
+    rebuild_bvh(c);
+}
+
+int mcrt_set_mesh_origin(mcrt_ctx* c, int32_t mesh, const float* origin3)
+{
+    if (!c || !origin3) return fail(MCRT_ERR_INVALID, "mcrt_set_mesh_origin: null argument");
+    if (mesh < 0 || (size_t)mesh >= c->scene.meshes.size()) return fail(MCRT_ERR_INVALID, "mcrt_set_mesh_origin: no such mesh");
+    for (int a = 0; a < 3; a++) c->scene.meshes[mesh].origin[a] = origin3[a];
+    c->scene_dirty = true;
+    return MCRT_OK;
+}
+
+int mcrt_set_mesh_vertices(mcrt_ctx* c, int32_t mesh, const float* tri_local9, int64_t n_triangles)
+{
+    if (!c || !tri_local9) return fail(MCRT_ERR_INVALID, "mcrt_set_mesh_vertices: null argument");
+    if (mesh < 0 || (size_t)mesh >= c->scene.meshes.size()) return fail(MCRT_ERR_INVALID, "mcrt_set_mesh_vertices: no such mesh");
+    HostScene& hs = c->scene;
+    size_t first = hs.tri_mesh.size(), count = 0;
+    for (size_t t = 0; t < hs.tri_mesh.size(); t++)
+        if (hs.tri_mesh[t] == mesh) { if (count == 0) first = t; count++; }
+    if ((int64_t)count != n_triangles) return fail(MCRT_ERR_INVALID, "mcrt_set_mesh_vertices: the triangle count of a mesh cannot change");
+    if (count) memcpy(hs.tri_local.data() + 9 * first, tri_local9, sizeof(float) * 9 * count);
+    c->scene_dirty = true;
+    return MCRT_OK;
+}
+
 int mcrt_get_info(const mcrt_ctx* c, mcrt_info* info)
 {
     if (!c || !info) return fail(MCRT_ERR_INVALID, "mcrt_get_info: null argument");
@@ -662,6 +825,7 @@ int mcrt_get_info(const mcrt_ctx* c, mcrt_info* info)
     info->axial_resolution_mm = c->dv.axial_resolution_mm; info->time_step_us = c->dv.time_step_us;
     info->row_period_us = c->dv.row_period_us; info->max_travel_time_us = c->dv.max_travel_time_us;
     info->voxel_fma_division = c->aq.voxel_fma_division;
+    info->bvh_cache_hit = c->bvh_cache_hit ? 1 : 0;
     return MCRT_OK;
 }
 
@@ -685,46 +849,11 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
         c->overlap = value != 0;
     }
     else if (n == "bvh_builder") {
-        // 0: device LBVH (default, lbvh.cu); 1: host binned-SAH tree (sah_builder.cpp).  Rebuilds in place.
+        // 0: device LBVH (default, lbvh.cu); 1: host binned-SAH tree (sah_builder.cpp), cached on disk when the environment
+        // variable MCRT_BVH_CACHE names a directory.  Rebuilds in place.
         return guarded("mcrt_set_option", [&]() {
-            CUDA_TRY(cudaSetDevice(c->device));
-            CUDA_TRY(cudaStreamSynchronize(c->stream));
-            for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
-            c->graphs.clear();
-            const HostScene& hs = c->scene;
-            LbvhResult nb{};
-            if (value == 0) {
-                const cudaError_t be = build_lbvh(hs.tri_local.data(), hs.tri_mesh.data(), (int)hs.tri_mesh.size(), c->d_meshes, c->stream, &nb);
-                if (be != cudaSuccess) throw CudaError(std::string("build_lbvh: ") + cudaGetErrorString(be));
-            } else {
-                std::vector<float> origins(hs.meshes.size() * 3 + 3);
-                for (size_t m = 0; m < hs.meshes.size(); m++)
-                    for (int a = 0; a < 3; a++) origins[3 * m + a] = hs.meshes[m].origin[a];
-                HostBvh hb;
-                build_sah_bvh(hs.tri_local.data(), hs.tri_mesh.data(), (int)hs.tri_mesh.size(), origins.data(), &hb);
-                const size_t n = hb.slots.size();
-                std::vector<TriSlot> slots(n);
-                for (size_t k = 0; k < n; k++) {
-                    const HostTriSlot& t = hb.slots[k];
-                    int mbits = t.mesh, tbits = t.tri;
-                    float mf, tf;
-                    memcpy(&mf, &mbits, 4); memcpy(&tf, &tbits, 4);
-                    slots[k].v0 = make_float4(t.v[0], t.v[1], t.v[2], mf);
-                    slots[k].v1 = make_float4(t.v[3], t.v[4], t.v[5], tf);
-                    slots[k].v2 = make_float4(t.v[6], t.v[7], t.v[8], 0.f);
-                }
-                static_assert(sizeof(HostBvhNode) == sizeof(BvhNode), "node layouts must match");
-                if (n) { dev_alloc(nb.tris, n); CUDA_TRY(cudaMemcpy(nb.tris, slots.data(), sizeof(TriSlot) * n, cudaMemcpyHostToDevice)); }
-                if (!hb.nodes.empty()) {
-                    dev_alloc(nb.nodes, hb.nodes.size());
-                    CUDA_TRY(cudaMemcpy(nb.nodes, hb.nodes.data(), sizeof(BvhNode) * hb.nodes.size(), cudaMemcpyHostToDevice));
-                }
-                nb.n_tri = (int)n; nb.n_nodes = (int)hb.nodes.size(); nb.max_depth = hb.max_depth; nb.max_abs = hb.max_abs;
-            }
-            if (nb.max_depth > MCRT_TRAVERSAL_STACK) { cudaFree(nb.nodes); cudaFree(nb.tris); throw std::invalid_argument("BVH deeper than the traversal stack"); }
-            dev_free(c->bvh.nodes); dev_free(c->bvh.tris);
-            c->bvh = nb;
-            c->sc.nodes = nb.nodes; c->sc.tris = nb.tris; c->sc.n_tri = nb.n_tri; c->sc.max_abs = nb.max_abs;
+            c->bvh_builder = value != 0 ? 1 : 0;
+            rebuild_bvh(c);
             return MCRT_OK;
         });
     }
@@ -795,6 +924,7 @@ int mcrt_simulate_scanlines(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, u
     if (c->log_compress) return fail(MCRT_ERR_INVALID, "mcrt_simulate_scanlines: log_compress needs the whole frame (its maximum)");
     return guarded("mcrt_simulate_scanlines", [&]() {
         CUDA_TRY(cudaSetDevice(c->device));
+        ensure_scene_current(c);
         ensure_workspace(c, 1);
         const int E = c->aq.elements, kl = c->params.psf_lateral;
         // the forward-looking lateral taps of the block's last scanlines reach Kl-1 scanlines to the right:
@@ -836,6 +966,7 @@ int mcrt_trace_debug(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, uint64_t
     if (!c || !pose || !segments || !n_segments) return fail(MCRT_ERR_INVALID, "mcrt_trace_debug: null argument");
     return guarded("mcrt_trace_debug", [&]() {
         CUDA_TRY(cudaSetDevice(c->device));
+        ensure_scene_current(c);
         ensure_workspace(c, 1);
         const size_t n_paths = (size_t)c->aq.elements * c->aq.samples;
         const size_t n_seg = n_paths * c->aq.max_depth;
@@ -884,6 +1015,7 @@ int mcrt_closest_hit(mcrt_ctx* c, int64_t n, const float* from3, const float* to
     if (n == 0) return MCRT_OK;
     return guarded("mcrt_closest_hit", [&]() {
         CUDA_TRY(cudaSetDevice(c->device));
+        ensure_scene_current(c);
         float *d_from = nullptr, *d_to = nullptr, *d_frac = nullptr, *d_pt = nullptr, *d_nr = nullptr;
         int32_t *d_tri = nullptr, *d_mesh = nullptr;
         int rc = MCRT_OK;
@@ -922,6 +1054,7 @@ int mcrt_transducer_elements(mcrt_ctx* c, const mcrt_pose* pose, float* pos3, fl
     if (!c || !pose || !pos3 || !dir3) return fail(MCRT_ERR_INVALID, "mcrt_transducer_elements: null argument");
     return guarded("mcrt_transducer_elements", [&]() {
         CUDA_TRY(cudaSetDevice(c->device));
+        ensure_scene_current(c);
         ensure_workspace(c, 1);
         float *d_pos = nullptr, *d_dir = nullptr;
         const size_t n = (size_t)c->aq.elements * 3;
@@ -945,6 +1078,7 @@ int mcrt_accumulate(mcrt_ctx* c, const mcrt_segment* segments, const int32_t* n_
     if (!c || !segments || !n_segments || !rf_out) return fail(MCRT_ERR_INVALID, "mcrt_accumulate: null argument");
     return guarded("mcrt_accumulate", [&]() {
         CUDA_TRY(cudaSetDevice(c->device));
+        ensure_scene_current(c);
         ensure_workspace(c, 1);
         const size_t n_paths = (size_t)c->aq.elements * c->aq.samples;
         const size_t n_seg = n_paths * c->aq.max_depth;
@@ -1017,6 +1151,7 @@ int mcrt_scan_convert(mcrt_ctx* c, const float* rf_in, float* scan_out)
     if (!c || !rf_in || !scan_out) return fail(MCRT_ERR_INVALID, "mcrt_scan_convert: null argument");
     return guarded("mcrt_scan_convert", [&]() {
         CUDA_TRY(cudaSetDevice(c->device));
+        ensure_scene_current(c);
         ensure_workspace(c, 1);
         const size_t n = (size_t)c->aq.elements * c->aq.rows;
         const size_t ns = (size_t)c->params.scan_rows * c->params.scan_cols;

@@ -300,3 +300,43 @@ def test_bmode_display_chain_and_cli_png(api, O, assets_dirs, tmp_path):
     assert np.array_equal(_read_png8(tmp_path / "bmode_0000.png"), img8[0])
     pre = _read_png8(tmp_path / "prelog.png")
     assert np.array_equal(pre, np.clip(np.rint(scan[0] * np.float32(255.0)), 0, 255).astype(np.uint8))
+
+
+def test_moving_and_deforming_meshes_and_sah_cache(api, O, tmp_path, monkeypatch):
+    """staged mesh updates (rigid move, vertex deformation) are applied by one device BVH rebuild and
+    give exactly the frames / segments of a context created from the modified scene (and of the oracle); the host SAH
+    tree is cached on disk under $MCRT_BVH_CACHE and a second build is a cache hit with identical results."""
+    from mcray_tracing_b200 import assets
+    A = assets.stress_scene_arrays(shells=4, nu=48, nv=24)
+    pose = np.concatenate([A["transducer_position"], A["transducer_angles"]])
+    poses = np.repeat(pose[None, :], 3, axis=0)
+    scaling = np.float32(A["scaling"])
+    A2 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in A.items()}
+    A2["mesh_deltas"][1] += np.array([0.6, -0.35, 0.25], np.float32) / scaling
+    b, e = int(A["tri_offsets"][2]), int(A["tri_offsets"][3])
+    v = A2["tri_vertices"][b:e].reshape(-1, 3)
+    v *= (1.0 + 0.04 * np.sin(3.0 * v[:, :1] * scaling)).astype(np.float32)          # bumpy radial deformation of mesh 2
+    kw = dict(elements=64, samples=4)
+    with api.Simulator(A, api.default_params(**kw)) as sim:
+        before = sim.simulate(poses, seed=8, first_frame=0)
+        sim.set_mesh_origin(1, A2["mesh_deltas"][1] * scaling)
+        sim.set_mesh_vertices(2, A2["tri_vertices"][b:e] * scaling)
+        after = sim.simulate(poses, seed=8, first_frame=0)
+        segs, nseg = sim.cast_rays(pose, seed=8, frame=0)
+        with pytest.raises(api.McrtError):
+            sim.set_mesh_vertices(2, A2["tri_vertices"][b:e - 1] * scaling)
+        # SAH tree + disk cache
+        monkeypatch.setenv("MCRT_BVH_CACHE", str(tmp_path))
+        sim.set_option("bvh_builder", 1)
+        assert sim.get_info().bvh_cache_hit == 0 and len(list(tmp_path.glob("sah_*.bvh"))) == 1
+        sah = sim.simulate(poses, seed=8, first_frame=0)
+        sim.set_option("bvh_builder", 1)
+        assert sim.get_info().bvh_cache_hit == 1
+        sah2 = sim.simulate(poses, seed=8, first_frame=0)
+    with api.Simulator(A2, api.default_params(**kw)) as fresh:
+        ref = fresh.simulate(poses, seed=8, first_frame=0)
+    assert not np.array_equal(before, after)
+    assert np.array_equal(after, ref) and np.array_equal(sah, ref) and np.array_equal(sah2, ref)
+    osc = O.OracleScene(A2)
+    os_, on, _ = osc.cast_rays(O.default_params(**kw), pose[:3], pose[3:], seed=8, frame=0, use_bvh=True)
+    _segments_equal(segs, nseg, os_, on)
