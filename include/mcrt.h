@@ -170,6 +170,13 @@ int mcrt_simulate_scanlines(mcrt_ctx* ctx, const mcrt_pose* pose, uint64_t seed,
 int mcrt_trace_debug(mcrt_ctx* ctx, const mcrt_pose* pose, uint64_t seed, uint64_t frame, mcrt_segment* segments,
                      int32_t* n_segments);
 
+/* Ray-tree mode (option "ray_tree" = segment budget per path > 0): BOTH children of every boundary hit
+ * are followed, as in the cited paper, instead of the one Monte-Carlo branch this fork of the reference keeps
+ * (ray.cpp:84-94).  Parity hook: all segments of one pose sorted by (path = element * samples + sample, node), node = 1 for
+ * the root, 2n / 2n+1 for the reflected / refracted child of node n.  capacity = entries the three arrays can hold. */
+int mcrt_trace_tree_debug(mcrt_ctx* ctx, const mcrt_pose* pose, uint64_t seed, uint64_t frame, int64_t capacity,
+                          mcrt_segment* segments, int32_t* path, int32_t* node, int64_t* n_out);
+
 /* ---- stage-level entry points (each one is the CUDA kernel of that stage; used by the parity
  * tests and by callers that want only part of the chain).  Host pointers unless noted. ---- */
 

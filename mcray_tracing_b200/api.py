@@ -70,7 +70,7 @@ assert SEGMENT_DTYPE.itemsize == 72
 EXPORTS = ["mcrt_default_params", "mcrt_create", "mcrt_create_from_arrays", "mcrt_destroy", "mcrt_last_error", "mcrt_get_info",
            "mcrt_get_stats", "mcrt_set_option", "mcrt_simulate", "mcrt_simulate_async", "mcrt_trace_debug", "mcrt_closest_hit",
            "mcrt_transducer_elements", "mcrt_accumulate", "mcrt_postprocess", "mcrt_scan_convert", "mcrt_get_psf_taps",
-           "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe", "mcrt_load_obj", "mcrt_scene_probe", "mcrt_host_tables", "mcrt_simulate_scanlines", "mcrt_bmode", "mcrt_set_mesh_origin", "mcrt_set_mesh_vertices"]
+           "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe", "mcrt_load_obj", "mcrt_scene_probe", "mcrt_host_tables", "mcrt_simulate_scanlines", "mcrt_bmode", "mcrt_set_mesh_origin", "mcrt_set_mesh_vertices", "mcrt_trace_tree_debug"]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
@@ -106,6 +106,7 @@ def lib():
         L.mcrt_trace_debug.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, vp]
         L.mcrt_simulate_scanlines.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, vp]
         L.mcrt_bmode.argtypes = [vp, vp, C.c_int32, vp, vp, vp]
+        L.mcrt_trace_tree_debug.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_int64, vp, vp, vp, vp]
         L.mcrt_set_mesh_origin.argtypes = [vp, C.c_int32, vp]
         L.mcrt_set_mesh_vertices.argtypes = [vp, C.c_int32, vp, C.c_int64]
         L.mcrt_closest_hit.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
@@ -202,6 +203,8 @@ class Simulator:
 
     def set_option(self, name: str, value: int):
         _check(lib().mcrt_set_option(self.h, name.encode(), int(value)))
+        self._options = getattr(self, "_options", {})
+        self._options[name] = int(value)
 
     def stats(self) -> Stats:
         s = Stats()
@@ -257,6 +260,16 @@ class Simulator:
         img8 = np.empty((n, self.info.scan_rows, self.info.scan_cols), np.uint8)
         _check(lib().mcrt_bmode(self.h, _p(e), n, C.byref(bp), _p(cmp_), _p(img8)))
         return cmp_, img8
+
+    def cast_rays_tree(self, pose, seed: int = 0, frame: int = 0, capacity: int | None = None):
+        """Ray-tree mode parity hook (option ray_tree > 0): (segments[n], path[n], node[n]) sorted by (path, node)."""
+        P = make_poses(pose)
+        budget = getattr(self, "_options", {}).get("ray_tree", 0)
+        cap = int(capacity or self.params.elements * self.params.samples * max(budget, 1))
+        segs = np.zeros(cap, SEGMENT_DTYPE); path = np.zeros(cap, np.int32); node = np.zeros(cap, np.int32)
+        n = C.c_int64(0)
+        _check(lib().mcrt_trace_tree_debug(self.h, _p(P), int(seed), int(frame), cap, _p(segs), _p(path), _p(node), C.byref(n)))
+        return segs[: n.value].copy(), path[: n.value].copy(), node[: n.value].copy()
 
     def set_mesh_origin(self, mesh: int, origin3):
         """Move a mesh: new body origin in world cm; applied (one BVH rebuild) at the next compute call."""

@@ -107,6 +107,9 @@ struct mcrt_ctx {
     float2* d_volume = nullptr;        // owned by the process-wide cache
     float2* d_elem_sincos = nullptr;
     bool voxel_fma_validated = false;
+    int tree_budget = 0;               // > 0: ray-tree mode with this many segments per path (option "ray_tree")
+    TreeBuffers tree{};
+    int* h_tree = nullptr;             // pinned: per batch {segments, overflow}
     int bvh_builder = 0;               // 0 device LBVH, 1 host binned SAH (option "bvh_builder")
     bool bvh_cache_hit = false;        // the last SAH build came from $MCRT_BVH_CACHE
     bool scene_dirty = false;          // staged mesh updates wait for a rebuild
@@ -178,6 +181,10 @@ void free_workspace(mcrt_ctx* c)
     dev_free(c->tb.queue_a); dev_free(c->tb.queue_b); dev_free(c->tb.counters);
     dev_free(c->tb.sort_keys); dev_free(c->tb.sort_keys_tmp); dev_free(c->tb.sort_queue_tmp);
     dev_free(c->tb.chunk_prefix_a); dev_free(c->tb.chunk_prefix_b); dev_free(c->tb.n_chunks); dev_free(c->tb.first_hits);
+    dev_free(c->tree.rays_a); dev_free(c->tree.rays_b); dev_free(c->tree.segments); dev_free(c->tree.keys); dev_free(c->tree.keys_sorted);
+    dev_free(c->tree.slots); dev_free(c->tree.slots_sorted); dev_free(c->tree.path_first); dev_free(c->tree.path_count); dev_free(c->tree.counters);
+    if (c->tree.sort_tmp) cudaFree(c->tree.sort_tmp);
+    c->tree = TreeBuffers{};
     if (c->tb.sort_tmp) cudaFree(c->tb.sort_tmp);
     c->tb.sort_tmp = nullptr; c->tb.sort_tmp_bytes = 0;
     dev_free(c->d_poses); dev_free(c->d_rf_acc); dev_free(c->d_rf_tmp0); dev_free(c->d_rf_tmp1); dev_free(c->d_rf_final);
@@ -211,7 +218,19 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
     dev_alloc(c->d_scan, (size_t)n_poses * c->params.scan_rows * c->params.scan_cols);
     dev_alloc(c->d_max_bits, (size_t)n_poses);
     // the windowed accumulate kernel keeps its columns in shared memory: no HBM columns at all
-    c->columns_bytes = c->aq.accumulate_windowed ? 0 : accumulate_columns_bytes(c->aq, n_poses);
+    c->columns_bytes = (c->aq.accumulate_windowed && c->tree_budget == 0) ? 0 : accumulate_columns_bytes(c->aq, n_poses);
+    if (c->tree_budget > 0) {
+        const size_t cap = n_paths * (size_t)c->tree_budget;
+        if (cap > 0x3fffffffULL) throw std::invalid_argument("ray_tree: batch too large for the segment pool; reduce max_batch_poses or the budget");
+        TreeBuffers& t = c->tree;
+        t.seg_capacity = (int)cap; t.ray_capacity = (int)(cap / 2 + n_paths);
+        dev_alloc(t.rays_a, (size_t)t.ray_capacity); dev_alloc(t.rays_b, (size_t)t.ray_capacity);
+        dev_alloc(t.segments, cap); dev_alloc(t.keys, cap); dev_alloc(t.keys_sorted, cap); dev_alloc(t.slots, cap); dev_alloc(t.slots_sorted, cap);
+        dev_alloc(t.path_first, n_paths); dev_alloc(t.path_count, n_paths);
+        dev_alloc(t.counters, (size_t)c->aq.max_depth + 3);
+        t.sort_tmp_bytes = tree_sort_tmp_bytes(t.seg_capacity);
+        CUDA_TRY(cudaMalloc(&t.sort_tmp, t.sort_tmp_bytes ? t.sort_tmp_bytes : 16));
+    }
     if (c->columns_bytes) dev_alloc(c->d_columns, c->columns_bytes / sizeof(float));
     CUDA_TRY(cudaMallocHost(&c->h_poses, sizeof(PoseTrig) * (size_t)n_poses));
     c->tb.trav_counters = c->count_traversal ? c->d_trav : nullptr;
@@ -361,6 +380,31 @@ void run_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches
     if (launches) *launches += c->graph_launches[key];
 }
 
+// ray-tree mode: trace the trees, sort the segments by (path, node), accumulate per path in that order, then the usual
+// PSF / envelope / scan chain.  Not graph-captured (the radix sort picks its passes at run time).
+void run_tree_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches)
+{
+    CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, 2 * sizeof(unsigned long long), s));
+    CUDA_TRY(cudaMemsetAsync(c->tb.counters, 0, sizeof(int) * (size_t)kMaxSub * (c->aq.max_depth + 1), s));
+    FrameDev fr;
+    fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = n; fr.frame_offset = 0;
+    TreeBuffers t = c->tree;
+    t.trav_counters = c->count_traversal ? c->d_trav : nullptr;
+    if (c->profile_stages) CUDA_TRY(cudaEventRecord(c->ev_a, s));
+    launch_trace_tree(c->sc, c->aq, fr, t, c->sm_count, s, launches);
+    if (c->profile_stages) CUDA_TRY(cudaEventRecord(c->ev_b, s));
+    CUDA_TRY(launch_accumulate_tree(c->sc, c->aq, c->d_volume, t, n, c->d_rf_acc, c->d_steps, c->d_columns, s, launches));
+    if (c->profile_stages) CUDA_TRY(cudaEventRecord(c->ev_c, s));
+    launch_post(c->d_rf_acc, n, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
+                c->d_rf_tmp0, c->d_rf_tmp1, c->d_rf_final, s, launches);
+    if (c->log_compress) launch_log_compress(c->d_rf_final, n, (int64_t)c->aq.elements * c->aq.rows, c->d_max_bits, s, launches);
+    if (c->params.rf_layout == 1) launch_transpose(c->d_rf_final, n, c->aq.elements, c->aq.rows, c->d_rf_t, s, launches);
+    if (want_scan)
+        launch_scan_convert(c->d_rf_final, n, c->aq.elements, c->aq.rows, c->d_map_x, c->d_map_y, c->params.scan_rows, c->params.scan_cols,
+                            c->d_scan, s, launches);
+    CUDA_TRY(cudaGetLastError());
+}
+
 int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t seed, uint64_t first_frame, float* rf_out,
                   float* scan_out, cudaStream_t user_stream, bool async)
 {
@@ -393,7 +437,12 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
             CUDA_TRY(cudaMemcpyAsync(c->d_seed_frame, c->h_seed_frame, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
             CUDA_TRY(cudaEventRecord(c->ev_up, s));
             c->upload_pending = true;
-            run_batch(c, n, scan_out != nullptr, s, &launches);
+            if (c->tree_budget > 0) {
+                run_tree_batch(c, n, scan_out != nullptr, s, &launches);
+                CUDA_TRY(cudaMemcpyAsync(c->h_tree + 2 * b, c->tree.counters + c->aq.max_depth + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+            } else {
+                run_batch(c, n, scan_out != nullptr, s, &launches);
+            }
             const float* rf_src = c->params.rf_layout == 1 ? c->d_rf_t : c->d_rf_final;
             CUDA_TRY(cudaMemcpyAsync(rf_out + (size_t)p0 * px_per_pose, rf_src, sizeof(float) * px_per_pose * n,
                                      rf_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
@@ -411,7 +460,11 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
         c->pending_launches = launches;
         c->stats = mcrt_stats{};
         c->stats.poses = n_poses;
-        if (!async) CUDA_TRY(cudaStreamSynchronize(s));
+        if (!async || c->tree_budget > 0) CUDA_TRY(cudaStreamSynchronize(s));
+        if (c->tree_budget > 0)
+            for (int b = 0; b < n_batches; b++)
+                if (c->h_tree[2 * b + 1] || c->h_tree[2 * b] > c->tree.seg_capacity)
+                    return fail(MCRT_ERR_NOMEM, "ray_tree: the segment budget per path was exceeded; raise option ray_tree");
     } catch (const CudaError& e) {
         return fail(MCRT_ERR_CUDA, e.what());
     } catch (const std::exception& e) {
@@ -436,6 +489,7 @@ void finalize_stats(mcrt_ctx* c)
         steps += (int64_t)c->h_steps[2 * b];
         late += (int64_t)c->h_steps[2 * b + 1];
     }
+    if (c->tree_budget > 0) { segs = 0; for (int b = 0; b < c->pending_batches; b++) segs += c->h_tree[2 * b]; }
     c->stats.segments = segs;
     c->stats.march_steps = steps;
     c->stats.late_echoes = late;
@@ -545,6 +599,8 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     CUDA_TRY(cudaMallocHost(&c->h_counters, sizeof(int) * kCounterSlot * kMaxBatchesPerCall));
     CUDA_TRY(cudaMallocHost(&c->h_steps, sizeof(unsigned long long) * 2 * kMaxBatchesPerCall));
     CUDA_TRY(cudaMallocHost(&c->h_trav, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMallocHost(&c->h_tree, sizeof(int) * 2 * kMaxBatchesPerCall));
+    memset(c->h_tree, 0, sizeof(int) * 2 * kMaxBatchesPerCall);
     c->h_trav[0] = c->h_trav[1] = 0;
     memset(c->h_counters, 0, sizeof(int) * kCounterSlot * kMaxBatchesPerCall);
     memset(c->h_steps, 0, sizeof(unsigned long long) * 2 * kMaxBatchesPerCall);
@@ -564,6 +620,7 @@ void destroy_impl(mcrt_ctx* c)
     if (c->h_seed_frame) cudaFreeHost(c->h_seed_frame);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_steps) cudaFreeHost(c->h_steps);
+    if (c->h_tree) cudaFreeHost(c->h_tree);
     if (c->h_trav) cudaFreeHost(c->h_trav);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -862,6 +919,13 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
         c->graphs.clear();
         c->log_compress = value != 0;
     }
+    else if (n == "ray_tree") {
+        // > 0: follow BOTH children of every boundary hit (TreeBuffers); the value is the segment budget per path
+        if (value < 0 || value > 4096) return fail(MCRT_ERR_INVALID, "ray_tree: budget must be in [0, 4096] segments per path");
+        CUDA_TRY_NOTHROW(cudaStreamSynchronize(c->stream));
+        free_workspace(c);
+        c->tree_budget = (int)value;
+    }
     else if (n == "first_hit_dedup") {
         CUDA_TRY_NOTHROW(cudaStreamSynchronize(c->stream));
         free_workspace(c);
@@ -1003,6 +1067,58 @@ int mcrt_trace_debug(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, uint64_t
                 memcpy(&o.distance_traveled, &bits, 8);
                 o.media_id = d.s3.z; o.tri_id = d.s3.w; o.mesh_id = hm[i]; o.hit_fraction = hf[i];
             }
+        return MCRT_OK;
+    });
+}
+
+int mcrt_trace_tree_debug(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, uint64_t frame, int64_t capacity, mcrt_segment* segments,
+                          int32_t* path, int32_t* node, int64_t* n_out)
+{
+    if (!c || !pose || !segments || !path || !node || !n_out) return fail(MCRT_ERR_INVALID, "mcrt_trace_tree_debug: null argument");
+    if (c->tree_budget <= 0) return fail(MCRT_ERR_INVALID, "mcrt_trace_tree_debug: option ray_tree is off");
+    return guarded("mcrt_trace_tree_debug", [&]() {
+        CUDA_TRY(cudaSetDevice(c->device));
+        ensure_scene_current(c);
+        ensure_workspace(c, 1);
+        c->h_poses[0] = pose_trig(*pose);
+        c->h_seed_frame[0] = seed; c->h_seed_frame[1] = frame;
+        cudaStream_t s = c->stream;
+        CUDA_TRY(cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->d_seed_frame, c->h_seed_frame, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+        FrameDev fr;
+        fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = 1; fr.frame_offset = 0;
+        int launches = 0;
+        TreeBuffers t = c->tree;
+        t.trav_counters = nullptr;
+        launch_trace_tree(c->sc, c->aq, fr, t, c->sm_count, s, &launches);
+        CUDA_TRY(cudaGetLastError());
+        int cnt[2] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(cnt, t.counters + c->aq.max_depth + 1, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (cnt[1] || cnt[0] > t.seg_capacity) return fail(MCRT_ERR_NOMEM, "ray_tree: the segment budget per path was exceeded; raise option ray_tree");
+        *n_out = cnt[0];
+        if (cnt[0] > capacity) return fail(MCRT_ERR_INVALID, "mcrt_trace_tree_debug: capacity too small");
+        const size_t n = (size_t)cnt[0];
+        std::vector<DevSegment> hs((size_t)t.seg_capacity);
+        std::vector<unsigned long long> keys(n);
+        std::vector<unsigned> slots(n);
+        CUDA_TRY(cudaMemcpy(hs.data(), t.segments, sizeof(DevSegment) * (size_t)t.seg_capacity, cudaMemcpyDeviceToHost));
+        if (n) {
+            CUDA_TRY(cudaMemcpy(keys.data(), t.keys_sorted, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(slots.data(), t.slots_sorted, sizeof(unsigned) * n, cudaMemcpyDeviceToHost));
+        }
+        memset(segments, 0, sizeof(mcrt_segment) * n);
+        for (size_t i = 0; i < n; i++) {
+            const DevSegment& d = hs[slots[i]];
+            mcrt_segment& o = segments[i];
+            o.from[0] = d.s0.x; o.from[1] = d.s0.y; o.from[2] = d.s0.z; o.reflected_intensity = d.s0.w;
+            o.dir[0] = d.s1.x; o.dir[1] = d.s1.y; o.dir[2] = d.s1.z; o.initial_intensity = d.s1.w;
+            o.to[0] = d.s2.x; o.to[1] = d.s2.y; o.to[2] = d.s2.z; o.attenuation = d.s2.w;
+            const unsigned long long bits = (unsigned long long)(unsigned int)d.s3.x | ((unsigned long long)(unsigned int)d.s3.y << 32);
+            memcpy(&o.distance_traveled, &bits, 8);
+            o.media_id = d.s3.z; o.tri_id = d.s3.w; o.mesh_id = -1; o.hit_fraction = 0.0f;
+            path[i] = (int32_t)(keys[i] >> 20); node[i] = (int32_t)(keys[i] & 0xfffffULL);
+        }
         return MCRT_OK;
     });
 }

@@ -175,8 +175,10 @@ template <bool FMADIV>
 __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate(const SceneDev sc, const AcqDev aq, const float2* __restrict__ volume,
                                                    const DevSegment* __restrict__ segments, const int32_t* __restrict__ nseg,
                                                    const int n_paths, float* __restrict__ columns,
-                                                   unsigned long long* __restrict__ steps_total)
+                                                   unsigned long long* __restrict__ steps_total,
+                                                   const unsigned* __restrict__ seg_index, const int* __restrict__ path_first)
 {
+    // seg_index != nullptr (ray-tree mode): segment k of path p is segments[seg_index[path_first[p] + k]], nseg = count per path
     __shared__ DevMaterial s_mat[MCRT_MAX_SMEM_MATERIALS];
     for (int i = threadIdx.x; i < sc.n_mat && i < MCRT_MAX_SMEM_MATERIALS; i += blockDim.x) s_mat[i] = sc.materials[i];
     __syncthreads();
@@ -206,8 +208,9 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate(const Sce
         const double block_safe_hi = 1.0 - 1e-6 - (double)(MCRT_ACC_UNROLL - 1) * row_delta;
 
         const int ns = nseg[p];
+        const int first = seg_index ? path_first[p] : 0;
         for (int k = 0; k < ns; k++) {
-            const DevSegment* sg = segments + (size_t)p * aq.max_depth + k;
+            const DevSegment* sg = seg_index ? segments + seg_index[first + k] : segments + (size_t)p * aq.max_depth + k;
             const float4 s0 = __ldg(&sg->s0), s1 = __ldg(&sg->s1), s2 = __ldg(&sg->s2);
             const int4 s3 = __ldg(&sg->s3);
             const DevMaterial media = s_mat[s3.z];
@@ -1118,9 +1121,28 @@ cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2
     if (!d_columns) return cudaErrorInvalidValue;
     const int block = 128;
     if (aq.voxel_fma_division)
-        k_accumulate<true><<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_paths, d_columns, d_steps);
+        k_accumulate<true><<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_paths, d_columns, d_steps, nullptr, nullptr);
     else
-        k_accumulate<false><<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_paths, d_columns, d_steps);
+        k_accumulate<false><<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_paths, d_columns, d_steps, nullptr, nullptr);
+    const int64_t n_pixels = (int64_t)n_poses * aq.elements * aq.rows;
+    k_reduce_samples<<<grid1d(n_pixels, 256), 256, 0, stream>>>(d_columns, n_pixels, aq.samples, d_rf);
+    if (launches) (*launches) += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_accumulate_tree(const SceneDev& sc, const AcqDev& aq, const float2* d_volume, const TreeBuffers& tb, int n_poses,
+                                   float* d_rf, unsigned long long* d_steps, float* d_columns, cudaStream_t stream, int* launches)
+{
+    if (!d_columns) return cudaErrorInvalidValue;
+    const int n_paths = n_poses * aq.elements * aq.samples;
+    const int block = 128;
+    // the tree's segments are not monotone in time: the column kernel (read-modify-write of the thread's own column on revisits)
+    if (aq.voxel_fma_division)
+        k_accumulate<true><<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, tb.segments, tb.path_count, n_paths, d_columns, d_steps,
+                                                                               tb.slots_sorted, tb.path_first);
+    else
+        k_accumulate<false><<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, tb.segments, tb.path_count, n_paths, d_columns, d_steps,
+                                                                                tb.slots_sorted, tb.path_first);
     const int64_t n_pixels = (int64_t)n_poses * aq.elements * aq.rows;
     k_reduce_samples<<<grid1d(n_pixels, 256), 256, 0, stream>>>(d_columns, n_pixels, aq.samples, d_rf);
     if (launches) (*launches) += 2;

@@ -60,6 +60,41 @@ struct TraceBuffers {
     float4* first_hits;
 };
 
+// ---- ray-tree mode: BOTH children of every boundary hit are followed, as in the cited paper, instead
+// of the one Monte-Carlo branch this fork of the reference keeps (ray.cpp:84-94).  The wavefront grows: rays live in two
+// ping-pong pools, children and segments are appended with warp-aggregated atomics, every segment carries the key
+// (path << 20 | node) with node = 1 for the root, 2n for the reflected and 2n + 1 for the refracted child of node n.
+struct TreeRay {                   // 48 B
+    float4 origin_intensity;
+    float4 dir_state;              // direction + packed (medium, outside medium, depth)
+    double distance;
+    int path, node;
+};
+struct TreeBuffers {
+    TreeRay* rays_a;               // [ray_capacity]
+    TreeRay* rays_b;
+    DevSegment* segments;          // [seg_capacity], in append order
+    unsigned long long* keys;      // [seg_capacity]
+    unsigned long long* keys_sorted;
+    unsigned* slots;               // [seg_capacity]: 0, 1, 2, ... (sort values)
+    unsigned* slots_sorted;        // segment slots ordered by (path, node)
+    int* path_first;               // [n_paths]: first entry of the path in slots_sorted
+    int* path_count;               // [n_paths]
+    int* counters;                 // [max_depth + 3]: rays entering level l; [max_depth + 1] segments; [max_depth + 2] overflow flag
+    unsigned long long* trav_counters;
+    void* sort_tmp;
+    size_t sort_tmp_bytes;
+    int ray_capacity, seg_capacity;
+};
+size_t tree_sort_tmp_bytes(int seg_capacity);
+// traces the trees of all paths of the uploaded poses, sorts the segments by (path, node) and fills path_first / path_count
+void launch_trace_tree(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, const TreeBuffers& tb, int sm_count, cudaStream_t stream,
+                       int* launches);
+// echo accumulation of tree segments: one thread per path marches its segments in (node) order into a private HBM column,
+// then the samples are summed in order (k_accumulate + k_reduce_samples with an indirection)
+cudaError_t launch_accumulate_tree(const SceneDev& sc, const AcqDev& aq, const float2* d_volume, const TreeBuffers& tb, int n_poses,
+                                   float* d_rf, unsigned long long* d_steps, float* d_columns, cudaStream_t stream, int* launches);
+
 // generate + max_depth x (intersect, shade, compact): scene::cast_rays (scene.cpp:50-183)
 void launch_trace(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, const TraceBuffers& tb, int sm_count, cudaStream_t stream,
                   int* launches);

@@ -46,6 +46,92 @@ __device__ __forceinline__ unsigned pack_state(int media, int outside, int depth
     return (unsigned)(media & 0xff) | ((unsigned)((outside + 2) & 0xff) << 8) | ((unsigned)(depth & 0xff) << 16);
 }
 
+// Everything scene::cast_rays and ray_physics::hit_boundary compute at a boundary hit (scene.cpp:128-150, ray.cpp:11-97) up
+// to, but not including, the choice between the two children: the single-path wavefront keeps one of them
+// (ray.cpp:84-94), the ray-tree mode follows both.
+struct ShadeResult {
+    float3 hit_point, inside_point;
+    float back;                    // echo towards the transducer (Eq. 8) * cos(theta')
+    float intensity_at_hit;        // after ray_physics::travel
+    double distance_after;         // distance_traveled after ray_physics::travel
+    float3 refl_dir, refr_dir;
+    float i_refl, i_refr;          // child intensities before the epsilon cut
+    int mac, mav;                  // medium / outside-medium of the refracted child
+    float x;                       // the reflect / refract uniform
+};
+
+__device__ __forceinline__ void shade_hit(const SceneDev& sc, const AcqDev& aq, const SharedScene& sh, const float3 from, const float3 dir,
+                                          float intensity, const double distance_traveled, const int media, const int outside,
+                                          const DevMaterial& med, const HitRec& h, const float3 from_test, const float3 to, const uint64_t seed,
+                                          const uint32_t frame, const uint32_t element, const uint32_t sample, const uint32_t rng_index,
+                                          ShadeResult& r)
+{
+    const float frequency = aq.frequency;
+    const int4 organ = sh.mesh_info[h.mesh];
+    const float3 hit_point = v_interpolate3(from_test, to, h.fraction);      // m_hitPointWorld
+    const float3 normal = hit_normal(h);
+    const mc_u32x4 b0 = mc_rng_block(seed, frame, element, sample, rng_index, 0);
+    // scene.cpp:132-139: penetration q = |N(0, thickness_inside)| (Box-Muller on block 0 words 0,1)
+    float q = 0.0f;
+    const float thickness = sh.materials[organ.x].thickness;
+    if (!aq.deterministic && thickness != 0.0f) {
+        const double u1 = mc_u01d(b0.v[0]), u2 = mc_u01d(b0.v[1]);
+        double sn, cs;
+        mc_sincos(2 * MC_PI_D * u2, &sn, &cs);
+        const double z = sqrt(-2.0 * mc_log(u1)) * cs;
+        q = (float)fabs(z * (double)thickness);
+    }
+    const float3 inside_point = v_add(v_scl(dir, q), hit_point);
+    // ray_physics::travel (ray.cpp:99-103)
+    const double mm = rp_distance_in_mm(sc.spacing, from, inside_point);
+    r.distance_after = distance_traveled + mm;
+    intensity = intensity * mc_expf(-med.attenuation * ((float)mm * 0.01f) * frequency);
+    // medium state machine, ray.cpp:14-47 as it behaves
+    int mac, mav;
+    if (outside != MCRT_OUTSIDE_NULL) {
+        if (organ.z) { mav = MCRT_OUTSIDE_NULL; mac = (outside == MCRT_OUTSIDE_SELF) ? media : outside; }
+        else { mav = (outside == organ.x) ? organ.y : organ.x; mac = media; }
+    } else {
+        if (organ.z) { mav = MCRT_OUTSIDE_SELF; mac = organ.x; }
+        else { mav = MCRT_OUTSIDE_NULL; mac = organ.x; }
+    }
+    const DevMaterial after = sh.materials[mac];
+    // ray.cpp:49-50: power-cosine jitter of the normal
+    float random_angle = 1.0f;
+    float3 random_normal = normal;
+    if (!aq.deterministic) {
+        random_angle = rp_power_cosine_variate((int)after.shininess, mc_u01d(b0.v[2]));
+        bool ok = false;
+        for (uint32_t attempt = 0; attempt < MC_RNG_BLOCKS_PER_BOUNCE - 1 && !ok; attempt++) {
+            const mc_u32x4 b = mc_rng_block(seed, frame, element, sample, rng_index, 1 + attempt);
+            ok = rp_random_unit_vector_attempt(normal, random_angle, mc_u01d(b.v[0]), mc_u01d(b.v[1]), random_normal);
+        }
+        if (!ok) random_normal = normal;
+    }
+    // ray.cpp:53-82
+    float incidence_angle = v_dot(dir, v_neg(random_normal));
+    if (incidence_angle < 0) incidence_angle = v_dot(dir, random_normal);
+    const float refr_ratio = med.impedance / after.impedance;
+    float refraction_angle = 1 - refr_ratio * refr_ratio * (1 - incidence_angle * incidence_angle);
+    const bool total_internal_reflection = refraction_angle < 0;
+    refraction_angle = sqrtf(refraction_angle);
+    float3 refraction_direction = rp_snells_law(dir, random_normal, incidence_angle, refraction_angle, refr_ratio);
+    refraction_direction = v_normalized(refraction_direction);
+    float3 reflection_direction = v_add(dir, v_scl(random_normal, 2 * incidence_angle));
+    reflection_direction = v_normalized(reflection_direction);
+    const float intensity_refl = total_internal_reflection
+                                     ? intensity
+                                     : rp_reflection_intensity(intensity, med.impedance, incidence_angle, after.impedance, refraction_angle);
+    r.i_refl = intensity_refl;
+    r.i_refr = intensity - intensity_refl;
+    r.back = rp_reflected_intensity_eq8(dir, refraction_direction, reflection_direction, after.specularity) * random_angle;
+    r.x = mc_u01f(b0.v[3]);
+    r.intensity_at_hit = intensity;
+    r.hit_point = hit_point; r.inside_point = inside_point;
+    r.refl_dir = reflection_direction; r.refr_dir = refraction_direction;
+    r.mac = mac; r.mav = mav;
+}
+
 // One bounce of one path.  Returns true if the path survives into the next bounce.
 template <bool FIRST>
 __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, const TraceBuffers& tb,
@@ -99,99 +185,43 @@ __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq
     bool alive = false;
     const size_t seg_idx = (size_t)p * aq.max_depth + bounce;
     if (h.tri_id >= 0) {
-        const double distance_before_hit = distance_traveled;
-        const float intensity_before_hit = intensity;
-        const int4 organ = sh.mesh_info[h.mesh];
-        const float3 hit_point = v_interpolate3(from_test, to, h.fraction);      // m_hitPointWorld
-        const float3 normal = hit_normal(h);
-        const mc_u32x4 b0 = mc_rng_block(seed, frame, (uint32_t)(element + aq.element_offset), (uint32_t)sample, (uint32_t)bounce, 0);
-        // scene.cpp:132-139: penetration q = |N(0, thickness_inside)| (Box-Muller on block 0 words 0,1)
-        float q = 0.0f;
-        const float thickness = sh.materials[organ.x].thickness;
-        if (!aq.deterministic && thickness != 0.0f) {
-            const double u1 = mc_u01d(b0.v[0]), u2 = mc_u01d(b0.v[1]);
-            double sn, cs;
-            mc_sincos(2 * MC_PI_D * u2, &sn, &cs);
-            const double z = sqrt(-2.0 * mc_log(u1)) * cs;
-            q = (float)fabs(z * (double)thickness);
-        }
-        const float3 inside_point = v_add(v_scl(dir, q), hit_point);
-        // ray_physics::travel (ray.cpp:99-103)
-        const double mm = rp_distance_in_mm(sc.spacing, from, inside_point);
-        distance_traveled = distance_traveled + mm;
-        intensity = intensity * mc_expf(-med.attenuation * ((float)mm * 0.01f) * frequency);
-        // medium state machine, ray.cpp:14-47 as it behaves
-        int mac, mav;
-        if (outside != MCRT_OUTSIDE_NULL) {
-            if (organ.z) { mav = MCRT_OUTSIDE_NULL; mac = (outside == MCRT_OUTSIDE_SELF) ? media : outside; }
-            else { mav = (outside == organ.x) ? organ.y : organ.x; mac = media; }
-        } else {
-            if (organ.z) { mav = MCRT_OUTSIDE_SELF; mac = organ.x; }
-            else { mav = MCRT_OUTSIDE_NULL; mac = organ.x; }
-        }
-        const DevMaterial after = sh.materials[mac];
-        // ray.cpp:49-50: power-cosine jitter of the normal
-        float random_angle = 1.0f;
-        float3 random_normal = normal;
-        if (!aq.deterministic) {
-            random_angle = rp_power_cosine_variate((int)after.shininess, mc_u01d(b0.v[2]));
-            bool ok = false;
-            for (uint32_t attempt = 0; attempt < MC_RNG_BLOCKS_PER_BOUNCE - 1 && !ok; attempt++) {
-                const mc_u32x4 b = mc_rng_block(seed, frame, (uint32_t)(element + aq.element_offset), (uint32_t)sample, (uint32_t)bounce, 1 + attempt);
-                ok = rp_random_unit_vector_attempt(normal, random_angle, mc_u01d(b.v[0]), mc_u01d(b.v[1]), random_normal);
-            }
-            if (!ok) random_normal = normal;
-        }
-        // ray.cpp:53-82
-        float incidence_angle = v_dot(dir, v_neg(random_normal));
-        if (incidence_angle < 0) incidence_angle = v_dot(dir, random_normal);
-        const float refr_ratio = med.impedance / after.impedance;
-        float refraction_angle = 1 - refr_ratio * refr_ratio * (1 - incidence_angle * incidence_angle);
-        const bool total_internal_reflection = refraction_angle < 0;
-        refraction_angle = sqrtf(refraction_angle);
-        float3 refraction_direction = rp_snells_law(dir, random_normal, incidence_angle, refraction_angle, refr_ratio);
-        refraction_direction = v_normalized(refraction_direction);
-        float3 reflection_direction = v_add(dir, v_scl(random_normal, 2 * incidence_angle));
-        reflection_direction = v_normalized(reflection_direction);
-        const float intensity_refl = total_internal_reflection
-                                         ? intensity
-                                         : rp_reflection_intensity(intensity, med.impedance, incidence_angle, after.impedance, refraction_angle);
-        const float intensity_refr = intensity - intensity_refl;
-        const float back = rp_reflected_intensity_eq8(dir, refraction_direction, reflection_direction, after.specularity) * random_angle;
+        ShadeResult r;
+        shade_hit(sc, aq, sh, from, dir, intensity, distance_traveled, media, outside, med, h, from_test, to, seed, frame,
+                  (uint32_t)(element + aq.element_offset), (uint32_t)sample, (uint32_t)bounce, r);
         // ray.cpp:84-94: keep exactly one branch
-        const float x = mc_u01f(b0.v[3]);
-        const float reflection_probability = intensity_refl / intensity;
+        const float reflection_probability = r.i_refl / r.intensity_at_hit;
         float3 ndir;
         float nint;
         int nmedia, noutside;
-        if (reflection_probability > x) {
-            ndir = reflection_direction; nmedia = media; noutside = outside;
-            nint = intensity_refl > MCRT_INTENSITY_EPSILON ? intensity_refl : 0.0f;
+        if (reflection_probability > r.x) {
+            ndir = r.refl_dir; nmedia = media; noutside = outside;
+            nint = r.i_refl > MCRT_INTENSITY_EPSILON ? r.i_refl : 0.0f;
         } else {
-            ndir = refraction_direction; nmedia = mac; noutside = mav;
-            nint = intensity_refr > MCRT_INTENSITY_EPSILON ? intensity_refr : 0.0f;
+            ndir = r.refr_dir; nmedia = r.mac; noutside = r.mav;
+            nint = r.i_refr > MCRT_INTENSITY_EPSILON ? r.i_refr : 0.0f;
         }
         // scene.cpp:148
-        seg.s0 = make_float4(from.x, from.y, from.z, back);
-        seg.s1 = make_float4(dir.x, dir.y, dir.z, intensity_before_hit);
-        seg.s2 = make_float4(inside_point.x, inside_point.y, inside_point.z, med.attenuation);
-        seg.s3 = make_int4(__double2loint(distance_before_hit), __double2hiint(distance_before_hit), media, h.tri_id);
+        seg.s0 = make_float4(from.x, from.y, from.z, r.back);
+        seg.s1 = make_float4(dir.x, dir.y, dir.z, intensity);
+        seg.s2 = make_float4(r.inside_point.x, r.inside_point.y, r.inside_point.z, med.attenuation);
+        seg.s3 = make_int4(__double2loint(distance_traveled), __double2hiint(distance_traveled), media, h.tri_id);
         // scene.cpp:151-157
         alive = nint > MCRT_INTENSITY_EPSILON;
         if (alive && bounce + 1 < aq.max_depth) {
             if (tb.sort_keys) {
                 // 27-bit Morton code of the next origin within the scene bounds + 3 bits of direction octant
-                const float qx = fminf(fmaxf((hit_point.x - sc.bounds_lo[0]) * sc.bounds_inv[0], 0.0f), 1.0f);
-                const float qy = fminf(fmaxf((hit_point.y - sc.bounds_lo[1]) * sc.bounds_inv[1], 0.0f), 1.0f);
-                const float qz = fminf(fmaxf((hit_point.z - sc.bounds_lo[2]) * sc.bounds_inv[2], 0.0f), 1.0f);
+                const float3 hp = r.hit_point;
+                const float qx = fminf(fmaxf((hp.x - sc.bounds_lo[0]) * sc.bounds_inv[0], 0.0f), 1.0f);
+                const float qy = fminf(fmaxf((hp.y - sc.bounds_lo[1]) * sc.bounds_inv[1], 0.0f), 1.0f);
+                const float qz = fminf(fmaxf((hp.z - sc.bounds_lo[2]) * sc.bounds_inv[2], 0.0f), 1.0f);
                 auto spread = [](unsigned v) { v &= 0x1ffu; v = (v | (v << 16)) & 0x30000ffu; v = (v | (v << 8)) & 0x300f00fu; v = (v | (v << 4)) & 0x30c30c3u; v = (v | (v << 2)) & 0x9249249u; return v; };
                 const unsigned m = (spread((unsigned)(qx * 511.0f)) << 2) | (spread((unsigned)(qy * 511.0f)) << 1) | spread((unsigned)(qz * 511.0f));
                 const unsigned oct = (ndir.x < 0.0f ? 4u : 0u) | (ndir.y < 0.0f ? 2u : 0u) | (ndir.z < 0.0f ? 1u : 0u);
                 sort_key = (m << 3) | oct;
             }
-            tb.paths.origin_intensity[p] = make_float4(hit_point.x, hit_point.y, hit_point.z, nint);
+            tb.paths.origin_intensity[p] = make_float4(r.hit_point.x, r.hit_point.y, r.hit_point.z, nint);
             tb.paths.dir_state[p] = make_float4(ndir.x, ndir.y, ndir.z, __uint_as_float(pack_state(nmedia, noutside, bounce + 1)));
-            tb.paths.distance[p] = distance_traveled;
+            tb.paths.distance[p] = r.distance_after;
         }
     } else {
         // scene.cpp:163-164
@@ -363,6 +393,149 @@ __global__ void __launch_bounds__(1024) k_scan_chunks(int* __restrict__ counts, 
 #ifndef MCRT_CH_MIN_CTAS
 #define MCRT_CH_MIN_CTAS 1
 #endif
+// ------------------------------------------------------------------------------------------------
+// Ray-tree mode: one launch per tree level.  Each ray emits one segment (appended to the segment pool) and up to two child
+// rays (appended to the next level's pool); both appends are warp-aggregated (one atomicAdd per warp and pool).
+// ------------------------------------------------------------------------------------------------
+template <bool FIRST>
+__global__ void __launch_bounds__(128, 5) k_tree_level(const SceneDev sc, const AcqDev aq, const FrameDev fr, const TreeBuffers tb, const int level)
+{
+    __shared__ SharedScene sh;
+    load_shared_scene(sc, sh);
+    const TreeRay* __restrict__ rin = (level & 1) ? tb.rays_b : tb.rays_a;
+    TreeRay* __restrict__ rout = (level & 1) ? tb.rays_a : tb.rays_b;
+    const int ES = aq.elements * aq.samples;
+    int n_in = FIRST ? fr.n_poses * ES : tb.counters[level];
+    if (n_in > tb.ray_capacity) n_in = tb.ray_capacity;
+    const int n_round = (n_in + 31) & ~31;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint64_t seed = __ldg(&fr.seed_frame[0]);
+    int node_visits = 0, tri_tests = 0;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += gridDim.x * blockDim.x) {
+        const bool valid = idx < n_in;
+        DevSegment seg;
+        unsigned long long key = 0ULL;
+        bool c_refl = false, c_refr = false;
+        TreeRay kid_refl, kid_refr;
+        if (valid) {
+            int path, node, media, outside, depth;
+            float3 from, dir;
+            float intensity;
+            double distance_traveled;
+            if (FIRST) {
+                path = idx; node = 1; depth = 0;
+                const int pose = path / ES, element = (path - pose * ES) / aq.samples;
+                element_pose(aq, fr.poses[pose], __ldg(&fr.elem_sincos[element]), from, dir);
+                intensity = 1.0f / (float)(unsigned)aq.samples;
+                distance_traveled = 0.0;
+                media = sc.starting_material; outside = MCRT_OUTSIDE_NULL;
+            } else {
+                const TreeRay r = rin[idx];
+                path = r.path; node = r.node;
+                from = make_float3(r.origin_intensity.x, r.origin_intensity.y, r.origin_intensity.z); intensity = r.origin_intensity.w;
+                dir = make_float3(r.dir_state.x, r.dir_state.y, r.dir_state.z);
+                const unsigned st = __float_as_uint(r.dir_state.w);
+                media = (int)(st & 0xff); outside = (int)((st >> 8) & 0xff) - 2; depth = (int)((st >> 16) & 0xff);
+                distance_traveled = r.distance;
+            }
+            const int pose = path / ES;
+            const int rem = path - pose * ES;
+            const int element = rem / aq.samples, sample = rem - element * aq.samples;
+            const uint32_t frame = (uint32_t)(__ldg(&fr.seed_frame[1]) + (uint64_t)fr.frame_offset + (uint64_t)pose);
+            const DevMaterial med = sh.materials[media];
+            const float r_length = rp_max_ray_length(med.attenuation, intensity, aq.frequency);
+            const float3 to = v_add(from, v_scl(make_float3(sc.spacing[0] * dir.x, sc.spacing[1] * dir.y, sc.spacing[2] * dir.z), r_length / 100.0f));
+            const float3 from_test = v_add(from, v_scl(dir, 0.1f));
+            HitRec h;
+            closest_hit(sc, sh.mesh_origin, from_test, to, h, node_visits, tri_tests);
+            key = ((unsigned long long)(unsigned)path << 20) | (unsigned long long)(unsigned)node;
+            if (h.tri_id >= 0) {
+                ShadeResult r;
+                // the Philox counter takes the node id where the single-path mode puts the bounce index
+                shade_hit(sc, aq, sh, from, dir, intensity, distance_traveled, media, outside, med, h, from_test, to, seed, frame,
+                          (uint32_t)(element + aq.element_offset), (uint32_t)sample, (uint32_t)node, r);
+                seg.s0 = make_float4(from.x, from.y, from.z, r.back);
+                seg.s1 = make_float4(dir.x, dir.y, dir.z, intensity);
+                seg.s2 = make_float4(r.inside_point.x, r.inside_point.y, r.inside_point.z, med.attenuation);
+                seg.s3 = make_int4(__double2loint(distance_traveled), __double2hiint(distance_traveled), media, h.tri_id);
+                if (depth + 1 < aq.max_depth) {
+                    c_refl = r.i_refl > MCRT_INTENSITY_EPSILON;
+                    c_refr = r.i_refr > MCRT_INTENSITY_EPSILON;
+                    kid_refl.origin_intensity = make_float4(r.hit_point.x, r.hit_point.y, r.hit_point.z, r.i_refl);
+                    kid_refl.dir_state = make_float4(r.refl_dir.x, r.refl_dir.y, r.refl_dir.z, __uint_as_float(pack_state(media, outside, depth + 1)));
+                    kid_refl.distance = r.distance_after; kid_refl.path = path; kid_refl.node = 2 * node;
+                    kid_refr.origin_intensity = make_float4(r.hit_point.x, r.hit_point.y, r.hit_point.z, r.i_refr);
+                    kid_refr.dir_state = make_float4(r.refr_dir.x, r.refr_dir.y, r.refr_dir.z, __uint_as_float(pack_state(r.mac, r.mav, depth + 1)));
+                    kid_refr.distance = r.distance_after; kid_refr.path = path; kid_refr.node = 2 * node + 1;
+                }
+            } else {
+                seg.s0 = make_float4(from.x, from.y, from.z, 0.0f);
+                seg.s1 = make_float4(dir.x, dir.y, dir.z, intensity);
+                seg.s2 = make_float4(to.x, to.y, to.z, med.attenuation);
+                seg.s3 = make_int4(__double2loint(distance_traveled), __double2hiint(distance_traveled), media, -1);
+            }
+        }
+        // segment append
+        const unsigned ms = __ballot_sync(0xffffffffu, valid);
+        const unsigned m1 = __ballot_sync(0xffffffffu, c_refl), m2 = __ballot_sync(0xffffffffu, c_refr);
+        if (ms) {
+            const int leader = __ffs(ms) - 1;
+            int sbase = 0, rbase = 0;
+            if ((int)lane == leader) {
+                sbase = atomicAdd(&tb.counters[aq.max_depth + 1], __popc(ms));
+                if (m1 | m2) rbase = atomicAdd(&tb.counters[level + 1], __popc(m1) + __popc(m2));
+            }
+            sbase = __shfl_sync(0xffffffffu, sbase, leader);
+            rbase = __shfl_sync(0xffffffffu, rbase, leader);
+            bool overflow = false;
+            if (valid) {
+                const int slot = sbase + __popc(ms & lt);
+                if (slot < tb.seg_capacity) { tb.segments[slot] = seg; tb.keys[slot] = key; tb.slots[slot] = (unsigned)slot; }
+                else overflow = true;
+            }
+            if (c_refl) {
+                const int pos = rbase + __popc(m1 & lt);
+                if (pos < tb.ray_capacity) rout[pos] = kid_refl; else overflow = true;
+            }
+            if (c_refr) {
+                const int pos = rbase + __popc(m1) + __popc(m2 & lt);
+                if (pos < tb.ray_capacity) rout[pos] = kid_refr; else overflow = true;
+            }
+            if (overflow) tb.counters[aq.max_depth + 2] = 1;
+        }
+    }
+    if (tb.trav_counters) {
+        for (int off = 16; off > 0; off >>= 1) {
+            node_visits += __shfl_xor_sync(0xffffffffu, node_visits, off);
+            tri_tests += __shfl_xor_sync(0xffffffffu, tri_tests, off);
+        }
+        if (lane == 0) {
+            atomicAdd(&tb.trav_counters[0], (unsigned long long)node_visits);
+            atomicAdd(&tb.trav_counters[1], (unsigned long long)tri_tests);
+        }
+    }
+}
+
+// after the (path, node) sort: first entry and number of entries of every path
+__global__ void __launch_bounds__(256) k_tree_path_ranges(const unsigned long long* __restrict__ keys_sorted, const int* __restrict__ counters,
+                                                         const int seg_counter_index, const int seg_capacity, int* __restrict__ path_first,
+                                                         int* __restrict__ path_count)
+{
+    int n = counters[seg_counter_index];
+    if (n > seg_capacity) n = seg_capacity;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int path = (int)(keys_sorted[i] >> 20);
+        if (i == 0 || (int)(keys_sorted[i - 1] >> 20) != path) path_first[path] = i;
+        if (i == n - 1 || (int)(keys_sorted[i + 1] >> 20) != path) path_count[path] = i + 1;      // end; turned into a count below
+    }
+}
+__global__ void __launch_bounds__(256) k_tree_path_counts(const int n_paths, const int* __restrict__ path_first, int* __restrict__ path_count)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_paths) path_count[p] = path_count[p] - path_first[p];
+}
+
 __global__ void __launch_bounds__(128, MCRT_CH_MIN_CTAS) k_closest_hit(const SceneDev sc, const int64_t n, const float* __restrict__ from3,
                                                     const float* __restrict__ to3, int32_t* __restrict__ tri, int32_t* __restrict__ mesh,
                                                     float* __restrict__ frac, float* __restrict__ point3, float* __restrict__ normal3)
@@ -470,6 +643,40 @@ void launch_trace(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, cons
             if (launches) (*launches) += 3;
         }
     }
+}
+
+size_t tree_sort_tmp_bytes(int seg_capacity)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr,
+                                    seg_capacity, 0, 52, 0);
+    return bytes;
+}
+
+void launch_trace_tree(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, const TreeBuffers& tb, int sm_count, cudaStream_t stream,
+                       int* launches)
+{
+    const int64_t n_paths = (int64_t)fr.n_poses * aq.elements * aq.samples;
+    cudaMemsetAsync(tb.counters, 0, sizeof(int) * (size_t)(aq.max_depth + 3), stream);
+    // unused key slots sort behind every real (path, node) key
+    cudaMemsetAsync(tb.keys, 0xff, sizeof(unsigned long long) * (size_t)tb.seg_capacity, stream);
+    const int block = 128;
+    for (int l = 0; l < aq.max_depth; l++) {
+        // level l holds at most min(2^l * n_paths, ray_capacity) rays
+        int64_t bound = n_paths;
+        for (int k = 0; k < l && bound < tb.ray_capacity; k++) bound *= 2;
+        if (bound > tb.ray_capacity) bound = tb.ray_capacity;
+        const int grid = grid_for(bound, block, sm_count, MCRT_BOUNCE_GRID_CTAS_PER_SM);
+        if (l == 0) k_tree_level<true><<<grid, block, 0, stream>>>(sc, aq, fr, tb, l);
+        else k_tree_level<false><<<grid, block, 0, stream>>>(sc, aq, fr, tb, l);
+        if (launches) (*launches)++;
+    }
+    size_t bytes = tb.sort_tmp_bytes;
+    cub::DeviceRadixSort::SortPairs(tb.sort_tmp, bytes, tb.keys, tb.keys_sorted, tb.slots, tb.slots_sorted, tb.seg_capacity, 0, 52, stream);
+    k_tree_path_ranges<<<grid_for(tb.seg_capacity, 256, sm_count, 8), 256, 0, stream>>>(tb.keys_sorted, tb.counters, aq.max_depth + 1, tb.seg_capacity,
+                                                                                         tb.path_first, tb.path_count);
+    k_tree_path_counts<<<(int)((n_paths + 255) / 256), 256, 0, stream>>>((int)n_paths, tb.path_first, tb.path_count);
+    if (launches) (*launches) += 3;
 }
 
 size_t trace_sort_tmp_bytes(int64_t n_paths)

@@ -778,6 +778,149 @@ int64_t orc_cast_rays(const orc_scene* sp, const orc_params* pp, const float* po
 }
 
 // ------------------------------------------------------------------------------------------------
+// Ray-tree mode (new functionality): the loop of scene::cast_rays with BOTH children of every
+// boundary hit followed (as in the cited paper) instead of the one branch ray.cpp:84-94 keeps.  Node ids: root 1, reflected
+// child 2n, refracted child 2n+1; the Philox counter takes the node id where the single-path loop puts the bounce index.
+// Output: segments of all paths in (path, node) order; returns the number written (or -1 if capacity is too small).
+// ------------------------------------------------------------------------------------------------
+int64_t orc_cast_rays_tree(const orc_scene* sp, const orc_params* pp, const float* pos3, const float* angles_deg3, uint64_t seed,
+                           uint32_t frame, int32_t use_bvh, int64_t capacity, orc_segment* segments, int32_t* seg_path, int32_t* seg_node)
+{
+    const orc_scene& s = *sp; const orc_params& p = *pp;
+    orc_derived dv; orc_derive(&p, &dv);
+    const int E = p.elements, S = p.samples, D = p.max_depth;
+    std::vector<float> epos((size_t)E * 3), edir((size_t)E * 3);
+    transducer_elements(p, dv, pos3, angles_deg3, epos.data(), edir.data());
+    struct node_t { path_t ray; int node; };
+    int64_t n_out = 0;
+    for (int ray_i = 0; ray_i < E; ray_i++) {
+        for (int sample_i = 0; sample_i < S; sample_i++) {
+            path_t first_ray;
+            first_ray.from = mk(epos[3 * ray_i], epos[3 * ray_i + 1], epos[3 * ray_i + 2]);
+            first_ray.direction = mk(edir[3 * ray_i], edir[3 * ray_i + 1], edir[3 * ray_i + 2]);
+            first_ray.depth = 0;
+            first_ray.media = s.starting_material;
+            first_ray.media_outside = OUTSIDE_NULL;
+            first_ray.intensity = 1.0f / (float)(unsigned)S;
+            first_ray.frequency = p.frequency_mhz;
+            first_ray.distance_traveled = 0;
+            first_ray.null = false;
+            // breadth-first: node ids of a level are ascending if the parents are, so the output is sorted by node id
+            std::vector<node_t> level{{first_ray, 1}}, next;
+            while (!level.empty()) {
+                next.clear();
+                for (const node_t& nd : level) {
+                    path_t ray_ = nd.ray;
+                    const material_t& media = s.materials[ray_.media];
+                    if (n_out >= capacity) return -1;
+                    orc_segment* seg_out = &segments[n_out];
+                    seg_path[n_out] = ray_i * S + sample_i; seg_node[n_out] = nd.node;
+                    n_out++;
+                    const float r_length = max_ray_length(media.attenuation, ray_.intensity, ray_.frequency);
+                    const v3 to = add(ray_.from, enlarge(s, ray_.direction, r_length));
+                    const v3 from_test = add(ray_.from, scl(ray_.direction, 0.1f));
+                    const hit_t h = use_bvh ? closest_hit_bvh(s, from_test, to) : closest_hit_brute(s, from_test, to);
+                    auto put = [&](v3 seg_to, float refl, float init_i, double dist_before, int tri, int mesh, float frac) {
+                        seg_out->from[0] = ray_.from.x; seg_out->from[1] = ray_.from.y; seg_out->from[2] = ray_.from.z;
+                        seg_out->to[0] = seg_to.x; seg_out->to[1] = seg_to.y; seg_out->to[2] = seg_to.z;
+                        seg_out->dir[0] = ray_.direction.x; seg_out->dir[1] = ray_.direction.y; seg_out->dir[2] = ray_.direction.z;
+                        seg_out->reflected_intensity = refl; seg_out->initial_intensity = init_i;
+                        seg_out->attenuation = media.attenuation; seg_out->distance_traveled = dist_before;
+                        seg_out->media_id = ray_.media; seg_out->tri_id = tri; seg_out->mesh_id = mesh; seg_out->hit_fraction = frac;
+                    };
+                    if (h.tri < 0) { put(to, 0.0f, ray_.intensity, ray_.distance_traveled, -1, -1, 1.0f); continue; }
+                    const double distance_before_hit = ray_.distance_traveled;
+                    const float intensity_before_hit = ray_.intensity;
+                    const mesh_t& organ = s.meshes[h.mesh];
+                    const v3 hit_point = interpolate3(from_test, to, h.fraction);
+                    const mc_u32x4 b0 = mc_rng_block(seed, frame, (uint32_t)ray_i, (uint32_t)sample_i, (uint32_t)nd.node, 0);
+                    float q = 0.0f;
+                    const float thickness = s.materials[organ.mat_in].thickness;
+                    if (!p.deterministic && thickness != 0.0f) {
+                        const double u1 = mc_u01d(b0.v[0]), u2 = mc_u01d(b0.v[1]);
+                        double sn, cs; mc_sincos(2 * MC_PI_D * u2, &sn, &cs);
+                        const double z = sqrt(-2.0 * mc_log(u1)) * cs;
+                        q = (float)fabs(z * (double)thickness);
+                    }
+                    const v3 inside_point = add(scl(ray_.direction, q), hit_point);
+                    travel(media.attenuation, ray_.frequency, ray_.intensity, ray_.distance_traveled, distance_in_mm(s, ray_.from, inside_point));
+                    int mac, mav; medium_after(ray_, organ, mac, mav);
+                    float random_angle = 1.0f; v3 random_normal = h.normal;
+                    if (!p.deterministic) {
+                        random_angle = power_cosine_variate((int)s.materials[mac].shininess, mc_u01d(b0.v[2]));
+                        bool ok = false;
+                        for (uint32_t attempt = 0; attempt < MC_RNG_BLOCKS_PER_BOUNCE - 1 && !ok; attempt++) {
+                            const mc_u32x4 b = mc_rng_block(seed, frame, (uint32_t)ray_i, (uint32_t)sample_i, (uint32_t)nd.node, 1 + attempt);
+                            ok = random_unit_vector_attempt(h.normal, random_angle, mc_u01d(b.v[0]), mc_u01d(b.v[1]), random_normal);
+                        }
+                        if (!ok) random_normal = h.normal;
+                    }
+                    // both branches of hit_boundary (force_branch 1 = reflection, 0 = refraction)
+                    const boundary_result refl = hit_boundary(s, ray_, hit_point, random_normal, random_angle, organ, mac, mav, 0.0f, 1);
+                    const boundary_result refr = hit_boundary(s, ray_, hit_point, random_normal, random_angle, organ, mac, mav, 0.0f, 0);
+                    put(inside_point, refl.reflected_intensity, intensity_before_hit, distance_before_hit, h.tri, h.mesh, h.fraction);
+                    if (ray_.depth + 1 < D) {
+                        if (refl.returned.intensity > INTENSITY_EPSILON) next.push_back({refl.returned, 2 * nd.node});
+                        if (refr.returned.intensity > INTENSITY_EPSILON) next.push_back({refr.returned, 2 * nd.node + 1});
+                    }
+                }
+                level.swap(next);
+            }
+        }
+    }
+    return n_out;
+}
+
+// main.cpp:106-144 on a flat segment list (ray-tree mode): segments are accumulated in the given order into column
+// seg_path / samples.
+int64_t orc_accumulate_flat(const orc_scene* sp, const orc_params* pp, const orc_volume* vol, const orc_segment* segments,
+                            const int32_t* seg_path, int64_t n_segments, float* rf)
+{
+    const orc_scene& s = *sp; const orc_params& p = *pp;
+    orc_derived dv; orc_derive(&p, &dv);
+    const int S = p.samples;
+    const int rows = dv.rows, cols = dv.cols;
+    const float vol_resolution = p.resolution_um / 1000.0f;
+    const float axres_f = dv.axial_resolution_f;
+    const double time_step = dv.time_step_us;
+    const double max_travel_time = dv.max_travel_time_us;
+    int64_t total_steps = 0;
+    auto add_echo = [&](int column, float echo, double micros) {
+        const double row = micros / dv.row_period_us;
+        if (row < (double)(unsigned)rows) rf[(size_t)(int)row * cols + column] += echo;
+    };
+    for (int64_t i = 0; i < n_segments; i++) {
+        const orc_segment& seg = segments[i];
+        const int column = seg_path[i] / S;
+        const material_t& media = s.materials[seg.media_id];
+        const double starting_micros = ((seg.distance_traveled * 1000) / 1) / (double)p.speed_of_sound;
+        const v3 from = mk(seg.from[0], seg.from[1], seg.from[2]), to = mk(seg.to[0], seg.to[1], seg.to[2]);
+        const double distance = (double)(length(sub(to, from)) * 10.0f);
+        const double steps_d = distance / dv.axial_resolution_mm;
+        uint64_t steps64;
+        if (!(steps_d >= 0.0)) steps64 = 0;
+        else if (steps_d >= 9.0e18) steps64 = (uint64_t)9000000000000000000ULL;
+        else steps64 = (uint64_t)steps_d;
+        const uint32_t steps32 = (uint32_t)steps64;
+        const v3 delta_step = scl(mk(seg.dir[0], seg.dir[1], seg.dir[2]), axres_f);
+        v3 point = from;
+        double time_elapsed = starting_micros;
+        float intensity = seg.initial_intensity;
+        const float decay = mc_expf(-seg.attenuation * axres_f * 0.01f * p.frequency_mhz * 1.0f);
+        for (uint64_t step = 0; step < steps64 && time_elapsed < max_travel_time; step++) {
+            const float scattering = get_scattering(*vol, vol_resolution, media.mu1, media.mu0, media.sigma, point.x, point.y, point.z);
+            add_echo(column, intensity * scattering, time_elapsed);
+            point = add(point, delta_step);
+            time_elapsed = time_elapsed + time_step;
+            intensity *= decay;
+            total_steps++;
+        }
+        add_echo(column, seg.reflected_intensity / (float)(size_t)S, starting_micros + time_step * (double)(uint32_t)(steps32 - 1u));
+    }
+    return total_steps;
+}
+
+// ------------------------------------------------------------------------------------------------
 // main.cpp:106-144 + rf_image::add_echo (rfimage.h:33-40)
 // ------------------------------------------------------------------------------------------------
 int64_t orc_accumulate(const orc_scene* sp, const orc_params* pp, const orc_volume* vol, const orc_segment* segments,

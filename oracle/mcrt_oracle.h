@@ -144,6 +144,10 @@ void orc_convolve(float* rf, int32_t rows, int32_t cols, const float* axial, int
 void orc_envelope(float* rf, int32_t rows, int32_t cols);
 /* rfimage.h:127-136, the log compression the reference keeps commented out; in place */
 void orc_log_compress(float* rf, int32_t rows, int32_t cols);
+int64_t orc_cast_rays_tree(const orc_scene* s, const orc_params* p, const float* pos3, const float* angles_deg3, uint64_t seed, uint32_t frame,
+                           int32_t use_bvh, int64_t capacity, orc_segment* segments, int32_t* seg_path, int32_t* seg_node);
+int64_t orc_accumulate_flat(const orc_scene* s, const orc_params* p, const orc_volume* vol, const orc_segment* segments, const int32_t* seg_path,
+                            int64_t n_segments, float* rf);
 void orc_bmode(float* rf, int32_t rows, int32_t cols, double depth_cm, float gain_db, float tgc_db_per_cm, float dynamic_range_db);
 /* rfimage.h:183-215: map_x (source row), map_y (source column), each scan_rows x scan_cols */
 void orc_create_mapping(const orc_params* p, float* map_x, float* map_y);

@@ -261,6 +261,37 @@ class OracleScene:
         steps = oracle().orc_accumulate(self.h, C.byref(params), oracle().orc_volume_get(), _p(segs), _p(nseg), _p(rf))
         return rf, int(steps)
 
+    def cast_rays_tree(self, params: OrcParams, pos, angles, seed=0, frame=0, use_bvh=True, capacity=None):
+        """Ray-tree mode: (segments[n], path[n], node[n]) in (path, node) order."""
+        cap = int(capacity or params.elements * params.samples * 256)
+        segs = np.zeros(cap, SEGMENT_DTYPE); path = np.zeros(cap, np.int32); node = np.zeros(cap, np.int32)
+        pos = np.ascontiguousarray(pos, np.float32); ang = np.ascontiguousarray(angles, np.float32)
+        L = oracle()
+        L.orc_cast_rays_tree.restype = C.c_int64
+        L.orc_cast_rays_tree.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+        n = L.orc_cast_rays_tree(self.h, C.byref(params), _p(pos), _p(ang), int(seed), int(frame), int(use_bvh), cap, _p(segs), _p(path), _p(node))
+        if n < 0:
+            raise RuntimeError("cast_rays_tree: capacity too small")
+        return segs[:n].copy(), path[:n].copy(), node[:n].copy()
+
+    def accumulate_flat(self, params: OrcParams, segs, path):
+        d = derive(params)
+        rf = np.zeros((d.rows, d.cols), np.float32)
+        L = oracle()
+        L.orc_accumulate_flat.restype = C.c_int64
+        L.orc_accumulate_flat.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        segs = np.ascontiguousarray(segs); path = np.ascontiguousarray(path, np.int32)
+        steps = L.orc_accumulate_flat(self.h, C.byref(params), L.orc_volume_get(), _p(segs), _p(path), len(segs), _p(rf))
+        return rf, int(steps)
+
+    def simulate_frame_tree(self, params: OrcParams, pos, angles, seed=0, frame=0):
+        """Ray-tree frame: tree cast, accumulation in (path, node) order, convolve, envelope -> rf [rows][cols]."""
+        segs, path, node = self.cast_rays_tree(params, pos, angles, seed, frame)
+        rf, steps = self.accumulate_flat(params, segs, path)
+        ax, lat = psf_taps(params)
+        return dict(rf=envelope(convolve(rf, ax, lat)), segments=len(segs), steps=steps)
+
     def simulate_frame(self, params: OrcParams, pos, angles, seed=0, frame=0, scan=False):
         d = derive(params)
         rf = np.zeros((d.rows, d.cols), np.float32)

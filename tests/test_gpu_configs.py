@@ -340,3 +340,42 @@ def test_moving_and_deforming_meshes_and_sah_cache(api, O, tmp_path, monkeypatch
     osc = O.OracleScene(A2)
     os_, on, _ = osc.cast_rays(O.default_params(**kw), pose[:3], pose[3:], seed=8, frame=0, use_bvh=True)
     _segments_equal(segs, nseg, os_, on)
+
+
+@pytest.mark.parametrize("scene_name,det", [("santi-liver-rough.scene", 0), ("santi-liver.scene", 1)])
+def test_ray_tree_mode_matches_oracle(api, O, assets_dirs, scene_name, det):
+    """SURVEY 8(f) item 4 / the north star's ray *tree*: with option ray_tree both children of every boundary hit are
+    followed (level-by-level wavefront, warp-aggregated appends of child rays and segments).  All segments of a frame,
+    sorted by (path, node), are bit-identical to the oracle's tree; the RF frame (per-path accumulation in node order)
+    is within the 1e-4 tolerance; the tree contains the single-path segments' root and is strictly larger."""
+    path = assets_dirs["ircad11"] / scene_name
+    A = O.load_scene_py(path)
+    osc = O.OracleScene(A)
+    kw = dict(elements=48, samples=3, deterministic=det)
+    gp, op = api.default_params(**kw), O.default_params(**kw)
+    with api.Simulator(path, gp) as sim:
+        pose = sim.start_pose
+        single = sim.simulate(pose[None, :], seed=6, first_frame=2)[0]
+        n_single = sim.stats().segments
+        sim.set_option("ray_tree", 256)
+        gs, gpath, gnode = sim.cast_rays_tree(pose, seed=6, frame=2)
+        rf = sim.simulate(np.repeat(pose[None, :], 2, axis=0), seed=6, first_frame=2)
+        st = sim.stats()
+        sim.set_option("ray_tree", 2)                                  # far too small a budget: an error, not silent truncation
+        with pytest.raises(api.McrtError):
+            sim.simulate(pose[None, :], seed=6, first_frame=2)
+        sim.set_option("ray_tree", 0)
+        assert np.array_equal(sim.simulate(pose[None, :], seed=6, first_frame=2)[0], single)
+    os_, opath, onode = osc.cast_rays_tree(op, pose[:3], pose[3:], seed=6, frame=2)
+    assert len(gs) == len(os_) and np.array_equal(gpath, opath) and np.array_equal(gnode, onode)
+    for name in gs.dtype.names:
+        if name in ("mesh_id", "hit_fraction"):
+            continue                                                   # not kept by the tree debug hook
+        a, b = gs[name], os_[name]
+        same = (a == b) | (np.isnan(a) & np.isnan(b)) if a.dtype.kind == "f" else (a == b)
+        assert np.all(same), f"{name}: {np.count_nonzero(~same)} of {same.size} differ"
+    assert len(gs) > n_single and np.count_nonzero(gnode == 1) == 48 * 3 and gnode.max() >= 8
+    ref = osc.simulate_frame_tree(op, pose[:3], pose[3:], seed=6, frame=2)
+    assert np.all(np.abs(rf[0] - ref["rf"].T) <= _tol(ref["rf"].T)), np.abs(rf[0] - ref["rf"].T).max()
+    assert st.segments == len(gs) + len(osc.cast_rays_tree(op, pose[:3], pose[3:], seed=6, frame=3)[0])
+    assert not np.array_equal(rf[0], single)
