@@ -216,11 +216,15 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     st = torch.cuda.Stream(device=dev)
     comm = torch.cuda.Stream(device=dev)
     # two output buffers: the gather of step k (comm stream) overlaps the simulation of step k+1 (stream st)
-    outs = [torch.empty((F, cols, rows), dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
+    # rank 0 simulates straight into its block of the (double-buffered) receive buffer: no self-copy in the gather
+    recvs = [torch.empty((world * F, cols, rows), dtype=torch.float32, device=dev) for _ in range(2)] if (world > 1 and rank == 0) else None
+    if recvs is not None:
+        outs = [r[:F] for r in recvs]
+    else:
+        outs = [torch.empty((F, cols, rows), dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
     out = outs[0]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     frames_per_step_total = F * world
-    recv = torch.empty((world * F, cols, rows), dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
     gather_done = [torch.cuda.Event() for _ in range(2)]
     pending = [False, False]
 
@@ -236,7 +240,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         b = i % len(outs)
         comm.wait_event(after)
         with torch.cuda.stream(comm):
-            sweep.gather_lines(outs[b], sizes, dst=0, out=recv)
+            sweep.gather_lines(outs[b], sizes, dst=0, out=recvs[b] if recvs is not None else None, in_place=recvs is not None)
             gather_done[b].record(comm)
         pending[b] = True
 
@@ -292,6 +296,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         dist.all_reduce(segs_all, op=dist.ReduceOp.SUM)
     total_ms = float(tmax.item())
     value = frames_per_step_total * args.steps / (total_ms * 1e-3)
+    per_rank_ms = [my_ms / args.steps]
+    if world > 1:
+        allms = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(allms, torch.tensor([my_ms / args.steps], dtype=torch.float64, device=dev))
+        per_rank_ms = [float(t.item()) for t in allms]
 
     # ---- e2e: host buffers through mcrt_simulate (pinned), copies inside the timed region ----------
     host_out = torch.empty((F, cols, rows), dtype=torch.float32, pin_memory=True)
@@ -431,6 +440,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "wall_s_timed_region": t_wall,
+            "ms_per_step_per_rank": per_rank_ms,      # the sweep's pose blocks differ in cost; value uses the slowest rank
         }
         line.update(extra)
         print(json.dumps(line), flush=True)

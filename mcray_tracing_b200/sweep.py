@@ -28,32 +28,43 @@ def all_shard_sizes(n_items: int, world_size: int) -> list[int]:
     return [shard_bounds(n_items, world_size, r)[1] - shard_bounds(n_items, world_size, r)[0] for r in range(world_size)]
 
 
-def gather_lines(local: torch.Tensor, sizes: list[int], group=None, dst: int = 0, out: torch.Tensor | None = None) -> torch.Tensor | None:
-    """Gather per-rank blocks [sizes[r], ...] on `dst` into [sum(sizes), ...] with one collective.
-    Ragged blocks are padded to the largest block so a single dist.gather / all_gather suffices.
-    `out` (rank `dst` only): a preallocated [world * max(sizes), ...] receive buffer, so a steady-state loop
-    that runs the gather on its own stream allocates nothing."""
+def gather_lines(local: torch.Tensor, sizes: list[int], group=None, dst: int = 0, out: torch.Tensor | None = None,
+                 in_place: bool = False) -> torch.Tensor | None:
+    """Gather per-rank blocks [sizes[r], ...] on `dst` into [sum(sizes), ...] with ONE collective: a group of point-to-point
+    transfers to `dst` (what ncclGather is: grouped ncclSend / ncclRecv), so nobody but `dst` receives anything.
+    Ragged blocks are padded to the largest block.
+    `out` (rank `dst` only): a preallocated [world * max(sizes), ...] receive buffer, so a steady-state loop that runs the
+    gather on its own stream allocates nothing.  `in_place`: on `dst`, `local` already IS out[dst * max : dst * max +
+    sizes[dst]] (the simulation wrote straight into the receive buffer), so the self-copy is skipped."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     if world == 1:
         return local
     max_n = max(sizes)
     tail = tuple(local.shape[1:])
-    if local.shape[0] != max_n:
-        padded = local.new_zeros((max_n,) + tail)
-        padded[: local.shape[0]] = local
-    else:
-        padded = local.contiguous()
     if rank == dst:
         if out is None:
             out = local.new_empty((world * max_n,) + tail)
         elif tuple(out.shape) != (world * max_n,) + tail or not out.is_contiguous():
             raise ValueError("gather_lines: out must be a contiguous [world * max(sizes), ...] tensor")
-        dist.gather(padded, list(out.view((world, max_n) + tail).unbind(0)), dst=dst, group=group)
+        blocks = out.view((world, max_n) + tail)
+        ops = [dist.P2POp(dist.irecv, blocks[r], r, group) for r in range(world) if r != dst]
+        if not in_place:
+            blocks[dst, : local.shape[0]].copy_(local)
+        elif local.data_ptr() != blocks[dst].data_ptr():
+            raise ValueError("gather_lines: in_place needs local to alias its block of out")
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
         if all(s == max_n for s in sizes):
             return out
         return torch.cat([out[r * max_n: r * max_n + sizes[r]] for r in range(world)], dim=0)
-    dist.gather(padded, None, dst=dst, group=group)
+    if local.shape[0] != max_n:
+        padded = local.new_zeros((max_n,) + tail)
+        padded[: local.shape[0]] = local
+    else:
+        padded = local.contiguous()
+    for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, padded, dst, group)]):
+        w.wait()
     return None
 
 
