@@ -107,6 +107,7 @@ struct mcrt_ctx {
     float2* d_volume = nullptr;        // owned by the process-wide cache
     float2* d_elem_sincos = nullptr;
     bool voxel_fma_validated = false;
+    Bvh4Node* d_nodes4 = nullptr;      // 4-wide copy of bvh.nodes (collapse_bvh4)
     int tree_budget = 0;               // > 0: ray-tree mode with this many segments per path (option "ray_tree")
     TreeBuffers tree{};
     int* h_tree = nullptr;             // pinned: per batch {segments, overflow}
@@ -559,7 +560,11 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     if (c->bvh.max_depth > MCRT_TRAVERSAL_STACK) throw std::invalid_argument("BVH deeper than the traversal stack (degenerate mesh?)");
     SceneDev& sc = c->sc;
     memset(&sc, 0, sizeof(sc));
-    sc.nodes = c->bvh.nodes; sc.tris = c->bvh.tris; sc.meshes = c->d_meshes; sc.materials = c->d_materials;
+    {
+        const cudaError_t ce = collapse_bvh4(c->bvh.nodes, c->bvh.n_nodes, &c->d_nodes4, c->stream);
+        if (ce != cudaSuccess) throw CudaError(std::string("collapse_bvh4: ") + cudaGetErrorString(ce));
+    }
+    sc.nodes = c->bvh.nodes; sc.nodes4 = c->d_nodes4; sc.tris = c->bvh.tris; sc.meshes = c->d_meshes; sc.materials = c->d_materials;
     sc.n_tri = c->bvh.n_tri; sc.n_mesh = (int)hs.meshes.size(); sc.n_mat = (int)hs.materials.size();
     sc.starting_material = hs.starting_material;
     for (int a = 0; a < 3; a++) sc.spacing[a] = hs.spacing[a];
@@ -614,7 +619,7 @@ void destroy_impl(mcrt_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_workspace(c);
-    dev_free(c->d_meshes); dev_free(c->d_materials); dev_free(c->bvh.nodes); dev_free(c->bvh.tris);
+    dev_free(c->d_meshes); dev_free(c->d_materials); dev_free(c->bvh.nodes); dev_free(c->bvh.tris); dev_free(c->d_nodes4);
     dev_free(c->d_elem_sincos); dev_free(c->d_axial); dev_free(c->d_lateral); dev_free(c->d_map_x); dev_free(c->d_map_y);
     dev_free(c->d_seed_frame); dev_free(c->d_steps); dev_free(c->d_trav);
     if (c->h_seed_frame) cudaFreeHost(c->h_seed_frame);
@@ -822,9 +827,15 @@ static void rebuild_bvh(mcrt_ctx* c)
         nb.n_tri = (int)n; nb.n_nodes = (int)hb.nodes.size(); nb.max_depth = hb.max_depth; nb.max_abs = hb.max_abs;
     }
     if (nb.max_depth > MCRT_TRAVERSAL_STACK) { cudaFree(nb.nodes); cudaFree(nb.tris); throw std::invalid_argument("BVH deeper than the traversal stack"); }
-    dev_free(c->bvh.nodes); dev_free(c->bvh.tris);
+    Bvh4Node* n4 = nullptr;
+    {
+        const cudaError_t ce = collapse_bvh4(nb.nodes, nb.n_nodes, &n4, c->stream);
+        if (ce != cudaSuccess) { cudaFree(nb.nodes); cudaFree(nb.tris); throw CudaError(std::string("collapse_bvh4: ") + cudaGetErrorString(ce)); }
+    }
+    dev_free(c->bvh.nodes); dev_free(c->bvh.tris); dev_free(c->d_nodes4);
     c->bvh = nb;
-    c->sc.nodes = nb.nodes; c->sc.tris = nb.tris; c->sc.n_tri = nb.n_tri; c->sc.max_abs = nb.max_abs;
+    c->d_nodes4 = n4;
+    c->sc.nodes = nb.nodes; c->sc.nodes4 = n4; c->sc.tris = nb.tris; c->sc.n_tri = nb.n_tri; c->sc.max_abs = nb.max_abs;
     update_scene_bounds(c);
     c->scene_dirty = false;
 }
@@ -1238,7 +1249,6 @@ int mcrt_postprocess(mcrt_ctx* c, const float* rf_in, int32_t cols, int32_t rows
         CUDA_TRY(cudaSetDevice(c->device));
         const size_t n = (size_t)cols * rows;
         float *d_in = nullptr, *d_t0 = nullptr, *d_t1 = nullptr, *d_out = nullptr, *d_ax = nullptr, *d_lat = nullptr;
-        cudaError_t e = cudaSuccess;
         try {
             dev_alloc(d_in, n); dev_alloc(d_t0, n); dev_alloc(d_t1, n); dev_alloc(d_out, n);
             dev_alloc(d_ax, (size_t)(n_axial > 0 ? n_axial : 1)); dev_alloc(d_lat, (size_t)(n_lateral > 0 ? n_lateral : 1));
@@ -1257,7 +1267,6 @@ int mcrt_postprocess(mcrt_ctx* c, const float* rf_in, int32_t cols, int32_t rows
             throw;
         }
         dev_free(d_in); dev_free(d_t0); dev_free(d_t1); dev_free(d_out); dev_free(d_ax); dev_free(d_lat);
-        (void)e;
         return MCRT_OK;
     });
 }

@@ -205,7 +205,55 @@ __global__ void k_emit_tris(const unsigned int* __restrict__ vals, const float* 
     slots[k] = s;
 }
 
+// BVH2 -> BVH4: node i takes, for each of its two children, the child itself if it is a leaf, else the child's two
+// children.  Built for EVERY inner BVH2 node (the traversal only ever reaches the even-depth ones from the root), so no
+// depth information is needed and the same kernel serves the device LBVH and the host SAH tree.
+__global__ void k_collapse_bvh4(const BvhNode* __restrict__ nodes2, const int n_nodes, Bvh4Node* __restrict__ nodes4)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    float lo[4][3], hi[4][3];
+    int child[4];
+    int n = 0;
+    auto put = [&](float lx, float ly, float lz, float hx, float hy, float hz, int ref) {
+        lo[n][0] = lx; lo[n][1] = ly; lo[n][2] = lz; hi[n][0] = hx; hi[n][1] = hy; hi[n][2] = hz; child[n] = ref; n++;
+    };
+    auto expand = [&](float lx, float ly, float lz, float hx, float hy, float hz, int ref) {
+        if (ref < 0) { put(lx, ly, lz, hx, hy, hz, ref); return; }
+        const BvhNode c = nodes2[ref];
+        put(c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y, c.d.x);
+        put(c.b.z, c.b.w, c.c.x, c.c.y, c.c.z, c.c.w, c.d.y);
+    };
+    const BvhNode nd = nodes2[i];
+    expand(nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y, nd.d.x);
+    expand(nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w, nd.d.y);
+    for (; n < 4;) { lo[n][0] = lo[n][1] = lo[n][2] = 3.0e38f; hi[n][0] = hi[n][1] = hi[n][2] = -3.0e38f; child[n] = MCRT_BVH4_EMPTY; n++; }
+    Bvh4Node o;
+    o.lox = make_float4(lo[0][0], lo[1][0], lo[2][0], lo[3][0]); o.loy = make_float4(lo[0][1], lo[1][1], lo[2][1], lo[3][1]);
+    o.loz = make_float4(lo[0][2], lo[1][2], lo[2][2], lo[3][2]);
+    o.hix = make_float4(hi[0][0], hi[1][0], hi[2][0], hi[3][0]); o.hiy = make_float4(hi[0][1], hi[1][1], hi[2][1], hi[3][1]);
+    o.hiz = make_float4(hi[0][2], hi[1][2], hi[2][2], hi[3][2]);
+    o.child = make_int4(child[0], child[1], child[2], child[3]);
+    o.pad = make_int4(0, 0, 0, 0);
+    nodes4[i] = o;
+}
+
 }  // namespace
+
+cudaError_t collapse_bvh4(const BvhNode* d_nodes2, int n_nodes, Bvh4Node** d_nodes4_out, cudaStream_t stream)
+{
+    *d_nodes4_out = nullptr;
+    if (n_nodes <= 0) return cudaSuccess;
+    Bvh4Node* d4 = nullptr;
+    cudaError_t e = cudaMalloc(&d4, sizeof(Bvh4Node) * (size_t)n_nodes);
+    if (e != cudaSuccess) return e;
+    k_collapse_bvh4<<<(n_nodes + 255) / 256, 256, 0, stream>>>(d_nodes2, n_nodes, d4);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { cudaFree(d4); return e; }
+    *d_nodes4_out = d4;
+    return cudaSuccess;
+}
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = e_; goto done; } } while (0)
 

@@ -31,6 +31,19 @@ struct DevMesh { float ox, oy, oz; int mat_in; int mat_out; int vascular; int pa
 #endif
 struct __align__(16) BvhNode { float4 a, b, c; int4 d; };
 
+// BVH4 node, 128 B = one cache line: every inner BVH2 node collapsed with its inner children (k_collapse_bvh4).  Planes are
+// stored per axis for the 4 children, so a ray picks its near / far planes by ADDRESS (sign of the direction) instead of
+// by selects, and one FFMA per plane does the slab test.  Empty slots hold an inverted box and child = MCRT_BVH4_EMPTY.
+//   lox, loy, loz, hix, hiy, hiz = planes of children 0..3;  child = the 4 child references (same encoding as BVH2)
+#ifndef MCRT_BVH4
+#define MCRT_BVH4 1           // measured against the BVH2 traversal in profiles/r01ab_ab_bvh4.txt
+#endif
+#define MCRT_BVH4_EMPTY 0x7fffffff
+#ifndef MCRT_BVH4_SORT
+#define MCRT_BVH4_SORT 1      // 1: the hit children of a node are visited in entry order; 0: nearest first, the rest in slot order
+#endif
+struct __align__(16) Bvh4Node { float4 lox, loy, loz, hix, hiy, hiz; int4 child; int4 pad; };
+
 // Triangle slot (48 B, Morton order): local-frame vertices v_obj*scaling; v0.w = mesh id bits,
 // v1.w = original (objloader-order) triangle id bits.
 struct __align__(16) TriSlot { float4 v0, v1, v2; };
@@ -45,6 +58,7 @@ struct __align__(16) DevSegment { float4 s0, s1, s2; int4 s3; };
 
 struct SceneDev {
     const BvhNode* nodes;
+    const Bvh4Node* nodes4;  // the same tree, 4-wide (nullptr when the scene has < 2 triangles)
     const TriSlot* tris;
     const DevMesh* meshes;
     const DevMaterial* materials;
@@ -87,6 +101,7 @@ struct PathState {
 #define MCRT_OUTSIDE_SELF (-2)
 #define MCRT_INTENSITY_EPSILON 1e-10f     // ray.h:24
 #define MCRT_STACK_DEPTH 64                // >= depth of the BVH (checked at build time)
+#define MCRT_STACK_DEPTH4 96               // BVH4: up to 3 pushes per level, ceil(depth / 2) levels (checked at build time)
 
 // ------------------------------------------------------------------------------------------------
 // btVector3, scalar path
@@ -339,6 +354,82 @@ __device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __
     if (sc.n_tri <= 0) return;
     if (sc.n_tri == 1) { tri_test(sc.tris, 0, s_mesh, from_w, to_w, best); tri_tests++; return; }
     const RayBox rb = make_raybox(from_w, to_w, sc.max_abs);
+#if MCRT_BVH4 && MCRT_BOX_FMA
+    {
+        // 4-wide traversal: half the dependent node fetches of the BVH2 loop below.  Near / far planes are picked by address.
+        const char* base = reinterpret_cast<const char*>(sc.nodes4);
+        const int onx = rb.px ? 0 : 48, ofx = rb.px ? 48 : 0;            // byte offsets of lox / hix
+        const int ony = rb.py ? 16 : 64, ofy = rb.py ? 64 : 16;
+        const int onz = rb.pz ? 32 : 80, ofz = rb.pz ? 80 : 32;
+        int stack4[MCRT_STACK_DEPTH4];
+        int sp4 = 0;
+        int node4 = 0;
+        while (true) {
+            if (node4 >= 0) {
+                node_visits++;
+                const char* nd = base + (size_t)node4 * sizeof(Bvh4Node);
+                const float4 nx = __ldg(reinterpret_cast<const float4*>(nd + onx)), fx = __ldg(reinterpret_cast<const float4*>(nd + ofx));
+                const float4 ny = __ldg(reinterpret_cast<const float4*>(nd + ony)), fy = __ldg(reinterpret_cast<const float4*>(nd + ofy));
+                const float4 nz = __ldg(reinterpret_cast<const float4*>(nd + onz)), fz = __ldg(reinterpret_cast<const float4*>(nd + ofz));
+                const int4 ch = __ldg(reinterpret_cast<const int4*>(nd + 96));
+                const float tb = best.fraction * 1.000002f;
+                float t[4];
+                int c[4] = {ch.x, ch.y, ch.z, ch.w};
+                {
+                    const float n0[4] = {nx.x, nx.y, nx.z, nx.w}, n1[4] = {ny.x, ny.y, ny.z, ny.w}, n2[4] = {nz.x, nz.y, nz.z, nz.w};
+                    const float f0[4] = {fx.x, fx.y, fx.z, fx.w}, f1[4] = {fy.x, fy.y, fy.z, fy.w}, f2[4] = {fz.x, fz.y, fz.z, fz.w};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float t0x = __fmaf_rn(n0[k], rb.ix, rb.cnx), t1x = __fmaf_rn(f0[k], rb.ix, rb.cfx);
+                        const float t0y = __fmaf_rn(n1[k], rb.iy, rb.cny), t1y = __fmaf_rn(f1[k], rb.iy, rb.cfy);
+                        const float t0z = __fmaf_rn(n2[k], rb.iz, rb.cnz), t1z = __fmaf_rn(f2[k], rb.iz, rb.cfz);
+                        const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+                        const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tb));
+                        // empty slots (inverted box) give tn = +inf / NaN-free miss; a miss sorts last
+                        t[k] = (tn <= __fmaf_rn(tf, 1.000002f, 1e-37f)) ? tn : 3.0e38f;      // an empty slot's inverted box never passes
+                    }
+                }
+#if MCRT_BVH4_SORT
+                // sort the 4 (t, child) pairs by entry parameter (5-comparator network); misses carry t = 3e38
+#define MCRT_CSWAP(i, j) { const bool sw = t[j] < t[i]; const float tt = sw ? t[j] : t[i]; t[j] = sw ? t[i] : t[j]; t[i] = tt; \
+                           const int cc = sw ? c[j] : c[i]; c[j] = sw ? c[i] : c[j]; c[i] = cc; }
+                MCRT_CSWAP(0, 1) MCRT_CSWAP(2, 3) MCRT_CSWAP(0, 2) MCRT_CSWAP(1, 3) MCRT_CSWAP(1, 2)
+#undef MCRT_CSWAP
+                if (t[0] < 3.0e38f) {
+                    // nearest first; the others go on the stack far-to-near so the nearer one is popped first
+                    if (t[3] < 3.0e38f) stack4[sp4++] = c[3];
+                    if (t[2] < 3.0e38f) stack4[sp4++] = c[2];
+                    if (t[1] < 3.0e38f) stack4[sp4++] = c[1];
+                    node4 = c[0];
+                    continue;
+                }
+#else
+                // nearest child first (slot index packed into the low mantissa bits of its entry parameter, t >= 0 so the
+                // bit pattern orders like the value); the other hit children are pushed in slot order
+                const unsigned k0 = (__float_as_uint(t[0]) & ~3u) | 0u, k1 = (__float_as_uint(t[1]) & ~3u) | 1u;
+                const unsigned k2 = (__float_as_uint(t[2]) & ~3u) | 2u, k3 = (__float_as_uint(t[3]) & ~3u) | 3u;
+                const unsigned kmin = min(min(k0, k1), min(k2, k3));
+                if (kmin < (__float_as_uint(3.0e38f) & ~3u)) {
+                    const int near_slot = (int)(kmin & 3u);
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (k != near_slot && t[k] < 3.0e38f) stack4[sp4++] = c[k];
+                    node4 = near_slot == 0 ? c[0] : (near_slot == 1 ? c[1] : (near_slot == 2 ? c[2] : c[3]));
+                    continue;
+                }
+#endif
+            } else {
+                const int code = -node4 - 1;
+                const int first = code >> 2, count = (code & 3) + 1;
+                tri_tests += count;
+                for (int k = 0; k < count; k++) tri_test(sc.tris, first + k, s_mesh, from_w, to_w, best);
+            }
+            if (sp4 == 0) break;
+            node4 = stack4[--sp4];
+        }
+        return;
+    }
+#endif
     int stack[MCRT_STACK_DEPTH];
 #if MCRT_STACK_CULL
     float stack_t[MCRT_STACK_DEPTH];     // entry parameter of the pushed subtree: lets a pop be culled without a fetch

@@ -1,9 +1,11 @@
 // trace.cu -- the Monte-Carlo path loop of scene::cast_rays<S,E> (scene.cpp:50-183) as a wavefront:
 // one launch per bounce; each launch does generate (bounce 0) / intersect (device BVH instead of
-// btCollisionWorld::rayTest) / shade (ray_physics::hit_boundary, ray.cpp:11-97) / compact (warp-
-// aggregated append of the surviving path ids into the next bounce's queue).  This fork of the
-// reference keeps exactly one of {reflection, refraction} per hit (ray.cpp:84-94), so the wavefront
-// never grows: compaction only.
+// btCollisionWorld::rayTest) / shade (ray_physics::hit_boundary, ray.cpp:11-97) / compact.  This fork of the
+// reference keeps exactly one of {reflection, refraction} per hit (ray.cpp:84-94), so the single-path wavefront
+// never grows: compaction only -- warp-aggregated atomic appends, or (large calls) an order-preserving per-chunk
+// compaction + k_scan_chunks; bounce 0 is traced once per element by k_first_hit (all samples share the ray).
+// The ray-tree mode (k_tree_level) follows both children: the wavefront grows level by level, child rays and
+// segments are appended with warp-aggregated atomics and sorted by (path, node) afterwards.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "mcrt_device.cuh"

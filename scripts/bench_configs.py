@@ -86,6 +86,18 @@ def c4():
     stg2 = stages(sim, poses, out)
     r["coherence_sort"] = dict(ms_per_call=ms2, frames_per_s=8 / ms2 * 1e3, segments_per_s=st2.segments / ms2 * 1e3,
                                trace_segments_per_s=st2.segments / stg2["trace"] * 1e3, stage_ms=stg2)
+    # a call large enough to fill the machine (64 frames = 524 288 paths): plain, and with the coherence sort
+    sim.set_option("coherence_sort", 0)
+    poses64 = np.repeat(pose, 64, axis=0)
+    out64 = torch.empty((64, sim.cols, sim.rows), dtype=torch.float32, device="cuda")
+    sim.set_option("max_batch_poses", 64)
+    for name, opt in (("plain", 0), ("coherence_sort", 1)):
+        sim.set_option("coherence_sort", opt)
+        ms3, st3 = timed(sim, poses64, out64, reps=3, warm=1)
+        stg3 = stages(sim, poses64, out64)
+        r["frames_per_call_64_" + name] = dict(ms_per_call=ms3, frames_per_s=64 / ms3 * 1e3, segments=int(st3.segments),
+                                               segments_per_s=st3.segments / ms3 * 1e3, trace_segments_per_s=st3.segments / stg3["trace"] * 1e3,
+                                               stage_ms=stg3)
     sim.close()
     return r
 
