@@ -522,6 +522,7 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) throw CudaError(std::string("device '") + prop.name + "' is not sm_100 (B200); libmcrt only carries sm_100a code");
     c->sm_count = prop.multiProcessorCount;
+    c->tb.tail_threshold = c->sm_count * 6 * 128;      // option "tail_merge"
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -936,6 +937,13 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
         CUDA_TRY_NOTHROW(cudaStreamSynchronize(c->stream));
         free_workspace(c);
         c->tree_budget = (int)value;
+    }
+    else if (n == "tail_merge") {
+        // N (default 1): once no more paths are alive than N resident waves of k_bounce threads, one launch finishes them
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear();
+        if (value < 0 || value > 64) return fail(MCRT_ERR_INVALID, "tail_merge: 0 (off) .. 64 resident waves");
+        c->tb.tail_threshold = (int)value * c->sm_count * 6 * 128;
     }
     else if (n == "first_hit_dedup") {
         CUDA_TRY_NOTHROW(cudaStreamSynchronize(c->stream));

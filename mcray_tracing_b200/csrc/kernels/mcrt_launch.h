@@ -40,7 +40,8 @@ struct TraceBuffers {
     int32_t* hit_mesh;             // [n_paths][max_depth] or nullptr
     int* queue_a;                  // [n_paths]
     int* queue_b;                  // [n_paths]
-    int* counters;                 // [max_depth + 1]: counters[b] = live paths entering bounce b
+    int* counters;                 // [max_depth + 1]: counters[b] = live paths entering bounce b; [max_depth] = bounce at which the tail merge started
+    int tail_threshold;            // > 0: once at most this many paths are alive, one launch finishes them (no more compaction)
     unsigned long long* trav_counters;   // nullptr, or {BVH node visits, triangle tests} accumulated over the call
     // optional coherence sort of the surviving paths between bounces (nullptr = off): Morton key of the next
     // ray's origin + direction octant, radix-sorted so neighbouring lanes traverse neighbouring rays

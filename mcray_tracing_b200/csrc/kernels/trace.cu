@@ -257,7 +257,14 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const Scen
     int* __restrict__ qout = (bounce & 1) ? tb.queue_a : tb.queue_b;
     const int* __restrict__ pin = (bounce & 1) ? tb.chunk_prefix_b : tb.chunk_prefix_a;     // ORDERED only
     int* __restrict__ pout = (bounce & 1) ? tb.chunk_prefix_a : tb.chunk_prefix_b;
+    // Tail merge: the late bounces have few live paths and each launch costs the latency of one full bounce (~40 us) however
+    // few they are.  Once at most tail_threshold paths (one resident wave) are alive, THIS launch walks each of them to its
+    // end in-thread (no compaction between the merged bounces) and the remaining bounce launches return immediately.
+    const int tail_from = FIRST ? 0 : tb.counters[aq.max_depth];
+    if (tail_from && bounce > tail_from) return;
     const int n_in = FIRST ? fr.n_poses * aq.elements * aq.samples : tb.counters[bounce];
+    const bool tail = !FIRST && tb.tail_threshold > 0 && n_in <= tb.tail_threshold && bounce + 1 < aq.max_depth;
+    if (tail && blockIdx.x == 0 && threadIdx.x == 0) tb.counters[aq.max_depth] = bounce;
     const int n_round = ORDERED ? (n_in + 127) & ~127 : (n_in + 31) & ~31;
     const int n_chunks_in = (ORDERED && !FIRST) ? tb.n_chunks[bounce] : 0;
     const unsigned lane = threadIdx.x & 31;
@@ -282,6 +289,16 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const Scen
                 p = qin[idx];
             }
             alive = bounce_path<FIRST>(sc, aq, fr, tb, sh, p, bounce, node_visits, tri_tests, sort_key);
+        }
+        if (tail) {
+            // finish the path here; counters[b] still receives the number of paths entering bounce b (mcrt_stats.segments)
+            for (int b = bounce + 1; b < aq.max_depth; b++) {
+                const unsigned ma = __ballot_sync(0xffffffffu, alive);
+                if (!ma) break;
+                if ((int)lane == __ffs(ma) - 1) atomicAdd(&tb.counters[b], __popc(ma));
+                if (alive) alive = bounce_path<false>(sc, aq, fr, tb, sh, p, b, node_visits, tri_tests, sort_key);
+            }
+            continue;                                               // `tail` is uniform over the launch: no barrier is skipped by part of a CTA
         }
         if (last) continue;
         const unsigned m = __ballot_sync(0xffffffffu, alive);
@@ -360,10 +377,13 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_first_hit(const S
 // (in place), counters[b + 1] = number of survivors, n_chunks[b + 1] = number of chunks.  One CTA; the arrays are small
 // (n_paths / 128 entries).
 __global__ void __launch_bounds__(1024) k_scan_chunks(int* __restrict__ counts, int* __restrict__ counters, int* __restrict__ n_chunks,
-                                                      const int bounce, const int n_paths_first)
+                                                      const int bounce, const int n_paths_first, const int tail_index)
 {
     __shared__ int s_warp[32];
     __shared__ int s_carry;
+    // after the tail merge (k_bounce) the bounces >= tail_from wrote no chunk counts and keep counters[] themselves
+    const int tail_from = counters[tail_index];
+    if (tail_from && bounce >= tail_from) return;
     const int n_in = bounce == 0 ? n_paths_first : counters[bounce];
     const int nch = (n_in + 127) >> 7;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -631,7 +651,7 @@ void launch_trace(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, cons
             if (b == 0) k_bounce<true, true><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
             else k_bounce<false, true><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
             if (b + 1 < aq.max_depth) {
-                k_scan_chunks<<<1, 1024, 0, stream>>>((b & 1) ? tb.chunk_prefix_a : tb.chunk_prefix_b, tb.counters, tb.n_chunks, b, (int)n_paths);
+                k_scan_chunks<<<1, 1024, 0, stream>>>((b & 1) ? tb.chunk_prefix_a : tb.chunk_prefix_b, tb.counters, tb.n_chunks, b, (int)n_paths, aq.max_depth);
                 if (launches) (*launches)++;
             }
         } else if (b == 0) k_bounce<true, false><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
