@@ -260,11 +260,11 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const Scen
     // Tail merge: the late bounces have few live paths and each launch costs the latency of one full bounce (~40 us) however
     // few they are.  Once at most tail_threshold paths (one resident wave) are alive, THIS launch walks each of them to its
     // end in-thread (no compaction between the merged bounces) and the remaining bounce launches return immediately.
-    const int tail_from = FIRST ? 0 : tb.counters[aq.max_depth];
-    if (tail_from && bounce > tail_from) return;
+    const int tail_mark = FIRST ? 0 : tb.counters[aq.max_depth];          // (bounce at which the tail started) + 1, 0 = not yet
+    if (tail_mark && bounce >= tail_mark) return;
     const int n_in = FIRST ? fr.n_poses * aq.elements * aq.samples : tb.counters[bounce];
-    const bool tail = !FIRST && tb.tail_threshold > 0 && n_in <= tb.tail_threshold && bounce + 1 < aq.max_depth;
-    if (tail && blockIdx.x == 0 && threadIdx.x == 0) tb.counters[aq.max_depth] = bounce;
+    const bool tail = tb.tail_threshold > 0 && n_in <= tb.tail_threshold && bounce + 1 < aq.max_depth;
+    if (tail && blockIdx.x == 0 && threadIdx.x == 0) tb.counters[aq.max_depth] = bounce + 1;
     const int n_round = ORDERED ? (n_in + 127) & ~127 : (n_in + 31) & ~31;
     const int n_chunks_in = (ORDERED && !FIRST) ? tb.n_chunks[bounce] : 0;
     const unsigned lane = threadIdx.x & 31;
@@ -382,8 +382,8 @@ __global__ void __launch_bounds__(1024) k_scan_chunks(int* __restrict__ counts, 
     __shared__ int s_warp[32];
     __shared__ int s_carry;
     // after the tail merge (k_bounce) the bounces >= tail_from wrote no chunk counts and keep counters[] themselves
-    const int tail_from = counters[tail_index];
-    if (tail_from && bounce >= tail_from) return;
+    const int tail_mark = counters[tail_index];                           // (bounce at which the tail started) + 1
+    if (tail_mark && bounce + 1 >= tail_mark) return;
     const int n_in = bounce == 0 ? n_paths_first : counters[bounce];
     const int nch = (n_in + 127) >> 7;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
