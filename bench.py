@@ -37,13 +37,14 @@ ELEMENTS, SAMPLES = 256, 16
 SCENE_REL = ("ircad11", "santi-liver.scene")
 
 
-def workload_config(frames_per_step: int, n_gpus: int) -> dict:
+def workload_config(frames_per_step: int, n_gpus: int, gather: str = "p2p") -> dict:
     return {
         "workload": "ircad11 (synthetic organs, 624640 triangles) santi-liver pose, 256 scanlines x 16 MC samples/element, "
-                    "465 RF rows, stochastic mode" + ("" if n_gpus == 1 else "; freehand probe sweep, contiguous pose blocks per rank, one NCCL gather of RF lines per step (on its own stream: the gather of step k overlaps the simulation of step k+1, every gather inside a timed interval)"),
+                    "465 RF rows, stochastic mode" + ("" if n_gpus == 1 else "; freehand probe sweep, contiguous pose blocks per rank, RF lines of every rank brought to rank 0 once per step (on its own stream: the transfer of step k overlaps the simulation of step k+1, every transfer inside a timed interval)"),
         "elements": ELEMENTS, "samples_per_element": SAMPLES, "max_depth": 10, "rf_rows": 465,
         "frames_per_step_per_gpu": frames_per_step,
         "parallelism": f"pose-sharded x{n_gpus}" if n_gpus > 1 else "single GPU",
+        "gather": gather if n_gpus > 1 else None,
         "l2": "L2 flushed (256 MiB memset) between timed steps, outside the per-step CUDA-event intervals",
     }
 
@@ -170,7 +171,7 @@ def run_reference(args, rank: int, world: int):
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args.frames_per_step, world),
+        "data": "synthetic", "config": workload_config(args.frames_per_step, world, args.gather),
         "ray_segments_per_s": segs / dt,
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": best_threads, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -216,9 +217,29 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     st = torch.cuda.Stream(device=dev)
     comm = torch.cuda.Stream(device=dev)
     # two output buffers: the gather of step k (comm stream) overlaps the simulation of step k+1 (stream st)
-    # rank 0 simulates straight into its block of the (double-buffered) receive buffer: no self-copy in the gather
-    recvs = [torch.empty((world * F, cols, rows), dtype=torch.float32, device=dev) for _ in range(2)] if (world > 1 and rank == 0) else None
-    if recvs is not None:
+    # N > 1: every rank DEPOSITS its finished RF lines straight into rank 0's double-buffered receive buffer over NVLink
+    # (sweep.PeerDeposit: CUDA-IPC peer copies + a 4-byte NCCL all-reduce as the completion signal); --gather nccl selects the
+    # grouped ncclSend/ncclRecv gather instead (sweep.gather_lines).  Rank 0 simulates in place in both cases.
+    peer = None
+    recvs = None
+    if world > 1 and args.gather == "p2p":
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            peer = sweep.PeerDeposit(F, (cols, rows), dev, n_slots=2, dst=0)
+        except Exception as e:                                  # e.g. no peer access: fall back on every rank
+            print(f"bench.py: rank {rank}: peer deposit unavailable ({e}); falling back to the NCCL gather", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            peer = None
+    if peer is not None:
+        if rank == 0:
+            recvs = [peer.slot_tensor(b) for b in range(2)]
+            outs = [r[:F] for r in recvs]
+        else:
+            outs = [torch.empty((F, cols, rows), dtype=torch.float32, device=dev) for _ in range(2)]
+    elif world > 1 and rank == 0:
+        recvs = [torch.empty((world * F, cols, rows), dtype=torch.float32, device=dev) for _ in range(2)]
         outs = [r[:F] for r in recvs]
     else:
         outs = [torch.empty((F, cols, rows), dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
@@ -236,12 +257,17 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         sim.simulate_device(poses, outs[b].data_ptr(), seed=seed, first_frame=k * frames_per_step_total + my_first, stream=st.cuda_stream, sync=False)
 
     def gather(i: int, after: "torch.cuda.Event"):
-        """ONE NCCL gather of the finished RF lines of outs[i % 2] to rank 0, on the comm stream, not before `after`"""
+        """bring the finished RF lines of outs[i % 2] to rank 0 on the comm stream, not before `after`"""
         b = i % len(outs)
         comm.wait_event(after)
-        with torch.cuda.stream(comm):
-            sweep.gather_lines(outs[b], sizes, dst=0, out=recvs[b] if recvs is not None else None, in_place=recvs is not None)
+        if peer is not None:
+            peer.deposit(b, outs[b], comm)
+            peer.commit(comm)
             gather_done[b].record(comm)
+        else:
+            with torch.cuda.stream(comm):
+                sweep.gather_lines(outs[b], sizes, dst=0, out=recvs[b] if recvs is not None else None, in_place=recvs is not None)
+                gather_done[b].record(comm)
         pending[b] = True
 
     def sync_all():
@@ -429,7 +455,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(F, world),
+            "data": "synthetic", "config": workload_config(F, world, ("p2p deposit over NVLink (CUDA IPC) + 4-byte NCCL all-reduce" if peer is not None else "NCCL grouped send/recv") if world > 1 else "p2p"),
             "ray_segments_per_s": float(segs_all.item()) * args.steps / (total_ms * 1e-3),
             "segments_per_step": float(segs_all.item()), "march_steps_per_step_per_gpu": march_per_step,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(F * 24 + 16), "d2h_bytes_per_step": int(F * cols * rows * 4),
@@ -444,6 +470,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         }
         line.update(extra)
         print(json.dumps(line), flush=True)
+    if peer is not None:
+        peer.close()
     sim.close()
     if world > 1:
         dist.destroy_process_group()
@@ -458,6 +486,7 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=256)
     ap.add_argument("--cpu-frames", type=int, default=60, help="frames per CPU-baseline variant (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N > 1: peer-memory deposit over NVLink (default) or NCCL send/recv gather")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -170,6 +170,19 @@ int mcrt_simulate_scanlines(mcrt_ctx* ctx, const mcrt_pose* pose, uint64_t seed,
 int mcrt_trace_debug(mcrt_ctx* ctx, const mcrt_pose* pose, uint64_t seed, uint64_t frame, mcrt_segment* segments,
                      int32_t* n_segments);
 
+/* ---- peer-memory plumbing for the multi-GPU gather (one process per GPU): the rank that collects the RF lines allocates the
+ * receive buffer with mcrt_device_alloc, exports it (CUDA IPC, 64-byte handle to ship through any host channel); every other
+ * rank opens it and DEPOSITS its finished lines straight into that memory over NVLink -- either by passing the peer pointer
+ * as rf_out_dev to mcrt_simulate_async, or with mcrt_copy_async from a local buffer on a copy stream (overlapping the next
+ * step's simulation).  No SM is spent on the transfer and nobody but the collector receives anything. */
+int mcrt_device_alloc(int device, size_t bytes, void** dev_ptr);
+int mcrt_device_free(int device, void* dev_ptr);
+int mcrt_ipc_export(int device, const void* dev_ptr, unsigned char handle64[64]);
+int mcrt_ipc_open(int device, const unsigned char handle64[64], void** peer_ptr);
+int mcrt_ipc_close(int device, void* peer_ptr);
+/* dst / src: device pointers (local or peer-mapped); cuda_stream: a cudaStream_t passed as void* (NULL = default stream) */
+int mcrt_copy_async(int device, void* dst, const void* src, size_t bytes, void* cuda_stream);
+
 /* Ray-tree mode (option "ray_tree" = segment budget per path > 0): BOTH children of every boundary hit
  * are followed, as in the cited paper, instead of the one Monte-Carlo branch this fork of the reference keeps
  * (ray.cpp:84-94).  Parity hook: all segments of one pose sorted by (path = element * samples + sample, node), node = 1 for

@@ -70,7 +70,8 @@ assert SEGMENT_DTYPE.itemsize == 72
 EXPORTS = ["mcrt_default_params", "mcrt_create", "mcrt_create_from_arrays", "mcrt_destroy", "mcrt_last_error", "mcrt_get_info",
            "mcrt_get_stats", "mcrt_set_option", "mcrt_simulate", "mcrt_simulate_async", "mcrt_trace_debug", "mcrt_closest_hit",
            "mcrt_transducer_elements", "mcrt_accumulate", "mcrt_postprocess", "mcrt_scan_convert", "mcrt_get_psf_taps",
-           "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe", "mcrt_load_obj", "mcrt_scene_probe", "mcrt_host_tables", "mcrt_simulate_scanlines", "mcrt_bmode", "mcrt_set_mesh_origin", "mcrt_set_mesh_vertices", "mcrt_trace_tree_debug"]
+           "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe", "mcrt_load_obj", "mcrt_scene_probe", "mcrt_host_tables", "mcrt_simulate_scanlines", "mcrt_bmode", "mcrt_set_mesh_origin", "mcrt_set_mesh_vertices", "mcrt_trace_tree_debug", "mcrt_device_alloc",
+           "mcrt_device_free", "mcrt_ipc_export", "mcrt_ipc_open", "mcrt_ipc_close", "mcrt_copy_async"]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
@@ -107,6 +108,12 @@ def lib():
         L.mcrt_simulate_scanlines.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, vp]
         L.mcrt_bmode.argtypes = [vp, vp, C.c_int32, vp, vp, vp]
         L.mcrt_trace_tree_debug.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_int64, vp, vp, vp, vp]
+        L.mcrt_device_alloc.argtypes = [C.c_int, C.c_size_t, vp]
+        L.mcrt_device_free.argtypes = [C.c_int, vp]
+        L.mcrt_ipc_export.argtypes = [C.c_int, vp, vp]
+        L.mcrt_ipc_open.argtypes = [C.c_int, vp, vp]
+        L.mcrt_ipc_close.argtypes = [C.c_int, vp]
+        L.mcrt_copy_async.argtypes = [C.c_int, vp, vp, C.c_size_t, vp]
         L.mcrt_set_mesh_origin.argtypes = [vp, C.c_int32, vp]
         L.mcrt_set_mesh_vertices.argtypes = [vp, C.c_int32, vp, C.c_int64]
         L.mcrt_closest_hit.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
@@ -132,6 +139,38 @@ def _check(rc: int):
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# ---- peer-memory plumbing (mcrt_device_alloc / mcrt_ipc_* / mcrt_copy_async) -----------------------------------------
+def device_alloc(device: int, nbytes: int) -> int:
+    p = C.c_void_p()
+    _check(lib().mcrt_device_alloc(int(device), int(nbytes), C.byref(p)))
+    return int(p.value)
+
+
+def device_free(device: int, ptr: int):
+    _check(lib().mcrt_device_free(int(device), C.c_void_p(ptr)))
+
+
+def ipc_export(device: int, ptr: int) -> bytes:
+    h = (C.c_ubyte * 64)()
+    _check(lib().mcrt_ipc_export(int(device), C.c_void_p(ptr), h))
+    return bytes(h)
+
+
+def ipc_open(device: int, handle: bytes) -> int:
+    h = (C.c_ubyte * 64).from_buffer_copy(handle)
+    p = C.c_void_p()
+    _check(lib().mcrt_ipc_open(int(device), h, C.byref(p)))
+    return int(p.value)
+
+
+def ipc_close(device: int, ptr: int):
+    _check(lib().mcrt_ipc_close(int(device), C.c_void_p(ptr)))
+
+
+def copy_async(device: int, dst: int, src: int, nbytes: int, stream: int = 0):
+    _check(lib().mcrt_copy_async(int(device), C.c_void_p(dst), C.c_void_p(src), int(nbytes), C.c_void_p(stream) if stream else None))
 
 
 def default_params(**kw) -> Params:

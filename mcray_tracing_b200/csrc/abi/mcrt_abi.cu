@@ -1090,6 +1090,69 @@ int mcrt_trace_debug(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, uint64_t
     });
 }
 
+int mcrt_device_alloc(int device, size_t bytes, void** dev_ptr)
+{
+    if (!dev_ptr || bytes == 0) return fail(MCRT_ERR_INVALID, "mcrt_device_alloc: bad argument");
+    return guarded("mcrt_device_alloc", [&]() {
+        CUDA_TRY(cudaSetDevice(device));
+        CUDA_TRY(cudaMalloc(dev_ptr, bytes));
+        return MCRT_OK;
+    });
+}
+
+int mcrt_device_free(int device, void* dev_ptr)
+{
+    return guarded("mcrt_device_free", [&]() {
+        CUDA_TRY(cudaSetDevice(device));
+        CUDA_TRY(cudaFree(dev_ptr));
+        return MCRT_OK;
+    });
+}
+
+int mcrt_ipc_export(int device, const void* dev_ptr, unsigned char handle64[64])
+{
+    if (!dev_ptr || !handle64) return fail(MCRT_ERR_INVALID, "mcrt_ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    return guarded("mcrt_ipc_export", [&]() {
+        CUDA_TRY(cudaSetDevice(device));
+        cudaIpcMemHandle_t h;
+        CUDA_TRY(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+        memcpy(handle64, &h, 64);
+        return MCRT_OK;
+    });
+}
+
+int mcrt_ipc_open(int device, const unsigned char handle64[64], void** peer_ptr)
+{
+    if (!handle64 || !peer_ptr) return fail(MCRT_ERR_INVALID, "mcrt_ipc_open: null argument");
+    return guarded("mcrt_ipc_open", [&]() {
+        CUDA_TRY(cudaSetDevice(device));
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle64, 64);
+        CUDA_TRY(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        return MCRT_OK;
+    });
+}
+
+int mcrt_ipc_close(int device, void* peer_ptr)
+{
+    return guarded("mcrt_ipc_close", [&]() {
+        CUDA_TRY(cudaSetDevice(device));
+        CUDA_TRY(cudaIpcCloseMemHandle(peer_ptr));
+        return MCRT_OK;
+    });
+}
+
+int mcrt_copy_async(int device, void* dst, const void* src, size_t bytes, void* cuda_stream)
+{
+    if (!dst || !src) return fail(MCRT_ERR_INVALID, "mcrt_copy_async: null argument");
+    return guarded("mcrt_copy_async", [&]() {
+        CUDA_TRY(cudaSetDevice(device));
+        CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)cuda_stream));
+        return MCRT_OK;
+    });
+}
+
 int mcrt_trace_tree_debug(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, uint64_t frame, int64_t capacity, mcrt_segment* segments,
                           int32_t* path, int32_t* node, int64_t* n_out)
 {

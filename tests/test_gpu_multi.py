@@ -32,8 +32,27 @@ pose = sim.start_pose
 def lines(first, n, out):
     sim.simulate_scanlines(pose, first, n, seed=21, frame=9, rf_ptr=out.data_ptr())
 frame = sweep.run_frame_scanline_blocks(lines, sim.cols, sim.rows, dev)
+# the same sweep through the peer-memory deposit (CUDA IPC copies over NVLink instead of the NCCL gather)
+b, e = sweep.shard_bounds(len(poses), world, rank)
+F = max(sweep.all_shard_sizes(len(poses), world))
+peer = sweep.PeerDeposit(F, (sim.cols, sim.rows), dev, n_slots=2, dst=0)
+comm = torch.cuda.Stream(device=dev)
+local = torch.zeros((F, sim.cols, sim.rows), dtype=torch.float32, device=dev)
+sim.simulate_device(poses[b:e], local.data_ptr(), seed=21, first_frame=300 + b)
+torch.cuda.synchronize(dev)
+for slot in (1, 0, 1):
+    peer.deposit(slot, local, comm)
+    peer.commit(comm)
+comm.synchronize()
+deposited = None
+if rank == 0:
+    t = peer.slot_tensor(1).cpu().numpy()
+    sizes = sweep.all_shard_sizes(len(poses), world)
+    deposited = np.concatenate([t[r * F: r * F + sizes[r]] for r in range(world)])
+peer.close()
 if rank == 0:
     single = sim.simulate(poses, seed=21, first_frame=300)
+    assert np.array_equal(deposited, single), "peer-deposited sweep differs from the 1-GPU sweep"
     assert np.array_equal(res.cpu().numpy(), single), "pose-sharded sweep differs from the 1-GPU sweep"
     whole = sim.simulate(pose[None, :], seed=21, first_frame=9)[0]
     assert np.array_equal(frame.cpu().numpy(), whole), "scanline-block frame differs from the 1-GPU frame"
