@@ -125,10 +125,13 @@ def oracle_frames_per_s(n_frames: int, threads: int, scene_path: Path, pose: np.
     osc.simulate_frame(p, pose[:3], pose[3:], seed=1234, frame=first_frame)          # warm caches
     t0 = time.perf_counter()
     tests = 0
+    stage = np.zeros(4)
     for f in range(n_frames):
         r = osc.simulate_frame(p, pose[:3], pose[3:], seed=1234, frame=first_frame + 1 + f)
         tests += r["tests"]
+        stage += np.asarray(r["stage_seconds"], dtype=np.float64)[:4]
     dt = time.perf_counter() - t0
+    oracle_frames_per_s.last_stage_ms_per_frame = (stage / n_frames * 1e3).tolist()      # cast, accumulate, convolve+envelope, scan
     return n_frames / dt, tests / dt, osc, p
 
 
@@ -445,12 +448,17 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             threads = host_threads()
             n = args.cpu_frames
             fps1, sps1, _, _ = oracle_frames_per_s(n, 1, scene, sim.start_pose)
+            stage1 = list(getattr(oracle_frames_per_s, "last_stage_ms_per_frame", []))
             fpsN, spsN = (fps1, sps1) if threads == 1 else oracle_frames_per_s(n, threads, scene, sim.start_pose)[:2]
+            stageN = list(getattr(oracle_frames_per_s, "last_stage_ms_per_frame", []))
             best_fps, best_sps, cores = (fpsN, spsN, threads) if fpsN > fps1 else (fps1, sps1, 1)
             cpu_baseline = {"value": best_fps, "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": f"{n} frames of the same workload per variant; single thread (as the reference ships, scene.cpp:74) = {fps1:.2f} frames/s, "
                                       f"OpenMP over elements on {threads} threads = {fpsN:.2f} frames/s; oracle port (the reference needs Bullet+OpenCV)",
-                            "ray_segments_per_s": best_sps}
+                            "ray_segments_per_s": best_sps,
+                            "single_thread": {"frames_per_s": fps1, "ray_segments_per_s": sps1, "stage_ms_per_frame": stage1},
+                            "all_threads": {"threads": threads, "frames_per_s": fpsN, "ray_segments_per_s": spsN, "stage_ms_per_frame": stageN},
+                            "stage_order": ["cast_rays", "accumulate", "convolve+envelope", "scan_convert"]}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
