@@ -363,3 +363,50 @@ def test_voxel_index_fma_division_is_exact(api, O, ircad_rough, resolution_um):
         assert validated == 1            # the reference's resolution (main.cpp:33) must take the fast path
     assert np.array_equal(on_rf, off_rf)
     assert np.all(np.abs(on_rf - ref.T) <= _tol(ref.T))
+
+
+@pytest.mark.parametrize("kw", [
+    dict(elements=1, samples=1), dict(elements=2, samples=1, max_depth=1), dict(elements=3, samples=7, max_depth=2),
+    dict(elements=512, samples=5), dict(elements=17, samples=33), dict(elements=5, samples=16, max_depth=16),
+], ids=["1x1", "2x1-depth1", "3x7-depth2", "reference-512x5", "17x33", "depth16"])
+def test_edge_sizes_full_frame(api, O, ircad_rough, kw):
+    """Smallest and odd acquisition sizes (one element, one sample, one bounce, sample counts that do not divide a warp,
+    the maximum depth) and the reference's own 512 x 5: bounce counts and hit ids exact, RF within tolerance, through
+    the default path (windowed accumulate with G = 32 / S scanlines per warp, or the CTA-wide variant for S > 32)."""
+    path, A, osc = ircad_rough
+    gp, op = api.default_params(**kw), O.default_params(**kw)
+    with api.Simulator(path, gp) as sim:
+        pose = sim.start_pose
+        rf = sim.simulate(pose[None, :], seed=13, first_frame=4)[0]
+        st = sim.stats()
+        segs, nseg = sim.cast_rays(pose, seed=13, frame=4)
+    o = osc.simulate_frame(op, pose[:3], pose[3:], seed=13, frame=4)
+    os_, on, _ = osc.cast_rays(op, pose[:3], pose[3:], seed=13, frame=4)
+    assert np.array_equal(nseg, on) and st.segments == o["tests"] and st.march_steps == o["steps"] and st.late_echoes == 0
+    valid = np.arange(segs.shape[-1])[None, None, :] < on[:, :, None]
+    assert np.array_equal(segs["tri_id"][valid], os_["tri_id"][valid])
+    ref = o["rf"].T
+    assert rf.shape == ref.shape and np.all(np.abs(rf - ref) <= _tol(ref)), np.abs(rf - ref).max()
+
+
+def test_empty_and_extreme_calls(api, ircad):
+    """Zero poses is a no-op; a frame index near 2^32 and a large seed work (the Philox counter takes frame modulo 2^32);
+    ragged batches smaller than max_batch_poses reuse the workspace; bad arguments are error codes."""
+    path, A, osc = ircad
+    with api.Simulator(path, api.default_params(elements=32, samples=2)) as sim:
+        pose = sim.start_pose
+        empty = sim.simulate(np.zeros((0, 6), np.float32), seed=1, first_frame=0)
+        assert empty.shape == (0, sim.cols, sim.rows)
+        a = sim.simulate(np.repeat(pose[None, :], 3, axis=0), seed=2**63 + 5, first_frame=2**32 - 2)
+        b = sim.simulate(pose[None, :], seed=2**63 + 5, first_frame=2**32 - 1)[0]
+        c = sim.simulate(pose[None, :], seed=2**63 + 5, first_frame=2**32)[0]
+        assert np.array_equal(a[1], b) and np.array_equal(a[2], c) and not np.array_equal(b, c)
+        for n in (7, 2, 5, 1):
+            assert sim.simulate(np.repeat(pose[None, :], n, axis=0), seed=3, first_frame=10).shape[0] == n
+        with pytest.raises(api.McrtError):
+            sim.set_option("no_such_option", 1)
+        with pytest.raises(api.McrtError):
+            sim.simulate_scanlines(pose, -1, 4)
+    for bad in (dict(elements=0), dict(samples=0), dict(max_depth=0), dict(max_depth=17), dict(psf_lateral=4)):
+        with pytest.raises(api.McrtError):
+            api.Simulator(path, api.default_params(**bad))
