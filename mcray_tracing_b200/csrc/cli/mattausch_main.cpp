@@ -7,11 +7,16 @@
 //   --png                      also write the scan-converted image as 8-bit PNG (frame 0 under the reference's name,
 //                              prelog.png, rfimage.h:147)
 //   --bmode DR [--gain dB] [--tgc dB/cm]   B-mode display chain (mcrt_bmode): TGC, log compression to DR dB -> bmode_NNNN.png
+//   --poses FILE [--gpus G] [--batch B]    probe sweep: one pose per line (x y z ax ay az), frame index = line index; the poses are
+//                              split into G contiguous blocks, one context + host thread per GPU (devices D .. D+G-1), B poses per
+//                              call; all frames go to sweep_rf.f32 ([pose][scanline][sample] float32)
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <chrono>
 #include <vector>
 
 #include "../../../include/mcrt.h"
@@ -106,7 +111,8 @@ int main(int argc, char** argv)
     }
     mcrt_params p;
     mcrt_default_params(&p);
-    int frames = 1, device = 0, log_compress = 0, png = 0, bmode = 0;
+    int frames = 1, device = 0, log_compress = 0, png = 0, bmode = 0, gpus = 1, batch = 64;
+    std::string poses_file;
     mcrt_bmode_params bp = {0.0f, 0.0f, 60.0f, 0.0f};
     unsigned long long seed = 0;
     std::string out_dir = ".";
@@ -122,10 +128,77 @@ int main(int argc, char** argv)
         else if (a == "--device") device = atoi(next());
         else if (a == "--log-compress") log_compress = 1;        // rfimage.h:131-136 (commented out in the reference)
         else if (a == "--png") png = 1;
+        else if (a == "--poses") poses_file = next();
+        else if (a == "--gpus") gpus = atoi(next());
+        else if (a == "--batch") batch = atoi(next());
         else if (a == "--bmode") { bmode = 1; bp.dynamic_range_db = (float)atof(next()); }
         else if (a == "--gain") bp.gain_db = (float)atof(next());
         else if (a == "--tgc") bp.tgc_db_per_cm = (float)atof(next());
         else { printf("Incorrect argument list.\n"); return 0; }
+    }
+    if (!poses_file.empty()) {
+        // ---- probe sweep sharded over the GPUs of this box (BASELINE config 3), C++ host: one context and one thread per GPU ----
+        std::vector<mcrt_pose> poses;
+        if (FILE* f = fopen(poses_file.c_str(), "r")) {
+            char line[512];
+            while (fgets(line, sizeof(line), f)) {
+                mcrt_pose q;
+                if (line[0] == '#') continue;
+                if (sscanf(line, "%f %f %f %f %f %f", &q.pos[0], &q.pos[1], &q.pos[2], &q.angles_deg[0], &q.angles_deg[1], &q.angles_deg[2]) == 6)
+                    poses.push_back(q);
+            }
+            fclose(f);
+        }
+        if (poses.empty() || gpus < 1 || batch < 1) { printf("Incorrect argument list.\n"); return 0; }
+        std::vector<mcrt_ctx*> ctxs(gpus, nullptr);
+        for (int g = 0; g < gpus; g++) {                               // contexts are created one after the other
+            if (mcrt_create(argv[1], &p, device + g, &ctxs[g]) != MCRT_OK) {
+                printf("The program found an error and will terminate.\nReason:\n%s\n", mcrt_last_error());
+                for (mcrt_ctx* c : ctxs) if (c) mcrt_destroy(c);
+                return 0;
+            }
+            if (log_compress) mcrt_set_option(ctxs[g], "log_compress", 1);
+            mcrt_set_option(ctxs[g], "max_batch_poses", batch);
+        }
+        mcrt_info info;
+        mcrt_get_info(ctxs[0], &info);
+        printf("%g us\n", info.max_travel_time_us);
+        printf("rf_image: %d, %d\n", info.rows, info.cols);
+        const size_t px = (size_t)info.rows * info.cols, n = poses.size();
+        std::vector<float> all(px * n);
+        std::vector<int> failed(gpus, 0);
+        std::vector<long long> segs(gpus, 0);
+        const auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> workers;
+        for (int g = 0; g < gpus; g++) {
+            workers.emplace_back([&, g]() {
+                // contiguous block of GPU g: the first (n % gpus) blocks get one pose more (sweep.py::shard_bounds)
+                const size_t base = n / gpus, extra = n % gpus;
+                const size_t b = g * base + ((size_t)g < extra ? (size_t)g : extra), e = b + base + ((size_t)g < extra ? 1 : 0);
+                for (size_t i = b; i < e; i += (size_t)batch) {
+                    const int m = (int)((e - i) < (size_t)batch ? (e - i) : (size_t)batch);
+                    if (mcrt_simulate(ctxs[g], &poses[i], m, seed, (uint64_t)i, all.data() + i * px, nullptr) != MCRT_OK) {
+                        fprintf(stderr, "GPU %d: %s\n", device + g, mcrt_last_error());
+                        failed[g] = 1;
+                        return;
+                    }
+                    mcrt_stats st;
+                    mcrt_get_stats(ctxs[g], &st);
+                    segs[g] += (long long)st.segments;
+                }
+            });
+        }
+        for (auto& w : workers) w.join();
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        long long total_segs = 0;
+        int any_failed = 0;
+        for (int g = 0; g < gpus; g++) { total_segs += segs[g]; any_failed |= failed[g]; }
+        for (mcrt_ctx* c : ctxs) mcrt_destroy(c);
+        if (any_failed) { printf("The program found an error and will terminate.\n"); return 0; }
+        // "fps tests total_collisions" of scene.cpp:178-179, for the whole sweep
+        printf("%g %lld %d\n", dt > 0 ? (double)n / dt : 0.0, total_segs, p.samples * p.elements);
+        if (FILE* fh = fopen((out_dir + "/sweep_rf.f32").c_str(), "wb")) { fwrite(all.data(), sizeof(float), all.size(), fh); fclose(fh); }
+        return 0;
     }
     mcrt_ctx* ctx = nullptr;
     if (mcrt_create(argv[1], &p, device, &ctx) != MCRT_OK) {

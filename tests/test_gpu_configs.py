@@ -379,3 +379,25 @@ def test_ray_tree_mode_matches_oracle(api, O, assets_dirs, scene_name, det):
     assert np.all(np.abs(rf[0] - ref["rf"].T) <= _tol(ref["rf"].T)), np.abs(rf[0] - ref["rf"].T).max()
     assert st.segments == len(gs) + len(osc.cast_rays_tree(op, pose[:3], pose[3:], seed=6, frame=3)[0])
     assert not np.array_equal(rf[0], single)
+
+
+def test_cli_pose_sweep(api, assets_dirs, tmp_path):
+    """`mattausch <scene> --poses FILE [--gpus G]`: the C++ host's probe sweep (one context + thread per GPU, contiguous
+    pose blocks) writes exactly the frames of one batched mcrt_simulate call."""
+    import subprocess
+    from pathlib import Path
+    import torch
+    from mcray_tracing_b200 import assets
+    path = assets_dirs["ircad11"] / "santi-liver.scene"
+    poses = assets.sweep_poses(11)
+    pf = tmp_path / "poses.txt"
+    pf.write_text("# x y z ax ay az\n" + "\n".join(" ".join(repr(float(v)) for v in q) for q in poses) + "\n")
+    with api.Simulator(path, api.default_params(elements=64, samples=4)) as sim:
+        ref = sim.simulate(poses, seed=5, first_frame=0)
+    exe = Path(api.__file__).resolve().parent / "mattausch"
+    for gpus in sorted({1, min(2, torch.cuda.device_count())}):
+        out = subprocess.run([str(exe), str(path), "--elements", "64", "--samples", "4", "--seed", "5", "--out", str(tmp_path), "--poses", str(pf),
+                              "--gpus", str(gpus), "--batch", "4"], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "rf_image: 465, 64" in out.stdout, out.stdout + out.stderr
+        got = np.fromfile(tmp_path / "sweep_rf.f32", np.float32).reshape(ref.shape)
+        assert np.array_equal(got, ref), f"gpus={gpus}"
