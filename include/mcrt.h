@@ -215,6 +215,12 @@ int mcrt_scan_convert(mcrt_ctx* ctx, const float* rf_in /* [cols][rows] */, floa
 int mcrt_set_mesh_origin(mcrt_ctx* ctx, int32_t mesh, const float* origin3);
 int mcrt_set_mesh_vertices(mcrt_ctx* ctx, int32_t mesh, const float* tri_local9, int64_t n_triangles);
 
+/* Depth-dependent lateral PSF (psf.h:11-25 describes lateral ranges that "vary according to distance to the
+ * transducer" while the reference fills one lateral kernel, psf.h:52-57): RF row r is convolved laterally with a Gaussian of
+ * variance var_y * w^2, w = 1 + spread * |depth(r) - focus_cm| / focus_cm.  spread = 0 restores the reference PSF.
+ * table_out (nullable): the taps, [psf_lateral][rows] floats. */
+int mcrt_set_psf_depth_profile(mcrt_ctx* ctx, float focus_cm, float spread, float* table_out);
+
 /* B-mode display chain on an envelope image (the reference stops at the envelope and keeps its
  * log compression commented out, rfimage.h:127-136, then writes the scan-converted image x255 as 8 bit, rfimage.h:142-148):
  *   v = |E| * 10^((gain_db + tgc_db_per_cm * depth_cm(row)) / 20),   y = clamp(1 + 20 log10(v / max v) / dynamic_range_db, 0, 1),

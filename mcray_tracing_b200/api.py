@@ -70,7 +70,7 @@ assert SEGMENT_DTYPE.itemsize == 72
 EXPORTS = ["mcrt_default_params", "mcrt_create", "mcrt_create_from_arrays", "mcrt_destroy", "mcrt_last_error", "mcrt_get_info",
            "mcrt_get_stats", "mcrt_set_option", "mcrt_simulate", "mcrt_simulate_async", "mcrt_trace_debug", "mcrt_closest_hit",
            "mcrt_transducer_elements", "mcrt_accumulate", "mcrt_postprocess", "mcrt_scan_convert", "mcrt_get_psf_taps",
-           "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe", "mcrt_load_obj", "mcrt_scene_probe", "mcrt_host_tables", "mcrt_simulate_scanlines", "mcrt_bmode", "mcrt_set_mesh_origin", "mcrt_set_mesh_vertices", "mcrt_trace_tree_debug", "mcrt_device_alloc",
+           "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe", "mcrt_load_obj", "mcrt_scene_probe", "mcrt_host_tables", "mcrt_simulate_scanlines", "mcrt_bmode", "mcrt_set_mesh_origin", "mcrt_set_mesh_vertices", "mcrt_trace_tree_debug", "mcrt_device_alloc", "mcrt_set_psf_depth_profile",
            "mcrt_device_free", "mcrt_ipc_export", "mcrt_ipc_open", "mcrt_ipc_close", "mcrt_copy_async"]
 
 
@@ -108,6 +108,7 @@ def lib():
         L.mcrt_simulate_scanlines.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, vp]
         L.mcrt_bmode.argtypes = [vp, vp, C.c_int32, vp, vp, vp]
         L.mcrt_trace_tree_debug.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_int64, vp, vp, vp, vp]
+        L.mcrt_set_psf_depth_profile.argtypes = [vp, C.c_float, C.c_float, vp]
         L.mcrt_device_alloc.argtypes = [C.c_int, C.c_size_t, vp]
         L.mcrt_device_free.argtypes = [C.c_int, vp]
         L.mcrt_ipc_export.argtypes = [C.c_int, vp, vp]
@@ -309,6 +310,12 @@ class Simulator:
         n = C.c_int64(0)
         _check(lib().mcrt_trace_tree_debug(self.h, _p(P), int(seed), int(frame), cap, _p(segs), _p(path), _p(node), C.byref(n)))
         return segs[: n.value].copy(), path[: n.value].copy(), node[: n.value].copy()
+
+    def set_psf_depth_profile(self, focus_cm: float, spread: float):
+        """Depth-dependent lateral PSF (spread = 0: off); returns the taps [psf_lateral][rows] (None when off)."""
+        tab = np.zeros((self.params.psf_lateral, self.rows), np.float32) if spread > 0 else None
+        _check(lib().mcrt_set_psf_depth_profile(self.h, float(focus_cm), float(spread), _p(tab)))
+        return tab
 
     def set_mesh_origin(self, mesh: int, origin3):
         """Move a mesh: new body origin in world cm; applied (one BVH rebuild) at the next compute call."""

@@ -116,6 +116,8 @@ struct mcrt_ctx {
     bool scene_dirty = false;          // staged mesh updates wait for a rebuild
     float* d_axial = nullptr;
     float* d_lateral = nullptr;
+    float* d_lat_by_row = nullptr;     // depth-dependent lateral PSF table [psf_lateral][rows] (mcrt_set_psf_depth_profile), or nullptr
+    std::vector<float> h_lat_by_row;
     float* d_map_x = nullptr;
     float* d_map_y = nullptr;
     std::vector<float> h_axial, h_lateral;
@@ -282,7 +284,7 @@ void enqueue_image(mcrt_ctx* c, int pose0, int n, bool want_scan, cudaStream_t s
     CUDA_TRY(launch_accumulate(c->sc, c->aq, c->d_volume, c->tb.segments + p0 * c->aq.max_depth, c->tb.n_segments + p0, n, c->d_rf_acc + px0,
                                c->d_steps, c->d_columns + p0 * c->aq.rows, s, launches));
     launch_post(c->d_rf_acc + px0, n, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
-                c->d_rf_tmp0 + px0, c->d_rf_tmp1 + px0, c->d_rf_final + px0, s, launches);
+                c->d_rf_tmp0 + px0, c->d_rf_tmp1 + px0, c->d_rf_final + px0, s, launches, 0, 0, c->d_lat_by_row);
     if (c->log_compress) launch_log_compress(c->d_rf_final + px0, n, (int64_t)c->aq.elements * c->aq.rows, c->d_max_bits + pose0, s, launches);
     if (c->params.rf_layout == 1) launch_transpose(c->d_rf_final + px0, n, c->aq.elements, c->aq.rows, c->d_rf_t + px0, s, launches);
     if (want_scan)
@@ -305,7 +307,7 @@ void enqueue_pipeline(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* l
                                    launches));
         CUDA_TRY(cudaEventRecord(c->ev_c, s));
         launch_post(c->d_rf_acc, n, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
-                    c->d_rf_tmp0, c->d_rf_tmp1, c->d_rf_final, s, launches);
+                    c->d_rf_tmp0, c->d_rf_tmp1, c->d_rf_final, s, launches, 0, 0, c->d_lat_by_row);
         if (c->log_compress) launch_log_compress(c->d_rf_final, n, (int64_t)c->aq.elements * c->aq.rows, c->d_max_bits, s, launches);
         if (c->params.rf_layout == 1) launch_transpose(c->d_rf_final, n, c->aq.elements, c->aq.rows, c->d_rf_t, s, launches);
         if (want_scan)
@@ -397,7 +399,7 @@ void run_tree_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* lau
     CUDA_TRY(launch_accumulate_tree(c->sc, c->aq, c->d_volume, t, n, c->d_rf_acc, c->d_steps, c->d_columns, s, launches));
     if (c->profile_stages) CUDA_TRY(cudaEventRecord(c->ev_c, s));
     launch_post(c->d_rf_acc, n, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
-                c->d_rf_tmp0, c->d_rf_tmp1, c->d_rf_final, s, launches);
+                c->d_rf_tmp0, c->d_rf_tmp1, c->d_rf_final, s, launches, 0, 0, c->d_lat_by_row);
     if (c->log_compress) launch_log_compress(c->d_rf_final, n, (int64_t)c->aq.elements * c->aq.rows, c->d_max_bits, s, launches);
     if (c->params.rf_layout == 1) launch_transpose(c->d_rf_final, n, c->aq.elements, c->aq.rows, c->d_rf_t, s, launches);
     if (want_scan)
@@ -621,7 +623,7 @@ void destroy_impl(mcrt_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_workspace(c);
     dev_free(c->d_meshes); dev_free(c->d_materials); dev_free(c->bvh.nodes); dev_free(c->bvh.tris); dev_free(c->d_nodes4);
-    dev_free(c->d_elem_sincos); dev_free(c->d_axial); dev_free(c->d_lateral); dev_free(c->d_map_x); dev_free(c->d_map_y);
+    dev_free(c->d_elem_sincos); dev_free(c->d_axial); dev_free(c->d_lateral); dev_free(c->d_lat_by_row); dev_free(c->d_map_x); dev_free(c->d_map_y);
     dev_free(c->d_seed_frame); dev_free(c->d_steps); dev_free(c->d_trav);
     if (c->h_seed_frame) cudaFreeHost(c->h_seed_frame);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -1032,7 +1034,7 @@ int mcrt_simulate_scanlines(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, u
         launch_trace(c->sc, aq, fr, c->tb, c->sm_count, s, &launches);
         CUDA_TRY(launch_accumulate(c->sc, aq, c->d_volume, c->tb.segments, c->tb.n_segments, 1, c->d_rf_acc, c->d_steps, c->d_columns, s, &launches));
         launch_post(c->d_rf_acc, 1, n_local, aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, kl, 3, c->d_rf_tmp0, c->d_rf_tmp1,
-                    c->d_rf_final, s, &launches, e0, E);
+                    c->d_rf_final, s, &launches, e0, E, c->d_lat_by_row);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(rf_out, c->d_rf_final, sizeof(float) * (size_t)n_elements * aq.rows,
                                  is_device_pointer(rf_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
@@ -1358,6 +1360,27 @@ int mcrt_scan_convert(mcrt_ctx* c, const float* rf_in, float* scan_out)
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(scan_out, c->d_scan, sizeof(float) * ns, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return MCRT_OK;
+    });
+}
+
+int mcrt_set_psf_depth_profile(mcrt_ctx* c, float focus_cm, float spread, float* table_out)
+{
+    if (!c) return fail(MCRT_ERR_INVALID, "mcrt_set_psf_depth_profile: null argument");
+    if (!(spread >= 0.0f) || (spread > 0.0f && !(focus_cm > 0.0f))) return fail(MCRT_ERR_INVALID, "mcrt_set_psf_depth_profile: spread >= 0 and focus_cm > 0");
+    return guarded("mcrt_set_psf_depth_profile", [&]() {
+        CUDA_TRY(cudaSetDevice(c->device));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear();
+        dev_free(c->d_lat_by_row);
+        c->h_lat_by_row.clear();
+        if (spread > 0.0f) {
+            psf_lateral_depth_table(c->params, c->aq.rows, focus_cm, spread, c->h_lat_by_row);
+            dev_alloc(c->d_lat_by_row, c->h_lat_by_row.size());
+            CUDA_TRY(cudaMemcpy(c->d_lat_by_row, c->h_lat_by_row.data(), sizeof(float) * c->h_lat_by_row.size(), cudaMemcpyHostToDevice));
+            if (table_out) memcpy(table_out, c->h_lat_by_row.data(), sizeof(float) * c->h_lat_by_row.size());
+        }
         return MCRT_OK;
     });
 }

@@ -337,6 +337,27 @@ void psf_taps(const mcrt_params& p, std::vector<float>& axial, std::vector<float
     }
 }
 
+// Depth-dependent lateral PSF (psf.h:11-25 says "lateral and elevation ranges vary according to distance to
+// the transducer" but the reference fills ONE lateral kernel): the lateral Gaussian of RF row r has the variance
+//   var_y(r) = var_y * w^2,  w = 1 + spread * |depth(r) - focus| / focus,  depth(r) = r * depth_cm / rows,
+// i.e. the beam is narrowest at the focus.  Same float / double mix as psf_taps (psf.h:80-92).  table: [kl][rows].
+void psf_lateral_depth_table(const mcrt_params& p, int rows, float focus_cm, float spread, std::vector<float>& table)
+{
+    const float half_lateral = (size_t)p.psf_lateral * (size_t)p.resolution_um / 1000.0f / 2.0f;
+    const float resolution = p.resolution_um / 1000.0f;
+    table.assign((size_t)p.psf_lateral * rows, 0.0f);
+    for (int r = 0; r < rows; r++) {
+        const double depth = (double)r * p.depth_cm / (double)rows;
+        const float w = (float)(1.0 + (double)spread * std::fabs(depth - (double)focus_cm) / (double)focus_cm);
+        const float var = p.psf_var_y * w * w;
+        for (int i = 0; i < p.psf_lateral; i++) {
+            const float y = (size_t)i * resolution - half_lateral;
+            const double yy = (double)y * (double)y;
+            table[(size_t)i * rows + r] = (float)std::exp(-0.5f * (yy / var));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // rf_image::create_mapping (rfimage.h:183-215): map_x = source row, map_y = source column
 // ------------------------------------------------------------------------------------------------

@@ -63,6 +63,8 @@ HostScene scene_from_arrays(const mcrt_scene_arrays& a);
 void element_angle_table(const mcrt_params& p, const Derived& d, std::vector<float>& sincos2);
 PoseTrig pose_trig(const mcrt_pose& pose);                                     // transducer.h:37-39,51-53
 void psf_taps(const mcrt_params& p, std::vector<float>& axial, std::vector<float>& lateral);    // psf.h:34-58
+// depth-dependent lateral PSF taps [psf_lateral][rows] (extension; see mcrt_host.cpp)
+void psf_lateral_depth_table(const mcrt_params& p, int rows, float focus_cm, float spread, std::vector<float>& table);
 void scan_mapping(const mcrt_params& p, const Derived& d, std::vector<float>& map_x, std::vector<float>& map_y);   // rfimage.h:183-215
 const std::vector<float>& scatterer_volume();                                  // volume.h:19-35, process-wide
 

@@ -714,8 +714,10 @@ __global__ void __launch_bounds__(256) k_psf_axial(const float* __restrict__ in,
 // scanlines; lanes walk consecutive rows, so every load/store is coalesced and no shared memory is needed.
 __global__ void __launch_bounds__(256) k_psf_lateral(const float* __restrict__ raw, const float* __restrict__ axial_buf, const int cols,
                                                     const int rows, const float* __restrict__ taps, const int ka, const int kl,
-                                                    const int col_offset, const int cols_total, float* __restrict__ out)
+                                                    const int col_offset, const int cols_total, float* __restrict__ out,
+                                                    const float* __restrict__ taps_by_row)
 {
+    // taps_by_row != nullptr: depth-dependent lateral PSF, tap k of RF row r = taps_by_row[k * rows + r]
     __shared__ float s_taps[MCRT_MAX_TAPS];
     for (int i = threadIdx.x; i < kl; i += blockDim.x) s_taps[i] = taps[i];
     __syncthreads();
@@ -738,7 +740,7 @@ __global__ void __launch_bounds__(256) k_psf_lateral(const float* __restrict__ r
             for (int kk = 0; kk < MCRT_PSF_R; kk++) {
                 const int k = k0 + kk;
                 if (k < kl) {
-                    const float t = s_taps[k];
+                    const float t = taps_by_row ? __ldg(&taps_by_row[(size_t)k * rows + r]) : s_taps[k];
 #pragma unroll
                     for (int j = 0; j < MCRT_PSF_R; j++) acc[j] += win[(kk + j) & (MCRT_PSF_R - 1)] * t;
                     win[kk] = ld(c0 + k + MCRT_PSF_R);
@@ -1199,7 +1201,7 @@ int post_launch_count(int cols, int rows, int n_lateral, int flags, int n_images
 
 void launch_post(const float* d_in, int n_images, int cols, int rows, const float* d_axial, int n_axial, const float* d_lateral,
                  int n_lateral, int flags, float* d_tmp0, float* d_tmp1, float* d_out, cudaStream_t stream, int* launches, int col_offset,
-                 int cols_total)
+                 int cols_total, const float* d_lateral_by_row)
 {
     if (cols_total <= 0) { col_offset = 0; cols_total = cols; }
     const int64_t n_scanlines = (int64_t)n_images * cols;
@@ -1211,7 +1213,7 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
         tc = tc > 8 ? tc / 2 : 4;
         smem = fused_smem_bytes(rows, n_lateral, flags, tc);
     }
-    if (tc > 0 && n_images <= 65535) {
+    if (tc > 0 && n_images <= 65535 && !d_lateral_by_row) {       // the fused kernel holds ONE set of lateral taps in registers
         // whole scanlines fit shared memory: one pass over HBM
         dim3 grid((cols + tc - 1) / tc, n_images, 1);
         if (n_axial == 7 && n_lateral == 13)      // the reference's psf<7,13,...> (main.cpp:34)
@@ -1235,7 +1237,7 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
         }
         float* dst = (flags & 2) ? d_tmp1 : d_out;
         dim3 gl((rows + 255) / 256, (cols + MCRT_PSF_R - 1) / MCRT_PSF_R, n_images);
-        k_psf_lateral<<<gl, 256, 0, stream>>>(cur, d_tmp0, cols, rows, d_lateral, n_axial, n_lateral, col_offset, cols_total, dst);
+        k_psf_lateral<<<gl, 256, 0, stream>>>(cur, d_tmp0, cols, rows, d_lateral, n_axial, n_lateral, col_offset, cols_total, dst, d_lateral_by_row);
         cur = dst;
         if (launches) (*launches)++;
     }

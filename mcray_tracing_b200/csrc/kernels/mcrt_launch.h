@@ -121,7 +121,8 @@ cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2
 // d_tmp0/d_tmp1: scratch of the same size as the image batch.  Result always lands in d_out.
 void launch_post(const float* d_in, int n_images, int cols, int rows, const float* d_axial, int n_axial, const float* d_lateral,
                  int n_lateral, int flags, float* d_tmp0, float* d_tmp1, float* d_out, cudaStream_t stream, int* launches,
-                 int col_offset = 0, int cols_total = 0);   // scanline-block runs: global index of scanline 0 / global scanline count
+                 int col_offset = 0, int cols_total = 0,     // scanline-block runs: global index of scanline 0 / global scanline count
+                 const float* d_lateral_by_row = nullptr);  // depth-dependent lateral PSF: [n_lateral][rows] taps (unfused kernels)
 // exhaustive device check (all 2^32 float bit patterns) that the 3-instruction FMA division reproduces the voxel index of
 // coord / resolution for this resolution; enables AcqDev::voxel_fma_division
 cudaError_t validate_fma_division(float resolution, bool* ok);

@@ -1023,6 +1023,42 @@ void orc_envelope(float* rf, int32_t rows, int32_t cols)
 }
 
 // rfimage.h:127-136 (commented out in the reference): max = minMaxLoc; I = log10(I + 1) / log10(max + 1)
+// Depth-dependent lateral PSF (new functionality on top of psf.h:52-57 / rfimage.h:111-122): taps of row r
+// are exp(-0.5 y^2 / (var_y w^2)), w = 1 + spread |depth(r) - focus| / focus; table [n_lateral][rows].
+void orc_psf_depth_table(const orc_params* p, int32_t rows, float focus_cm, float spread, float* table)
+{
+    const float half_lateral = (size_t)p->psf_lateral * (size_t)p->resolution_um / 1000.0f / 2.0f;
+    const float resolution = p->resolution_um / 1000.0f;
+    for (int32_t r = 0; r < rows; r++) {
+        const double depth = (double)r * p->depth_cm / (double)rows;
+        const float w = (float)(1.0 + (double)spread * std::fabs(depth - (double)focus_cm) / (double)focus_cm);
+        const float var = p->psf_var_y * w * w;
+        for (int32_t i = 0; i < p->psf_lateral; i++) {
+            const float y = (size_t)i * resolution - half_lateral;
+            const double yy = (double)y * (double)y;
+            table[(size_t)i * rows + r] = (float)std::exp(-0.5f * (yy / var));
+        }
+    }
+}
+
+// rf_image::convolve (rfimage.h:93-123) with per-row lateral taps lateral_by_row[k * rows + row]
+void orc_convolve_depth(float* rf, int32_t rows, int32_t cols, const float* axial, int32_t n_axial, const float* lateral_by_row, int32_t n_lateral)
+{
+    std::vector<float> buf((size_t)rows * cols, 0.0f);
+    for (int col = 0; col < cols; col++)
+        for (int row = n_axial; row < rows - n_axial; row++) {
+            float convolution = 0;
+            for (int k = 0; k < n_axial; k++) convolution += rf[(size_t)(row + k) * cols + col] * axial[k];
+            buf[(size_t)row * cols + col] = convolution;
+        }
+    for (int row = n_axial; row < rows - n_axial; row++)
+        for (int col = n_lateral / 2; col < cols - n_lateral; col++) {
+            float convolution = 0;
+            for (int k = 0; k < n_lateral; k++) convolution += buf[(size_t)row * cols + col + k] * lateral_by_row[(size_t)k * rows + row];
+            rf[(size_t)row * cols + col] = convolution;
+        }
+}
+
 // B-mode display chain (new functionality on top of rfimage.h:127-148): TGC gain, log compression to a
 // dynamic range.  rf: [rows][cols] envelope image (oracle layout), in place -> [0, 1].
 void orc_bmode(float* rf, int32_t rows, int32_t cols, double depth_cm, float gain_db, float tgc_db_per_cm, float dynamic_range_db)

@@ -343,6 +343,24 @@ def convolve(rf, ax, lat):
     return out
 
 
+def psf_depth_table(p: OrcParams, focus_cm, spread):
+    rows = derive(p).rows
+    tab = np.zeros((p.psf_lateral, rows), np.float32)
+    L = oracle()
+    L.orc_psf_depth_table.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p]
+    L.orc_psf_depth_table(C.byref(p), rows, float(focus_cm), float(spread), _p(tab))
+    return tab
+
+
+def convolve_depth(rf, ax, lat_by_row):
+    out = np.ascontiguousarray(rf, np.float32).copy()
+    ax = np.ascontiguousarray(ax, np.float32); tab = np.ascontiguousarray(lat_by_row, np.float32)
+    L = oracle()
+    L.orc_convolve_depth.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+    L.orc_convolve_depth(_p(out), out.shape[0], out.shape[1], _p(ax), len(ax), _p(tab), tab.shape[0])
+    return out
+
+
 def envelope(rf):
     out = np.ascontiguousarray(rf, np.float32).copy()
     oracle().orc_envelope(_p(out), out.shape[0], out.shape[1])

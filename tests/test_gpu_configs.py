@@ -401,3 +401,38 @@ def test_cli_pose_sweep(api, assets_dirs, tmp_path):
         assert out.returncode == 0 and "rf_image: 465, 64" in out.stdout, out.stdout + out.stderr
         got = np.fromfile(tmp_path / "sweep_rf.f32", np.float32).reshape(ref.shape)
         assert np.array_equal(got, ref), f"gpus={gpus}"
+
+
+def test_depth_dependent_lateral_psf(api, O, assets_dirs):
+    """the lateral PSF widens away from the focus (per-row lateral taps).  The tap table equals the
+    oracle's bit for bit, the frame equals accumulate -> orc_convolve_depth -> envelope within the RF tolerance (the
+    PSF/envelope arithmetic itself is bit-exact on identical input, checked through the scanline-block path), spread = 0
+    restores the reference PSF exactly."""
+    from mcray_tracing_b200 import sweep
+    path = assets_dirs["ircad11"] / "santi-liver-rough.scene"
+    A = O.load_scene_py(path)
+    osc = O.OracleScene(A)
+    kw = dict(elements=96, samples=4)
+    gp, op = api.default_params(**kw), O.default_params(**kw)
+    with api.Simulator(path, gp) as sim:
+        pose = sim.start_pose
+        plain = sim.simulate(pose[None, :], seed=3, first_frame=1)[0]
+        tab = sim.set_psf_depth_profile(6.0, 1.5)
+        deep = sim.simulate(np.repeat(pose[None, :], 2, axis=0), seed=3, first_frame=1)
+        parts = [sim.simulate_scanlines(pose, *sweep.shard_bounds(sim.cols, 3, r)[:1], sweep.shard_bounds(sim.cols, 3, r)[1] - sweep.shard_bounds(sim.cols, 3, r)[0],
+                                        seed=3, frame=1) for r in range(3)]
+        assert sim.set_psf_depth_profile(6.0, 0.0) is None
+        back = sim.simulate(pose[None, :], seed=3, first_frame=1)[0]
+        with pytest.raises(api.McrtError):
+            sim.set_psf_depth_profile(0.0, 1.0)
+    assert np.array_equal(tab, O.psf_depth_table(op, 6.0, 1.5))
+    assert np.array_equal(back, plain) and not np.array_equal(deep[0], plain)
+    assert np.array_equal(np.concatenate(parts), deep[0])                      # scanline blocks use global rows / columns too
+    os_, on, _ = osc.cast_rays(op, pose[:3], pose[3:], seed=3, frame=1)
+    acc, _ = osc.accumulate(op, os_, on)
+    ax, lat = O.psf_taps(op)
+    ref = O.envelope(O.convolve_depth(acc, ax, tab)).T
+    assert np.all(np.abs(deep[0] - ref) <= _tol(ref)), np.abs(deep[0] - ref).max()
+    # at the focus row the table is the reference lateral kernel
+    focus_row = int(round(6.0 / gp.depth_cm * tab.shape[1]))
+    assert np.allclose(tab[:, focus_row], lat, rtol=0, atol=2e-3)
