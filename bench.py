@@ -427,7 +427,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         tf = ROOT / "profiles" / "accumulate_traffic.json"
         if tf.exists():
             try:
-                traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+                tj = json.loads(tf.read_text())
+                # the ncu capture was taken at frames_per_launch frames per call; DRAM bytes scale with the frames of a launch
+                traffic = int(tj["dram_bytes_per_launch"] * F / tj.get("frames_per_launch", F))
             except Exception:
                 traffic = None
         roofline = {"kernel": "k_accumulate_win (echo accumulation + scatterer-volume gather + sample reduction, one kernel)", "bound": "hbm", "achieved": achieved, "peak": peak,
@@ -491,7 +493,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=256)
+    ap.add_argument("--frames-per-step", type=int, default=512,
+                    help="independent frames per C-ABI call and per GPU (measured: 256 -> 81.7k, 512 -> 87.0k, 1024 -> 89.4k frames/s)")
     ap.add_argument("--cpu-frames", type=int, default=60, help="frames per CPU-baseline variant (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N > 1: peer-memory deposit over NVLink (default) or NCCL send/recv gather")
