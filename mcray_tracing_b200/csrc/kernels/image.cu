@@ -597,12 +597,15 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
             if (written < wend) written = wend;
         }
         group_sync();
-        // sample reduction in sample order (= k_reduce_samples), coalesced row stores
+        // sample reduction in sample order (= k_reduce_samples): thread r of the group owns row base + r of the window and walks
+        // the group's scanlines, so consecutive lanes store consecutive rows (coalesced) and no index arithmetic is needed
         const int wrows = wend - base;
-        for (int j = t; j < MCRT_WIN_ROWS * G; j += group_size) {
-            const int g = j / MCRT_WIN_ROWS, r = j - g * MCRT_WIN_ROWS;                    // constant divisor
-            if (r < wrows && scanline0 + g < n_scanlines) {
-                const float* src = s_win + MCRT_WIN_SLOT(base + r) * stride + g * S;
+        if (t < wrows) {
+            const float* rowp = s_win + MCRT_WIN_SLOT(base + t) * stride;
+            float* dst = rf + (size_t)scanline0 * rows + base + t;
+            const int g_end = n_scanlines - scanline0 < G ? n_scanlines - scanline0 : G;
+            for (int g = 0; g < g_end; g++) {
+                const float* src = rowp + g * S;
                 float sum;
                 if ((S & 3) == 0) {
                     const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -613,7 +616,7 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
                     sum = src[0];
                     for (int s = 1; s < S; s++) sum += src[s];
                 }
-                rf[(size_t)(scanline0 + g) * rows + base + r] = sum;
+                dst[(size_t)g * rows] = sum;
             }
         }
         group_sync();
