@@ -513,7 +513,10 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
                 const double f0 = rowd0 - (double)row0;
                 if (!(fast_rows && f0 >= 1e-6 && f0 <= block_safe_hi && row0 < wend && row0 + MCRT_WIN_UNROLL <= rows && row0 >= base && row0 >= cur_row)) break;
                 uint32_t idx[MCRT_WIN_UNROLL];
-                if (fma_ok) {
+                if (FMADIV) {
+                    // a segment that could leave the range of the 32-bit conversion (never in practice) takes the checked
+                    // single-step path instead: keeps the guarded-reciprocal code out of this kernel's hot loop
+                    if (!fma_ok) break;
 #pragma unroll
                     for (int u = 0; u < MCRT_WIN_UNROLL; u++) { idx[u] = voxel_linear_fma(point, vres, inv_vres); point = v_add(point, delta_step); }
                 } else {
@@ -560,7 +563,7 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
             bool seg_done = false;
             while (true) {
                 if (!(remaining > 0 && time_elapsed < max_travel_time)) { seg_done = true; break; }
-                if (n_safe >= MCRT_WIN_UNROLL) {
+                if (n_safe >= MCRT_WIN_UNROLL && (!FMADIV || fma_ok)) {
                     // back to the block path as soon as a whole block fits this window again
                     const int row_now = __double2int_rd(time_elapsed * inv_row_period);
                     if (fast_rows && row_now < wend && row_now + MCRT_WIN_UNROLL <= rows && row_now >= base) {
