@@ -364,6 +364,21 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate(const Sce
 #define MCRT_WIN_ROWS (MCRT_WIN_RING - MCRT_WIN_UNROLL)
 #define MCRT_WIN_SLOT(row) ((row) & (MCRT_WIN_RING - 1))
 
+// Cold paths of the windowed writer, out of line so the hot loop stays small (instruction-cache footprint matters here:
+// profiles/r01_traversal_ab.txt).  An echo for a row of an already finished window (time ran backwards):
+__device__ __noinline__ void win_late_echo(float* rf_px, float echo, unsigned long long* late_echoes)
+{
+    atomicAdd(rf_px, echo);
+    atomicAdd(late_echoes, 1ULL);
+}
+// ... and for an already closed row of the thread's own column in the current window; returns the new `written`
+__device__ __noinline__ int win_revisit_row(float* my_col, int stride, int base, int written, int cur_row, int row, float echo)
+{
+    for (int r = written > base ? written : base; r < cur_row; r++) my_col[((r) & (MCRT_WIN_RING - 1)) * stride] = 0.0f;
+    my_col[((row) & (MCRT_WIN_RING - 1)) * stride] += echo;
+    return cur_row;
+}
+
 // ring row stride (floats) of a group with T active threads: a multiple of 4 (float4 reduce loads) whose quarter is odd
 // (conflict-free quarter-warp phases for consecutive rows)
 __host__ __device__ __forceinline__ int win_stride(int T) { const int q = (T + 3) / 4; return 4 * (q | 1); }
@@ -450,14 +465,11 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
             }
             if (row >= wend) return false;
             if (row < base) {                                                                   // a finished window: see header
-                atomicAdd(&rf[(size_t)my_scanline * rows + row], echo);
-                atomicAdd(late_echoes, 1ULL);
+                win_late_echo(&rf[(size_t)my_scanline * rows + row], echo, late_echoes);
                 return true;
             }
             if (row < cur_row) {                                                                // revisited row of my own column
-                for (int r = written > base ? written : base; r < cur_row; r++) my_col[MCRT_WIN_SLOT(r) * stride] = 0.0f;
-                written = cur_row;
-                my_col[MCRT_WIN_SLOT(row) * stride] += echo;
+                written = win_revisit_row(my_col, stride, base, written, cur_row, row, echo);
                 return true;
             }
             add_row(echo, row);
@@ -571,7 +583,8 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
                         if (fast_rows && f0 >= 1e-6 && f0 <= block_safe_hi && row_now >= cur_row) break;
                     }
                 }
-                const float2 vox = __ldg(&volume[voxel_linear(point, vres, inv_vres)]);
+                const float2 vox = __ldg(&volume[FMADIV ? (fma_ok ? voxel_linear_fma(point, vres, inv_vres) : voxel_linear_exact(point.x, point.y, point.z, vres))
+                                                         : voxel_linear(point, vres, inv_vres)]);
                 const float scattering = vox.y >= m_mu1 ? vox.x * m_sigma + m_mu0 : 0.0f;
                 if (!try_echo(intensity * scattering, time_elapsed)) { waiting = true; break; }
                 point = v_add(point, delta_step);
