@@ -288,17 +288,23 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const Scen
             } else {
                 p = qin[idx];
             }
-            alive = bounce_path<FIRST>(sc, aq, fr, tb, sh, p, bounce, node_visits, tri_tests, sort_key);
+            if (FIRST) alive = bounce_path<true>(sc, aq, fr, tb, sh, p, bounce, node_visits, tri_tests, sort_key);
+            else alive = true;                                     // traced by the loop below (ONE inlined copy of bounce_path<false>)
         }
-        if (tail) {
-            // finish the path here; counters[b] still receives the number of paths entering bounce b (mcrt_stats.segments)
-            for (int b = bounce + 1; b < aq.max_depth; b++) {
-                const unsigned ma = __ballot_sync(0xffffffffu, alive);
-                if (!ma) break;
-                if ((int)lane == __ffs(ma) - 1) atomicAdd(&tb.counters[b], __popc(ma));
+        if (!FIRST || tail) {
+            // bounce `bounce` (non-first kernels) and, in tail mode, every later bounce of the path; counters[b] still receives
+            // the number of paths entering bounce b (mcrt_stats.segments).  The body is shared so that the kernel holds a single
+            // copy of the ~50 KB bounce code (instruction-cache footprint, profiles/r01_traversal_ab.txt).
+            for (int b = FIRST ? bounce + 1 : bounce; b < aq.max_depth; b++) {
+                if (b > bounce) {
+                    const unsigned ma = __ballot_sync(0xffffffffu, alive);
+                    if (!ma) break;
+                    if ((int)lane == __ffs(ma) - 1) atomicAdd(&tb.counters[b], __popc(ma));
+                }
                 if (alive) alive = bounce_path<false>(sc, aq, fr, tb, sh, p, b, node_visits, tri_tests, sort_key);
+                if (!tail) break;
             }
-            continue;                                               // `tail` is uniform over the launch: no barrier is skipped by part of a CTA
+            if (tail) continue;                                     // `tail` is uniform over the launch: no barrier is skipped by part of a CTA
         }
         if (last) continue;
         const unsigned m = __ballot_sync(0xffffffffu, alive);
