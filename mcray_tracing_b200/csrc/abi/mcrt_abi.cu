@@ -564,8 +564,10 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     SceneDev& sc = c->sc;
     memset(&sc, 0, sizeof(sc));
     {
-        const cudaError_t ce = collapse_bvh4(c->bvh.nodes, c->bvh.n_nodes, &c->d_nodes4, c->stream);
+        int depth4 = 0;
+        const cudaError_t ce = collapse_bvh4(c->bvh.nodes, c->bvh.n_nodes, &c->d_nodes4, c->stream, &depth4);
         if (ce != cudaSuccess) throw CudaError(std::string("collapse_bvh4: ") + cudaGetErrorString(ce));
+        if (3 * depth4 + 1 > MCRT_STACK_DEPTH4) throw std::invalid_argument("4-wide BVH deeper than the traversal stack (degenerate mesh?)");
     }
     sc.nodes = c->bvh.nodes; sc.nodes4 = c->d_nodes4; sc.tris = c->bvh.tris; sc.meshes = c->d_meshes; sc.materials = c->d_materials;
     sc.n_tri = c->bvh.n_tri; sc.n_mesh = (int)hs.meshes.size(); sc.n_mat = (int)hs.materials.size();
@@ -832,8 +834,10 @@ static void rebuild_bvh(mcrt_ctx* c)
     if (nb.max_depth > MCRT_TRAVERSAL_STACK) { cudaFree(nb.nodes); cudaFree(nb.tris); throw std::invalid_argument("BVH deeper than the traversal stack"); }
     Bvh4Node* n4 = nullptr;
     {
-        const cudaError_t ce = collapse_bvh4(nb.nodes, nb.n_nodes, &n4, c->stream);
+        int depth4 = 0;
+        const cudaError_t ce = collapse_bvh4(nb.nodes, nb.n_nodes, &n4, c->stream, &depth4);
         if (ce != cudaSuccess) { cudaFree(nb.nodes); cudaFree(nb.tris); throw CudaError(std::string("collapse_bvh4: ") + cudaGetErrorString(ce)); }
+        if (3 * depth4 + 1 > MCRT_STACK_DEPTH4) { cudaFree(nb.nodes); cudaFree(nb.tris); cudaFree(n4); throw std::invalid_argument("4-wide BVH deeper than the traversal stack"); }
     }
     dev_free(c->bvh.nodes); dev_free(c->bvh.tris); dev_free(c->d_nodes4);
     c->bvh = nb;

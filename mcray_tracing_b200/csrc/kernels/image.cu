@@ -396,7 +396,6 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
     const int S = aq.samples, rows = aq.rows;
     const int T = G * S;                                   // active threads of a group
     const int stride = win_stride(T);
-    const int group_size = WARP ? 32 : 128;
     const int group = WARP ? (int)(blockIdx.x * 4 + (threadIdx.x >> 5)) : (int)blockIdx.x;
     const int t = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;          // index within the group
     float* const s_win = reinterpret_cast<float*>(s_win4) + (WARP ? (size_t)(threadIdx.x >> 5) * MCRT_WIN_RING * stride : 0);

@@ -9,6 +9,9 @@
 // 48-byte triangle slots.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <utility>
+#include <vector>
+
 #include "mcrt_device.cuh"
 #include "mcrt_launch.h"
 
@@ -205,29 +208,50 @@ __global__ void k_emit_tris(const unsigned int* __restrict__ vals, const float* 
     slots[k] = s;
 }
 
-// BVH2 -> BVH4: node i takes, for each of its two children, the child itself if it is a leaf, else the child's two
-// children.  Built for EVERY inner BVH2 node (the traversal only ever reaches the even-depth ones from the root), so no
-// depth information is needed and the same kernel serves the device LBVH and the host SAH tree.
-__global__ void k_collapse_bvh4(const BvhNode* __restrict__ nodes2, const int n_nodes, Bvh4Node* __restrict__ nodes4)
+// BVH2 -> BVH4.  Node i starts from its two BVH2 children and, twice, replaces the inner child with the LARGEST surface area by
+// that child's two children (greedy surface-area collapse: the big boxes, which rays hit most often, are the ones opened up;
+// MCRT_BVH4_GREEDY=0 gives the fixed shape "each child replaced by its children").  Built for EVERY inner BVH2 node -- any
+// inner descendant can then be referenced as a child -- so no depth information is needed and the same kernel serves the
+// device LBVH and the host SAH tree.
+#ifndef MCRT_BVH4_GREEDY
+#define MCRT_BVH4_GREEDY 1
+#endif
+__global__ void k_collapse_bvh4(const BvhNode* __restrict__ nodes2, const int n_nodes, Bvh4Node* __restrict__ nodes4, const int greedy)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     float lo[4][3], hi[4][3];
     int child[4];
     int n = 0;
-    auto put = [&](float lx, float ly, float lz, float hx, float hy, float hz, int ref) {
-        lo[n][0] = lx; lo[n][1] = ly; lo[n][2] = lz; hi[n][0] = hx; hi[n][1] = hy; hi[n][2] = hz; child[n] = ref; n++;
-    };
-    auto expand = [&](float lx, float ly, float lz, float hx, float hy, float hz, int ref) {
-        if (ref < 0) { put(lx, ly, lz, hx, hy, hz, ref); return; }
-        const BvhNode c = nodes2[ref];
-        put(c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y, c.d.x);
-        put(c.b.z, c.b.w, c.c.x, c.c.y, c.c.z, c.c.w, c.d.y);
+    auto put = [&](int at, float lx, float ly, float lz, float hx, float hy, float hz, int ref) {
+        lo[at][0] = lx; lo[at][1] = ly; lo[at][2] = lz; hi[at][0] = hx; hi[at][1] = hy; hi[at][2] = hz; child[at] = ref;
     };
     const BvhNode nd = nodes2[i];
-    expand(nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y, nd.d.x);
-    expand(nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w, nd.d.y);
-    for (; n < 4;) { lo[n][0] = lo[n][1] = lo[n][2] = 3.0e38f; hi[n][0] = hi[n][1] = hi[n][2] = -3.0e38f; child[n] = MCRT_BVH4_EMPTY; n++; }
+    put(0, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y, nd.d.x);
+    put(1, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w, nd.d.y);
+    n = 2;
+    if (greedy) {
+    for (int round = 0; round < 2; round++) {
+        int pick = -1;
+        float best = -1.0f;
+        for (int k = 0; k < n; k++) {
+            if (child[k] < 0) continue;                      // leaves cannot be opened
+            const float dx = hi[k][0] - lo[k][0], dy = hi[k][1] - lo[k][1], dz = hi[k][2] - lo[k][2];
+            const float area = dx * dy + dy * dz + dz * dx;
+            if (area > best) { best = area; pick = k; }
+        }
+        if (pick < 0) break;
+        const BvhNode c = nodes2[child[pick]];
+        put(pick, c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y, c.d.x);
+        put(n, c.b.z, c.b.w, c.c.x, c.c.y, c.c.z, c.c.w, c.d.y);
+        n++;
+    }
+    } else {
+        const int r0 = child[0], r1 = child[1];
+        if (r1 >= 0) { const BvhNode c = nodes2[r1]; put(1, c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y, c.d.x); put(n, c.b.z, c.b.w, c.c.x, c.c.y, c.c.z, c.c.w, c.d.y); n++; }
+        if (r0 >= 0) { const BvhNode c = nodes2[r0]; put(0, c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y, c.d.x); put(n, c.b.z, c.b.w, c.c.x, c.c.y, c.c.z, c.c.w, c.d.y); n++; }
+    }
+    for (; n < 4; n++) { lo[n][0] = lo[n][1] = lo[n][2] = 3.0e38f; hi[n][0] = hi[n][1] = hi[n][2] = -3.0e38f; child[n] = MCRT_BVH4_EMPTY; }
     Bvh4Node o;
     o.lox = make_float4(lo[0][0], lo[1][0], lo[2][0], lo[3][0]); o.loy = make_float4(lo[0][1], lo[1][1], lo[2][1], lo[3][1]);
     o.loz = make_float4(lo[0][2], lo[1][2], lo[2][2], lo[3][2]);
@@ -240,17 +264,44 @@ __global__ void k_collapse_bvh4(const BvhNode* __restrict__ nodes2, const int n_
 
 }  // namespace
 
-cudaError_t collapse_bvh4(const BvhNode* d_nodes2, int n_nodes, Bvh4Node** d_nodes4_out, cudaStream_t stream)
+static int bvh4_depth(const std::vector<Bvh4Node>& h)
+{
+    std::vector<std::pair<int, int>> stack;          // (node, depth)
+    stack.emplace_back(0, 1);
+    int deepest = 0;
+    while (!stack.empty()) {
+        const std::pair<int, int> top = stack.back();
+        stack.pop_back();
+        if (top.second > deepest) deepest = top.second;
+        const int c[4] = {h[top.first].child.x, h[top.first].child.y, h[top.first].child.z, h[top.first].child.w};
+        for (int k = 0; k < 4; k++)
+            if (c[k] >= 0 && c[k] != MCRT_BVH4_EMPTY) stack.emplace_back(c[k], top.second + 1);
+    }
+    return deepest;
+}
+
+// Greedy collapse first; if its longest root-to-leaf chain does not fit the traversal stack (3 pushes per level), the fixed-shape
+// collapse (half the BVH2 depth) is used instead.  *depth4_out = the chain length of the tree that was kept.
+cudaError_t collapse_bvh4(const BvhNode* d_nodes2, int n_nodes, Bvh4Node** d_nodes4_out, cudaStream_t stream, int* depth4_out)
 {
     *d_nodes4_out = nullptr;
+    if (depth4_out) *depth4_out = 0;
     if (n_nodes <= 0) return cudaSuccess;
     Bvh4Node* d4 = nullptr;
     cudaError_t e = cudaMalloc(&d4, sizeof(Bvh4Node) * (size_t)n_nodes);
     if (e != cudaSuccess) return e;
-    k_collapse_bvh4<<<(n_nodes + 255) / 256, 256, 0, stream>>>(d_nodes2, n_nodes, d4);
-    e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    if (e != cudaSuccess) { cudaFree(d4); return e; }
+    std::vector<Bvh4Node> h((size_t)n_nodes);
+    int depth = 0;
+    for (int greedy = MCRT_BVH4_GREEDY; greedy >= 0; greedy--) {
+        k_collapse_bvh4<<<(n_nodes + 255) / 256, 256, 0, stream>>>(d_nodes2, n_nodes, d4, greedy);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess) e = cudaMemcpy(h.data(), d4, sizeof(Bvh4Node) * (size_t)n_nodes, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { cudaFree(d4); return e; }
+        depth = bvh4_depth(h);                             // start-up only
+        if (3 * depth + 1 <= MCRT_STACK_DEPTH4) break;
+    }
+    if (depth4_out) *depth4_out = depth;
     *d_nodes4_out = d4;
     return cudaSuccess;
 }

@@ -18,7 +18,8 @@ struct LbvhResult {
 };
 #define MCRT_TRAVERSAL_STACK 62      // BVH2 stack 64; the 4-wide traversal needs 3 * ceil(depth / 2) + 2 <= 96
 // 4-wide copy of a BVH2 node array (device LBVH or uploaded host SAH tree); caller frees *d_nodes4_out with cudaFree
-cudaError_t collapse_bvh4(const BvhNode* d_nodes2, int n_nodes, Bvh4Node** d_nodes4_out, cudaStream_t stream);
+// *depth4_out (nullable): longest chain of BVH4 nodes from the root; the traversal needs 3 * depth4 + 1 <= MCRT_STACK_DEPTH4
+cudaError_t collapse_bvh4(const BvhNode* d_nodes2, int n_nodes, Bvh4Node** d_nodes4_out, cudaStream_t stream, int* depth4_out = nullptr);
 
 // builds the device BVH from host triangle data; d_meshes must already be on the device
 cudaError_t build_lbvh(const float* h_tri_local, const int32_t* h_tri_mesh, int n_tri, const DevMesh* d_meshes, cudaStream_t stream,
