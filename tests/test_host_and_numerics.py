@@ -328,3 +328,17 @@ def test_psf_of_delta_and_envelope_of_sinusoid(O):
     env = O.envelope(col)
     inner = env[8:380, 0]
     assert inner.min() > 0.99 and inner.max() < 1.0 + 1e-6                 # envelope of a unit sinusoid ~ 1 between its peaks
+
+
+# ---- the headless CLI's argument and error behaviour (no GPU needed: it fails before any CUDA call) ------------------------
+def test_cli_argument_and_scene_errors(api, tmp_path):
+    """`mattausch` keeps the reference's messages: wrong argument list -> "Incorrect argument list." and exit code 0
+    (main.cpp:46-50); an unloadable scene -> "The program found an error and will terminate." + the scene.cpp:23-26 reason."""
+    exe = Path(api.__file__).resolve().parent / "mattausch"
+    assert exe.exists()
+    for argv in ([], ["--frames", "2"], [str(tmp_path / "x.scene"), "--no-such-flag"]):
+        out = subprocess.run([str(exe)] + argv, capture_output=True, text=True, timeout=60)
+        assert out.returncode == 0 and out.stdout.strip() == "Incorrect argument list.", (argv, out.stdout, out.stderr)
+    out = subprocess.run([str(exe), str(tmp_path / "missing.scene")], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0
+    assert "The program found an error and will terminate." in out.stdout and "Error while loading scene" in out.stdout
