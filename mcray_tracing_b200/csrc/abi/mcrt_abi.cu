@@ -133,7 +133,7 @@ struct mcrt_ctx {
     bool log_compress = false;             // rfimage.h:127-136, commented out in the reference
     int* d_max_bits = nullptr;             // [cap_poses] per-image maximum (ordered-int encoding)
     int first_hit_dedup = 1;               // bounce 0 traced once per element (TraceBuffers::first_hits) when samples >= 4: 0 off, 1 large calls, 2 always
-    int ordered_compaction = 1;            // order-preserving compaction between bounces (TraceBuffers::chunk_prefix_a): 0 off, 1 large calls, 2 always
+    int ordered_compaction = 1;            // order-preserving compaction between bounces (TraceBuffers::warp_counts): 0 off, 1 large calls, 2 always
     bool coherence_sort = false;           // radix-sort surviving paths between bounces (rough scenes)
     float* d_rf_acc = nullptr;
     float* d_rf_tmp0 = nullptr;
@@ -183,7 +183,7 @@ void free_workspace(mcrt_ctx* c)
     dev_free(c->tb.segments); dev_free(c->tb.n_segments); dev_free(c->tb.hit_fraction); dev_free(c->tb.hit_mesh);
     dev_free(c->tb.queue_a); dev_free(c->tb.queue_b); dev_free(c->tb.counters);
     dev_free(c->tb.sort_keys); dev_free(c->tb.sort_keys_tmp); dev_free(c->tb.sort_queue_tmp);
-    dev_free(c->tb.chunk_prefix_a); dev_free(c->tb.chunk_prefix_b); dev_free(c->tb.n_chunks); dev_free(c->tb.first_hits);
+    dev_free(c->tb.warp_counts); dev_free(c->tb.tile_counts); c->tb.n_tiles = 0; dev_free(c->tb.first_hits);
     dev_free(c->tree.rays_a); dev_free(c->tree.rays_b); dev_free(c->tree.segments); dev_free(c->tree.keys); dev_free(c->tree.keys_sorted);
     dev_free(c->tree.slots); dev_free(c->tree.slots_sorted); dev_free(c->tree.path_first); dev_free(c->tree.path_count); dev_free(c->tree.counters);
     if (c->tree.sort_tmp) cudaFree(c->tree.sort_tmp);
@@ -239,9 +239,10 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
     c->tb.trav_counters = c->count_traversal ? c->d_trav : nullptr;
     if (c->first_hit_dedup && c->aq.samples >= 4) dev_alloc(c->tb.first_hits, 2 * (size_t)n_poses * c->aq.elements);
     if (c->ordered_compaction) {
-        const size_t n_chunks = (n_paths + 127) / 128 + 2;
-        dev_alloc(c->tb.chunk_prefix_a, n_chunks); dev_alloc(c->tb.chunk_prefix_b, n_chunks);
-        dev_alloc(c->tb.n_chunks, (size_t)c->aq.max_depth + 1);
+        const size_t n_chunks = (n_paths + 31) / 32;
+        c->tb.n_tiles = (int)((n_chunks + 255) / 256);
+        dev_alloc(c->tb.warp_counts, n_chunks + 1);
+        dev_alloc(c->tb.tile_counts, (size_t)c->aq.max_depth * c->tb.n_tiles);
     }
     if (c->coherence_sort) {
         dev_alloc(c->tb.sort_keys, n_paths); dev_alloc(c->tb.sort_keys_tmp, n_paths); dev_alloc(c->tb.sort_queue_tmp, n_paths);
@@ -269,7 +270,7 @@ void enqueue_trace(mcrt_ctx* c, int pose0, int n, int slot, cudaStream_t s, int*
     // sub-batches keep the atomic compaction; small calls too (the 9 extra scan launches cost more than the order returns:
     // +1.6 % frames/s at 256 frames per call, profiles/r01o_ab_ordered.txt)
     if (pose0 != 0 || slot != 0 || c->coherence_sort || (c->ordered_compaction == 1 && (int64_t)n * c->aq.elements * c->aq.samples < kOrderedMinPaths)) {
-        tb.chunk_prefix_a = nullptr; tb.chunk_prefix_b = nullptr; tb.n_chunks = nullptr;
+        tb.warp_counts = nullptr; tb.tile_counts = nullptr; tb.n_tiles = 0;
     }
     if (tb.sort_keys) { tb.sort_keys += p0; tb.sort_keys_tmp += p0; tb.sort_queue_tmp += p0; }
     tb.counters += (size_t)slot * (c->aq.max_depth + 1);

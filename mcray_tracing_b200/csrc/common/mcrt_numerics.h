@@ -8,10 +8,11 @@
 // are not.  Every transcendental the reference's hot path calls
 //   std::exp(float)  ray.cpp:102, main.cpp:135      std::log(float)  ray.cpp:112
 //   std::pow         ray.cpp:131,158,160,223        sin/cos (double) ray.cpp:181-182
-// is therefore implemented here once, in plain IEEE double arithmetic (+,-,*,/ only), and
-// rounded to float where the reference rounds to float.  The double result has <= ~2 ulp(double)
-// error, so the float rounding equals the correctly-rounded value except with probability
-// ~2^-28 per call; tests/test_numerics.py pins these against glibc.
+// is therefore implemented here once, in plain IEEE double arithmetic (+,-,*,/, floor and the
+// explicitly written IEEE fused multiply-add -- all correctly rounded, hence identical on both
+// sides), and rounded to float where the reference rounds to float.  The double result has
+// <= ~1 ulp(double) error, so the float rounding equals the correctly-rounded value except with
+// probability ~2^-28 per call; tests/test_host_and_numerics.py pins these against glibc.
 //
 // Also here: the counter-based Philox4x32-10 generator that replaces the reference's
 // per-call std::random_device + std::mt19937 (scene.cpp:132-135, ray.cpp:85-88,175-179,216-219).
@@ -92,8 +93,23 @@ MCRT_HD double mc_scale2(double p, int k)
 }
 
 // ----------------------------------------------------------------------------------------------
-// exp / log / pow in double, built from IEEE basic operations only
+// exp / log / pow in double, built from IEEE basic operations and the IEEE fused multiply-add
 // ----------------------------------------------------------------------------------------------
+// fma(a, b, c) is an IEEE-754 operation (one rounding): __fma_rn on the device and the hardware / libm fma on the host
+// return the same bits, so using it EXPLICITLY keeps the contract (what is forbidden is the compiler contracting a
+// separate multiply and add behind our back: -fmad=false / -ffp-contract=off stay).  Round 2: the polynomial cores
+// below are near-minimax fits (scripts/gen_numerics_coeffs.py, mpmath) evaluated with FMAs in two interleaved
+// Horner chains -- half the fp64 operations and a third of the dependent-chain depth of the round-1 Taylor/Horner
+// forms, which made the shading phase of the trace kernels wait on the fp64 pipe (profiles/r02*_numerics*).
+MCRT_HD double mc_fma(double a, double b, double c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
+
 MCRT_HD double mc_exp(double x)
 {
     if (x != x) return x;
@@ -101,24 +117,19 @@ MCRT_HD double mc_exp(double x)
     if (x < -745.2) return 0.0;
     const double LN2_HI = 6.93147180369123816490e-01;  // 0x3fe62e42fee00000, 32 significant bits
     const double LN2_LO = 1.90821492927058770002e-10;
-    const double kf = floor(x * 1.44269504088896338700e+00 + 0.5);
-    const double r = (x - kf * LN2_HI) - kf * LN2_LO;   // |r| <= 0.3466
-    // Taylor/Horner, degree 14: remainder < 5e-18
-    double p = 1.0 / 87178291200.0;
-    p = p * r + 1.0 / 6227020800.0;
-    p = p * r + 1.0 / 479001600.0;
-    p = p * r + 1.0 / 39916800.0;
-    p = p * r + 1.0 / 3628800.0;
-    p = p * r + 1.0 / 362880.0;
-    p = p * r + 1.0 / 40320.0;
-    p = p * r + 1.0 / 5040.0;
-    p = p * r + 1.0 / 720.0;
-    p = p * r + 1.0 / 120.0;
-    p = p * r + 1.0 / 24.0;
-    p = p * r + 1.0 / 6.0;
-    p = p * r + 0.5;
-    p = p * r + 1.0;
-    p = p * r + 1.0;
+    const double kf = floor(mc_fma(x, 1.44269504088896338700e+00, 0.5));
+    const double r = mc_fma(-kf, LN2_LO, mc_fma(-kf, LN2_HI, x));   // |r| <= ln2/2 (+ rounding)
+    // exp(r) = 1 + r + r^2 G(r); G = degree-9 near-minimax on |r| <= 0.34661: relative error of the sum < 1.7e-17
+    const double G0 = 0x1.0000000000001p-1, G1 = 0x1.5555555555556p-3, G2 = 0x1.5555555553d63p-5, G3 = 0x1.11111111109b3p-7,
+                 G4 = 0x1.6c16c1788bd90p-10, G5 = 0x1.a01a01a7c41d5p-13, G6 = 0x1.a019b90d2ae7ap-16, G7 = 0x1.71de0dae63bb3p-19,
+                 G8 = 0x1.289185613a3d6p-22, G9 = 0x1.af38a9b0ec855p-26;
+    const double w = r * r;
+    double ge = mc_fma(w, G8, G6), go = mc_fma(w, G9, G7);          // G(r) = ge(w) + r go(w)
+    ge = mc_fma(w, ge, G4); go = mc_fma(w, go, G5);
+    ge = mc_fma(w, ge, G2); go = mc_fma(w, go, G3);
+    ge = mc_fma(w, ge, G0); go = mc_fma(w, go, G1);
+    const double g = mc_fma(r, go, ge);
+    const double p = mc_fma(w, g, r) + 1.0;
     return mc_scale2(p, (int)kf);
 }
 
@@ -141,26 +152,20 @@ MCRT_HD double mc_log(double x)
     const double f = m - 1.0;
     const double s = f / (2.0 + f);     // |s| <= 0.1716
     const double z = s * s;
-    // log(m) = 2s (1 + z/3 + z^2/5 + ... + z^12/25): remainder < 1e-19
-    double t = 1.0 / 25.0;
-    t = t * z + 1.0 / 23.0;
-    t = t * z + 1.0 / 21.0;
-    t = t * z + 1.0 / 19.0;
-    t = t * z + 1.0 / 17.0;
-    t = t * z + 1.0 / 15.0;
-    t = t * z + 1.0 / 13.0;
-    t = t * z + 1.0 / 11.0;
-    t = t * z + 1.0 / 9.0;
-    t = t * z + 1.0 / 7.0;
-    t = t * z + 1.0 / 5.0;
-    t = t * z + 1.0 / 3.0;
-    t = t * z;
+    // log(m) = 2 atanh(s) = 2s (1 + z Q(z)); Q = degree-6 near-minimax on z <= 0.029438: error of the bracket < 4.7e-18
+    const double L0 = 0x1.5555555555558p-2, L1 = 0x1.99999999952d7p-3, L2 = 0x1.2492492df281ap-3, L3 = 0x1.c71c62e3f11e6p-4,
+                 L4 = 0x1.7462b51cb66b1p-4, L5 = 0x1.39fe51a7c18f9p-4, L6 = 0x1.2b5900de53b32p-4;
+    const double w = z * z;
+    double qe = mc_fma(w, L6, L4), qo = mc_fma(w, L5, L3);          // Q(z) = qe(w) + z qo(w)
+    qe = mc_fma(w, qe, L2); qo = mc_fma(w, qo, L1);
+    qe = mc_fma(w, qe, L0);
+    const double t = z * mc_fma(z, qo, qe);
     const double s2 = s + s;
-    const double logm = s2 + s2 * t;
+    const double logm = mc_fma(s2, t, s2);
     const double LN2_HI = 6.93147180369123816490e-01;
     const double LN2_LO = 1.90821492927058770002e-10;
     const double ef = (double)e;
-    return ef * LN2_HI + (logm + ef * LN2_LO);
+    return mc_fma(ef, LN2_HI, mc_fma(ef, LN2_LO, logm));
 }
 
 // pow(x,y) with the C99 special cases the hot path can reach.
@@ -208,33 +213,19 @@ MCRT_HD void mc_sincos(double a, double* sn, double* cs)
 {
     const double PIO2_HI = 1.57079632673412561417e+00;   // first 33 bits of pi/2
     const double PIO2_LO = 6.07710050650619224932e-11;
-    const double kf = floor(a * 6.36619772367581382433e-01 + 0.5);
-    const double r = (a - kf * PIO2_HI) - kf * PIO2_LO;  // |r| <= pi/4 (+eps)
-    const double z = r * r;
-    // sin(r) = r (1 - z/3! + z^2/5! - ... + z^9/19!)
-    double ps = 1.0 / 121645100408832000.0;
-    ps = -ps * z + 1.0 / 355687428096000.0;
-    ps = -ps * z + 1.0 / 1307674368000.0;
-    ps = -ps * z + 1.0 / 6227020800.0;
-    ps = -ps * z + 1.0 / 39916800.0;
-    ps = -ps * z + 1.0 / 362880.0;
-    ps = -ps * z + 1.0 / 5040.0;
-    ps = -ps * z + 1.0 / 120.0;
-    ps = -ps * z + 1.0 / 6.0;
-    ps = -ps * z + 1.0;
-    const double sr = r * ps;
-    // cos(r) = 1 - z/2! + z^2/4! - ... + z^9/18!
-    double pc = 1.0 / 6402373705728000.0;
-    pc = -pc * z + 1.0 / 20922789888000.0;
-    pc = -pc * z + 1.0 / 87178291200.0;
-    pc = -pc * z + 1.0 / 479001600.0;
-    pc = -pc * z + 1.0 / 3628800.0;
-    pc = -pc * z + 1.0 / 40320.0;
-    pc = -pc * z + 1.0 / 720.0;
-    pc = -pc * z + 1.0 / 24.0;
-    pc = -pc * z + 0.5;
-    pc = -pc * z + 1.0;
-    const double cr = pc;
+    const double kf = floor(mc_fma(a, 6.36619772367581382433e-01, 0.5));
+    const double r = mc_fma(-kf, PIO2_LO, mc_fma(-kf, PIO2_HI, a));  // |r| <= pi/4 (+ rounding)
+    const double z = r * r, w = z * z;
+    // sin(r) = r + r z S(z), cos(r) = 1 - z/2 + z^2 C(z); S, C = degree-5 near-minimax on z <= (pi/4)^2:
+    // absolute errors < 1.4e-17 and < 9e-19 before rounding
+    const double S0 = -0x1.5555555555555p-3, S1 = 0x1.1111111110bb1p-7, S2 = -0x1.a01a019e8357dp-13, S3 = 0x1.71de37961e4c6p-19,
+                 S4 = -0x1.ae600a926c89ap-26, S5 = 0x1.5e0af186af739p-33;
+    const double C0 = 0x1.5555555555555p-5, C1 = -0x1.6c16c16c16966p-10, C2 = 0x1.a01a019f4e867p-16, C3 = -0x1.27e4fa17a41b4p-22,
+                 C4 = 0x1.1eeb68b109173p-29, C5 = -0x1.907d7aebd5e3dp-37;
+    double se = mc_fma(w, S4, S2), so = mc_fma(w, S5, S3), ce = mc_fma(w, C4, C2), co = mc_fma(w, C5, C3);
+    se = mc_fma(w, se, S0); so = mc_fma(w, so, S1); ce = mc_fma(w, ce, C0); co = mc_fma(w, co, C1);
+    const double sr = mc_fma(r * z, mc_fma(z, so, se), r);
+    const double cr = mc_fma(w, mc_fma(z, co, ce), mc_fma(-0.5, z, 1.0));
     // quadrant
     const double q4 = kf - 4.0 * floor(kf * 0.25);
     const int q = (int)q4;

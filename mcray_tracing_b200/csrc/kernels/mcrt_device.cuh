@@ -357,21 +357,24 @@ __device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __
 #if MCRT_BVH4 && MCRT_BOX_FMA
     {
         // 4-wide traversal: half the dependent node fetches of the BVH2 loop below.  Near / far planes are picked by address.
-        const char* base = reinterpret_cast<const char*>(sc.nodes4);
-        const int onx = rb.px ? 0 : 48, ofx = rb.px ? 48 : 0;            // byte offsets of lox / hix
-        const int ony = rb.py ? 16 : 64, ofy = rb.py ? 64 : 16;
-        const int onz = rb.pz ? 32 : 80, ofz = rb.pz ? 80 : 32;
+        // A node is 128-byte aligned and the plane offsets are < 128, so (node address | offset) == (node address + offset):
+        // ONE 64-bit multiply-add forms the node address and each of the seven loads only ORs its offset into the low word
+        // (was: a 64-bit add per load, 21 of the ~135 instructions of a node visit).
+        const unsigned long long base = (unsigned long long)reinterpret_cast<uintptr_t>(sc.nodes4);
+        const unsigned onx = rb.px ? 0u : 48u, ofx = rb.px ? 48u : 0u;   // byte offsets of lox / hix
+        const unsigned ony = rb.py ? 16u : 64u, ofy = rb.py ? 64u : 16u;
+        const unsigned onz = rb.pz ? 32u : 80u, ofz = rb.pz ? 80u : 32u;
         int stack4[MCRT_STACK_DEPTH4];
         int sp4 = 0;
         int node4 = 0;
         while (true) {
             if (node4 >= 0) {
                 node_visits++;
-                const char* nd = base + (size_t)node4 * sizeof(Bvh4Node);
-                const float4 nx = __ldg(reinterpret_cast<const float4*>(nd + onx)), fx = __ldg(reinterpret_cast<const float4*>(nd + ofx));
-                const float4 ny = __ldg(reinterpret_cast<const float4*>(nd + ony)), fy = __ldg(reinterpret_cast<const float4*>(nd + ofy));
-                const float4 nz = __ldg(reinterpret_cast<const float4*>(nd + onz)), fz = __ldg(reinterpret_cast<const float4*>(nd + ofz));
-                const int4 ch = __ldg(reinterpret_cast<const int4*>(nd + 96));
+                const unsigned long long nd = base + (unsigned long long)(unsigned)node4 * (unsigned long long)sizeof(Bvh4Node);
+                const float4 nx = __ldg(reinterpret_cast<const float4*>(nd | onx)), fx = __ldg(reinterpret_cast<const float4*>(nd | ofx));
+                const float4 ny = __ldg(reinterpret_cast<const float4*>(nd | ony)), fy = __ldg(reinterpret_cast<const float4*>(nd | ofy));
+                const float4 nz = __ldg(reinterpret_cast<const float4*>(nd | onz)), fz = __ldg(reinterpret_cast<const float4*>(nd | ofz));
+                const int4 ch = __ldg(reinterpret_cast<const int4*>(nd) + 6);
                 const float tb = best.fraction * 1.000002f;
                 float t[4];
                 int c[4] = {ch.x, ch.y, ch.z, ch.w};

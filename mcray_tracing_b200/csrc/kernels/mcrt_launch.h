@@ -51,13 +51,15 @@ struct TraceBuffers {
     int* sort_queue_tmp;           // [n_paths]
     void* sort_tmp;                // cub temporary storage
     size_t sort_tmp_bytes;
-    // optional order-preserving compaction (nullptr = off): every 128-path chunk compacts its survivors into its own slot
-    // of queue_a/queue_b and records how many; k_scan_chunks turns the counts into an exclusive prefix and the next bounce
-    // finds path idx by a binary search over it.  Survivors stay sorted by (pose, element, sample), so the lanes of a warp
-    // keep tracing neighbouring rays instead of pieces of unrelated warps glued together by atomic order.
-    int* chunk_prefix_a;           // [ceil(n_paths / 128) + 1]
-    int* chunk_prefix_b;
-    int* n_chunks;                 // [max_depth + 1]: chunks written by bounce b - 1 = entries of the prefix bounce b reads
+    // optional order-preserving compaction (nullptr = off): queue_a is the dense queue every bounce reads, queue_b the sparse
+    // one it writes -- every warp compacts the survivors of its 32 paths into its own 32 slots and records how many (no CTA
+    // barrier); k_compact then packs the sparse queue into the dense one.  Survivors stay sorted by (pose, element, sample),
+    // so the lanes of a warp keep tracing neighbouring rays instead of pieces of unrelated warps glued together by atomic
+    // order.  (Round 1 compacted per 128-path CTA chunk behind two CTA barriers and looked paths up by binary search over a
+    // chunk prefix: 15 % + 9 % of the bounce kernels' stall samples, profiles/r02a_k_bounce_hot_lines.txt.)
+    int* warp_counts;              // [ceil(n_paths / 32)]: survivors of warp chunk w of the current bounce
+    int* tile_counts;              // [max_depth][n_tiles]: survivors per tile of 256 warp chunks (8192 paths)
+    int n_tiles;
     // optional (nullptr = off): closest hit of bounce 0 per (pose, element).  All samples of an element leave the transducer
     // on the same ray (scene.cpp:84-100), so k_first_hit traces it once and bounce 0 only shades: 2 float4 per element =
     // (fraction, tri_id, mesh, dist_a), (n_raw.xyz, -)

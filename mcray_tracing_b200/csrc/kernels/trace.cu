@@ -245,18 +245,17 @@ __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq
 #ifndef MCRT_BOUNCE_MIN_CTAS
 #define MCRT_BOUNCE_MIN_CTAS 6      // 80 registers, 24 warps/SM: measured best of 4/5/6/8 (profiles/r01_traversal_ab.txt)
 #endif
-// ORDERED: order-preserving compaction (see TraceBuffers::chunk_prefix_a); otherwise survivors are appended to the next
-// queue with one warp-aggregated atomicAdd per warp.
+// ORDERED: order-preserving compaction (see TraceBuffers::warp_counts): every warp compacts its survivors into its own
+// 32-slot piece of the sparse queue and records how many, k_compact turns that into the dense queue of the next bounce.
+// Otherwise survivors are appended to the next queue with one warp-aggregated atomicAdd per warp.
 template <bool FIRST, bool ORDERED>
 __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const SceneDev sc, const AcqDev aq, const FrameDev fr, const TraceBuffers tb, const int bounce)
 {
     __shared__ SharedScene sh;
-    __shared__ int s_wcount[4];
     load_shared_scene(sc, sh);
-    const int* __restrict__ qin = (bounce & 1) ? tb.queue_b : tb.queue_a;
-    int* __restrict__ qout = (bounce & 1) ? tb.queue_a : tb.queue_b;
-    const int* __restrict__ pin = (bounce & 1) ? tb.chunk_prefix_b : tb.chunk_prefix_a;     // ORDERED only
-    int* __restrict__ pout = (bounce & 1) ? tb.chunk_prefix_a : tb.chunk_prefix_b;
+    // ORDERED: queue_a is always the dense input queue, queue_b the sparse output (k_compact runs between the bounces)
+    const int* __restrict__ qin = ORDERED ? tb.queue_a : ((bounce & 1) ? tb.queue_b : tb.queue_a);
+    int* __restrict__ qout = ORDERED ? tb.queue_b : ((bounce & 1) ? tb.queue_a : tb.queue_b);
     // Tail merge: the late bounces have few live paths and each launch costs the latency of one full bounce (~40 us) however
     // few they are.  Once at most tail_threshold paths (one resident wave) are alive, THIS launch walks each of them to its
     // end in-thread (no compaction between the merged bounces) and the remaining bounce launches return immediately.
@@ -265,8 +264,7 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const Scen
     const int n_in = FIRST ? fr.n_poses * aq.elements * aq.samples : tb.counters[bounce];
     const bool tail = tb.tail_threshold > 0 && n_in <= tb.tail_threshold && bounce + 1 < aq.max_depth;
     if (tail && blockIdx.x == 0 && threadIdx.x == 0) tb.counters[aq.max_depth] = bounce + 1;
-    const int n_round = ORDERED ? (n_in + 127) & ~127 : (n_in + 31) & ~31;
-    const int n_chunks_in = (ORDERED && !FIRST) ? tb.n_chunks[bounce] : 0;
+    const int n_round = (n_in + 31) & ~31;
     const unsigned lane = threadIdx.x & 31;
     const bool last = bounce + 1 >= aq.max_depth;
     int node_visits = 0, tri_tests = 0;
@@ -275,19 +273,7 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const Scen
         bool alive = false;
         unsigned sort_key = 0u;
         if (idx < n_in) {
-            if (FIRST) {
-                p = idx;
-            } else if (ORDERED) {
-                // largest chunk c with prefix[c] <= idx (prefix[n_chunks_in] = n_in > idx)
-                int lo = 0, hi = n_chunks_in;
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (__ldg(&pin[mid]) <= idx) lo = mid; else hi = mid;
-                }
-                p = qin[lo * 128 + (idx - __ldg(&pin[lo]))];
-            } else {
-                p = qin[idx];
-            }
+            p = FIRST ? idx : qin[idx];
             if (FIRST) alive = bounce_path<true>(sc, aq, fr, tb, sh, p, bounce, node_visits, tri_tests, sort_key);
             else alive = true;                                     // traced by the loop below (ONE inlined copy of bounce_path<false>)
         }
@@ -309,17 +295,14 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const Scen
         if (last) continue;
         const unsigned m = __ballot_sync(0xffffffffu, alive);
         if (ORDERED) {
-            // the CTA's 128 paths of this iteration are one chunk: compact into the chunk's own slot, in order
-            const int warp = threadIdx.x >> 5;
-            if (lane == 0) s_wcount[warp] = __popc(m);
-            __syncthreads();
-            int base = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < 4; w++) { const int cw = s_wcount[w]; if (w < warp) base += cw; total += cw; }
-            const int chunk = idx >> 7;
-            if (alive) qout[chunk * 128 + base + __popc(m & ((1u << lane) - 1u))] = p;
-            if (threadIdx.x == 0) pout[chunk] = total;
-            __syncthreads();
+            // the warp's 32 paths of this iteration are one chunk (idx is warp-aligned): compact them into the chunk's own
+            // 32 slots, in order -- no CTA barrier, nobody waits for a slower warp
+            const int chunk = idx >> 5;
+            if (alive) qout[chunk * 32 + __popc(m & ((1u << lane) - 1u))] = p;
+            if (lane == 0) {
+                tb.warp_counts[chunk] = __popc(m);
+                if (m) atomicAdd(&tb.tile_counts[(size_t)bounce * tb.n_tiles + (chunk >> 8)], __popc(m));
+            }
         } else if (m) {
             // compact: warp-aggregated queue append (one atomic per warp)
             const int leader = __ffs(m) - 1;
@@ -379,43 +362,49 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_first_hit(const S
     }
 }
 
-// ORDERED compaction, between bounce b and b + 1: exclusive prefix of the per-chunk survivor counts bounce b wrote
-// (in place), counters[b + 1] = number of survivors, n_chunks[b + 1] = number of chunks.  One CTA; the arrays are small
-// (n_paths / 128 entries).
-__global__ void __launch_bounds__(1024) k_scan_chunks(int* __restrict__ counts, int* __restrict__ counters, int* __restrict__ n_chunks,
-                                                      const int bounce, const int n_paths_first, const int tail_index)
+// ORDERED compaction, between bounce b and b + 1: sparse queue (32 slots per warp chunk, warp_counts[chunk] of them used)
+// -> dense queue, survivors in (pose, element, sample) order.  A tile = 256 consecutive warp chunks = one CTA.  The tile's
+// base is the sum of the survivor counts of the tiles before it (k_bounce accumulated them in tile_counts with one atomic
+// per warp chunk), so there is no scan pass and no look-back chain: every CTA is independent.  counters[b + 1] receives
+// the number of survivors.
+__global__ void __launch_bounds__(256) k_compact(const int* __restrict__ sparse, int* __restrict__ dense, const int* __restrict__ warp_counts,
+                                                const int* __restrict__ tile_counts, int* __restrict__ counters, const int bounce,
+                                                const int n_paths_first, const int tail_index)
 {
-    __shared__ int s_warp[32];
-    __shared__ int s_carry;
-    // after the tail merge (k_bounce) the bounces >= tail_from wrote no chunk counts and keep counters[] themselves
+    __shared__ int s_red[8];
+    __shared__ int s_scan[8];
+    // after the tail merge (k_bounce) the bounces >= tail_from do not compact and keep counters[] themselves
     const int tail_mark = counters[tail_index];                           // (bounce at which the tail started) + 1
     if (tail_mark && bounce + 1 >= tail_mark) return;
     const int n_in = bounce == 0 ? n_paths_first : counters[bounce];
-    const int nch = (n_in + 127) >> 7;
+    const int n_chunks = (n_in + 31) >> 5;
+    const int tile = blockIdx.x;
+    if (tile * 256 >= n_chunks) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
+    // base of this tile
+    int part = 0;
+    for (int i = threadIdx.x; i < tile; i += 256) part += __ldg(&tile_counts[i]);
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if (lane == 0) s_red[warp] = part;
+    // exclusive scan of the tile's 256 chunk counts
+    const int chunk = tile * 256 + threadIdx.x;
+    const int cnt = chunk < n_chunks ? __ldg(&warp_counts[chunk]) : 0;
+    int incl = cnt;
+    for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += y; }
+    if (lane == 31) s_scan[warp] = incl;
     __syncthreads();
-    for (int base = 0; base < nch; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int v = i < nch ? counts[i] : 0;
-        int x = v;                                               // inclusive warp scan
-        for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            int w = s_warp[lane];
-            for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += y; }
-            s_warp[lane] = w;                                    // inclusive scan of the warp totals
-        }
-        __syncthreads();
-        const int carry = s_carry;
-        const int excl = carry + (warp ? s_warp[warp - 1] : 0) + x - v;
-        if (i < nch) counts[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
-        __syncthreads();
+    int base = 0, before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { base += s_red[w]; const int t = s_scan[w]; if (w < warp) before += t; total += t; }
+    const int excl = base + before + incl - cnt;
+    // gather: the warp walks its 32 chunks, lanes copy the chunk's survivors (coalesced on both sides)
+#pragma unroll 4
+    for (int c = 0; c < 32; c++) {
+        const int n_c = __shfl_sync(0xffffffffu, cnt, c);
+        const int o_c = __shfl_sync(0xffffffffu, excl, c);
+        if (lane < n_c) dense[o_c + lane] = __ldg(&sparse[(size_t)(tile * 256 + warp * 32 + c) * 32 + lane]);
     }
-    if (threadIdx.x == 0) { counts[nch] = s_carry; counters[bounce + 1] = s_carry; n_chunks[bounce + 1] = nch; }
+    if (threadIdx.x == 0 && total) atomicAdd(&counters[bounce + 1], total);
 }
 
 #ifndef MCRT_CH_MIN_CTAS
@@ -640,6 +629,7 @@ void launch_trace(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, cons
     const int64_t n_paths = (int64_t)fr.n_poses * aq.elements * aq.samples;
     // counters[0] is informational; counters[1..] are the compaction cursors
     cudaMemsetAsync(tb.counters, 0, sizeof(int) * (size_t)(aq.max_depth + 1), stream);
+    if (tb.warp_counts) cudaMemsetAsync(tb.tile_counts, 0, sizeof(int) * (size_t)aq.max_depth * tb.n_tiles, stream);
     const int block = 128;
     // persistent-style grid: a multiple of the SM count, grid-stride loop inside
     const int grid = grid_for(n_paths, block, sm_count, MCRT_BOUNCE_GRID_CTAS_PER_SM);
@@ -649,15 +639,16 @@ void launch_trace(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, cons
         if (launches) (*launches)++;
     }
     for (int b = 0; b < aq.max_depth; b++) {
-        const bool sort = tb.sort_keys && !tb.chunk_prefix_a && b + 1 < aq.max_depth;
+        const bool sort = tb.sort_keys && !tb.warp_counts && b + 1 < aq.max_depth;
         // unused queue slots get the largest key so they sort behind the survivors
         if (sort) cudaMemsetAsync(tb.sort_keys, 0xff, sizeof(unsigned) * (size_t)n_paths, stream);
-        const bool ordered = tb.chunk_prefix_a != nullptr;
+        const bool ordered = tb.warp_counts != nullptr;
         if (ordered) {
             if (b == 0) k_bounce<true, true><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
             else k_bounce<false, true><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
             if (b + 1 < aq.max_depth) {
-                k_scan_chunks<<<1, 1024, 0, stream>>>((b & 1) ? tb.chunk_prefix_a : tb.chunk_prefix_b, tb.counters, tb.n_chunks, b, (int)n_paths, aq.max_depth);
+                k_compact<<<tb.n_tiles, 256, 0, stream>>>(tb.queue_b, tb.queue_a, tb.warp_counts, tb.tile_counts + (size_t)b * tb.n_tiles, tb.counters, b,
+                                                          (int)n_paths, aq.max_depth);
                 if (launches) (*launches)++;
             }
         } else if (b == 0) k_bounce<true, false><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
