@@ -107,7 +107,10 @@ struct mcrt_ctx {
     float2* d_volume = nullptr;        // owned by the process-wide cache
     float2* d_elem_sincos = nullptr;
     bool voxel_fma_validated = false;
-    Bvh4Node* d_nodes4 = nullptr;      // 4-wide copy of bvh.nodes (collapse_bvh4)
+    Bvh4Node* d_nodes4 = nullptr;      // 4-wide copy of bvh.nodes (collapse_bvh4; only when built with MCRT_BVH8=0)
+    Bvh8Node* d_nodes8 = nullptr;      // 8-wide tree (collapse_bvh8), the default traversal structure
+    TriSlot* d_tris8 = nullptr;        // triangle slots in the 8-wide tree's leaf order
+    int n_nodes_wide = 0, depth_wide = 0;
     int tree_budget = 0;               // > 0: ray-tree mode with this many segments per path (option "ray_tree")
     TreeBuffers tree{};
     int* h_tree = nullptr;             // pinned: per batch {segments, overflow}
@@ -250,6 +253,25 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
         CUDA_TRY(cudaMalloc(&c->tb.sort_tmp, c->tb.sort_tmp_bytes ? c->tb.sort_tmp_bytes : 16));
     }
     c->cap_poses = n_poses;
+}
+
+// the wide traversal tree over a freshly built BVH2 (device LBVH or uploaded host SAH tree)
+struct WideTree { Bvh4Node* n4 = nullptr; Bvh8Node* n8 = nullptr; TriSlot* t8 = nullptr; int n_nodes = 0, depth = 0; };
+void build_wide_tree(const LbvhResult& b, cudaStream_t stream, WideTree* w)
+{
+#if MCRT_BVH8
+    const cudaError_t ce = collapse_bvh8(b.nodes, b.n_nodes, b.tris, b.n_tri, &w->n8, &w->t8, stream, &w->depth, &w->n_nodes);
+    if (ce != cudaSuccess) throw CudaError(std::string("collapse_bvh8: ") + cudaGetErrorString(ce));
+    if (w->depth > MCRT_STACK_DEPTH8) {
+        cudaFree(w->n8); cudaFree(w->t8);
+        throw std::invalid_argument("8-wide BVH deeper than the traversal stack (degenerate mesh?)");
+    }
+#else
+    const cudaError_t ce = collapse_bvh4(b.nodes, b.n_nodes, &w->n4, stream, &w->depth);
+    if (ce != cudaSuccess) throw CudaError(std::string("collapse_bvh4: ") + cudaGetErrorString(ce));
+    if (3 * w->depth + 1 > MCRT_STACK_DEPTH4) { cudaFree(w->n4); throw std::invalid_argument("4-wide BVH deeper than the traversal stack (degenerate mesh?)"); }
+    w->n_nodes = b.n_nodes;
+#endif
 }
 
 // wavefront trace of poses [pose0, pose0 + n) of the uploaded batch; `slot` selects its compaction counters
@@ -565,12 +587,13 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     SceneDev& sc = c->sc;
     memset(&sc, 0, sizeof(sc));
     {
-        int depth4 = 0;
-        const cudaError_t ce = collapse_bvh4(c->bvh.nodes, c->bvh.n_nodes, &c->d_nodes4, c->stream, &depth4);
-        if (ce != cudaSuccess) throw CudaError(std::string("collapse_bvh4: ") + cudaGetErrorString(ce));
-        if (3 * depth4 + 1 > MCRT_STACK_DEPTH4) throw std::invalid_argument("4-wide BVH deeper than the traversal stack (degenerate mesh?)");
+        CUDA_TRY(init_trace_kernels());
+        WideTree w;
+        build_wide_tree(c->bvh, c->stream, &w);
+        c->d_nodes4 = w.n4; c->d_nodes8 = w.n8; c->d_tris8 = w.t8; c->n_nodes_wide = w.n_nodes; c->depth_wide = w.depth;
     }
-    sc.nodes = c->bvh.nodes; sc.nodes4 = c->d_nodes4; sc.tris = c->bvh.tris; sc.meshes = c->d_meshes; sc.materials = c->d_materials;
+    sc.nodes = c->bvh.nodes; sc.nodes4 = c->d_nodes4; sc.nodes8 = c->d_nodes8; sc.tris = c->d_tris8 ? c->d_tris8 : c->bvh.tris;
+    sc.meshes = c->d_meshes; sc.materials = c->d_materials;
     sc.n_tri = c->bvh.n_tri; sc.n_mesh = (int)hs.meshes.size(); sc.n_mat = (int)hs.materials.size();
     sc.starting_material = hs.starting_material;
     for (int a = 0; a < 3; a++) sc.spacing[a] = hs.spacing[a];
@@ -626,6 +649,7 @@ void destroy_impl(mcrt_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_workspace(c);
     dev_free(c->d_meshes); dev_free(c->d_materials); dev_free(c->bvh.nodes); dev_free(c->bvh.tris); dev_free(c->d_nodes4);
+    dev_free(c->d_nodes8); dev_free(c->d_tris8);
     dev_free(c->d_elem_sincos); dev_free(c->d_axial); dev_free(c->d_lateral); dev_free(c->d_lat_by_row); dev_free(c->d_map_x); dev_free(c->d_map_y);
     dev_free(c->d_seed_frame); dev_free(c->d_steps); dev_free(c->d_trav);
     if (c->h_seed_frame) cudaFreeHost(c->h_seed_frame);
@@ -833,17 +857,14 @@ static void rebuild_bvh(mcrt_ctx* c)
         nb.n_tri = (int)n; nb.n_nodes = (int)hb.nodes.size(); nb.max_depth = hb.max_depth; nb.max_abs = hb.max_abs;
     }
     if (nb.max_depth > MCRT_TRAVERSAL_STACK) { cudaFree(nb.nodes); cudaFree(nb.tris); throw std::invalid_argument("BVH deeper than the traversal stack"); }
-    Bvh4Node* n4 = nullptr;
-    {
-        int depth4 = 0;
-        const cudaError_t ce = collapse_bvh4(nb.nodes, nb.n_nodes, &n4, c->stream, &depth4);
-        if (ce != cudaSuccess) { cudaFree(nb.nodes); cudaFree(nb.tris); throw CudaError(std::string("collapse_bvh4: ") + cudaGetErrorString(ce)); }
-        if (3 * depth4 + 1 > MCRT_STACK_DEPTH4) { cudaFree(nb.nodes); cudaFree(nb.tris); cudaFree(n4); throw std::invalid_argument("4-wide BVH deeper than the traversal stack"); }
-    }
-    dev_free(c->bvh.nodes); dev_free(c->bvh.tris); dev_free(c->d_nodes4);
+    WideTree w;
+    try {
+        build_wide_tree(nb, c->stream, &w);
+    } catch (...) { cudaFree(nb.nodes); cudaFree(nb.tris); throw; }
+    dev_free(c->bvh.nodes); dev_free(c->bvh.tris); dev_free(c->d_nodes4); dev_free(c->d_nodes8); dev_free(c->d_tris8);
     c->bvh = nb;
-    c->d_nodes4 = n4;
-    c->sc.nodes = nb.nodes; c->sc.nodes4 = n4; c->sc.tris = nb.tris; c->sc.n_tri = nb.n_tri; c->sc.max_abs = nb.max_abs;
+    c->d_nodes4 = w.n4; c->d_nodes8 = w.n8; c->d_tris8 = w.t8; c->n_nodes_wide = w.n_nodes; c->depth_wide = w.depth;
+    c->sc.nodes = nb.nodes; c->sc.nodes4 = w.n4; c->sc.nodes8 = w.n8; c->sc.tris = w.t8 ? w.t8 : nb.tris; c->sc.n_tri = nb.n_tri; c->sc.max_abs = nb.max_abs;
     update_scene_bounds(c);
     c->scene_dirty = false;
 }

@@ -306,6 +306,151 @@ cudaError_t collapse_bvh4(const BvhNode* d_nodes2, int n_nodes, Bvh4Node** d_nod
     return cudaSuccess;
 }
 
+// ------------------------------------------------------------------------------------------------
+// BVH2 -> BVH8 (round 2).  Top-down, one launch per level of the wide tree.  A work item = (BVH2 node, BVH8 node it
+// becomes).  The item starts from the BVH2 node's two children and up to six times replaces the inner child with the
+// largest surface area by that child's two children (the greedy collapse of k_collapse_bvh4, taken to 8); the resulting
+// 2..8 children are assigned to the 8 slots by octant -- slot bit a set = the child lies towards +axis a of the node's
+// centre (greedy on dot(child centre - node centre, slot direction), Ylitie et al. 2017) -- so that a ray can visit the
+// slots in the order (slot XOR ray octant) without sorting entry distances.  Inner children get consecutive node indices
+// and leaf children consecutive triangle slots (one atomicAdd each per node), in slot order: a child is addressed by the
+// node's base + the number of like children in lower slots, and the traversal stack holds one (base, masks) entry per
+// node instead of one entry per child.
+// ------------------------------------------------------------------------------------------------
+struct WideItem { int node2; int node8; };
+
+__global__ void __launch_bounds__(128) k_collapse_bvh8_level(const BvhNode* __restrict__ nodes2, const TriSlot* __restrict__ tris_in,
+                                                            const WideItem* __restrict__ items_in, const int n_in,
+                                                            WideItem* __restrict__ items_out, int* __restrict__ counters /* {nodes, tris, out} */,
+                                                            Bvh8Node* __restrict__ nodes8, TriSlot* __restrict__ tris_out)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_in) return;
+    const WideItem it = items_in[w];
+    float lo[8][3], hi[8][3];
+    int ref[8];
+    int n = 2;
+    auto put = [&](int at, float lx, float ly, float lz, float hx, float hy, float hz, int r) {
+        lo[at][0] = lx; lo[at][1] = ly; lo[at][2] = lz; hi[at][0] = hx; hi[at][1] = hy; hi[at][2] = hz; ref[at] = r;
+    };
+    {
+        const BvhNode nd = nodes2[it.node2];
+        put(0, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y, nd.d.x);
+        put(1, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w, nd.d.y);
+    }
+    while (n < 8) {
+        int pick = -1;
+        float best = -1.0f;
+        for (int k = 0; k < n; k++) {
+            if (ref[k] < 0) continue;                            // leaves cannot be opened
+            const float dx = hi[k][0] - lo[k][0], dy = hi[k][1] - lo[k][1], dz = hi[k][2] - lo[k][2];
+            const float area = dx * dy + dy * dz + dz * dx;
+            if (area > best) { best = area; pick = k; }
+        }
+        if (pick < 0) break;
+        const BvhNode c = nodes2[ref[pick]];
+        put(pick, c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y, c.d.x);
+        put(n, c.b.z, c.b.w, c.c.x, c.c.y, c.c.z, c.c.w, c.d.y);
+        n++;
+    }
+    // node centre, child centres
+    float nlo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, nhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int k = 0; k < n; k++)
+        for (int a = 0; a < 3; a++) { nlo[a] = fminf(nlo[a], lo[k][a]); nhi[a] = fmaxf(nhi[a], hi[k][a]); }
+    float cc[8][3];
+    for (int k = 0; k < n; k++)
+        for (int a = 0; a < 3; a++) cc[k][a] = 0.5f * (lo[k][a] + hi[k][a]) - 0.5f * (nlo[a] + nhi[a]);
+    // greedy octant assignment: repeatedly take the (child, free slot) pair with the largest dot(centre offset, slot direction)
+    int slot_of[8];
+    unsigned used_slots = 0u, done_children = 0u;
+    for (int round = 0; round < n; round++) {
+        float bestc = -3.0e38f;
+        int bk = 0, bs = 0;
+        for (int k = 0; k < n; k++) {
+            if (done_children & (1u << k)) continue;
+            for (int sl = 0; sl < 8; sl++) {
+                if (used_slots & (1u << sl)) continue;
+                const float cost = ((sl & 1) ? cc[k][0] : -cc[k][0]) + ((sl & 2) ? cc[k][1] : -cc[k][1]) + ((sl & 4) ? cc[k][2] : -cc[k][2]);
+                if (cost > bestc) { bestc = cost; bk = k; bs = sl; }
+            }
+        }
+        slot_of[bk] = bs; used_slots |= 1u << bs; done_children |= 1u << bk;
+    }
+    unsigned imask = 0u, lmask = 0u;
+    for (int k = 0; k < n; k++) { if (ref[k] >= 0) imask |= 1u << slot_of[k]; else lmask |= 1u << slot_of[k]; }
+    const int ni = __popc(imask), nl = __popc(lmask);
+    const int cbase = ni ? atomicAdd(&counters[0], ni) : 0;
+    const int tbase = nl ? atomicAdd(&counters[1], nl) : 0;
+    const int obase = ni ? atomicAdd(&counters[2], ni) : 0;
+    Bvh8Node o;
+    for (int sl = 0; sl < 8; sl++) {
+        o.lox[sl] = o.loy[sl] = o.loz[sl] = 3.0e38f;             // empty slot: inverted box, never hit
+        o.hix[sl] = o.hiy[sl] = o.hiz[sl] = -3.0e38f;
+    }
+    for (int k = 0; k < n; k++) {
+        const int sl = slot_of[k];
+        o.lox[sl] = lo[k][0]; o.loy[sl] = lo[k][1]; o.loz[sl] = lo[k][2];
+        o.hix[sl] = hi[k][0]; o.hiy[sl] = hi[k][1]; o.hiz[sl] = hi[k][2];
+        if (ref[k] >= 0) {
+            const int rank = __popc(imask & ((1u << sl) - 1u));
+            items_out[obase + rank] = WideItem{ref[k], cbase + rank};
+        } else {
+            const int rank = __popc(lmask & ((1u << sl) - 1u));
+            const int code = -ref[k] - 1;                           // leaf of exactly one triangle (MCRT_LEAF_MAX == 1)
+            tris_out[tbase + rank] = tris_in[code >> 2];
+        }
+    }
+    o.child_base = cbase; o.tri_base = tbase; o.masks = imask | (lmask << 8);
+    for (int k = 0; k < 13; k++) o.pad[k] = 0;
+    nodes8[it.node8] = o;
+}
+
+cudaError_t collapse_bvh8(const BvhNode* d_nodes2, int n_nodes2, const TriSlot* d_tris_in, int n_tri, Bvh8Node** d_nodes8_out,
+                          TriSlot** d_tris8_out, cudaStream_t stream, int* depth8_out, int* n_nodes8_out)
+{
+    static_assert(sizeof(Bvh8Node) == 256, "Bvh8Node must be two cache lines");
+    static_assert(MCRT_LEAF_MAX == 1, "the 8-wide collapse expects single-triangle leaves");
+    *d_nodes8_out = nullptr; *d_tris8_out = nullptr;
+    if (depth8_out) *depth8_out = 0;
+    if (n_nodes8_out) *n_nodes8_out = 0;
+    if (n_nodes2 <= 0 || n_tri <= 0) return cudaSuccess;
+    Bvh8Node* d8 = nullptr;
+    TriSlot* t8 = nullptr;
+    WideItem *qa = nullptr, *qb = nullptr;
+    int* d_cnt = nullptr;
+    cudaError_t e = cudaMalloc(&d8, sizeof(Bvh8Node) * (size_t)n_nodes2);
+    if (e == cudaSuccess) e = cudaMalloc(&t8, sizeof(TriSlot) * (size_t)n_tri);
+    if (e == cudaSuccess) e = cudaMalloc(&qa, sizeof(WideItem) * (size_t)n_nodes2);
+    if (e == cudaSuccess) e = cudaMalloc(&qb, sizeof(WideItem) * (size_t)n_nodes2);
+    if (e == cudaSuccess) e = cudaMalloc(&d_cnt, sizeof(int) * 3);
+    int depth = 0, total_nodes = 1;
+    if (e == cudaSuccess) {
+        const WideItem root{0, 0};
+        int h_cnt[3] = {1, 0, 0};                                  // node 0 = the root is taken
+        e = cudaMemcpyAsync(qa, &root, sizeof(root), cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_cnt, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, stream);
+        int n_in = 1;
+        while (e == cudaSuccess && n_in > 0) {
+            depth++;
+            k_collapse_bvh8_level<<<(n_in + 127) / 128, 128, 0, stream>>>(d_nodes2, d_tris_in, qa, n_in, qb, d_cnt, d8, t8);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            n_in = h_cnt[2];
+            total_nodes = h_cnt[0];
+            if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt + 2, 0, sizeof(int), stream);
+            WideItem* t = qa; qa = qb; qb = t;
+        }
+        if (e == cudaSuccess && h_cnt[1] != n_tri) e = cudaErrorUnknown;     // every triangle is the leaf child of exactly one node
+    }
+    cudaFree(qa); cudaFree(qb); cudaFree(d_cnt);
+    if (e != cudaSuccess) { cudaFree(d8); cudaFree(t8); return e; }
+    *d_nodes8_out = d8; *d_tris8_out = t8;
+    if (depth8_out) *depth8_out = depth;
+    if (n_nodes8_out) *n_nodes8_out = total_nodes;
+    return cudaSuccess;
+}
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = e_; goto done; } } while (0)
 
 cudaError_t build_lbvh(const float* h_tri_local, const int32_t* h_tri_mesh, int n_tri, const DevMesh* d_meshes, cudaStream_t stream,

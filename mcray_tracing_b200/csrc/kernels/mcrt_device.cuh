@@ -39,10 +39,40 @@ struct __align__(16) BvhNode { float4 a, b, c; int4 d; };
 #define MCRT_BVH4 1           // measured against the BVH2 traversal in profiles/r01ab_ab_bvh4.txt
 #endif
 #define MCRT_BVH4_EMPTY 0x7fffffff
+#ifndef MCRT_PREFETCH
+#define MCRT_PREFETCH 0       // 1: prefetch the cache line of every reference pushed on the traversal stack.  Measured slower
+                              // (trace 2.64 vs 2.57 ms per 512 frames, config 4 4.79 vs 4.57 ms; profiles/r02d_ab_prefetch_smemstack.txt):
+                              // the loop is bound by ALU issue, not by the latency of its node fetches
+#endif
+#ifndef MCRT_SMEM_STACK
+#define MCRT_SMEM_STACK 0     // > 0: the first N entries of the 4-wide traversal stack live in shared memory ([entry][thread], conflict-free),
+                              // deeper entries in local memory.  Measured slower with N = 8 (trace +6.7 %, same file): the range check per
+                              // push / pop costs more ALU issue slots than the L1-resident local-memory stack ever waited for
+#endif
+#define MCRT_TRACE_THREADS 128            // CTA size of every kernel that traverses (stride of the shared-memory stack)
 #ifndef MCRT_BVH4_SORT
 #define MCRT_BVH4_SORT 1      // 1: the hit children of a node are visited in entry order; 0: nearest first, the rest in slot order
 #endif
 struct __align__(16) Bvh4Node { float4 lox, loy, loz, hix, hiy, hiz; int4 child; int4 pad; };
+
+// BVH8 node, 256 B = two cache lines (round 2, the default): built by k_collapse_bvh8_level.  Planes per axis for the 8
+// slots (empty slot = inverted box); slot bit a set = the child lies towards +axis a of the node centre, so a ray visits
+// the slots in the order of descending (slot XOR oinv), oinv bit a = the ray travels towards +a, without sorting.  The
+// inner children are nodes child_base + (number of inner slots below this one), the leaf children the triangle slots
+// tri_base + (number of leaf slots below): the stack holds ONE entry per visited node, not one per child.
+#ifndef MCRT_BVH8
+#define MCRT_BVH8 0           // measured against the sorted 4-wide traversal (profiles/r02c_ab_bvh8.txt): 13.4 instead of 17.5 node
+                              // visits per query, but 107 instead of 70 child boxes tested and 2.2 instead of 1.7 triangle tests
+                              // (octant order is approximate) -- on a kernel bound by the ALU pipe that is 13 % slower (trace 2.91 vs
+                              // 2.56 ms per 512 frames, config 4: 5.13 vs 4.57 ms).  Kept as a build option (-DMCRT_BVH8=1), bit-identical.
+#endif
+struct __align__(16) Bvh8Node {
+    float lox[8], loy[8], loz[8], hix[8], hiy[8], hiz[8];
+    int child_base, tri_base;
+    unsigned masks;           // bits 0..7: slot holds an inner node; bits 8..15: slot holds a triangle
+    int pad[13];
+};
+#define MCRT_STACK_DEPTH8 40               // one entry per level of the wide tree (checked at build time)
 
 // Triangle slot (48 B, Morton order): local-frame vertices v_obj*scaling; v0.w = mesh id bits,
 // v1.w = original (objloader-order) triangle id bits.
@@ -58,7 +88,8 @@ struct __align__(16) DevSegment { float4 s0, s1, s2; int4 s3; };
 
 struct SceneDev {
     const BvhNode* nodes;
-    const Bvh4Node* nodes4;  // the same tree, 4-wide (nullptr when the scene has < 2 triangles)
+    const Bvh4Node* nodes4;  // the same tree, 4-wide (nullptr when the scene has < 2 triangles or MCRT_BVH8)
+    const Bvh8Node* nodes8;  // the same tree, 8-wide (MCRT_BVH8; `tris` is then in the wide tree's leaf order)
     const TriSlot* tris;
     const DevMesh* meshes;
     const DevMaterial* materials;
@@ -347,19 +378,91 @@ __device__ __forceinline__ bool box_test(const RayBox& r, float lox, float loy, 
 
 // Stack-based closest-hit traversal, near child first.  `node_visits` / `tri_tests` are per-thread work
 // counters (two integer adds per iteration; reported through mcrt_stats when "count_traversal" is on).
-__device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __restrict__ s_mesh, float3 from_w, float3 to_w, HitRec& best,
-                                            int& node_visits, int& tri_tests)
+__device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __restrict__ s_mesh, const unsigned char* __restrict__ s_perm,
+                                            int* __restrict__ s_stack /* this thread's column of the shared-memory stack, or nullptr */,
+                                            float3 from_w, float3 to_w, HitRec& best, int& node_visits, int& tri_tests)
 {
     best.fraction = 1.0f; best.tri_id = -1; best.mesh = -1; best.n_raw = make_float3(0.f, 0.f, 0.f); best.dist_a = 0.0f;
     if (sc.n_tri <= 0) return;
     if (sc.n_tri == 1) { tri_test(sc.tris, 0, s_mesh, from_w, to_w, best); tri_tests++; return; }
     const RayBox rb = make_raybox(from_w, to_w, sc.max_abs);
+#if MCRT_BVH8 && MCRT_BOX_FMA
+    {
+        // 8-wide traversal in octant order with a node-group stack.  Per node: 12 LDG.128 of planes (near / far picked by
+        // address) + 1 of the header, one FFMA per plane, the 8 hit bits, one table look-up that moves hit bit `slot` to
+        // bit (slot XOR oinv) -- the visiting priority -- and at most one stack push.
+        const unsigned long long base = (unsigned long long)reinterpret_cast<uintptr_t>(sc.nodes8);
+        const unsigned onx = rb.px ? 0u : 96u, ofx = rb.px ? 96u : 0u;     // byte offsets of lox / hix
+        const unsigned ony = rb.py ? 32u : 128u, ofy = rb.py ? 128u : 32u;
+        const unsigned onz = rb.pz ? 64u : 160u, ofz = rb.pz ? 160u : 64u;
+        const unsigned oinv = (rb.px ? 1u : 0u) | (rb.py ? 2u : 0u) | (rb.pz ? 4u : 0u);
+        const unsigned char* perm = s_perm + (oinv << 8);
+        uint2 stack8[MCRT_STACK_DEPTH8];
+        int sp = 0;
+        unsigned cur_base = 0u, cur_imask = 1u, cur_hp = 1u << oinv;        // the root: "slot 0" of a virtual parent
+        while (true) {
+            if (cur_hp == 0u) {
+                if (sp == 0) break;
+                const uint2 e = stack8[--sp];
+                cur_base = e.x; cur_imask = e.y >> 8; cur_hp = e.y & 0xffu;
+            }
+            // next child of the current group: highest priority bit
+            const unsigned bit = 31u - (unsigned)__clz((int)cur_hp);
+            cur_hp ^= 1u << bit;                                             // the rest of the group
+            const unsigned slot = bit ^ oinv;
+            const unsigned node = cur_base + (unsigned)__popc(cur_imask & ((1u << slot) - 1u));
+            node_visits++;
+            const unsigned long long nd = base + (unsigned long long)node * (unsigned long long)sizeof(Bvh8Node);
+            const float4* pnx = reinterpret_cast<const float4*>(nd | onx); const float4* pfx = reinterpret_cast<const float4*>(nd | ofx);
+            const float4* pny = reinterpret_cast<const float4*>(nd | ony); const float4* pfy = reinterpret_cast<const float4*>(nd | ofy);
+            const float4* pnz = reinterpret_cast<const float4*>(nd | onz); const float4* pfz = reinterpret_cast<const float4*>(nd | ofz);
+            const int4 hd = __ldg(reinterpret_cast<const int4*>(nd) + 12);
+            const float tb = best.fraction * 1.000002f;
+            unsigned h = 0u;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const float4 nx = __ldg(pnx + half), fx = __ldg(pfx + half), ny = __ldg(pny + half), fy = __ldg(pfy + half);
+                const float4 nz = __ldg(pnz + half), fz = __ldg(pfz + half);
+                const float n0[4] = {nx.x, nx.y, nx.z, nx.w}, n1[4] = {ny.x, ny.y, ny.z, ny.w}, n2[4] = {nz.x, nz.y, nz.z, nz.w};
+                const float f0[4] = {fx.x, fx.y, fx.z, fx.w}, f1[4] = {fy.x, fy.y, fy.z, fy.w}, f2[4] = {fz.x, fz.y, fz.z, fz.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float t0x = __fmaf_rn(n0[k], rb.ix, rb.cnx), t1x = __fmaf_rn(f0[k], rb.ix, rb.cfx);
+                    const float t0y = __fmaf_rn(n1[k], rb.iy, rb.cny), t1y = __fmaf_rn(f1[k], rb.iy, rb.cfy);
+                    const float t0z = __fmaf_rn(n2[k], rb.iz, rb.cnz), t1z = __fmaf_rn(f2[k], rb.iz, rb.cfz);
+                    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+                    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tb));
+                    if (tn <= __fmaf_rn(tf, 1.000002f, 1e-37f)) h |= 1u << (half * 4 + k);      // an empty slot's inverted box never passes
+                }
+            }
+            const unsigned masks = (unsigned)hd.z;
+            // the node's triangles first: a hit shortens the ray for everything that follows
+            unsigned hl = h & (masks >> 8);
+            while (hl) {
+                const unsigned sl = 31u - (unsigned)__clz((int)hl);
+                hl ^= 1u << sl;
+                tri_tests++;
+                tri_test(sc.tris, hd.y + __popc((masks >> 8) & ((1u << sl) - 1u)), s_mesh, from_w, to_w, best);
+            }
+            const unsigned hi = h & masks & 0xffu;
+            if (hi) {
+                // descend: the rest of the old group goes on the stack, this node's hit children become the current group
+                if (cur_hp) stack8[sp++] = make_uint2(cur_base, (cur_imask << 8) | cur_hp);
+                cur_base = (unsigned)hd.x; cur_imask = masks & 0xffu; cur_hp = perm[hi];
+            }
+        }
+        return;
+    }
+#endif
 #if MCRT_BVH4 && MCRT_BOX_FMA
     {
         // 4-wide traversal: half the dependent node fetches of the BVH2 loop below.  Near / far planes are picked by address.
         // A node is 128-byte aligned and the plane offsets are < 128, so (node address | offset) == (node address + offset):
         // ONE 64-bit multiply-add forms the node address and each of the seven loads only ORs its offset into the low word
-        // (was: a 64-bit add per load, 21 of the ~135 instructions of a node visit).
+        // (round 1: a 64-bit add per load, 21 of the ~135 instructions of a node visit).  Forming all seven addresses on the
+        // FMA pipe instead (six per-ray plane bases, one IMAD.WIDE each, no ALU instruction at all) measured 3.7 % SLOWER:
+        // the visit is as sensitive to the length of its dependent chain as to its instruction count
+        // (profiles/r02f_ab_fma_addresses.txt).
         const unsigned long long base = (unsigned long long)reinterpret_cast<uintptr_t>(sc.nodes4);
         const unsigned onx = rb.px ? 0u : 48u, ofx = rb.px ? 48u : 0u;   // byte offsets of lox / hix
         const unsigned ony = rb.py ? 16u : 64u, ofy = rb.py ? 64u : 16u;
@@ -367,6 +470,21 @@ __device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __
         int stack4[MCRT_STACK_DEPTH4];
         int sp4 = 0;
         int node4 = 0;
+#if MCRT_SMEM_STACK > 0
+#define MCRT_PUSH(v) { if (sp4 < MCRT_SMEM_STACK) s_stack[sp4 * MCRT_TRACE_THREADS] = (v); else stack4[sp4 - MCRT_SMEM_STACK] = (v); sp4++; }
+#define MCRT_POP() (--sp4, sp4 < MCRT_SMEM_STACK ? s_stack[sp4 * MCRT_TRACE_THREADS] : stack4[sp4 - MCRT_SMEM_STACK])
+#else
+#define MCRT_PUSH(v) { stack4[sp4++] = (v); }
+#define MCRT_POP() (stack4[--sp4])
+#endif
+#if MCRT_PREFETCH
+        const unsigned long long tri_base_addr = (unsigned long long)reinterpret_cast<uintptr_t>(sc.tris);
+#define MCRT_PREFETCH_REF(ref) { const int r_ = (ref); \
+            const unsigned long long a_ = r_ >= 0 ? base + (unsigned long long)(unsigned)r_ * 128ull : tri_base_addr + (unsigned long long)(unsigned)((-r_ - 1) >> 2) * 48ull; \
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(a_)); }
+#else
+#define MCRT_PREFETCH_REF(ref) {}
+#endif
         while (true) {
             if (node4 >= 0) {
                 node_visits++;
@@ -383,6 +501,9 @@ __device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __
                     const float f0[4] = {fx.x, fx.y, fx.z, fx.w}, f1[4] = {fy.x, fy.y, fy.z, fy.w}, f2[4] = {fz.x, fz.y, fz.z, fz.w};
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
+                        // (the clamp of the entry parameter at 0 cannot ride on an FFMA as its saturate modifier: an axis-parallel ray
+                        // outside a box's slab has t0 = +1e30, which .SAT would turn into 1 -- a hit while nothing closer is known:
+                        // 17.5 -> 21.7 node visits per query, profiles/r02e_ab_fma_addresses_sat.txt)
                         const float t0x = __fmaf_rn(n0[k], rb.ix, rb.cnx), t1x = __fmaf_rn(f0[k], rb.ix, rb.cfx);
                         const float t0y = __fmaf_rn(n1[k], rb.iy, rb.cny), t1y = __fmaf_rn(f1[k], rb.iy, rb.cfy);
                         const float t0z = __fmaf_rn(n2[k], rb.iz, rb.cnz), t1z = __fmaf_rn(f2[k], rb.iz, rb.cfz);
@@ -399,10 +520,12 @@ __device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __
                 MCRT_CSWAP(0, 1) MCRT_CSWAP(2, 3) MCRT_CSWAP(0, 2) MCRT_CSWAP(1, 3) MCRT_CSWAP(1, 2)
 #undef MCRT_CSWAP
                 if (t[0] < 3.0e38f) {
-                    // nearest first; the others go on the stack far-to-near so the nearer one is popped first
-                    if (t[3] < 3.0e38f) stack4[sp4++] = c[3];
-                    if (t[2] < 3.0e38f) stack4[sp4++] = c[2];
-                    if (t[1] < 3.0e38f) stack4[sp4++] = c[1];
+                    // nearest first; the others go on the stack far-to-near so the nearer one is popped first.  Every pushed
+                    // reference WILL be fetched when it is popped (there is no culling on the stack), so its cache line is
+                    // requested now: one LSU instruction that turns an L2 round trip at pop time into an L1 hit.
+                    if (t[3] < 3.0e38f) { MCRT_PUSH(c[3]); MCRT_PREFETCH_REF(c[3]); }
+                    if (t[2] < 3.0e38f) { MCRT_PUSH(c[2]); MCRT_PREFETCH_REF(c[2]); }
+                    if (t[1] < 3.0e38f) { MCRT_PUSH(c[1]); MCRT_PREFETCH_REF(c[1]); }
                     node4 = c[0];
                     continue;
                 }
@@ -416,7 +539,7 @@ __device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __
                     const int near_slot = (int)(kmin & 3u);
 #pragma unroll
                     for (int k = 0; k < 4; k++)
-                        if (k != near_slot && t[k] < 3.0e38f) stack4[sp4++] = c[k];
+                        if (k != near_slot && t[k] < 3.0e38f) MCRT_PUSH(c[k]);
                     node4 = near_slot == 0 ? c[0] : (near_slot == 1 ? c[1] : (near_slot == 2 ? c[2] : c[3]));
                     continue;
                 }
@@ -428,7 +551,7 @@ __device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __
                 for (int k = 0; k < count; k++) tri_test(sc.tris, first + k, s_mesh, from_w, to_w, best);
             }
             if (sp4 == 0) break;
-            node4 = stack4[--sp4];
+            node4 = MCRT_POP();
         }
         return;
     }

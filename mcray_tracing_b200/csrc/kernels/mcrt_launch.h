@@ -21,6 +21,14 @@ struct LbvhResult {
 // *depth4_out (nullable): longest chain of BVH4 nodes from the root; the traversal needs 3 * depth4 + 1 <= MCRT_STACK_DEPTH4
 cudaError_t collapse_bvh4(const BvhNode* d_nodes2, int n_nodes, Bvh4Node** d_nodes4_out, cudaStream_t stream, int* depth4_out = nullptr);
 
+// 8-wide tree from the same BVH2 node array (round 2, the default traversal structure): nodes in breadth-first order with
+// the inner children of a node consecutive, triangles re-ordered so the leaf children of a node are consecutive.  Caller
+// frees both outputs with cudaFree.  *depth8_out = levels of the wide tree (the traversal stack holds one entry per level).
+cudaError_t collapse_bvh8(const BvhNode* d_nodes2, int n_nodes2, const TriSlot* d_tris_in, int n_tri, Bvh8Node** d_nodes8_out,
+                          TriSlot** d_tris8_out, cudaStream_t stream, int* depth8_out, int* n_nodes8_out);
+// uploads the slot-permutation table of the 8-wide traversal (once per device)
+cudaError_t init_trace_kernels();
+
 // builds the device BVH from host triangle data; d_meshes must already be on the device
 cudaError_t build_lbvh(const float* h_tri_local, const int32_t* h_tri_mesh, int n_tri, const DevMesh* d_meshes, cudaStream_t stream,
                        LbvhResult* out);

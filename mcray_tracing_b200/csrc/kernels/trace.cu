@@ -15,14 +15,43 @@ namespace mcrt {
 
 namespace {
 
+// 8-wide traversal: perm[oinv][h] = the hit mask h (bit = slot) with every bit moved to position (slot XOR oinv), the
+// visiting priority of that slot for a ray of octant oinv (init_trace_kernels fills it; every CTA copies it to shared memory)
+__device__ uint4 g_perm8[128];
+
 struct SharedScene {
     float4 mesh_origin[MCRT_MAX_SMEM_MESHES];
     int4 mesh_info[MCRT_MAX_SMEM_MESHES];      // (mat_in, mat_out, vascular, -)
     DevMaterial materials[MCRT_MAX_SMEM_MATERIALS];
+#if MCRT_BVH8
+    uint4 perm4[128];                          // unsigned char [8][256]
+#endif
+#if MCRT_SMEM_STACK > 0
+    int stack[MCRT_SMEM_STACK * MCRT_TRACE_THREADS];   // [entry][thread]: the top of every thread's traversal stack
+#endif
+    __device__ __forceinline__ int* stack_column()
+    {
+#if MCRT_SMEM_STACK > 0
+        return stack + threadIdx.x;
+#else
+        return nullptr;
+#endif
+    }
+    __device__ __forceinline__ const unsigned char* perm() const
+    {
+#if MCRT_BVH8
+        return reinterpret_cast<const unsigned char*>(perm4);
+#else
+        return nullptr;
+#endif
+    }
 };
 
 __device__ __forceinline__ void load_shared_scene(const SceneDev& sc, SharedScene& sh)
 {
+#if MCRT_BVH8
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) sh.perm4[i] = g_perm8[i];
+#endif
     for (int i = threadIdx.x; i < sc.n_mesh && i < MCRT_MAX_SMEM_MESHES; i += blockDim.x) {
         const DevMesh m = sc.meshes[i];
         sh.mesh_origin[i] = make_float4(m.ox, m.oy, m.oz, 0.f);
@@ -137,7 +166,7 @@ __device__ __forceinline__ void shade_hit(const SceneDev& sc, const AcqDev& aq, 
 // One bounce of one path.  Returns true if the path survives into the next bounce.
 template <bool FIRST>
 __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, const TraceBuffers& tb,
-                                            const SharedScene& sh, int p, int bounce, int& node_visits, int& tri_tests, unsigned& sort_key)
+                                            SharedScene& sh, int p, int bounce, int& node_visits, int& tri_tests, unsigned& sort_key)
 {
     const int ES = aq.elements * aq.samples;
     const int pose = p / ES;
@@ -180,7 +209,7 @@ __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq
         h.fraction = a.x; h.tri_id = __float_as_int(a.y); h.mesh = __float_as_int(a.z); h.dist_a = a.w;
         h.n_raw = make_float3(b.x, b.y, b.z);
     } else {
-        closest_hit(sc, sh.mesh_origin, from_test, to, h, node_visits, tri_tests);
+        closest_hit(sc, sh.mesh_origin, sh.perm(), sh.stack_column(), from_test, to, h, node_visits, tri_tests);
     }
 
     DevSegment seg;
@@ -346,7 +375,7 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_first_hit(const S
         const float3 to = v_add(from, v_scl(make_float3(sc.spacing[0] * dir.x, sc.spacing[1] * dir.y, sc.spacing[2] * dir.z), r_length / 100.0f));
         const float3 from_test = v_add(from, v_scl(dir, 0.1f));
         HitRec h;
-        closest_hit(sc, sh.mesh_origin, from_test, to, h, node_visits, tri_tests);
+        closest_hit(sc, sh.mesh_origin, sh.perm(), sh.stack_column(), from_test, to, h, node_visits, tri_tests);
         tb.first_hits[2 * (size_t)i] = make_float4(h.fraction, __int_as_float(h.tri_id), __int_as_float(h.mesh), h.dist_a);
         tb.first_hits[2 * (size_t)i + 1] = make_float4(h.n_raw.x, h.n_raw.y, h.n_raw.z, 0.0f);
     }
@@ -465,7 +494,7 @@ __global__ void __launch_bounds__(128, 5) k_tree_level(const SceneDev sc, const 
             const float3 to = v_add(from, v_scl(make_float3(sc.spacing[0] * dir.x, sc.spacing[1] * dir.y, sc.spacing[2] * dir.z), r_length / 100.0f));
             const float3 from_test = v_add(from, v_scl(dir, 0.1f));
             HitRec h;
-            closest_hit(sc, sh.mesh_origin, from_test, to, h, node_visits, tri_tests);
+            closest_hit(sc, sh.mesh_origin, sh.perm(), sh.stack_column(), from_test, to, h, node_visits, tri_tests);
             key = ((unsigned long long)(unsigned)path << 20) | (unsigned long long)(unsigned)node;
             if (h.tri_id >= 0) {
                 ShadeResult r;
@@ -564,7 +593,7 @@ __global__ void __launch_bounds__(128, MCRT_CH_MIN_CTAS) k_closest_hit(const Sce
         const float3 t = make_float3(to3[3 * i], to3[3 * i + 1], to3[3 * i + 2]);
         HitRec h;
         int nv = 0, nt = 0;
-        closest_hit(sc, sh.mesh_origin, f, t, h, nv, nt);
+        closest_hit(sc, sh.mesh_origin, sh.perm(), sh.stack_column(), f, t, h, nv, nt);
         tri[i] = h.tri_id;
         mesh[i] = h.mesh;
         frac[i] = h.fraction;
@@ -621,6 +650,19 @@ static int grid_for(int64_t n_threads, int block, int sm_count, int ctas_per_sm)
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;
+}
+
+cudaError_t init_trace_kernels()
+{
+    unsigned char lut[8][256];
+    for (unsigned o = 0; o < 8; o++)
+        for (unsigned h = 0; h < 256; h++) {
+            unsigned p = 0;
+            for (unsigned sl = 0; sl < 8; sl++)
+                if (h & (1u << sl)) p |= 1u << (sl ^ o);
+            lut[o][h] = (unsigned char)p;
+        }
+    return cudaMemcpyToSymbol(g_perm8, lut, sizeof(lut));
 }
 
 void launch_trace(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, const TraceBuffers& tb, int sm_count, cudaStream_t stream,
