@@ -135,6 +135,7 @@ struct mcrt_ctx {
     bool count_traversal = false;
     bool log_compress = false;             // rfimage.h:127-136, commented out in the reference
     int* d_max_bits = nullptr;             // [cap_poses] per-image maximum (ordered-int encoding)
+    bool post_tma = true;                  // TMA-staged fused post kernel (option "post_tma"; 0 = round 1's k_post_fused, for A/B and equivalence tests)
     int first_hit_dedup = 1;               // bounce 0 traced once per element (TraceBuffers::first_hits) when samples >= 4: 0 off, 1 large calls, 2 always
     int ordered_compaction = 1;            // order-preserving compaction between bounces (TraceBuffers::warp_counts): 0 off, 1 large calls, 2 always
     bool coherence_sort = false;           // radix-sort surviving paths between bounces (rough scenes)
@@ -206,6 +207,7 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
     free_workspace(c);
     const size_t n_paths = (size_t)n_poses * c->aq.elements * c->aq.samples;
     const size_t n_px = (size_t)n_poses * c->aq.elements * c->aq.rows;
+    const size_t n_px_acc = (size_t)n_poses * c->aq.elements * c->aq.rf_pitch;      // raw image: 16-byte row pitch (AcqDev::rf_pitch)
     if (n_paths * c->aq.max_depth > 0x7fffffffULL) throw std::invalid_argument("batch too large: reduce max_batch_poses");
     dev_alloc(c->tb.paths.origin_intensity, n_paths);
     dev_alloc(c->tb.paths.dir_state, n_paths);
@@ -216,7 +218,8 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
     dev_alloc(c->tb.queue_b, n_paths);
     dev_alloc(c->tb.counters, (size_t)kMaxSub * (c->aq.max_depth + 1));
     dev_alloc(c->d_poses, (size_t)n_poses);
-    dev_alloc(c->d_rf_acc, n_px);
+    dev_alloc(c->d_rf_acc, n_px_acc);
+    CUDA_TRY(cudaMemset(c->d_rf_acc, 0, sizeof(float) * n_px_acc));                 // the pad words of every row stay 0
     dev_alloc(c->d_rf_tmp0, n_px);
     dev_alloc(c->d_rf_tmp1, n_px);
     dev_alloc(c->d_rf_final, n_px);
@@ -304,10 +307,12 @@ void enqueue_image(mcrt_ctx* c, int pose0, int n, bool want_scan, cudaStream_t s
 {
     const size_t p0 = (size_t)pose0 * c->aq.elements * c->aq.samples;
     const size_t px0 = (size_t)pose0 * c->aq.elements * c->aq.rows;
-    CUDA_TRY(launch_accumulate(c->sc, c->aq, c->d_volume, c->tb.segments + p0 * c->aq.max_depth, c->tb.n_segments + p0, n, c->d_rf_acc + px0,
+    const size_t ax0 = (size_t)pose0 * c->aq.elements * c->aq.rf_pitch;
+    CUDA_TRY(launch_accumulate(c->sc, c->aq, c->d_volume, c->tb.segments + p0 * c->aq.max_depth, c->tb.n_segments + p0, n, c->d_rf_acc + ax0,
                                c->d_steps, c->d_columns + p0 * c->aq.rows, s, launches));
-    launch_post(c->d_rf_acc + px0, n, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
-                c->d_rf_tmp0 + px0, c->d_rf_tmp1 + px0, c->d_rf_final + px0, s, launches, 0, 0, c->d_lat_by_row);
+    launch_post(c->d_rf_acc + ax0, n, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
+                c->d_rf_tmp0 + px0, c->d_rf_tmp1 + px0, c->d_rf_final + px0, s, launches, 0, 0, c->d_lat_by_row, c->aq.rf_pitch,
+                c->post_tma ? c->h_axial.data() : nullptr, c->h_lateral.data());
     if (c->log_compress) launch_log_compress(c->d_rf_final + px0, n, (int64_t)c->aq.elements * c->aq.rows, c->d_max_bits + pose0, s, launches);
     if (c->params.rf_layout == 1) launch_transpose(c->d_rf_final + px0, n, c->aq.elements, c->aq.rows, c->d_rf_t + px0, s, launches);
     if (want_scan)
@@ -330,7 +335,8 @@ void enqueue_pipeline(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* l
                                    launches));
         CUDA_TRY(cudaEventRecord(c->ev_c, s));
         launch_post(c->d_rf_acc, n, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
-                    c->d_rf_tmp0, c->d_rf_tmp1, c->d_rf_final, s, launches, 0, 0, c->d_lat_by_row);
+                    c->d_rf_tmp0, c->d_rf_tmp1, c->d_rf_final, s, launches, 0, 0, c->d_lat_by_row, c->aq.rf_pitch, c->post_tma ? c->h_axial.data() : nullptr,
+                    c->h_lateral.data());
         if (c->log_compress) launch_log_compress(c->d_rf_final, n, (int64_t)c->aq.elements * c->aq.rows, c->d_max_bits, s, launches);
         if (c->params.rf_layout == 1) launch_transpose(c->d_rf_final, n, c->aq.elements, c->aq.rows, c->d_rf_t, s, launches);
         if (want_scan)
@@ -422,7 +428,8 @@ void run_tree_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* lau
     CUDA_TRY(launch_accumulate_tree(c->sc, c->aq, c->d_volume, t, n, c->d_rf_acc, c->d_steps, c->d_columns, s, launches));
     if (c->profile_stages) CUDA_TRY(cudaEventRecord(c->ev_c, s));
     launch_post(c->d_rf_acc, n, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
-                c->d_rf_tmp0, c->d_rf_tmp1, c->d_rf_final, s, launches, 0, 0, c->d_lat_by_row);
+                c->d_rf_tmp0, c->d_rf_tmp1, c->d_rf_final, s, launches, 0, 0, c->d_lat_by_row, c->aq.rf_pitch, c->post_tma ? c->h_axial.data() : nullptr,
+                c->h_lateral.data());
     if (c->log_compress) launch_log_compress(c->d_rf_final, n, (int64_t)c->aq.elements * c->aq.rows, c->d_max_bits, s, launches);
     if (c->params.rf_layout == 1) launch_transpose(c->d_rf_final, n, c->aq.elements, c->aq.rows, c->d_rf_t, s, launches);
     if (want_scan)
@@ -567,6 +574,7 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     aq.axres_mm = c->dv.axial_resolution_mm; aq.time_step_us = c->dv.time_step_us; aq.row_period_us = c->dv.row_period_us;
     aq.inv_row_period = 1.0 / c->dv.row_period_us; aq.max_travel_time_us = c->dv.max_travel_time_us;
     aq.speed = (double)c->params.speed_of_sound; aq.deterministic = c->params.deterministic;
+    aq.rf_pitch = post_preferred_pitch(aq.rows, c->params.psf_axial, c->params.psf_lateral);
 
     // scene tables
     const HostScene& hs = c->scene;
@@ -1003,6 +1011,11 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
         free_workspace(c);
         c->aq.accumulate_windowed = (value != 0 && accumulate_windowed_supported(c->sc, c->aq)) ? 1 : 0;
     }
+    else if (n == "post_tma") {
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear();
+        c->post_tma = value != 0;
+    }
     else if (n == "voxel_fma_division") {
         // A/B switch; can only be turned on for a resolution that passed the exhaustive check at mcrt_create
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
@@ -1060,7 +1073,7 @@ int mcrt_simulate_scanlines(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, u
         launch_trace(c->sc, aq, fr, c->tb, c->sm_count, s, &launches);
         CUDA_TRY(launch_accumulate(c->sc, aq, c->d_volume, c->tb.segments, c->tb.n_segments, 1, c->d_rf_acc, c->d_steps, c->d_columns, s, &launches));
         launch_post(c->d_rf_acc, 1, n_local, aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, kl, 3, c->d_rf_tmp0, c->d_rf_tmp1,
-                    c->d_rf_final, s, &launches, e0, E, c->d_lat_by_row);
+                    c->d_rf_final, s, &launches, e0, E, c->d_lat_by_row, aq.rf_pitch, c->post_tma ? c->h_axial.data() : nullptr, c->h_lateral.data());
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(rf_out, c->d_rf_final, sizeof(float) * (size_t)n_elements * aq.rows,
                                  is_device_pointer(rf_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
@@ -1325,7 +1338,8 @@ int mcrt_accumulate(mcrt_ctx* c, const mcrt_segment* segments, const int32_t* n_
         int launches = 0;
         CUDA_TRY(launch_accumulate(c->sc, c->aq, c->d_volume, c->tb.segments, c->tb.n_segments, 1, c->d_rf_acc, c->d_steps, c->d_columns,
                                    c->stream, &launches));
-        CUDA_TRY(cudaMemcpyAsync(rf_out, c->d_rf_acc, sizeof(float) * (size_t)c->aq.elements * c->aq.rows, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpy2DAsync(rf_out, sizeof(float) * c->aq.rows, c->d_rf_acc, sizeof(float) * c->aq.rf_pitch, sizeof(float) * c->aq.rows,
+                                   (size_t)c->aq.elements, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaMemcpyAsync(c->h_steps, c->d_steps, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->stats = mcrt_stats{};
@@ -1347,17 +1361,21 @@ int mcrt_postprocess(mcrt_ctx* c, const float* rf_in, int32_t cols, int32_t rows
     return guarded("mcrt_postprocess", [&]() {
         CUDA_TRY(cudaSetDevice(c->device));
         const size_t n = (size_t)cols * rows;
+        // the shape the fused TMA-staged kernel takes (both passes, 7 x 13 taps, short scanlines) is uploaded with its 16-byte row pitch
+        const int pitch = (flags == 3 && c->post_tma) ? post_preferred_pitch(rows, n_axial, n_lateral) : rows;
         float *d_in = nullptr, *d_t0 = nullptr, *d_t1 = nullptr, *d_out = nullptr, *d_ax = nullptr, *d_lat = nullptr;
         try {
-            dev_alloc(d_in, n); dev_alloc(d_t0, n); dev_alloc(d_t1, n); dev_alloc(d_out, n);
+            dev_alloc(d_in, (size_t)cols * pitch); dev_alloc(d_t0, n); dev_alloc(d_t1, n); dev_alloc(d_out, n);
             dev_alloc(d_ax, (size_t)(n_axial > 0 ? n_axial : 1)); dev_alloc(d_lat, (size_t)(n_lateral > 0 ? n_lateral : 1));
-            CUDA_TRY(cudaMemcpyAsync(d_in, rf_in, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+            if (pitch != rows) CUDA_TRY(cudaMemsetAsync(d_in, 0, sizeof(float) * (size_t)cols * pitch, c->stream));
+            CUDA_TRY(cudaMemcpy2DAsync(d_in, sizeof(float) * pitch, rf_in, sizeof(float) * rows, sizeof(float) * rows, (size_t)cols, cudaMemcpyHostToDevice, c->stream));
             if (flags & 1) {
                 CUDA_TRY(cudaMemcpyAsync(d_ax, axial, sizeof(float) * n_axial, cudaMemcpyHostToDevice, c->stream));
                 CUDA_TRY(cudaMemcpyAsync(d_lat, lateral, sizeof(float) * n_lateral, cudaMemcpyHostToDevice, c->stream));
             }
             int launches = 0;
-            launch_post(d_in, 1, cols, rows, d_ax, n_axial, d_lat, n_lateral, flags, d_t0, d_t1, d_out, c->stream, &launches);
+            launch_post(d_in, 1, cols, rows, d_ax, n_axial, d_lat, n_lateral, flags, d_t0, d_t1, d_out, c->stream, &launches, 0, 0, nullptr, pitch,
+                        (flags == 3 && c->post_tma) ? axial : nullptr, lateral);
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaMemcpyAsync(rf_out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));

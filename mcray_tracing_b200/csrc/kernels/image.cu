@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
     __shared__ DevMaterial s_mat[MCRT_MAX_SMEM_MATERIALS];
     for (int i = threadIdx.x; i < sc.n_mat && i < MCRT_MAX_SMEM_MATERIALS; i += blockDim.x) s_mat[i] = sc.materials[i];
     const int S = aq.samples, rows = aq.rows;
+    const int rf_pitch = aq.rf_pitch;                      // row stride of rf (>= rows; padded to 16 B for the TMA-staged post kernel)
     const int T = G * S;                                   // active threads of a group
     const int stride = win_stride(T);
     const int group = WARP ? (int)(blockIdx.x * 4 + (threadIdx.x >> 5)) : (int)blockIdx.x;
@@ -464,7 +465,7 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
             }
             if (row >= wend) return false;
             if (row < base) {                                                                   // a finished window: see header
-                win_late_echo(&rf[(size_t)my_scanline * rows + row], echo, late_echoes);
+                win_late_echo(&rf[(size_t)my_scanline * rf_pitch + row], echo, late_echoes);
                 return true;
             }
             if (row < cur_row) {                                                                // revisited row of my own column
@@ -617,7 +618,7 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
         const int wrows = wend - base;
         if (t < wrows) {
             const float* rowp = s_win + MCRT_WIN_SLOT(base + t) * stride;
-            float* dst = rf + (size_t)scanline0 * rows + base + t;
+            float* dst = rf + (size_t)scanline0 * rf_pitch + base + t;
             const int g_end = n_scanlines - scanline0 < G ? n_scanlines - scanline0 : G;
             for (int g = 0; g < g_end; g++) {
                 const float* src = rowp + g * S;
@@ -631,7 +632,7 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
                     sum = src[0];
                     for (int s = 1; s < S; s++) sum += src[s];
                 }
-                dst[(size_t)g * rows] = sum;
+                dst[(size_t)g * rf_pitch] = sum;
             }
         }
         group_sync();
@@ -643,7 +644,7 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
 }
 
 __global__ void __launch_bounds__(256) k_reduce_samples(const float* __restrict__ columns, const int64_t n_pixels, const int samples,
-                                                       float* __restrict__ rf)
+                                                       float* __restrict__ rf, const int rows, const int rf_pitch)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += (int64_t)gridDim.x * blockDim.x) {
         const float* src = columns + i * samples;
@@ -660,7 +661,8 @@ __global__ void __launch_bounds__(256) k_reduce_samples(const float* __restrict_
             sum = __ldg(&src[0]);
             for (int t = 1; t < samples; t++) sum += __ldg(&src[t]);
         }
-        rf[i] = sum;
+        if (rf_pitch == rows) rf[i] = sum;
+        else { const int64_t sl = i / rows; rf[sl * rf_pitch + (i - sl * rows)] = sum; }
     }
 }
 
@@ -687,13 +689,13 @@ __host__ __device__ __forceinline__ int psf_pad(int i) { return i + (i >> 3); }
 // along the taps.  For every output the taps are applied in order k = 0.. with separate multiply and add
 // (the reference's sequential fp32 sum).  Rows outside [ka, rows-ka) are never read downstream.
 __global__ void __launch_bounds__(256) k_psf_axial(const float* __restrict__ in, const int rows, const float* __restrict__ taps, const int ka,
-                                                  float* __restrict__ out)
+                                                  float* __restrict__ out, const int in_pitch)
 {
     extern __shared__ float s_row[];                       // psf_pad(MCRT_PSF_CHUNK + ka + MCRT_PSF_R) words
     __shared__ float s_taps[MCRT_MAX_TAPS];
     const int tid = threadIdx.x;
     const int chunk0 = blockIdx.x * MCRT_PSF_CHUNK;        // first output row of this CTA
-    const float* src = in + (size_t)blockIdx.y * rows;
+    const float* src = in + (size_t)blockIdx.y * in_pitch;
     float* dst = out + (size_t)blockIdx.y * rows;
     for (int i = tid; i < ka; i += blockDim.x) s_taps[i] = taps[i];
     const int n_stage = MCRT_PSF_CHUNK + ka + MCRT_PSF_R;
@@ -733,7 +735,7 @@ __global__ void __launch_bounds__(256) k_psf_axial(const float* __restrict__ in,
 __global__ void __launch_bounds__(256) k_psf_lateral(const float* __restrict__ raw, const float* __restrict__ axial_buf, const int cols,
                                                     const int rows, const float* __restrict__ taps, const int ka, const int kl,
                                                     const int col_offset, const int cols_total, float* __restrict__ out,
-                                                    const float* __restrict__ taps_by_row)
+                                                    const float* __restrict__ taps_by_row, const int raw_pitch)
 {
     // taps_by_row != nullptr: depth-dependent lateral PSF, tap k of RF row r = taps_by_row[k * rows + r]
     __shared__ float s_taps[MCRT_MAX_TAPS];
@@ -771,7 +773,8 @@ __global__ void __launch_bounds__(256) k_psf_lateral(const float* __restrict__ r
         const int c = c0 + j;
         if (c >= cols) break;
         const size_t o = img + (size_t)c * rows + r;
-        out[o] = (any && col_offset + c >= kl / 2 && col_offset + c < cols_total - kl) ? acc[j] : __ldg(&raw[o]);
+        out[o] = (any && col_offset + c >= kl / 2 && col_offset + c < cols_total - kl)
+                     ? acc[j] : __ldg(&raw[((size_t)blockIdx.z * cols + c) * raw_pitch + r]);
     }
 }
 
@@ -869,7 +872,8 @@ template <int KA, int KL>
 __global__ void __launch_bounds__(MCRT_FUSED_THREADS) k_post_fused(const float* __restrict__ in, const int cols, const int rows,
                                                                   const float* __restrict__ ax_taps, const int ka,
                                                                   const float* __restrict__ lat_taps, const int kl, const int flags,
-                                                                  const int TC, const int col_offset, const int cols_total, float* __restrict__ out)
+                                                                  const int TC, const int col_offset, const int cols_total, float* __restrict__ out,
+                                                                  const int in_pitch)
 {
     extern __shared__ float sm[];
     __shared__ float s_taps_a[MCRT_MAX_TAPS], s_taps_l[MCRT_MAX_TAPS];
@@ -882,7 +886,7 @@ __global__ void __launch_bounds__(MCRT_FUSED_THREADS) k_post_fused(const float* 
     float* s_out = s_in;                                   //             in place by the lateral pass
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, NW = blockDim.x >> 5;
     const int c0 = blockIdx.x * TC;
-    const float* img_in = in + (size_t)blockIdx.y * cols * rows;
+    const float* img_in = in + (size_t)blockIdx.y * cols * in_pitch;
     float* img_out = out + (size_t)blockIdx.y * cols * rows;
     if (conv) {
         for (int i = tid; i < ka; i += blockDim.x) s_taps_a[i] = ax_taps[i];
@@ -894,7 +898,7 @@ __global__ void __launch_bounds__(MCRT_FUSED_THREADS) k_post_fused(const float* 
         const int gc = c0 + c;
         float* dst = s_in + (size_t)c * rows;
         if (gc < cols) {
-            const float* src = img_in + (size_t)gc * rows;
+            const float* src = img_in + (size_t)gc * in_pitch;
             for (int r = lane; r < rows; r += 32) dst[r] = __ldg(&src[r]);
         }
     }
@@ -967,6 +971,160 @@ __global__ void __launch_bounds__(MCRT_FUSED_THREADS) k_post_fused(const float* 
     for (int c = w; c < TC; c += NW) {
         if (c0 + c >= cols) continue;                      // warp-uniform
         const float* I = s_out + (size_t)c * rows;
+        float* O = img_out + (size_t)(c0 + c) * rows;
+        int next = rows;
+        for (int ch = n_chunks - 1; ch >= 0; ch--) {
+            const unsigned m = peak_mask_smem(I, rows, ch, lane);
+            if (lane == 0) { s_mask[w][ch] = m; s_next[w][ch] = next; }
+            if (m) next = (ch << 5) + (__ffs(m) - 1);
+        }
+        __syncwarp();
+        int last_peak = 0;
+        for (int ch = 0; ch < n_chunks; ch++) {
+            const unsigned mask = s_mask[w][ch];
+            const int i = (ch << 5) + lane;
+            const unsigned le = mask & (0xffffffffu >> (31 - lane));
+            const int p = le ? (ch << 5) + (31 - __clz(le)) : last_peak;
+            const unsigned gt = lane == 31 ? 0u : (mask & (0xffffffffu << (lane + 1)));
+            const int q = gt ? (ch << 5) + (__ffs(gt) - 1) : s_next[w][ch];
+            if (i < rows) {
+                float r = I[i];
+                if (q < rows) {
+                    const float last = (p == 0) ? I[0] : fabsf(I[p]);
+                    const float new_peak = fabsf(I[q]);
+                    const float alpha = ((float)i - (float)p) / ((float)q - (float)p);
+                    r = last * (1 - alpha) + new_peak * alpha;
+                }
+                O[i] = r;
+            }
+            if (mask) last_peak = (ch << 5) + (31 - __clz(mask));
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Round 2: the fused post kernel for the reference's image geometry, rebuilt around three facts measured on round 1's
+// k_post_fused<7,13> (238 thread instructions per pixel, issue-bound; profiles/r02a_hot_lines.txt):
+//  * staging: the raw image arrives with a 16-byte-aligned row pitch (AcqDev::rf_pitch), so the tile + halo scanlines of a
+//    CTA are ONE contiguous, aligned span of HBM: a single TMA bulk copy (cp.async.bulk -> UBLKCP) signalled on an mbarrier
+//    replaces 12 700 LDG.32 + STS.32 per CTA;
+//  * taps: each tap application is one multiply and one add (the reference's un-contracted sum), but the operands now come
+//    from registers: the axial pass computes 4 consecutive rows per thread from 3 LDS.128 (was 7 LDS.32 per row), the
+//    lateral pass keeps 8 consecutive scanlines of a row pair in registers and streams the 20 scanlines they need past them
+//    (2.5 LDS.64 per 2 pixels instead of 13 LDS.32 per pixel); the taps are kernel parameters (constant-bank operands);
+//  * the envelope (one warp per scanline) is unchanged.
+// Same arithmetic, same order, same untouched borders: bit-identical to k_post_fused and the unfused kernels.
+// ------------------------------------------------------------------------------------------------
+#define MCRT_TMA_THREADS 1024
+#define MCRT_TMA_RUN 8               // scanlines per thread in the lateral pass
+#define MCRT_TMA_MAX_CHUNKS 20       // rows <= 640
+#define MCRT_TMA_SMEM_LIMIT (200 * 1024)
+struct PostTaps { float a[8]; float l[16]; };
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int KA, int KL>
+__global__ void __launch_bounds__(MCRT_TMA_THREADS, 1) k_post_tma(const float* __restrict__ in, const int cols, const int rows, const int pitch,
+                                                                 const __grid_constant__ PostTaps taps, const int TC, const int col_offset,
+                                                                 const int cols_total, float* __restrict__ out)
+{
+    extern __shared__ __align__(128) float sm[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ unsigned s_mask[MCRT_TMA_THREADS / 32][MCRT_TMA_MAX_CHUNKS];
+    __shared__ int s_next[MCRT_TMA_THREADS / 32][MCRT_TMA_MAX_CHUNKS];
+    const int W = TC + KL - 1;                             // staged scanlines (tile + right halo)
+    float* s_raw = sm;                                     // [W][pitch] raw scanlines; the first TC become the result
+    float* s_ax = sm + (size_t)W * pitch;                  // [W][pitch] axial pass
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int c0 = blockIdx.x * TC;
+    const int wl = cols - c0 < W ? cols - c0 : W;          // staged scanlines that exist
+    const float* img_in = in + ((size_t)blockIdx.y * cols + c0) * pitch;
+    float* img_out = out + (size_t)blockIdx.y * cols * rows;
+    const unsigned bar = smem_u32(&s_bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned bytes = (unsigned)((size_t)wl * pitch * sizeof(float));     // multiple of 16: pitch % 4 == 0
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(s_raw)), "l"(img_in), "r"(bytes), "r"(bar) : "memory");
+    }
+    {
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar) : "memory");
+        }
+    }
+    // ---- axial pass (rfimage.h:97-108): warp = scanline, lane = 4 consecutive rows; forward-looking taps, sequential fp32 sum
+    const int Q = pitch >> 2;
+    for (int c = w; c < wl; c += MCRT_TMA_THREADS / 32) {
+        const float4* src4 = reinterpret_cast<const float4*>(s_raw + (size_t)c * pitch);
+        float4* dst4 = reinterpret_cast<float4*>(s_ax + (size_t)c * pitch);
+        for (int q = lane; q < Q; q += 32) {
+            float x[12];
+            const float4 v0 = src4[q];
+            const float4 v1 = q + 1 < Q ? src4[q + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 v2 = q + 2 < Q ? src4[q + 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+            x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+            x[8] = v2.x; x[9] = v2.y; x[10] = v2.z; x[11] = v2.w;
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float convolution = 0;
+#pragma unroll
+                for (int k = 0; k < KA; k++) convolution += x[j + k] * taps.a[k];
+                o[j] = convolution;
+            }
+            dst4[q] = make_float4(o[0], o[1], o[2], o[3]);       // rows outside [KA, rows - KA) are never read below
+        }
+    }
+    __syncthreads();
+    // ---- lateral pass (rfimage.h:111-122), into the raw tile; borders keep the raw samples (B-9).  Thread = one pair of
+    // rows x MCRT_TMA_RUN consecutive scanlines; the RUN + KL - 1 axial scanlines they need stream through registers once.
+    {
+        const int P2 = pitch >> 1;                             // row pairs per scanline
+        const int n_runs = TC / MCRT_TMA_RUN;
+        const int run = tid / P2, p = tid - run * P2;
+        if (run < n_runs) {
+            const int cs = run * MCRT_TMA_RUN;
+            const float2* ax2 = reinterpret_cast<const float2*>(s_ax) + p;
+            float2 acc[MCRT_TMA_RUN];
+#pragma unroll
+            for (int cc = 0; cc < MCRT_TMA_RUN; cc++) acc[cc] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int jj = 0; jj < MCRT_TMA_RUN + KL - 1; jj++) {
+                const int j = cs + jj;
+                const float2 v = j < wl ? ax2[(size_t)j * P2] : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int cc = 0; cc < MCRT_TMA_RUN; cc++) {
+                    const int k = jj - cc;                      // compile-time after unrolling
+                    if (k >= 0 && k < KL) { acc[cc].x += v.x * taps.l[k]; acc[cc].y += v.y * taps.l[k]; }
+                }
+            }
+            const int r0 = 2 * p;
+            const bool ok0 = r0 >= KA && r0 < rows - KA, ok1 = r0 + 1 >= KA && r0 + 1 < rows - KA;
+#pragma unroll
+            for (int cc = 0; cc < MCRT_TMA_RUN; cc++) {
+                const int c = cs + cc, gc = c0 + c;
+                if (gc < cols && col_offset + gc >= KL / 2 && col_offset + gc < cols_total - KL) {     // global indices
+                    float* dst = s_raw + (size_t)c * pitch + r0;
+                    if (ok0) dst[0] = acc[cc].x;
+                    if (ok1) dst[1] = acc[cc].y;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- envelope (rfimage.h:54-91): one warp per scanline, see k_post_fused
+    const int n_chunks = (rows + 31) >> 5;
+    for (int c = w; c < TC; c += MCRT_TMA_THREADS / 32) {
+        if (c0 + c >= cols) continue;                      // warp-uniform
+        const float* I = s_raw + (size_t)c * pitch;
         float* O = img_out + (size_t)(c0 + c) * rows;
         int next = rows;
         for (int ch = n_chunks - 1; ch >= 0; ch--) {
@@ -1145,7 +1303,7 @@ cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2
     else
         k_accumulate<false><<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_paths, d_columns, d_steps, nullptr, nullptr);
     const int64_t n_pixels = (int64_t)n_poses * aq.elements * aq.rows;
-    k_reduce_samples<<<grid1d(n_pixels, 256), 256, 0, stream>>>(d_columns, n_pixels, aq.samples, d_rf);
+    k_reduce_samples<<<grid1d(n_pixels, 256), 256, 0, stream>>>(d_columns, n_pixels, aq.samples, d_rf, aq.rows, aq.rf_pitch);
     if (launches) (*launches) += 2;
     return cudaGetLastError();
 }
@@ -1164,7 +1322,7 @@ cudaError_t launch_accumulate_tree(const SceneDev& sc, const AcqDev& aq, const f
         k_accumulate<false><<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, tb.segments, tb.path_count, n_paths, d_columns, d_steps,
                                                                                 tb.slots_sorted, tb.path_first);
     const int64_t n_pixels = (int64_t)n_poses * aq.elements * aq.rows;
-    k_reduce_samples<<<grid1d(n_pixels, 256), 256, 0, stream>>>(d_columns, n_pixels, aq.samples, d_rf);
+    k_reduce_samples<<<grid1d(n_pixels, 256), 256, 0, stream>>>(d_columns, n_pixels, aq.samples, d_rf, aq.rows, aq.rf_pitch);
     if (launches) (*launches) += 2;
     return cudaGetLastError();
 }
@@ -1205,6 +1363,8 @@ cudaError_t init_image_kernels()
     // per-device function attribute; must not be issued inside a stream capture
     cudaError_t e = cudaFuncSetAttribute(k_post_fused<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MCRT_FUSED_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_post_tma<7, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, MCRT_TMA_SMEM_LIMIT);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_post_fused<7, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, MCRT_FUSED_SMEM_LIMIT);
 }
 
@@ -1217,11 +1377,33 @@ int post_launch_count(int cols, int rows, int n_lateral, int flags, int n_images
     return ((flags & 1) ? (int)((n_scanlines + 65534) / 65535) + 1 : 0) + ((flags & 2) ? 2 : ((flags & 1) ? 0 : 1));
 }
 
+// the TMA-staged kernel needs both passes, the reference's tap counts, a 16-byte row pitch and scanlines that fit shared memory
+static bool post_tma_usable(int rows, int pitch, int n_axial, int n_lateral, int flags, const float* h_axial, const float* h_lateral)
+{
+    return flags == 3 && n_axial == 7 && n_lateral == 13 && (pitch & 3) == 0 && pitch >= rows && rows <= 32 * MCRT_TMA_MAX_CHUNKS && rows > 2 * 7 &&
+           h_axial && h_lateral && pitch * 2 <= MCRT_TMA_THREADS;
+}
+static size_t post_tma_smem(int pitch, int tc) { return sizeof(float) * 2 * (size_t)(tc + 13 - 1) * pitch; }
 void launch_post(const float* d_in, int n_images, int cols, int rows, const float* d_axial, int n_axial, const float* d_lateral,
                  int n_lateral, int flags, float* d_tmp0, float* d_tmp1, float* d_out, cudaStream_t stream, int* launches, int col_offset,
-                 int cols_total, const float* d_lateral_by_row)
+                 int cols_total, const float* d_lateral_by_row, int in_pitch, const float* h_axial, const float* h_lateral)
 {
     if (cols_total <= 0) { col_offset = 0; cols_total = cols; }
+    if (in_pitch <= 0) in_pitch = rows;
+    if (!d_lateral_by_row && n_images <= 65535 && post_tma_usable(rows, in_pitch, n_axial, n_lateral, flags, h_axial, h_lateral)) {
+        // widest tile of 8 / 16 / 32 scanlines that fits; few images (latency mode): narrower tiles so the grid still covers the SMs
+        int tc = 32;
+        while (tc > 8 && (post_tma_smem(in_pitch, tc) > MCRT_TMA_SMEM_LIMIT || (int64_t)((cols + tc - 1) / tc) * n_images < 148)) tc >>= 1;
+        if (post_tma_smem(in_pitch, tc) <= MCRT_TMA_SMEM_LIMIT && (in_pitch / 2) * (tc / MCRT_TMA_RUN) <= MCRT_TMA_THREADS) {
+            PostTaps taps;
+            for (int k = 0; k < 8; k++) taps.a[k] = k < 7 ? h_axial[k] : 0.0f;
+            for (int k = 0; k < 16; k++) taps.l[k] = k < 13 ? h_lateral[k] : 0.0f;
+            dim3 grid((cols + tc - 1) / tc, n_images, 1);
+            k_post_tma<7, 13><<<grid, MCRT_TMA_THREADS, post_tma_smem(in_pitch, tc), stream>>>(d_in, cols, rows, in_pitch, taps, tc, col_offset, cols_total, d_out);
+            if (launches) (*launches)++;
+            return;
+        }
+    }
     const int64_t n_scanlines = (int64_t)n_images * cols;
     const int64_t total = n_scanlines * rows;
     size_t smem = 0;
@@ -1235,9 +1417,9 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
         // whole scanlines fit shared memory: one pass over HBM
         dim3 grid((cols + tc - 1) / tc, n_images, 1);
         if (n_axial == 7 && n_lateral == 13)      // the reference's psf<7,13,...> (main.cpp:34)
-            k_post_fused<7, 13><<<grid, MCRT_FUSED_THREADS, smem, stream>>>(d_in, cols, rows, d_axial, 7, d_lateral, 13, flags, tc, col_offset, cols_total, d_out);
+            k_post_fused<7, 13><<<grid, MCRT_FUSED_THREADS, smem, stream>>>(d_in, cols, rows, d_axial, 7, d_lateral, 13, flags, tc, col_offset, cols_total, d_out, in_pitch);
         else
-            k_post_fused<0, 0><<<grid, MCRT_FUSED_THREADS, smem, stream>>>(d_in, cols, rows, d_axial, n_axial, d_lateral, n_lateral, flags, tc, col_offset, cols_total, d_out);
+            k_post_fused<0, 0><<<grid, MCRT_FUSED_THREADS, smem, stream>>>(d_in, cols, rows, d_axial, n_axial, d_lateral, n_lateral, flags, tc, col_offset, cols_total, d_out, in_pitch);
         if (launches) (*launches)++;
         return;
     }
@@ -1250,12 +1432,12 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
         for (int64_t s0 = 0; s0 < n_scanlines; s0 += 65535) {
             const int64_t ns = n_scanlines - s0 < 65535 ? n_scanlines - s0 : 65535;
             ga.y = (unsigned)ns;
-            k_psf_axial<<<ga, 256, smem_ax, stream>>>(cur + s0 * rows, rows, d_axial, n_axial, d_tmp0 + s0 * rows);
+            k_psf_axial<<<ga, 256, smem_ax, stream>>>(cur + s0 * in_pitch, rows, d_axial, n_axial, d_tmp0 + s0 * rows, in_pitch);
             if (launches) (*launches)++;
         }
         float* dst = (flags & 2) ? d_tmp1 : d_out;
         dim3 gl((rows + 255) / 256, (cols + MCRT_PSF_R - 1) / MCRT_PSF_R, n_images);
-        k_psf_lateral<<<gl, 256, 0, stream>>>(cur, d_tmp0, cols, rows, d_lateral, n_axial, n_lateral, col_offset, cols_total, dst, d_lateral_by_row);
+        k_psf_lateral<<<gl, 256, 0, stream>>>(cur, d_tmp0, cols, rows, d_lateral, n_axial, n_lateral, col_offset, cols_total, dst, d_lateral_by_row, in_pitch);
         cur = dst;
         if (launches) (*launches)++;
     }
@@ -1270,6 +1452,13 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
         k_copy<<<grid1d(total, 256), 256, 0, stream>>>(cur, total, d_out);
         if (launches) (*launches)++;
     }
+}
+
+int post_preferred_pitch(int rows, int n_axial, int n_lateral)
+{
+    const int pitch = (rows + 3) & ~3;
+    const float dummy = 0.0f;
+    return post_tma_usable(rows, pitch, n_axial, n_lateral, 3, &dummy, &dummy) && post_tma_smem(pitch, 8) <= MCRT_TMA_SMEM_LIMIT ? pitch : rows;
 }
 
 void launch_log_compress(float* d_img, int n_images, int64_t px_per_image, int* d_max_bits, cudaStream_t stream, int* launches)

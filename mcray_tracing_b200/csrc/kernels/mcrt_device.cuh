@@ -117,6 +117,8 @@ struct AcqDev {
     int element_offset;     // global index of local element 0 (scanline-block runs; 0 otherwise): RNG key, PSF borders
     int voxel_fma_division; // 1: coord / vol_resolution via div_fma was validated exhaustively for this resolution (image.cu)
     int accumulate_windowed;// 1: row-window synchronous accumulate (no columns in HBM) when the scene allows it (image.cu)
+    int rf_pitch;           // row stride (floats) of the raw RF image the accumulate stage writes: rows, or rows rounded up to a
+                            // multiple of 4 so that every scanline starts 16-byte aligned (TMA bulk copies / 128-bit staging in the post kernel)
 };
 
 struct PoseTrigDev { float px, py, pz, cz, sz, cx, sx, cy, sy, pad0, pad1, pad2; };   // = mcrt::PoseTrig, 48 B

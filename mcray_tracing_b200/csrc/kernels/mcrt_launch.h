@@ -133,7 +133,12 @@ cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2
 void launch_post(const float* d_in, int n_images, int cols, int rows, const float* d_axial, int n_axial, const float* d_lateral,
                  int n_lateral, int flags, float* d_tmp0, float* d_tmp1, float* d_out, cudaStream_t stream, int* launches,
                  int col_offset = 0, int cols_total = 0,     // scanline-block runs: global index of scanline 0 / global scanline count
-                 const float* d_lateral_by_row = nullptr);  // depth-dependent lateral PSF: [n_lateral][rows] taps (unfused kernels)
+                 const float* d_lateral_by_row = nullptr,   // depth-dependent lateral PSF: [n_lateral][rows] taps (unfused kernels)
+                 int in_pitch = 0,                          // row stride of d_in in floats (0 = rows); flags & 1 == 0 needs a dense input
+                 const float* h_axial = nullptr, const float* h_lateral = nullptr);   // host copies of the taps: enable the TMA-staged
+                                                                                      // kernel (taps travel as kernel parameters)
+// row pitch the raw RF image should have so that launch_post can stage it with TMA bulk copies (rows rounded up to 4 floats), or rows
+int post_preferred_pitch(int rows, int n_axial, int n_lateral);
 // exhaustive device check (all 2^32 float bit patterns) that the 3-instruction FMA division reproduces the voxel index of
 // coord / resolution for this resolution; enables AcqDev::voxel_fma_division
 cudaError_t validate_fma_division(float resolution, bool* ok);

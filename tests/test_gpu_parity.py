@@ -219,6 +219,22 @@ def test_convolve_and_envelope_bit_exact(api, O, sphere, cols, rows, ka, kl):
     assert np.array_equal(g_both.T, O.envelope(o_conv))
 
 
+@pytest.mark.parametrize("cols,rows", [(256, 465), (37, 465), (50, 466), (8, 64), (45, 639), (300, 17)])
+def test_tma_staged_post_kernel_equals_round1_kernel(api, O, sphere, cols, rows):
+    """The TMA-staged fused post kernel (k_post_tma: one bulk copy per tile, register-blocked taps) against the oracle AND
+    against round 1's k_post_fused (option post_tma = 0), incl. ragged tiles, pitch == rows and rows at the kernel's limits."""
+    rng = np.random.default_rng(cols * 7 + rows)
+    img = rng.normal(size=(rows, cols)).astype(np.float32)
+    img[rng.random(img.shape) < 0.3] = 0.0
+    with api.Simulator(sphere[0], api.default_params(elements=64, samples=1)) as sim:
+        ax, lat = sim.psf_taps()                                     # the reference's 7 x 13 taps
+        new = sim.postprocess(img.T, ax, lat)
+        sim.set_option("post_tma", 0)
+        old = sim.postprocess(img.T, ax, lat)
+    assert np.array_equal(new, old)
+    assert np.array_equal(new.T, O.envelope(O.convolve(img, ax, lat)))
+
+
 def test_scan_convert_bit_exact(api, O, sphere):
     rng = np.random.default_rng(9)
     with api.Simulator(sphere[0], api.default_params(elements=512, samples=1)) as sim:
