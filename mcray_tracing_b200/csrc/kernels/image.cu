@@ -1024,136 +1024,182 @@ struct PostTaps { float a[8]; float l[16]; };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// a / b for integers 0 <= a < b <= 2048 held in floats, correctly rounded, from the correctly rounded reciprocal y = fl(1 / b):
+// Markstein's sequence q0 = a y, r = fma(-q0, b, a) (exact), q = fma(r, y, q0).  Equal to the IEEE quotient for EVERY such pair
+// (exhaustive check: tests/test_host_and_numerics.py::test_envelope_alpha_division_is_exact); 3 FP instructions instead of the
+// ~10 of the IEEE division the reference's alpha = (j - p) / (q - p) compiles to (rfimage.h:80).
+__device__ __forceinline__ float div_small_int(float a, float b, float y)
+{
+    const float q0 = a * y;
+    const float r = __fmaf_rn(-q0, b, a);
+    return __fmaf_rn(r, y, q0);
+}
+
+// PERSISTENT: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Two shared-memory buffers alternate as
+// (raw tile, axial result); while the envelope of tile n runs out of the first, the raw scanlines of tile n + 1 are already
+// streaming into the second (its axial values are dead once the lateral pass is done), so no warp ever waits for HBM after
+// the first tile.
 template <int KA, int KL>
 __global__ void __launch_bounds__(MCRT_TMA_THREADS, 1) k_post_tma(const float* __restrict__ in, const int cols, const int rows, const int pitch,
-                                                                 const __grid_constant__ PostTaps taps, const int TC, const int col_offset,
-                                                                 const int cols_total, float* __restrict__ out)
+                                                                 const __grid_constant__ PostTaps taps, const int TC, const int tiles_per_image,
+                                                                 const int n_tiles, const int col_offset, const int cols_total,
+                                                                 float* __restrict__ out)
 {
     extern __shared__ __align__(128) float sm[];
-    __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ unsigned s_mask[MCRT_TMA_THREADS / 32][MCRT_TMA_MAX_CHUNKS];
-    __shared__ int s_next[MCRT_TMA_THREADS / 32][MCRT_TMA_MAX_CHUNKS];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ float s_rcp[32 * MCRT_TMA_MAX_CHUNKS + 1];  // fl(1 / b), b = 1 .. rows
     const int W = TC + KL - 1;                             // staged scanlines (tile + right halo)
-    float* s_raw = sm;                                     // [W][pitch] raw scanlines; the first TC become the result
-    float* s_ax = sm + (size_t)W * pitch;                  // [W][pitch] axial pass
+    float* const buf0 = sm;                                // [W][pitch]
+    float* const buf1 = sm + (size_t)W * pitch;            // [W][pitch]
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int c0 = blockIdx.x * TC;
-    const int wl = cols - c0 < W ? cols - c0 : W;          // staged scanlines that exist
-    const float* img_in = in + ((size_t)blockIdx.y * cols + c0) * pitch;
-    float* img_out = out + (size_t)blockIdx.y * cols * rows;
-    const unsigned bar = smem_u32(&s_bar);
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
+    const unsigned bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]);
+    // tile t -> first scanline, number of staged scanlines, source address
+    auto issue_load = [&](int t, float* dst, unsigned bar) {
+        const int img = t / tiles_per_image, c0 = (t - img * tiles_per_image) * TC;
+        const int wl = cols - c0 < W ? cols - c0 : W;
         const unsigned bytes = (unsigned)((size_t)wl * pitch * sizeof(float));     // multiple of 16: pitch % 4 == 0
+        const float* src = in + ((size_t)img * cols + c0) * pitch;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(s_raw)), "l"(img_in), "r"(bytes), "r"(bar) : "memory");
+                     ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    };
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    {
-        unsigned done = 0;
-        while (!done) {
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(done) : "r"(bar) : "memory");
-        }
-    }
-    // ---- axial pass (rfimage.h:97-108): warp = scanline, lane = 4 consecutive rows; forward-looking taps, sequential fp32 sum
-    const int Q = pitch >> 2;
-    for (int c = w; c < wl; c += MCRT_TMA_THREADS / 32) {
-        const float4* src4 = reinterpret_cast<const float4*>(s_raw + (size_t)c * pitch);
-        float4* dst4 = reinterpret_cast<float4*>(s_ax + (size_t)c * pitch);
-        for (int q = lane; q < Q; q += 32) {
-            float x[12];
-            const float4 v0 = src4[q];
-            const float4 v1 = q + 1 < Q ? src4[q + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 v2 = q + 2 < Q ? src4[q + 2] : make_float4(0.f, 0.f, 0.f, 0.f);
-            x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-            x[8] = v2.x; x[9] = v2.y; x[10] = v2.z; x[11] = v2.w;
-            float o[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                float convolution = 0;
-#pragma unroll
-                for (int k = 0; k < KA; k++) convolution += x[j + k] * taps.a[k];
-                o[j] = convolution;
-            }
-            dst4[q] = make_float4(o[0], o[1], o[2], o[3]);       // rows outside [KA, rows - KA) are never read below
-        }
-    }
+    for (int i = tid; i <= rows; i += MCRT_TMA_THREADS) s_rcp[i] = i > 0 ? 1.0f / (float)i : 0.0f;
     __syncthreads();
-    // ---- lateral pass (rfimage.h:111-122), into the raw tile; borders keep the raw samples (B-9).  Thread = one pair of
-    // rows x MCRT_TMA_RUN consecutive scanlines; the RUN + KL - 1 axial scanlines they need stream through registers once.
-    {
-        const int P2 = pitch >> 1;                             // row pairs per scanline
-        const int n_runs = TC / MCRT_TMA_RUN;
-        const int run = tid / P2, p = tid - run * P2;
-        if (run < n_runs) {
-            const int cs = run * MCRT_TMA_RUN;
-            const float2* ax2 = reinterpret_cast<const float2*>(s_ax) + p;
-            float2 acc[MCRT_TMA_RUN];
+    if (tid == 0 && (int)blockIdx.x < n_tiles) issue_load(blockIdx.x, buf0, bar0);
+    const int Q = pitch >> 2, P2 = pitch >> 1;
+    const int n_chunks = (rows + 31) >> 5;
+    int n = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, n++) {
+        float* const s_raw = (n & 1) ? buf1 : buf0;        // raw scanlines; the first TC become the result
+        float* const s_ax = (n & 1) ? buf0 : buf1;         // axial pass
+        const int img = t / tiles_per_image, c0 = (t - img * tiles_per_image) * TC;
+        const int wl = cols - c0 < W ? cols - c0 : W;      // staged scanlines that exist
+        float* img_out = out + (size_t)img * cols * rows;
+        {
+            const unsigned bar = (n & 1) ? bar1 : bar0, parity = (unsigned)(n >> 1) & 1u;
+            unsigned done = 0;
+            while (!done) {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            }
+        }
+        // ---- axial pass (rfimage.h:97-108): item = (scanline, block of 32 x 4 rows), lane = 4 consecutive rows; forward-looking
+        // taps, sequential fp32 sum
+        {
+            const int qblocks = (Q + 31) >> 5;
+            for (int it = w; it < wl * qblocks; it += MCRT_TMA_THREADS / 32) {
+                const int c = it / qblocks, q = (it - c * qblocks) * 32 + lane;
+                if (q >= Q) continue;
+                const float4* src4 = reinterpret_cast<const float4*>(s_raw + (size_t)c * pitch);
+                float x[12];
+                const float4 v0 = src4[q];
+                const float4 v1 = q + 1 < Q ? src4[q + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 v2 = q + 2 < Q ? src4[q + 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+                x[8] = v2.x; x[9] = v2.y; x[10] = v2.z; x[11] = v2.w;
+                float o[4];
 #pragma unroll
-            for (int cc = 0; cc < MCRT_TMA_RUN; cc++) acc[cc] = make_float2(0.f, 0.f);
+                for (int j = 0; j < 4; j++) {
+                    float convolution = 0;
 #pragma unroll
-            for (int jj = 0; jj < MCRT_TMA_RUN + KL - 1; jj++) {
-                const int j = cs + jj;
-                const float2 v = j < wl ? ax2[(size_t)j * P2] : make_float2(0.f, 0.f);
+                    for (int k = 0; k < KA; k++) convolution += x[j + k] * taps.a[k];
+                    o[j] = convolution;
+                }
+                reinterpret_cast<float4*>(s_ax + (size_t)c * pitch)[q] = make_float4(o[0], o[1], o[2], o[3]);   // rows outside [KA, rows - KA) are never read below
+            }
+        }
+        __syncthreads();
+        // ---- lateral pass (rfimage.h:111-122), into the raw tile; borders keep the raw samples (B-9).  Thread = one pair of
+        // rows x MCRT_TMA_RUN consecutive scanlines; the RUN + KL - 1 axial scanlines they need stream through registers once.
+        {
+            const int n_runs = TC / MCRT_TMA_RUN;
+            const int run = tid / P2, p = tid - run * P2;
+            if (run < n_runs) {
+                const int cs = run * MCRT_TMA_RUN;
+                const float2* ax2 = reinterpret_cast<const float2*>(s_ax) + p;
+                float2 acc[MCRT_TMA_RUN];
+#pragma unroll
+                for (int cc = 0; cc < MCRT_TMA_RUN; cc++) acc[cc] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int jj = 0; jj < MCRT_TMA_RUN + KL - 1; jj++) {
+                    const int j = cs + jj;
+                    const float2 v = j < wl ? ax2[(size_t)j * P2] : make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int cc = 0; cc < MCRT_TMA_RUN; cc++) {
+                        const int k = jj - cc;                      // compile-time after unrolling
+                        if (k >= 0 && k < KL) { acc[cc].x += v.x * taps.l[k]; acc[cc].y += v.y * taps.l[k]; }
+                    }
+                }
+                const int r0 = 2 * p;
+                const bool ok0 = r0 >= KA && r0 < rows - KA, ok1 = r0 + 1 >= KA && r0 + 1 < rows - KA;
 #pragma unroll
                 for (int cc = 0; cc < MCRT_TMA_RUN; cc++) {
-                    const int k = jj - cc;                      // compile-time after unrolling
-                    if (k >= 0 && k < KL) { acc[cc].x += v.x * taps.l[k]; acc[cc].y += v.y * taps.l[k]; }
+                    const int c = cs + cc, gc = c0 + c;
+                    if (gc < cols && col_offset + gc >= KL / 2 && col_offset + gc < cols_total - KL) {     // global indices
+                        float* dst = s_raw + (size_t)c * pitch + r0;
+                        if (ok0) dst[0] = acc[cc].x;
+                        if (ok1) dst[1] = acc[cc].y;
+                    }
                 }
             }
-            const int r0 = 2 * p;
-            const bool ok0 = r0 >= KA && r0 < rows - KA, ok1 = r0 + 1 >= KA && r0 + 1 < rows - KA;
+        }
+        __syncthreads();
+        // the axial buffer is dead: start streaming the next tile's raw scanlines into it (generic-proxy accesses to it are
+        // ordered before the async-proxy write by the barrier above + the proxy fence)
+        if (tid == 0 && t + (int)gridDim.x < n_tiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue_load(t + gridDim.x, s_ax, (n & 1) ? bar0 : bar1);
+        }
+        // ---- envelope (rfimage.h:54-91): one warp per scanline.  A sample i in [1, rows-2] is a peak iff I[i-1] < I[i] and not
+        // I[i] < I[i+1]; the peak masks of all 32-row chunks and "first peak after the chunk" stay in (warp-uniform) registers.
+        for (int c = w; c < TC; c += MCRT_TMA_THREADS / 32) {
+            if (c0 + c >= cols) continue;                      // warp-uniform
+            const float* I = s_raw + (size_t)c * pitch;
+            float* O = img_out + (size_t)(c0 + c) * rows;
+            unsigned mask[MCRT_TMA_MAX_CHUNKS];
+            int nxt[MCRT_TMA_MAX_CHUNKS];
+            int next = rows;
 #pragma unroll
-            for (int cc = 0; cc < MCRT_TMA_RUN; cc++) {
-                const int c = cs + cc, gc = c0 + c;
-                if (gc < cols && col_offset + gc >= KL / 2 && col_offset + gc < cols_total - KL) {     // global indices
-                    float* dst = s_raw + (size_t)c * pitch + r0;
-                    if (ok0) dst[0] = acc[cc].x;
-                    if (ok1) dst[1] = acc[cc].y;
+            for (int ch = MCRT_TMA_MAX_CHUNKS - 1; ch >= 0; ch--) {
+                mask[ch] = 0u; nxt[ch] = rows;
+                if (ch < n_chunks) {
+                    const unsigned m = peak_mask_smem(I, rows, ch, lane);
+                    mask[ch] = m; nxt[ch] = next;
+                    if (m) next = (ch << 5) + (__ffs(m) - 1);
+                }
+            }
+            const float first = I[0];
+            int last_peak = 0;
+#pragma unroll
+            for (int ch = 0; ch < MCRT_TMA_MAX_CHUNKS; ch++) {
+                if (ch < n_chunks) {
+                    const unsigned m = mask[ch];
+                    const int i = (ch << 5) + lane;
+                    const unsigned le = m & (0xffffffffu >> (31 - lane));
+                    const int p = le ? (ch << 5) + (31 - __clz(le)) : last_peak;
+                    const unsigned gt = lane == 31 ? 0u : (m & (0xffffffffu << (lane + 1)));
+                    const int q = gt ? (ch << 5) + (__ffs(gt) - 1) : nxt[ch];
+                    if (i < rows) {
+                        float r = I[i];
+                        if (q < rows) {
+                            const float last = (p == 0) ? first : fabsf(I[p]);
+                            const float new_peak = fabsf(I[q]);
+                            const int d = q - p;
+                            const float alpha = div_small_int((float)(i - p), (float)d, s_rcp[d]);   // == ((float)i - (float)p) / ((float)q - (float)p)
+                            r = last * (1 - alpha) + new_peak * alpha;
+                        }
+                        O[i] = r;
+                    }
+                    if (m) last_peak = (ch << 5) + (31 - __clz(m));
                 }
             }
         }
-    }
-    __syncthreads();
-    // ---- envelope (rfimage.h:54-91): one warp per scanline, see k_post_fused
-    const int n_chunks = (rows + 31) >> 5;
-    for (int c = w; c < TC; c += MCRT_TMA_THREADS / 32) {
-        if (c0 + c >= cols) continue;                      // warp-uniform
-        const float* I = s_raw + (size_t)c * pitch;
-        float* O = img_out + (size_t)(c0 + c) * rows;
-        int next = rows;
-        for (int ch = n_chunks - 1; ch >= 0; ch--) {
-            const unsigned m = peak_mask_smem(I, rows, ch, lane);
-            if (lane == 0) { s_mask[w][ch] = m; s_next[w][ch] = next; }
-            if (m) next = (ch << 5) + (__ffs(m) - 1);
-        }
-        __syncwarp();
-        int last_peak = 0;
-        for (int ch = 0; ch < n_chunks; ch++) {
-            const unsigned mask = s_mask[w][ch];
-            const int i = (ch << 5) + lane;
-            const unsigned le = mask & (0xffffffffu >> (31 - lane));
-            const int p = le ? (ch << 5) + (31 - __clz(le)) : last_peak;
-            const unsigned gt = lane == 31 ? 0u : (mask & (0xffffffffu << (lane + 1)));
-            const int q = gt ? (ch << 5) + (__ffs(gt) - 1) : s_next[w][ch];
-            if (i < rows) {
-                float r = I[i];
-                if (q < rows) {
-                    const float last = (p == 0) ? I[0] : fabsf(I[p]);
-                    const float new_peak = fabsf(I[q]);
-                    const float alpha = ((float)i - (float)p) / ((float)q - (float)p);
-                    r = last * (1 - alpha) + new_peak * alpha;
-                }
-                O[i] = r;
-            }
-            if (mask) last_peak = (ch << 5) + (31 - __clz(mask));
-        }
-        __syncwarp();
+        __syncthreads();                                       // the next tile's axial pass overwrites this tile's result buffer
     }
 }
 
@@ -1390,7 +1436,7 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
 {
     if (cols_total <= 0) { col_offset = 0; cols_total = cols; }
     if (in_pitch <= 0) in_pitch = rows;
-    if (!d_lateral_by_row && n_images <= 65535 && post_tma_usable(rows, in_pitch, n_axial, n_lateral, flags, h_axial, h_lateral)) {
+    if (!d_lateral_by_row && (int64_t)n_images * cols < 0x7fffffff && post_tma_usable(rows, in_pitch, n_axial, n_lateral, flags, h_axial, h_lateral)) {
         // widest tile of 8 / 16 / 32 scanlines that fits; few images (latency mode): narrower tiles so the grid still covers the SMs
         int tc = 32;
         while (tc > 8 && (post_tma_smem(in_pitch, tc) > MCRT_TMA_SMEM_LIMIT || (int64_t)((cols + tc - 1) / tc) * n_images < 148)) tc >>= 1;
@@ -1398,8 +1444,13 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
             PostTaps taps;
             for (int k = 0; k < 8; k++) taps.a[k] = k < 7 ? h_axial[k] : 0.0f;
             for (int k = 0; k < 16; k++) taps.l[k] = k < 13 ? h_lateral[k] : 0.0f;
-            dim3 grid((cols + tc - 1) / tc, n_images, 1);
-            k_post_tma<7, 13><<<grid, MCRT_TMA_THREADS, post_tma_smem(in_pitch, tc), stream>>>(d_in, cols, rows, in_pitch, taps, tc, col_offset, cols_total, d_out);
+            const int tiles_per_image = (cols + tc - 1) / tc;
+            const int64_t n_tiles = (int64_t)tiles_per_image * n_images;
+            int sms = 148;
+            { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+            const int grid = (int)(n_tiles < sms ? n_tiles : sms);                 // persistent: one CTA per SM
+            k_post_tma<7, 13><<<grid, MCRT_TMA_THREADS, post_tma_smem(in_pitch, tc), stream>>>(d_in, cols, rows, in_pitch, taps, tc, tiles_per_image, (int)n_tiles,
+                                                                                             col_offset, cols_total, d_out);
             if (launches) (*launches)++;
             return;
         }

@@ -1178,6 +1178,16 @@ void orc_numerics(int32_t op, int64_t n, const double* a, const double* b, doubl
             case 6: r = mc_pow(a[i], b[i]); break;
             case 7: r = mc_exp(a[i]); break;
             case 8: r = mc_log(a[i]); break;
+            case 9: {
+                // Markstein's division step in fp32 with a true IEEE fma, as the device evaluates the envelope's
+                // alpha = (j - p) / (q - p) (k_post_tma, div_small_int): q0 = a y, r = fma(-q0, b, a), q = fma(r, y, q0), y = fl(1 / b)
+                const float fa = (float)a[i], fb = (float)b[i];
+                const float y = 1.0f / fb;
+                const float q0 = fa * y;
+                const float rr = __builtin_fmaf(-q0, fb, fa);
+                r = (double)__builtin_fmaf(rr, y, q0);
+                break;
+            }
             default: break;
         }
         out[i] = r;

@@ -1,6 +1,6 @@
 #!/bin/bash
 # r02g: TMA-staged fused post kernel (k_post_tma) -- parity, A/B against round 1's k_post_fused (option post_tma), bench
-TAG=r02g
+TAG=r02i
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -12 | tee gpurun_out/${TAG}_pytest.log
 python scripts/ab_option.py post_tma=0,1 512 2>&1 | tee gpurun_out/${TAG}_ab_post_tma.txt

@@ -77,6 +77,19 @@ def test_contract_double_functions_accuracy(O):
     assert vals[6] == 1.0 and np.isnan(vals[7])
 
 
+def test_envelope_alpha_division_is_exact(O):
+    """k_post_tma evaluates the envelope's alpha = (j - p) / (q - p) (rfimage.h:80) with Markstein's three-instruction division
+    from a correctly rounded reciprocal instead of the IEEE division; exhaustive over every pair the kernel can meet
+    (0 <= a < b <= 2048, the kernel is limited to 640 rows) the two are bit-identical."""
+    b = np.arange(1, 2049, dtype=np.float64)
+    A, B = np.meshgrid(np.arange(0, 2048, dtype=np.float64), b, indexing="ij")
+    keep = A < B
+    a, bb = A[keep], B[keep]
+    got = O.numerics(9, a, bb).astype(np.float32)
+    ref = a.astype(np.float32) / bb.astype(np.float32)
+    assert got.size > 2_000_000 and np.array_equal(got, ref)
+
+
 def test_philox_known_answer(O):
     """Philox4x32-10 known-answer vectors of Random123 (kat_vectors): zero counter/key and the
     'pi' vector; checked through an independent pure-Python restatement of the round function."""
