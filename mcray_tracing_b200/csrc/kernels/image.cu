@@ -1039,7 +1039,9 @@ __device__ __forceinline__ float div_small_int(float a, float b, float y)
 // (raw tile, axial result); while the envelope of tile n runs out of the first, the raw scanlines of tile n + 1 are already
 // streaming into the second (its axial values are dead once the lateral pass is done), so no warp ever waits for HBM after
 // the first tile.
-template <int KA, int KL>
+// NCH > 0: compile-time number of 32-row chunks of a scanline (15 for the reference's 465 rows): the envelope's unrolled chunk
+// loops carry no guards; NCH == 0: any rows <= 32 * MCRT_TMA_MAX_CHUNKS.
+template <int KA, int KL, int NCH>
 __global__ void __launch_bounds__(MCRT_TMA_THREADS, 1) k_post_tma(const float* __restrict__ in, const int cols, const int rows, const int pitch,
                                                                  const __grid_constant__ PostTaps taps, const int TC, const int tiles_per_image,
                                                                  const int n_tiles, const int col_offset, const int cols_total,
@@ -1072,7 +1074,11 @@ __global__ void __launch_bounds__(MCRT_TMA_THREADS, 1) k_post_tma(const float* _
     __syncthreads();
     if (tid == 0 && (int)blockIdx.x < n_tiles) issue_load(blockIdx.x, buf0, bar0);
     const int Q = pitch >> 2, P2 = pitch >> 1;
-    const int n_chunks = (rows + 31) >> 5;
+    const int n_chunks = NCH > 0 ? NCH : (rows + 31) >> 5;
+    constexpr int kMaxChunks = NCH > 0 ? NCH : MCRT_TMA_MAX_CHUNKS;
+    // (scanline, block of 32 quads) items of the axial pass: blocks per scanline is a power of two for the reference geometry
+    const int qblocks = (Q + 31) >> 5;
+    const int qshift = (qblocks & (qblocks - 1)) == 0 ? 31 - __clz(qblocks) : -1;
     int n = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, n++) {
         float* const s_raw = (n & 1) ? buf1 : buf0;        // raw scanlines; the first TC become the result
@@ -1091,9 +1097,8 @@ __global__ void __launch_bounds__(MCRT_TMA_THREADS, 1) k_post_tma(const float* _
         // ---- axial pass (rfimage.h:97-108): item = (scanline, block of 32 x 4 rows), lane = 4 consecutive rows; forward-looking
         // taps, sequential fp32 sum
         {
-            const int qblocks = (Q + 31) >> 5;
             for (int it = w; it < wl * qblocks; it += MCRT_TMA_THREADS / 32) {
-                const int c = it / qblocks, q = (it - c * qblocks) * 32 + lane;
+                const int c = qshift >= 0 ? it >> qshift : it / qblocks, q = (it - c * qblocks) * 32 + lane;
                 if (q >= Q) continue;
                 const float4* src4 = reinterpret_cast<const float4*>(s_raw + (size_t)c * pitch);
                 float x[12];
@@ -1161,11 +1166,11 @@ __global__ void __launch_bounds__(MCRT_TMA_THREADS, 1) k_post_tma(const float* _
             if (c0 + c >= cols) continue;                      // warp-uniform
             const float* I = s_raw + (size_t)c * pitch;
             float* O = img_out + (size_t)(c0 + c) * rows;
-            unsigned mask[MCRT_TMA_MAX_CHUNKS];
-            int nxt[MCRT_TMA_MAX_CHUNKS];
+            unsigned mask[kMaxChunks];
+            int nxt[kMaxChunks];
             int next = rows;
 #pragma unroll
-            for (int ch = MCRT_TMA_MAX_CHUNKS - 1; ch >= 0; ch--) {
+            for (int ch = kMaxChunks - 1; ch >= 0; ch--) {
                 mask[ch] = 0u; nxt[ch] = rows;
                 if (ch < n_chunks) {
                     const unsigned m = peak_mask_smem(I, rows, ch, lane);
@@ -1176,7 +1181,7 @@ __global__ void __launch_bounds__(MCRT_TMA_THREADS, 1) k_post_tma(const float* _
             const float first = I[0];
             int last_peak = 0;
 #pragma unroll
-            for (int ch = 0; ch < MCRT_TMA_MAX_CHUNKS; ch++) {
+            for (int ch = 0; ch < kMaxChunks; ch++) {
                 if (ch < n_chunks) {
                     const unsigned m = mask[ch];
                     const int i = (ch << 5) + lane;
@@ -1409,7 +1414,9 @@ cudaError_t init_image_kernels()
     // per-device function attribute; must not be issued inside a stream capture
     cudaError_t e = cudaFuncSetAttribute(k_post_fused<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MCRT_FUSED_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_post_tma<7, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, MCRT_TMA_SMEM_LIMIT);
+    e = cudaFuncSetAttribute(k_post_tma<7, 13, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, MCRT_TMA_SMEM_LIMIT);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_post_tma<7, 13, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MCRT_TMA_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_post_fused<7, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, MCRT_FUSED_SMEM_LIMIT);
 }
@@ -1449,8 +1456,12 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
             int sms = 148;
             { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
             const int grid = (int)(n_tiles < sms ? n_tiles : sms);                 // persistent: one CTA per SM
-            k_post_tma<7, 13><<<grid, MCRT_TMA_THREADS, post_tma_smem(in_pitch, tc), stream>>>(d_in, cols, rows, in_pitch, taps, tc, tiles_per_image, (int)n_tiles,
-                                                                                             col_offset, cols_total, d_out);
+            if (((rows + 31) >> 5) == 15)          // the reference's 465-row image (main.cpp:30, rfimage.h:180)
+                k_post_tma<7, 13, 15><<<grid, MCRT_TMA_THREADS, post_tma_smem(in_pitch, tc), stream>>>(d_in, cols, rows, in_pitch, taps, tc, tiles_per_image,
+                                                                                                     (int)n_tiles, col_offset, cols_total, d_out);
+            else
+                k_post_tma<7, 13, 0><<<grid, MCRT_TMA_THREADS, post_tma_smem(in_pitch, tc), stream>>>(d_in, cols, rows, in_pitch, taps, tc, tiles_per_image,
+                                                                                                    (int)n_tiles, col_offset, cols_total, d_out);
             if (launches) (*launches)++;
             return;
         }
