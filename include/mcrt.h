@@ -182,6 +182,10 @@ int mcrt_ipc_open(int device, const unsigned char handle64[64], void** peer_ptr)
 int mcrt_ipc_close(int device, void* peer_ptr);
 /* dst / src: device pointers (local or peer-mapped); cuda_stream: a cudaStream_t passed as void* (NULL = default stream) */
 int mcrt_copy_async(int device, void* dst, const void* src, size_t bytes, void* cuda_stream);
+/* strided variant (cudaMemcpy2DAsync): `height` rows of `width_bytes`; used to deposit the frames of a round-robin pose
+ * partition (rank r holds poses r, r + G, ...) into the collector's buffer in global pose order with ONE copy */
+int mcrt_copy2d_async(int device, void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t height,
+                      void* cuda_stream);
 
 /* Ray-tree mode (option "ray_tree" = segment budget per path > 0): BOTH children of every boundary hit
  * are followed, as in the cited paper, instead of the one Monte-Carlo branch this fork of the reference keeps

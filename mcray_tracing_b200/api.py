@@ -71,7 +71,7 @@ EXPORTS = ["mcrt_default_params", "mcrt_create", "mcrt_create_from_arrays", "mcr
            "mcrt_get_stats", "mcrt_set_option", "mcrt_simulate", "mcrt_simulate_async", "mcrt_trace_debug", "mcrt_closest_hit",
            "mcrt_transducer_elements", "mcrt_accumulate", "mcrt_postprocess", "mcrt_scan_convert", "mcrt_get_psf_taps",
            "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe", "mcrt_load_obj", "mcrt_scene_probe", "mcrt_host_tables", "mcrt_simulate_scanlines", "mcrt_bmode", "mcrt_set_mesh_origin", "mcrt_set_mesh_vertices", "mcrt_trace_tree_debug", "mcrt_device_alloc", "mcrt_set_psf_depth_profile",
-           "mcrt_device_free", "mcrt_ipc_export", "mcrt_ipc_open", "mcrt_ipc_close", "mcrt_copy_async"]
+           "mcrt_device_free", "mcrt_ipc_export", "mcrt_ipc_open", "mcrt_ipc_close", "mcrt_copy_async", "mcrt_copy2d_async"]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
@@ -115,6 +115,7 @@ def lib():
         L.mcrt_ipc_open.argtypes = [C.c_int, vp, vp]
         L.mcrt_ipc_close.argtypes = [C.c_int, vp]
         L.mcrt_copy_async.argtypes = [C.c_int, vp, vp, C.c_size_t, vp]
+        L.mcrt_copy2d_async.argtypes = [C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]
         L.mcrt_set_mesh_origin.argtypes = [vp, C.c_int32, vp]
         L.mcrt_set_mesh_vertices.argtypes = [vp, C.c_int32, vp, C.c_int64]
         L.mcrt_closest_hit.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
@@ -172,6 +173,11 @@ def ipc_close(device: int, ptr: int):
 
 def copy_async(device: int, dst: int, src: int, nbytes: int, stream: int = 0):
     _check(lib().mcrt_copy_async(int(device), C.c_void_p(dst), C.c_void_p(src), int(nbytes), C.c_void_p(stream) if stream else None))
+
+
+def copy2d_async(device: int, dst: int, dst_pitch: int, src: int, src_pitch: int, width_bytes: int, height: int, stream: int = 0):
+    _check(lib().mcrt_copy2d_async(int(device), C.c_void_p(dst), int(dst_pitch), C.c_void_p(src), int(src_pitch), int(width_bytes), int(height),
+                                   C.c_void_p(stream) if stream else None))
 
 
 def default_params(**kw) -> Params:

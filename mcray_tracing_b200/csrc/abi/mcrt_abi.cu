@@ -135,6 +135,12 @@ struct mcrt_ctx {
     bool count_traversal = false;
     bool log_compress = false;             // rfimage.h:127-136, commented out in the reference
     int* d_max_bits = nullptr;             // [cap_poses] per-image maximum (ordered-int encoding)
+    // mcrt_bmode workspace (grow-only: a cudaMalloc / cudaFree pair of ~0.75 GB per call cost more than the kernels)
+    float *bm_gain = nullptr, *bm_env = nullptr, *bm_cmp = nullptr, *bm_scan = nullptr;
+    unsigned char* bm_q = nullptr;
+    int* bm_max = nullptr;
+    int bm_cap = 0;
+    int frame_stride = 1;                  // frame index of pose i of a call = first_frame + i * frame_stride (option "frame_stride")
     bool post_tma = true;                  // TMA-staged fused post kernel (option "post_tma"; 0 = round 1's k_post_fused, for A/B and equivalence tests)
     int first_hit_dedup = 1;               // bounce 0 traced once per element (TraceBuffers::first_hits) when samples >= 4: 0 off, 1 large calls, 2 always
     int ordered_compaction = 1;            // order-preserving compaction between bounces (TraceBuffers::warp_counts): 0 off, 1 large calls, 2 always
@@ -282,7 +288,7 @@ void enqueue_trace(mcrt_ctx* c, int pose0, int n, int slot, cudaStream_t s, int*
 {
     const size_t p0 = (size_t)pose0 * c->aq.elements * c->aq.samples;
     FrameDev fr;
-    fr.poses = c->d_poses + pose0; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = n; fr.frame_offset = pose0;
+    fr.poses = c->d_poses + pose0; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = n; fr.frame_offset = pose0; fr.frame_stride = c->frame_stride;
     TraceBuffers tb = c->tb;
     tb.paths.origin_intensity += p0; tb.paths.dir_state += p0; tb.paths.distance += p0;
     tb.segments += p0 * c->aq.max_depth; tb.n_segments += p0;
@@ -419,7 +425,7 @@ void run_tree_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* lau
     CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, 2 * sizeof(unsigned long long), s));
     CUDA_TRY(cudaMemsetAsync(c->tb.counters, 0, sizeof(int) * (size_t)kMaxSub * (c->aq.max_depth + 1), s));
     FrameDev fr;
-    fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = n; fr.frame_offset = 0;
+    fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = n; fr.frame_offset = 0; fr.frame_stride = c->frame_stride;
     TreeBuffers t = c->tree;
     t.trav_counters = c->count_traversal ? c->d_trav : nullptr;
     if (c->profile_stages) CUDA_TRY(cudaEventRecord(c->ev_a, s));
@@ -465,7 +471,7 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
             if (c->upload_pending) { CUDA_TRY(cudaEventSynchronize(c->ev_up)); c->upload_pending = false; }
             for (int i = 0; i < n; i++) c->h_poses[i] = pose_trig(poses[p0 + i]);
             c->h_seed_frame[0] = seed;
-            c->h_seed_frame[1] = first_frame + (uint64_t)p0;
+            c->h_seed_frame[1] = first_frame + (uint64_t)p0 * (uint64_t)c->frame_stride;
             CUDA_TRY(cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig) * (size_t)n, cudaMemcpyHostToDevice, s));
             CUDA_TRY(cudaMemcpyAsync(c->d_seed_frame, c->h_seed_frame, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
             CUDA_TRY(cudaEventRecord(c->ev_up, s));
@@ -658,6 +664,7 @@ void destroy_impl(mcrt_ctx* c)
     free_workspace(c);
     dev_free(c->d_meshes); dev_free(c->d_materials); dev_free(c->bvh.nodes); dev_free(c->bvh.tris); dev_free(c->d_nodes4);
     dev_free(c->d_nodes8); dev_free(c->d_tris8);
+    dev_free(c->bm_gain); dev_free(c->bm_env); dev_free(c->bm_cmp); dev_free(c->bm_scan); dev_free(c->bm_q); dev_free(c->bm_max);
     dev_free(c->d_elem_sincos); dev_free(c->d_axial); dev_free(c->d_lateral); dev_free(c->d_lat_by_row); dev_free(c->d_map_x); dev_free(c->d_map_y);
     dev_free(c->d_seed_frame); dev_free(c->d_steps); dev_free(c->d_trav);
     if (c->h_seed_frame) cudaFreeHost(c->h_seed_frame);
@@ -1011,6 +1018,14 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
         free_workspace(c);
         c->aq.accumulate_windowed = (value != 0 && accumulate_windowed_supported(c->sc, c->aq)) ? 1 : 0;
     }
+    else if (n == "frame_stride") {
+        // frame (Philox counter) of pose i of a call = first_frame + i * stride: a sweep dealt out round-robin to G GPUs (rank r
+        // simulates poses r, r + G, ...) keeps its global frame indices with stride G, so N GPUs stay bit-identical to one
+        if (value < 1 || value > 65536) return fail(MCRT_ERR_INVALID, "frame_stride: 1 .. 65536");
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear();
+        c->frame_stride = (int)value;
+    }
     else if (n == "post_tma") {
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear();
@@ -1066,7 +1081,7 @@ int mcrt_simulate_scanlines(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, u
         CUDA_TRY(cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig), cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemcpyAsync(c->d_seed_frame, c->h_seed_frame, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
         FrameDev fr;
-        fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos + e0; fr.seed_frame = c->d_seed_frame; fr.n_poses = 1; fr.frame_offset = 0;
+        fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos + e0; fr.seed_frame = c->d_seed_frame; fr.n_poses = 1; fr.frame_offset = 0; fr.frame_stride = 1;
         int launches = 0;
         CUDA_TRY(cudaMemsetAsync(c->tb.counters, 0, sizeof(int) * (size_t)kMaxSub * (c->aq.max_depth + 1), s));
         CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, 2 * sizeof(unsigned long long), s));
@@ -1100,7 +1115,7 @@ int mcrt_trace_debug(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, uint64_t
         CUDA_TRY(cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaMemcpyAsync(c->d_seed_frame, c->h_seed_frame, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
         FrameDev fr;
-        fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = 1; fr.frame_offset = 0;
+        fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = 1; fr.frame_offset = 0; fr.frame_stride = 1;
         int launches = 0;
         launch_trace(c->sc, c->aq, fr, c->tb, c->sm_count, c->stream, &launches);
         CUDA_TRY(cudaGetLastError());
@@ -1194,6 +1209,16 @@ int mcrt_copy_async(int device, void* dst, const void* src, size_t bytes, void* 
     });
 }
 
+int mcrt_copy2d_async(int device, void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t height, void* cuda_stream)
+{
+    if (!dst || !src) return fail(MCRT_ERR_INVALID, "mcrt_copy2d_async: null argument");
+    return guarded("mcrt_copy2d_async", [&]() {
+        CUDA_TRY(cudaSetDevice(device));
+        CUDA_TRY(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, height, cudaMemcpyDefault, (cudaStream_t)cuda_stream));
+        return MCRT_OK;
+    });
+}
+
 int mcrt_trace_tree_debug(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, uint64_t frame, int64_t capacity, mcrt_segment* segments,
                           int32_t* path, int32_t* node, int64_t* n_out)
 {
@@ -1209,7 +1234,7 @@ int mcrt_trace_tree_debug(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, uin
         CUDA_TRY(cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig), cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemcpyAsync(c->d_seed_frame, c->h_seed_frame, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
         FrameDev fr;
-        fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = 1; fr.frame_offset = 0;
+        fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = 1; fr.frame_offset = 0; fr.frame_stride = 1;
         int launches = 0;
         TreeBuffers t = c->tree;
         t.trav_counters = nullptr;
@@ -1301,7 +1326,7 @@ int mcrt_transducer_elements(mcrt_ctx* c, const mcrt_pose* pose, float* pos3, fl
         c->h_poses[0] = pose_trig(*pose);
         cudaError_t e = cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig), cudaMemcpyHostToDevice, c->stream);
         FrameDev fr;
-        fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = 1; fr.frame_offset = 0;
+        fr.poses = c->d_poses; fr.elem_sincos = c->d_elem_sincos; fr.seed_frame = c->d_seed_frame; fr.n_poses = 1; fr.frame_offset = 0; fr.frame_stride = 1;
         if (e == cudaSuccess) { launch_elements(c->aq, fr, d_pos, d_dir, c->stream); e = cudaGetLastError(); }
         if (e == cudaSuccess) e = cudaMemcpyAsync(pos3, d_pos, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(dir3, d_dir, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream);
@@ -1443,38 +1468,36 @@ int mcrt_bmode(mcrt_ctx* c, const float* env_in, int32_t n_images, const mcrt_bm
             const double depth_cm = (double)r * c->params.depth_cm / (double)rows;
             gain[r] = (float)mc_exp(((double)bp->gain_db + (double)bp->tgc_db_per_cm * depth_cm) * (2.30258509299404568402 / 20.0));
         }
-        float *d_gain = nullptr, *d_env = nullptr, *d_cmp = nullptr, *d_scan = nullptr;
-        unsigned char* d_q = nullptr;
-        int* d_max = nullptr;
         cudaStream_t s = c->stream;
-        auto cleanup = [&]() { dev_free(d_gain); dev_free(d_env); dev_free(d_cmp); dev_free(d_scan); dev_free(d_q); dev_free(d_max); };
-        try {
-            dev_alloc(d_gain, (size_t)rows); dev_alloc(d_cmp, px * n_images); dev_alloc(d_max, (size_t)n_images);
-            CUDA_TRY(cudaMemcpyAsync(d_gain, gain.data(), sizeof(float) * rows, cudaMemcpyHostToDevice, s));
-            const float* src = env_in;
-            if (!is_device_pointer(env_in)) {
-                dev_alloc(d_env, px * n_images);
-                CUDA_TRY(cudaMemcpyAsync(d_env, env_in, sizeof(float) * px * n_images, cudaMemcpyHostToDevice, s));
-                src = d_env;
-            }
-            int launches = 0;
-            launch_bmode(src, n_images, cols, rows, d_gain, bp->dynamic_range_db, d_cmp, d_max, s, &launches);
-            if (compressed_out)
-                CUDA_TRY(cudaMemcpyAsync(compressed_out, d_cmp, sizeof(float) * px * n_images,
-                                         is_device_pointer(compressed_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
-            if (bmode8_out) {
-                dev_alloc(d_scan, ns * n_images); dev_alloc(d_q, ns * n_images);
-                launch_scan_convert(d_cmp, n_images, cols, rows, c->d_map_x, c->d_map_y, c->params.scan_rows, c->params.scan_cols, d_scan, s, &launches);
-                launch_quantize8(d_scan, (int64_t)(ns * n_images), d_q, s, &launches);
-                CUDA_TRY(cudaMemcpyAsync(bmode8_out, d_q, ns * n_images, is_device_pointer(bmode8_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
-            }
-            CUDA_TRY(cudaGetLastError());
+        if (n_images > c->bm_cap) {
             CUDA_TRY(cudaStreamSynchronize(s));
-            c->stats = mcrt_stats{};
-            c->stats.poses = n_images; c->stats.kernel_launches = launches;
-            c->stats_pending = false;
-        } catch (...) { cleanup(); throw; }
-        cleanup();
+            dev_free(c->bm_gain); dev_free(c->bm_env); dev_free(c->bm_cmp); dev_free(c->bm_scan); dev_free(c->bm_q); dev_free(c->bm_max);
+            c->bm_cap = 0;
+            dev_alloc(c->bm_gain, (size_t)rows); dev_alloc(c->bm_env, px * n_images); dev_alloc(c->bm_cmp, px * n_images);
+            dev_alloc(c->bm_scan, ns * n_images); dev_alloc(c->bm_q, ns * n_images); dev_alloc(c->bm_max, (size_t)n_images);
+            c->bm_cap = n_images;
+        }
+        CUDA_TRY(cudaMemcpyAsync(c->bm_gain, gain.data(), sizeof(float) * rows, cudaMemcpyHostToDevice, s));
+        const float* src = env_in;
+        if (!is_device_pointer(env_in)) {
+            CUDA_TRY(cudaMemcpyAsync(c->bm_env, env_in, sizeof(float) * px * n_images, cudaMemcpyHostToDevice, s));
+            src = c->bm_env;
+        }
+        int launches = 0;
+        launch_bmode(src, n_images, cols, rows, c->bm_gain, bp->dynamic_range_db, c->bm_cmp, c->bm_max, s, &launches);
+        if (compressed_out)
+            CUDA_TRY(cudaMemcpyAsync(compressed_out, c->bm_cmp, sizeof(float) * px * n_images,
+                                     is_device_pointer(compressed_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+        if (bmode8_out) {
+            launch_scan_convert(c->bm_cmp, n_images, cols, rows, c->d_map_x, c->d_map_y, c->params.scan_rows, c->params.scan_cols, c->bm_scan, s, &launches);
+            launch_quantize8(c->bm_scan, (int64_t)(ns * n_images), c->bm_q, s, &launches);
+            CUDA_TRY(cudaMemcpyAsync(bmode8_out, c->bm_q, ns * n_images, is_device_pointer(bmode8_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+        }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(s));        // gain.data() is a stack-owned staging buffer: the upload must be complete
+        c->stats = mcrt_stats{};
+        c->stats.poses = n_images; c->stats.kernel_launches = launches;
+        c->stats_pending = false;
         return MCRT_OK;
     });
 }

@@ -38,7 +38,9 @@ struct FrameDev {
     const float2* elem_sincos;           // [elements] (sin a_t, cos a_t)
     const unsigned long long* seed_frame;   // device: {Philox seed, first frame}; kept in HBM so a captured graph stays valid
     int n_poses;
-    int frame_offset;                    // added to the first frame: index of poses[0] within the call's batch
+    int frame_offset;                    // index of poses[0] within the call's batch
+    int frame_stride;                    // frame (Philox counter) of pose i = first frame + (frame_offset + i) * frame_stride; 1 unless the
+                                         // poses of a sweep are dealt out to the GPUs round-robin (option "frame_stride")
 };
 
 struct TraceBuffers {

@@ -174,7 +174,7 @@ __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq
     const int element = rem / aq.samples;
     const int sample = rem - element * aq.samples;
     const uint64_t seed = __ldg(&fr.seed_frame[0]);
-    const uint32_t frame = (uint32_t)(__ldg(&fr.seed_frame[1]) + (uint64_t)fr.frame_offset + (uint64_t)pose);
+    const uint32_t frame = (uint32_t)(__ldg(&fr.seed_frame[1]) + ((uint64_t)fr.frame_offset + (uint64_t)pose) * (uint64_t)fr.frame_stride);
 
     float3 from, dir;
     float intensity;
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(128, 5) k_tree_level(const SceneDev sc, const 
             const int pose = path / ES;
             const int rem = path - pose * ES;
             const int element = rem / aq.samples, sample = rem - element * aq.samples;
-            const uint32_t frame = (uint32_t)(__ldg(&fr.seed_frame[1]) + (uint64_t)fr.frame_offset + (uint64_t)pose);
+            const uint32_t frame = (uint32_t)(__ldg(&fr.seed_frame[1]) + ((uint64_t)fr.frame_offset + (uint64_t)pose) * (uint64_t)fr.frame_stride);
             const DevMaterial med = sh.materials[media];
             const float r_length = rp_max_ray_length(med.attenuation, intensity, aq.frequency);
             const float3 to = v_add(from, v_scl(make_float3(sc.spacing[0] * dir.x, sc.spacing[1] * dir.y, sc.spacing[2] * dir.z), r_length / 100.0f));

@@ -49,16 +49,30 @@ if rank == 0:
     t = peer.slot_tensor(1).cpu().numpy()
     sizes = sweep.all_shard_sizes(len(poses), world)
     deposited = np.concatenate([t[r * F: r * F + sizes[r]] for r in range(world)])
+# round-robin deal (rank r: poses r, r + G, ...; option frame_stride = G), NCCL gather and strided peer deposit
+sim.set_option("frame_stride", world)
+res_il = sweep.run_sweep(block, poses, (sim.cols, sim.rows), dev, seed_first_frame=300, interleave=True)
+idx = sweep.shard_indices(len(poses), world, rank, interleave=True)
+local.zero_()
+sim.simulate_device(poses[idx], local.data_ptr(), seed=21, first_frame=300 + rank)
+sim.set_option("frame_stride", 1)
+torch.cuda.synchronize(dev)
+peer.deposit(0, local[:len(idx)], comm, interleave=True)
+peer.commit(comm)
+comm.synchronize()
+deposited_il = peer.slot_tensor(0).cpu().numpy()[:len(poses)] if rank == 0 else None
 peer.close()
 if rank == 0:
     single = sim.simulate(poses, seed=21, first_frame=300)
+    assert np.array_equal(res_il.cpu().numpy(), single), "round-robin sweep (NCCL gather) differs from the 1-GPU sweep"
+    assert np.array_equal(deposited_il, single), "round-robin sweep (strided peer deposit) differs from the 1-GPU sweep"
     assert np.array_equal(deposited, single), "peer-deposited sweep differs from the 1-GPU sweep"
     assert np.array_equal(res.cpu().numpy(), single), "pose-sharded sweep differs from the 1-GPU sweep"
     whole = sim.simulate(pose[None, :], seed=21, first_frame=9)[0]
     assert np.array_equal(frame.cpu().numpy(), whole), "scanline-block frame differs from the 1-GPU frame"
     print("OK multi", world)
 else:
-    assert res is None and frame is None
+    assert res is None and frame is None and res_il is None
 sim.close()
 dist.destroy_process_group()
 """

@@ -194,6 +194,11 @@ def test_shard_bounds_partition():
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [e - s for s, e in b]
             assert max(sizes) - min(sizes) <= 1 and sizes == sweep.all_shard_sizes(n, w)
+            # the round-robin deal: a partition too, rank r holds r, r + w, ...
+            idx = [sweep.shard_indices(n, w, r, interleave=True) for r in range(w)]
+            assert sorted(np.concatenate(idx).tolist()) == list(range(n)) and [len(i) for i in idx] == sweep.interleaved_sizes(n, w)
+            assert all((i % w == r).all() for r, i in enumerate(idx))
+            assert [sweep.shard_indices(n, w, r).tolist() for r in range(w)] == [list(range(*b[r])) for r in range(w)]
 
 
 _WORKER = r"""
@@ -204,17 +209,22 @@ from mcray_tracing_b200 import sweep
 dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
 n = int(sys.argv[1])
 poses = np.arange(n * 6, dtype=np.float32).reshape(n, 6)
+stride = 1
 def fake(block, first_frame, out):          # stands in for Simulator.simulate_device: a pure function of (pose, global frame)
     for i in range(len(block)):
-        out[i] = torch.arange(12, dtype=torch.float32).reshape(3, 4) * float(first_frame + i + 1) + float(block[i, 0])
+        out[i] = torch.arange(12, dtype=torch.float32).reshape(3, 4) * float(first_frame + i * stride + 1) + float(block[i, 0])
 res = sweep.run_sweep(fake, poses, (3, 4), torch.device("cpu"), seed_first_frame=100)
+stride = dist.get_world_size()               # option frame_stride = G of the round-robin deal
+res_il = sweep.run_sweep(fake, poses, (3, 4), torch.device("cpu"), seed_first_frame=100, interleave=True)
+stride = 1
 if dist.get_rank() == 0:
     single = torch.empty((n, 3, 4))
     fake(poses, 100, single)
     assert res.shape == single.shape and torch.equal(res, single), "sharded sweep differs from the single-rank sweep"
+    assert res_il.shape == single.shape and torch.equal(res_il, single), "round-robin sweep differs from the single-rank sweep"
     print("OK", n)
 else:
-    assert res is None
+    assert res is None and res_il is None
 dist.destroy_process_group()
 """
 
