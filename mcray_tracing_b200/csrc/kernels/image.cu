@@ -677,54 +677,61 @@ __global__ void __launch_bounds__(256) k_reduce_samples(const float* __restrict_
 // ---- long-scanline path (rows that do not fit the fused kernel's shared memory, BASELINE config 5) ----
 // Register-blocked so each loaded sample feeds MCRT_PSF_R outputs: 2 + ~1/R instructions per tap and
 // output instead of a load + multiply + add + loop overhead per tap.
-#define MCRT_PSF_R 8                  // consecutive outputs per thread
-#define MCRT_PSF_CHUNK (256 * MCRT_PSF_R)   // output rows per CTA of k_psf_axial
+#define MCRT_PSF_R 8                  // consecutive scanlines per thread (lateral pass)
+#define MCRT_PSF_RA 8                 // consecutive rows per thread (axial pass).  16 cuts the instruction count by 12 % (2 LDS + 1 branch per
+                                      // 32 tap applications) but leaves a third of every CTA's threads idle on 8333-row scanlines: 0.51 vs 0.44 ms
+#define MCRT_PSF_CHUNK (256 * MCRT_PSF_RA)   // most output rows per CTA of k_psf_axial
 
-// logical row index within the staged chunk -> shared-memory word: one pad word per MCRT_PSF_R words, so
-// the lanes of a warp (whose windows start MCRT_PSF_R apart) hit distinct banks
-__host__ __device__ __forceinline__ int psf_pad(int i) { return i + (i >> 3); }
+// logical row index within the staged chunk -> shared-memory word: one pad word per MCRT_PSF_RA words, so
+// the lanes of a warp (whose windows start MCRT_PSF_RA apart) hit distinct banks
+__host__ __device__ __forceinline__ int psf_pad(int i) { return i + i / MCRT_PSF_RA; }
 
-// Axial pass (rfimage.h:97-108).  CTA = one MCRT_PSF_CHUNK-row piece of one scanline, staged through shared
-// memory (coalesced 128 B loads); thread t owns outputs [8t, 8t+8) and slides an 8-sample register window
-// along the taps.  For every output the taps are applied in order k = 0.. with separate multiply and add
-// (the reference's sequential fp32 sum).  Rows outside [ka, rows-ka) are never read downstream.
+// Axial pass (rfimage.h:97-108).  CTA = one piece of one scanline, staged through shared memory (coalesced 128 B
+// loads); thread t owns MCRT_PSF_RA consecutive outputs and slides a register window of that many samples along the taps.  For every
+// output the taps are applied in order k = 0.. with separate multiply and add (the reference's sequential fp32 sum).
+// Rows outside [ka, rows-ka) are never read downstream.
 __global__ void __launch_bounds__(256) k_psf_axial(const float* __restrict__ in, const int rows, const float* __restrict__ taps, const int ka,
-                                                  float* __restrict__ out, const int in_pitch)
+                                                  float* __restrict__ out, const int in_pitch, const int chunk_rows)
 {
-    extern __shared__ float s_row[];                       // psf_pad(MCRT_PSF_CHUNK + ka + MCRT_PSF_R) words
-    __shared__ float s_taps[MCRT_MAX_TAPS];
+    // chunk_rows <= MCRT_PSF_CHUNK, a multiple of MCRT_PSF_RA: the scanline is cut into EVEN pieces (round 1: 4 x 2048 + 141 rows
+    // for 8333, whose fifth CTA staged and synchronised for 7 % of a chunk)
+    extern __shared__ float s_row[];                       // psf_pad(chunk_rows + ka + MCRT_PSF_RA) words
+    __shared__ float s_taps[MCRT_MAX_TAPS + MCRT_PSF_RA];
     const int tid = threadIdx.x;
-    const int chunk0 = blockIdx.x * MCRT_PSF_CHUNK;        // first output row of this CTA
+    const int chunk0 = blockIdx.x * chunk_rows;            // first output row of this CTA
     const float* src = in + (size_t)blockIdx.y * in_pitch;
     float* dst = out + (size_t)blockIdx.y * rows;
     for (int i = tid; i < ka; i += blockDim.x) s_taps[i] = taps[i];
-    const int n_stage = MCRT_PSF_CHUNK + ka + MCRT_PSF_R;
+    const int n_stage = chunk_rows + ka + MCRT_PSF_RA;
     for (int i = tid; i < n_stage; i += blockDim.x) {
         const int r = chunk0 + i;
         s_row[psf_pad(i)] = r < rows ? __ldg(&src[r]) : 0.0f;
     }
     __syncthreads();
-    const int l0 = tid * MCRT_PSF_R;                       // first output row of this thread, chunk-local
+    const int l0 = tid * MCRT_PSF_RA;                      // first output row of this thread, chunk-local
     const int r0 = chunk0 + l0;
-    if (r0 >= rows - ka || r0 + MCRT_PSF_R <= ka) return;
-    float acc[MCRT_PSF_R], win[MCRT_PSF_R];
+    if (l0 >= chunk_rows || r0 >= rows - ka || r0 + MCRT_PSF_RA <= ka) return;
+    float acc[MCRT_PSF_RA], win[MCRT_PSF_RA];
 #pragma unroll
-    for (int j = 0; j < MCRT_PSF_R; j++) { acc[j] = 0.0f; win[j] = s_row[psf_pad(l0 + j)]; }
-    for (int k0 = 0; k0 < ka; k0 += MCRT_PSF_R) {
+    for (int j = 0; j < MCRT_PSF_RA; j++) { acc[j] = 0.0f; win[j] = s_row[psf_pad(l0 + j)]; }
+    // the window refill of tap k reads logical row l0 + k + R = R (tid + 1) + k, i.e. padded word (R + 1) (tid + 1) + (R + 1) (k / R) + k % R:
+    // a pointer that advances R + 1 words per group of R taps plus a compile-time offset -- no address arithmetic in the tap loop
+    const float* wp = s_row + psf_pad(l0 + MCRT_PSF_RA);
+    const float* tp = s_taps;
+    for (int k0 = 0; k0 < ka; k0 += MCRT_PSF_RA, wp += MCRT_PSF_RA + 1, tp += MCRT_PSF_RA) {
 #pragma unroll
-        for (int kk = 0; kk < MCRT_PSF_R; kk++) {
-            const int k = k0 + kk;
-            if (k < ka) {
-                const float t = s_taps[k];
-                // window invariant: win[(kk + j) & 7] == sample at row l0 + k + j
+        for (int kk = 0; kk < MCRT_PSF_RA; kk++) {
+            if (k0 + kk < ka) {
+                const float t = tp[kk];
+                // window invariant: win[(kk + j) % R] == sample at row l0 + k + j
 #pragma unroll
-                for (int j = 0; j < MCRT_PSF_R; j++) acc[j] += win[(kk + j) & (MCRT_PSF_R - 1)] * t;
-                win[kk] = s_row[psf_pad(l0 + k + MCRT_PSF_R)];   // slot kk held row l0+k, now row l0+k+8
+                for (int j = 0; j < MCRT_PSF_RA; j++) acc[j] += win[(kk + j) & (MCRT_PSF_RA - 1)] * t;
+                win[kk] = wp[kk];                                  // slot kk held row l0+k, now row l0+k+R
             }
         }
     }
 #pragma unroll
-    for (int j = 0; j < MCRT_PSF_R; j++) {
+    for (int j = 0; j < MCRT_PSF_RA; j++) {
         const int r = r0 + j;
         if (r >= ka && r < rows - ka) dst[r] = acc[j];
     }
@@ -732,12 +739,13 @@ __global__ void __launch_bounds__(256) k_psf_axial(const float* __restrict__ in,
 
 // Lateral pass (rfimage.h:111-122) + untouched borders (B-9).  Thread = one row, MCRT_PSF_R consecutive
 // scanlines; lanes walk consecutive rows, so every load/store is coalesced and no shared memory is needed.
+// BYROW: depth-dependent lateral PSF, tap k of RF row r = taps_by_row[k * rows + r].
+template <bool BYROW>
 __global__ void __launch_bounds__(256) k_psf_lateral(const float* __restrict__ raw, const float* __restrict__ axial_buf, const int cols,
                                                     const int rows, const float* __restrict__ taps, const int ka, const int kl,
                                                     const int col_offset, const int cols_total, float* __restrict__ out,
                                                     const float* __restrict__ taps_by_row, const int raw_pitch)
 {
-    // taps_by_row != nullptr: depth-dependent lateral PSF, tap k of RF row r = taps_by_row[k * rows + r]
     __shared__ float s_taps[MCRT_MAX_TAPS];
     for (int i = threadIdx.x; i < kl; i += blockDim.x) s_taps[i] = taps[i];
     __syncthreads();
@@ -745,36 +753,41 @@ __global__ void __launch_bounds__(256) k_psf_lateral(const float* __restrict__ r
     if (r >= rows) return;
     const int c0 = blockIdx.y * MCRT_PSF_R;
     const size_t img = (size_t)blockIdx.z * cols * rows;
-    const float* ax = axial_buf + img;
     const bool row_ok = r >= ka && r < rows - ka;
+    // border rule in GLOBAL scanline indices (a scanline-block run holds scanlines col_offset.. of cols_total);
     // does any of the 8 scanlines get convolved at all?
-    // border rule in GLOBAL scanline indices (a scanline-block run holds scanlines col_offset.. of cols_total)
     const bool any = row_ok && (col_offset + c0 + MCRT_PSF_R > kl / 2) && (col_offset + c0 < cols_total - kl);
     float acc[MCRT_PSF_R], win[MCRT_PSF_R];
     if (any) {
-        auto ld = [&](int c) -> float { return c < cols ? __ldg(&ax[(size_t)c * rows + r]) : 0.0f; };
+        // scanline c0 + j of this row; the pointer walks one scanline (rows floats) per tap
+        const float* p = axial_buf + img + (size_t)c0 * rows + r;
+        const int c_left = cols - c0;                          // scanlines that exist from c0 on
 #pragma unroll
-        for (int j = 0; j < MCRT_PSF_R; j++) { acc[j] = 0.0f; win[j] = ld(c0 + j); }
+        for (int j = 0; j < MCRT_PSF_R; j++) { acc[j] = 0.0f; win[j] = j < c_left ? __ldg(p + (size_t)j * rows) : 0.0f; }
+        p += (size_t)MCRT_PSF_R * rows;
+        const float* tr = BYROW ? taps_by_row + r : nullptr;
         for (int k0 = 0; k0 < kl; k0 += MCRT_PSF_R) {
 #pragma unroll
             for (int kk = 0; kk < MCRT_PSF_R; kk++) {
                 const int k = k0 + kk;
                 if (k < kl) {
-                    const float t = taps_by_row ? __ldg(&taps_by_row[(size_t)k * rows + r]) : s_taps[k];
+                    const float t = BYROW ? __ldg(tr + (size_t)k * rows) : s_taps[k];
+                    // window invariant: win[(kk + j) & 7] == axial value of scanline c0 + k + j
 #pragma unroll
                     for (int j = 0; j < MCRT_PSF_R; j++) acc[j] += win[(kk + j) & (MCRT_PSF_R - 1)] * t;
-                    win[kk] = ld(c0 + k + MCRT_PSF_R);
+                    win[kk] = k + MCRT_PSF_R < c_left ? __ldg(p) : 0.0f;
+                    p += rows;
                 }
             }
         }
     }
+    float* o = out + img + (size_t)c0 * rows + r;
+    const float* rw = raw + ((size_t)blockIdx.z * cols + c0) * raw_pitch + r;
 #pragma unroll
     for (int j = 0; j < MCRT_PSF_R; j++) {
         const int c = c0 + j;
         if (c >= cols) break;
-        const size_t o = img + (size_t)c * rows + r;
-        out[o] = (any && col_offset + c >= kl / 2 && col_offset + c < cols_total - kl)
-                     ? acc[j] : __ldg(&raw[((size_t)blockIdx.z * cols + c) * raw_pitch + r]);
+        o[(size_t)j * rows] = (any && col_offset + c >= kl / 2 && col_offset + c < cols_total - kl) ? acc[j] : __ldg(rw + (size_t)j * raw_pitch);
     }
 }
 
@@ -843,6 +856,66 @@ __global__ void __launch_bounds__(256) k_envelope_lerp(const float* __restrict__
             r = last * (1 - alpha) + new_peak * alpha;
         }
         out[idx] = r;
+    }
+}
+
+// Long scanlines, round 2: ONE kernel (round 1: k_peak_masks + a fully parallel k_envelope_lerp that paid a 64-bit division and two
+// mask scans per SAMPLE, 190 instruction slots per pixel).  Same arithmetic as k_post_fused's envelope: bit-identical.
+#define MCRT_ENV_WARPS 8
+__global__ void __launch_bounds__(MCRT_ENV_WARPS * 32) k_envelope_stream(const float* __restrict__ in, const int64_t n_scanlines, const int rows,
+                                                                        const int words, float* __restrict__ out)
+{
+    // one CTA per scanline: the 32-row chunks are independent once every chunk knows the last peak before it and the first peak
+    // after it, so the warps take chunks round-robin (many independent loads in flight) and only the tiny scan over the chunk
+    // masks in between is serial
+    extern __shared__ unsigned s_env[];                    // masks[words], next[words], last[words]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned* mask = s_env;
+    int* nxt = reinterpret_cast<int*>(mask + words);
+    int* lst = nxt + words;
+    for (int64_t sl = blockIdx.x; sl < n_scanlines; sl += gridDim.x) {
+        const float* I = in + sl * rows;
+        float* O = out + sl * rows;
+        for (int ch = w; ch < words; ch += MCRT_ENV_WARPS) {
+            const int i = (ch << 5) + lane;
+            const float v = i < rows ? __ldg(&I[i]) : 0.0f;
+            const float vm = (i >= 1 && i < rows) ? __ldg(&I[i - 1]) : 0.0f;
+            const float vp = (i + 1 < rows) ? __ldg(&I[i + 1]) : 0.0f;
+            const bool peak = (i >= 1) && (i + 1 < rows) && (vm < v) && !(v < vp);
+            const unsigned m = __ballot_sync(0xffffffffu, peak);
+            if (lane == 0) mask[ch] = m;
+        }
+        __syncthreads();
+        // first peak after chunk ch / last peak before chunk ch (0 = the virtual first peak): peaks are a few samples apart in RF
+        // data, so the scans almost always stop at the neighbouring word
+        for (int ch = threadIdx.x; ch < words; ch += blockDim.x) {
+            int q = rows;
+            for (int c = ch + 1; c < words; c++) { const unsigned m = mask[c]; if (m) { q = (c << 5) + (__ffs(m) - 1); break; } }
+            int p = 0;
+            for (int c = ch - 1; c >= 0; c--) { const unsigned m = mask[c]; if (m) { p = (c << 5) + (31 - __clz(m)); break; } }
+            nxt[ch] = q; lst[ch] = p;
+        }
+        __syncthreads();
+        const float first = __ldg(&I[0]);
+        for (int ch = w; ch < words; ch += MCRT_ENV_WARPS) {
+            const unsigned m = mask[ch];
+            const int i = (ch << 5) + lane;
+            const unsigned le = m & (0xffffffffu >> (31 - lane));
+            const int p = le ? (ch << 5) + (31 - __clz(le)) : lst[ch];
+            const unsigned gt = lane == 31 ? 0u : (m & (0xffffffffu << (lane + 1)));
+            const int q = gt ? (ch << 5) + (__ffs(gt) - 1) : nxt[ch];
+            if (i < rows) {
+                float r = __ldg(&I[i]);
+                if (q < rows) {
+                    const float last = (p == 0) ? first : fabsf(__ldg(&I[p]));
+                    const float new_peak = fabsf(__ldg(&I[q]));
+                    const float alpha = ((float)i - (float)p) / ((float)q - (float)p);
+                    r = last * (1 - alpha) + new_peak * alpha;
+                }
+                O[i] = r;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -1414,6 +1487,8 @@ cudaError_t init_image_kernels()
     // per-device function attribute; must not be issued inside a stream capture
     cudaError_t e = cudaFuncSetAttribute(k_post_fused<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MCRT_FUSED_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_envelope_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);     // rows <= 32768
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_post_tma<7, 13, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, MCRT_TMA_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_post_tma<7, 13, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MCRT_TMA_SMEM_LIMIT);
@@ -1427,7 +1502,7 @@ int post_launch_count(int cols, int rows, int n_lateral, int flags, int n_images
     (void)cols;
     if ((flags & 3) && fused_tile_cols(rows, n_lateral, flags, &smem) > 0 && n_images <= 65535) return 1;
     const int64_t n_scanlines = (int64_t)n_images * cols;
-    return ((flags & 1) ? (int)((n_scanlines + 65534) / 65535) + 1 : 0) + ((flags & 2) ? 2 : ((flags & 1) ? 0 : 1));
+    return ((flags & 1) ? (int)((n_scanlines + 65534) / 65535) + 1 : 0) + ((flags & 2) ? 1 : ((flags & 1) ? 0 : 1));
 }
 
 // the TMA-staged kernel needs both passes, the reference's tap counts, a 16-byte row pitch and scanlines that fit shared memory
@@ -1488,28 +1563,35 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
     // long scanlines: register-blocked axial / lateral passes, mask-based parallel envelope
     const float* cur = d_in;
     if (flags & 1) {
-        const size_t smem_ax = sizeof(float) * (size_t)(psf_pad(MCRT_PSF_CHUNK + n_axial + MCRT_PSF_R) + 1);
-        dim3 ga((rows + MCRT_PSF_CHUNK - 1) / MCRT_PSF_CHUNK, (unsigned)n_scanlines, 1);
+        // even chunks: as few CTAs per scanline as fit MCRT_PSF_CHUNK, all the same size
+        const int n_ch = (rows + MCRT_PSF_CHUNK - 1) / MCRT_PSF_CHUNK;
+        const int chunk_rows = (((rows + n_ch - 1) / n_ch) + MCRT_PSF_RA - 1) / MCRT_PSF_RA * MCRT_PSF_RA;
+        const size_t smem_ax = sizeof(float) * (size_t)(psf_pad(chunk_rows + n_axial + 2 * MCRT_PSF_RA) + 1);
+        dim3 ga((rows + chunk_rows - 1) / chunk_rows, (unsigned)n_scanlines, 1);
         if (n_scanlines > 65535) ga = dim3(ga.x, 65535, 1);   // guarded below
         for (int64_t s0 = 0; s0 < n_scanlines; s0 += 65535) {
             const int64_t ns = n_scanlines - s0 < 65535 ? n_scanlines - s0 : 65535;
             ga.y = (unsigned)ns;
-            k_psf_axial<<<ga, 256, smem_ax, stream>>>(cur + s0 * in_pitch, rows, d_axial, n_axial, d_tmp0 + s0 * rows, in_pitch);
+            k_psf_axial<<<ga, 256, smem_ax, stream>>>(cur + s0 * in_pitch, rows, d_axial, n_axial, d_tmp0 + s0 * rows, in_pitch, chunk_rows);
             if (launches) (*launches)++;
         }
         float* dst = (flags & 2) ? d_tmp1 : d_out;
         dim3 gl((rows + 255) / 256, (cols + MCRT_PSF_R - 1) / MCRT_PSF_R, n_images);
-        k_psf_lateral<<<gl, 256, 0, stream>>>(cur, d_tmp0, cols, rows, d_lateral, n_axial, n_lateral, col_offset, cols_total, dst, d_lateral_by_row, in_pitch);
+        if (d_lateral_by_row)
+            k_psf_lateral<true><<<gl, 256, 0, stream>>>(cur, d_tmp0, cols, rows, d_lateral, n_axial, n_lateral, col_offset, cols_total, dst, d_lateral_by_row, in_pitch);
+        else
+            k_psf_lateral<false><<<gl, 256, 0, stream>>>(cur, d_tmp0, cols, rows, d_lateral, n_axial, n_lateral, col_offset, cols_total, dst, nullptr, in_pitch);
         cur = dst;
         if (launches) (*launches)++;
     }
     if (flags & 2) {
-        // the peak masks live in the (now free) axial scratch buffer: rows/32 words per scanline
+        // one CTA per scanline; the per-chunk peak masks live in shared memory (3 words per 32 rows)
         const int words = (rows + 31) >> 5;
-        unsigned* masks = reinterpret_cast<unsigned*>((flags & 1) ? d_tmp0 : d_tmp1);
-        k_peak_masks<<<grid1d(n_scanlines * words * 32, 256), 256, 0, stream>>>(cur, n_scanlines, rows, words, masks);
-        k_envelope_lerp<<<grid1d(total, 256), 256, 0, stream>>>(cur, masks, n_scanlines, rows, words, d_out);
-        if (launches) (*launches) += 2;
+        const size_t smem_env = sizeof(unsigned) * 3 * (size_t)words;
+        int64_t g = n_scanlines;
+        if (g > 148 * 64) g = 148 * 64;
+        k_envelope_stream<<<(int)g, MCRT_ENV_WARPS * 32, smem_env, stream>>>(cur, n_scanlines, rows, words, d_out);
+        if (launches) (*launches) += 1;
     } else if (!(flags & 1)) {
         k_copy<<<grid1d(total, 256), 256, 0, stream>>>(cur, total, d_out);
         if (launches) (*launches)++;
