@@ -400,6 +400,24 @@ def volume_raw() -> np.ndarray:
     return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(256, 256, 256, 2))
 
 
+def ref_accumulate_loop(R, segs, nseg, materials) -> np.ndarray:
+    """The reference's own accumulation loop (main.cpp:106-144, compiled into the reference probe) on oracle-layout segments
+    [512][5][D] -> raw RF image [465][512].  The segment's medium is copied at emission (SURVEY B-1)."""
+    E, S, D = segs.shape
+    assert (E, S) == (512, 5), "the reference's sizes are compile-time constants (main.cpp:26-27)"
+    f = np.zeros((E, S, D, 12), np.float32)
+    f[..., 0:3] = segs["from"]; f[..., 3:6] = segs["to"]; f[..., 6:9] = segs["dir"]
+    f[..., 9] = segs["reflected_intensity"]; f[..., 10] = segs["initial_intensity"]; f[..., 11] = segs["attenuation"]
+    dist = np.ascontiguousarray(segs["distance_traveled"], np.float64)
+    mats = np.asarray(materials, np.float32).reshape(-1, 8)
+    mid = np.clip(segs["media_id"], 0, len(mats) - 1)
+    media3 = np.ascontiguousarray(mats[mid][..., [2, 3, 4]], np.float32)         # mu0, mu1, sigma
+    n = np.ascontiguousarray(nseg, np.int32)
+    out = np.zeros((465, 512), np.float32)
+    R.ref_accumulate_loop(_p(f), _p(dist), _p(media3), _p(n), C.c_int(D), _p(out))
+    return out
+
+
 def numerics(op: int, a, b=None) -> np.ndarray:
     a = np.ascontiguousarray(a, np.float64)
     b = np.ascontiguousarray(b if b is not None else np.zeros_like(a), np.float64)

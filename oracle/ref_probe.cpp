@@ -5,9 +5,9 @@
 // rf_image / tinyobj+objloader code through a C ABI so tests/golden/make_golden.py can record
 // known-answer vectors and tests can pin the oracle restatement to the reference.
 //
-// What cannot be probed: scene.cpp (needs Bullet's collision world) and the body of main()
-// (main.cpp:102-148).  main.cpp's constants block (lines 17-37) is extracted at build time into
-// oracle/_ref/main_constants.inc by the Makefile.
+// What cannot be probed: scene.cpp's cast_rays (needs Bullet's collision world).  main.cpp's constants block (lines 17-37), its
+// echo-accumulation loop (lines 106-144) and scene::distance (scene.cpp:341-346) are extracted verbatim at build time into
+// oracle/_ref/*.inc by the Makefile and compiled here (ref_accumulate_loop).
 #define private public      // reach rf_image::intensities / map_x / map_y (test-only)
 #define protected public
 #include "rfimage.h"        // pulls psf.h, units.h and the cv::Mat shim
@@ -28,6 +28,11 @@
 
 using psf_ref = psf_;
 using rf_ref = rf_image_;
+
+// scene::distance is the one member of scene the accumulation loop calls; the class around it is Bullet-bound, so only the
+// member's own definition is taken from scene.cpp (the extracted text defines scene::distance)
+struct scene { units::length::millimeter_t distance(const btVector3& from, const btVector3& to) const; };
+#include "_ref/scene_distance.inc"
 
 extern "C" {
 
@@ -190,6 +195,35 @@ void ref_rf_mapping(float* map_x, float* map_y)
 {
     memcpy(map_x, rf()->map_x.data.data(), sizeof(float) * 400 * 500);
     memcpy(map_y, rf()->map_y.data.data(), sizeof(float) * 400 * 500);
+}
+
+// ---- main.cpp:106-144, the echo-accumulation loop, verbatim -----------------------------------
+// segs: [E][S][D][12] = from3, to3, dir3, reflected_intensity, initial_intensity, attenuation; dist_mm: [E][S][D];
+// media3: [E][S][D][3] = mu0, mu1, sigma of the segment's medium (copied at emission: SURVEY B-1); nseg: [E][S].
+// Runs the reference's own loop over its own rf_image / volume and returns `intensities` ([465][512]).
+void ref_accumulate_loop(const float* segs, const double* dist_mm, const float* media3, const int* nseg, int max_depth, float* rf_out)
+{
+    using rays_t = std::array<std::array<std::vector<ray_physics::segment>, samples_te>, transducer_elements>;
+    std::unique_ptr<rays_t> rays_ptr(new rays_t());
+    std::vector<material> mats((size_t)transducer_elements * samples_te * max_depth);
+    for (size_t e = 0; e < transducer_elements; e++)
+        for (size_t s = 0; s < samples_te; s++)
+            for (int k = 0; k < nseg[e * samples_te + s]; k++) {
+                const size_t i = (e * samples_te + s) * max_depth + k;
+                const float* f = segs + 12 * i;
+                material& m = mats[i];
+                m = material{};
+                m.mu0 = media3[3 * i]; m.mu1 = media3[3 * i + 1]; m.sigma = media3[3 * i + 2]; m.attenuation = f[11];
+                (*rays_ptr)[e][s].emplace_back(ray_physics::segment{btVector3(f[0], f[1], f[2]), btVector3(f[3], f[4], f[5]), btVector3(f[6], f[7], f[8]),
+                                                                     f[9], f[10], f[11], units::length::millimeter_t(dist_mm[i]), m});
+            }
+    auto& rays = *rays_ptr;
+    auto& rf_image = *rf();
+    rf_image.clear();                                   // main.cpp:102
+    scene scene;
+    const auto& texture_volume = *ref_vol();
+#include "_ref/main_accumulate_loop.inc"
+    memcpy(rf_out, rf_image.intensities.data.data(), sizeof(float) * rf_image.intensities.data.size());
 }
 
 // ---- tinyobj + objloader.h --------------------------------------------------------------------

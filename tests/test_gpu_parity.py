@@ -2,10 +2,13 @@
 the CPU oracle on the same seeded inputs.  Bars: bit-exact for hit ids / bounce counts / every
 segment field / PSF / envelope / scan conversion; RF after accumulation within
 |gpu - oracle| <= 1e-4 * max(|oracle|, 1e-3 * max|oracle image|)."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
 
 
 def _tol(ref):
@@ -217,6 +220,22 @@ def test_convolve_and_envelope_bit_exact(api, O, sphere, cols, rows, ka, kl):
     assert np.array_equal(g_conv.T, o_conv)
     assert np.array_equal(g_env.T, O.envelope(img))
     assert np.array_equal(g_both.T, O.envelope(o_conv))
+
+
+def test_accumulate_against_the_reference_loop_golden(api, O, sphere):
+    """mcrt_accumulate (k_accumulate_win) on the fixed segments against the committed image of the REFERENCE'S OWN accumulation
+    loop (main.cpp:106-144 compiled from the reference, tests/golden/reference_accumulate_loop.npz): 1e-4 relative (the GPU
+    sums the samples of a scanline per row, the reference path by path)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_accumulate", GOLD / "make_golden_accumulate.py")
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    gold = np.load(GOLD / "reference_accumulate_loop.npz")["rf"]
+    segs, nseg, mats, p, osc = mg.fixed_segments()
+    with api.Simulator(sphere[0], api.default_params(elements=512, samples=5)) as sim:
+        rf = sim.accumulate(segs, nseg).T
+        assert sim.stats().late_echoes == 0
+    assert np.array_equal(rf != 0, gold != 0)
+    assert np.all(np.abs(rf - gold) <= _tol(gold)), np.abs(rf - gold).max()
 
 
 @pytest.mark.parametrize("cols,rows", [(256, 465), (37, 465), (50, 466), (8, 64), (45, 639), (300, 17)])

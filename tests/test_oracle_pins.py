@@ -226,6 +226,63 @@ def test_add_echo_row_mapping(G, O):
     assert np.array_equal(np.unique(mine[mine >= 0]).astype(np.int32), G["echo_nonzero_rows"])
 
 
+def test_add_echo_row_mapping_through_orc_accumulate(G, O, assets_dirs):
+    """The same golden echo times, this time THROUGH orc_accumulate (the oracle's restatement of main.cpp:106-144): every echo
+    becomes a one-step segment whose start time is the golden time, in a medium that scatters exactly 1 (sigma 0, mu0 1,
+    density threshold -inf); the image must show each echo in the reference's row."""
+    A = O.load_scene_py(assets_dirs["sphere"] / "sphere.scene")
+    mats = np.asarray(A["materials"], np.float32).reshape(-1, 8).copy()
+    mats[0, 2:5] = (1.0, -3.0e38, 0.0)                       # mu0, mu1 (density threshold), sigma
+    mats[0, 1] = 0.0                                         # no attenuation
+    A = dict(A); A["materials"] = mats
+    osc = O.OracleScene(A)
+    p = O.default_params(elements=512, samples=5)
+    times, cols, want_row = G["echo_times"], G["echo_cols"], G["echo_row_of_time"]
+    dist = times * 1500.0 / 1000.0
+    back = ((dist * 1000) / 1) / 1500.0                      # main.cpp:114 as the oracle evaluates it
+    keep = back == times                                     # times the mm -> us conversion reproduces bit for bit
+    assert keep.mean() > 0.5
+    segs = np.zeros((512, 5, 10), O.SEGMENT_DTYPE)
+    nseg = np.zeros((512, 5), np.int32)
+    expect = np.zeros((465, 512), np.float32)
+    used = 0
+    for t, d, c, r in zip(times[keep], dist[keep], cols[keep], want_row[keep]):
+        slot = np.flatnonzero(nseg[c] < 10)
+        if len(slot) == 0:
+            continue
+        s_ = slot[0]; k = nseg[c, s_]
+        sg = segs[c, s_, k]
+        sg["from"] = (0.0, 0.0, 0.0); sg["to"] = (0.04, 0.0, 0.0); sg["dir"] = (1.0, 0.0, 0.0)     # 0.4 mm: exactly one march step
+        sg["reflected_intensity"] = 0.0; sg["initial_intensity"] = 1.0; sg["attenuation"] = 0.0
+        sg["distance_traveled"] = d; sg["media_id"] = 0; sg["tri_id"] = -1
+        nseg[c, s_] = k + 1
+        if r >= 0:
+            expect[r, c] += 1.0
+        used += 1
+    rf, steps = osc.accumulate(p, segs, nseg)
+    assert used > 1500 and steps <= used
+    assert np.array_equal(rf, expect)
+
+
+def test_accumulate_loop_bit_exact_to_the_reference_loop(O):
+    """LOOP-LEVEL pin: the reference's own echo-accumulation loop (main.cpp:106-144, extracted verbatim at build time and
+    compiled into the reference probe around the real rf_image / volume / scene::distance) ran on fixed segments and its raw
+    `intensities` image is committed (tests/golden/make_golden_accumulate.py).  orc_accumulate on the same segments must
+    reproduce it BIT FOR BIT -- row mapping, march, voxel lookup, iterated decay, closing echoes, summation order."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_accumulate", GOLD / "make_golden_accumulate.py")
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    gold = np.load(GOLD / "reference_accumulate_loop.npz")
+    segs, nseg, mats, p, osc = mg.fixed_segments()
+    assert int(nseg.sum()) == int(gold["n_segments_total"][0])
+    rf, steps = osc.accumulate(p, segs, nseg)
+    assert np.count_nonzero(gold["rf"]) > 40000 and steps > 500000
+    assert np.array_equal(rf, gold["rf"])
+    R = O.ref_probe()
+    if R is not None and hasattr(R, "ref_accumulate_loop"):              # live: the reference loop itself, where its sources are mounted
+        assert np.array_equal(O.ref_accumulate_loop(R, segs, nseg, mats), gold["rf"])
+
+
 def _img(G):
     seed = int(G["img_seed"][0])
     src = np.random.default_rng(seed).standard_normal((465, 512)).astype(np.float32)
