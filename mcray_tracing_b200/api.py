@@ -207,11 +207,13 @@ class Simulator:
         if isinstance(scene, (str, os.PathLike)):
             rc = L.mcrt_create(str(scene).encode(), C.byref(self.params), int(device), C.byref(h))
         else:
-            self._keep = {k: np.ascontiguousarray(scene[k]) for k in ("materials", "mesh_material_inside", "mesh_material_outside",
-                                                                        "mesh_vascular", "mesh_deltas", "tri_offsets", "tri_vertices")}
+            # explicit dtypes: the C side reads raw memory, and the arrays must outlive the call (pointers are taken from _keep only)
+            dt = {"materials": np.float32, "mesh_material_inside": np.int32, "mesh_material_outside": np.int32, "mesh_vascular": np.int32,
+                  "mesh_deltas": np.float32, "tri_offsets": np.int64, "tri_vertices": np.float32}
+            self._keep = {k: np.ascontiguousarray(scene[k], dtype=t) for k, t in dt.items()}
             k = self._keep
             sa = SceneArrays()
-            sa.n_materials = len(k["materials"]); sa.materials8 = _p(k["materials"].astype(np.float32, copy=False))
+            sa.n_materials = len(k["materials"].reshape(-1, 8)); sa.materials8 = _p(k["materials"])
             sa.starting_material = int(scene["starting_material"]); sa.n_meshes = len(k["mesh_material_inside"])
             sa.mesh_material_inside = _p(k["mesh_material_inside"]); sa.mesh_material_outside = _p(k["mesh_material_outside"])
             sa.mesh_vascular = _p(k["mesh_vascular"]); sa.mesh_deltas = _p(k["mesh_deltas"]); sa.tri_offsets = _p(k["tri_offsets"])

@@ -29,10 +29,63 @@
 using psf_ref = psf_;
 using rf_ref = rf_image_;
 
-// scene::distance is the one member of scene the accumulation loop calls; the class around it is Bullet-bound, so only the
-// member's own definition is taken from scene.cpp (the extracted text defines scene::distance)
-struct scene { units::length::millimeter_t distance(const btVector3& from, const btVector3& to) const; };
+// ---- a stand-in for the Bullet-bound parts of class scene (scene.h:19-76) -------------------------------------------------
+// The reference's scene::cast_rays<S,E> (scene.cpp:50-183), distance_in_mm / enlarge (:281-298) and distance (:341-346) are
+// compiled VERBATIM from the extracted text below; only the collision world behind m_dynamicsWorld->rayTest is replaced: it
+// forwards the query to a caller-supplied closest-hit function (the oracle's), so what gets pinned is everything the reference
+// does AROUND the ray test (ray set-up, max_ray_length / enlarge, the 1 mm start offset, travel, hit_boundary, segment
+// emission, path termination, the bounce / sample / element loop order), not Bullet's triangle arithmetic.
+#include <ctime>
+#include <iostream>
+#include <sstream>
+#include <cassert>
+#include <random>
+struct btCollisionObject { void* m_user = nullptr; void* getUserPointer() const { return m_user; } };
+struct btCollisionWorld {
+    struct ClosestRayResultCallback {
+        ClosestRayResultCallback(const btVector3& f, const btVector3& t) : m_rayFromWorld(f), m_rayToWorld(t) {}
+        bool hasHit() const { return m_collisionObject != nullptr; }
+        btVector3 m_rayFromWorld, m_rayToWorld, m_hitPointWorld, m_hitNormalWorld;
+        const btCollisionObject* m_collisionObject = nullptr;
+    };
+};
+typedef int (*ref_hit_fn)(const void* ctx, const float* from3, const float* to3, int use_bvh, float* out_f7, int* out_mesh);   // = orc_closest_hit
+struct shim_world {
+    ref_hit_fn fn = nullptr;
+    const void* ctx = nullptr;
+    std::vector<btCollisionObject> bodies;
+    void rayTest(const btVector3& from, const btVector3& to, btCollisionWorld::ClosestRayResultCallback& cb) const
+    {
+        const float f[3] = {from.x(), from.y(), from.z()}, t[3] = {to.x(), to.y(), to.z()};
+        float o[7];
+        int m = -1;
+        if (fn(ctx, f, t, 1, o, &m) >= 0) {
+            cb.m_hitPointWorld = btVector3(o[1], o[2], o[3]);
+            cb.m_hitNormalWorld = btVector3(o[4], o[5], o[6]);
+            cb.m_collisionObject = &bodies[(size_t)m];
+        }
+    }
+};
+class scene
+{
+    using transducer_ = transducer<512>;
+public:
+    template<unsigned int sample_count,unsigned int ray_count>
+    std::array<std::array<std::vector<ray_physics::segment>,sample_count>, ray_count>cast_rays(transducer_ & transducer);
+    units::length::millimeter_t distance(const btVector3 & from, const btVector3 & to) const;
+    units::length::millimeter_t distance_in_mm(const btVector3 & v1, const btVector3 & v2) const;
+    btVector3 enlarge(const btVector3 & versor, float mm) const;
+    std::unordered_map<std::string, material> materials;
+    std::string starting_material;
+    std::vector<mesh> meshes;
+    const float initial_intensity { 1.0f };
+    std::array<float,3> spacing;
+    std::unique_ptr<shim_world> m_dynamicsWorld;
+    clock_t frame_start;
+};
 #include "_ref/scene_distance.inc"
+#include "_ref/scene_helpers.inc"
+#include "_ref/scene_cast_rays.inc"
 
 extern "C" {
 
@@ -224,6 +277,54 @@ void ref_accumulate_loop(const float* segs, const double* dist_mm, const float* 
     const auto& texture_volume = *ref_vol();
 #include "_ref/main_accumulate_loop.inc"
     memcpy(rf_out, rf_image.intensities.data.data(), sizeof(float) * rf_image.intensities.data.size());
+}
+
+// ---- scene.cpp:50-183, scene::cast_rays<5,512>, verbatim ------------------------------------------
+// materials8: [n_mat][8]; mesh tables as in the scene JSON; hit_fn / hit_ctx: closest-hit oracle.  Outputs per segment
+// [512][5][10]: seg12 = from3, to3, dir3, reflected_intensity, initial_intensity, attenuation; dist_mm; nseg [512][5].
+// segment::media is NOT read: it dangles once cast_rays returns (SURVEY B-1).
+int64_t ref_cast_rays(const float* materials8, int n_mat, const int* mesh_in, const int* mesh_out, const int* mesh_vasc, int n_mesh,
+                      int starting_material, const float* spacing3, const float* pos3, const float* angles_deg3, void* hit_fn,
+                      const void* hit_ctx, float* seg12, double* dist_mm, int* nseg)
+{
+    using namespace units::angle;
+    scene sc;
+    for (int i = 0; i < n_mat; i++) sc.materials[std::to_string(i)] = mk_mat(materials8 + 8 * i);
+    sc.starting_material = std::to_string(starting_material);
+    sc.meshes.reserve(n_mesh);
+    for (int i = 0; i < n_mesh; i++)
+        sc.meshes.emplace_back(mesh{"m", true, mesh_vasc[i] != 0, {0.f, 0.f, 0.f}, true, sc.materials.at(std::to_string(mesh_in[i])),
+                                    sc.materials.at(std::to_string(mesh_out[i]))});
+    sc.spacing = {spacing3[0], spacing3[1], spacing3[2]};
+    sc.m_dynamicsWorld.reset(new shim_world());
+    sc.m_dynamicsWorld->fn = (ref_hit_fn)hit_fn;
+    sc.m_dynamicsWorld->ctx = hit_ctx;
+    sc.m_dynamicsWorld->bodies.resize(n_mesh);
+    for (int i = 0; i < n_mesh; i++) sc.m_dynamicsWorld->bodies[i].m_user = &sc.meshes[i];          // scene.cpp:46 setUserPointer(&mesh)
+    sc.frame_start = clock();
+    millimeter_t sep = transducer_amplitude.to<float>() * transducer_radius / transducer_elements;   // main.cpp:66
+    std::array<degree_t, 3> ang = {degree_t((float)angles_deg3[0]), degree_t((float)angles_deg3[1]), degree_t((float)angles_deg3[2])};
+    transducer_ tr(transducer_frequency, transducer_radius, sep, btVector3(pos3[0], pos3[1], pos3[2]), ang);   // main.cpp:65-72
+    std::ostringstream sink;                                  // scene.cpp:141-142,179 print two lines per hit and one per frame
+    std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
+    auto rays = sc.cast_rays<samples_te, transducer_elements>(tr);
+    std::cout.rdbuf(old);
+    int64_t total = 0;
+    const int D = (int)ray_physics::ray::max_depth;
+    for (size_t e = 0; e < transducer_elements; e++)
+        for (size_t s = 0; s < samples_te; s++) {
+            const auto& v = rays[e][s];
+            nseg[e * samples_te + s] = (int)v.size();
+            total += (int64_t)v.size();
+            for (size_t k = 0; k < v.size() && (int)k < D; k++) {
+                const size_t i = (e * samples_te + s) * D + k;
+                float* f = seg12 + 12 * i;
+                for (int a = 0; a < 3; a++) { f[a] = v[k].from[a]; f[3 + a] = v[k].to[a]; f[6 + a] = v[k].direction[a]; }
+                f[9] = v[k].reflected_intensity; f[10] = v[k].initial_intensity; f[11] = v[k].attenuation;
+                dist_mm[i] = v[k].distance_traveled.to<double>();
+            }
+        }
+    return total;
 }
 
 // ---- tinyobj + objloader.h --------------------------------------------------------------------

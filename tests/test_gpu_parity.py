@@ -222,6 +222,28 @@ def test_convolve_and_envelope_bit_exact(api, O, sphere, cols, rows, ka, kl):
     assert np.array_equal(g_both.T, O.envelope(o_conv))
 
 
+def test_cast_rays_bit_exact_to_the_reference_loop_golden(api, O):
+    """mcrt_trace_debug (k_first_hit / k_bounce / k_compact) against the committed segments of the REFERENCE'S OWN
+    scene::cast_rays<5,512> (scene.cpp:50-183 compiled from the reference, tests/golden/reference_cast_rays.npz), on the
+    impedance-matched scene where the reference's random draws have no effect: every field of every segment bit for bit."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_cast_rays", GOLD / "make_golden_cast_rays.py")
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    gold = np.load(GOLD / "reference_cast_rays.npz")
+    A = mg.matched_scene()
+    pose = np.concatenate([A["transducer_position"], A["transducer_angles"]]).astype(np.float32)
+    with api.Simulator(A, api.default_params(elements=512, samples=5)) as sim:
+        segs, nseg = sim.cast_rays(pose, seed=mg.SEED, frame=mg.FRAME)
+    segs = segs.reshape(512, 5, 10); nseg = nseg.reshape(512, 5)
+    assert np.array_equal(nseg, gold["nseg"])
+    live = np.arange(10)[None, None, :] < nseg[..., None]
+    for k, (lo, hi) in {"from": (0, 3), "to": (3, 6), "dir": (6, 9)}.items():
+        assert np.array_equal(segs[k][live], gold["seg12"][..., lo:hi][live]), k
+    for k, i in {"reflected_intensity": 9, "initial_intensity": 10, "attenuation": 11}.items():
+        assert np.array_equal(segs[k][live], gold["seg12"][..., i][live]), k
+    assert np.array_equal(segs["distance_traveled"][live], gold["dist_mm"][live])
+
+
 def test_accumulate_against_the_reference_loop_golden(api, O, sphere):
     """mcrt_accumulate (k_accumulate_win) on the fixed segments against the committed image of the REFERENCE'S OWN accumulation
     loop (main.cpp:106-144 compiled from the reference, tests/golden/reference_accumulate_loop.npz): 1e-4 relative (the GPU

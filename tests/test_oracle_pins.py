@@ -283,6 +283,35 @@ def test_accumulate_loop_bit_exact_to_the_reference_loop(O):
         assert np.array_equal(O.ref_accumulate_loop(R, segs, nseg, mats), gold["rf"])
 
 
+def _golden_module(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, GOLD / (name + ".py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m
+
+
+def test_cast_rays_loop_bit_exact_to_the_reference_loop(O):
+    """LOOP-LEVEL pin of scene::cast_rays<5,512> (scene.cpp:50-183): the reference's own template member, extracted verbatim at build
+    time and compiled into the reference probe with its collision world forwarding rayTest to the oracle's closest hit, ran on a
+    scene where none of its random_device draws has any effect (tests/golden/make_golden_cast_rays.py); its segments are
+    committed.  orc_cast_rays must reproduce every segment field BIT FOR BIT, and every bounce count."""
+    mg = _golden_module("make_golden_cast_rays")
+    gold = np.load(GOLD / "reference_cast_rays.npz")
+    A = mg.matched_scene()
+    segs, nseg, tests, osc, p = mg.oracle_segments(A)
+    assert np.array_equal(nseg, gold["nseg"]) and tests == int(gold["nseg"].sum()) and int(nseg.max()) >= 4
+    live = np.arange(10)[None, None, :] < nseg[..., None]
+    for k, (lo, hi) in {"from": (0, 3), "to": (3, 6), "dir": (6, 9)}.items():
+        assert np.array_equal(segs[k][live], gold["seg12"][..., lo:hi][live]), k
+    for k, i in {"reflected_intensity": 9, "initial_intensity": 10, "attenuation": 11}.items():
+        assert np.array_equal(segs[k][live], gold["seg12"][..., i][live]), k
+    assert np.array_equal(segs["distance_traveled"][live], gold["dist_mm"][live])
+    R = O.ref_probe()
+    if R is not None and hasattr(R, "ref_cast_rays"):                    # live: the reference loop itself, where its sources are mounted
+        seg12, dist, rnseg, total = mg.reference_segments(R, A, osc)
+        assert np.array_equal(rnseg, gold["nseg"]) and np.array_equal(seg12, gold["seg12"]) and np.array_equal(dist, gold["dist_mm"])
+
+
 def _img(G):
     seed = int(G["img_seed"][0])
     src = np.random.default_rng(seed).standard_normal((465, 512)).astype(np.float32)
