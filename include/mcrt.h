@@ -154,7 +154,13 @@ int mcrt_simulate(mcrt_ctx* ctx, const mcrt_pose* poses, int32_t n_poses, uint64
 
 /* Same, but rf_out/scan_out must be DEVICE pointers and nothing is synchronised: the work is
  * enqueued on `cuda_stream` (a cudaStream_t passed as void*; NULL = the library's own stream)
- * so a caller can overlap it or follow it with a collective. */
+ * so a caller can overlap it or follow it with a collective.
+ * Stream contract: a context owns ONE workspace (pose staging, path state, segments, RF images, captured graphs) that every
+ * entry point uses.  Calls on one context must come from one host thread at a time; they may use different streams -- each
+ * entry point makes its stream wait for the work the previous call enqueued (an event recorded at the end of every call), so
+ * mixing mcrt_simulate_async on a user stream with the blocking entry points, or switching user streams, is ordered
+ * correctly; what is NOT provided is concurrency between two calls on the same context (use one context per stream for that).
+ * The results of an async call may be read once its stream has reached the point of the call. */
 int mcrt_simulate_async(mcrt_ctx* ctx, const mcrt_pose* poses, int32_t n_poses, uint64_t seed, uint64_t first_frame,
                         float* rf_out_dev, float* scan_out_dev, void* cuda_stream);
 

@@ -100,6 +100,11 @@ struct mcrt_ctx {
     bool overlap = false;                  // software-pipeline sub-batches inside the graph (measured slower: off)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_up = nullptr;
     bool upload_pending = false;
+    // cross-stream ordering of the shared workspace: every entry point records ev_last on the stream it used; an entry point that
+    // runs on a DIFFERENT stream first makes that stream wait for it (begin_call / end_call)
+    cudaEvent_t ev_last = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool last_valid = false;
 
     DevMesh* d_meshes = nullptr;
     DevMaterial* d_materials = nullptr;
@@ -174,6 +179,7 @@ extern "C" {   // defined next to the entry points below
 static void update_scene_bounds(mcrt_ctx* c);
 static void ensure_scene_current(mcrt_ctx* c);
 static void rebuild_bvh(mcrt_ctx* c);
+static void make_bvh2(mcrt_ctx* c, mcrt::LbvhResult* nb);
 }
 
 namespace {
@@ -262,6 +268,20 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
         CUDA_TRY(cudaMalloc(&c->tb.sort_tmp, c->tb.sort_tmp_bytes ? c->tb.sort_tmp_bytes : 16));
     }
     c->cap_poses = n_poses;
+}
+
+// One workspace (d_poses, tb.*, d_rf_*, the pinned pose / seed staging, the captured graphs) serves every entry point.  Work of a
+// previous call may still be in flight on another stream (mcrt_simulate_async returns without synchronising): the stream of
+// this call waits for it, and the pinned staging is not rewritten before its last upload has been consumed.
+void begin_call(mcrt_ctx* c, cudaStream_t s)
+{
+    if (c->last_valid && c->last_stream != s) CUDA_TRY(cudaStreamWaitEvent(s, c->ev_last, 0));
+    if (c->upload_pending) { CUDA_TRY(cudaEventSynchronize(c->ev_up)); c->upload_pending = false; }
+}
+void end_call(mcrt_ctx* c, cudaStream_t s)
+{
+    CUDA_TRY(cudaEventRecord(c->ev_last, s));
+    c->last_stream = s; c->last_valid = true;
 }
 
 // the wide traversal tree over a freshly built BVH2 (device LBVH or uploaded host SAH tree)
@@ -462,6 +482,7 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
         const size_t px_per_pose = (size_t)c->aq.elements * c->aq.rows;
         const size_t scan_per_pose = (size_t)c->params.scan_rows * c->params.scan_cols;
         int launches = 0;
+        begin_call(c, s);
         CUDA_TRY(cudaEventRecord(c->ev0, s));
         if (c->count_traversal) CUDA_TRY(cudaMemsetAsync(c->d_trav, 0, 2 * sizeof(unsigned long long), s));
         for (int b = 0; b < n_batches; b++) {
@@ -494,6 +515,7 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
         }
         if (c->count_traversal) CUDA_TRY(cudaMemcpyAsync(c->h_trav, c->d_trav, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaEventRecord(c->ev1, s));
+        end_call(c, s);
         c->stats_pending = true;
         c->pending_batches = n_batches;
         c->pending_launches = launches;
@@ -569,6 +591,7 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     CUDA_TRY(cudaEventCreate(&c->ev0)); CUDA_TRY(cudaEventCreate(&c->ev1));
     CUDA_TRY(cudaEventCreate(&c->ev_a)); CUDA_TRY(cudaEventCreate(&c->ev_b)); CUDA_TRY(cudaEventCreate(&c->ev_c));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming));
 
     // acquisition constants
     AcqDev& aq = c->aq;
@@ -595,8 +618,7 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     if (!meshes.empty()) CUDA_TRY(cudaMemcpy(c->d_meshes, meshes.data(), sizeof(DevMesh) * meshes.size(), cudaMemcpyHostToDevice));
     dev_alloc(c->d_materials, hs.materials.size());
     CUDA_TRY(cudaMemcpy(c->d_materials, hs.materials.data(), sizeof(DevMaterial) * hs.materials.size(), cudaMemcpyHostToDevice));
-    const cudaError_t be = build_lbvh(hs.tri_local.data(), hs.tri_mesh.data(), (int)hs.tri_mesh.size(), c->d_meshes, c->stream, &c->bvh);
-    if (be != cudaSuccess) throw CudaError(std::string("build_lbvh: ") + cudaGetErrorString(be));
+    make_bvh2(c.get(), &c->bvh);                       // device LBVH, or a validated tree from $MCRT_BVH_CACHE
     if (c->bvh.max_depth > MCRT_TRAVERSAL_STACK) throw std::invalid_argument("BVH deeper than the traversal stack (degenerate mesh?)");
     SceneDev& sc = c->sc;
     memset(&sc, 0, sizeof(sc));
@@ -678,6 +700,7 @@ void destroy_impl(mcrt_ctx* c)
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     if (c->ev_c) cudaEventDestroy(c->ev_c);
     if (c->ev_up) cudaEventDestroy(c->ev_up);
+    if (c->ev_last) cudaEventDestroy(c->ev_last);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (int k = 0; k < 4; k++) if (c->ev_sub[k]) cudaEventDestroy(c->ev_sub[k]);
@@ -762,26 +785,71 @@ static uint64_t fnv1a64(const void* data, size_t n, uint64_t h)
     return h;
 }
 
-// SAH tree cache: $MCRT_BVH_CACHE/sah_<hash>.bvh = {magic, n_nodes, n_slots, max_depth, max_abs, nodes, slots}
-static std::string sah_cache_path(const HostScene& hs, const std::vector<float>& origins)
+// Tree cache: $MCRT_BVH_CACHE/<builder>_<hash>.bvh = {magic, n_nodes, n_slots, 0, max_depth, max_abs, nodes, slots}
+// for every builder (lbvh = the default device build, sah = the host binned-SAH tree).  The key hashes the triangle data, the
+// body origins, the builder and a format / builder version, so a file written by another version is simply never looked up;
+// a file that IS found is still validated in full before use (child references, leaf slots, every slot's vertices against
+// the scene, the depth): a stale, truncated or hostile file in a shared cache directory falls back to rebuilding.
+static const uint64_t kTreeCacheVersion = 2;          // bump when a builder or the file layout changes
+static std::string tree_cache_path(const HostScene& hs, const std::vector<float>& origins, int builder)
 {
     const char* dir = getenv("MCRT_BVH_CACHE");
     if (!dir || !*dir) return std::string();
     uint64_t h = 1469598103934665603ULL;
+    const uint64_t tag[3] = {kTreeCacheVersion, (uint64_t)builder, (uint64_t)MCRT_LEAF_MAX};
+    h = fnv1a64(tag, sizeof(tag), h);
     h = fnv1a64(hs.tri_local.data(), sizeof(float) * hs.tri_local.size(), h);
     h = fnv1a64(hs.tri_mesh.data(), sizeof(int32_t) * hs.tri_mesh.size(), h);
     h = fnv1a64(origins.data(), sizeof(float) * origins.size(), h);
     char name[64];
-    snprintf(name, sizeof(name), "/sah_%016llx.bvh", (unsigned long long)h);
+    snprintf(name, sizeof(name), "/%s_%016llx.bvh", builder == 0 ? "lbvh" : "sah", (unsigned long long)h);
     return std::string(dir) + name;
 }
-static const uint64_t kSahCacheMagic = 0x3142564853544d43ULL;   // "CMTSHVB1"
-static bool sah_cache_load(const std::string& path, size_t n_tri, HostBvh* hb)
+static const uint64_t kTreeCacheMagic = 0x3242564854544d43ULL;   // "CMTTHVB2"
+static bool tree_cache_valid(const HostBvh& hb, const HostScene& hs)
+{
+    const size_t n_tri = hs.tri_mesh.size(), n_nodes = hb.nodes.size();
+    if (hb.slots.size() != n_tri || n_nodes + 1 != (n_tri ? n_tri : 1)) return false;
+    std::vector<unsigned char> seen(n_tri, 0);
+    for (size_t k = 0; k < n_tri; k++) {
+        const HostTriSlot& t = hb.slots[k];
+        if (t.tri < 0 || (size_t)t.tri >= n_tri || seen[t.tri] || t.mesh != hs.tri_mesh[t.tri]) return false;
+        if (memcmp(t.v, hs.tri_local.data() + 9 * (size_t)t.tri, sizeof(float) * 9) != 0) return false;
+        seen[t.tri] = 1;
+    }
+    if (n_nodes == 0) return true;
+    // every node reachable exactly once from the root, every leaf slot referenced exactly once, depth as recorded
+    std::vector<unsigned char> node_seen(n_nodes, 0), slot_seen(n_tri, 0);
+    std::vector<std::pair<int, int>> stack;
+    stack.emplace_back(0, 1);
+    int deepest = 0;
+    size_t visited = 0;
+    while (!stack.empty()) {
+        const std::pair<int, int> top = stack.back();
+        stack.pop_back();
+        if (top.first < 0 || (size_t)top.first >= n_nodes || node_seen[top.first]) return false;
+        node_seen[top.first] = 1; visited++;
+        for (int k = 0; k < 2; k++) {
+            const int ch = hb.nodes[top.first].child[k];
+            if (ch >= 0) { stack.emplace_back(ch, top.second + 1); continue; }
+            const int code = -ch - 1, first = code >> 2, count = (code & 3) + 1;
+            if (count > MCRT_LEAF_MAX || first < 0 || (size_t)(first + count) > n_tri) return false;
+            for (int j = 0; j < count; j++) { if (slot_seen[first + j]) return false; slot_seen[first + j] = 1; }
+            if (top.second + 1 > deepest) deepest = top.second + 1;
+        }
+        for (int k = 0; k < 12; k++) if (!(hb.nodes[top.first].f[k] == hb.nodes[top.first].f[k])) return false;      // NaN planes
+    }
+    for (size_t k = 0; k < n_tri; k++) if (!slot_seen[k]) return false;
+    // deepest counts the root as 1 and the leaf as one more: deepest - 1 inner nodes on the longest chain
+    return visited == n_nodes && deepest - 1 <= hb.max_depth && hb.max_depth <= MCRT_TRAVERSAL_STACK && hb.max_abs >= 0.0f && hb.max_abs < 3.0e38f;
+}
+static bool tree_cache_load(const std::string& path, const HostScene& hs, HostBvh* hb)
 {
     FILE* f = path.empty() ? nullptr : fopen(path.c_str(), "rb");
     if (!f) return false;
+    const size_t n_tri = hs.tri_mesh.size();
     uint64_t head[4] = {0, 0, 0, 0};
-    bool ok = fread(head, sizeof(head), 1, f) == 1 && head[0] == kSahCacheMagic && head[2] == n_tri && head[1] + 1 == (n_tri ? n_tri : 1);
+    bool ok = fread(head, sizeof(head), 1, f) == 1 && head[0] == kTreeCacheMagic && head[2] == n_tri && head[1] + 1 == (n_tri ? n_tri : 1);
     int32_t depth = 0; float max_abs = 0.0f;
     ok = ok && fread(&depth, sizeof(depth), 1, f) == 1 && fread(&max_abs, sizeof(max_abs), 1, f) == 1;
     if (ok) {
@@ -791,21 +859,58 @@ static bool sah_cache_load(const std::string& path, size_t n_tri, HostBvh* hb)
         hb->max_depth = depth; hb->max_abs = max_abs;
     }
     fclose(f);
-    return ok;
+    return ok && tree_cache_valid(*hb, hs);
 }
-static void sah_cache_store(const std::string& path, const HostBvh& hb)
+static void tree_cache_store(const std::string& path, const HostBvh& hb)
 {
     if (path.empty()) return;
     const std::string tmp = path + ".tmp";
     FILE* f = fopen(tmp.c_str(), "wb");
     if (!f) return;                                   // an unwritable cache directory is not an error
-    const uint64_t head[4] = {kSahCacheMagic, hb.nodes.size(), hb.slots.size(), 0};
+    const uint64_t head[4] = {kTreeCacheMagic, hb.nodes.size(), hb.slots.size(), 0};
     const int32_t depth = hb.max_depth;
     bool ok = fwrite(head, sizeof(head), 1, f) == 1 && fwrite(&depth, sizeof(depth), 1, f) == 1 && fwrite(&hb.max_abs, sizeof(float), 1, f) == 1;
     ok = ok && (hb.nodes.empty() || fwrite(hb.nodes.data(), sizeof(HostBvhNode), hb.nodes.size(), f) == hb.nodes.size());
     ok = ok && (hb.slots.empty() || fwrite(hb.slots.data(), sizeof(HostTriSlot), hb.slots.size(), f) == hb.slots.size());
     fclose(f);
     if (ok) rename(tmp.c_str(), path.c_str()); else remove(tmp.c_str());
+}
+// host tree -> device arrays (a cache hit of either builder, or a fresh host SAH build)
+static void upload_host_tree(const HostBvh& hb, LbvhResult* nb)
+{
+    const size_t n = hb.slots.size();
+    std::vector<TriSlot> slots(n);
+    for (size_t k = 0; k < n; k++) {
+        const HostTriSlot& t = hb.slots[k];
+        int mbits = t.mesh, tbits = t.tri;
+        float mf, tf;
+        memcpy(&mf, &mbits, 4); memcpy(&tf, &tbits, 4);
+        slots[k].v0 = make_float4(t.v[0], t.v[1], t.v[2], mf);
+        slots[k].v1 = make_float4(t.v[3], t.v[4], t.v[5], tf);
+        slots[k].v2 = make_float4(t.v[6], t.v[7], t.v[8], 0.f);
+    }
+    static_assert(sizeof(HostBvhNode) == sizeof(BvhNode), "node layouts must match");
+    if (n) { dev_alloc(nb->tris, n); CUDA_TRY(cudaMemcpy(nb->tris, slots.data(), sizeof(TriSlot) * n, cudaMemcpyHostToDevice)); }
+    if (!hb.nodes.empty()) {
+        dev_alloc(nb->nodes, hb.nodes.size());
+        CUDA_TRY(cudaMemcpy(nb->nodes, hb.nodes.data(), sizeof(BvhNode) * hb.nodes.size(), cudaMemcpyHostToDevice));
+    }
+    nb->n_tri = (int)n; nb->n_nodes = (int)hb.nodes.size(); nb->max_depth = hb.max_depth; nb->max_abs = hb.max_abs;
+}
+// device LBVH -> host tree (to store it)
+static void download_device_tree(const LbvhResult& b, HostBvh* hb)
+{
+    hb->nodes.resize((size_t)b.n_nodes); hb->slots.resize((size_t)b.n_tri);
+    std::vector<TriSlot> slots((size_t)b.n_tri);
+    if (b.n_nodes) CUDA_TRY(cudaMemcpy(hb->nodes.data(), b.nodes, sizeof(BvhNode) * (size_t)b.n_nodes, cudaMemcpyDeviceToHost));
+    if (b.n_tri) CUDA_TRY(cudaMemcpy(slots.data(), b.tris, sizeof(TriSlot) * (size_t)b.n_tri, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < slots.size(); k++) {
+        HostTriSlot& t = hb->slots[k];
+        const float v[9] = {slots[k].v0.x, slots[k].v0.y, slots[k].v0.z, slots[k].v1.x, slots[k].v1.y, slots[k].v1.z, slots[k].v2.x, slots[k].v2.y, slots[k].v2.z};
+        memcpy(t.v, v, sizeof(v));
+        memcpy(&t.mesh, &slots[k].v0.w, 4); memcpy(&t.tri, &slots[k].v1.w, 4);
+    }
+    hb->max_depth = b.max_depth; hb->max_abs = b.max_abs;
 }
 
 // scene bounds for the coherence-sort keys
@@ -827,6 +932,30 @@ static void update_scene_bounds(mcrt_ctx* c)
     }
 }
 
+// the BVH2 of the current scene with the selected builder: from the validated disk cache when there is one, else built
+static void make_bvh2(mcrt_ctx* c, LbvhResult* nb)
+{
+    const HostScene& hs = c->scene;
+    memset(nb, 0, sizeof(*nb));
+    std::vector<float> origins(hs.meshes.size() * 3 + 3);
+    for (size_t m = 0; m < hs.meshes.size(); m++)
+        for (int a = 0; a < 3; a++) origins[3 * m + a] = hs.meshes[m].origin[a];
+    const std::string cache = tree_cache_path(hs, origins, c->bvh_builder);
+    HostBvh hb;
+    c->bvh_cache_hit = tree_cache_load(cache, hs, &hb);
+    if (c->bvh_cache_hit) {
+        upload_host_tree(hb, nb);
+    } else if (c->bvh_builder == 0) {
+        const cudaError_t be = build_lbvh(hs.tri_local.data(), hs.tri_mesh.data(), (int)hs.tri_mesh.size(), c->d_meshes, c->stream, nb);
+        if (be != cudaSuccess) throw CudaError(std::string("build_lbvh: ") + cudaGetErrorString(be));
+        if (!cache.empty()) { download_device_tree(*nb, &hb); tree_cache_store(cache, hb); }     // only when a cache directory is set
+    } else {
+        build_sah_bvh(hs.tri_local.data(), hs.tri_mesh.data(), (int)hs.tri_mesh.size(), origins.data(), &hb);
+        tree_cache_store(cache, hb);
+        upload_host_tree(hb, nb);
+    }
+}
+
 // (Re)build the acceleration structure from c->scene with the selected builder and swap it in.  Used by the bvh_builder
 // option and after mesh updates (mcrt_set_mesh_origin / mcrt_set_mesh_vertices): the device LBVH build is ~0.3 ms of
 // kernels for 624 640 triangles, so moving or deforming meshes are handled by rebuilding, not by refitting.
@@ -838,39 +967,7 @@ static void rebuild_bvh(mcrt_ctx* c)
     c->graphs.clear();
     const HostScene& hs = c->scene;
     LbvhResult nb{};
-    if (c->bvh_builder == 0) {
-        const cudaError_t be = build_lbvh(hs.tri_local.data(), hs.tri_mesh.data(), (int)hs.tri_mesh.size(), c->d_meshes, c->stream, &nb);
-        if (be != cudaSuccess) throw CudaError(std::string("build_lbvh: ") + cudaGetErrorString(be));
-    } else {
-        std::vector<float> origins(hs.meshes.size() * 3 + 3);
-        for (size_t m = 0; m < hs.meshes.size(); m++)
-            for (int a = 0; a < 3; a++) origins[3 * m + a] = hs.meshes[m].origin[a];
-        HostBvh hb;
-        const std::string cache = sah_cache_path(hs, origins);
-        c->bvh_cache_hit = sah_cache_load(cache, hs.tri_mesh.size(), &hb);
-        if (!c->bvh_cache_hit) {
-            build_sah_bvh(hs.tri_local.data(), hs.tri_mesh.data(), (int)hs.tri_mesh.size(), origins.data(), &hb);
-            sah_cache_store(cache, hb);
-        }
-        const size_t n = hb.slots.size();
-        std::vector<TriSlot> slots(n);
-        for (size_t k = 0; k < n; k++) {
-            const HostTriSlot& t = hb.slots[k];
-            int mbits = t.mesh, tbits = t.tri;
-            float mf, tf;
-            memcpy(&mf, &mbits, 4); memcpy(&tf, &tbits, 4);
-            slots[k].v0 = make_float4(t.v[0], t.v[1], t.v[2], mf);
-            slots[k].v1 = make_float4(t.v[3], t.v[4], t.v[5], tf);
-            slots[k].v2 = make_float4(t.v[6], t.v[7], t.v[8], 0.f);
-        }
-        static_assert(sizeof(HostBvhNode) == sizeof(BvhNode), "node layouts must match");
-        if (n) { dev_alloc(nb.tris, n); CUDA_TRY(cudaMemcpy(nb.tris, slots.data(), sizeof(TriSlot) * n, cudaMemcpyHostToDevice)); }
-        if (!hb.nodes.empty()) {
-            dev_alloc(nb.nodes, hb.nodes.size());
-            CUDA_TRY(cudaMemcpy(nb.nodes, hb.nodes.data(), sizeof(BvhNode) * hb.nodes.size(), cudaMemcpyHostToDevice));
-        }
-        nb.n_tri = (int)n; nb.n_nodes = (int)hb.nodes.size(); nb.max_depth = hb.max_depth; nb.max_abs = hb.max_abs;
-    }
+    make_bvh2(c, &nb);
     if (nb.max_depth > MCRT_TRAVERSAL_STACK) { cudaFree(nb.nodes); cudaFree(nb.tris); throw std::invalid_argument("BVH deeper than the traversal stack"); }
     WideTree w;
     try {
@@ -1074,10 +1171,10 @@ int mcrt_simulate_scanlines(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, u
         AcqDev aq = c->aq;
         aq.elements = n_local;
         aq.element_offset = e0;
-        c->h_poses[0] = pose_trig(*pose);
-        if (c->upload_pending) { CUDA_TRY(cudaEventSynchronize(c->ev_up)); c->upload_pending = false; }
-        c->h_seed_frame[0] = seed; c->h_seed_frame[1] = frame;
         cudaStream_t s = c->stream;
+        begin_call(c, s);
+        c->h_poses[0] = pose_trig(*pose);
+        c->h_seed_frame[0] = seed; c->h_seed_frame[1] = frame;
         CUDA_TRY(cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig), cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemcpyAsync(c->d_seed_frame, c->h_seed_frame, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
         FrameDev fr;
@@ -1110,6 +1207,7 @@ int mcrt_trace_debug(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, uint64_t
         const size_t n_paths = (size_t)c->aq.elements * c->aq.samples;
         const size_t n_seg = n_paths * c->aq.max_depth;
         if (!c->tb.hit_fraction) { dev_alloc(c->tb.hit_fraction, (size_t)c->cap_poses * n_seg); dev_alloc(c->tb.hit_mesh, (size_t)c->cap_poses * n_seg); }
+        begin_call(c, c->stream);
         c->h_poses[0] = pose_trig(*pose);
         c->h_seed_frame[0] = seed; c->h_seed_frame[1] = frame;
         CUDA_TRY(cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig), cudaMemcpyHostToDevice, c->stream));
@@ -1228,9 +1326,10 @@ int mcrt_trace_tree_debug(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, uin
         CUDA_TRY(cudaSetDevice(c->device));
         ensure_scene_current(c);
         ensure_workspace(c, 1);
+        cudaStream_t s = c->stream;
+        begin_call(c, s);
         c->h_poses[0] = pose_trig(*pose);
         c->h_seed_frame[0] = seed; c->h_seed_frame[1] = frame;
-        cudaStream_t s = c->stream;
         CUDA_TRY(cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig), cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemcpyAsync(c->d_seed_frame, c->h_seed_frame, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
         FrameDev fr;
@@ -1323,6 +1422,7 @@ int mcrt_transducer_elements(mcrt_ctx* c, const mcrt_pose* pose, float* pos3, fl
         float *d_pos = nullptr, *d_dir = nullptr;
         const size_t n = (size_t)c->aq.elements * 3;
         dev_alloc(d_pos, n); dev_alloc(d_dir, n);
+        begin_call(c, c->stream);
         c->h_poses[0] = pose_trig(*pose);
         cudaError_t e = cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig), cudaMemcpyHostToDevice, c->stream);
         FrameDev fr;
@@ -1357,6 +1457,7 @@ int mcrt_accumulate(mcrt_ctx* c, const mcrt_segment* segments, const int32_t* n_
             }
             hs[i] = to_dev_segment(segments[i]);
         }
+        begin_call(c, c->stream);
         CUDA_TRY(cudaMemcpyAsync(c->tb.segments, hs.data(), sizeof(DevSegment) * n_seg, cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaMemcpyAsync(c->tb.n_segments, n_segments, sizeof(int32_t) * n_paths, cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, 2 * sizeof(unsigned long long), c->stream));
@@ -1422,6 +1523,7 @@ int mcrt_scan_convert(mcrt_ctx* c, const float* rf_in, float* scan_out)
         ensure_workspace(c, 1);
         const size_t n = (size_t)c->aq.elements * c->aq.rows;
         const size_t ns = (size_t)c->params.scan_rows * c->params.scan_cols;
+        begin_call(c, c->stream);
         CUDA_TRY(cudaMemcpyAsync(c->d_rf_final, rf_in, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
         int launches = 0;
         launch_scan_convert(c->d_rf_final, 1, c->aq.elements, c->aq.rows, c->d_map_x, c->d_map_y, c->params.scan_rows, c->params.scan_cols,

@@ -197,6 +197,34 @@ def test_streaming_driver_matches_batched_call(api, assets_dirs):
     assert np.array_equal(np.concatenate(got_scan), ref_scan)
 
 
+def test_entry_points_on_different_streams_are_ordered(api, assets_dirs):
+    """One context = one workspace: an mcrt_simulate_async call still in flight on a user stream, followed at once by blocking
+    entry points on the library's stream (simulate, cast_rays, transducer elements) and by an async call on a SECOND user
+    stream, must not be corrupted by them, nor they by it (every entry point waits for the previous call's event)."""
+    import torch
+    from mcray_tracing_b200 import assets
+    path = assets_dirs["ircad11"] / "santi-liver.scene"
+    poses = assets.sweep_poses(48)
+    with api.Simulator(path, api.default_params(elements=128, samples=8)) as sim:
+        want_a = sim.simulate(poses[:32], seed=9, first_frame=0)
+        want_b = sim.simulate(poses[32:], seed=9, first_frame=500)
+        want_segs, want_n = sim.cast_rays(poses[40], seed=9, frame=77)
+        dev = torch.device("cuda", sim.info.device)
+        s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        for rep in range(3):
+            a = torch.zeros((32, sim.cols, sim.rows), dtype=torch.float32, device=dev)
+            c = torch.zeros((32, sim.cols, sim.rows), dtype=torch.float32, device=dev)
+            sim.simulate_device(poses[:32], a.data_ptr(), seed=9, first_frame=0, stream=s1.cuda_stream, sync=False)      # in flight on s1
+            got_b = sim.simulate(poses[32:], seed=9, first_frame=500)                                                  # library stream, blocking
+            sim.simulate_device(poses[:32], c.data_ptr(), seed=9, first_frame=0, stream=s2.cuda_stream, sync=False)      # in flight on s2
+            segs, n = sim.cast_rays(poses[40], seed=9, frame=77)
+            sim.transducer_elements(poses[3])
+            s1.synchronize(); s2.synchronize()
+            assert np.array_equal(got_b, want_b)
+            assert np.array_equal(a.cpu().numpy(), want_a) and np.array_equal(c.cpu().numpy(), want_a)
+            assert np.array_equal(n, want_n) and np.array_equal(segs["tri_id"], want_segs["tri_id"])
+
+
 @pytest.mark.parametrize("kw", [
     dict(elements=96, samples=4),                                                     # fused PSF+envelope kernel (465 rows)
     dict(elements=70, samples=2, axial_scale=5.0, psf_axial=15, psf_lateral=9),       # long-scanline kernels (2 k+ rows)
@@ -336,6 +364,28 @@ def test_moving_and_deforming_meshes_and_sah_cache(api, O, tmp_path, monkeypatch
         sah2 = sim.simulate(poses, seed=8, first_frame=0)
     with api.Simulator(A2, api.default_params(**kw)) as fresh:
         ref = fresh.simulate(poses, seed=8, first_frame=0)
+        # the DEFAULT tree (device LBVH) is cached too: written by the first context created with a cache directory ...
+        assert fresh.get_info().bvh_cache_hit == 0 and len(list(tmp_path.glob("lbvh_*.bvh"))) == 1
+    with api.Simulator(A2, api.default_params(**kw)) as cached:                    # ... and loaded (after validation) by the next one
+        assert cached.get_info().bvh_cache_hit == 1
+        assert np.array_equal(cached.simulate(poses, seed=8, first_frame=0), ref)
+    # a damaged cache file is detected and ignored: child reference out of range, then a swapped triangle
+    f = next(tmp_path.glob("lbvh_*.bvh"))
+    good = f.read_bytes()
+    for damage in ("child", "slot", "truncated"):
+        raw = bytearray(good)
+        if damage == "child":
+            raw[40 + 48:40 + 52] = (2 ** 30).to_bytes(4, "little")                # node 0, child[0]
+        elif damage == "slot":
+            n_nodes = int.from_bytes(good[8:16], "little")
+            off = 40 + 64 * n_nodes
+            raw[off:off + 4] = np.float32(123.5).tobytes()                         # first vertex coordinate of slot 0
+        else:
+            raw = raw[: len(raw) // 2]
+        f.write_bytes(bytes(raw))
+        with api.Simulator(A2, api.default_params(**kw)) as rebuilt:
+            assert rebuilt.get_info().bvh_cache_hit == 0, damage
+            assert np.array_equal(rebuilt.simulate(poses, seed=8, first_frame=0), ref), damage
     assert not np.array_equal(before, after)
     assert np.array_equal(after, ref) and np.array_equal(sah, ref) and np.array_equal(sah2, ref)
     osc = O.OracleScene(A2)

@@ -365,3 +365,87 @@ def test_cli_argument_and_scene_errors(api, tmp_path):
     out = subprocess.run([str(exe), str(tmp_path / "missing.scene")], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0
     assert "The program found an error and will terminate." in out.stdout and "Error while loading scene" in out.stdout
+
+
+# ---- asset conversion (replaces utils/vtp_to_obj.py) ------------------------------------------------------
+def _vtp_text(points, polys, strips, flavour):
+    import base64, struct, zlib
+    pts = np.asarray(points, np.float32)
+    conn = np.concatenate(polys).astype(np.int64); offs = np.cumsum([len(c) for c in polys]).astype(np.int64)
+    sconn = np.concatenate(strips).astype(np.int64) if strips else np.zeros(0, np.int64)
+    soffs = np.cumsum([len(c) for c in strips]).astype(np.int64) if strips else np.zeros(0, np.int64)
+    arrays = [("Points", None, pts.ravel(), "Float32", 3), ("Polys", "connectivity", conn, "Int64", 1), ("Polys", "offsets", offs, "Int64", 1),
+              ("Strips", "connectivity", sconn, "Int64", 1), ("Strips", "offsets", soffs, "Int64", 1)]
+    hdr = "<Q" if flavour == "appended_raw64" else "<I"
+    attrs = 'byte_order="LittleEndian"' + (' header_type="UInt64"' if hdr == "<Q" else "") + (' compressor="vtkZLibDataCompressor"' if flavour == "zlib" else "")
+    appended = b""
+    def payload(a):
+        raw = a.tobytes()
+        if flavour == "zlib":
+            comp = zlib.compress(raw)
+            head = struct.pack("<4I", 1, len(raw), len(raw), len(comp))
+            return base64.b64encode(head).decode() + base64.b64encode(comp).decode()
+        return base64.b64encode(struct.pack(hdr, len(raw)) + raw).decode()
+    def da(name, a, typ, nc):
+        nonlocal appended
+        nm = f' Name="{name}"' if name else ""
+        if flavour == "ascii":
+            return f'<DataArray type="{typ}"{nm} NumberOfComponents="{nc}" format="ascii">{" ".join(repr(float(x)) if typ.startswith("F") else str(int(x)) for x in a)}</DataArray>'
+        if flavour == "appended_raw64":
+            off = len(appended)
+            appended += struct.pack(hdr, a.nbytes) + a.tobytes()
+            return f'<DataArray type="{typ}"{nm} NumberOfComponents="{nc}" format="appended" offset="{off}"/>'
+        return f'<DataArray type="{typ}"{nm} NumberOfComponents="{nc}" format="binary">{payload(a)}</DataArray>'
+    sec = {"Points": "", "Polys": "", "Strips": ""}
+    for s_, name, a, typ, nc in arrays:
+        sec[s_] += da(name, a, typ, nc)
+    body = (f'<?xml version="1.0"?><VTKFile type="PolyData" version="1.0" {attrs}><PolyData><Piece NumberOfPoints="{len(pts)}" NumberOfPolys="{len(polys)}" '
+            f'NumberOfStrips="{len(strips)}"><Points>{sec["Points"]}</Points><Polys>{sec["Polys"]}</Polys><Strips>{sec["Strips"]}</Strips></Piece></PolyData>').encode()
+    if flavour == "appended_raw64":
+        body += b'<AppendedData encoding="raw">_' + appended + b"</AppendedData>"
+    return body + b"</VTKFile>"
+
+
+@pytest.mark.parametrize("flavour", ["ascii", "base64", "zlib", "appended_raw64"])
+def test_vtp_to_obj_matches_the_loader(api, tmp_path, flavour):
+    """convert.py reads VTK XML PolyData without vtk (ascii / base64 / zlib / appended raw) and writes OBJ files the C++ loader
+    (mcrt_load_obj = tinyobj + objloader.h semantics) turns into exactly the fan-triangulated polygons."""
+    from mcray_tracing_b200 import convert
+    rng = np.random.default_rng(11)
+    pts = rng.normal(size=(12, 3)).astype(np.float32) * 37.5
+    polys = [np.array([0, 1, 2]), np.array([2, 3, 4, 5]), np.array([5, 6, 7, 8, 9]), np.array([11, 10, 0])]
+    strips = [np.array([3, 4, 5, 6, 7])]
+    (tmp_path / "m.vtp").write_bytes(_vtp_text(pts, polys, strips, flavour))
+    rp, rpoly = convert.read_vtp(tmp_path / "m.vtp")
+    assert np.array_equal(rp.astype(np.float32), pts)
+    want_polys = polys + [np.array([3, 4, 5]), np.array([5, 4, 6]), np.array([5, 6, 7])]
+    assert len(rpoly) == len(want_polys) and all(np.array_equal(a, b) for a, b in zip(rpoly, want_polys))
+    n = convert.convert(tmp_path / "m.vtp", tmp_path / "m.obj")
+    soup = api.load_obj(tmp_path / "m.obj")
+    assert n == len(soup) == 1 + 2 + 3 + 1 + 3
+    assert np.array_equal(soup.reshape(-1, 3, 3), convert.indexed_to_soup(pts, want_polys))
+
+
+def test_stl_to_obj_weld_and_dump(api, tmp_path):
+    import struct
+    from mcray_tracing_b200 import convert
+    rng = np.random.default_rng(12)
+    v = rng.normal(size=(9, 3)).astype(np.float32)
+    tri = np.array([[0, 1, 2], [2, 1, 3], [3, 4, 5], [6, 7, 8], [8, 7, 0]])
+    soup = v[tri]
+    with open(tmp_path / "b.stl", "wb") as f:
+        f.write(b"solid looks-like-ascii".ljust(80, b" ") + struct.pack("<I", len(soup)))
+        for t in soup:
+            f.write(struct.pack("<12fH", 0, 0, 0, *t.ravel(), 0))
+    with open(tmp_path / "a.stl", "w") as f:
+        f.write("solid s\n" + "".join("facet normal 0 0 0\n outer loop\n" + "".join("  vertex %.9g %.9g %.9g\n" % tuple(p) for p in t) + " endloop\nendfacet\n"
+                                       for t in soup) + "endsolid s\n")
+    for name in ("a.stl", "b.stl"):
+        assert np.array_equal(convert.read_stl(tmp_path / name), soup)
+        assert convert.convert(tmp_path / name, tmp_path / (name + ".obj")) == len(soup)
+        assert np.array_equal(api.load_obj(tmp_path / (name + ".obj")).reshape(-1, 3, 3), soup)
+    verts, idx = convert.weld(soup)
+    assert len(verts) == 9 and np.array_equal(verts[idx], soup) and np.array_equal(convert.indexed_to_soup(verts, idx), soup)
+    convert.convert(tmp_path / "b.stl", tmp_path / "nw.obj", weld_vertices=False)
+    assert sum(ln.startswith("v ") for ln in (tmp_path / "nw.obj").read_text().splitlines()) == 3 * len(soup)
+    assert np.array_equal(api.load_obj(tmp_path / "nw.obj").reshape(-1, 3, 3), soup)
