@@ -71,7 +71,7 @@ EXPORTS = ["mcrt_default_params", "mcrt_create", "mcrt_create_from_arrays", "mcr
            "mcrt_get_stats", "mcrt_set_option", "mcrt_simulate", "mcrt_simulate_async", "mcrt_trace_debug", "mcrt_closest_hit",
            "mcrt_transducer_elements", "mcrt_accumulate", "mcrt_postprocess", "mcrt_scan_convert", "mcrt_get_psf_taps",
            "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe", "mcrt_load_obj", "mcrt_scene_probe", "mcrt_host_tables", "mcrt_simulate_scanlines", "mcrt_bmode", "mcrt_set_mesh_origin", "mcrt_set_mesh_vertices", "mcrt_trace_tree_debug", "mcrt_device_alloc", "mcrt_set_psf_depth_profile",
-           "mcrt_device_free", "mcrt_ipc_export", "mcrt_ipc_open", "mcrt_ipc_close", "mcrt_copy_async", "mcrt_copy2d_async"]
+           "mcrt_device_free", "mcrt_ipc_export", "mcrt_ipc_open", "mcrt_ipc_close", "mcrt_copy_async", "mcrt_copy2d_async", "mcrt_set_elevation", "mcrt_elevation_pose"]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
@@ -318,6 +318,18 @@ class Simulator:
         n = C.c_int64(0)
         _check(lib().mcrt_trace_tree_debug(self.h, _p(P), int(seed), int(frame), cap, _p(segs), _p(path), _p(node), C.byref(n)))
         return segs[: n.value].copy(), path[: n.value].copy(), node[: n.value].copy()
+
+    def set_elevation(self, n_planes: int, var_z: float = 0.1):
+        """Elevational PSF (mcrt_set_elevation): n_planes ray fans per frame (odd; 1 = off).  Returns (taps, z_mm)."""
+        taps = np.zeros(max(n_planes, 1), np.float32); z = np.zeros(max(n_planes, 1), np.float32)
+        _check(lib().mcrt_set_elevation(self.h, int(n_planes), C.c_float(var_z), _p(taps), _p(z)))
+        return taps, z
+
+    def elevation_pose(self, pose, plane: int) -> np.ndarray:
+        P = make_poses(pose)
+        out = make_poses(np.zeros(6, np.float32))
+        _check(lib().mcrt_elevation_pose(self.h, _p(P), int(plane), _p(out)))
+        return out[0].copy()
 
     def set_psf_depth_profile(self, focus_cm: float, spread: float):
         """Depth-dependent lateral PSF (spread = 0: off); returns the taps [psf_lateral][rows] (None when off)."""

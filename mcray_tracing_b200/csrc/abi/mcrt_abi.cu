@@ -145,6 +145,11 @@ struct mcrt_ctx {
     unsigned char* bm_q = nullptr;
     int* bm_max = nullptr;
     int bm_cap = 0;
+    // elevational PSF (mcrt_set_elevation): every output frame is traced as elev_n ray fans offset along the elevation axis
+    int elev_n = 1;
+    std::vector<float> h_elev_w, h_elev_z;
+    float* d_elev_w = nullptr;
+    float* d_rf_elev = nullptr;            // raw RF images of the output frames after the elevational combine ([frames][E][rf_pitch])
     int frame_stride = 1;                  // frame index of pose i of a call = first_frame + i * frame_stride (option "frame_stride")
     bool post_tma = true;                  // TMA-staged fused post kernel (option "post_tma"; 0 = round 1's k_post_fused, for A/B and equivalence tests)
     int first_hit_dedup = 1;               // bounce 0 traced once per element (TraceBuffers::first_hits) when samples >= 4: 0 off, 1 large calls, 2 always
@@ -207,7 +212,7 @@ void free_workspace(mcrt_ctx* c)
     if (c->tb.sort_tmp) cudaFree(c->tb.sort_tmp);
     c->tb.sort_tmp = nullptr; c->tb.sort_tmp_bytes = 0;
     dev_free(c->d_poses); dev_free(c->d_rf_acc); dev_free(c->d_rf_tmp0); dev_free(c->d_rf_tmp1); dev_free(c->d_rf_final);
-    dev_free(c->d_rf_t); dev_free(c->d_scan); dev_free(c->d_columns); dev_free(c->d_max_bits);
+    dev_free(c->d_rf_t); dev_free(c->d_scan); dev_free(c->d_columns); dev_free(c->d_max_bits); dev_free(c->d_rf_elev);
     if (c->h_poses) cudaFreeHost(c->h_poses);
     c->h_poses = nullptr;
     c->cap_poses = 0;
@@ -230,6 +235,7 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
     dev_alloc(c->tb.queue_b, n_paths);
     dev_alloc(c->tb.counters, (size_t)kMaxSub * (c->aq.max_depth + 1));
     dev_alloc(c->d_poses, (size_t)n_poses);
+    if (c->elev_n > 1) dev_alloc(c->d_rf_elev, n_px_acc / (size_t)c->elev_n + 4);
     dev_alloc(c->d_rf_acc, n_px_acc);
     CUDA_TRY(cudaMemset(c->d_rf_acc, 0, sizeof(float) * n_px_acc));                 // the pad words of every row stay 0
     dev_alloc(c->d_rf_tmp0, n_px);
@@ -329,24 +335,36 @@ void enqueue_trace(mcrt_ctx* c, int pose0, int n, int slot, cudaStream_t s, int*
 }
 
 // accumulate -> PSF -> envelope (-> transpose, scan conversion) of poses [pose0, pose0 + n)
-void enqueue_image(mcrt_ctx* c, int pose0, int n, bool want_scan, cudaStream_t s, int* launches)
+// `n` counts SUB-frames (elev_n ray fans per output frame; 1 without the elevational PSF), pose0 likewise.
+void enqueue_image(mcrt_ctx* c, int pose0, int n, bool want_scan, cudaStream_t s, int* launches, cudaEvent_t ev_after_accumulate = nullptr)
 {
+    const int N = c->elev_n;
     const size_t p0 = (size_t)pose0 * c->aq.elements * c->aq.samples;
-    const size_t px0 = (size_t)pose0 * c->aq.elements * c->aq.rows;
     const size_t ax0 = (size_t)pose0 * c->aq.elements * c->aq.rf_pitch;
     CUDA_TRY(launch_accumulate(c->sc, c->aq, c->d_volume, c->tb.segments + p0 * c->aq.max_depth, c->tb.n_segments + p0, n, c->d_rf_acc + ax0,
                                c->d_steps, c->d_columns + p0 * c->aq.rows, s, launches));
-    launch_post(c->d_rf_acc + ax0, n, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
+    // output frames of this piece
+    const int f0 = pose0 / N, nf = n / N;
+    const size_t px0 = (size_t)f0 * c->aq.elements * c->aq.rows;
+    const float* raw = c->d_rf_acc + ax0;
+    if (N > 1) {
+        const int64_t px_img = (int64_t)c->aq.elements * c->aq.rf_pitch;
+        float* comb = c->d_rf_elev + (size_t)f0 * px_img;
+        launch_elevation_combine(raw, nf, px_img, N, c->d_elev_w, comb, s, launches);
+        raw = comb;
+    }
+    if (ev_after_accumulate) CUDA_TRY(cudaEventRecord(ev_after_accumulate, s));
+    launch_post(raw, nf, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
                 c->d_rf_tmp0 + px0, c->d_rf_tmp1 + px0, c->d_rf_final + px0, s, launches, 0, 0, c->d_lat_by_row, c->aq.rf_pitch,
                 c->post_tma ? c->h_axial.data() : nullptr, c->h_lateral.data());
-    if (c->log_compress) launch_log_compress(c->d_rf_final + px0, n, (int64_t)c->aq.elements * c->aq.rows, c->d_max_bits + pose0, s, launches);
-    if (c->params.rf_layout == 1) launch_transpose(c->d_rf_final + px0, n, c->aq.elements, c->aq.rows, c->d_rf_t + px0, s, launches);
+    if (c->log_compress) launch_log_compress(c->d_rf_final + px0, nf, (int64_t)c->aq.elements * c->aq.rows, c->d_max_bits + f0, s, launches);
+    if (c->params.rf_layout == 1) launch_transpose(c->d_rf_final + px0, nf, c->aq.elements, c->aq.rows, c->d_rf_t + px0, s, launches);
     if (want_scan)
-        launch_scan_convert(c->d_rf_final + px0, n, c->aq.elements, c->aq.rows, c->d_map_x, c->d_map_y, c->params.scan_rows, c->params.scan_cols,
-                            c->d_scan + (size_t)pose0 * c->params.scan_rows * c->params.scan_cols, s, launches);
+        launch_scan_convert(c->d_rf_final + px0, nf, c->aq.elements, c->aq.rows, c->d_map_x, c->d_map_y, c->params.scan_rows, c->params.scan_cols,
+                            c->d_scan + (size_t)f0 * c->params.scan_rows * c->params.scan_cols, s, launches);
 }
 
-// enqueue the whole per-frame chain for `n` poses already uploaded to d_poses / d_seed_frame, one stream
+// enqueue the whole per-frame chain for `n` (sub-)poses already uploaded to d_poses / d_seed_frame, one stream
 void enqueue_pipeline(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches, bool stage_events)
 {
     CUDA_TRY(cudaMemsetAsync(c->tb.counters, 0, sizeof(int) * (size_t)kMaxSub * (c->aq.max_depth + 1), s));
@@ -354,23 +372,8 @@ void enqueue_pipeline(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* l
     if (stage_events) CUDA_TRY(cudaEventRecord(c->ev_a, s));
     enqueue_trace(c, 0, n, 0, s, launches);
     if (stage_events) CUDA_TRY(cudaEventRecord(c->ev_b, s));
-    // stage split for the profile: accumulate (+ sample reduction) | PSF + envelope (+ transpose, scan)
-    const size_t dummy = 0; (void)dummy;
-    if (stage_events) {
-        CUDA_TRY(launch_accumulate(c->sc, c->aq, c->d_volume, c->tb.segments, c->tb.n_segments, n, c->d_rf_acc, c->d_steps, c->d_columns, s,
-                                   launches));
-        CUDA_TRY(cudaEventRecord(c->ev_c, s));
-        launch_post(c->d_rf_acc, n, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
-                    c->d_rf_tmp0, c->d_rf_tmp1, c->d_rf_final, s, launches, 0, 0, c->d_lat_by_row, c->aq.rf_pitch, c->post_tma ? c->h_axial.data() : nullptr,
-                    c->h_lateral.data());
-        if (c->log_compress) launch_log_compress(c->d_rf_final, n, (int64_t)c->aq.elements * c->aq.rows, c->d_max_bits, s, launches);
-        if (c->params.rf_layout == 1) launch_transpose(c->d_rf_final, n, c->aq.elements, c->aq.rows, c->d_rf_t, s, launches);
-        if (want_scan)
-            launch_scan_convert(c->d_rf_final, n, c->aq.elements, c->aq.rows, c->d_map_x, c->d_map_y, c->params.scan_rows,
-                                c->params.scan_cols, c->d_scan, s, launches);
-    } else {
-        enqueue_image(c, 0, n, want_scan, s, launches);
-    }
+    // stage split for the profile: accumulate (+ sample reduction, + elevational combine) | PSF + envelope (+ transpose, scan)
+    enqueue_image(c, 0, n, want_scan, s, launches, stage_events ? c->ev_c : nullptr);
     CUDA_TRY(cudaGetLastError());
 }
 
@@ -398,7 +401,7 @@ void enqueue_pipeline_overlapped(mcrt_ctx* c, int n, int nsub, bool want_scan, c
 
 int pipeline_sub_batches(const mcrt_ctx* c, int n)
 {
-    if (!c->overlap || n < 2 * kMinPosesPerSub) return 1;
+    if (!c->overlap || n < 2 * kMinPosesPerSub || c->elev_n > 1) return 1;
     int nsub = n / kMinPosesPerSub;
     return nsub > kMaxSub ? kMaxSub : nsub;
 }
@@ -474,11 +477,17 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
         const bool rf_dev = async ? true : is_device_pointer(rf_out);
         const bool scan_dev = scan_out ? (async ? true : is_device_pointer(scan_out)) : true;
         cudaStream_t s = (async && user_stream) ? user_stream : c->stream;
-        const int batch_cap = c->max_batch_poses < 1 ? 1 : c->max_batch_poses;
-        const int n_batches = (n_poses + batch_cap - 1) / batch_cap;
+        // elevational PSF: every output frame = N ray fans (sub-frames); batches hold whole frames
+        const int N = c->elev_n;
+        if (N > 1 && c->frame_stride != 1) return fail(MCRT_ERR_INVALID, "mcrt_simulate: the elevational PSF cannot be combined with frame_stride != 1");
+        if (N > 1 && c->tree_budget > 0) return fail(MCRT_ERR_INVALID, "mcrt_simulate: the elevational PSF is not available in ray-tree mode");
+        int batch_cap = c->max_batch_poses < 1 ? 1 : c->max_batch_poses;          // in sub-frames
+        batch_cap = batch_cap / N < 1 ? N : (batch_cap / N) * N;
+        const int frames_per_batch = batch_cap / N;
+        const int n_batches = (n_poses + frames_per_batch - 1) / frames_per_batch;
         if (n_batches > kMaxBatchesPerCall) return fail(MCRT_ERR_INVALID, "mcrt_simulate: too many batches; raise max_batch_poses");
         ensure_scene_current(c);
-        ensure_workspace(c, n_poses < batch_cap ? n_poses : batch_cap);
+        ensure_workspace(c, (n_poses < frames_per_batch ? n_poses : frames_per_batch) * N);
         const size_t px_per_pose = (size_t)c->aq.elements * c->aq.rows;
         const size_t scan_per_pose = (size_t)c->params.scan_rows * c->params.scan_cols;
         int launches = 0;
@@ -486,13 +495,20 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
         CUDA_TRY(cudaEventRecord(c->ev0, s));
         if (c->count_traversal) CUDA_TRY(cudaMemsetAsync(c->d_trav, 0, 2 * sizeof(unsigned long long), s));
         for (int b = 0; b < n_batches; b++) {
-            const int p0 = b * batch_cap;
-            const int n = (n_poses - p0) < batch_cap ? (n_poses - p0) : batch_cap;
+            const int p0 = b * frames_per_batch;                                     // first output frame of the batch
+            const int nf = (n_poses - p0) < frames_per_batch ? (n_poses - p0) : frames_per_batch;
+            const int n = nf * N;                                                    // sub-frames
             // the pinned pose staging is reused: wait for the previous upload (not the previous frame) to finish
             if (c->upload_pending) { CUDA_TRY(cudaEventSynchronize(c->ev_up)); c->upload_pending = false; }
-            for (int i = 0; i < n; i++) c->h_poses[i] = pose_trig(poses[p0 + i]);
+            if (N == 1) {
+                for (int i = 0; i < n; i++) c->h_poses[i] = pose_trig(poses[p0 + i]);
+            } else {
+                for (int i = 0; i < nf; i++)
+                    for (int j = 0; j < N; j++) c->h_poses[i * N + j] = pose_trig(elevation_pose(poses[p0 + i], c->h_elev_z[j]));
+            }
             c->h_seed_frame[0] = seed;
-            c->h_seed_frame[1] = first_frame + (uint64_t)p0 * (uint64_t)c->frame_stride;
+            // frame (Philox counter) of sub-frame (i, j) = (first_frame + i) * N + j
+            c->h_seed_frame[1] = N == 1 ? first_frame + (uint64_t)p0 * (uint64_t)c->frame_stride : (first_frame + (uint64_t)p0) * (uint64_t)N;
             CUDA_TRY(cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig) * (size_t)n, cudaMemcpyHostToDevice, s));
             CUDA_TRY(cudaMemcpyAsync(c->d_seed_frame, c->h_seed_frame, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
             CUDA_TRY(cudaEventRecord(c->ev_up, s));
@@ -504,10 +520,10 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
                 run_batch(c, n, scan_out != nullptr, s, &launches);
             }
             const float* rf_src = c->params.rf_layout == 1 ? c->d_rf_t : c->d_rf_final;
-            CUDA_TRY(cudaMemcpyAsync(rf_out + (size_t)p0 * px_per_pose, rf_src, sizeof(float) * px_per_pose * n,
+            CUDA_TRY(cudaMemcpyAsync(rf_out + (size_t)p0 * px_per_pose, rf_src, sizeof(float) * px_per_pose * nf,
                                      rf_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
             if (scan_out)
-                CUDA_TRY(cudaMemcpyAsync(scan_out + (size_t)p0 * scan_per_pose, c->d_scan, sizeof(float) * scan_per_pose * n,
+                CUDA_TRY(cudaMemcpyAsync(scan_out + (size_t)p0 * scan_per_pose, c->d_scan, sizeof(float) * scan_per_pose * nf,
                                          scan_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaMemcpyAsync(c->h_counters + kCounterSlot * b, c->tb.counters, sizeof(int) * (size_t)kMaxSub * (c->aq.max_depth + 1),
                                      cudaMemcpyDeviceToHost, s));
@@ -520,7 +536,7 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
         c->pending_batches = n_batches;
         c->pending_launches = launches;
         c->stats = mcrt_stats{};
-        c->stats.poses = n_poses;
+        c->stats.poses = (int64_t)n_poses * N;             // simulated ray fans (= frames without the elevational PSF)
         if (!async || c->tree_budget > 0) CUDA_TRY(cudaStreamSynchronize(s));
         if (c->tree_budget > 0)
             for (int b = 0; b < n_batches; b++)
@@ -686,6 +702,7 @@ void destroy_impl(mcrt_ctx* c)
     free_workspace(c);
     dev_free(c->d_meshes); dev_free(c->d_materials); dev_free(c->bvh.nodes); dev_free(c->bvh.tris); dev_free(c->d_nodes4);
     dev_free(c->d_nodes8); dev_free(c->d_tris8);
+    dev_free(c->d_elev_w);
     dev_free(c->bm_gain); dev_free(c->bm_env); dev_free(c->bm_cmp); dev_free(c->bm_scan); dev_free(c->bm_q); dev_free(c->bm_max);
     dev_free(c->d_elem_sincos); dev_free(c->d_axial); dev_free(c->d_lateral); dev_free(c->d_lat_by_row); dev_free(c->d_map_x); dev_free(c->d_map_y);
     dev_free(c->d_seed_frame); dev_free(c->d_steps); dev_free(c->d_trav);
@@ -1554,6 +1571,37 @@ int mcrt_set_psf_depth_profile(mcrt_ctx* c, float focus_cm, float spread, float*
         }
         return MCRT_OK;
     });
+}
+
+int mcrt_set_elevation(mcrt_ctx* c, int32_t n_planes, float var_z, float* taps_out, float* z_mm_out)
+{
+    if (!c) return fail(MCRT_ERR_INVALID, "mcrt_set_elevation: null argument");
+    if (n_planes < 1 || n_planes > 63 || (n_planes % 2) == 0) return fail(MCRT_ERR_INVALID, "mcrt_set_elevation: n_planes must be odd, 1 .. 63 (psf.h:31)");
+    if (n_planes > 1 && !(var_z > 0.0f)) return fail(MCRT_ERR_INVALID, "mcrt_set_elevation: var_z must be > 0");
+    return guarded("mcrt_set_elevation", [&]() {
+        CUDA_TRY(cudaSetDevice(c->device));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        free_workspace(c);                                  // the workspace holds n_planes sub-frames per frame; graphs are dropped with it
+        dev_free(c->d_elev_w);
+        c->elev_n = n_planes;
+        c->h_elev_w.clear(); c->h_elev_z.clear();
+        if (n_planes > 1) {
+            psf_elevation_taps(c->params, n_planes, var_z, c->h_elev_w, c->h_elev_z);
+            dev_alloc(c->d_elev_w, (size_t)n_planes);
+            CUDA_TRY(cudaMemcpy(c->d_elev_w, c->h_elev_w.data(), sizeof(float) * n_planes, cudaMemcpyHostToDevice));
+            if (taps_out) memcpy(taps_out, c->h_elev_w.data(), sizeof(float) * n_planes);
+            if (z_mm_out) memcpy(z_mm_out, c->h_elev_z.data(), sizeof(float) * n_planes);
+        }
+        return MCRT_OK;
+    });
+}
+
+int mcrt_elevation_pose(const mcrt_ctx* c, const mcrt_pose* pose, int32_t plane, mcrt_pose* out)
+{
+    if (!c || !pose || !out) return fail(MCRT_ERR_INVALID, "mcrt_elevation_pose: null argument");
+    if (plane < 0 || plane >= c->elev_n || c->elev_n < 2) return fail(MCRT_ERR_INVALID, "mcrt_elevation_pose: no such plane (mcrt_set_elevation first)");
+    *out = elevation_pose(*pose, c->h_elev_z[plane]);
+    return MCRT_OK;
 }
 
 int mcrt_bmode(mcrt_ctx* c, const float* env_in, int32_t n_images, const mcrt_bmode_params* bp, float* compressed_out, uint8_t* bmode8_out)

@@ -337,6 +337,31 @@ void psf_taps(const mcrt_params& p, std::vector<float>& axial, std::vector<float
     }
 }
 
+void psf_elevation_taps(const mcrt_params& p, int n, float var_z, std::vector<float>& taps, std::vector<float>& z_mm)
+{
+    const float half_elevation = (size_t)n * (size_t)p.resolution_um / 1000.0f / 2.0f;       // psf.h:46
+    const float resolution = p.resolution_um / 1000.0f;
+    taps.resize(n); z_mm.resize(n);
+    for (int i = 0; i < n; i++) {
+        const float z = (size_t)i * resolution - half_elevation;
+        const double zz = (double)z * (double)z;
+        taps[i] = (float)std::exp(-0.5f * (zz / var_z));                                   // the form of lateral_function, psf.h:87-92
+        z_mm[i] = z;
+    }
+}
+
+mcrt_pose elevation_pose(const mcrt_pose& pose, float z_mm)
+{
+    // the fan lies in the transducer's local xy plane (transducer.h:45-59: directions (sin a, cos a, 0) rotated about Z, X, Y);
+    // its normal, local (0, 0, 1), rotated the same way is (cx sy, -sx, cx cy) -- btVector3::rotate term by term
+    const PoseTrig t = pose_trig(pose);
+    const float ez[3] = {t.cx * t.sy, -t.sx, t.cx * t.cy};
+    const float s = z_mm * 0.1f;                                                             // mm -> world units (cm)
+    mcrt_pose q = pose;
+    for (int a = 0; a < 3; a++) q.pos[a] = pose.pos[a] + ez[a] * s;
+    return q;
+}
+
 // Depth-dependent lateral PSF (psf.h:11-25 says "lateral and elevation ranges vary according to distance to
 // the transducer" but the reference fills ONE lateral kernel): the lateral Gaussian of RF row r has the variance
 //   var_y(r) = var_y * w^2,  w = 1 + spread * |depth(r) - focus| / focus,  depth(r) = r * depth_cm / rows,

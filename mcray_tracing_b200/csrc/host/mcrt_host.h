@@ -64,6 +64,12 @@ void element_angle_table(const mcrt_params& p, const Derived& d, std::vector<flo
 PoseTrig pose_trig(const mcrt_pose& pose);                                     // transducer.h:37-39,51-53
 void psf_taps(const mcrt_params& p, std::vector<float>& axial, std::vector<float>& lateral);    // psf.h:34-58
 // depth-dependent lateral PSF taps [psf_lateral][rows] (extension; see mcrt_host.cpp)
+// Elevational PSF (psf.h:42,77 declares elevation_kernel and never fills it; psf.h:16-18 "three ranges: axial, lateral and
+// elevation"): filled by analogy with the lateral kernel, taps[i] = exp(-0.5 z_i^2 / var_z), z_i = i * resolution - n * resolution / 2
+// (not normalised, not centred -- psf.h:40-57), plus the elevational offset z_i [mm] of the ray-fan plane the tap weighs.
+void psf_elevation_taps(const mcrt_params& p, int n, float var_z, std::vector<float>& taps, std::vector<float>& z_mm);
+// the probe pose whose fan lies z_mm off the imaging plane along the transducer's elevation axis (its local z, rotated by the pose)
+mcrt_pose elevation_pose(const mcrt_pose& pose, float z_mm);
 void psf_lateral_depth_table(const mcrt_params& p, int rows, float focus_cm, float spread, std::vector<float>& table);
 void scan_mapping(const mcrt_params& p, const Derived& d, std::vector<float>& map_x, std::vector<float>& map_y);   // rfimage.h:183-215
 const std::vector<float>& scatterer_volume();                                  // volume.h:19-35, process-wide

@@ -1605,6 +1605,32 @@ int post_preferred_pitch(int rows, int n_axial, int n_lateral)
     return post_tma_usable(rows, pitch, n_axial, n_lateral, 3, &dummy, &dummy) && post_tma_smem(pitch, 8) <= MCRT_TMA_SMEM_LIMIT ? pitch : rows;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Elevational PSF: the third separable pass.  Every output frame is traced as n_planes ray fans offset along the elevation
+// axis; their raw RF images are combined with the elevation taps before the axial / lateral passes (the passes are linear, so
+// the order does not matter mathematically; combining first costs one pass over the raw images):
+//   out[i] = sum_j in[plane j][i] * w[j], j ascending, separate multiply and add (the oracle's order).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_elevation_combine(const float* __restrict__ in, const int64_t n_out_px, const int64_t px_per_image,
+                                                          const int n_planes, const float* __restrict__ w, float* __restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out_px; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t img = i / px_per_image, px = i - img * px_per_image;
+        const float* src = in + img * n_planes * px_per_image + px;
+        float acc = 0.0f;
+        for (int j = 0; j < n_planes; j++) acc += __ldg(&src[(int64_t)j * px_per_image]) * __ldg(&w[j]);
+        out[i] = acc;
+    }
+}
+
+void launch_elevation_combine(const float* d_in, int n_out_images, int64_t px_per_image, int n_planes, const float* d_w, float* d_out,
+                              cudaStream_t stream, int* launches)
+{
+    const int64_t n = (int64_t)n_out_images * px_per_image;
+    k_elevation_combine<<<grid1d(n, 256), 256, 0, stream>>>(d_in, n, px_per_image, n_planes, d_w, d_out);
+    if (launches) (*launches)++;
+}
+
 void launch_log_compress(float* d_img, int n_images, int64_t px_per_image, int* d_max_bits, cudaStream_t stream, int* launches)
 {
     // ordered-int encoding of -FLT_MAX-ish: any finite sample is larger

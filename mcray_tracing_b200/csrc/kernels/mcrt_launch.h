@@ -146,6 +146,9 @@ int post_preferred_pitch(int rows, int n_axial, int n_lateral);
 cudaError_t validate_fma_division(float resolution, bool* ok);
 // can launch_accumulate use the windowed kernel for this scene / acquisition (then d_columns may be nullptr)?
 bool accumulate_windowed_supported(const SceneDev& sc, const AcqDev& aq);
+// elevational PSF: out[img][px] = sum_j in[img * n_planes + j][px] * w[j] (raw RF images of the n_planes ray fans of one frame)
+void launch_elevation_combine(const float* d_in, int n_out_images, int64_t px_per_image, int n_planes, const float* d_w, float* d_out,
+                              cudaStream_t stream, int* launches);
 // rfimage.h:127-136 (commented out in the reference): I = log10(I+1)/log10(max+1) per image, in place
 void launch_log_compress(float* d_img, int n_images, int64_t px_per_image, int* d_max_bits, cudaStream_t stream, int* launches);
 // B-mode display chain on the envelope image [n][cols][rows]: TGC gain table (per row), log compression to a dynamic range;

@@ -607,6 +607,34 @@ void orc_psf_taps(const orc_params* p, float* axial, float* lateral)
     }
 }
 
+// Elevational PSF: psf.h:42,77 declares elevation_kernel and never fills it; filled here by analogy with
+// lateral_function (psf.h:87-92) on the grid of psf.h:46-57.  z_mm[i] = elevational offset of ray-fan plane i.
+void orc_elevation_taps(const orc_params* p, int32_t n, float var_z, float* taps, float* z_mm)
+{
+    const float half_elevation = (size_t)n * (size_t)p->resolution_um / 1000.0f / 2.0f;
+    const float resolution = p->resolution_um / 1000.0f;
+    for (int i = 0; i < n; i++) {
+        const float z = (size_t)i * resolution - half_elevation;
+        taps[i] = (float)exp(-0.5f * (((double)z * (double)z) / var_z));
+        z_mm[i] = z;
+    }
+}
+
+// position of the probe whose fan lies z_mm off the imaging plane: the fan plane's normal is the transducer's local z axis
+// pushed through the same three btVector3::rotate calls as the element directions (transducer.h:51-56)
+void orc_elevation_position(const float* pos3, const float* angles_deg3, float z_mm, float* out_pos3)
+{
+    const float x_angle = (float)deg_to_rad((double)angles_deg3[0]);
+    const float y_angle = (float)deg_to_rad((double)angles_deg3[1]);
+    const float z_angle = (float)deg_to_rad((double)angles_deg3[2]);
+    v3 e = mk(0, 0, 1);
+    e = rotate(e, mk(0, 0, 1), z_angle);
+    e = rotate(e, mk(1, 0, 0), x_angle);
+    e = rotate(e, mk(0, 1, 0), y_angle);
+    const float s = z_mm * 0.1f;                        // mm -> cm world units
+    out_pos3[0] = pos3[0] + e.x * s; out_pos3[1] = pos3[1] + e.y * s; out_pos3[2] = pos3[2] + e.z * s;
+}
+
 orc_volume* orc_volume_get(void)
 {
     // volume.h:19-35: default-seeded std::default_random_engine + std::normal_distribution<double>,

@@ -144,6 +144,9 @@ void orc_convolve(float* rf, int32_t rows, int32_t cols, const float* axial, int
 void orc_envelope(float* rf, int32_t rows, int32_t cols);
 /* rfimage.h:127-136, the log compression the reference keeps commented out; in place */
 void orc_log_compress(float* rf, int32_t rows, int32_t cols);
+/* elevational PSF: taps / fan offsets, and the probe position of the fan z_mm off the imaging plane */
+void orc_elevation_taps(const orc_params* p, int32_t n, float var_z, float* taps, float* z_mm);
+void orc_elevation_position(const float* pos3, const float* angles_deg3, float z_mm, float* out_pos3);
 void orc_psf_depth_table(const orc_params* p, int32_t rows, float focus_cm, float spread, float* table);
 void orc_convolve_depth(float* rf, int32_t rows, int32_t cols, const float* axial, int32_t n_axial, const float* lateral_by_row, int32_t n_lateral);
 int64_t orc_cast_rays_tree(const orc_scene* s, const orc_params* p, const float* pos3, const float* angles_deg3, uint64_t seed, uint32_t frame,

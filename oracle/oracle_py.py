@@ -400,6 +400,40 @@ def volume_raw() -> np.ndarray:
     return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(256, 256, 256, 2))
 
 
+def elevation_taps(params, n: int, var_z: float):
+    taps = np.zeros(n, np.float32); z = np.zeros(n, np.float32)
+    L = oracle()
+    L.orc_elevation_taps.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]
+    L.orc_elevation_taps(C.byref(params), int(n), float(var_z), _p(taps), _p(z))
+    return taps, z
+
+
+def elevation_position(pos, angles, z_mm: float) -> np.ndarray:
+    pos = np.ascontiguousarray(pos, np.float32); ang = np.ascontiguousarray(angles, np.float32)
+    out = np.zeros(3, np.float32)
+    L = oracle()
+    L.orc_elevation_position.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    L.orc_elevation_position(_p(pos), _p(ang), float(z_mm), _p(out))
+    return out
+
+
+def simulate_frame_elevation(osc, params, pos, angles, seed: int, frame: int, n_planes: int, var_z: float) -> np.ndarray:
+    """Frame with the elevational PSF: n_planes ray fans offset along the elevation axis, Philox frame counter frame * n + j,
+    raw RF images combined with the elevation taps (j ascending, separate multiply and add), then convolve + envelope.
+    -> rf [rows][cols]."""
+    taps, z = elevation_taps(params, n_planes, var_z)
+    acc = None
+    for j in range(n_planes):
+        pj = elevation_position(pos, angles, float(z[j]))
+        segs, nseg, _ = osc.cast_rays(params, pj, angles, seed=seed, frame=frame * n_planes + j)
+        rf, _ = osc.accumulate(params, segs, nseg)
+        if acc is None:
+            acc = np.zeros_like(rf)
+        acc = (acc + (rf * np.float32(taps[j])).astype(np.float32)).astype(np.float32)
+    ax, lat = psf_taps(params)
+    return envelope(convolve(acc, ax, lat))
+
+
 def ref_accumulate_loop(R, segs, nseg, materials) -> np.ndarray:
     """The reference's own accumulation loop (main.cpp:106-144, compiled into the reference probe) on oracle-layout segments
     [512][5][D] -> raw RF image [465][512].  The segment's medium is copied at emission (SURVEY B-1)."""

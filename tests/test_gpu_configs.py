@@ -393,6 +393,40 @@ def test_moving_and_deforming_meshes_and_sah_cache(api, O, tmp_path, monkeypatch
     _segments_equal(segs, nseg, os_, on)
 
 
+def test_elevational_psf_and_ray_fans(api, O, assets_dirs):
+    """SURVEY 8(f) item 2, the elevation kernel the reference declares and never fills (psf.h:42,77): n_planes ray fans per
+    frame offset along the elevation axis, combined with the elevation taps before the axial / lateral passes.  Taps and fan
+    poses bit-equal to the oracle's restatement, frames within the RF tolerance, batching irrelevant, n_planes = 1 = off."""
+    path = assets_dirs["ircad11"] / "santi-liver-rough.scene"
+    A = O.load_scene_py(path)
+    osc = O.OracleScene(A)
+    kw = dict(elements=64, samples=3)
+    op = O.default_params(**kw)
+    with api.Simulator(path, api.default_params(**kw)) as sim:
+        pose = sim.start_pose
+        plain = sim.simulate(np.repeat(pose[None, :], 2, axis=0), seed=6, first_frame=4)
+        taps, z = sim.set_elevation(5, 0.1)
+        otaps, oz = O.elevation_taps(op, 5, 0.1)
+        assert np.array_equal(taps, otaps) and np.array_equal(z, oz) and taps.max() <= 1.0 and len(set(taps.tolist())) > 2
+        for j in range(5):
+            pj = sim.elevation_pose(pose, j)
+            assert np.array_equal(pj[:3], O.elevation_position(pose[:3], pose[3:], float(z[j]))) and np.array_equal(pj[3:], pose[3:])
+        poses = np.stack([pose, sim.elevation_pose(pose, 0), pose])
+        rf = sim.simulate(poses, seed=6, first_frame=4)
+        assert sim.stats().poses == 15
+        sim.set_option("max_batch_poses", 7)                        # one frame (5 fans) per batch
+        assert np.array_equal(sim.simulate(poses, seed=6, first_frame=4), rf)
+        sim.set_option("max_batch_poses", 256)
+        for i in (0, 2):
+            ref = O.simulate_frame_elevation(osc, op, poses[i][:3], poses[i][3:], seed=6, frame=4 + i, n_planes=5, var_z=0.1).T
+            assert np.all(np.abs(rf[i] - ref) <= _tol(ref)), np.abs(rf[i] - ref).max()
+        assert not np.array_equal(rf[0], plain[0])
+        sim.set_elevation(1)
+        assert np.array_equal(sim.simulate(np.repeat(pose[None, :], 2, axis=0), seed=6, first_frame=4), plain)
+        with pytest.raises(api.McrtError):
+            sim.set_elevation(4)
+
+
 @pytest.mark.parametrize("scene_name,det", [("santi-liver-rough.scene", 0), ("santi-liver.scene", 1)])
 def test_ray_tree_mode_matches_oracle(api, O, assets_dirs, scene_name, det):
     """SURVEY 8(f) item 4 / the north star's ray *tree*: with option ray_tree both children of every boundary hit are
