@@ -819,7 +819,7 @@ static std::string tree_cache_path(const HostScene& hs, const std::vector<float>
     h = fnv1a64(hs.tri_mesh.data(), sizeof(int32_t) * hs.tri_mesh.size(), h);
     h = fnv1a64(origins.data(), sizeof(float) * origins.size(), h);
     char name[64];
-    snprintf(name, sizeof(name), "/%s_%016llx.bvh", builder == 0 ? "lbvh" : "sah", (unsigned long long)h);
+    snprintf(name, sizeof(name), "/%s_%016llx.bvh", builder == 0 ? "lbvh" : (builder == 1 ? "sah" : "ploc"), (unsigned long long)h);
     return std::string(dir) + name;
 }
 static const uint64_t kTreeCacheMagic = 0x3242564854544d43ULL;   // "CMTTHVB2"
@@ -962,8 +962,8 @@ static void make_bvh2(mcrt_ctx* c, LbvhResult* nb)
     c->bvh_cache_hit = tree_cache_load(cache, hs, &hb);
     if (c->bvh_cache_hit) {
         upload_host_tree(hb, nb);
-    } else if (c->bvh_builder == 0) {
-        const cudaError_t be = build_lbvh(hs.tri_local.data(), hs.tri_mesh.data(), (int)hs.tri_mesh.size(), c->d_meshes, c->stream, nb);
+    } else if (c->bvh_builder == 0 || c->bvh_builder == 2) {
+        const cudaError_t be = build_lbvh(hs.tri_local.data(), hs.tri_mesh.data(), (int)hs.tri_mesh.size(), c->d_meshes, c->stream, nb, c->bvh_builder == 2);
         if (be != cudaSuccess) throw CudaError(std::string("build_lbvh: ") + cudaGetErrorString(be));
         if (!cache.empty()) { download_device_tree(*nb, &hb); tree_cache_store(cache, hb); }     // only when a cache directory is set
     } else {
@@ -1078,7 +1078,8 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
         // 0: device LBVH (default, lbvh.cu); 1: host binned-SAH tree (sah_builder.cpp), cached on disk when the environment
         // variable MCRT_BVH_CACHE names a directory.  Rebuilds in place.
         return guarded("mcrt_set_option", [&]() {
-            c->bvh_builder = value != 0 ? 1 : 0;
+            if (value < 0 || value > 2) throw std::invalid_argument("bvh_builder: 0 device LBVH, 1 host binned SAH, 2 device PLOC");
+            c->bvh_builder = (int)value;
             rebuild_bvh(c);
             return MCRT_OK;
         });

@@ -8,6 +8,7 @@
 // hierarchy -> bottom-up refit with arrival counters -> 64-byte traversal nodes + Morton-ordered
 // 48-byte triangle slots.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <utility>
 #include <vector>
@@ -451,10 +452,101 @@ cudaError_t collapse_bvh8(const BvhNode* d_nodes2, int n_nodes2, const TriSlot* 
     return cudaSuccess;
 }
 
+// ------------------------------------------------------------------------------------------------
+// PLOC (parallel locally-ordered clustering, Meister & Bittner 2018), round 2: a SAH-quality hierarchy ON THE DEVICE over the
+// same Morton-sorted triangles as the Karras tree.  Clusters start as the sorted triangles; every iteration each cluster looks
+// `radius` places left and right in the (still Morton-ordered) cluster array for the partner with the smallest merged surface
+// area, mutual nearest neighbours merge into a new inner node, and the array is compacted in order.  The binary tree comes out
+// in the layout k_collapse_bvh4 / k_collapse_bvh8 expect (BvhNode with both child boxes, root = node 0: node ids are handed
+// out downwards from n - 2 and the last merge is the root).  Option bvh_builder = 2; bit-identical results
+// (test_traversal_options_do_not_change_results).  MEASURED WORSE than the Karras tree on the ircad11 stand-in meshes
+// (20.8 instead of 17.5 node visits per query, trace 2.97 vs 2.57 ms; the host binned-SAH tree: 16.1 visits, 2.44 ms;
+// profiles/r02r_ab_ploc.txt): the regular triangulation of those meshes makes the merged-area criterion tie massively, few
+// pairs are mutual per iteration and the clusters grow as chains.  Kept as an option, not the default.
+// ------------------------------------------------------------------------------------------------
+#ifndef MCRT_PLOC_RADIUS
+#define MCRT_PLOC_RADIUS 16
+#endif
+__device__ __forceinline__ float merged_area(float4 alo, float4 ahi, float4 blo, float4 bhi)
+{
+    const float dx = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x), dy = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y),
+                dz = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void k_ploc_init(const unsigned int* __restrict__ vals, const float4* __restrict__ box_lo, const float4* __restrict__ box_hi, int n,
+                            float4* __restrict__ c_lo, float4* __restrict__ c_hi, int* __restrict__ c_ref)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const unsigned int t = vals[k];
+    c_lo[k] = box_lo[t]; c_hi[k] = box_hi[t];
+    c_ref[k] = -(1 + k * 4);                                     // leaf of the single triangle in sorted slot k
+}
+
+__global__ void k_ploc_nearest(const float4* __restrict__ c_lo, const float4* __restrict__ c_hi, int m, int* __restrict__ nn)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const float4 lo = c_lo[i], hi = c_hi[i];
+    float best = 3.0e38f;
+    int bj = -1;
+    const int j0 = i - MCRT_PLOC_RADIUS < 0 ? 0 : i - MCRT_PLOC_RADIUS, j1 = i + MCRT_PLOC_RADIUS >= m ? m - 1 : i + MCRT_PLOC_RADIUS;
+    for (int j = j0; j <= j1; j++) {
+        if (j == i) continue;
+        const float a = merged_area(lo, hi, c_lo[j], c_hi[j]);
+        if (a < best) { best = a; bj = j; }                       // ties: the lower index, on both sides -> mutual pairs stay mutual
+    }
+    nn[i] = bj;
+}
+
+__global__ void k_ploc_merge(const float4* __restrict__ c_lo, const float4* __restrict__ c_hi, const int* __restrict__ c_ref, const int* __restrict__ nn,
+                             int m, int* __restrict__ next_node, BvhNode* __restrict__ nodes, int* __restrict__ parent_internal,
+                             int* __restrict__ parent_leaf, float4* __restrict__ o_lo, float4* __restrict__ o_hi, int* __restrict__ o_ref,
+                             int* __restrict__ keep)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int j = nn[i];
+    float4 lo = c_lo[i], hi = c_hi[i];
+    int ref = c_ref[i], k = 1;
+    if (j >= 0 && nn[j] == i) {
+        if (i < j) {
+            const float4 blo = c_lo[j], bhi = c_hi[j];
+            const int rj = c_ref[j];
+            const int id = atomicSub(next_node, 1);
+            BvhNode nd;
+            nd.a = make_float4(lo.x, lo.y, lo.z, hi.x);
+            nd.b = make_float4(hi.y, hi.z, blo.x, blo.y);
+            nd.c = make_float4(blo.z, bhi.x, bhi.y, bhi.z);
+            nd.d = make_int4(ref, rj, 0, 0);
+            nodes[id] = nd;
+            if (ref >= 0) parent_internal[ref] = id; else parent_leaf[(-ref - 1) >> 2] = id;
+            if (rj >= 0) parent_internal[rj] = id; else parent_leaf[(-rj - 1) >> 2] = id;
+            lo = make_float4(fminf(lo.x, blo.x), fminf(lo.y, blo.y), fminf(lo.z, blo.z), 0.f);
+            hi = make_float4(fmaxf(hi.x, bhi.x), fmaxf(hi.y, bhi.y), fmaxf(hi.z, bhi.z), 0.f);
+            ref = id;
+        } else {
+            k = 0;                                                // absorbed by cluster j
+        }
+    }
+    o_lo[i] = lo; o_hi[i] = hi; o_ref[i] = ref; keep[i] = k;
+}
+
+__global__ void k_ploc_compact(const float4* __restrict__ o_lo, const float4* __restrict__ o_hi, const int* __restrict__ o_ref,
+                               const int* __restrict__ keep, const int* __restrict__ pos, int m, float4* __restrict__ c_lo,
+                               float4* __restrict__ c_hi, int* __restrict__ c_ref, int* __restrict__ m_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    if (keep[i]) { const int p = pos[i]; c_lo[p] = o_lo[i]; c_hi[p] = o_hi[i]; c_ref[p] = o_ref[i]; }
+    if (i == m - 1) *m_out = pos[i] + keep[i];
+}
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = e_; goto done; } } while (0)
 
 cudaError_t build_lbvh(const float* h_tri_local, const int32_t* h_tri_mesh, int n_tri, const DevMesh* d_meshes, cudaStream_t stream,
-                       LbvhResult* out)
+                       LbvhResult* out, int ploc)
 {
     cudaError_t err = cudaSuccess;
     memset(out, 0, sizeof(*out));
@@ -466,6 +558,11 @@ cudaError_t build_lbvh(const float* h_tri_local, const int32_t* h_tri_mesh, int 
     unsigned int *d_vals = nullptr, *d_vals2 = nullptr;
     void* d_tmp = nullptr;
     size_t tmp_bytes = 0;
+    // PLOC working set
+    float4 *d_clo = nullptr, *d_chi = nullptr, *d_olo = nullptr, *d_ohi = nullptr;
+    int *d_cref = nullptr, *d_oref = nullptr, *d_nn = nullptr, *d_keep = nullptr, *d_pos = nullptr, *d_ctr = nullptr;
+    void* d_scan_tmp = nullptr;
+    size_t scan_bytes = 0;
     const int n = n_tri;
     const int B = 256, G = (n + B - 1) / B;
     int h_bounds[6];
@@ -506,6 +603,7 @@ cudaError_t build_lbvh(const float* h_tri_local, const int32_t* h_tri_mesh, int 
         CK(cudaMalloc(&d_nhi, sizeof(float4) * (size_t)(n - 1)));
         CK(cudaMemsetAsync(d_arr, 0, sizeof(int) * (size_t)(n - 1), stream));
         CK(cudaMemsetAsync(d_depth, 0, sizeof(int) * 2, stream));
+        if (!ploc) {
         k_karras<<<G, B, 0, stream>>>(d_keys, n, d_left, d_right, d_pi, d_pl, d_range);
         CK(cudaGetLastError());
         k_refit<<<G, B, 0, stream>>>(d_vals, d_lo, d_hi, n, d_left, d_right, d_pi, d_pl, d_arr, d_nlo, d_nhi, d_depth);
@@ -515,6 +613,39 @@ cudaError_t build_lbvh(const float* h_tri_local, const int32_t* h_tri_mesh, int 
         CK(cudaMalloc(&out->nodes, sizeof(BvhNode) * (size_t)(n - 1)));
         k_emit_nodes<<<G, B, 0, stream>>>(d_vals, d_lo, d_hi, n, d_left, d_right, d_nlo, d_nhi, d_range, out->nodes);
         CK(cudaGetLastError());
+        } else {
+            // ---- PLOC over the Morton-sorted triangles ----
+            CK(cudaMalloc(&out->nodes, sizeof(BvhNode) * (size_t)(n - 1)));
+            CK(cudaMalloc(&d_clo, sizeof(float4) * (size_t)n)); CK(cudaMalloc(&d_chi, sizeof(float4) * (size_t)n));
+            CK(cudaMalloc(&d_olo, sizeof(float4) * (size_t)n)); CK(cudaMalloc(&d_ohi, sizeof(float4) * (size_t)n));
+            CK(cudaMalloc(&d_cref, sizeof(int) * (size_t)n)); CK(cudaMalloc(&d_oref, sizeof(int) * (size_t)n));
+            CK(cudaMalloc(&d_nn, sizeof(int) * (size_t)n)); CK(cudaMalloc(&d_keep, sizeof(int) * (size_t)n)); CK(cudaMalloc(&d_pos, sizeof(int) * (size_t)n));
+            CK(cudaMalloc(&d_ctr, sizeof(int) * 2));
+            CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_keep, d_pos, n, stream));
+            CK(cudaMalloc(&d_scan_tmp, scan_bytes ? scan_bytes : 16));
+            int h_ctr[2] = {n - 2, n};                             // next node id (handed out downwards), cluster count
+            CK(cudaMemcpyAsync(d_ctr, h_ctr, sizeof(h_ctr), cudaMemcpyHostToDevice, stream));
+            CK(cudaMemsetAsync(d_pi, 0xff, sizeof(int) * (size_t)(n - 1), stream));       // parent of the root stays -1
+            k_ploc_init<<<G, B, 0, stream>>>(d_vals, d_lo, d_hi, n, d_clo, d_chi, d_cref);
+            CK(cudaGetLastError());
+            int m = n, iterations = 0;
+            while (m > 1) {
+                const int Gm = (m + B - 1) / B;
+                k_ploc_nearest<<<Gm, B, 0, stream>>>(d_clo, d_chi, m, d_nn);
+                k_ploc_merge<<<Gm, B, 0, stream>>>(d_clo, d_chi, d_cref, d_nn, m, d_ctr, out->nodes, d_pi, d_pl, d_olo, d_ohi, d_oref, d_keep);
+                CK(cudaGetLastError());
+                CK(cub::DeviceScan::ExclusiveSum(d_scan_tmp, scan_bytes, d_keep, d_pos, m, stream));
+                k_ploc_compact<<<Gm, B, 0, stream>>>(d_olo, d_ohi, d_oref, d_keep, d_pos, m, d_clo, d_chi, d_cref, d_ctr + 1);
+                CK(cudaGetLastError());
+                int m_new = 0;
+                CK(cudaMemcpyAsync(&m_new, d_ctr + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                CK(cudaStreamSynchronize(stream));
+                if (m_new >= m || ++iterations > 4096) { err = cudaErrorUnknown; goto done; }     // every iteration merges at least the globally closest pair
+                m = m_new;
+            }
+            k_leaf_depth<<<G, B, 0, stream>>>(n, d_pi, d_pl, d_depth + 1);
+            CK(cudaGetLastError());
+        }
         CK(cudaMemcpyAsync(h_depth, d_depth, sizeof(h_depth), cudaMemcpyDeviceToHost, stream));
     } else {
         const unsigned int zero = 0;
@@ -533,6 +664,8 @@ done:
     cudaFree(d_tri_local); cudaFree(d_tri_mesh); cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_nlo); cudaFree(d_nhi);
     cudaFree(d_bounds); cudaFree(d_left); cudaFree(d_right); cudaFree(d_pi); cudaFree(d_pl); cudaFree(d_arr); cudaFree(d_depth);
     cudaFree(d_range); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_tmp);
+    cudaFree(d_clo); cudaFree(d_chi); cudaFree(d_olo); cudaFree(d_ohi); cudaFree(d_cref); cudaFree(d_oref); cudaFree(d_nn); cudaFree(d_keep);
+    cudaFree(d_pos); cudaFree(d_ctr); cudaFree(d_scan_tmp);
     if (err != cudaSuccess) { cudaFree(out->nodes); cudaFree(out->tris); memset(out, 0, sizeof(*out)); }
     return err;
 }

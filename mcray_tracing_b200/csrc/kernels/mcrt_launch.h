@@ -30,8 +30,9 @@ cudaError_t collapse_bvh8(const BvhNode* d_nodes2, int n_nodes2, const TriSlot* 
 cudaError_t init_trace_kernels();
 
 // builds the device BVH from host triangle data; d_meshes must already be on the device
+// ploc = 0: Karras radix tree over the Morton order (LBVH); 1: PLOC agglomerative clustering over the same order (SAH-quality)
 cudaError_t build_lbvh(const float* h_tri_local, const int32_t* h_tri_mesh, int n_tri, const DevMesh* d_meshes, cudaStream_t stream,
-                       LbvhResult* out);
+                       LbvhResult* out, int ploc = 0);
 
 struct FrameDev {
     const PoseTrigDev* poses;            // [n_poses]
