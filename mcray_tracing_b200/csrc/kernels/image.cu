@@ -383,20 +383,23 @@ __device__ __noinline__ int win_revisit_row(float* my_col, int stride, int base,
 // (conflict-free quarter-warp phases for consecutive rows)
 __host__ __device__ __forceinline__ int win_stride(int T) { const int q = (T + 3) / 4; return 4 * (q | 1); }
 
-template <bool FMADIV, bool WARP>
+// SCT > 0 (WARP only): the number of samples per element as a compile-time constant dividing 32 (16 in BASELINE's configuration):
+// the ring stride, the ring stores of an unrolled block and the sample reduction then carry no run-time index arithmetic.
+template <bool FMADIV, bool WARP, int SCT>
 __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const SceneDev sc, const AcqDev aq, const float2* __restrict__ volume,
                                                        const DevSegment* __restrict__ segments, const int32_t* __restrict__ nseg,
-                                                       const int n_scanlines, const int G, float* __restrict__ rf,
+                                                       const int n_scanlines, const int G_rt, float* __restrict__ rf,
                                                        unsigned long long* __restrict__ steps_total,
                                                        unsigned long long* __restrict__ late_echoes)
 {
     extern __shared__ float4 s_win4[];                     // per group: [MCRT_WIN_RING][stride]; row r lives in slot r % RING
     __shared__ DevMaterial s_mat[MCRT_MAX_SMEM_MATERIALS];
     for (int i = threadIdx.x; i < sc.n_mat && i < MCRT_MAX_SMEM_MATERIALS; i += blockDim.x) s_mat[i] = sc.materials[i];
-    const int S = aq.samples, rows = aq.rows;
+    const int S = SCT > 0 ? SCT : aq.samples, rows = aq.rows;
+    const int G = SCT > 0 ? 32 / SCT : G_rt;
     const int rf_pitch = aq.rf_pitch;                      // row stride of rf (>= rows; padded to 16 B for the TMA-staged post kernel)
     const int T = G * S;                                   // active threads of a group
-    const int stride = win_stride(T);
+    const int stride = SCT > 0 ? 36 /* = win_stride(32) */ : win_stride(T);
     const int group = WARP ? (int)(blockIdx.x * 4 + (threadIdx.x >> 5)) : (int)blockIdx.x;
     const int t = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;          // index within the group
     float* const s_win = reinterpret_cast<float*>(s_win4) + (WARP ? (size_t)(threadIdx.x >> 5) * MCRT_WIN_RING * stride : 0);
@@ -547,23 +550,36 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
                     time_elapsed = time_elapsed + time_step;
                     intensity *= decay;
                 }
-                add_row(echo[0], row0);
-                for (int r = written > base ? written : base; r < row0; r++) my_col[MCRT_WIN_SLOT(r) * stride] = 0.0f;   // gap (time jumped ahead)
-                // rows row0+1 .. row0+U-1 receive exactly one echo each: close every row straight into the column
                 const int slot0 = MCRT_WIN_SLOT(row0);
-                if (slot0 + MCRT_WIN_UNROLL <= MCRT_WIN_RING) {                                 // no wrap inside the block
+                // the two common cases, neither wrapping in the ring: the block continues the column row by row (a pending row right
+                // below row0), or it opens the window (nothing pending, the column is written up to row0) -- the pending row and the
+                // first U - 1 echoes go to consecutive ring rows at constant offsets, the last echo stays pending
+                const bool cont = cur_row + 1 == row0 && written == cur_row && cur_row >= base && slot0 >= 1;
+                const bool fresh = cur_row < 0 && written == row0;
+                if ((cont || fresh) && slot0 + MCRT_WIN_UNROLL <= MCRT_WIN_RING) {
                     float* dst = my_col + slot0 * stride;
+                    if (cont) dst[-stride] = cur_acc;
 #pragma unroll
-                    for (int u = 1; u < MCRT_WIN_UNROLL; u++) {
-                        *dst = cur_acc;
-                        dst += stride;
-                        cur_acc = echo[u];
-                    }
+                    for (int u = 0; u < MCRT_WIN_UNROLL - 1; u++) dst[u * stride] = echo[u];
+                    cur_acc = echo[MCRT_WIN_UNROLL - 1];
                 } else {
+                    add_row(echo[0], row0);
+                    for (int r = written > base ? written : base; r < row0; r++) my_col[MCRT_WIN_SLOT(r) * stride] = 0.0f;   // gap (time jumped ahead)
+                    // rows row0+1 .. row0+U-1 receive exactly one echo each: close every row straight into the column
+                    if (slot0 + MCRT_WIN_UNROLL <= MCRT_WIN_RING) {                                 // no wrap inside the block
+                        float* dst = my_col + slot0 * stride;
 #pragma unroll
-                    for (int u = 1; u < MCRT_WIN_UNROLL; u++) {
-                        my_col[MCRT_WIN_SLOT(row0 + u - 1) * stride] = cur_acc;
-                        cur_acc = echo[u];
+                        for (int u = 1; u < MCRT_WIN_UNROLL; u++) {
+                            *dst = cur_acc;
+                            dst += stride;
+                            cur_acc = echo[u];
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 1; u < MCRT_WIN_UNROLL; u++) {
+                            my_col[MCRT_WIN_SLOT(row0 + u - 1) * stride] = cur_acc;
+                            cur_acc = echo[u];
+                        }
                     }
                 }
                 written = row0 + MCRT_WIN_UNROLL - 1;
@@ -620,19 +636,33 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
             const float* rowp = s_win + MCRT_WIN_SLOT(base + t) * stride;
             float* dst = rf + (size_t)scanline0 * rf_pitch + base + t;
             const int g_end = n_scanlines - scanline0 < G ? n_scanlines - scanline0 : G;
-            for (int g = 0; g < g_end; g++) {
-                const float* src = rowp + g * S;
-                float sum;
-                if ((S & 3) == 0) {
-                    const float4* s4 = reinterpret_cast<const float4*>(src);
-                    float4 v = s4[0];
-                    sum = v.x; sum += v.y; sum += v.z; sum += v.w;
-                    for (int q = 1; q < (S >> 2); q++) { v = s4[q]; sum += v.x; sum += v.y; sum += v.z; sum += v.w; }
-                } else {
-                    sum = src[0];
-                    for (int s = 1; s < S; s++) sum += src[s];
+            if (SCT > 0 && (SCT & 3) == 0) {
+#pragma unroll
+                for (int g = 0; g < 32 / (SCT > 0 ? SCT : 32); g++) {
+                    if (g < g_end) {
+                        const float4* s4 = reinterpret_cast<const float4*>(rowp + g * SCT);
+                        float4 v = s4[0];
+                        float sum = v.x; sum += v.y; sum += v.z; sum += v.w;
+#pragma unroll
+                        for (int q = 1; q < (SCT > 0 ? SCT : 4) / 4; q++) { v = s4[q]; sum += v.x; sum += v.y; sum += v.z; sum += v.w; }
+                        dst[(size_t)g * rf_pitch] = sum;
+                    }
                 }
-                dst[(size_t)g * rf_pitch] = sum;
+            } else {
+                for (int g = 0; g < g_end; g++) {
+                    const float* src = rowp + g * S;
+                    float sum;
+                    if ((S & 3) == 0) {
+                        const float4* s4 = reinterpret_cast<const float4*>(src);
+                        float4 v = s4[0];
+                        sum = v.x; sum += v.y; sum += v.z; sum += v.w;
+                        for (int q = 1; q < (S >> 2); q++) { v = s4[q]; sum += v.x; sum += v.y; sum += v.z; sum += v.w; }
+                    } else {
+                        sum = src[0];
+                        for (int s = 1; s < S; s++) sum += src[s];
+                    }
+                    dst[(size_t)g * rf_pitch] = sum;
+                }
             }
         }
         group_sync();
@@ -1407,15 +1437,20 @@ cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2
         const size_t smem = sizeof(float) * MCRT_WIN_RING * (size_t)win_stride(G * aq.samples) * (warp ? 4 : 1);
         const int grid = warp ? (n_groups + 3) / 4 : n_groups;
         if (warp) {
-            if (aq.voxel_fma_division)
-                k_accumulate_win<true, true><<<grid, 128, smem, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_scanlines, G, d_rf, d_steps, d_steps + 1);
+            if (aq.samples == 16) {            // BASELINE's 16 samples per element: compile-time sample count
+                if (aq.voxel_fma_division)
+                    k_accumulate_win<true, true, 16><<<grid, 128, smem, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_scanlines, G, d_rf, d_steps, d_steps + 1);
+                else
+                    k_accumulate_win<false, true, 16><<<grid, 128, smem, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_scanlines, G, d_rf, d_steps, d_steps + 1);
+            } else if (aq.voxel_fma_division)
+                k_accumulate_win<true, true, 0><<<grid, 128, smem, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_scanlines, G, d_rf, d_steps, d_steps + 1);
             else
-                k_accumulate_win<false, true><<<grid, 128, smem, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_scanlines, G, d_rf, d_steps, d_steps + 1);
+                k_accumulate_win<false, true, 0><<<grid, 128, smem, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_scanlines, G, d_rf, d_steps, d_steps + 1);
         } else {
             if (aq.voxel_fma_division)
-                k_accumulate_win<true, false><<<grid, 128, smem, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_scanlines, G, d_rf, d_steps, d_steps + 1);
+                k_accumulate_win<true, false, 0><<<grid, 128, smem, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_scanlines, G, d_rf, d_steps, d_steps + 1);
             else
-                k_accumulate_win<false, false><<<grid, 128, smem, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_scanlines, G, d_rf, d_steps, d_steps + 1);
+                k_accumulate_win<false, false, 0><<<grid, 128, smem, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_scanlines, G, d_rf, d_steps, d_steps + 1);
         }
         if (launches) (*launches) += 1;
         return cudaGetLastError();
