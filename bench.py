@@ -232,15 +232,19 @@ def run_reference(args, rank: int, world: int):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def stage_counters() -> dict | None:
+def stage_counters(config: str = "c2") -> dict | None:
     """warp / thread instructions per stage and frame from the kept ncu counter file (profiles/stage_counters.json, written by
     scripts/collect_stage_counters.py): instruction counts per frame do not depend on the run, so the live stage times turn
     them into issue-slot utilisation"""
-    p = ROOT / "profiles" / "stage_counters.json"
-    try:
-        return json.loads(p.read_text())
-    except Exception:
-        return None
+    for p in (ROOT / "profiles" / f"stage_counters_{config}.json", ROOT / "profiles" / "stage_counters.json"):
+        try:
+            d = json.loads(p.read_text())
+            if d.get("config") == config:
+                d["file"] = "profiles/" + p.name
+                return d
+        except Exception:
+            pass
+    return None
 
 
 def run_ours(args, rank: int, local_rank: int, world: int):
@@ -571,7 +575,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         S = w["params"]["samples"]
         dedup = S >= 4 and F * cols >= 4096
         queries = seg_per_step - (F * cols * (S - 1) if dedup else 0)
-        sc = stage_counters()
+        sc = stage_counters(args.config)
         stages = []
         for name, ms in (("trace", ms_tr), ("accumulate", ms_acc), ("post", ms_po)):
             e = {"stage": name, "ms": ms, "share_of_step": ms / (ms_tr + ms_acc + ms_po)}
@@ -580,7 +584,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 scale = F / float(sc["frames_per_launch"])
                 wi, ti = cnt["warp_inst"] * scale, cnt["thread_inst"] * scale
                 e.update({"warp_inst": wi, "issue_frac": wi / (ms * 1e-3) / issue_peak, "lanes_per_inst": ti / wi,
-                          "counters": "profiles/stage_counters.json (ncu smsp__inst_executed.sum / smsp__thread_inst_executed.sum of one step)"})
+                          "counters": sc.get("file", "profiles/stage_counters.json") + " (ncu smsp__inst_executed.sum / smsp__thread_inst_executed.sum of one step)"})
                 if name == "trace":
                     e["thread_inst_per_query"] = ti / queries
                 if name == "accumulate":

@@ -2,6 +2,7 @@
 the CPU oracle on the same seeded inputs.  Bars: bit-exact for hit ids / bounce counts / every
 segment field / PSF / envelope / scan conversion; RF after accumulation within
 |gpu - oracle| <= 1e-4 * max(|oracle|, 1e-3 * max|oracle image|)."""
+import os
 from pathlib import Path
 
 import numpy as np
@@ -355,7 +356,8 @@ def test_errors_are_codes_not_crashes(api, assets_dirs, tmp_path):
     assert e.value.code == api.MCRT_ERR_INVALID
 
 
-def test_stochastic_mode_statistics_over_independent_seeds(api, O, ircad_rough):
+@pytest.mark.parametrize("elements,samples", [(32, 4), (256, 16)], ids=["32x4", "256x16-baseline-config-2"])
+def test_stochastic_mode_statistics_over_independent_seeds(api, O, ircad_rough, elements, samples):
     """North-star stochastic criterion, made independent of the shared Philox keying: the GPU simulates N = 256
     frames with seeds 0..255, the oracle N frames with DIFFERENT seeds (independent draws), rough ircad11 scene
     (thickness + shininess jitter active).  Per pixel with non-zero variance:
@@ -365,12 +367,14 @@ def test_stochastic_mode_statistics_over_independent_seeds(api, O, ircad_rough):
         asked for 99 % in [0.7, 1.4]; that is unreachable for ANY correct implementation because RF pixels are
         heavy-tailed (rare specular paths): the oracle against itself with two seed sets reaches 88.9 % / 96.2 %.
         So the bar that matters is the control: the GPU's fractions are within 2 points of the oracle-vs-oracle
-        fractions computed in this same test."""
+        fractions computed in this same test.
+    Run at a reduced acquisition (32 x 4) and at BASELINE.json's configuration 2 itself (256 scanlines x 16 samples, 256 seeds:
+    measured fractions are recorded in DESIGN.md section 2)."""
     path, A, osc = ircad_rough
     N = 256
-    kw = dict(elements=32, samples=4)
+    kw = dict(elements=elements, samples=samples)
     op = O.default_params(**kw)
-    O.oracle().orc_set_threads(8)
+    O.oracle().orc_set_threads(min(16, os.cpu_count() or 1))
     with api.Simulator(path, api.default_params(**kw)) as sim:
         pose = sim.start_pose
         g = np.stack([sim.simulate(pose[None, :], seed=s, first_frame=0)[0] for s in range(N)])           # [N][cols][rows]
@@ -391,7 +395,7 @@ def test_stochastic_mode_statistics_over_independent_seeds(api, O, ircad_rough):
 
     gm, gv, gw, npx = fractions(g, o_b)
     cm, cv, cw, _ = fractions(o_c, o_b)
-    print(f"stochastic statistics over {N} seeds, {npx} pixels: GPU-vs-oracle mean {gm:.4f} var[0.7,1.4] {gv:.4f} var[1/3,3] {gw:.4f}; "
+    print(f"stochastic statistics {elements}x{samples} over {N} seeds, {npx} pixels: GPU-vs-oracle mean {gm:.4f} var[0.7,1.4] {gv:.4f} var[1/3,3] {gw:.4f}; "
           f"oracle-vs-oracle control {cm:.4f} {cv:.4f} {cw:.4f}")
     assert npx > 0.9 * g[0].size
     assert gm >= 0.99 and gv >= 0.85 and gw >= 0.94
