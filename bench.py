@@ -275,6 +275,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     params = api.default_params(**w["params"])
     sim = api.Simulator(w["scene"], params, device=local_rank)
     sim.set_option("max_batch_poses", max(F, 1))
+    for ov in args.option:
+        oname, oval = ov.split("=")
+        sim.set_option(oname, int(oval))
     rows, cols = sim.rows, sim.cols
     total = F * world                                                     # frames per step, whole job
     base_pose = w["pose"] if w["pose"] is not None else sim.start_pose
@@ -662,7 +665,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(args.config, w, world, par, gat),
+            "data": "synthetic", "config": dict(workload_config(args.config, w, world, par, gat), **({"options": args.option} if args.option else {})),
             "ray_segments_per_s": float(segs_all.item()) * args.steps / (total_ms * 1e-3),
             "segments_per_step": float(segs_all.item()), "march_steps_per_step_per_gpu": march_per_step,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(F * 24 + 16), "d2h_bytes_per_step": int(d2h_bytes),
@@ -709,6 +712,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=60, help="frames per CPU-baseline variant (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N > 1: peer-memory deposit over NVLink (default) or NCCL send/recv gather")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE", help="development A/B: mcrt_set_option before the run (recorded in config.options)")
     ap.add_argument("--contiguous", action="store_true", help="N > 1: contiguous pose blocks per rank instead of the round-robin deal")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -1146,6 +1146,12 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
         c->graphs.clear();
         c->post_tma = value != 0;
     }
+    else if (n == "long_ct") {
+        // A/B switch (process-wide): compile-time-tap axial / lateral kernels + shared-memory envelope on the long-scanline path
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear();
+        set_long_scanline_ct(value != 0);
+    }
     else if (n == "voxel_fma_division") {
         // A/B switch; can only be turned on for a resolution that passed the exhaustive check at mcrt_create
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
@@ -1519,7 +1525,7 @@ int mcrt_postprocess(mcrt_ctx* c, const float* rf_in, int32_t cols, int32_t rows
             }
             int launches = 0;
             launch_post(d_in, 1, cols, rows, d_ax, n_axial, d_lat, n_lateral, flags, d_t0, d_t1, d_out, c->stream, &launches, 0, 0, nullptr, pitch,
-                        (flags == 3 && c->post_tma) ? axial : nullptr, lateral);
+                        c->post_tma ? axial : nullptr, lateral);
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaMemcpyAsync(rf_out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));

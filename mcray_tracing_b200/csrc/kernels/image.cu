@@ -767,6 +767,54 @@ __global__ void __launch_bounds__(256) k_psf_axial(const float* __restrict__ in,
     }
 }
 
+// The same pass with the tap loop resolved at compile time.  NG = number of groups of MCRT_PSF_RA taps (ka <= NG * MCRT_PSF_RA; only the
+// LAST group checks k < ka, a uniform branch per tail tap), taps = kernel parameters, so every multiply takes its tap from the constant
+// bank and every window refill is an LDS at an immediate offset: per 8 outputs and tap 16 FP instructions + 1 LDS, nothing else
+// (the run-time loop above spends another LDS for the tap, a predicate and the loop arithmetic: 1 550 instead of ~1 100 warp
+// instructions per 8 x 63 tap applications).  Same arithmetic and order: bit-identical.
+struct LongTaps { float t[64]; };
+template <int NG>
+__global__ void __launch_bounds__(256) k_psf_axial_ct(const float* __restrict__ in, const int rows, const __grid_constant__ LongTaps taps, const int ka,
+                                                     float* __restrict__ out, const int in_pitch, const int chunk_rows)
+{
+    extern __shared__ float s_row[];                       // psf_pad(chunk_rows + ka + MCRT_PSF_RA) words
+    const int tid = threadIdx.x;
+    const int chunk0 = blockIdx.x * chunk_rows;
+    const float* src = in + (size_t)blockIdx.y * in_pitch;
+    float* dst = out + (size_t)blockIdx.y * rows;
+    const int n_stage = chunk_rows + NG * MCRT_PSF_RA + MCRT_PSF_RA;
+    for (int i = tid; i < n_stage; i += 256) {
+        const int r = chunk0 + i;
+        s_row[psf_pad(i)] = r < rows ? __ldg(&src[r]) : 0.0f;
+    }
+    __syncthreads();
+    const int l0 = tid * MCRT_PSF_RA;
+    const int r0 = chunk0 + l0;
+    if (l0 >= chunk_rows || r0 >= rows - ka || r0 + MCRT_PSF_RA <= ka) return;
+    float acc[MCRT_PSF_RA], win[MCRT_PSF_RA];
+    const float* wp = s_row + psf_pad(l0);
+#pragma unroll
+    for (int j = 0; j < MCRT_PSF_RA; j++) { acc[j] = 0.0f; win[j] = wp[j]; }
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+#pragma unroll
+        for (int kk = 0; kk < MCRT_PSF_RA; kk++) {
+            const int k = g * MCRT_PSF_RA + kk;
+            if (g < NG - 1 || k < ka) {
+                const float t = taps.t[k];
+#pragma unroll
+                for (int j = 0; j < MCRT_PSF_RA; j++) acc[j] += win[(kk + j) & (MCRT_PSF_RA - 1)] * t;
+                win[kk] = wp[(g + 1) * (MCRT_PSF_RA + 1) + kk];       // logical row l0 + k + R
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < MCRT_PSF_RA; j++) {
+        const int r = r0 + j;
+        if (r >= ka && r < rows - ka) dst[r] = acc[j];
+    }
+}
+
 // Lateral pass (rfimage.h:111-122) + untouched borders (B-9).  Thread = one row, MCRT_PSF_R consecutive
 // scanlines; lanes walk consecutive rows, so every load/store is coalesced and no shared memory is needed.
 // BYROW: depth-dependent lateral PSF, tap k of RF row r = taps_by_row[k * rows + r].
@@ -821,74 +869,83 @@ __global__ void __launch_bounds__(256) k_psf_lateral(const float* __restrict__ r
     }
 }
 
+// The lateral pass with the tap loop resolved at compile time (NG groups of MCRT_PSF_RL taps, only the last group checks k < kl; taps in
+// the constant bank) and 16 scanlines per thread: every loaded value feeds 16 outputs (32 FP instructions per LDG + pointer step, and
+// (16 + kl - 1) / 16 = 2.9 reads of every input value through L2 instead of 4.75 with 8 scanlines).  Interior scanline groups -- all
+// 16 outputs convolved, all kl + 15 inputs inside the image -- carry no guards at all.  Same arithmetic and order: bit-identical.
+#define MCRT_PSF_RL 16
+template <int NG, bool GUARD>
+__device__ __forceinline__ void lateral_ct_body(const float* __restrict__ p, const int rows, const LongTaps& taps, const int kl, const int c_left,
+                                                float (&acc)[MCRT_PSF_RL])
+{
+    float win[MCRT_PSF_RL];
+#pragma unroll
+    for (int j = 0; j < MCRT_PSF_RL; j++) { acc[j] = 0.0f; win[j] = (!GUARD || j < c_left) ? __ldg(p + (size_t)j * rows) : 0.0f; }
+    p += (size_t)MCRT_PSF_RL * rows;
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+#pragma unroll
+        for (int kk = 0; kk < MCRT_PSF_RL; kk++) {
+            const int k = g * MCRT_PSF_RL + kk;
+            if (g < NG - 1 || k < kl) {
+                const float t = taps.t[k];
+#pragma unroll
+                for (int j = 0; j < MCRT_PSF_RL; j++) acc[j] += win[(kk + j) & (MCRT_PSF_RL - 1)] * t;
+                // the refill of tap k is first used by tap k + 1: not needed after the last tap
+                if (g < NG - 1 || k + 1 < kl) win[kk] = (!GUARD || k + MCRT_PSF_RL < c_left) ? __ldg(p) : 0.0f;
+                p += rows;
+            }
+        }
+    }
+}
+
+template <int NG>
+__global__ void __launch_bounds__(256) k_psf_lateral_ct(const float* __restrict__ raw, const float* __restrict__ axial_buf, const int cols,
+                                                       const int rows, const __grid_constant__ LongTaps taps, const int ka, const int kl,
+                                                       const int col_offset, const int cols_total, float* __restrict__ out, const int raw_pitch)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int c0 = blockIdx.y * MCRT_PSF_RL;
+    const size_t img = (size_t)blockIdx.z * cols * rows;
+    const bool row_ok = r >= ka && r < rows - ka;
+    const int c_left = cols - c0;
+    float* o = out + img + (size_t)c0 * rows + r;
+    const float* p = axial_buf + img + (size_t)c0 * rows + r;
+    float acc[MCRT_PSF_RL];
+    // interior group (uniform per CTA): every scanline of the group is convolved and every input scanline exists
+    if (col_offset + c0 >= kl / 2 && col_offset + c0 + MCRT_PSF_RL <= cols_total - kl && c_left >= MCRT_PSF_RL + kl - 1) {
+        if (row_ok) {
+            lateral_ct_body<NG, false>(p, rows, taps, kl, c_left, acc);
+#pragma unroll
+            for (int j = 0; j < MCRT_PSF_RL; j++) o[(size_t)j * rows] = acc[j];
+            return;
+        }
+        const float* rw = raw + ((size_t)blockIdx.z * cols + c0) * raw_pitch + r;
+#pragma unroll
+        for (int j = 0; j < MCRT_PSF_RL; j++) o[(size_t)j * rows] = __ldg(rw + (size_t)j * raw_pitch);
+        return;
+    }
+    // border groups: the rule in GLOBAL scanline indices (a scanline-block run holds scanlines col_offset.. of cols_total)
+    const bool any = row_ok && (col_offset + c0 + MCRT_PSF_RL > kl / 2) && (col_offset + c0 < cols_total - kl);
+    if (any) lateral_ct_body<NG, true>(p, rows, taps, kl, c_left, acc);
+    const float* rw = raw + ((size_t)blockIdx.z * cols + c0) * raw_pitch + r;
+#pragma unroll
+    for (int j = 0; j < MCRT_PSF_RL; j++) {
+        const int c = c0 + j;
+        if (c >= cols) break;
+        o[(size_t)j * rows] = (any && col_offset + c >= kl / 2 && col_offset + c < cols_total - kl) ? acc[j] : __ldg(rw + (size_t)j * raw_pitch);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // rf_image::envelope (rfimage.h:54-91).  A sample i in [1, rows-2] is a peak iff I[i-1] < I[i] and not
 // I[i] < I[i+1] (the sequential `ascending` flag reduces to this because peak detection only ever reads
 // samples that have not been rewritten yet).  Between consecutive peaks p < q the output is
 // lerp(last, |I[q]|) with last = I[0] (signed) for the virtual first peak and |I[p]| otherwise; samples
 // from the last peak on keep their raw value.
-// Long-scanline version: k_peak_masks writes one 32-row peak bit mask per word, then k_envelope_lerp
-// is fully parallel -- each sample finds its enclosing peaks by scanning mask words (peaks are a few
-// samples apart in RF data, so the scan almost always ends in the sample's own word).
+// Long-scanline versions below (round 1's k_peak_masks + k_envelope_lerp pair is gone).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_peak_masks(const float* __restrict__ in, const int64_t n_scanlines, const int rows, const int words,
-                                                   unsigned* __restrict__ masks)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t total = n_scanlines * words;
-    for (int64_t wdx = warp; wdx < total; wdx += n_warps) {
-        const int64_t sl = wdx / words;
-        const int c = (int)(wdx - sl * words);
-        const float* I = in + sl * rows;
-        const int i = (c << 5) + lane;
-        const float v = i < rows ? __ldg(&I[i]) : 0.0f;
-        const float vm = (i >= 1 && i < rows) ? __ldg(&I[i - 1]) : 0.0f;
-        const float vp = (i + 1 < rows) ? __ldg(&I[i + 1]) : 0.0f;
-        const bool peak = (i >= 1) && (i + 1 < rows) && (vm < v) && !(v < vp);
-        const unsigned m = __ballot_sync(0xffffffffu, peak);
-        if (lane == 0) masks[wdx] = m;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_envelope_lerp(const float* __restrict__ in, const unsigned* __restrict__ masks, const int64_t n_scanlines,
-                                                      const int rows, const int words, float* __restrict__ out)
-{
-    const int64_t total = n_scanlines * rows;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t sl = idx / rows;
-        const int i = (int)(idx - sl * rows);
-        const float* I = in + sl * rows;
-        const unsigned* M = masks + sl * words;
-        const int w0 = i >> 5, b = i & 31;
-        // last peak at or before i (0 = the virtual first peak (0, I[0]) of rfimage.h:63-64)
-        int p = 0;
-        {
-            unsigned m = __ldg(&M[w0]) & (0xffffffffu >> (31 - b));
-            int w = w0;
-            while (m == 0u && w > 0) m = __ldg(&M[--w]);
-            if (m) p = (w << 5) + (31 - __clz(m));
-        }
-        // first peak strictly after i (rows = none)
-        int q = rows;
-        {
-            unsigned m = b == 31 ? 0u : (__ldg(&M[w0]) & (0xffffffffu << (b + 1)));
-            int w = w0;
-            while (m == 0u && w + 1 < words) m = __ldg(&M[++w]);
-            if (m) q = (w << 5) + (__ffs(m) - 1);
-        }
-        float r = __ldg(&I[i]);
-        if (q < rows) {
-            const float last = (p == 0) ? __ldg(&I[0]) : fabsf(__ldg(&I[p]));
-            const float new_peak = fabsf(__ldg(&I[q]));
-            const float alpha = ((float)i - (float)p) / ((float)q - (float)p);
-            r = last * (1 - alpha) + new_peak * alpha;
-        }
-        out[idx] = r;
-    }
-}
-
 // Long scanlines, round 2: ONE kernel (round 1: k_peak_masks + a fully parallel k_envelope_lerp that paid a 64-bit division and two
 // mask scans per SAMPLE, 190 instruction slots per pixel).  Same arithmetic as k_post_fused's envelope: bit-identical.
 #define MCRT_ENV_WARPS 8
@@ -946,6 +1003,121 @@ __global__ void __launch_bounds__(MCRT_ENV_WARPS * 32) k_envelope_stream(const f
             }
         }
         __syncthreads();
+    }
+}
+
+// Round 2, second step (k_envelope_tiles): a scanline is cut into tiles of 32 chunks (1024 rows), ONE WARP PER TILE, a CTA per scanline.
+// The warp loads its tile with 32 independent coalesced loads and keeps it in registers; the peak test takes its neighbours from
+// the adjacent lanes (shuffles), a peak value inside the sample's own chunk is a shuffle as well, and the nearest peaks outside the
+// chunk travel as warp-uniform (position, value) pairs: a backward sweep over the tile's chunk masks gives every chunk the first
+// peak after it, a running pair the last peak before it, and the tiles exchange their first / last peak through a few words of
+// shared memory -- ONE barrier per scanline, no per-sample mask scans, no re-read of the scanline.
+// alpha = (i - p) / (q - p) is the 3-instruction Markstein division from a reciprocal table (div_small_int, exhaustively equal to the
+// IEEE quotient for gaps up to 2048 rows; larger gaps take the IEEE division).  Same arithmetic as k_envelope_stream: bit-identical.
+#define MCRT_ENV_RCP 2048
+#ifndef MCRT_ENVT_CH
+#define MCRT_ENVT_CH 32                                   // chunks per warp tile
+#endif
+#ifndef MCRT_ENVT_MINB
+#define MCRT_ENVT_MINB 3                                  // resident CTAs per SM the register allocation aims at (<= 640-thread variants)
+#endif
+__device__ __forceinline__ float div_small_int(float a, float b, float y);
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, (MAXT <= 640 ? MCRT_ENVT_MINB : 1)) k_envelope_tiles(const float* __restrict__ in, const int64_t n_scanlines, const int rows,
+                                                        float* __restrict__ out)
+{
+    extern __shared__ unsigned s_env[];    // rcp[n_rcp + 1] | per warp: 7 x 32 words (below) | 2 x per warp: first pos / val, last pos / val
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int n_rcp = rows < MCRT_ENV_RCP ? rows : MCRT_ENV_RCP;
+    float* rcp = reinterpret_cast<float*>(s_env);
+    unsigned* wmask = s_env + (n_rcp + 1) + w * (7 * MCRT_ENVT_CH);      // peak mask of chunk c
+    float* wfv = reinterpret_cast<float*>(wmask + MCRT_ENVT_CH);        // |value| of the chunk's first peak
+    float* wlv = wfv + MCRT_ENVT_CH;                                    // |value| of the chunk's last peak
+    int* wnq = reinterpret_cast<int*>(wlv + MCRT_ENVT_CH);              // first peak after chunk c: row (rows: none) ...
+    float* wnv = reinterpret_cast<float*>(wnq + MCRT_ENVT_CH);          // ... and |value|
+    int* wlp = reinterpret_cast<int*>(wnv + MCRT_ENVT_CH);              // last peak before chunk c: row (0: the virtual first peak) ...
+    float* wlq = reinterpret_cast<float*>(wlp + MCRT_ENVT_CH);          // ... and value
+    int* summ = reinterpret_cast<int*>(s_env + (n_rcp + 1) + nw * (7 * MCRT_ENVT_CH));   // [2][nw][4]
+    for (int i = threadIdx.x; i <= n_rcp; i += blockDim.x) rcp[i] = i > 0 ? 1.0f / (float)i : 0.0f;
+    const unsigned le_mask = 0xffffffffu >> (31 - lane);                  // bits <= lane
+    const unsigned gt_mask = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int tile0 = w * (32 * MCRT_ENVT_CH);
+    int parity = 0;
+    for (int64_t sl = blockIdx.x; sl < n_scanlines; sl += gridDim.x, parity ^= 1) {
+        const float* I = in + sl * rows + tile0;
+        float* O = out + sl * rows + tile0;
+        // ---- the tile -> registers; per chunk: peak mask and the values of its first / last peak -> shared memory ----
+        float v[MCRT_ENVT_CH];
+#pragma unroll
+        for (int c = 0; c < MCRT_ENVT_CH; c++) v[c] = tile0 + 32 * c + lane < rows ? __ldg(I + 32 * c + lane) : 0.0f;
+        const float left = (lane == 0 && tile0 >= 1) ? __ldg(I - 1) : 0.0f;
+        const float right = (lane == 31 && tile0 + 32 * MCRT_ENVT_CH < rows) ? __ldg(I + 32 * MCRT_ENVT_CH) : 0.0f;
+#pragma unroll
+        for (int c = 0; c < MCRT_ENVT_CH; c++) {
+            const int i = tile0 + 32 * c + lane;
+            float vm = __shfl_up_sync(0xffffffffu, v[c], 1), vp = __shfl_down_sync(0xffffffffu, v[c], 1);
+            const float prev_last = c > 0 ? __shfl_sync(0xffffffffu, v[c > 0 ? c - 1 : 0], 31) : left;
+            const float next_first = c + 1 < MCRT_ENVT_CH ? __shfl_sync(0xffffffffu, v[c + 1 < MCRT_ENVT_CH ? c + 1 : c], 0) : right;
+            if (lane == 0) vm = prev_last;
+            if (lane == 31) vp = next_first;
+            const bool peak = (i >= 1) && (i + 1 < rows) && (vm < v[c]) && !(v[c] < vp);
+            const unsigned m = __ballot_sync(0xffffffffu, peak);
+            // (an empty mask shuffles from lanes 31 / 0: the values are never used)
+            const float fv = __shfl_sync(0xffffffffu, v[c], (__ffs(m) - 1) & 31), lv = __shfl_sync(0xffffffffu, v[c], (31 - __clz(m)) & 31);
+            if (lane == 0) { wmask[c] = m; wfv[c] = fabsf(fv); wlv[c] = fabsf(lv); }
+        }
+        __syncwarp();
+        // ---- lane c = chunk c: the nearest non-empty chunks of the tile on either side ----
+        const unsigned mc = wmask[lane];
+        const unsigned B = __ballot_sync(0xffffffffu, mc != 0u);
+        const unsigned after = B & gt_mask, before = B & lt_mask;
+        const int na = __ffs(after) - 1, nb = 31 - __clz(before);
+        const int nq_in = after ? tile0 + 32 * na + (__ffs(wmask[na & 31]) - 1) : -1;
+        const float nv_in = wfv[na & 31];
+        const int lp_in = before ? tile0 + 32 * nb + (31 - __clz(wmask[nb & 31])) : -1;
+        const float lv_in = wlv[nb & 31];
+        // the tile's first / last peak for the other tiles
+        int* my = summ + (parity * nw + w) * 4;
+        if (lane == 0) {
+            const int f = __ffs(B) - 1, l = 31 - __clz(B);
+            my[0] = B ? tile0 + 32 * f + (__ffs(wmask[f & 31]) - 1) : -1; my[1] = __float_as_int(wfv[f & 31]);
+            my[2] = B ? tile0 + 32 * l + (31 - __clz(wmask[l & 31])) : -1; my[3] = __float_as_int(wlv[l & 31]);
+        }
+        __syncthreads();
+        // ---- nearest peaks outside the tile ----
+        int rq = rows; float rv = 0.0f;                                      // first peak after the tile (rows: none)
+        for (int t = w + 1; t < nw; t++) { const int* o = summ + (parity * nw + t) * 4; if (o[0] >= 0) { rq = o[0]; rv = __int_as_float(o[1]); break; } }
+        int lp = 0; float lval = __ldg(in + sl * rows);                        // last peak before the tile (0: the virtual first peak (0, I[0]))
+        for (int t = w - 1; t >= 0; t--) { const int* o = summ + (parity * nw + t) * 4; if (o[2] >= 0) { lp = o[2]; lval = __int_as_float(o[3]); break; } }
+        wnq[lane] = nq_in >= 0 ? nq_in : rq; wnv[lane] = nq_in >= 0 ? nv_in : rv;
+        wlp[lane] = lp_in >= 0 ? lp_in : lp; wlq[lane] = lp_in >= 0 ? lv_in : lval;
+        __syncwarp();
+        // ---- interpolate ----
+#pragma unroll
+        for (int c = 0; c < MCRT_ENVT_CH; c++) {
+            const int base = tile0 + 32 * c;
+            if (base < rows) {                                               // warp-uniform
+                const int i = base + lane;
+                const unsigned m = wmask[c];
+                const unsigned le = m & le_mask, gt = m & gt_mask;
+                const int jl = 31 - __clz(le), jg = __ffs(gt) - 1;           // (garbage lanes when le / gt are empty: masked below)
+                const float vl = __shfl_sync(0xffffffffu, v[c], jl & 31), vg = __shfl_sync(0xffffffffu, v[c], jg & 31);
+                const int p = le ? base + jl : wlp[c];
+                const float last = le ? fabsf(vl) : wlq[c];
+                const int q = gt ? base + jg : wnq[c];
+                const float new_peak = gt ? fabsf(vg) : wnv[c];
+                float r = v[c];
+                if (q < rows) {
+                    const int d = q - p;
+                    const float fa = (float)(i - p), fd = (float)d;          // == (float)i - (float)p, (float)q - (float)p: exact integers
+                    const float alpha = d <= MCRT_ENV_RCP ? div_small_int(fa, fd, rcp[d <= MCRT_ENV_RCP ? d : 0]) : fa / fd;
+                    r = last * (1 - alpha) + new_peak * alpha;
+                }
+                if (i < rows) O[32 * c + lane] = r;
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -1547,6 +1719,10 @@ static bool post_tma_usable(int rows, int pitch, int n_axial, int n_lateral, int
            h_axial && h_lateral && pitch * 2 <= MCRT_TMA_THREADS;
 }
 static size_t post_tma_smem(int pitch, int tc) { return sizeof(float) * 2 * (size_t)(tc + 13 - 1) * pitch; }
+// A/B switch (option "long_ct"): compile-time-tap axial / lateral kernels and the shared-memory envelope on the long-scanline path
+static bool g_long_ct = true;
+void set_long_scanline_ct(bool on) { g_long_ct = on; }
+
 void launch_post(const float* d_in, int n_images, int cols, int rows, const float* d_axial, int n_axial, const float* d_lateral,
                  int n_lateral, int flags, float* d_tmp0, float* d_tmp1, float* d_out, cudaStream_t stream, int* launches, int col_offset,
                  int cols_total, const float* d_lateral_by_row, int in_pitch, const float* h_axial, const float* h_lateral)
@@ -1597,6 +1773,12 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
     }
     // long scanlines: register-blocked axial / lateral passes, mask-based parallel envelope
     const float* cur = d_in;
+    // compile-time tap loops (taps as kernel parameters) whenever the host copy of the taps is at hand and they fit
+    LongTaps ltaps_a, ltaps_l;
+    const int ng_ax = (n_axial + MCRT_PSF_RA - 1) / MCRT_PSF_RA, ng_lat = (n_lateral + MCRT_PSF_RL - 1) / MCRT_PSF_RL;
+    const bool ct_ax = h_axial && n_axial >= 1 && n_axial <= 64 && g_long_ct;
+    const bool ct_lat = h_lateral && n_lateral >= 1 && n_lateral <= 64 && !d_lateral_by_row && g_long_ct;
+    for (int k = 0; k < 64; k++) { ltaps_a.t[k] = ct_ax && k < n_axial ? h_axial[k] : 0.0f; ltaps_l.t[k] = ct_lat && k < n_lateral ? h_lateral[k] : 0.0f; }
     if (flags & 1) {
         // even chunks: as few CTAs per scanline as fit MCRT_PSF_CHUNK, all the same size
         const int n_ch = (rows + MCRT_PSF_CHUNK - 1) / MCRT_PSF_CHUNK;
@@ -1607,14 +1789,27 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
         for (int64_t s0 = 0; s0 < n_scanlines; s0 += 65535) {
             const int64_t ns = n_scanlines - s0 < 65535 ? n_scanlines - s0 : 65535;
             ga.y = (unsigned)ns;
-            k_psf_axial<<<ga, 256, smem_ax, stream>>>(cur + s0 * in_pitch, rows, d_axial, n_axial, d_tmp0 + s0 * rows, in_pitch, chunk_rows);
+            if (ct_ax) {
+                const size_t smem_ct = sizeof(float) * (size_t)(psf_pad(chunk_rows + ng_ax * MCRT_PSF_RA + 2 * MCRT_PSF_RA) + 1);
+                const float* a_in = cur + s0 * in_pitch;
+                float* a_out = d_tmp0 + s0 * rows;
+#define MCRT_AX_CASE(G) case G: k_psf_axial_ct<G><<<ga, 256, smem_ct, stream>>>(a_in, rows, ltaps_a, n_axial, a_out, in_pitch, chunk_rows); break;
+                switch (ng_ax) { MCRT_AX_CASE(1) MCRT_AX_CASE(2) MCRT_AX_CASE(3) MCRT_AX_CASE(4) MCRT_AX_CASE(5) MCRT_AX_CASE(6) MCRT_AX_CASE(7) MCRT_AX_CASE(8) default: break; }
+#undef MCRT_AX_CASE
+            } else
+                k_psf_axial<<<ga, 256, smem_ax, stream>>>(cur + s0 * in_pitch, rows, d_axial, n_axial, d_tmp0 + s0 * rows, in_pitch, chunk_rows);
             if (launches) (*launches)++;
         }
         float* dst = (flags & 2) ? d_tmp1 : d_out;
         dim3 gl((rows + 255) / 256, (cols + MCRT_PSF_R - 1) / MCRT_PSF_R, n_images);
         if (d_lateral_by_row)
             k_psf_lateral<true><<<gl, 256, 0, stream>>>(cur, d_tmp0, cols, rows, d_lateral, n_axial, n_lateral, col_offset, cols_total, dst, d_lateral_by_row, in_pitch);
-        else
+        else if (ct_lat) {
+            const dim3 gc((rows + 255) / 256, (cols + MCRT_PSF_RL - 1) / MCRT_PSF_RL, n_images);
+#define MCRT_LAT_CASE(G) case G: k_psf_lateral_ct<G><<<gc, 256, 0, stream>>>(cur, d_tmp0, cols, rows, ltaps_l, n_axial, n_lateral, col_offset, cols_total, dst, in_pitch); break;
+            switch (ng_lat) { MCRT_LAT_CASE(1) MCRT_LAT_CASE(2) MCRT_LAT_CASE(3) MCRT_LAT_CASE(4) default: break; }
+#undef MCRT_LAT_CASE
+        } else
             k_psf_lateral<false><<<gl, 256, 0, stream>>>(cur, d_tmp0, cols, rows, d_lateral, n_axial, n_lateral, col_offset, cols_total, dst, nullptr, in_pitch);
         cur = dst;
         if (launches) (*launches)++;
@@ -1625,7 +1820,18 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
         const size_t smem_env = sizeof(unsigned) * 3 * (size_t)words;
         int64_t g = n_scanlines;
         if (g > 148 * 64) g = 148 * 64;
-        k_envelope_stream<<<(int)g, MCRT_ENV_WARPS * 32, smem_env, stream>>>(cur, n_scanlines, rows, words, d_out);
+        const int nw_t = (words + MCRT_ENVT_CH - 1) / MCRT_ENVT_CH;           // warps (tiles) per scanline: <= 32 for rows <= 32768
+        const size_t smem_t = sizeof(unsigned) * ((size_t)(rows < MCRT_ENV_RCP ? rows : MCRT_ENV_RCP) + 1 + (size_t)nw_t * (7 * MCRT_ENVT_CH) + 2 * (size_t)nw_t * 4);
+        if (g_long_ct && nw_t <= 32) {                                         // (MCRT_ENVT_CH = 32: every rows <= 32768)
+            // persistent: a few CTAs per SM walk the scanlines (the reciprocal table is built once per CTA)
+            int64_t gt = n_scanlines;
+            const int64_t cap = 148 * (int64_t)(2048 / (32 * nw_t) > 0 ? 2048 / (32 * nw_t) : 1) * 2;
+            if (gt > cap) gt = cap;
+            if (nw_t <= 12) k_envelope_tiles<384><<<(int)gt, 32 * nw_t, smem_t, stream>>>(cur, n_scanlines, rows, d_out);
+            else if (nw_t <= 20) k_envelope_tiles<640><<<(int)gt, 32 * nw_t, smem_t, stream>>>(cur, n_scanlines, rows, d_out);
+            else k_envelope_tiles<1024><<<(int)gt, 32 * nw_t, smem_t, stream>>>(cur, n_scanlines, rows, d_out);
+        } else
+            k_envelope_stream<<<(int)g, MCRT_ENV_WARPS * 32, smem_env, stream>>>(cur, n_scanlines, rows, words, d_out);
         if (launches) (*launches) += 1;
     } else if (!(flags & 1)) {
         k_copy<<<grid1d(total, 256), 256, 0, stream>>>(cur, total, d_out);

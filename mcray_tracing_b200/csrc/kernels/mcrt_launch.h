@@ -133,6 +133,7 @@ cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2
 
 // rf_image::convolve + envelope (rfimage.h:93-123, 54-91) on [n_images][cols][rows]; flags bit0 convolve, bit1 envelope.
 // d_tmp0/d_tmp1: scratch of the same size as the image batch.  Result always lands in d_out.
+void set_long_scanline_ct(bool on);   // A/B switch of the round-2 long-scanline post kernels (default on)
 void launch_post(const float* d_in, int n_images, int cols, int rows, const float* d_axial, int n_axial, const float* d_lateral,
                  int n_lateral, int flags, float* d_tmp0, float* d_tmp1, float* d_out, cudaStream_t stream, int* launches,
                  int col_offset = 0, int cols_total = 0,     // scanline-block runs: global index of scanline 0 / global scanline count

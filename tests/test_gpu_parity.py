@@ -206,7 +206,10 @@ def test_accumulate_matches_oracle(api, O, ircad_rough):
 
 @pytest.mark.parametrize("cols,rows,ka,kl", [(512, 465, 7, 13), (256, 465, 7, 13), (40, 64, 7, 13), (64, 300, 31, 15), (33, 31, 3, 5),
                                               # rows > 2048: the long-scanline kernels (register-blocked PSF, mask-based envelope)
-                                              (40, 2500, 7, 13), (9, 2100, 3, 5), (70, 4099, 63, 31), (17, 2049, 9, 1)])
+                                              (40, 2500, 7, 13), (9, 2100, 3, 5), (70, 4099, 63, 31), (17, 2049, 9, 1),
+                                              # tap counts on and around the 8-tap (axial) / 16-tap (lateral) groups of the compile-time kernels,
+                                              # scanline counts that leave interior AND border groups of 16, the largest supported taps
+                                              (150, 2100, 40, 17), (130, 2300, 64, 32), (50, 2200, 16, 16), (97, 2070, 8, 33), (35, 2060, 1, 48)])
 def test_convolve_and_envelope_bit_exact(api, O, sphere, cols, rows, ka, kl):
     rng = np.random.default_rng(cols * 1000 + rows)
     img = rng.normal(size=(rows, cols)).astype(np.float32)          # oracle layout [rows][cols]
@@ -221,6 +224,32 @@ def test_convolve_and_envelope_bit_exact(api, O, sphere, cols, rows, ka, kl):
     assert np.array_equal(g_conv.T, o_conv)
     assert np.array_equal(g_env.T, O.envelope(img))
     assert np.array_equal(g_both.T, O.envelope(o_conv))
+    if rows > 2048:
+        # the round-1 long-scanline kernels (run-time tap loops, global-memory envelope) give the same bits
+        with api.Simulator(sphere[0], api.default_params(elements=64, samples=1)) as sim:
+            sim.set_option("long_ct", 0)
+            try:
+                assert np.array_equal(sim.postprocess(img.T, ax, lat, convolve=True, envelope=True), g_both)
+            finally:
+                sim.set_option("long_ct", 1)
+
+
+def test_envelope_long_peak_gaps(api, O, sphere):
+    """Long scanlines whose peaks lie more than 2048 rows apart (the envelope's reciprocal-table division covers gaps up to 2048 rows
+    and falls back to the IEEE division beyond), a scanline without any peak, and one with a peak in every other row."""
+    rows, cols = 9000, 6
+    r = np.arange(rows, dtype=np.float32)
+    img = np.zeros((rows, cols), np.float32)
+    img[:, 0] = r * 0.25 - 7.0                                           # monotone: no peak at all
+    img[:, 1] = -np.abs(r - 4500.0)                                      # one peak in the middle: gaps of 4500 rows
+    img[:, 2] = np.where(r < 3000, r, 6000.0 - r) + np.where(r > 8000, (r - 8000) * 5, 0)   # peak at 3000, then a valley: gap > 2048
+    img[:, 3] = (np.arange(rows) % 2).astype(np.float32) * (1.0 + r / 100)               # a peak in every other row
+    rng = np.random.default_rng(5)
+    img[:, 4] = rng.normal(size=rows).astype(np.float32)
+    img[::2500, 5] = 3.0                                                  # isolated spikes 2500 rows apart
+    with api.Simulator(sphere[0], api.default_params(elements=64, samples=1)) as sim:
+        g = sim.postprocess(img.T, np.ones(1, np.float32), np.ones(1, np.float32), convolve=False, envelope=True)
+    assert np.array_equal(g.T, O.envelope(img))
 
 
 def test_cast_rays_bit_exact_to_the_reference_loop_golden(api, O):
