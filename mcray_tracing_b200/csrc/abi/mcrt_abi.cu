@@ -2,6 +2,7 @@
 // (upload poses -> wavefront trace -> accumulate -> PSF -> envelope -> scan conversion), CUDA-graph
 // capture of that pipeline, and the stage-level entry points the parity tests call.
 // No CPU fallback anywhere: every compute entry point launches the kernels of csrc/kernels/.
+#include <algorithm>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -205,9 +206,9 @@ void free_workspace(mcrt_ctx* c)
     dev_free(c->tb.queue_a); dev_free(c->tb.queue_b); dev_free(c->tb.counters);
     dev_free(c->tb.sort_keys); dev_free(c->tb.sort_keys_tmp); dev_free(c->tb.sort_queue_tmp);
     dev_free(c->tb.warp_counts); dev_free(c->tb.tile_counts); c->tb.n_tiles = 0; dev_free(c->tb.first_hits);
-    dev_free(c->tree.rays_a); dev_free(c->tree.rays_b); dev_free(c->tree.segments); dev_free(c->tree.keys); dev_free(c->tree.keys_sorted);
-    dev_free(c->tree.slots); dev_free(c->tree.slots_sorted); dev_free(c->tree.path_first); dev_free(c->tree.path_count); dev_free(c->tree.counters);
-    if (c->tree.sort_tmp) cudaFree(c->tree.sort_tmp);
+    dev_free(c->tree.rays_a); dev_free(c->tree.rays_b); dev_free(c->tree.queue_a); dev_free(c->tree.queue_b); dev_free(c->tree.warp_counts);
+    dev_free(c->tree.tile_counts); dev_free(c->tree.segments); dev_free(c->tree.keys); dev_free(c->tree.level_first); dev_free(c->tree.level_end);
+    dev_free(c->tree.counters);
     c->tree = TreeBuffers{};
     if (c->tb.sort_tmp) cudaFree(c->tb.sort_tmp);
     c->tb.sort_tmp = nullptr; c->tb.sort_tmp_bytes = 0;
@@ -245,18 +246,21 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
     dev_alloc(c->d_scan, (size_t)n_poses * c->params.scan_rows * c->params.scan_cols);
     dev_alloc(c->d_max_bits, (size_t)n_poses);
     // the windowed accumulate kernel keeps its columns in shared memory: no HBM columns at all
-    c->columns_bytes = (c->aq.accumulate_windowed && c->tree_budget == 0) ? 0 : accumulate_columns_bytes(c->aq, n_poses);
+    c->columns_bytes = (c->aq.accumulate_windowed || c->tree_budget > 0) ? 0 : accumulate_columns_bytes(c->aq, n_poses);
     if (c->tree_budget > 0) {
         const size_t cap = n_paths * (size_t)c->tree_budget;
         if (cap > 0x3fffffffULL) throw std::invalid_argument("ray_tree: batch too large for the segment pool; reduce max_batch_poses or the budget");
         TreeBuffers& t = c->tree;
         t.seg_capacity = (int)cap; t.ray_capacity = (int)(cap / 2 + n_paths);
-        dev_alloc(t.rays_a, (size_t)t.ray_capacity); dev_alloc(t.rays_b, (size_t)t.ray_capacity);
-        dev_alloc(t.segments, cap); dev_alloc(t.keys, cap); dev_alloc(t.keys_sorted, cap); dev_alloc(t.slots, cap); dev_alloc(t.slots_sorted, cap);
-        dev_alloc(t.path_first, n_paths); dev_alloc(t.path_count, n_paths);
+        t.n_scanlines = n_poses * c->aq.elements;
+        const size_t n_chunks = (size_t)t.ray_capacity / 32 + 1;
+        t.n_tiles = (int)((n_chunks + 255) / 256);
+        dev_alloc(t.rays_a, 64 * n_chunks); dev_alloc(t.rays_b, 64 * n_chunks);
+        dev_alloc(t.queue_a, (size_t)t.ray_capacity); dev_alloc(t.queue_b, (size_t)t.ray_capacity);
+        dev_alloc(t.warp_counts, n_chunks); dev_alloc(t.tile_counts, (size_t)c->aq.max_depth * t.n_tiles);
+        dev_alloc(t.segments, cap); dev_alloc(t.keys, cap);
+        dev_alloc(t.level_first, (size_t)c->aq.max_depth * t.n_scanlines); dev_alloc(t.level_end, (size_t)c->aq.max_depth * t.n_scanlines);
         dev_alloc(t.counters, (size_t)c->aq.max_depth + 3);
-        t.sort_tmp_bytes = tree_sort_tmp_bytes(t.seg_capacity);
-        CUDA_TRY(cudaMalloc(&t.sort_tmp, t.sort_tmp_bytes ? t.sort_tmp_bytes : 16));
     }
     if (c->columns_bytes) dev_alloc(c->d_columns, c->columns_bytes / sizeof(float));
     CUDA_TRY(cudaMallocHost(&c->h_poses, sizeof(PoseTrig) * (size_t)n_poses));
@@ -441,8 +445,8 @@ void run_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches
     if (launches) *launches += c->graph_launches[key];
 }
 
-// ray-tree mode: trace the trees, sort the segments by (path, node), accumulate per path in that order, then the usual
-// PSF / envelope / scan chain.  Not graph-captured (the radix sort picks its passes at run time).
+// ray-tree mode: trace the trees level by level (ordered, nothing is sorted), accumulate a lane per segment, then the usual
+// PSF / envelope / scan chain.  Not graph-captured (rarely used; the launch sequence itself is static).
 void run_tree_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches)
 {
     CUDA_TRY(cudaMemsetAsync(c->d_steps, 0, 2 * sizeof(unsigned long long), s));
@@ -454,7 +458,7 @@ void run_tree_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* lau
     if (c->profile_stages) CUDA_TRY(cudaEventRecord(c->ev_a, s));
     launch_trace_tree(c->sc, c->aq, fr, t, c->sm_count, s, launches);
     if (c->profile_stages) CUDA_TRY(cudaEventRecord(c->ev_b, s));
-    CUDA_TRY(launch_accumulate_tree(c->sc, c->aq, c->d_volume, t, n, c->d_rf_acc, c->d_steps, c->d_columns, s, launches));
+    CUDA_TRY(launch_accumulate_tree(c->sc, c->aq, c->d_volume, t, n, c->d_rf_acc, c->d_steps, s, launches));
     if (c->profile_stages) CUDA_TRY(cudaEventRecord(c->ev_c, s));
     launch_post(c->d_rf_acc, n, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
                 c->d_rf_tmp0, c->d_rf_tmp1, c->d_rf_final, s, launches, 0, 0, c->d_lat_by_row, c->aq.rf_pitch, c->post_tma ? c->h_axial.data() : nullptr,
@@ -1370,14 +1374,17 @@ int mcrt_trace_tree_debug(mcrt_ctx* c, const mcrt_pose* pose, uint64_t seed, uin
         *n_out = cnt[0];
         if (cnt[0] > capacity) return fail(MCRT_ERR_INVALID, "mcrt_trace_tree_debug: capacity too small");
         const size_t n = (size_t)cnt[0];
-        std::vector<DevSegment> hs((size_t)t.seg_capacity);
-        std::vector<unsigned long long> keys(n);
+        // the device keeps the segments level by level; this debug hook returns them ordered by (path, node): sorted here, on the host
+        std::vector<DevSegment> hs(n);
+        std::vector<unsigned long long> keys_raw(n), keys(n);
         std::vector<unsigned> slots(n);
-        CUDA_TRY(cudaMemcpy(hs.data(), t.segments, sizeof(DevSegment) * (size_t)t.seg_capacity, cudaMemcpyDeviceToHost));
         if (n) {
-            CUDA_TRY(cudaMemcpy(keys.data(), t.keys_sorted, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
-            CUDA_TRY(cudaMemcpy(slots.data(), t.slots_sorted, sizeof(unsigned) * n, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(hs.data(), t.segments, sizeof(DevSegment) * n, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(keys_raw.data(), t.keys, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
         }
+        for (size_t i = 0; i < n; i++) slots[i] = (unsigned)i;
+        std::sort(slots.begin(), slots.end(), [&](unsigned a, unsigned b) { return keys_raw[a] < keys_raw[b]; });
+        for (size_t i = 0; i < n; i++) keys[i] = keys_raw[slots[i]];
         memset(segments, 0, sizeof(mcrt_segment) * n);
         for (size_t i = 0; i < n; i++) {
             const DevSegment& d = hs[slots[i]];

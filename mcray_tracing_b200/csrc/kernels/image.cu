@@ -385,12 +385,18 @@ __host__ __device__ __forceinline__ int win_stride(int T) { const int q = (T + 3
 
 // SCT > 0 (WARP only): the number of samples per element as a compile-time constant dividing 32 (16 in BASELINE's configuration):
 // the ring stride, the ring stores of an unrolled block and the sample reduction then carry no run-time index arithmetic.
-template <bool FMADIV, bool WARP, int SCT>
+// TREE (ray-tree mode, WARP and SCT = 32): the warp owns ONE scanline and a lane marches ONE SEGMENT of its ray trees per round (a
+// segment is self-contained: start point, start time, initial intensity), 32 segments per round in (level, path, node) order
+// (tree_first / tree_end: the scanline's segment range per level, TreeBuffers).  The 32 columns of a round are summed in lane order
+// and ADDED to the scanline's RF rows (rf is cleared before the launch); windows no lane of the round touches are skipped.
+template <bool FMADIV, bool WARP, int SCT, bool TREE = false>
 __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const SceneDev sc, const AcqDev aq, const float2* __restrict__ volume,
                                                        const DevSegment* __restrict__ segments, const int32_t* __restrict__ nseg,
                                                        const int n_scanlines, const int G_rt, float* __restrict__ rf,
                                                        unsigned long long* __restrict__ steps_total,
-                                                       unsigned long long* __restrict__ late_echoes)
+                                                       unsigned long long* __restrict__ late_echoes,
+                                                       const int* __restrict__ tree_first = nullptr, const int* __restrict__ tree_end = nullptr,
+                                                       const int tree_levels = 0, const int tree_stride = 0)
 {
     extern __shared__ float4 s_win4[];                     // per group: [MCRT_WIN_RING][stride]; row r lives in slot r % RING
     __shared__ DevMaterial s_mat[MCRT_MAX_SMEM_MATERIALS];
@@ -415,14 +421,36 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
     const double inv_time_step = 1.0 / aq.time_step_us;
     const double max_travel_time = aq.max_travel_time_us;
     const double row_period = aq.row_period_us, inv_row_period = aq.inv_row_period;
-    const float samples_f = (float)(size_t)S;
+    const float samples_f = (float)(size_t)(TREE ? aq.samples : S);   // (TREE: the 32 lanes of the group are segments, not samples)
     const float vres = aq.vol_resolution, inv_vres = 1.0f / aq.vol_resolution;
     const double row_delta = aq.time_step_us * aq.inv_row_period - 1.0;
     const bool fast_rows = row_delta >= 0.0 && row_delta < 0.2;
     const double block_safe_hi = 1.0 - 1e-6 - (double)(MCRT_WIN_UNROLL - 1) * row_delta;
 
+    // TREE: the scanline's segments, level by level; round r gives lane t the (32 r + t)-th of them
+    int tree_total = 0;
+    if (TREE && scanline0 < n_scanlines)
+        for (int l = 0; l < tree_levels; l++) { const int e = tree_end[(size_t)l * tree_stride + scanline0]; if (e) tree_total += e - tree_first[(size_t)l * tree_stride + scanline0]; }
+    unsigned long long my_steps = 0;
+    for (int round0 = 0; round0 < (TREE ? tree_total : 1); round0 += 32) {
+    int tree_slot = -1;
+    if (TREE) {
+        int j = round0 + t;
+        for (int l = 0; l < tree_levels && tree_slot < 0; l++) {
+            const int e = tree_end[(size_t)l * tree_stride + scanline0];
+            const int f = e ? tree_first[(size_t)l * tree_stride + scanline0] : 0;
+            if (j < e - f) tree_slot = f + j; else j -= e - f;
+        }
+    }
     // ---- per-path march state, kept in registers across windows ----
-    const int ns = active ? nseg[p] : 0;
+    const int ns = TREE ? (tree_slot >= 0 ? 1 : 0) : (active ? nseg[p] : 0);
+    int pend_row = -1;               // TREE: the RF row of the lane's next echo once it is known to lie beyond the current window
+    if (TREE && tree_slot >= 0) {
+        // a lower bound of the segment's first echo row (the exact row is found by try_echo): lets the warp skip the windows before it
+        const int4 s3 = __ldg(&segments[tree_slot].s3);
+        const double row_lo = ((__hiloint2double(s3.y, s3.x) * 1000) / aq.speed) * inv_row_period - 2.0;
+        pend_row = row_lo > 0.0 ? (row_lo < 2.0e9 ? (int)row_lo : 2000000000) : 0;
+    }
     int k = 0;                       // next segment to load
     bool in_seg = false;             // a segment is loaded and not finished
     bool fma_ok = false;
@@ -434,7 +462,6 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
     int n_safe = 0;                  // of those, steps that certainly satisfy the time bound
     float end_echo = 0.0f;           // the segment's closing echo (main.cpp:139) ...
     double end_micros = 0.0;         // ... and its time
-    unsigned long long my_steps = 0;
     // column writer state: rows [.., written) of my column are stored; cur_row accumulates in cur_acc
     int written = 0, cur_row = -1;
     float cur_acc = 0.0f;
@@ -442,6 +469,12 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
 
     for (int base = 0; base < rows; base += MCRT_WIN_ROWS) {
         const int wend = base + MCRT_WIN_ROWS < rows ? base + MCRT_WIN_ROWS : rows;
+        if (TREE) {
+            // nothing of this round lands in the window: no lane has a pending row in it, and every lane is finished or knows that
+            // its next echo lies beyond it
+            const bool idle = cur_row < 0 && ((k >= ns && !in_seg) || pend_row >= wend);
+            if (__all_sync(0xffffffffu, idle)) { if (written < wend) written = wend; continue; }
+        }
         // put `echo` into RF row `row` of my column (base <= row < wend, row >= cur_row)
         auto add_row = [&](float echo, int row) {
             if (row == cur_row) { cur_acc += echo; return; }
@@ -466,7 +499,7 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
             } else if (row >= rows) {
                 return true;
             }
-            if (row >= wend) return false;
+            if (row >= wend) { if (TREE) pend_row = row; return false; }
             if (row < base) {                                                                   // a finished window: see header
                 win_late_echo(&rf[(size_t)my_scanline * rf_pitch + row], echo, late_echoes);
                 return true;
@@ -479,11 +512,11 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
             return true;
         };
 
-        bool waiting = !active;                      // true: my next echo lies beyond this window (or the path is done)
+        bool waiting = !active || (TREE && pend_row >= wend);   // true: my next echo lies beyond this window (or the path is done)
         while (!waiting) {
             if (!in_seg) {
                 if (k >= ns) break;
-                const DevSegment* sg = segments + (size_t)p * aq.max_depth + k;
+                const DevSegment* sg = TREE ? segments + tree_slot : segments + (size_t)p * aq.max_depth + k;
                 const float4 s0 = __ldg(&sg->s0), s1 = __ldg(&sg->s1), s2 = __ldg(&sg->s2);
                 const int4 s3 = __ldg(&sg->s3);
                 const DevMaterial media = s_mat[s3.z];
@@ -645,7 +678,8 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
                         float sum = v.x; sum += v.y; sum += v.z; sum += v.w;
 #pragma unroll
                         for (int q = 1; q < (SCT > 0 ? SCT : 4) / 4; q++) { v = s4[q]; sum += v.x; sum += v.y; sum += v.z; sum += v.w; }
-                        dst[(size_t)g * rf_pitch] = sum;
+                        if (TREE) dst[(size_t)g * rf_pitch] += sum;           // rounds accumulate (same warp, program order)
+                        else dst[(size_t)g * rf_pitch] = sum;
                     }
                 }
             } else {
@@ -667,6 +701,7 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
         }
         group_sync();
     }
+    }   // rounds (TREE), a single pass otherwise
     if (steps_total) {
         for (int off = 16; off > 0; off >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, off);
         if ((threadIdx.x & 31) == 0 && my_steps) atomicAdd(steps_total, my_steps);
@@ -1640,21 +1675,22 @@ cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2
 }
 
 cudaError_t launch_accumulate_tree(const SceneDev& sc, const AcqDev& aq, const float2* d_volume, const TreeBuffers& tb, int n_poses,
-                                   float* d_rf, unsigned long long* d_steps, float* d_columns, cudaStream_t stream, int* launches)
+                                   float* d_rf, unsigned long long* d_steps, cudaStream_t stream, int* launches)
 {
-    if (!d_columns) return cudaErrorInvalidValue;
-    const int n_paths = n_poses * aq.elements * aq.samples;
-    const int block = 128;
-    // the tree's segments are not monotone in time: the column kernel (read-modify-write of the thread's own column on revisits)
+    // (no spacing restriction here: time is monotone inside ONE segment whatever the spacing; the single-path kernel needs it across
+    // the consecutive segments of a path)
+    const int n_scanlines = n_poses * aq.elements;
+    cudaError_t e = cudaMemsetAsync(d_rf, 0, sizeof(float) * (size_t)n_scanlines * aq.rf_pitch, stream);
+    if (e != cudaSuccess) return e;
+    const size_t smem = sizeof(float) * MCRT_WIN_RING * (size_t)win_stride(32) * 4;
+    const int grid = (n_scanlines + 3) / 4;                       // a warp per scanline
     if (aq.voxel_fma_division)
-        k_accumulate<true><<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, tb.segments, tb.path_count, n_paths, d_columns, d_steps,
-                                                                               tb.slots_sorted, tb.path_first);
+        k_accumulate_win<true, true, 32, true><<<grid, 128, smem, stream>>>(sc, aq, d_volume, tb.segments, nullptr, n_scanlines, 1, d_rf, d_steps, d_steps + 1,
+                                                                            tb.level_first, tb.level_end, aq.max_depth, tb.n_scanlines);
     else
-        k_accumulate<false><<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, tb.segments, tb.path_count, n_paths, d_columns, d_steps,
-                                                                                tb.slots_sorted, tb.path_first);
-    const int64_t n_pixels = (int64_t)n_poses * aq.elements * aq.rows;
-    k_reduce_samples<<<grid1d(n_pixels, 256), 256, 0, stream>>>(d_columns, n_pixels, aq.samples, d_rf, aq.rows, aq.rf_pitch);
-    if (launches) (*launches) += 2;
+        k_accumulate_win<false, true, 32, true><<<grid, 128, smem, stream>>>(sc, aq, d_volume, tb.segments, nullptr, n_scanlines, 1, d_rf, d_steps, d_steps + 1,
+                                                                             tb.level_first, tb.level_end, aq.max_depth, tb.n_scanlines);
+    if (launches) (*launches) += 1;
     return cudaGetLastError();
 }
 

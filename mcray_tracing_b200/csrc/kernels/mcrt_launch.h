@@ -78,9 +78,13 @@ struct TraceBuffers {
 };
 
 // ---- ray-tree mode: BOTH children of every boundary hit are followed, as in the cited paper, instead
-// of the one Monte-Carlo branch this fork of the reference keeps (ray.cpp:84-94).  The wavefront grows: rays live in two
-// ping-pong pools, children and segments are appended with warp-aggregated atomics, every segment carries the key
-// (path << 20 | node) with node = 1 for the root, 2n for the reflected and 2n + 1 for the refracted child of node n.
+// of the one Monte-Carlo branch this fork of the reference keeps (ray.cpp:84-94).  The wavefront grows level by level; node ids
+// are heap indices (root 1, reflected child 2n, refracted child 2n + 1) and key the Philox counter.
+// Everything stays ORDERED, so nothing is ever sorted: the rays of a level are processed in (path, node) order; every warp writes the
+// children of its 32 rays, in that order, into its own 64 slots of a sparse pool and k_compact_tree packs the slot indices into the
+// next level's dense queue (the scheme of k_bounce / k_compact).  A level's segments are stored at [seg_base(level) + queue index],
+// so the segments of a scanline at one level are contiguous; level_first / level_end give that range per (level, scanline) and the
+// accumulate kernel walks a scanline's segments level by level = in (level, path, node) order.
 struct TreeRay {                   // 48 B
     float4 origin_intensity;
     float4 dir_state;              // direction + packed (medium, outside medium, depth)
@@ -88,29 +92,28 @@ struct TreeRay {                   // 48 B
     int path, node;
 };
 struct TreeBuffers {
-    TreeRay* rays_a;               // [ray_capacity]
+    TreeRay* rays_a;               // sparse pools, [2 * ray_capacity + 64]: 64 slots per warp chunk of the level that wrote them
     TreeRay* rays_b;
-    DevSegment* segments;          // [seg_capacity], in append order
-    unsigned long long* keys;      // [seg_capacity]
-    unsigned long long* keys_sorted;
-    unsigned* slots;               // [seg_capacity]: 0, 1, 2, ... (sort values)
-    unsigned* slots_sorted;        // segment slots ordered by (path, node)
-    int* path_first;               // [n_paths]: first entry of the path in slots_sorted
-    int* path_count;               // [n_paths]
+    int* queue_a;                  // dense queues, [ray_capacity]: pool slots of the rays entering a level, in (path, node) order
+    int* queue_b;
+    int* warp_counts;              // [ray_capacity / 32 + 1]: children written by warp chunk w of the current level
+    int* tile_counts;              // [max_depth][n_tiles]: children per tile of 256 warp chunks
+    int n_tiles;
+    DevSegment* segments;          // [seg_capacity]: level 0 first, then level 1, ...; queue order inside a level
+    unsigned long long* keys;      // [seg_capacity]: (path << 20 | node) of the segment in the same slot (mcrt_trace_tree_debug)
+    int* level_first;              // [max_depth][n_scanlines]: first segment slot of the scanline at that level
+    int* level_end;                // [max_depth][n_scanlines]: one past its last slot (0: the scanline has no ray at that level)
     int* counters;                 // [max_depth + 3]: rays entering level l; [max_depth + 1] segments; [max_depth + 2] overflow flag
     unsigned long long* trav_counters;
-    void* sort_tmp;
-    size_t sort_tmp_bytes;
-    int ray_capacity, seg_capacity;
+    int ray_capacity, seg_capacity, n_scanlines;
 };
-size_t tree_sort_tmp_bytes(int seg_capacity);
-// traces the trees of all paths of the uploaded poses, sorts the segments by (path, node) and fills path_first / path_count
+// traces the trees of all paths of the uploaded poses; fills segments / keys / level_first / level_end / counters
 void launch_trace_tree(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, const TreeBuffers& tb, int sm_count, cudaStream_t stream,
                        int* launches);
-// echo accumulation of tree segments: one thread per path marches its segments in (node) order into a private HBM column,
-// then the samples are summed in order (k_accumulate + k_reduce_samples with an indirection)
+// echo accumulation of tree segments: a warp per scanline, a lane per SEGMENT (a segment is self-contained: start point, start
+// time, initial intensity), rounds of 32 segments through the windowed shared-memory ring of k_accumulate_win; no columns in HBM
 cudaError_t launch_accumulate_tree(const SceneDev& sc, const AcqDev& aq, const float2* d_volume, const TreeBuffers& tb, int n_poses,
-                                   float* d_rf, unsigned long long* d_steps, float* d_columns, cudaStream_t stream, int* launches);
+                                   float* d_rf, unsigned long long* d_steps, cudaStream_t stream, int* launches);
 
 // generate + max_depth x (intersect, shade, compact): scene::cast_rays (scene.cpp:50-183)
 void launch_trace(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, const TraceBuffers& tb, int sm_count, cudaStream_t stream,

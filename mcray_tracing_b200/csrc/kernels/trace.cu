@@ -440,8 +440,10 @@ __global__ void __launch_bounds__(256) k_compact(const int* __restrict__ sparse,
 #define MCRT_CH_MIN_CTAS 1
 #endif
 // ------------------------------------------------------------------------------------------------
-// Ray-tree mode: one launch per tree level.  Each ray emits one segment (appended to the segment pool) and up to two child
-// rays (appended to the next level's pool); both appends are warp-aggregated (one atomicAdd per warp and pool).
+// Ray-tree mode: one launch per tree level, everything ORDERED (see TreeBuffers): ray idx of the level's dense queue emits segment
+// seg_base + idx; the children of a warp's 32 rays go, in ray order and reflected before refracted, into the warp's own 64 slots of
+// the sparse output pool; k_compact_tree packs the slot indices into the next level's queue.  No atomics on the data path besides
+// one add per warp into its tile's child count, no sort.
 // ------------------------------------------------------------------------------------------------
 template <bool FIRST>
 __global__ void __launch_bounds__(128, 5) k_tree_level(const SceneDev sc, const AcqDev aq, const FrameDev fr, const TreeBuffers tb, const int level)
@@ -450,20 +452,32 @@ __global__ void __launch_bounds__(128, 5) k_tree_level(const SceneDev sc, const 
     load_shared_scene(sc, sh);
     const TreeRay* __restrict__ rin = (level & 1) ? tb.rays_b : tb.rays_a;
     TreeRay* __restrict__ rout = (level & 1) ? tb.rays_a : tb.rays_b;
+    const int* __restrict__ qin = (level & 1) ? tb.queue_b : tb.queue_a;
     const int ES = aq.elements * aq.samples;
-    int n_in = FIRST ? fr.n_poses * ES : tb.counters[level];
-    if (n_in > tb.ray_capacity) n_in = tb.ray_capacity;
+    const int n_paths = fr.n_poses * ES;
+    // rays entering this level and the first segment slot of the level
+    int n_in = FIRST ? n_paths : tb.counters[level];
+    bool overflow = false;
+    if (n_in > tb.ray_capacity) { n_in = tb.ray_capacity; overflow = true; }
+    int seg_base = 0;
+    for (int l = 0; l < level; l++) { const int c = l == 0 ? n_paths : tb.counters[l]; seg_base += c < tb.ray_capacity ? c : tb.ray_capacity; }
+    if (seg_base + n_in > tb.seg_capacity) { n_in = tb.seg_capacity - seg_base > 0 ? tb.seg_capacity - seg_base : 0; overflow = true; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        tb.counters[aq.max_depth + 1] = seg_base + n_in;
+        if (overflow) tb.counters[aq.max_depth + 2] = 1;
+    }
     const int n_round = (n_in + 31) & ~31;
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const uint64_t seed = __ldg(&fr.seed_frame[0]);
+    int* __restrict__ lvl_first = tb.level_first + (size_t)level * tb.n_scanlines;
+    int* __restrict__ lvl_end = tb.level_end + (size_t)level * tb.n_scanlines;
     int node_visits = 0, tri_tests = 0;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += gridDim.x * blockDim.x) {
         const bool valid = idx < n_in;
-        DevSegment seg;
-        unsigned long long key = 0ULL;
         bool c_refl = false, c_refr = false;
         TreeRay kid_refl, kid_refr;
+        int scanline = -2;
         if (valid) {
             int path, node, media, outside, depth;
             float3 from, dir;
@@ -477,7 +491,7 @@ __global__ void __launch_bounds__(128, 5) k_tree_level(const SceneDev sc, const 
                 distance_traveled = 0.0;
                 media = sc.starting_material; outside = MCRT_OUTSIDE_NULL;
             } else {
-                const TreeRay r = rin[idx];
+                const TreeRay r = rin[qin[idx]];
                 path = r.path; node = r.node;
                 from = make_float3(r.origin_intensity.x, r.origin_intensity.y, r.origin_intensity.z); intensity = r.origin_intensity.w;
                 dir = make_float3(r.dir_state.x, r.dir_state.y, r.dir_state.z);
@@ -488,6 +502,7 @@ __global__ void __launch_bounds__(128, 5) k_tree_level(const SceneDev sc, const 
             const int pose = path / ES;
             const int rem = path - pose * ES;
             const int element = rem / aq.samples, sample = rem - element * aq.samples;
+            scanline = pose * aq.elements + element;
             const uint32_t frame = (uint32_t)(__ldg(&fr.seed_frame[1]) + ((uint64_t)fr.frame_offset + (uint64_t)pose) * (uint64_t)fr.frame_stride);
             const DevMaterial med = sh.materials[media];
             const float r_length = rp_max_ray_length(med.attenuation, intensity, aq.frequency);
@@ -495,7 +510,7 @@ __global__ void __launch_bounds__(128, 5) k_tree_level(const SceneDev sc, const 
             const float3 from_test = v_add(from, v_scl(dir, 0.1f));
             HitRec h;
             closest_hit(sc, sh.mesh_origin, sh.perm(), sh.stack_column(), from_test, to, h, node_visits, tri_tests);
-            key = ((unsigned long long)(unsigned)path << 20) | (unsigned long long)(unsigned)node;
+            DevSegment seg;
             if (h.tri_id >= 0) {
                 ShadeResult r;
                 // the Philox counter takes the node id where the single-path mode puts the bounce index
@@ -521,34 +536,29 @@ __global__ void __launch_bounds__(128, 5) k_tree_level(const SceneDev sc, const 
                 seg.s2 = make_float4(to.x, to.y, to.z, med.attenuation);
                 seg.s3 = make_int4(__double2loint(distance_traveled), __double2hiint(distance_traveled), media, -1);
             }
+            tb.segments[seg_base + idx] = seg;
+            tb.keys[seg_base + idx] = ((unsigned long long)(unsigned)path << 20) | (unsigned long long)(unsigned)node;
         }
-        // segment append
-        const unsigned ms = __ballot_sync(0xffffffffu, valid);
-        const unsigned m1 = __ballot_sync(0xffffffffu, c_refl), m2 = __ballot_sync(0xffffffffu, c_refr);
-        if (ms) {
-            const int leader = __ffs(ms) - 1;
-            int sbase = 0, rbase = 0;
-            if ((int)lane == leader) {
-                sbase = atomicAdd(&tb.counters[aq.max_depth + 1], __popc(ms));
-                if (m1 | m2) rbase = atomicAdd(&tb.counters[level + 1], __popc(m1) + __popc(m2));
-            }
-            sbase = __shfl_sync(0xffffffffu, sbase, leader);
-            rbase = __shfl_sync(0xffffffffu, rbase, leader);
-            bool overflow = false;
+        // the scanline's segment range at this level: rays are in (path, node) order, so a scanline's rays are consecutive
+        {
+            int prev = __shfl_up_sync(0xffffffffu, scanline, 1), next = __shfl_down_sync(0xffffffffu, scanline, 1);
             if (valid) {
-                const int slot = sbase + __popc(ms & lt);
-                if (slot < tb.seg_capacity) { tb.segments[slot] = seg; tb.keys[slot] = key; tb.slots[slot] = (unsigned)slot; }
-                else overflow = true;
+                if (lane == 0) prev = idx == 0 ? -1 : (FIRST ? (idx - 1) / aq.samples : rin[qin[idx - 1]].path / aq.samples);
+                if (lane == 31) next = idx + 1 >= n_in ? -1 : (FIRST ? (idx + 1) / aq.samples : rin[qin[idx + 1]].path / aq.samples);
+                if (prev != scanline) lvl_first[scanline] = seg_base + idx;
+                if (next != scanline) lvl_end[scanline] = seg_base + idx + 1;
             }
-            if (c_refl) {
-                const int pos = rbase + __popc(m1 & lt);
-                if (pos < tb.ray_capacity) rout[pos] = kid_refl; else overflow = true;
-            }
-            if (c_refr) {
-                const int pos = rbase + __popc(m1) + __popc(m2 & lt);
-                if (pos < tb.ray_capacity) rout[pos] = kid_refr; else overflow = true;
-            }
-            if (overflow) tb.counters[aq.max_depth + 2] = 1;
+        }
+        // children -> this warp chunk's 64 slots of the sparse pool, in ray order, reflected before refracted
+        const unsigned m1 = __ballot_sync(0xffffffffu, c_refl), m2 = __ballot_sync(0xffffffffu, c_refr);
+        const int chunk = idx >> 5;
+        const int before = __popc(m1 & lt) + __popc(m2 & lt);
+        if (c_refl) rout[(size_t)chunk * 64 + before] = kid_refl;
+        if (c_refr) rout[(size_t)chunk * 64 + before + (c_refl ? 1 : 0)] = kid_refr;
+        if (lane == 0) {
+            const int n = __popc(m1) + __popc(m2);
+            tb.warp_counts[chunk] = n;
+            if (n) atomicAdd(&tb.tile_counts[(size_t)level * tb.n_tiles + (chunk >> 8)], n);
         }
     }
     if (tb.trav_counters) {
@@ -563,23 +573,42 @@ __global__ void __launch_bounds__(128, 5) k_tree_level(const SceneDev sc, const 
     }
 }
 
-// after the (path, node) sort: first entry and number of entries of every path
-__global__ void __launch_bounds__(256) k_tree_path_ranges(const unsigned long long* __restrict__ keys_sorted, const int* __restrict__ counters,
-                                                         const int seg_counter_index, const int seg_capacity, int* __restrict__ path_first,
-                                                         int* __restrict__ path_count)
+// sparse pool of level `level` (64 slots per warp chunk, warp_counts[chunk] of them used) -> dense queue of level + 1 (the slot
+// indices, in order).  One CTA per tile of 256 warp chunks; the tile's base is the sum of the tile counts before it (k_compact).
+__global__ void __launch_bounds__(256) k_compact_tree(int* __restrict__ dense, const int* __restrict__ warp_counts, const int* __restrict__ tile_counts,
+                                                     int* __restrict__ counters, const int level, const int n_paths_first, const int ray_capacity)
 {
-    int n = counters[seg_counter_index];
-    if (n > seg_capacity) n = seg_capacity;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int path = (int)(keys_sorted[i] >> 20);
-        if (i == 0 || (int)(keys_sorted[i - 1] >> 20) != path) path_first[path] = i;
-        if (i == n - 1 || (int)(keys_sorted[i + 1] >> 20) != path) path_count[path] = i + 1;      // end; turned into a count below
+    __shared__ int s_red[8];
+    __shared__ int s_scan[8];
+    int n_in = level == 0 ? n_paths_first : counters[level];
+    if (n_in > ray_capacity) n_in = ray_capacity;
+    const int n_chunks = (n_in + 31) >> 5;
+    const int tile = blockIdx.x;
+    if (tile * 256 >= n_chunks) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int part = 0;
+    for (int i = threadIdx.x; i < tile; i += 256) part += __ldg(&tile_counts[i]);
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if (lane == 0) s_red[warp] = part;
+    const int chunk = tile * 256 + threadIdx.x;
+    const int cnt = chunk < n_chunks ? __ldg(&warp_counts[chunk]) : 0;
+    int incl = cnt;
+    for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += y; }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    int base = 0, before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { base += s_red[w]; const int t = s_scan[w]; if (w < warp) before += t; total += t; }
+    const int excl = base + before + incl - cnt;
+#pragma unroll 4
+    for (int c = 0; c < 32; c++) {
+        const int n_c = __shfl_sync(0xffffffffu, cnt, c);
+        const int o_c = __shfl_sync(0xffffffffu, excl, c);
+        const int slot0 = (tile * 256 + warp * 32 + c) * 64;
+        if (lane < n_c && o_c + lane < ray_capacity) dense[o_c + lane] = slot0 + lane;
+        if (lane + 32 < n_c && o_c + lane + 32 < ray_capacity) dense[o_c + lane + 32] = slot0 + lane + 32;
     }
-}
-__global__ void __launch_bounds__(256) k_tree_path_counts(const int n_paths, const int* __restrict__ path_first, int* __restrict__ path_count)
-{
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < n_paths) path_count[p] = path_count[p] - path_first[p];
+    if (threadIdx.x == 0 && total) atomicAdd(&counters[level + 1], total);
 }
 
 __global__ void __launch_bounds__(128, MCRT_CH_MIN_CTAS) k_closest_hit(const SceneDev sc, const int64_t n, const float* __restrict__ from3,
@@ -706,21 +735,13 @@ void launch_trace(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, cons
     }
 }
 
-size_t tree_sort_tmp_bytes(int seg_capacity)
-{
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr,
-                                    seg_capacity, 0, 52, 0);
-    return bytes;
-}
-
 void launch_trace_tree(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, const TreeBuffers& tb, int sm_count, cudaStream_t stream,
                        int* launches)
 {
     const int64_t n_paths = (int64_t)fr.n_poses * aq.elements * aq.samples;
     cudaMemsetAsync(tb.counters, 0, sizeof(int) * (size_t)(aq.max_depth + 3), stream);
-    // unused key slots sort behind every real (path, node) key
-    cudaMemsetAsync(tb.keys, 0xff, sizeof(unsigned long long) * (size_t)tb.seg_capacity, stream);
+    cudaMemsetAsync(tb.tile_counts, 0, sizeof(int) * (size_t)aq.max_depth * tb.n_tiles, stream);
+    cudaMemsetAsync(tb.level_end, 0, sizeof(int) * (size_t)aq.max_depth * tb.n_scanlines, stream);
     const int block = 128;
     for (int l = 0; l < aq.max_depth; l++) {
         // level l holds at most min(2^l * n_paths, ray_capacity) rays
@@ -731,13 +752,13 @@ void launch_trace_tree(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr,
         if (l == 0) k_tree_level<true><<<grid, block, 0, stream>>>(sc, aq, fr, tb, l);
         else k_tree_level<false><<<grid, block, 0, stream>>>(sc, aq, fr, tb, l);
         if (launches) (*launches)++;
+        if (l + 1 < aq.max_depth) {
+            const int tiles = (int)(((bound + 31) / 32 + 255) / 256);
+            k_compact_tree<<<tiles, 256, 0, stream>>>((l & 1) ? tb.queue_a : tb.queue_b, tb.warp_counts, tb.tile_counts + (size_t)l * tb.n_tiles, tb.counters, l,
+                                                      (int)n_paths, tb.ray_capacity);
+            if (launches) (*launches)++;
+        }
     }
-    size_t bytes = tb.sort_tmp_bytes;
-    cub::DeviceRadixSort::SortPairs(tb.sort_tmp, bytes, tb.keys, tb.keys_sorted, tb.slots, tb.slots_sorted, tb.seg_capacity, 0, 52, stream);
-    k_tree_path_ranges<<<grid_for(tb.seg_capacity, 256, sm_count, 8), 256, 0, stream>>>(tb.keys_sorted, tb.counters, aq.max_depth + 1, tb.seg_capacity,
-                                                                                         tb.path_first, tb.path_count);
-    k_tree_path_counts<<<(int)((n_paths + 255) / 256), 256, 0, stream>>>((int)n_paths, tb.path_first, tb.path_count);
-    if (launches) (*launches) += 3;
 }
 
 size_t trace_sort_tmp_bytes(int64_t n_paths)

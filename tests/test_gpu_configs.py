@@ -430,9 +430,10 @@ def test_elevational_psf_and_ray_fans(api, O, assets_dirs):
 @pytest.mark.parametrize("scene_name,det", [("santi-liver-rough.scene", 0), ("santi-liver.scene", 1)])
 def test_ray_tree_mode_matches_oracle(api, O, assets_dirs, scene_name, det):
     """SURVEY 8(f) item 4 / the north star's ray *tree*: with option ray_tree both children of every boundary hit are
-    followed (level-by-level wavefront, warp-aggregated appends of child rays and segments).  All segments of a frame,
-    sorted by (path, node), are bit-identical to the oracle's tree; the RF frame (per-path accumulation in node order)
-    is within the 1e-4 tolerance; the tree contains the single-path segments' root and is strictly larger."""
+    followed (level-by-level wavefront kept in (path, node) order by warp-local compaction: no sort, no library kernel).  All
+    segments of a frame, by (path, node), are bit-identical to the oracle's tree; the RF frame (a lane per segment through the
+    windowed accumulate kernel, 32 segments per round in (level, path, node) order) is within the 1e-4 tolerance, identical
+    from run to run and independent of the batch size; the tree contains the single-path segments' root and is strictly larger."""
     path = assets_dirs["ircad11"] / scene_name
     A = O.load_scene_py(path)
     osc = O.OracleScene(A)
@@ -446,6 +447,9 @@ def test_ray_tree_mode_matches_oracle(api, O, assets_dirs, scene_name, det):
         gs, gpath, gnode = sim.cast_rays_tree(pose, seed=6, frame=2)
         rf = sim.simulate(np.repeat(pose[None, :], 2, axis=0), seed=6, first_frame=2)
         st = sim.stats()
+        rf_again = sim.simulate(np.repeat(pose[None, :], 5, axis=0), seed=6, first_frame=2)
+        assert np.array_equal(rf_again[0], rf[0]) and np.array_equal(rf_again[1], rf[1])      # deterministic, batch-independent
+        assert np.array_equal(rf_again[4], sim.simulate(pose[None, :], seed=6, first_frame=6)[0])
         sim.set_option("ray_tree", 2)                                  # far too small a budget: an error, not silent truncation
         with pytest.raises(api.McrtError):
             sim.simulate(pose[None, :], seed=6, first_frame=2)
