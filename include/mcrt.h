@@ -139,8 +139,7 @@ int mcrt_get_stats(const mcrt_ctx* ctx, mcrt_stats* stats);
 /* options: "profile_stages"=0/1 (per-stage events, disables the CUDA graph), "use_graph"=0/1,
  * "max_batch_poses"=N, "log_compress"=0/1 (apply the log compression the reference keeps commented out at
  * rfimage.h:131-136 to the envelope image: affects rf_out and scan_out; default 0), "overlap"=0/1 (two-stream software pipelining of pose sub-batches inside the graph; measured slower than one stream, default 0),
- * "count_traversal"=0/1 (BVH work counters in mcrt_stats), "coherence_sort"=0/1 (radix-sort the surviving paths by
- * origin Morton code + direction octant between bounces; pays on rough scenes, default 0), "bvh_builder"=0 device LBVH
+ * "count_traversal"=0/1 (BVH work counters in mcrt_stats), "bvh_builder"=0 device LBVH
  * (default) / 1 host binned-SAH tree (rebuilds the acceleration structure in place) */
 int mcrt_set_option(mcrt_ctx* ctx, const char* name, int64_t value);
 

@@ -155,7 +155,6 @@ struct mcrt_ctx {
     bool post_tma = true;                  // TMA-staged fused post kernel (option "post_tma"; 0 = round 1's k_post_fused, for A/B and equivalence tests)
     int first_hit_dedup = 1;               // bounce 0 traced once per element (TraceBuffers::first_hits) when samples >= 4: 0 off, 1 large calls, 2 always
     int ordered_compaction = 1;            // order-preserving compaction between bounces (TraceBuffers::warp_counts): 0 off, 1 large calls, 2 always
-    bool coherence_sort = false;           // radix-sort surviving paths between bounces (rough scenes)
     float* d_rf_acc = nullptr;
     float* d_rf_tmp0 = nullptr;
     float* d_rf_tmp1 = nullptr;
@@ -204,14 +203,11 @@ void free_workspace(mcrt_ctx* c)
     dev_free(c->tb.paths.origin_intensity); dev_free(c->tb.paths.dir_state); dev_free(c->tb.paths.distance);
     dev_free(c->tb.segments); dev_free(c->tb.n_segments); dev_free(c->tb.hit_fraction); dev_free(c->tb.hit_mesh);
     dev_free(c->tb.queue_a); dev_free(c->tb.queue_b); dev_free(c->tb.counters);
-    dev_free(c->tb.sort_keys); dev_free(c->tb.sort_keys_tmp); dev_free(c->tb.sort_queue_tmp);
     dev_free(c->tb.warp_counts); dev_free(c->tb.tile_counts); c->tb.n_tiles = 0; dev_free(c->tb.first_hits);
     dev_free(c->tree.rays_a); dev_free(c->tree.rays_b); dev_free(c->tree.queue_a); dev_free(c->tree.queue_b); dev_free(c->tree.warp_counts);
     dev_free(c->tree.tile_counts); dev_free(c->tree.segments); dev_free(c->tree.keys); dev_free(c->tree.level_first); dev_free(c->tree.level_end);
     dev_free(c->tree.counters);
     c->tree = TreeBuffers{};
-    if (c->tb.sort_tmp) cudaFree(c->tb.sort_tmp);
-    c->tb.sort_tmp = nullptr; c->tb.sort_tmp_bytes = 0;
     dev_free(c->d_poses); dev_free(c->d_rf_acc); dev_free(c->d_rf_tmp0); dev_free(c->d_rf_tmp1); dev_free(c->d_rf_final);
     dev_free(c->d_rf_t); dev_free(c->d_scan); dev_free(c->d_columns); dev_free(c->d_max_bits); dev_free(c->d_rf_elev);
     if (c->h_poses) cudaFreeHost(c->h_poses);
@@ -272,11 +268,6 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
         dev_alloc(c->tb.warp_counts, n_chunks + 1);
         dev_alloc(c->tb.tile_counts, (size_t)c->aq.max_depth * c->tb.n_tiles);
     }
-    if (c->coherence_sort) {
-        dev_alloc(c->tb.sort_keys, n_paths); dev_alloc(c->tb.sort_keys_tmp, n_paths); dev_alloc(c->tb.sort_queue_tmp, n_paths);
-        c->tb.sort_tmp_bytes = trace_sort_tmp_bytes((int64_t)n_paths);
-        CUDA_TRY(cudaMalloc(&c->tb.sort_tmp, c->tb.sort_tmp_bytes ? c->tb.sort_tmp_bytes : 16));
-    }
     c->cap_poses = n_poses;
 }
 
@@ -330,10 +321,9 @@ void enqueue_trace(mcrt_ctx* c, int pose0, int n, int slot, cudaStream_t s, int*
     if (tb.first_hits) tb.first_hits += 2 * (size_t)pose0 * c->aq.elements;
     // sub-batches keep the atomic compaction; small calls too (the 9 extra scan launches cost more than the order returns:
     // +1.6 % frames/s at 256 frames per call, profiles/r01o_ab_ordered.txt)
-    if (pose0 != 0 || slot != 0 || c->coherence_sort || (c->ordered_compaction == 1 && (int64_t)n * c->aq.elements * c->aq.samples < kOrderedMinPaths)) {
+    if (pose0 != 0 || slot != 0 || (c->ordered_compaction == 1 && (int64_t)n * c->aq.elements * c->aq.samples < kOrderedMinPaths)) {
         tb.warp_counts = nullptr; tb.tile_counts = nullptr; tb.n_tiles = 0;
     }
-    if (tb.sort_keys) { tb.sort_keys += p0; tb.sort_keys_tmp += p0; tb.sort_queue_tmp += p0; }
     tb.counters += (size_t)slot * (c->aq.max_depth + 1);
     launch_trace(c->sc, c->aq, fr, tb, c->sm_count, s, launches);
 }
@@ -986,7 +976,6 @@ static void rebuild_bvh(mcrt_ctx* c)
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
     c->graphs.clear();
-    const HostScene& hs = c->scene;
     LbvhResult nb{};
     make_bvh2(c, &nb);
     if (nb.max_depth > MCRT_TRAVERSAL_STACK) { cudaFree(nb.nodes); cudaFree(nb.tris); throw std::invalid_argument("BVH deeper than the traversal stack"); }
@@ -1117,12 +1106,6 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
         CUDA_TRY_NOTHROW(cudaStreamSynchronize(c->stream));
         free_workspace(c);
         c->ordered_compaction = value < 0 ? 0 : (value > 2 ? 2 : (int)value);
-    }
-    else if (n == "coherence_sort") {
-        // changes the workspace and the captured graphs: drop both, they are rebuilt on the next call
-        CUDA_TRY_NOTHROW(cudaStreamSynchronize(c->stream));
-        free_workspace(c);
-        c->coherence_sort = value != 0;
     }
     else if (n == "count_traversal") {
         // changes the kernel arguments baked into captured graphs: drop them

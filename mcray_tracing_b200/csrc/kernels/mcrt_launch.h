@@ -55,13 +55,6 @@ struct TraceBuffers {
     int* counters;                 // [max_depth + 1]: counters[b] = live paths entering bounce b; [max_depth] = bounce at which the tail merge started
     int tail_threshold;            // > 0: once at most this many paths are alive, one launch finishes them (no more compaction)
     unsigned long long* trav_counters;   // nullptr, or {BVH node visits, triangle tests} accumulated over the call
-    // optional coherence sort of the surviving paths between bounces (nullptr = off): Morton key of the next
-    // ray's origin + direction octant, radix-sorted so neighbouring lanes traverse neighbouring rays
-    unsigned* sort_keys;           // [n_paths]
-    unsigned* sort_keys_tmp;       // [n_paths]
-    int* sort_queue_tmp;           // [n_paths]
-    void* sort_tmp;                // cub temporary storage
-    size_t sort_tmp_bytes;
     // optional order-preserving compaction (nullptr = off): queue_a is the dense queue every bounce reads, queue_b the sparse
     // one it writes -- every warp compacts the survivors of its 32 paths into its own 32 slots and records how many (no CTA
     // barrier); k_compact then packs the sparse queue into the dense one.  Survivors stay sorted by (pose, element, sample),
@@ -118,7 +111,6 @@ cudaError_t launch_accumulate_tree(const SceneDev& sc, const AcqDev& aq, const f
 // generate + max_depth x (intersect, shade, compact): scene::cast_rays (scene.cpp:50-183)
 void launch_trace(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, const TraceBuffers& tb, int sm_count, cudaStream_t stream,
                   int* launches);
-size_t trace_sort_tmp_bytes(int64_t n_paths);
 void launch_closest_hit(const SceneDev& sc, int64_t n, const float* d_from, const float* d_to, int32_t* d_tri, int32_t* d_mesh,
                         float* d_frac, float* d_point, float* d_normal, cudaStream_t stream);
 void launch_elements(const AcqDev& aq, const FrameDev& fr, float* d_pos, float* d_dir, cudaStream_t stream);

@@ -6,7 +6,6 @@
 // compaction + k_scan_chunks; bounce 0 is traced once per element by k_first_hit (all samples share the ray).
 // The ray-tree mode (k_tree_level) follows both children: the wavefront grows level by level, child rays and
 // segments are appended with warp-aggregated atomics and sorted by (path, node) afterwards.
-#include <cub/device/device_radix_sort.cuh>
 
 #include "mcrt_device.cuh"
 #include "mcrt_launch.h"
@@ -166,7 +165,7 @@ __device__ __forceinline__ void shade_hit(const SceneDev& sc, const AcqDev& aq, 
 // One bounce of one path.  Returns true if the path survives into the next bounce.
 template <bool FIRST>
 __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, const TraceBuffers& tb,
-                                            SharedScene& sh, int p, int bounce, int& node_visits, int& tri_tests, unsigned& sort_key)
+                                            SharedScene& sh, int p, int bounce, int& node_visits, int& tri_tests)
 {
     const int ES = aq.elements * aq.samples;
     const int pose = p / ES;
@@ -239,17 +238,6 @@ __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq
         // scene.cpp:151-157
         alive = nint > MCRT_INTENSITY_EPSILON;
         if (alive && bounce + 1 < aq.max_depth) {
-            if (tb.sort_keys) {
-                // 27-bit Morton code of the next origin within the scene bounds + 3 bits of direction octant
-                const float3 hp = r.hit_point;
-                const float qx = fminf(fmaxf((hp.x - sc.bounds_lo[0]) * sc.bounds_inv[0], 0.0f), 1.0f);
-                const float qy = fminf(fmaxf((hp.y - sc.bounds_lo[1]) * sc.bounds_inv[1], 0.0f), 1.0f);
-                const float qz = fminf(fmaxf((hp.z - sc.bounds_lo[2]) * sc.bounds_inv[2], 0.0f), 1.0f);
-                auto spread = [](unsigned v) { v &= 0x1ffu; v = (v | (v << 16)) & 0x30000ffu; v = (v | (v << 8)) & 0x300f00fu; v = (v | (v << 4)) & 0x30c30c3u; v = (v | (v << 2)) & 0x9249249u; return v; };
-                const unsigned m = (spread((unsigned)(qx * 511.0f)) << 2) | (spread((unsigned)(qy * 511.0f)) << 1) | spread((unsigned)(qz * 511.0f));
-                const unsigned oct = (ndir.x < 0.0f ? 4u : 0u) | (ndir.y < 0.0f ? 2u : 0u) | (ndir.z < 0.0f ? 1u : 0u);
-                sort_key = (m << 3) | oct;
-            }
             tb.paths.origin_intensity[p] = make_float4(r.hit_point.x, r.hit_point.y, r.hit_point.z, nint);
             tb.paths.dir_state[p] = make_float4(ndir.x, ndir.y, ndir.z, __uint_as_float(pack_state(nmedia, noutside, bounce + 1)));
             tb.paths.distance[p] = r.distance_after;
@@ -300,10 +288,9 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const Scen
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += gridDim.x * blockDim.x) {
         int p = -1;
         bool alive = false;
-        unsigned sort_key = 0u;
         if (idx < n_in) {
             p = FIRST ? idx : qin[idx];
-            if (FIRST) alive = bounce_path<true>(sc, aq, fr, tb, sh, p, bounce, node_visits, tri_tests, sort_key);
+            if (FIRST) alive = bounce_path<true>(sc, aq, fr, tb, sh, p, bounce, node_visits, tri_tests);
             else alive = true;                                     // traced by the loop below (ONE inlined copy of bounce_path<false>)
         }
         if (!FIRST || tail) {
@@ -316,7 +303,7 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const Scen
                     if (!ma) break;
                     if ((int)lane == __ffs(ma) - 1) atomicAdd(&tb.counters[b], __popc(ma));
                 }
-                if (alive) alive = bounce_path<false>(sc, aq, fr, tb, sh, p, b, node_visits, tri_tests, sort_key);
+                if (alive) alive = bounce_path<false>(sc, aq, fr, tb, sh, p, b, node_visits, tri_tests);
                 if (!tail) break;
             }
             if (tail) continue;                                     // `tail` is uniform over the launch: no barrier is skipped by part of a CTA
@@ -341,7 +328,6 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const Scen
             if (alive) {
                 const int pos = base + __popc(m & ((1u << lane) - 1u));
                 qout[pos] = p;
-                if (tb.sort_keys) tb.sort_keys[pos] = sort_key;
             }
         }
     }
@@ -710,9 +696,6 @@ void launch_trace(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, cons
         if (launches) (*launches)++;
     }
     for (int b = 0; b < aq.max_depth; b++) {
-        const bool sort = tb.sort_keys && !tb.warp_counts && b + 1 < aq.max_depth;
-        // unused queue slots get the largest key so they sort behind the survivors
-        if (sort) cudaMemsetAsync(tb.sort_keys, 0xff, sizeof(unsigned) * (size_t)n_paths, stream);
         const bool ordered = tb.warp_counts != nullptr;
         if (ordered) {
             if (b == 0) k_bounce<true, true><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
@@ -725,13 +708,6 @@ void launch_trace(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, cons
         } else if (b == 0) k_bounce<true, false><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
         else k_bounce<false, false><<<grid, block, 0, stream>>>(sc, aq, fr, tb, b);
         if (launches) (*launches)++;
-        if (sort) {
-            int* qout = (b & 1) ? tb.queue_a : tb.queue_b;
-            size_t bytes = tb.sort_tmp_bytes;
-            cub::DeviceRadixSort::SortPairs(tb.sort_tmp, bytes, tb.sort_keys, tb.sort_keys_tmp, qout, tb.sort_queue_tmp, (int)n_paths, 0, 30, stream);
-            cudaMemcpyAsync(qout, tb.sort_queue_tmp, sizeof(int) * (size_t)n_paths, cudaMemcpyDeviceToDevice, stream);
-            if (launches) (*launches) += 3;
-        }
     }
 }
 
@@ -759,13 +735,6 @@ void launch_trace_tree(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr,
             if (launches) (*launches)++;
         }
     }
-}
-
-size_t trace_sort_tmp_bytes(int64_t n_paths)
-{
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, (int)n_paths, 0, 30, 0);
-    return bytes;
 }
 
 void launch_closest_hit(const SceneDev& sc, int64_t n, const float* d_from, const float* d_to, int32_t* d_tri, int32_t* d_mesh,
