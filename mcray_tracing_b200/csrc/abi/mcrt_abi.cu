@@ -155,6 +155,7 @@ struct mcrt_ctx {
     bool post_tma = true;                  // TMA-staged fused post kernel (option "post_tma"; 0 = round 1's k_post_fused, for A/B and equivalence tests)
     int first_hit_dedup = 1;               // bounce 0 traced once per element (TraceBuffers::first_hits) when samples >= 4: 0 off, 1 large calls, 2 always
     int ordered_compaction = 1;            // order-preserving compaction between bounces (TraceBuffers::warp_counts): 0 off, 1 large calls, 2 always
+    bool group_histories = false;          // ... with the refracted survivors before the reflected ones (option "group_histories"; measured slower: profiles/r02ab_ab_group_histories.txt)
     float* d_rf_acc = nullptr;
     float* d_rf_tmp0 = nullptr;
     float* d_rf_tmp1 = nullptr;
@@ -266,7 +267,8 @@ void ensure_workspace(mcrt_ctx* c, int n_poses)
         const size_t n_chunks = (n_paths + 31) / 32;
         c->tb.n_tiles = (int)((n_chunks + 255) / 256);
         dev_alloc(c->tb.warp_counts, n_chunks + 1);
-        dev_alloc(c->tb.tile_counts, (size_t)c->aq.max_depth * c->tb.n_tiles);
+        dev_alloc(c->tb.tile_counts, 2 * (size_t)c->aq.max_depth * c->tb.n_tiles);
+        c->tb.group_histories = c->group_histories ? 1 : 0;
     }
     c->cap_poses = n_poses;
 }
@@ -1132,6 +1134,13 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear();
         c->post_tma = value != 0;
+    }
+    else if (n == "group_histories") {
+        // changes a kernel argument baked into captured graphs: drop them (the workspace keeps its size)
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear();
+        c->group_histories = value != 0;
+        c->tb.group_histories = c->group_histories ? 1 : 0;
     }
     else if (n == "long_ct") {
         // A/B switch (process-wide): compile-time-tap axial / lateral kernels + shared-memory envelope on the long-scanline path

@@ -62,8 +62,9 @@ struct TraceBuffers {
     // order.  (Round 1 compacted per 128-path CTA chunk behind two CTA barriers and looked paths up by binary search over a
     // chunk prefix: 15 % + 9 % of the bounce kernels' stall samples, profiles/r02a_k_bounce_hot_lines.txt.)
     int* warp_counts;              // [ceil(n_paths / 32)]: survivors of warp chunk w of the current bounce
-    int* tile_counts;              // [max_depth][n_tiles]: survivors per tile of 256 warp chunks (8192 paths)
+    int* tile_counts;              // [max_depth][2][n_tiles]: refracted / reflected survivors per tile of 256 warp chunks (8192 paths)
     int n_tiles;
+    int group_histories;           // 1: the dense queue holds all refracted survivors before all reflected ones (option "group_histories")
     // optional (nullptr = off): closest hit of bounce 0 per (pose, element).  All samples of an element leave the transducer
     // on the same ray (scene.cpp:84-100), so k_first_hit traces it once and bounce 0 only shades: 2 float4 per element =
     // (fraction, tri_id, mesh, dist_a), (n_raw.xyz, -)
