@@ -645,6 +645,109 @@ __device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __
 #endif
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-coherent ("packet") traversal with the node staged through shared memory -- the north star's literal design point, built as
+// a compile-time option (MCRT_PACKET: 0 off, 1 the bounce-0 kernel k_first_hit only, 2 every traversal) and measured against the
+// per-lane traversal above (profiles/r02ae_ab_packet.txt).  The warp walks ONE path through the tree with ONE stack (shared memory,
+// entries = node reference + mask of the lanes whose rays entered it); a visited node's 128 bytes are fetched once, by eight lanes,
+// into a per-warp shared-memory buffer, and every lane of the entry's mask tests its own ray (own direction signs, own closest hit
+// so far) against the four children from there.  The children any lane hit are visited in the entry order of the mask's first lane.
+// Leaves are tested by the lanes of their mask only.  Results are identical to the per-lane traversal (ties resolve by triangle id).
+// The cost is the UNION of the nodes the 32 rays need, so it pays only while the rays of a warp are neighbours.
+// ------------------------------------------------------------------------------------------------
+#ifndef MCRT_PACKET
+#define MCRT_PACKET 0
+#endif
+#define MCRT_PK_DEPTH 128
+struct PacketShared {
+    int2 stack[MCRT_TRACE_THREADS / 32][MCRT_PK_DEPTH];
+    float4 node[MCRT_TRACE_THREADS / 32][8];
+};
+
+// wm: the lanes that take part -- established by the caller with a __ballot_sync executed by the whole warp, so the named lanes converge
+// at the first __syncwarp(wm) even if the warp was split when it got here.
+__device__ __forceinline__ void closest_hit_packet(const SceneDev& sc, const float4* __restrict__ s_mesh, PacketShared& ps, const unsigned wm,
+                                                   float3 from_w, float3 to_w, HitRec& best, int& node_visits, int& tri_tests)
+{
+    best.fraction = 1.0f; best.tri_id = -1; best.mesh = -1; best.n_raw = make_float3(0.f, 0.f, 0.f); best.dist_a = 0.0f;
+    if (sc.n_tri <= 0) return;
+    if (sc.n_tri == 1) { tri_test(sc.tris, 0, s_mesh, from_w, to_w, best); tri_tests++; return; }
+    __syncwarp(wm);
+    const unsigned lane = threadIdx.x & 31u;
+    const int w = threadIdx.x >> 5;
+    const int n_act = __popc(wm), rank = __popc(wm & ((1u << lane) - 1u));
+    const RayBox rb = make_raybox(from_w, to_w, sc.max_abs);
+    const int inx = rb.px ? 0 : 3, ifx = rb.px ? 3 : 0;    // float4 index of lox / hix within the staged node
+    const int iny = rb.py ? 1 : 4, ify = rb.py ? 4 : 1;
+    const int inz = rb.pz ? 2 : 5, ifz = rb.pz ? 5 : 2;
+    int2* __restrict__ stack = ps.stack[w];
+    float4* __restrict__ nd = ps.node[w];
+    const float4* __restrict__ nodes = reinterpret_cast<const float4*>(sc.nodes4);
+    int sp = 0;
+    int cur = 0;
+    unsigned cur_mask = wm;
+    while (true) {
+        const bool mine = (cur_mask >> lane) & 1u;
+        if (cur >= 0) {
+            if (mine) node_visits++;
+            for (int i = rank; i < 8; i += n_act) nd[i] = __ldg(nodes + (size_t)cur * 8 + i);
+            __syncwarp(wm);
+            const float4 nx = nd[inx], fx = nd[ifx], ny = nd[iny], fy = nd[ify], nz = nd[inz], fz = nd[ifz];
+            const float4 chf = nd[6];
+            __syncwarp(wm);                                    // everybody has read the buffer before the next node overwrites it
+            const int c[4] = {__float_as_int(chf.x), __float_as_int(chf.y), __float_as_int(chf.z), __float_as_int(chf.w)};
+            const float tb = best.fraction * 1.000002f;
+            float t[4];
+            {
+                const float n0[4] = {nx.x, nx.y, nx.z, nx.w}, n1[4] = {ny.x, ny.y, ny.z, ny.w}, n2[4] = {nz.x, nz.y, nz.z, nz.w};
+                const float f0[4] = {fx.x, fx.y, fx.z, fx.w}, f1[4] = {fy.x, fy.y, fy.z, fy.w}, f2[4] = {fz.x, fz.y, fz.z, fz.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float t0x = __fmaf_rn(n0[k], rb.ix, rb.cnx), t1x = __fmaf_rn(f0[k], rb.ix, rb.cfx);
+                    const float t0y = __fmaf_rn(n1[k], rb.iy, rb.cny), t1y = __fmaf_rn(f1[k], rb.iy, rb.cfy);
+                    const float t0z = __fmaf_rn(n2[k], rb.iz, rb.cnz), t1z = __fmaf_rn(f2[k], rb.iz, rb.cfz);
+                    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+                    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tb));
+                    t[k] = (mine && tn <= __fmaf_rn(tf, 1.000002f, 1e-37f)) ? tn : 3.0e38f;
+                }
+            }
+            unsigned m[4];
+            float tl[4];
+            const int leader = __ffs(cur_mask) - 1;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                m[k] = __ballot_sync(wm, t[k] < 3.0e38f);
+                tl[k] = __shfl_sync(wm, t[k], leader);
+                if (m[k] == 0u) tl[k] = 3.0e38f;                 // nobody enters: sorts last
+                else if (!(tl[k] < 3.0e38f)) tl[k] = 2.9e38f;    // entered by others only: behind the leader's own children
+            }
+            int cc[4] = {c[0], c[1], c[2], c[3]};
+#define MCRT_PSWAP(i, j) { const bool sw = tl[j] < tl[i]; const float tt = sw ? tl[j] : tl[i]; tl[j] = sw ? tl[i] : tl[j]; tl[i] = tt; \
+                           const int q = sw ? cc[j] : cc[i]; cc[j] = sw ? cc[i] : cc[j]; cc[i] = q; \
+                           const unsigned u = sw ? m[j] : m[i]; m[j] = sw ? m[i] : m[j]; m[i] = u; }
+            MCRT_PSWAP(0, 1) MCRT_PSWAP(2, 3) MCRT_PSWAP(0, 2) MCRT_PSWAP(1, 3) MCRT_PSWAP(1, 2)
+#undef MCRT_PSWAP
+            if (m[0]) {
+                if (m[3]) { stack[sp] = make_int2(cc[3], (int)m[3]); sp++; }
+                if (m[2]) { stack[sp] = make_int2(cc[2], (int)m[2]); sp++; }
+                if (m[1]) { stack[sp] = make_int2(cc[1], (int)m[1]); sp++; }
+                cur = cc[0]; cur_mask = m[0];
+                continue;
+            }
+        } else if (mine) {
+            const int code = -cur - 1;
+            const int first = code >> 2, count = (code & 3) + 1;
+            tri_tests += count;
+            for (int k = 0; k < count; k++) tri_test(sc.tris, first + k, s_mesh, from_w, to_w, best);
+        }
+        if (sp == 0) break;
+        --sp;
+        const int2 e = stack[sp];
+        cur = e.x; cur_mask = (unsigned)e.y;
+    }
+    __syncwarp(wm);
+}
+
 // final normal of the best hit: normalise, face the ray origin (btTriangleRaycastCallback)
 __device__ __forceinline__ float3 hit_normal(const HitRec& h)
 {

@@ -28,6 +28,9 @@ struct SharedScene {
 #if MCRT_SMEM_STACK > 0
     int stack[MCRT_SMEM_STACK * MCRT_TRACE_THREADS];   // [entry][thread]: the top of every thread's traversal stack
 #endif
+#if MCRT_PACKET
+    PacketShared pk;                                   // warp-coherent traversal: one stack and one staged node per warp
+#endif
     __device__ __forceinline__ int* stack_column()
     {
 #if MCRT_SMEM_STACK > 0
@@ -165,7 +168,8 @@ __device__ __forceinline__ void shade_hit(const SceneDev& sc, const AcqDev& aq, 
 // One bounce of one path.  Returns true if the path survives into the next bounce.
 template <bool FIRST>
 __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq, const FrameDev& fr, const TraceBuffers& tb,
-                                            SharedScene& sh, int p, int bounce, int& node_visits, int& tri_tests, bool& reflected)
+                                            SharedScene& sh, int p, int bounce, int& node_visits, int& tri_tests, bool& reflected,
+                                            const unsigned wm /* MCRT_PACKET: the lanes of the warp inside this call */)
 {
     const int ES = aq.elements * aq.samples;
     const int pose = p / ES;
@@ -208,7 +212,11 @@ __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq
         h.fraction = a.x; h.tri_id = __float_as_int(a.y); h.mesh = __float_as_int(a.z); h.dist_a = a.w;
         h.n_raw = make_float3(b.x, b.y, b.z);
     } else {
+#if MCRT_PACKET >= 2
+        closest_hit_packet(sc, sh.mesh_origin, sh.pk, wm, from_test, to, h, node_visits, tri_tests);
+#else
         closest_hit(sc, sh.mesh_origin, sh.perm(), sh.stack_column(), from_test, to, h, node_visits, tri_tests);
+#endif
     }
 
     DevSegment seg;
@@ -289,9 +297,14 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const Scen
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += gridDim.x * blockDim.x) {
         int p = -1;
         bool alive = false, reflected = false;
+#if MCRT_PACKET >= 2
+        unsigned wm = __ballot_sync(0xffffffffu, idx < n_in);
+#else
+        const unsigned wm = 0u;
+#endif
         if (idx < n_in) {
             p = FIRST ? idx : qin[idx];
-            if (FIRST) alive = bounce_path<true>(sc, aq, fr, tb, sh, p, bounce, node_visits, tri_tests, reflected);
+            if (FIRST) alive = bounce_path<true>(sc, aq, fr, tb, sh, p, bounce, node_visits, tri_tests, reflected, wm);
             else alive = true;                                     // traced by the loop below (ONE inlined copy of bounce_path<false>)
         }
         if (!FIRST || tail) {
@@ -303,8 +316,11 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_bounce(const Scen
                     const unsigned ma = __ballot_sync(0xffffffffu, alive);
                     if (!ma) break;
                     if ((int)lane == __ffs(ma) - 1) atomicAdd(&tb.counters[b], __popc(ma));
+#if MCRT_PACKET >= 2
+                    wm = ma;
+#endif
                 }
-                if (alive) { reflected = false; alive = bounce_path<false>(sc, aq, fr, tb, sh, p, b, node_visits, tri_tests, reflected); }
+                if (alive) { reflected = false; alive = bounce_path<false>(sc, aq, fr, tb, sh, p, b, node_visits, tri_tests, reflected, wm); }
                 if (!tail) break;
             }
             if (tail) continue;                                     // `tail` is uniform over the launch: no barrier is skipped by part of a CTA
@@ -361,7 +377,14 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_first_hit(const S
     load_shared_scene(sc, sh);
     const int n = fr.n_poses * aq.elements;
     int node_visits = 0, tri_tests = 0;
+#if MCRT_PACKET >= 1
+    // warp-uniform trip count: the whole warp establishes the mask of the lanes that trace
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31); i += gridDim.x * blockDim.x) {
+        const unsigned wm = __ballot_sync(0xffffffffu, i < n);
+        if (i >= n) continue;
+#else
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#endif
         const int pose = i / aq.elements, element = i - pose * aq.elements;
         float3 from, dir;
         element_pose(aq, fr.poses[pose], __ldg(&fr.elem_sincos[element]), from, dir);
@@ -371,7 +394,11 @@ __global__ void __launch_bounds__(128, MCRT_BOUNCE_MIN_CTAS) k_first_hit(const S
         const float3 to = v_add(from, v_scl(make_float3(sc.spacing[0] * dir.x, sc.spacing[1] * dir.y, sc.spacing[2] * dir.z), r_length / 100.0f));
         const float3 from_test = v_add(from, v_scl(dir, 0.1f));
         HitRec h;
+#if MCRT_PACKET >= 1
+        closest_hit_packet(sc, sh.mesh_origin, sh.pk, wm, from_test, to, h, node_visits, tri_tests);
+#else
         closest_hit(sc, sh.mesh_origin, sh.perm(), sh.stack_column(), from_test, to, h, node_visits, tri_tests);
+#endif
         tb.first_hits[2 * (size_t)i] = make_float4(h.fraction, __int_as_float(h.tri_id), __int_as_float(h.mesh), h.dist_a);
         tb.first_hits[2 * (size_t)i + 1] = make_float4(h.n_raw.x, h.n_raw.y, h.n_raw.z, 0.0f);
     }
