@@ -56,11 +56,11 @@ def workload(name: str, frames_per_step: int | None):
     if name == "c4":
         A = assets.stress_scene_arrays()
         pose = np.concatenate([A["transducer_position"], A["transducer_angles"]]).astype(np.float32)
-        return dict(scene=A, params=dict(elements=512, samples=16), F=frames_per_step or 64, sweep=False, pose=pose,
+        return dict(scene=A, params=dict(elements=512, samples=16), F=frames_per_step or 128, sweep=False, pose=pose,
                     label="synthetic 2 097 152-triangle nested-shell tissue mesh, shininess 2 / thickness 0.5 on every material (rough), "
                           "512 scanlines x 16 MC samples x 10 bounces (BASELINE configs[3])")
     if name == "c5":
-        return dict(scene=d["ircad11"] / "santi-liver.scene", F=frames_per_step or 8, sweep=False, pose=None,
+        return dict(scene=d["ircad11"] / "santi-liver.scene", F=frames_per_step or 32, sweep=False, pose=None,
                     params=dict(elements=1024, samples=16, axial_scale=17.6, psf_axial=63, psf_lateral=31),
                     label="ircad11 at 1024 scanlines x 8333 RF rows (axial_scale 17.6: 18 um rows; the reference's integer row formula "
                           "rfimage.h:180 has no setting that gives exactly 8192), 16 MC samples/element, 63 x 31-tap PSF (BASELINE configs[4])")
@@ -707,7 +707,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"], help="BASELINE.json configuration (default c2: the one the metric is quoted on)")
     ap.add_argument("--frames-per-step", type=int, default=None,
-                    help="independent frames per C-ABI call and per GPU (defaults: c2 1024, c3 512 / N, c4 64, c5 8; "
+                    help="independent frames per C-ABI call and per GPU (defaults: c2 1024, c3 512 / N, c4 128, c5 32; "
                          "measured on one B200: 256 -> 99k, 512 -> 107k, 1024 -> 112k frames/s)")
     ap.add_argument("--cpu-frames", type=int, default=60, help="frames per CPU-baseline variant (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
