@@ -239,7 +239,13 @@ int mcrt_set_psf_depth_profile(mcrt_ctx* ctx, float focus_cm, float spread, floa
 typedef struct mcrt_bmode_params {
     float gain_db;           /* overall gain */
     float tgc_db_per_cm;     /* time-gain compensation slope; depth_cm(row) = row * depth_cm / rows */
-    float dynamic_range_db;  /* Elevational PSF.  psf.h:16-18 describes three ranges -- axial, lateral and elevation -- and psf.h:42,77
+    float dynamic_range_db;  /* > 0, e.g. 60 */
+    float reserved0;
+} mcrt_bmode_params;
+int mcrt_bmode(mcrt_ctx* ctx, const float* env_in, int32_t n_images, const mcrt_bmode_params* bp, float* compressed_out,
+               uint8_t* bmode8_out);
+
+/* Elevational PSF.  psf.h:16-18 describes three ranges -- axial, lateral and elevation -- and psf.h:42,77
  * declares an elevation_kernel the reference never fills.  With n_planes > 1 (odd) every frame is traced as n_planes ray fans,
  * fan j offset by z_j = j * resolution - n_planes * resolution / 2 [mm] along the transducer's elevation axis (the normal of its
  * fan plane), Philox frame counter (frame * n_planes + j); the raw RF images of the fans are combined with the elevation taps
@@ -247,12 +253,6 @@ typedef struct mcrt_bmode_params {
  * taps_out / z_mm_out (nullable): n_planes floats each.  mcrt_elevation_pose: the pose of fan `plane` (test hook). */
 int mcrt_set_elevation(mcrt_ctx* ctx, int32_t n_planes, float var_z, float* taps_out, float* z_mm_out);
 int mcrt_elevation_pose(const mcrt_ctx* ctx, const mcrt_pose* pose, int32_t plane, mcrt_pose* out);
-
-/* > 0, e.g. 60 */
-    float reserved0;
-} mcrt_bmode_params;
-int mcrt_bmode(mcrt_ctx* ctx, const float* env_in, int32_t n_images, const mcrt_bmode_params* bp, float* compressed_out,
-               uint8_t* bmode8_out);
 int mcrt_get_psf_taps(const mcrt_ctx* ctx, float* axial, float* lateral);
 /* scene as loaded (for loader parity): local-frame vertices (v_obj*scaling) 9 floats/triangle in
  * objloader order, mesh id per triangle, body origin per mesh (scene.cpp:313-324) */

@@ -112,6 +112,8 @@ int main(int argc, char** argv)
     mcrt_params p;
     mcrt_default_params(&p);
     int frames = 1, device = 0, log_compress = 0, png = 0, bmode = 0, gpus = 1, batch = 64;
+    int elevation = 1, ray_tree = 0, psf_depth = 0;
+    float elevation_var = 0.0f, psf_focus = 0.0f, psf_spread = 0.0f;
     std::string poses_file;
     mcrt_bmode_params bp = {0.0f, 0.0f, 60.0f, 0.0f};
     unsigned long long seed = 0;
@@ -134,8 +136,19 @@ int main(int argc, char** argv)
         else if (a == "--bmode") { bmode = 1; bp.dynamic_range_db = (float)atof(next()); }
         else if (a == "--gain") bp.gain_db = (float)atof(next());
         else if (a == "--tgc") bp.tgc_db_per_cm = (float)atof(next());
+        else if (a == "--elevation") { elevation = atoi(next()); elevation_var = (float)atof(next()); }    // fans, variance [mm^2] (psf.h:16-18)
+        else if (a == "--psf-depth") { psf_depth = 1; psf_focus = (float)atof(next()); psf_spread = (float)atof(next()); }   // focus [cm], spread
+        else if (a == "--ray-tree") ray_tree = atoi(next());         // follow both children of every hit; segment budget per path
         else { printf("Incorrect argument list.\n"); return 0; }
     }
+    // the optional extensions of the display / physics chain; false: the library's message is in mcrt_last_error()
+    auto configure = [&](mcrt_ctx* c) -> bool {
+        if (log_compress && mcrt_set_option(c, "log_compress", 1) != MCRT_OK) return false;
+        if (ray_tree > 0 && mcrt_set_option(c, "ray_tree", ray_tree) != MCRT_OK) return false;
+        if (psf_depth && mcrt_set_psf_depth_profile(c, psf_focus, psf_spread, nullptr) != MCRT_OK) return false;
+        if (elevation > 1 && mcrt_set_elevation(c, elevation, elevation_var, nullptr, nullptr) != MCRT_OK) return false;
+        return true;
+    };
     if (!poses_file.empty()) {
         // ---- probe sweep sharded over the GPUs of this box (BASELINE config 3), C++ host: one context and one thread per GPU ----
         std::vector<mcrt_pose> poses;
@@ -152,12 +165,11 @@ int main(int argc, char** argv)
         if (poses.empty() || gpus < 1 || batch < 1) { printf("Incorrect argument list.\n"); return 0; }
         std::vector<mcrt_ctx*> ctxs(gpus, nullptr);
         for (int g = 0; g < gpus; g++) {                               // contexts are created one after the other
-            if (mcrt_create(argv[1], &p, device + g, &ctxs[g]) != MCRT_OK) {
+            if (mcrt_create(argv[1], &p, device + g, &ctxs[g]) != MCRT_OK || !configure(ctxs[g])) {
                 printf("The program found an error and will terminate.\nReason:\n%s\n", mcrt_last_error());
                 for (mcrt_ctx* c : ctxs) if (c) mcrt_destroy(c);
                 return 0;
             }
-            if (log_compress) mcrt_set_option(ctxs[g], "log_compress", 1);
             mcrt_set_option(ctxs[g], "max_batch_poses", batch);
         }
         mcrt_info info;
@@ -201,12 +213,12 @@ int main(int argc, char** argv)
         return 0;
     }
     mcrt_ctx* ctx = nullptr;
-    if (mcrt_create(argv[1], &p, device, &ctx) != MCRT_OK) {
+    if (mcrt_create(argv[1], &p, device, &ctx) != MCRT_OK || !configure(ctx)) {
         // main.cpp:154-159
         printf("The program found an error and will terminate.\nReason:\n%s\n", mcrt_last_error());
+        if (ctx) mcrt_destroy(ctx);
         return 0;
     }
-    if (log_compress) mcrt_set_option(ctx, "log_compress", 1);
     mcrt_info info;
     mcrt_get_info(ctx, &info);
     printf("%g us\n", info.max_travel_time_us);                      // main.cpp:76

@@ -1,6 +1,8 @@
 """GPU parity at the other BASELINE configurations (parity cases, not bench lines) and edge cases:
 config 4 (2 097 152-triangle nested tissue mesh, rough surfaces, 10 bounces), config 5 (long
 scanlines / large PSF), degenerate scenes (no mesh, one triangle, two triangles)."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -393,7 +395,7 @@ def test_moving_and_deforming_meshes_and_sah_cache(api, O, tmp_path, monkeypatch
     _segments_equal(segs, nseg, os_, on)
 
 
-def test_elevational_psf_and_ray_fans(api, O, assets_dirs):
+def test_elevational_psf_and_ray_fans(api, O, assets_dirs, tmp_path):
     """SURVEY 8(f) item 2, the elevation kernel the reference declares and never fills (psf.h:42,77): n_planes ray fans per
     frame offset along the elevation axis, combined with the elevation taps before the axial / lateral passes.  Taps and fan
     poses bit-equal to the oracle's restatement, frames within the RF tolerance, batching irrelevant, n_planes = 1 = off."""
@@ -421,10 +423,22 @@ def test_elevational_psf_and_ray_fans(api, O, assets_dirs):
             ref = O.simulate_frame_elevation(osc, op, poses[i][:3], poses[i][3:], seed=6, frame=4 + i, n_planes=5, var_z=0.1).T
             assert np.all(np.abs(rf[i] - ref) <= _tol(ref)), np.abs(rf[i] - ref).max()
         assert not np.array_equal(rf[0], plain[0])
+        # the same chain (+ the depth-dependent lateral PSF) from the headless CLI: --elevation N VAR, --psf-depth FOCUS SPREAD
+        sim.set_psf_depth_profile(4.0, 0.5)
+        rf_cli_ref = sim.simulate(pose[None, :], seed=6, first_frame=0)[0]
+        sim.set_psf_depth_profile(4.0, 0.0)
         sim.set_elevation(1)
         assert np.array_equal(sim.simulate(np.repeat(pose[None, :], 2, axis=0), seed=6, first_frame=4), plain)
         with pytest.raises(api.McrtError):
             sim.set_elevation(4)
+    import subprocess
+    exe = Path(api.__file__).resolve().parent / "mattausch"
+    out = subprocess.run([str(exe), str(path), "--elements", "64", "--samples", "3", "--seed", "6", "--elevation", "5", "0.1", "--psf-depth", "4", "0.5",
+                          "--out", str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "rf_image: 465, 64" in out.stdout, out.stdout + out.stderr
+    assert np.array_equal(np.fromfile(tmp_path / "rf_0000.f32", np.float32).reshape(64, 465), rf_cli_ref)
+    bad = subprocess.run([str(exe), str(path), "--elements", "64", "--elevation", "4", "0.1", "--out", str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert "The program found an error and will terminate." in bad.stdout and "elevation" in bad.stdout
 
 
 @pytest.mark.parametrize("scene_name,det", [("santi-liver-rough.scene", 0), ("santi-liver.scene", 1)])

@@ -125,6 +125,23 @@ def test_library_exports_every_declared_symbol(api):
     assert declared <= exported
 
 
+def test_header_is_plain_c_and_links(api, tmp_path):
+    """include/mcrt.h is a C header (the reference-side binding may be C): it compiles as strict C99, and a C program that takes the
+    address of every declared entry point links against libmcrt.so."""
+    header = (ROOT / "include" / "mcrt.h").read_text()
+    names = sorted(set(re.findall(r"\b(mcrt_[a-z_0-9]+)\s*\(", header)))
+    src = tmp_path / "use_all.c"
+    src.write_text('#include "mcrt.h"\n#include <stdio.h>\nint main(void) {\n    mcrt_params p; mcrt_bmode_params b; mcrt_pose q; mcrt_info i; mcrt_stats s;\n'
+                   '    (void)p; (void)b; (void)q; (void)i; (void)s;\n    const void* f[] = {' + ", ".join("(const void*)" + n for n in names) + '};\n'
+                   '    printf("%d\\n", (int)(sizeof(f) / sizeof(f[0])));\n    return 0;\n}\n')
+    exe = tmp_path / "use_all"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(src), "-o", str(exe),
+                        "-L", str(api.LIB_PATH.parent), "-lmcrt", "-Wl,-rpath," + str(api.LIB_PATH.parent)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and int(out.stdout) == len(names)
+
+
 def test_library_contains_sm100a_code_only(api):
     out = subprocess.run(["cuobjdump", "-lelf", str(api.LIB_PATH)], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))
