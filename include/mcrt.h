@@ -109,7 +109,7 @@ typedef struct mcrt_info {
     float start_pose[6];      /* the scene file's transducerPosition / transducerAngles */
     double axial_resolution_mm, time_step_us, row_period_us, max_travel_time_us;
     int32_t voxel_fma_division; /* 1: the 3-instruction voxel index passed its exhaustive check for this resolution and is in use */
-    int32_t bvh_cache_hit;      /* 1: the SAH tree (option bvh_builder=1) was loaded from $MCRT_BVH_CACHE instead of being built */
+    int32_t bvh_cache_hit;      /* 1: the acceleration structure (any builder) was loaded from $MCRT_BVH_CACHE instead of being built */
 } mcrt_info;
 
 typedef struct mcrt_stats {   /* of the most recent mcrt_simulate call */
@@ -136,11 +136,19 @@ const char* mcrt_last_error(void); /* thread-local, never NULL */
 
 int mcrt_get_info(const mcrt_ctx* ctx, mcrt_info* info);
 int mcrt_get_stats(const mcrt_ctx* ctx, mcrt_stats* stats);
-/* options: "profile_stages"=0/1 (per-stage events, disables the CUDA graph), "use_graph"=0/1,
- * "max_batch_poses"=N, "log_compress"=0/1 (apply the log compression the reference keeps commented out at
- * rfimage.h:131-136 to the envelope image: affects rf_out and scan_out; default 0), "overlap"=0/1 (two-stream software pipelining of pose sub-batches inside the graph; measured slower than one stream, default 0),
- * "count_traversal"=0/1 (BVH work counters in mcrt_stats), "bvh_builder"=0 device LBVH
- * (default) / 1 host binned-SAH tree (rebuilds the acceleration structure in place) */
+/* options (name = value; unknown names fail with MCRT_ERR_INVALID):
+ *   behaviour   "max_batch_poses"=N (poses per internal batch; sizes the workspace), "log_compress"=0/1 (apply the log compression the
+ *               reference keeps commented out at rfimage.h:131-136 to the envelope image: affects rf_out and scan_out; default 0),
+ *               "ray_tree"=B (> 0: follow BOTH children of every boundary hit with a budget of B segments per path, see
+ *               mcrt_trace_tree_debug; 0 = off), "frame_stride"=G (pose i of a call is frame first_frame + i * G of the Philox stream:
+ *               the round-robin pose deal of a G-rank sweep; default 1), "bvh_builder"=0 device LBVH (default) / 1 host binned-SAH
+ *               tree / 2 device PLOC (rebuilds the acceleration structure in place; every builder gives the same results)
+ *   diagnostics "profile_stages"=0/1 (per-stage events in mcrt_stats, disables the CUDA graph), "count_traversal"=0/1 (BVH work counters
+ *               in mcrt_stats), "use_graph"=0/1
+ *   A/B switches of measured design choices (results are bit-identical either way; DESIGN.md section 5, profiles/):
+ *               "tail_merge" (1), "first_hit_dedup" (1: large calls, 2: always, 0: off), "ordered_compaction" (1: large calls, 2: always,
+ *               0: warp-aggregated atomic appends), "group_histories" (0), "accumulate_windowed" (1), "voxel_fma_division" (1 when the
+ *               resolution passed its exhaustive check), "post_tma" (1), "long_ct" (1), "overlap" (0) */
 int mcrt_set_option(mcrt_ctx* ctx, const char* name, int64_t value);
 
 /* replaces one iteration of main.cpp:92-152 per pose: rf_image.clear(); scene.cast_rays();
