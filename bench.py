@@ -332,20 +332,33 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     def first_frame(k: int) -> int:
         return k * total + my_first
 
+    # round-robin deal on the collecting rank: its frames go STRAIGHT into their interleaved slots of the receive buffer (the post kernel
+    # writes them there: option rf_out_frame_stride), no local copy at all
+    direct_slot = peer is not None and interleave and rank == 0 and recvs is not None
+
     def compute(k: int, i: int):
         """simulate this rank's poses of step k into outs[i % 2] on stream st"""
         b = i % len(outs)
         if pending[b]:                                   # the gather that last read this buffer must be done
             st.wait_event(gather_done[b]); pending[b] = False
+        if direct_slot:
+            sim.set_option("rf_out_frame_stride", world)
+            sim.simulate_device(poses, recvs[b].data_ptr() + rank * cols * rows * 4, seed=seed, first_frame=first_frame(k), stream=st.cuda_stream, sync=False)
+            sim.set_option("rf_out_frame_stride", 1)
+            return
         sim.simulate_device(poses, outs[b].data_ptr(), seed=seed, first_frame=first_frame(k), stream=st.cuda_stream, sync=False)
 
     def gather(i: int, after: "torch.cuda.Event"):
         """bring the finished RF lines of outs[i % 2] to rank 0 on the comm stream, not before `after`"""
         b = i % len(outs)
         comm.wait_event(after)
-        if peer is not None:
-            peer.deposit(b, outs[b], comm, interleave=interleave)
-            peer.commit(comm)
+        if args.gather == "none":
+            gather_done[b].record(comm)
+        elif peer is not None:
+            if not os.environ.get("MCRT_DIAG_SKIP_DEPOSIT") and not direct_slot:   # (env: diagnostics of the gather's cost, profiles/r02ai_*)
+                peer.deposit(b, outs[b], comm, interleave=interleave)
+            if not os.environ.get("MCRT_DIAG_SKIP_COMMIT"):
+                peer.commit(comm)
             gather_done[b].record(comm)
         else:
             with torch.cuda.stream(comm):
@@ -412,7 +425,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # ---- N > 1: is the gathered result the 1-GPU result?  rank 0 re-simulates a sample of the last step's frames (every
     # rank's share) on its own GPU and compares them, bit for bit, with what landed in its receive buffer ---------------------
     multi_check = None
-    if world > 1 and rank == 0:
+    if world > 1 and rank == 0 and args.gather == "none":
+        multi_check = {"invalid_for_scaling": "diagnostic run without any exchange (--gather none)"}
+    elif world > 1 and rank == 0:
         k_last = 1000 + args.steps - 1
         got = recvs[(args.steps - 1) % 2]
         order_is_global = (peer is not None and interleave) or not interleave   # NCCL gather of a round-robin deal stays in rank-block order
@@ -555,6 +570,19 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             warm.append(sim.stats().ms_total)
         extra["latency_mode"]["ms_per_frame_device_warm_l2"] = float(np.median(warm))
         extra["latency_mode"]["frames_per_s_warm_l2"] = 1e3 / float(np.median(warm))
+        # the headline's neighbour (c2, one GPU): the same call size on the POSES OF THE PROBE SWEEP -- the workload every rank runs at
+        # --gpus N > 1 -- so that the N-GPU values have a like-for-like single-GPU figure beside them
+        if world == 1 and args.config == "c2":
+            sp = assets.sweep_poses(F)
+            sw = []
+            for k in range(2 + 5):
+                flush.fill_(0.0)
+                torch.cuda.synchronize(dev)
+                sim.simulate_device(sp, out.data_ptr(), seed=seed, first_frame=3000 + k * F)
+                if k >= 2:
+                    sw.append(sim.stats().ms_total)
+            extra["sweep_workload_1gpu"] = {"value": F / float(np.mean(sw)) * 1e3, "unit": UNIT, "ms_per_step": float(np.mean(sw)), "frames_per_step": F,
+                                            "poses": f"the first {F} poses of the ircad11 probe sweep (what each rank simulates at --gpus N > 1)"}
         # per-stage device times: separate pass, stage events between the kernels (no CUDA graph)
         sim.set_option("profile_stages", 1)
         tr, ac, po, tot, msteps = [], [], [], [], []
@@ -690,6 +718,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         }
         if multi_check is not None:
             line.update(multi_check)
+        if "sweep_workload_1gpu" in extra:                                      # beside the headline, not among the extras
+            items = list(line.items())
+            i = [k for k, _ in items].index("ms_per_step") + 1
+            line = dict(items[:i] + [("sweep_workload_1gpu", extra.pop("sweep_workload_1gpu"))] + items[i:])
         line.update(extra)
         print(json.dumps(line), flush=True)
     if peer is not None:
@@ -711,7 +743,9 @@ def main():
                          "measured on one B200: 256 -> 99k, 512 -> 107k, 1024 -> 112k frames/s)")
     ap.add_argument("--cpu-frames", type=int, default=60, help="frames per CPU-baseline variant (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N > 1: peer-memory deposit over NVLink (default) or NCCL send/recv gather")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "none"],
+                    help="N > 1: peer-memory deposit over NVLink (default), NCCL send/recv gather, or none (diagnostic: no exchange at all, "
+                         "the line is marked invalid_for_scaling)")
     ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE", help="development A/B: mcrt_set_option before the run (recorded in config.options)")
     ap.add_argument("--contiguous", action="store_true", help="N > 1: contiguous pose blocks per rank instead of the round-robin deal")
     args = ap.parse_args()

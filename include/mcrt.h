@@ -141,14 +141,17 @@ int mcrt_get_stats(const mcrt_ctx* ctx, mcrt_stats* stats);
  *               reference keeps commented out at rfimage.h:131-136 to the envelope image: affects rf_out and scan_out; default 0),
  *               "ray_tree"=B (> 0: follow BOTH children of every boundary hit with a budget of B segments per path, see
  *               mcrt_trace_tree_debug; 0 = off), "frame_stride"=G (pose i of a call is frame first_frame + i * G of the Philox stream:
- *               the round-robin pose deal of a G-rank sweep; default 1), "bvh_builder"=0 device LBVH (default) / 1 host binned-SAH
+ *               the round-robin pose deal of a G-rank sweep; default 1), "rf_out_frame_stride"=G (device rf_out only: frame i of a call
+ *               is written at rf_out + i * G frames -- the interleaved slots of that deal in a buffer in global pose order; default 1),
+ *               "bvh_builder"=0 device LBVH (default) / 1 host binned-SAH
  *               tree / 2 device PLOC (rebuilds the acceleration structure in place; every builder gives the same results)
  *   diagnostics "profile_stages"=0/1 (per-stage events in mcrt_stats, disables the CUDA graph), "count_traversal"=0/1 (BVH work counters
  *               in mcrt_stats), "use_graph"=0/1
  *   A/B switches of measured design choices (results are bit-identical either way; DESIGN.md section 5, profiles/):
  *               "tail_merge" (1), "first_hit_dedup" (1: large calls, 2: always, 0: off), "ordered_compaction" (1: large calls, 2: always,
  *               0: warp-aggregated atomic appends), "group_histories" (0), "accumulate_windowed" (1), "voxel_fma_division" (1 when the
- *               resolution passed its exhaustive check), "post_tma" (1), "long_ct" (1), "overlap" (0) */
+ *               resolution passed its exhaustive check), "post_tma" (1), "long_ct" (1), "overlap" (0), "direct_out" (1: with a device rf_out the
+ *               last kernel of the chain writes the frames straight into it; 0: internal image + device-to-device copy) */
 int mcrt_set_option(mcrt_ctx* ctx, const char* name, int64_t value);
 
 /* replaces one iteration of main.cpp:92-152 per pose: rf_image.clear(); scene.cast_rays();

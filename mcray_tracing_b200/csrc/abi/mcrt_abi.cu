@@ -152,6 +152,9 @@ struct mcrt_ctx {
     float* d_elev_w = nullptr;
     float* d_rf_elev = nullptr;            // raw RF images of the output frames after the elevational combine ([frames][E][rf_pitch])
     int frame_stride = 1;                  // frame index of pose i of a call = first_frame + i * frame_stride (option "frame_stride")
+    bool direct_out = true;                // option "direct_out": the post kernel writes the frames straight into the caller's device buffer
+    bool cur_direct = false;               // ... decided per call (simulate_impl)
+    int out_frame_stride = 1;              // option "rf_out_frame_stride": frame i of a call lands at rf_out + i * stride frames
     bool post_tma = true;                  // TMA-staged fused post kernel (option "post_tma"; 0 = round 1's k_post_fused, for A/B and equivalence tests)
     int first_hit_dedup = 1;               // bounce 0 traced once per element (TraceBuffers::first_hits) when samples >= 4: 0 off, 1 large calls, 2 always
     int ordered_compaction = 1;            // order-preserving compaction between bounces (TraceBuffers::warp_counts): 0 off, 1 large calls, 2 always
@@ -352,7 +355,7 @@ void enqueue_image(mcrt_ctx* c, int pose0, int n, bool want_scan, cudaStream_t s
     if (ev_after_accumulate) CUDA_TRY(cudaEventRecord(ev_after_accumulate, s));
     launch_post(raw, nf, c->aq.elements, c->aq.rows, c->d_axial, c->params.psf_axial, c->d_lateral, c->params.psf_lateral, 3,
                 c->d_rf_tmp0 + px0, c->d_rf_tmp1 + px0, c->d_rf_final + px0, s, launches, 0, 0, c->d_lat_by_row, c->aq.rf_pitch,
-                c->post_tma ? c->h_axial.data() : nullptr, c->h_lateral.data());
+                c->post_tma ? c->h_axial.data() : nullptr, c->h_lateral.data(), c->cur_direct ? c->d_seed_frame + 2 : nullptr);
     if (c->log_compress) launch_log_compress(c->d_rf_final + px0, nf, (int64_t)c->aq.elements * c->aq.rows, c->d_max_bits + f0, s, launches);
     if (c->params.rf_layout == 1) launch_transpose(c->d_rf_final + px0, nf, c->aq.elements, c->aq.rows, c->d_rf_t + px0, s, launches);
     if (want_scan)
@@ -409,7 +412,7 @@ void run_batch(mcrt_ctx* c, int n, bool want_scan, cudaStream_t s, int* launches
         enqueue_pipeline(c, n, want_scan, s, launches, c->profile_stages);
         return;
     }
-    const auto key = std::make_pair(n, want_scan ? 1 : 0);
+    const auto key = std::make_pair(n, (want_scan ? 1 : 0) | (c->cur_direct ? 2 : 0));
     const int nsub = pipeline_sub_batches(c, n);
     auto it = c->graphs.find(key);
     if (it == c->graphs.end()) {
@@ -487,6 +490,15 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
         const size_t px_per_pose = (size_t)c->aq.elements * c->aq.rows;
         const size_t scan_per_pose = (size_t)c->params.scan_rows * c->params.scan_cols;
         int launches = 0;
+        // frame i of the call lands at rf_out + i * ostride frames (option "rf_out_frame_stride": the interleaved slots of a round-robin sweep)
+        const int ostride = c->out_frame_stride;
+        if (ostride != 1 && !rf_dev) return fail(MCRT_ERR_INVALID, "mcrt_simulate: rf_out_frame_stride needs a device rf_out");
+        // the post kernel can write the frames straight into rf_out (no internal image + device-to-device copy) when the chain ends there
+        const int first_nf = n_poses < frames_per_batch ? n_poses : frames_per_batch;
+        c->cur_direct = c->direct_out && rf_dev && c->params.rf_layout == 0 && !c->log_compress && !scan_out && c->tree_budget == 0 &&
+                        pipeline_sub_batches(c, first_nf * N) == 1 &&
+                        post_writes_through_target(first_nf, c->aq.elements, c->aq.rows, c->aq.rf_pitch, c->params.psf_axial, c->params.psf_lateral, 3,
+                                                   c->post_tma ? c->h_axial.data() : nullptr, c->h_lateral.data(), c->d_lat_by_row != nullptr);
         begin_call(c, s);
         CUDA_TRY(cudaEventRecord(c->ev0, s));
         if (c->count_traversal) CUDA_TRY(cudaMemsetAsync(c->d_trav, 0, 2 * sizeof(unsigned long long), s));
@@ -505,8 +517,12 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
             c->h_seed_frame[0] = seed;
             // frame (Philox counter) of sub-frame (i, j) = (first_frame + i) * N + j
             c->h_seed_frame[1] = N == 1 ? first_frame + (uint64_t)p0 * (uint64_t)c->frame_stride : (first_frame + (uint64_t)p0) * (uint64_t)N;
+            // where the post kernel writes this batch's frames when it writes through the output target (cur_direct)
+            float* const rf_dst = rf_out + (size_t)p0 * px_per_pose * (size_t)ostride;
+            c->h_seed_frame[2] = (unsigned long long)reinterpret_cast<uintptr_t>(rf_dst);
+            c->h_seed_frame[3] = (unsigned long long)(px_per_pose * (size_t)ostride);
             CUDA_TRY(cudaMemcpyAsync(c->d_poses, c->h_poses, sizeof(PoseTrig) * (size_t)n, cudaMemcpyHostToDevice, s));
-            CUDA_TRY(cudaMemcpyAsync(c->d_seed_frame, c->h_seed_frame, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(c->d_seed_frame, c->h_seed_frame, 4 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
             CUDA_TRY(cudaEventRecord(c->ev_up, s));
             c->upload_pending = true;
             if (c->tree_budget > 0) {
@@ -515,9 +531,14 @@ int simulate_impl(mcrt_ctx* c, const mcrt_pose* poses, int32_t n_poses, uint64_t
             } else {
                 run_batch(c, n, scan_out != nullptr, s, &launches);
             }
-            const float* rf_src = c->params.rf_layout == 1 ? c->d_rf_t : c->d_rf_final;
-            CUDA_TRY(cudaMemcpyAsync(rf_out + (size_t)p0 * px_per_pose, rf_src, sizeof(float) * px_per_pose * nf,
-                                     rf_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+            if (!c->cur_direct) {
+                const float* rf_src = c->params.rf_layout == 1 ? c->d_rf_t : c->d_rf_final;
+                if (ostride == 1)
+                    CUDA_TRY(cudaMemcpyAsync(rf_dst, rf_src, sizeof(float) * px_per_pose * nf, rf_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+                else
+                    CUDA_TRY(cudaMemcpy2DAsync(rf_dst, sizeof(float) * px_per_pose * (size_t)ostride, rf_src, sizeof(float) * px_per_pose,
+                                               sizeof(float) * px_per_pose, (size_t)nf, rf_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+            }
             if (scan_out)
                 CUDA_TRY(cudaMemcpyAsync(scan_out + (size_t)p0 * scan_per_pose, c->d_scan, sizeof(float) * scan_per_pose * nf,
                                          scan_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
@@ -674,10 +695,10 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
         c->aq.voxel_fma_division = ok ? 1 : 0;
     }
 
-    dev_alloc(c->d_seed_frame, 2);
+    dev_alloc(c->d_seed_frame, 4);                      // seed, first frame | output target: base pointer, image stride (floats)
     dev_alloc(c->d_trav, 2);
     dev_alloc(c->d_steps, 2);
-    CUDA_TRY(cudaMallocHost(&c->h_seed_frame, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMallocHost(&c->h_seed_frame, 4 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMallocHost(&c->h_counters, sizeof(int) * kCounterSlot * kMaxBatchesPerCall));
     CUDA_TRY(cudaMallocHost(&c->h_steps, sizeof(unsigned long long) * 2 * kMaxBatchesPerCall));
     CUDA_TRY(cudaMallocHost(&c->h_trav, 2 * sizeof(unsigned long long)));
@@ -1134,6 +1155,11 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear();
         c->post_tma = value != 0;
+    }
+    else if (n == "direct_out") c->direct_out = value != 0;          // A/B switch; decided per call, part of the graph key
+    else if (n == "rf_out_frame_stride") {
+        if (value < 1 || value > 65536) return fail(MCRT_ERR_INVALID, "rf_out_frame_stride: 1 .. 65536 frames");
+        c->out_frame_stride = (int)value;
     }
     else if (n == "group_histories") {
         // changes a kernel argument baked into captured graphs: drop them (the workspace keeps its size)

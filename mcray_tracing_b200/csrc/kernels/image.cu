@@ -1355,8 +1355,14 @@ template <int KA, int KL, int NCH>
 __global__ void __launch_bounds__(MCRT_TMA_THREADS, 1) k_post_tma(const float* __restrict__ in, const int cols, const int rows, const int pitch,
                                                                  const __grid_constant__ PostTaps taps, const int TC, const int tiles_per_image,
                                                                  const int n_tiles, const int col_offset, const int cols_total,
-                                                                 float* __restrict__ out)
+                                                                 float* __restrict__ out, const unsigned long long* __restrict__ out_target)
 {
+    // out_target (nullable): {destination base pointer, image stride in floats} kept in device memory, so that a captured CUDA graph can
+    // write every call's frames STRAIGHT into the caller's buffer (and, with a stride, into the interleaved slots of a round-robin sweep)
+    // instead of an internal image that is copied afterwards
+    float* out_eff = out;
+    size_t img_stride = (size_t)cols * rows;
+    if (out_target) { out_eff = reinterpret_cast<float*>(__ldg(&out_target[0])); img_stride = (size_t)__ldg(&out_target[1]); }
     extern __shared__ __align__(128) float sm[];
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ float s_rcp[32 * MCRT_TMA_MAX_CHUNKS + 1];  // fl(1 / b), b = 1 .. rows
@@ -1395,7 +1401,7 @@ __global__ void __launch_bounds__(MCRT_TMA_THREADS, 1) k_post_tma(const float* _
         float* const s_ax = (n & 1) ? buf0 : buf1;         // axial pass
         const int img = t / tiles_per_image, c0 = (t - img * tiles_per_image) * TC;
         const int wl = cols - c0 < W ? cols - c0 : W;      // staged scanlines that exist
-        float* img_out = out + (size_t)img * cols * rows;
+        float* img_out = out_eff + (size_t)img * img_stride;
         {
             const unsigned bar = (n & 1) ? bar1 : bar0, parity = (unsigned)(n >> 1) & 1u;
             unsigned done = 0;
@@ -1759,17 +1765,34 @@ static size_t post_tma_smem(int pitch, int tc) { return sizeof(float) * 2 * (siz
 static bool g_long_ct = true;
 void set_long_scanline_ct(bool on) { g_long_ct = on; }
 
+// scanlines per tile of the TMA-staged kernel for this call, 0 when another kernel has to take it
+static int post_tma_tile_cols(int n_images, int cols, int rows, int in_pitch, int n_axial, int n_lateral, int flags, const float* h_axial,
+                              const float* h_lateral, bool by_row)
+{
+    if (by_row || !((int64_t)n_images * cols < 0x7fffffff) || !post_tma_usable(rows, in_pitch, n_axial, n_lateral, flags, h_axial, h_lateral)) return 0;
+    // widest tile of 8 / 16 / 32 scanlines that fits; few images (latency mode): narrower tiles so the grid still covers the SMs
+    int tc = 32;
+    while (tc > 8 && (post_tma_smem(in_pitch, tc) > MCRT_TMA_SMEM_LIMIT || (int64_t)((cols + tc - 1) / tc) * n_images < 148)) tc >>= 1;
+    return (post_tma_smem(in_pitch, tc) <= MCRT_TMA_SMEM_LIMIT && (in_pitch / 2) * (tc / MCRT_TMA_RUN) <= MCRT_TMA_THREADS) ? tc : 0;
+}
+
+bool post_writes_through_target(int n_images, int cols, int rows, int in_pitch, int n_axial, int n_lateral, int flags, const float* h_axial,
+                                const float* h_lateral, bool by_row)
+{
+    if (in_pitch <= 0) in_pitch = rows;
+    return post_tma_tile_cols(n_images, cols, rows, in_pitch, n_axial, n_lateral, flags, h_axial, h_lateral, by_row) > 0;
+}
+
 void launch_post(const float* d_in, int n_images, int cols, int rows, const float* d_axial, int n_axial, const float* d_lateral,
                  int n_lateral, int flags, float* d_tmp0, float* d_tmp1, float* d_out, cudaStream_t stream, int* launches, int col_offset,
-                 int cols_total, const float* d_lateral_by_row, int in_pitch, const float* h_axial, const float* h_lateral)
+                 int cols_total, const float* d_lateral_by_row, int in_pitch, const float* h_axial, const float* h_lateral,
+                 const unsigned long long* d_out_target)
 {
     if (cols_total <= 0) { col_offset = 0; cols_total = cols; }
     if (in_pitch <= 0) in_pitch = rows;
-    if (!d_lateral_by_row && (int64_t)n_images * cols < 0x7fffffff && post_tma_usable(rows, in_pitch, n_axial, n_lateral, flags, h_axial, h_lateral)) {
-        // widest tile of 8 / 16 / 32 scanlines that fits; few images (latency mode): narrower tiles so the grid still covers the SMs
-        int tc = 32;
-        while (tc > 8 && (post_tma_smem(in_pitch, tc) > MCRT_TMA_SMEM_LIMIT || (int64_t)((cols + tc - 1) / tc) * n_images < 148)) tc >>= 1;
-        if (post_tma_smem(in_pitch, tc) <= MCRT_TMA_SMEM_LIMIT && (in_pitch / 2) * (tc / MCRT_TMA_RUN) <= MCRT_TMA_THREADS) {
+    {
+        const int tc = post_tma_tile_cols(n_images, cols, rows, in_pitch, n_axial, n_lateral, flags, h_axial, h_lateral, d_lateral_by_row != nullptr);
+        if (tc > 0) {
             PostTaps taps;
             for (int k = 0; k < 8; k++) taps.a[k] = k < 7 ? h_axial[k] : 0.0f;
             for (int k = 0; k < 16; k++) taps.l[k] = k < 13 ? h_lateral[k] : 0.0f;
@@ -1780,10 +1803,10 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
             const int grid = (int)(n_tiles < sms ? n_tiles : sms);                 // persistent: one CTA per SM
             if (((rows + 31) >> 5) == 15)          // the reference's 465-row image (main.cpp:30, rfimage.h:180)
                 k_post_tma<7, 13, 15><<<grid, MCRT_TMA_THREADS, post_tma_smem(in_pitch, tc), stream>>>(d_in, cols, rows, in_pitch, taps, tc, tiles_per_image,
-                                                                                                     (int)n_tiles, col_offset, cols_total, d_out);
+                                                                                                     (int)n_tiles, col_offset, cols_total, d_out, d_out_target);
             else
                 k_post_tma<7, 13, 0><<<grid, MCRT_TMA_THREADS, post_tma_smem(in_pitch, tc), stream>>>(d_in, cols, rows, in_pitch, taps, tc, tiles_per_image,
-                                                                                                    (int)n_tiles, col_offset, cols_total, d_out);
+                                                                                                    (int)n_tiles, col_offset, cols_total, d_out, d_out_target);
             if (launches) (*launches)++;
             return;
         }

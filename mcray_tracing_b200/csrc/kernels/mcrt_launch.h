@@ -135,8 +135,13 @@ void launch_post(const float* d_in, int n_images, int cols, int rows, const floa
                  int col_offset = 0, int cols_total = 0,     // scanline-block runs: global index of scanline 0 / global scanline count
                  const float* d_lateral_by_row = nullptr,   // depth-dependent lateral PSF: [n_lateral][rows] taps (unfused kernels)
                  int in_pitch = 0,                          // row stride of d_in in floats (0 = rows); flags & 1 == 0 needs a dense input
-                 const float* h_axial = nullptr, const float* h_lateral = nullptr);   // host copies of the taps: enable the TMA-staged
+                 const float* h_axial = nullptr, const float* h_lateral = nullptr,    // host copies of the taps: enable the TMA-staged
                                                                                       // kernel (taps travel as kernel parameters)
+                 const unsigned long long* d_out_target = nullptr);  // device {base pointer, image stride in floats}: the result goes there instead
+                                                                     // of d_out -- ONLY honoured when post_writes_through_target() says so
+// true when launch_post would take the kernel that can write through a device-resident output target (the TMA-staged fused kernel)
+bool post_writes_through_target(int n_images, int cols, int rows, int in_pitch, int n_axial, int n_lateral, int flags, const float* h_axial,
+                                const float* h_lateral, bool by_row);
 // row pitch the raw RF image should have so that launch_post can stage it with TMA bulk copies (rows rounded up to 4 floats), or rows
 int post_preferred_pitch(int rows, int n_axial, int n_lateral);
 // exhaustive device check (all 2^32 float bit patterns) that the 3-instruction FMA division reproduces the voxel index of

@@ -353,6 +353,50 @@ def test_batched_poses_equal_single_pose_calls(api, ircad, O):
     assert len({all_rf[i].tobytes() for i in range(len(poses))}) == len(poses)
 
 
+def test_device_output_direct_and_strided(api, ircad):
+    """Device-buffer calls: the post kernel writes the frames straight into the caller's buffer (option direct_out, default on) --
+    same bits as the internal-image + copy path and as the host call, across batch splits, with and without the CUDA graph, with the
+    elevational PSF; option rf_out_frame_stride = G puts frame i at slot i * G (the interleaved slots of a round-robin sweep) and leaves
+    the slots in between untouched."""
+    import torch
+    from mcray_tracing_b200 import assets
+    path, A, osc = ircad
+    poses = assets.sweep_poses(11)
+    with api.Simulator(path, api.default_params(elements=128, samples=4)) as sim:
+        cols, rows = sim.cols, sim.rows
+        host = sim.simulate(poses, seed=9, first_frame=40)
+
+        def dev_call(n_slots=len(poses), fill=0.0):
+            out = torch.full((n_slots, cols, rows), fill, dtype=torch.float32, device="cuda")
+            sim.simulate_device(poses, out.data_ptr(), seed=9, first_frame=40)
+            return out.cpu().numpy()
+
+        assert np.array_equal(dev_call(), host)
+        for opt, val in (("direct_out", 0), ("max_batch_poses", 4), ("use_graph", 0)):
+            sim.set_option(opt, val)
+            assert np.array_equal(dev_call(), host), opt
+            sim.set_option(opt, {"direct_out": 1, "max_batch_poses": 256, "use_graph": 1}[opt])
+        for direct in (1, 0):
+            sim.set_option("direct_out", direct)
+            sim.set_option("rf_out_frame_stride", 3)
+            sim.set_option("max_batch_poses", 4)
+            strided = dev_call(3 * len(poses), fill=-7.0)
+            assert np.array_equal(strided[0::3], host)
+            assert np.all(strided[1::3] == -7.0) and np.all(strided[2::3] == -7.0)
+            sim.set_option("rf_out_frame_stride", 1)
+            sim.set_option("max_batch_poses", 256)
+        sim.set_option("direct_out", 1)
+        with pytest.raises(api.McrtError):                                  # a stride needs a device buffer
+            sim.set_option("rf_out_frame_stride", 2)
+            sim.simulate(poses[:2], seed=9, first_frame=40)
+        sim.set_option("rf_out_frame_stride", 1)
+        sim.set_elevation(3, 0.1)
+        e_host = sim.simulate(poses[:3], seed=9, first_frame=40)
+        out = torch.zeros((3, cols, rows), dtype=torch.float32, device="cuda")
+        sim.simulate_device(poses[:3], out.data_ptr(), seed=9, first_frame=40)
+        assert np.array_equal(out.cpu().numpy(), e_host)
+
+
 def test_rf_layout_cv_mat(api, sphere):
     gp0 = api.default_params(elements=128, samples=2)
     gp1 = api.default_params(elements=128, samples=2, rf_layout=1)
