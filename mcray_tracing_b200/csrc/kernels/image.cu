@@ -175,10 +175,8 @@ template <bool FMADIV>
 __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate(const SceneDev sc, const AcqDev aq, const float2* __restrict__ volume,
                                                    const DevSegment* __restrict__ segments, const int32_t* __restrict__ nseg,
                                                    const int n_paths, float* __restrict__ columns,
-                                                   unsigned long long* __restrict__ steps_total,
-                                                   const unsigned* __restrict__ seg_index, const int* __restrict__ path_first)
+                                                   unsigned long long* __restrict__ steps_total)
 {
-    // seg_index != nullptr (ray-tree mode): segment k of path p is segments[seg_index[path_first[p] + k]], nseg = count per path
     __shared__ DevMaterial s_mat[MCRT_MAX_SMEM_MATERIALS];
     for (int i = threadIdx.x; i < sc.n_mat && i < MCRT_MAX_SMEM_MATERIALS; i += blockDim.x) s_mat[i] = sc.materials[i];
     __syncthreads();
@@ -208,9 +206,8 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate(const Sce
         const double block_safe_hi = 1.0 - 1e-6 - (double)(MCRT_ACC_UNROLL - 1) * row_delta;
 
         const int ns = nseg[p];
-        const int first = seg_index ? path_first[p] : 0;
         for (int k = 0; k < ns; k++) {
-            const DevSegment* sg = seg_index ? segments + seg_index[first + k] : segments + (size_t)p * aq.max_depth + k;
+            const DevSegment* sg = segments + (size_t)p * aq.max_depth + k;
             const float4 s0 = __ldg(&sg->s0), s1 = __ldg(&sg->s1), s2 = __ldg(&sg->s2);
             const int4 s3 = __ldg(&sg->s3);
             const DevMaterial media = s_mat[s3.z];
@@ -1671,9 +1668,9 @@ cudaError_t launch_accumulate(const SceneDev& sc, const AcqDev& aq, const float2
     if (!d_columns) return cudaErrorInvalidValue;
     const int block = 128;
     if (aq.voxel_fma_division)
-        k_accumulate<true><<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_paths, d_columns, d_steps, nullptr, nullptr);
+        k_accumulate<true><<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_paths, d_columns, d_steps);
     else
-        k_accumulate<false><<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_paths, d_columns, d_steps, nullptr, nullptr);
+        k_accumulate<false><<<(n_paths + block - 1) / block, block, 0, stream>>>(sc, aq, d_volume, d_segments, d_nseg, n_paths, d_columns, d_steps);
     const int64_t n_pixels = (int64_t)n_poses * aq.elements * aq.rows;
     k_reduce_samples<<<grid1d(n_pixels, 256), 256, 0, stream>>>(d_columns, n_pixels, aq.samples, d_rf, aq.rows, aq.rf_pitch);
     if (launches) (*launches) += 2;
