@@ -269,7 +269,8 @@ __device__ __forceinline__ bool bounce_path(const SceneDev& sc, const AcqDev& aq
 #define MCRT_BOUNCE_GRID_CTAS_PER_SM 64   // measured: an (effectively) uncapped grid beats a persistent 8-CTA/SM grid by 15 % at 256 frames
 #endif
 #ifndef MCRT_BOUNCE_MIN_CTAS
-#define MCRT_BOUNCE_MIN_CTAS 6      // 80 registers, 24 warps/SM: measured best of 4/5/6/8 (profiles/r01_traversal_ab.txt)
+#define MCRT_BOUNCE_MIN_CTAS 8      // 64 registers, 32 warps/SM.  Round 1 measured 6 (80 registers) best; with the round-2 kernel 8 is 1-2 % faster at
+                                    // 1024 frames, one frame and on config 4, 0.5 % slower at 64 frames; 10 (48 registers) -11 % (profiles/r02ap_ab_bounce_regs.txt)
 #endif
 // ORDERED: order-preserving compaction (see TraceBuffers::warp_counts): every warp compacts its survivors into its own
 // 32-slot piece of the sparse queue and records how many, k_compact turns that into the dense queue of the next bounce.
