@@ -148,7 +148,7 @@ int mcrt_get_stats(const mcrt_ctx* ctx, mcrt_stats* stats);
  *   diagnostics "profile_stages"=0/1 (per-stage events in mcrt_stats, disables the CUDA graph), "count_traversal"=0/1 (BVH work counters
  *               in mcrt_stats), "use_graph"=0/1
  *   A/B switches of measured design choices (results are bit-identical either way; DESIGN.md section 5, profiles/):
- *               "tail_merge" (1), "first_hit_dedup" (1: large calls, 2: always, 0: off), "ordered_compaction" (1: large calls, 2: always,
+ *               "tail_merge" (12, in units of 768 paths per SM; 0 = off), "first_hit_dedup" (1: large calls, 2: always, 0: off), "ordered_compaction" (1: large calls, 2: always,
  *               0: warp-aggregated atomic appends), "group_histories" (0), "accumulate_windowed" (1), "voxel_fma_division" (1 when the
  *               resolution passed its exhaustive check), "post_tma" (1), "long_ct" (1), "overlap" (0), "direct_out" (1: with a device rf_out the
  *               last kernel of the chain writes the frames straight into it; 0: internal image + device-to-device copy) */

@@ -615,7 +615,11 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) throw CudaError(std::string("device '") + prop.name + "' is not sm_100 (B200); libmcrt only carries sm_100a code");
     c->sm_count = prop.multiProcessorCount;
-    c->tb.tail_threshold = c->sm_count * 6 * 128;      // option "tail_merge"
+    // option "tail_merge" (units of sm_count * 768 paths): once at most this many paths are alive one launch walks them to their end.  12 units
+    // (1.36 M paths on a B200) measured best with the round-2 kernels: a call of up to 256 frames of 256 x 16 is traced by ONE launch
+    // (+17 % at 32 frames per call, +13 % at 64, +5 % at 128, +1.6 % at 256, config 4 +3..10 %), larger calls compact until they fit;
+    // 20 units already lose at 512 frames per call (profiles/r02at_ab_tail_threshold.txt)
+    c->tb.tail_threshold = 12 * c->sm_count * 6 * 128;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));

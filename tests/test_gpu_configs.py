@@ -151,7 +151,7 @@ def test_traversal_options_do_not_change_results(api, O):
     with api.Simulator(A, api.default_params(elements=64, samples=8)) as sim:
         base = sim.simulate(poses, seed=5, first_frame=7)
         segs0, n0 = sim.cast_rays(pose, seed=5, frame=7)
-        for opt, val in (("tail_merge", 0), ("first_hit_dedup", 2), ("ordered_compaction", 2), ("group_histories", 1), ("bvh_builder", 1), ("bvh_builder", 2), ("overlap", 1),
+        for opt, val in (("tail_merge", 0), ("tail_merge", 1), ("first_hit_dedup", 2), ("ordered_compaction", 2), ("group_histories", 1), ("bvh_builder", 1), ("bvh_builder", 2), ("overlap", 1),
                          ("post_tma", 0)):       # round 1's fused post kernel instead of the TMA-staged one
             sim.set_option(opt, val)
             assert np.array_equal(sim.simulate(poses, seed=5, first_frame=7), base), opt
