@@ -110,6 +110,8 @@ typedef struct mcrt_info {
     double axial_resolution_mm, time_step_us, row_period_us, max_travel_time_us;
     int32_t voxel_fma_division; /* 1: the 3-instruction voxel index passed its exhaustive check for this resolution and is in use */
     int32_t bvh_cache_hit;      /* 1: the acceleration structure (any builder) was loaded from $MCRT_BVH_CACHE instead of being built */
+    int32_t bvh_optimised;      /* 1: the background-built SAH tree has replaced the device LBVH (options "bvh_optimise", "bvh_wait") */
+    int32_t reserved0;
 } mcrt_info;
 
 typedef struct mcrt_stats {   /* of the most recent mcrt_simulate call */
@@ -144,7 +146,12 @@ int mcrt_get_stats(const mcrt_ctx* ctx, mcrt_stats* stats);
  *               the round-robin pose deal of a G-rank sweep; default 1), "rf_out_frame_stride"=G (device rf_out only: frame i of a call
  *               is written at rf_out + i * G frames -- the interleaved slots of that deal in a buffer in global pose order; default 1),
  *               "bvh_builder"=0 device LBVH (default) / 1 host binned-SAH
- *               tree / 2 device PLOC (rebuilds the acceleration structure in place; every builder gives the same results)
+ *               tree / 2 device PLOC (rebuilds the acceleration structure in place; every builder gives the same results),
+ *               "bvh_optimise"=1/0 (default 1; builder 0, scenes of >= 32768 triangles: the device LBVH serves a new or changed scene at
+ *               once while a host thread builds the binned-SAH tree of the same triangles; the first compute call after it has finished
+ *               adopts it -- mcrt_info.bvh_optimised; after mesh updates the optimiser waits for 8 calls on an unchanged scene; the
+ *               environment variable MCRT_BVH_OPTIMISE=0 disables it at mcrt_create), "bvh_wait"=1 (block until a running optimisation
+ *               has finished and adopt its tree: keeps the swap out of a timed region)
  *   diagnostics "profile_stages"=0/1 (per-stage events in mcrt_stats, disables the CUDA graph), "count_traversal"=0/1 (BVH work counters
  *               in mcrt_stats), "use_graph"=0/1
  *   A/B switches of measured design choices (results are bit-identical either way; DESIGN.md section 5, profiles/):
@@ -284,6 +291,14 @@ int mcrt_scene_probe(const char* scene_json_path, int64_t* n_triangles, int32_t*
  * maps (rfimage.h:183-215).  Any output pointer may be NULL. */
 int mcrt_host_tables(const mcrt_params* params, mcrt_info* info, float* elem_sincos2, float* axial, float* lateral, float* map_x,
                      float* map_y);
+
+/* the host tree builder of the background optimisation (option "bvh_optimise") and of "bvh_builder"=1: binned-SAH BVH2 over
+ * n_triangles triangles (9 floats each, mesh-local; world = local + mesh_origin3[mesh]).  nodes16: (n_triangles - 1) x 16 words =
+ * {child0 lo.xyz hi.xyz, child1 lo.xyz hi.xyz} as float + {child0, child1, 0, 0} as int32 (child >= 0: node index, pre-order, root 0;
+ * child < 0: leaf slot -(1 + 4 * slot)); slot_triangle: the triangle of every leaf slot.  threads <= 0: all host threads; the
+ * tree does not depend on it.  Replaces the Bullet btBvhTriangleMeshShape build of scene.cpp:319-330. */
+int mcrt_host_build_sah(const float* tri_local9, const int32_t* tri_mesh, int64_t n_triangles, const float* mesh_origin3, int32_t n_meshes,
+                        int32_t threads, float* nodes16, int32_t* slot_triangle, int32_t* max_depth);
 
 /* numerics contract self-test: evaluates the shared transcendentals ON THE DEVICE.
  * op 0 expf, 1 logf, 2 powf(a,b), 3 sin (double), 4 cos (double), 5 philox (a=counter as float bits) */

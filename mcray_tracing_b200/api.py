@@ -48,7 +48,8 @@ class Info(C.Structure):
     _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("scan_rows", C.c_int32), ("scan_cols", C.c_int32), ("n_materials", C.c_int32),
                 ("n_meshes", C.c_int32), ("n_triangles", C.c_int64), ("n_bvh_nodes", C.c_int64), ("device", C.c_int32),
                 ("sm_count", C.c_int32), ("start_pose", C.c_float * 6), ("axial_resolution_mm", C.c_double), ("time_step_us", C.c_double),
-                ("row_period_us", C.c_double), ("max_travel_time_us", C.c_double), ("voxel_fma_division", C.c_int32), ("bvh_cache_hit", C.c_int32)]
+                ("row_period_us", C.c_double), ("max_travel_time_us", C.c_double), ("voxel_fma_division", C.c_int32), ("bvh_cache_hit", C.c_int32),
+                ("bvh_optimised", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class BmodeParams(C.Structure):
@@ -71,7 +72,8 @@ EXPORTS = ["mcrt_default_params", "mcrt_create", "mcrt_create_from_arrays", "mcr
            "mcrt_get_stats", "mcrt_set_option", "mcrt_simulate", "mcrt_simulate_async", "mcrt_trace_debug", "mcrt_closest_hit",
            "mcrt_transducer_elements", "mcrt_accumulate", "mcrt_postprocess", "mcrt_scan_convert", "mcrt_get_psf_taps",
            "mcrt_get_scene", "mcrt_get_volume", "mcrt_numerics_probe", "mcrt_load_obj", "mcrt_scene_probe", "mcrt_host_tables", "mcrt_simulate_scanlines", "mcrt_bmode", "mcrt_set_mesh_origin", "mcrt_set_mesh_vertices", "mcrt_trace_tree_debug", "mcrt_device_alloc", "mcrt_set_psf_depth_profile",
-           "mcrt_device_free", "mcrt_ipc_export", "mcrt_ipc_open", "mcrt_ipc_close", "mcrt_copy_async", "mcrt_copy2d_async", "mcrt_set_elevation", "mcrt_elevation_pose"]
+           "mcrt_device_free", "mcrt_ipc_export", "mcrt_ipc_open", "mcrt_ipc_close", "mcrt_copy_async", "mcrt_copy2d_async", "mcrt_set_elevation", "mcrt_elevation_pose",
+           "mcrt_host_build_sah"]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
@@ -130,6 +132,7 @@ def lib():
         L.mcrt_load_obj.argtypes = [C.c_char_p, vp, C.c_int64, vp]
         L.mcrt_scene_probe.argtypes = [C.c_char_p, vp, vp, vp, vp]
         L.mcrt_host_tables.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.mcrt_host_build_sah.argtypes = [vp, vp, C.c_int64, vp, C.c_int32, C.c_int32, vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -435,6 +438,21 @@ def load_obj(path) -> np.ndarray:
     out = np.empty((n.value, 9), np.float32)
     _check(lib().mcrt_load_obj(str(path).encode(), _p(out), n.value, C.byref(n)))
     return out
+
+
+def host_build_sah(tri_local, tri_mesh, mesh_origins, threads: int = 0):
+    """The host binned-SAH tree of the background optimisation (no GPU needed): (nodes [n - 1, 16] as float32 whose words 12, 13 are the
+    int32 child references, slot_triangle [n], max_depth)."""
+    tri_local = np.ascontiguousarray(tri_local, np.float32).reshape(-1, 9)
+    tri_mesh = np.ascontiguousarray(tri_mesh, np.int32)
+    mesh_origins = np.ascontiguousarray(mesh_origins, np.float32).reshape(-1, 3)
+    n = len(tri_mesh)
+    nodes = np.zeros((max(n - 1, 0), 16), np.float32)
+    slots = np.zeros(n, np.int32)
+    depth = C.c_int32(0)
+    _check(lib().mcrt_host_build_sah(_p(tri_local), _p(tri_mesh), n, _p(mesh_origins), len(mesh_origins), threads, _p(nodes), _p(slots),
+                                     C.byref(depth)))
+    return nodes, slots, depth.value
 
 
 def scene_probe(path) -> dict:

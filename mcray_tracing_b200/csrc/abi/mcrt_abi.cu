@@ -3,6 +3,7 @@
 // capture of that pipeline, and the stage-level entry points the parity tests call.
 // No CPU fallback anywhere: every compute entry point launches the kernels of csrc/kernels/.
 #include <algorithm>
+#include <atomic>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -12,6 +13,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/mcrt.h"
@@ -123,6 +125,24 @@ struct mcrt_ctx {
     int bvh_builder = 0;               // 0 device LBVH, 1 host binned SAH (option "bvh_builder")
     bool bvh_cache_hit = false;        // the last SAH build came from $MCRT_BVH_CACHE
     bool scene_dirty = false;          // staged mesh updates wait for a rebuild
+    // Background tree optimisation (option "bvh_optimise", default on, builder 0 only): the device LBVH serves a new or changed
+    // scene at once; a host thread builds the binned-SAH tree of the same triangles and the first compute call after it has
+    // finished swaps it in (results do not depend on the tree: closest hits tie-break by triangle id).
+    struct BgTree {
+        std::thread th;
+        std::atomic<int> state{0};         // 0 idle, 1 building, 2 ready, 3 failed
+        std::atomic<bool> cancel{false};   // abandon the running build (mcrt_destroy, builder / option changes)
+        uint64_t version = 0;              // scene_version the snapshot below was taken at
+        std::vector<float> tri_local, origins;
+        std::vector<int32_t> tri_mesh;
+        HostBvh tree;
+        ~BgTree() { cancel.store(true); if (th.joinable()) th.join(); }
+    };
+    std::unique_ptr<BgTree> bg;
+    uint64_t scene_version = 0;        // bumped by every staged mesh update
+    int bvh_optimise = 1;
+    bool bvh_optimised = false;        // the traversal tree in use is the optimised one
+    int quiet_calls = 0;               // compute calls since the last mesh update (a deforming scene is not re-optimised every frame)
     float* d_axial = nullptr;
     float* d_lateral = nullptr;
     float* d_lat_by_row = nullptr;     // depth-dependent lateral PSF table [psf_lateral][rows] (mcrt_set_psf_depth_profile), or nullptr
@@ -189,6 +209,9 @@ static void update_scene_bounds(mcrt_ctx* c);
 static void ensure_scene_current(mcrt_ctx* c);
 static void rebuild_bvh(mcrt_ctx* c);
 static void make_bvh2(mcrt_ctx* c, mcrt::LbvhResult* nb);
+static void bg_tree_start(mcrt_ctx* c);
+static void bg_tree_adopt(mcrt_ctx* c, bool wait);
+static void bg_tree_cancel(mcrt_ctx* c);
 }
 
 namespace {
@@ -673,6 +696,12 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
     c->aq.accumulate_windowed = accumulate_windowed_supported(sc, c->aq) ? 1 : 0;
     sc.max_abs = c->bvh.max_abs;
     update_scene_bounds(c.get());
+    {   // the better tree is built on a host thread while the rest of the start-up runs (MCRT_BVH_OPTIMISE=0: never)
+        const char* e = getenv("MCRT_BVH_OPTIMISE");
+        if (e && *e == '0') c->bvh_optimise = 0;
+        c->quiet_calls = 8;
+        bg_tree_start(c.get());
+    }
 
     // transducer table, psf taps, scan maps, scatterer volume
     std::vector<float> sincos;
@@ -718,6 +747,7 @@ int create_impl(HostScene&& scene, const mcrt_params* params, int device, mcrt_c
 void destroy_impl(mcrt_ctx* c)
 {
     if (!c) return;
+    if (c->bg) { c->bg->cancel.store(true); if (c->bg->th.joinable()) c->bg->th.join(); }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_workspace(c);
@@ -828,7 +858,7 @@ static uint64_t fnv1a64(const void* data, size_t n, uint64_t h)
 // body origins, the builder and a format / builder version, so a file written by another version is simply never looked up;
 // a file that IS found is still validated in full before use (child references, leaf slots, every slot's vertices against
 // the scene, the depth): a stale, truncated or hostile file in a shared cache directory falls back to rebuilding.
-static const uint64_t kTreeCacheVersion = 2;          // bump when a builder or the file layout changes
+static const uint64_t kTreeCacheVersion = 3;          // bump when a builder or the file layout changes
 static std::string tree_cache_path(const HostScene& hs, const std::vector<float>& origins, int builder)
 {
     const char* dir = getenv("MCRT_BVH_CACHE");
@@ -997,31 +1027,110 @@ static void make_bvh2(mcrt_ctx* c, LbvhResult* nb)
 // (Re)build the acceleration structure from c->scene with the selected builder and swap it in.  Used by the bvh_builder
 // option and after mesh updates (mcrt_set_mesh_origin / mcrt_set_mesh_vertices): the device LBVH build is ~0.3 ms of
 // kernels for 624 640 triangles, so moving or deforming meshes are handled by rebuilding, not by refitting.
-static void rebuild_bvh(mcrt_ctx* c)
+// a freshly built BVH2 becomes the traversal structure of the context (wide tree built, old trees freed, graphs dropped: they hold
+// the old pointers).  Takes ownership of nb's device arrays.
+static void install_bvh2(mcrt_ctx* c, LbvhResult nb)
 {
-    CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
-    c->graphs.clear();
-    LbvhResult nb{};
-    make_bvh2(c, &nb);
     if (nb.max_depth > MCRT_TRAVERSAL_STACK) { cudaFree(nb.nodes); cudaFree(nb.tris); throw std::invalid_argument("BVH deeper than the traversal stack"); }
     WideTree w;
     try {
         build_wide_tree(nb, c->stream, &w);
     } catch (...) { cudaFree(nb.nodes); cudaFree(nb.tris); throw; }
+    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    c->graphs.clear();
     dev_free(c->bvh.nodes); dev_free(c->bvh.tris); dev_free(c->d_nodes4); dev_free(c->d_nodes8); dev_free(c->d_tris8);
     c->bvh = nb;
     c->d_nodes4 = w.n4; c->d_nodes8 = w.n8; c->d_tris8 = w.t8; c->n_nodes_wide = w.n_nodes; c->depth_wide = w.depth;
     c->sc.nodes = nb.nodes; c->sc.nodes4 = w.n4; c->sc.nodes8 = w.n8; c->sc.tris = w.t8 ? w.t8 : nb.tris; c->sc.n_tri = nb.n_tri; c->sc.max_abs = nb.max_abs;
+}
+
+static void rebuild_bvh(mcrt_ctx* c)
+{
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    LbvhResult nb{};
+    make_bvh2(c, &nb);
+    install_bvh2(c, nb);
     update_scene_bounds(c);
     c->scene_dirty = false;
+    c->bvh_optimised = false;
+}
+
+// ---- background tree optimisation (see mcrt_ctx::BgTree) ----
+static const size_t kOptimiseMinTriangles = 32768;     // below this a closest-hit query visits so few nodes that the better tree buys nothing
+static std::vector<float> scene_origins(const HostScene& hs)
+{
+    std::vector<float> origins(hs.meshes.size() * 3 + 3);
+    for (size_t m = 0; m < hs.meshes.size(); m++)
+        for (int a = 0; a < 3; a++) origins[3 * m + a] = hs.meshes[m].origin[a];
+    return origins;
+}
+static void bg_tree_cancel(mcrt_ctx* c)
+{
+    if (!c->bg) return;
+    c->bg->cancel.store(true);
+    if (c->bg->th.joinable()) c->bg->th.join();
+    c->bg->cancel.store(false);
+    c->bg->state.store(0);
+    c->bg->tree = HostBvh();
+}
+// start the optimisation of the CURRENT scene unless it is pointless, disabled, already done or already running
+static void bg_tree_start(mcrt_ctx* c)
+{
+    const HostScene& hs = c->scene;
+    if (!c->bvh_optimise || c->bvh_builder != 0 || c->bvh_optimised || c->scene_dirty || hs.tri_mesh.size() < kOptimiseMinTriangles) return;
+    if (c->bg && c->bg->state.load() != 0) return;       // building, or a result waits to be adopted
+    if (!c->bg) c->bg.reset(new mcrt_ctx::BgTree());
+    mcrt_ctx::BgTree* bg = c->bg.get();
+    if (bg->th.joinable()) bg->th.join();
+    bg->version = c->scene_version;
+    bg->origins = scene_origins(hs);
+    // a tree of this very scene in $MCRT_BVH_CACHE (validated) needs no thread
+    const std::string cache = tree_cache_path(hs, bg->origins, 1);
+    if (tree_cache_load(cache, hs, &bg->tree)) { bg->state.store(2); return; }
+    bg->tri_local = hs.tri_local; bg->tri_mesh = hs.tri_mesh;          // snapshot: mesh updates may be staged while the thread runs
+    bg->state.store(1);
+    bg->th = std::thread([bg]() {
+        try {
+            build_sah_bvh(bg->tri_local.data(), bg->tri_mesh.data(), (int)bg->tri_mesh.size(), bg->origins.data(), &bg->tree, 0, &bg->cancel);
+            bg->state.store(2);
+        } catch (...) { bg->state.store(3); }
+    });
+}
+// swap the finished tree in (wait: block until the running build has finished).  Called at the start of compute entry points.
+static void bg_tree_adopt(mcrt_ctx* c, bool wait)
+{
+    mcrt_ctx::BgTree* bg = c->bg.get();
+    if (!bg) return;
+    int st = bg->state.load();
+    if (st == 1 && wait) { if (bg->th.joinable()) bg->th.join(); st = bg->state.load(); }
+    if (st != 2 && st != 3) return;
+    if (bg->th.joinable()) bg->th.join();
+    bg->state.store(0);
+    const bool usable = st == 2 && bg->version == c->scene_version && !c->scene_dirty && c->bvh_builder == 0 && c->bvh_optimise;
+    if (usable) {
+        CUDA_TRY(cudaSetDevice(c->device));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (c->last_valid) CUDA_TRY(cudaEventSynchronize(c->ev_last));          // work of an asynchronous call may still read the old tree
+        LbvhResult nb{};
+        upload_host_tree(bg->tree, &nb);
+        install_bvh2(c, nb);
+        c->bvh_optimised = true;
+        tree_cache_store(tree_cache_path(c->scene, bg->origins, 1), bg->tree);  // no-op without $MCRT_BVH_CACHE
+    }
+    bg->tree = HostBvh(); bg->tri_local.clear(); bg->tri_local.shrink_to_fit(); bg->tri_mesh.clear(); bg->tri_mesh.shrink_to_fit();
 }
 
 // mesh updates are staged on the host and applied by ONE rebuild at the next compute call
 static void ensure_scene_current(mcrt_ctx* c)
 {
-    if (!c->scene_dirty) return;
+    if (!c->scene_dirty) {
+        bg_tree_adopt(c, false);
+        // after mesh updates the optimiser waits for 8 compute calls on an unchanged scene before it starts again
+        if (!c->bvh_optimised && c->bvh_optimise && c->bvh_builder == 0 && ++c->quiet_calls >= 8) bg_tree_start(c);
+        return;
+    }
+    c->quiet_calls = 0;
     const HostScene& hs = c->scene;
     std::vector<DevMesh> meshes(hs.meshes.size());
     for (size_t m = 0; m < hs.meshes.size(); m++) {
@@ -1041,7 +1150,7 @@ int mcrt_set_mesh_origin(mcrt_ctx* c, int32_t mesh, const float* origin3)
     if (!c || !origin3) return fail(MCRT_ERR_INVALID, "mcrt_set_mesh_origin: null argument");
     if (mesh < 0 || (size_t)mesh >= c->scene.meshes.size()) return fail(MCRT_ERR_INVALID, "mcrt_set_mesh_origin: no such mesh");
     for (int a = 0; a < 3; a++) c->scene.meshes[mesh].origin[a] = origin3[a];
-    c->scene_dirty = true;
+    c->scene_dirty = true; c->scene_version++;
     return MCRT_OK;
 }
 
@@ -1055,7 +1164,7 @@ int mcrt_set_mesh_vertices(mcrt_ctx* c, int32_t mesh, const float* tri_local9, i
         if (hs.tri_mesh[t] == mesh) { if (count == 0) first = t; count++; }
     if ((int64_t)count != n_triangles) return fail(MCRT_ERR_INVALID, "mcrt_set_mesh_vertices: the triangle count of a mesh cannot change");
     if (count) memcpy(hs.tri_local.data() + 9 * first, tri_local9, sizeof(float) * 9 * count);
-    c->scene_dirty = true;
+    c->scene_dirty = true; c->scene_version++;
     return MCRT_OK;
 }
 
@@ -1072,6 +1181,7 @@ int mcrt_get_info(const mcrt_ctx* c, mcrt_info* info)
     info->row_period_us = c->dv.row_period_us; info->max_travel_time_us = c->dv.max_travel_time_us;
     info->voxel_fma_division = c->aq.voxel_fma_division;
     info->bvh_cache_hit = c->bvh_cache_hit ? 1 : 0;
+    info->bvh_optimised = c->bvh_optimised ? 1 : 0;
     return MCRT_OK;
 }
 
@@ -1095,12 +1205,35 @@ int mcrt_set_option(mcrt_ctx* c, const char* name, int64_t value)
         c->overlap = value != 0;
     }
     else if (n == "bvh_builder") {
-        // 0: device LBVH (default, lbvh.cu); 1: host binned-SAH tree (sah_builder.cpp), cached on disk when the environment
-        // variable MCRT_BVH_CACHE names a directory.  Rebuilds in place.
+        // 0: device LBVH (default, lbvh.cu) + background optimisation (option "bvh_optimise"); 1: host binned-SAH tree
+        // (sah_builder.cpp) built in place; 2: device PLOC.  Every tree is cached on disk when the environment variable
+        // MCRT_BVH_CACHE names a directory.  Rebuilds in place.
         return guarded("mcrt_set_option", [&]() {
             if (value < 0 || value > 2) throw std::invalid_argument("bvh_builder: 0 device LBVH, 1 host binned SAH, 2 device PLOC");
+            bg_tree_cancel(c);
             c->bvh_builder = (int)value;
             rebuild_bvh(c);
+            c->quiet_calls = 8;
+            bg_tree_start(c);
+            return MCRT_OK;
+        });
+    }
+    else if (n == "bvh_optimise") {
+        // 1 (default): with builder 0, a host thread builds the binned-SAH tree of the scene in the background and the first compute
+        // call after it has finished adopts it; 0: keep (or go back to) the plain device LBVH
+        return guarded("mcrt_set_option", [&]() {
+            c->bvh_optimise = value != 0 ? 1 : 0;
+            if (!c->bvh_optimise) { bg_tree_cancel(c); if (c->bvh_optimised) rebuild_bvh(c); }
+            else { c->quiet_calls = 8; bg_tree_start(c); }
+            return MCRT_OK;
+        });
+    }
+    else if (n == "bvh_wait") {
+        // block until a running background optimisation has finished and adopt its tree (benchmarks: no swap inside a timed region)
+        return guarded("mcrt_set_option", [&]() {
+            if (c->scene_dirty) ensure_scene_current(c);
+            // (a build that was started before the last mesh update is stale: its result is dropped and a second round builds the current scene)
+            for (int round = 0; value != 0 && round < 2 && !c->bvh_optimised; round++) { c->quiet_calls = 8; bg_tree_start(c); bg_tree_adopt(c, true); }
             return MCRT_OK;
         });
     }
@@ -1727,6 +1860,24 @@ int mcrt_load_obj(const char* obj_path, float* out9, int64_t capacity_tris, int6
         const int64_t n = (int64_t)(soup.size() / 9);
         *n_tris = n;
         if (out9 && capacity_tris > 0) memcpy(out9, soup.data(), sizeof(float) * 9 * (size_t)(n < capacity_tris ? n : capacity_tris));
+        return MCRT_OK;
+    });
+}
+
+int mcrt_host_build_sah(const float* tri_local9, const int32_t* tri_mesh, int64_t n_triangles, const float* mesh_origin3, int32_t n_meshes,
+                        int32_t threads, float* nodes16, int32_t* slot_triangle, int32_t* max_depth)
+{
+    if (!tri_local9 || !tri_mesh || !mesh_origin3 || n_triangles < 0 || n_triangles > 0x1fffffff || n_meshes <= 0)
+        return fail(MCRT_ERR_INVALID, "mcrt_host_build_sah: bad argument");
+    for (int64_t t = 0; t < n_triangles; t++)
+        if (tri_mesh[t] < 0 || tri_mesh[t] >= n_meshes) return fail(MCRT_ERR_INVALID, "mcrt_host_build_sah: mesh index out of range");
+    return guarded("mcrt_host_build_sah", [&]() {
+        HostBvh hb;
+        build_sah_bvh(tri_local9, tri_mesh, (int)n_triangles, mesh_origin3, &hb, threads);
+        static_assert(sizeof(HostBvhNode) == 64, "16 words per node");
+        if (nodes16 && !hb.nodes.empty()) memcpy(nodes16, hb.nodes.data(), sizeof(HostBvhNode) * hb.nodes.size());
+        if (slot_triangle) for (size_t k = 0; k < hb.slots.size(); k++) slot_triangle[k] = hb.slots[k].tri;
+        if (max_depth) *max_depth = hb.max_depth;
         return MCRT_OK;
     });
 }

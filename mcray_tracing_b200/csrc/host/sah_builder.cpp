@@ -1,12 +1,16 @@
-// sah_builder.cpp -- optional host-side BVH builder (binned surface-area heuristic) producing the
-// same 64-byte node / 48-byte triangle-slot layout as the device LBVH (kernels/lbvh.cu).  The device
-// LBVH is the default (it rebuilds in < 1 ms); a SAH tree costs ~1 s on the host for 600 k triangles
-// but is visited with fewer node fetches per ray, which pays for static scenes.  Selected with
-// mcrt_set_option(ctx, "bvh_builder", 1) (rebuilds in place).
+// sah_builder.cpp -- host-side BVH builder (binned surface-area heuristic) producing the same 64-byte node /
+// 48-byte triangle-slot layout as the device LBVH (kernels/lbvh.cu).  The device LBVH serves a new or changed scene at
+// once (it builds in < 1 ms); this tree is visited with ~8 % fewer node fetches per ray, so a context builds it on a
+// background thread and swaps it in when it is ready (mcrt_abi.cu, option "bvh_optimise"), or builds it in place with
+// mcrt_set_option(ctx, "bvh_builder", 1).  Node ids are the pre-order positions, known before a subtree is built
+// (a range of n triangles holds n - 1 nodes), so the two children of a large node are built by different threads
+// and the result does not depend on the number of threads.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
 #include <vector>
 
 #include "sah_builder.h"
@@ -30,14 +34,24 @@ struct Box {
 struct Builder {
     const std::vector<Box>& tri_box;
     std::vector<float> cent;          // 3 per triangle
-    std::vector<int32_t> order;       // triangle ids, permuted in place
-    std::vector<HostBvhNode> nodes;
-    int max_depth = 0;
+    std::vector<int32_t> order;       // triangle ids, permuted in place (disjoint ranges per subtree)
+    std::vector<HostBvhNode> nodes;   // n_tri - 1, pre-order; every subtree writes its own id range
+    std::atomic<int> max_depth{0};
+    std::atomic<int> spare_threads{0};
+    std::atomic<bool> failed{false};
+    const std::atomic<bool>* cancel = nullptr;     // set by the owner to abandon the build
 
     explicit Builder(const std::vector<Box>& tb) : tri_box(tb) {}
 
-    // returns child reference: >= 0 internal node index, < 0 leaf -(1 + slot*4)
-    int build(int first, int count, int depth, Box* out_box)
+    void note_depth(int d)
+    {
+        int cur = max_depth.load(std::memory_order_relaxed);
+        while (d > cur && !max_depth.compare_exchange_weak(cur, d, std::memory_order_relaxed)) {}
+    }
+
+    // builds the subtree of order[first, first + count) into nodes[id ...]; returns the child reference of its root:
+    // >= 0 internal node index, < 0 leaf -(1 + slot*4)
+    int build(int first, int count, int depth, int id, Box* out_box)
     {
         Box bb; bb.reset();
         Box cb; cb.reset();
@@ -48,7 +62,8 @@ struct Builder {
         }
         *out_box = bb;
         if (count == 1) return -(1 + first * 4);
-        max_depth = std::max(max_depth, depth + 1);
+        if (count >= 256 && cancel && cancel->load(std::memory_order_relaxed)) throw std::runtime_error("sah builder: cancelled");
+        note_depth(depth + 1);
         // binned SAH over the centroid bounds
         const int NB = 16;
         int best_axis = -1, best_bin = -1;
@@ -81,7 +96,8 @@ struct Builder {
             const float ext = cb.hi[best_axis] - cb.lo[best_axis];
             const float scale = NB / ext;
             const float lo = cb.lo[best_axis];
-            auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](int32_t t) {
+            // stable: the triangle order inside a leaf range (and with it the tree) does not depend on the library's partition algorithm
+            auto it = std::stable_partition(order.begin() + first, order.begin() + first + count, [&](int32_t t) {
                 int b = (int)((cent[3 * (size_t)t + best_axis] - lo) * scale);
                 b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
                 return b <= best_bin;
@@ -91,22 +107,40 @@ struct Builder {
             mid = first + count / 2;       // all centroids coincide: split by index
         }
         if (mid == first || mid == first + count) mid = first + count / 2;
-        const int id = (int)nodes.size();
-        nodes.emplace_back();
+        const int left = mid - first, right = first + count - mid;
+        // pre-order ids: the left subtree (left - 1 nodes) follows this node, the right subtree follows the left one
+        const int id_left = id + 1, id_right = id + left;
         Box lb, rb;
-        const int lc = build(first, mid - first, depth + 1, &lb);
-        const int rc = build(mid, first + count - mid, depth + 1, &rb);
+        int lc = 0, rc = 0;
+        bool fork = false;
+        if (left >= kForkMin && right >= kForkMin) {
+            if (spare_threads.fetch_sub(1, std::memory_order_relaxed) > 0) fork = true;
+            else spare_threads.fetch_add(1, std::memory_order_relaxed);
+        }
+        if (fork) {
+            std::thread th([&]() {
+                try { lc = build(first, left, depth + 1, id_left, &lb); } catch (...) { failed.store(true); }
+            });
+            try { rc = build(mid, right, depth + 1, id_right, &rb); } catch (...) { failed.store(true); }
+            th.join();
+            spare_threads.fetch_add(1, std::memory_order_relaxed);
+        } else {
+            lc = build(first, left, depth + 1, id_left, &lb);
+            rc = build(mid, right, depth + 1, id_right, &rb);
+        }
         HostBvhNode& nd = nodes[id];
         nd.f[0] = lb.lo[0]; nd.f[1] = lb.lo[1]; nd.f[2] = lb.lo[2]; nd.f[3] = lb.hi[0]; nd.f[4] = lb.hi[1]; nd.f[5] = lb.hi[2];
         nd.f[6] = rb.lo[0]; nd.f[7] = rb.lo[1]; nd.f[8] = rb.lo[2]; nd.f[9] = rb.hi[0]; nd.f[10] = rb.hi[1]; nd.f[11] = rb.hi[2];
         nd.child[0] = lc; nd.child[1] = rc; nd.child[2] = nd.child[3] = 0;
         return id;
     }
+    static constexpr int kForkMin = 8192;     // both children at least this large before a thread is worth starting
 };
 
 }  // namespace
 
-void build_sah_bvh(const float* tri_local, const int32_t* tri_mesh, int n_tri, const float* mesh_origin3, HostBvh* out)
+void build_sah_bvh(const float* tri_local, const int32_t* tri_mesh, int n_tri, const float* mesh_origin3, HostBvh* out, int max_threads,
+                   const std::atomic<bool>* cancel)
 {
     out->nodes.clear(); out->slots.clear(); out->max_depth = 0; out->max_abs = 0.0f;
     if (n_tri <= 0) return;
@@ -130,13 +164,18 @@ void build_sah_bvh(const float* tri_local, const int32_t* tri_mesh, int n_tri, c
         b.order[t] = t;
     }
     if (n_tri >= 2) {
-        b.nodes.reserve((size_t)n_tri);
+        b.nodes.resize((size_t)n_tri - 1);
+        int threads = max_threads > 0 ? max_threads : (int)std::thread::hardware_concurrency();
+        threads = threads < 1 ? 1 : (threads > 32 ? 32 : threads);
+        b.spare_threads.store(threads - 1);
+        b.cancel = cancel;
         Box root;
-        const int r = b.build(0, n_tri, 0, &root);
+        const int r = b.build(0, n_tri, 0, 0, &root);
+        if (b.failed.load()) throw std::runtime_error("sah builder: a worker thread failed or the build was cancelled");
         if (r != 0) throw std::runtime_error("sah builder: root is not node 0");
     }
     out->nodes.swap(b.nodes);
-    out->max_depth = b.max_depth;
+    out->max_depth = b.max_depth.load();
     out->slots.resize((size_t)n_tri);
     for (int k = 0; k < n_tri; k++) {
         const int t = b.order[k];

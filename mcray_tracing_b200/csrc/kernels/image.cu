@@ -358,6 +358,9 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate(const Sce
 #endif
 // A window finishes MCRT_WIN_ROWS rows; an unrolled block only has to START inside the window, its last rows may run
 // up to MCRT_WIN_UNROLL - 1 rows ahead into the ring's slack (they belong to the next window and stay in the ring).
+#ifndef MCRT_WIN_EDGE_SKIP
+#define MCRT_WIN_EDGE_SKIP 1       // a lane whose next unrolled block starts beyond the window waits for the next window at once (see the checked-step loop)
+#endif
 #define MCRT_WIN_ROWS (MCRT_WIN_RING - MCRT_WIN_UNROLL)
 #define MCRT_WIN_SLOT(row) ((row) & (MCRT_WIN_RING - 1))
 
@@ -628,6 +631,15 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
                         const double f0 = time_elapsed * inv_row_period - (double)row_now;
                         if (fast_rows && f0 >= 1e-6 && f0 <= block_safe_hi && row_now >= cur_row) break;
                     }
+#if MCRT_WIN_EDGE_SKIP
+                    else if (fast_rows && row_now >= wend && row_now < rows) {
+                        // the common way out of the block loop: the next echo lies in a later window.  Under the guard on f0 row_now IS the row
+                        // try_echo would compute, so the checked step below would load its voxel, form the echo and learn that nothing can be
+                        // consumed; say so here (kept out of the block loop: any state added there costs registers the kernel does not have)
+                        const double f0 = time_elapsed * inv_row_period - (double)row_now;
+                        if (f0 >= 1e-6 && f0 <= 1.0 - 1e-6) { if (TREE) pend_row = row_now; waiting = true; break; }
+                    }
+#endif
                 }
                 const float2 vox = __ldg(&volume[FMADIV ? (fma_ok ? voxel_linear_fma(point, vres, inv_vres) : voxel_linear_exact(point.x, point.y, point.z, vres))
                                                          : voxel_linear(point, vres, inv_vres)]);

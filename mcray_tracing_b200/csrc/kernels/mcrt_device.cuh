@@ -49,6 +49,15 @@ struct __align__(16) BvhNode { float4 a, b, c; int4 d; };
                               // deeper entries in local memory.  Measured slower with N = 8 (trace +6.7 %, same file): the range check per
                               // push / pop costs more ALU issue slots than the L1-resident local-memory stack ever waited for
 #endif
+#ifndef MCRT_STACK_CULL4
+#define MCRT_STACK_CULL4 0    // 1 (4-wide, sorted traversal): a stack entry is the 64-bit pair (child reference, entry parameter), written with one
+                              // STL.64; a popped entry whose entry parameter already lies beyond the current best hit -- by the very test its parent's
+                              // visit applied -- is dropped without fetching the node
+#endif
+#ifndef MCRT_FOLD_SLACK
+#define MCRT_FOLD_SLACK 0     // 1: the relative slack of the interval test (1 + 2e-6) is folded into the ray's far-plane constants at set-up
+                              // instead of one FFMA per child box and visit
+#endif
 #define MCRT_TRACE_THREADS 128            // CTA size of every kernel that traverses (stride of the shared-memory stack)
 #ifndef MCRT_BVH4_SORT
 #define MCRT_BVH4_SORT 1      // 1: the hit children of a node are visited in entry order; 0: nearest first, the rest in slot order
@@ -320,6 +329,10 @@ struct RayBox {
     float ofx, ofy, ofz;   // origin for the far plane
 #endif
     float ix, iy, iz;      // 1 / (to - from)
+#if MCRT_FOLD_SLACK
+    float sfx, sfy, sfz;   // ix, iy, iz times (1 + 2e-6) and ...
+    float scx, scy, scz;   // ... cfx, cfy, cfz times (1 + 2e-6): far planes that carry the interval test's relative slack (4-wide traversal)
+#endif
     bool px, py, pz;       // inv >= 0
 };
 
@@ -343,6 +356,10 @@ __device__ __forceinline__ RayBox make_raybox(float3 from_w, float3 to_w, float 
     r.cnx = -((r.px ? from_w.x + e : from_w.x - e) * r.ix); r.cfx = -((r.px ? from_w.x - e : from_w.x + e) * r.ix);
     r.cny = -((r.py ? from_w.y + e : from_w.y - e) * r.iy); r.cfy = -((r.py ? from_w.y - e : from_w.y + e) * r.iy);
     r.cnz = -((r.pz ? from_w.z + e : from_w.z - e) * r.iz); r.cfz = -((r.pz ? from_w.z - e : from_w.z + e) * r.iz);
+#if MCRT_FOLD_SLACK
+    r.sfx = r.ix * 1.000002f; r.sfy = r.iy * 1.000002f; r.sfz = r.iz * 1.000002f;
+    r.scx = r.cfx * 1.000002f; r.scy = r.cfy * 1.000002f; r.scz = r.cfz * 1.000002f;
+#endif
 #else
     r.onx = r.px ? from_w.x + e : from_w.x - e; r.ofx = r.px ? from_w.x - e : from_w.x + e;
     r.ony = r.py ? from_w.y + e : from_w.y - e; r.ofy = r.py ? from_w.y - e : from_w.y + e;
@@ -469,12 +486,18 @@ __device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __
         const unsigned onx = rb.px ? 0u : 48u, ofx = rb.px ? 48u : 0u;   // byte offsets of lox / hix
         const unsigned ony = rb.py ? 16u : 64u, ofy = rb.py ? 64u : 16u;
         const unsigned onz = rb.pz ? 32u : 80u, ofz = rb.pz ? 80u : 32u;
+#if MCRT_STACK_CULL4
+        unsigned long long stack4[MCRT_STACK_DEPTH4];   // (entry parameter bits << 32) | child reference
+#else
         int stack4[MCRT_STACK_DEPTH4];
+#endif
         int sp4 = 0;
         int node4 = 0;
 #if MCRT_SMEM_STACK > 0
 #define MCRT_PUSH(v) { if (sp4 < MCRT_SMEM_STACK) s_stack[sp4 * MCRT_TRACE_THREADS] = (v); else stack4[sp4 - MCRT_SMEM_STACK] = (v); sp4++; }
 #define MCRT_POP() (--sp4, sp4 < MCRT_SMEM_STACK ? s_stack[sp4 * MCRT_TRACE_THREADS] : stack4[sp4 - MCRT_SMEM_STACK])
+#elif MCRT_STACK_CULL4
+#define MCRT_PUSH_T(v, tt) { stack4[sp4++] = ((unsigned long long)__float_as_uint(tt) << 32) | (unsigned long long)(unsigned)(v); }
 #else
 #define MCRT_PUSH(v) { stack4[sp4++] = (v); }
 #define MCRT_POP() (stack4[--sp4])
@@ -495,7 +518,11 @@ __device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __
                 const float4 ny = __ldg(reinterpret_cast<const float4*>(nd | ony)), fy = __ldg(reinterpret_cast<const float4*>(nd | ofy));
                 const float4 nz = __ldg(reinterpret_cast<const float4*>(nd | onz)), fz = __ldg(reinterpret_cast<const float4*>(nd | ofz));
                 const int4 ch = __ldg(reinterpret_cast<const int4*>(nd) + 6);
+#if MCRT_FOLD_SLACK
+                const float tb = best.fraction * 1.0000041f;     // (1 + 2e-6)^2 rounded up: the slack of the best hit and of the interval test
+#else
                 const float tb = best.fraction * 1.000002f;
+#endif
                 float t[4];
                 int c[4] = {ch.x, ch.y, ch.z, ch.w};
                 {
@@ -503,6 +530,16 @@ __device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __
                     const float f0[4] = {fx.x, fx.y, fx.z, fx.w}, f1[4] = {fy.x, fy.y, fy.z, fy.w}, f2[4] = {fz.x, fz.y, fz.z, fz.w};
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
+#if MCRT_FOLD_SLACK
+                        // the far planes are evaluated with constants that already carry the factor (1 + 2e-6): tf here IS tf * 1.000002 of the
+                        // other branch up to one rounding (the slack is 17 ulp), and a box whose far side lies behind the origin still misses
+                        const float t0x = __fmaf_rn(n0[k], rb.ix, rb.cnx), t1x = __fmaf_rn(f0[k], rb.sfx, rb.scx);
+                        const float t0y = __fmaf_rn(n1[k], rb.iy, rb.cny), t1y = __fmaf_rn(f1[k], rb.sfy, rb.scy);
+                        const float t0z = __fmaf_rn(n2[k], rb.iz, rb.cnz), t1z = __fmaf_rn(f2[k], rb.sfz, rb.scz);
+                        const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+                        const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tb));
+                        t[k] = (tn <= tf) ? tn : 3.0e38f;
+#else
                         // (the clamp of the entry parameter at 0 cannot ride on an FFMA as its saturate modifier: an axis-parallel ray
                         // outside a box's slab has t0 = +1e30, which .SAT would turn into 1 -- a hit while nothing closer is known:
                         // 17.5 -> 21.7 node visits per query, profiles/r02e_ab_fma_addresses_sat.txt)
@@ -513,6 +550,7 @@ __device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __
                         const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tb));
                         // empty slots (inverted box) give tn = +inf / NaN-free miss; a miss sorts last
                         t[k] = (tn <= __fmaf_rn(tf, 1.000002f, 1e-37f)) ? tn : 3.0e38f;      // an empty slot's inverted box never passes
+#endif
                     }
                 }
 #if MCRT_BVH4_SORT
@@ -525,9 +563,15 @@ __device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __
                     // nearest first; the others go on the stack far-to-near so the nearer one is popped first.  Every pushed
                     // reference WILL be fetched when it is popped (there is no culling on the stack), so its cache line is
                     // requested now: one LSU instruction that turns an L2 round trip at pop time into an L1 hit.
+#if MCRT_STACK_CULL4
+                    if (t[3] < 3.0e38f) MCRT_PUSH_T(c[3], t[3]);
+                    if (t[2] < 3.0e38f) MCRT_PUSH_T(c[2], t[2]);
+                    if (t[1] < 3.0e38f) MCRT_PUSH_T(c[1], t[1]);
+#else
                     if (t[3] < 3.0e38f) { MCRT_PUSH(c[3]); MCRT_PREFETCH_REF(c[3]); }
                     if (t[2] < 3.0e38f) { MCRT_PUSH(c[2]); MCRT_PREFETCH_REF(c[2]); }
                     if (t[1] < 3.0e38f) { MCRT_PUSH(c[1]); MCRT_PREFETCH_REF(c[1]); }
+#endif
                     node4 = c[0];
                     continue;
                 }
@@ -552,8 +596,27 @@ __device__ __forceinline__ void closest_hit(const SceneDev& sc, const float4* __
                 tri_tests += count;
                 for (int k = 0; k < count; k++) tri_test(sc.tris, first + k, s_mesh, from_w, to_w, best);
             }
+#if MCRT_STACK_CULL4
+            // pop; an entry whose box the ray enters beyond the best hit found since it was pushed is dropped unfetched.  The bound is
+            // the one its parent's visit would apply now (entry parameter <= min(far planes, best * s) * s implies <= best * s * s),
+            // so nothing is culled here that the visit itself would not cull child by child
+            {
+#if MCRT_FOLD_SLACK
+                const float tcull = best.fraction * 1.0000041f;
+#else
+                const float tcull = __fmaf_rn(best.fraction * 1.000002f, 1.000002f, 1e-37f);
+#endif
+                bool found = false;
+                while (sp4 > 0) {
+                    const unsigned long long e = stack4[--sp4];
+                    if (__uint_as_float((unsigned)(e >> 32)) <= tcull) { node4 = (int)(unsigned)e; found = true; break; }
+                }
+                if (!found) break;
+            }
+#else
             if (sp4 == 0) break;
             node4 = MCRT_POP();
+#endif
         }
         return;
     }

@@ -26,6 +26,10 @@ def run(sim, poses, label):
     sim.set_option("max_batch_poses", n)
     for k, v in opts:
         sim.set_option(k, v)
+    try:
+        sim.set_option("bvh_wait", 1)          # (older A/B libraries do not know the option)
+    except Exception:
+        pass
     sim.set_option("profile_stages", 1)
     acc = []
     for k in range(7):

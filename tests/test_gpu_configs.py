@@ -163,6 +163,67 @@ def test_traversal_options_do_not_change_results(api, O):
         assert st.bvh_node_visits > st.segments and st.bvh_triangle_tests > 0
 
 
+def test_background_tree_optimisation(api, tmp_path, monkeypatch):
+    """mcrt.h "bvh_optimise": the device LBVH serves a new or changed scene at once, a host thread builds the binned-SAH tree and a later
+    compute call adopts it.  Frames never depend on which tree is in use; the optimised tree is visited with fewer node fetches; mesh
+    updates fall back to the LBVH and the scene is optimised again once it has been left alone; $MCRT_BVH_CACHE keeps the tree."""
+    from mcray_tracing_b200 import assets
+    A = assets.stress_scene_arrays(shells=4, nu=128, nv=64)                   # 65 536 triangles (the optimiser starts at 32 768)
+    pose = np.concatenate([A["transducer_position"], A["transducer_angles"]])
+    poses = np.repeat(pose[None, :], 4, axis=0)
+    kw = dict(elements=64, samples=4)
+
+    def visits(sim):
+        sim.set_option("count_traversal", 1)
+        sim.simulate(poses, seed=3, first_frame=0)
+        v = sim.stats().bvh_node_visits
+        sim.set_option("count_traversal", 0)
+        return v
+
+    monkeypatch.setenv("MCRT_BVH_OPTIMISE", "0")
+    with api.Simulator(A, api.default_params(**kw)) as plain:
+        ref = plain.simulate(poses, seed=3, first_frame=0)
+        plain.set_option("bvh_wait", 1)                                       # nothing to wait for
+        assert plain.get_info().bvh_optimised == 0
+        v_plain = visits(plain)
+        plain.set_option("bvh_optimise", 1)                                   # switched on later
+        plain.set_option("bvh_wait", 1)
+        assert plain.get_info().bvh_optimised == 1
+        assert np.array_equal(plain.simulate(poses, seed=3, first_frame=0), ref)
+    monkeypatch.delenv("MCRT_BVH_OPTIMISE")
+    with api.Simulator(A, api.default_params(**kw)) as sim:
+        assert np.array_equal(sim.simulate(poses, seed=3, first_frame=0), ref)       # whichever tree is in use by now
+        sim.set_option("bvh_wait", 1)
+        assert sim.get_info().bvh_optimised == 1
+        assert np.array_equal(sim.simulate(poses, seed=3, first_frame=0), ref)
+        segs, nseg = sim.cast_rays(pose, seed=3, frame=0)
+        v_opt = visits(sim)
+        assert v_opt < 0.97 * v_plain, (v_opt, v_plain)
+        # a mesh update: the LBVH of the new scene at once ...
+        sim.set_mesh_origin(1, np.array([0.5, -0.3, 0.2], np.float32))
+        moved = sim.simulate(poses, seed=3, first_frame=0)
+        assert sim.get_info().bvh_optimised == 0 and not np.array_equal(moved, ref)
+        # ... the optimiser again after eight calls on the unchanged scene
+        for _ in range(9):
+            assert np.array_equal(sim.simulate(poses, seed=3, first_frame=0), moved)
+        sim.set_option("bvh_wait", 1)
+        assert sim.get_info().bvh_optimised == 1
+        assert np.array_equal(sim.simulate(poses, seed=3, first_frame=0), moved)
+        sim.set_option("bvh_optimise", 0)                                     # and back to the plain LBVH
+        assert sim.get_info().bvh_optimised == 0
+        assert np.array_equal(sim.simulate(poses, seed=3, first_frame=0), moved)
+    monkeypatch.setenv("MCRT_BVH_CACHE", str(tmp_path))
+    with api.Simulator(A, api.default_params(**kw)) as first:
+        first.set_option("bvh_wait", 1)
+        assert first.get_info().bvh_optimised == 1 and len(list(tmp_path.glob("sah_*.bvh"))) == 1
+    with api.Simulator(A, api.default_params(**kw)) as second:               # adopts the validated cached tree, no build
+        second.set_option("bvh_wait", 1)
+        assert second.get_info().bvh_optimised == 1
+        assert np.array_equal(second.simulate(poses, seed=3, first_frame=0), ref)
+        s2, n2 = second.cast_rays(pose, seed=3, frame=0)
+        assert np.array_equal(n2, nseg) and np.array_equal(s2["tri_id"], segs["tri_id"])
+
+
 def test_log_compression_option(api, O, assets_dirs):
     """The log compression the reference keeps commented out (rfimage.h:127-136), as an option: applied to
     the envelope image, so both rf_out and the scan-converted image change; bit-exact to the oracle."""

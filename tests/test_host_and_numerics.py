@@ -466,3 +466,47 @@ def test_stl_to_obj_weld_and_dump(api, tmp_path):
     convert.convert(tmp_path / "b.stl", tmp_path / "nw.obj", weld_vertices=False)
     assert sum(ln.startswith("v ") for ln in (tmp_path / "nw.obj").read_text().splitlines()) == 3 * len(soup)
     assert np.array_equal(api.load_obj(tmp_path / "nw.obj").reshape(-1, 3, 3), soup)
+
+
+def test_host_sah_builder_is_valid_and_thread_independent(api):
+    """The host tree of the background optimisation (mcrt.h "bvh_optimise"; sah_builder.cpp): a valid BVH2 -- pre-order ids, every triangle
+    in exactly one leaf, every child box the exact union of what lies below it -- that does not depend on the number of threads
+    (subtrees are forked from 8192 triangles up, so a 49 152-triangle scene forks several times)."""
+    from mcray_tracing_b200 import assets
+    A = assets.stress_scene_arrays(shells=3, nu=128, nv=64)
+    tri = (A["tri_vertices"] * np.float32(A["scaling"])).astype(np.float32).reshape(-1, 9)
+    offs = A["tri_offsets"]
+    mesh = np.concatenate([np.full(int(offs[m + 1] - offs[m]), m, np.int32) for m in range(len(offs) - 1)])
+    origins = (A["mesh_deltas"] * np.float32(A["scaling"])).astype(np.float32)
+    origins[1] += np.float32(0.37)                                       # body origins enter the world boxes
+    n = len(mesh)
+    nodes1, slots1, depth1 = api.host_build_sah(tri, mesh, origins, threads=1)
+    for threads in (2, 5, 0):
+        nodes, slots, depth = api.host_build_sah(tri, mesh, origins, threads=threads)
+        assert depth == depth1 and np.array_equal(slots, slots1) and nodes.tobytes() == nodes1.tobytes(), threads
+    assert nodes1.shape == (n - 1, 16) and sorted(slots1.tolist()) == list(range(n)) and 16 <= depth1 <= 96
+    child = nodes1[:, 12:14].copy().view(np.int32)
+    world = tri.reshape(n, 3, 3) + origins[mesh][:, None, :]
+    lo, hi = world.min(axis=1), world.max(axis=1)
+    # bottom-up in reverse pre-order: children always have larger ids than their parent
+    box_lo, box_hi = np.empty((n - 1, 3), np.float32), np.empty((n - 1, 3), np.float32)
+    seen_nodes, seen_slots = np.zeros(n - 1, bool), np.zeros(n, bool)
+    for i in range(n - 2, -1, -1):
+        los, his = [], []
+        for k in range(2):
+            ch = int(child[i, k])
+            if ch >= 0:
+                assert i < ch < n - 1 and not seen_nodes[ch]
+                seen_nodes[ch] = True
+                l, h = box_lo[ch], box_hi[ch]
+            else:
+                code = -ch - 1
+                slot = code >> 2
+                assert code & 3 == 0 and 0 <= slot < n and not seen_slots[slot]
+                seen_slots[slot] = True
+                l, h = lo[slots1[slot]], hi[slots1[slot]]
+            assert np.array_equal(nodes1[i, 6 * k:6 * k + 3], l) and np.array_equal(nodes1[i, 6 * k + 3:6 * k + 6], h), (i, k)
+            los.append(l); his.append(h)
+        box_lo[i], box_hi[i] = np.minimum(los[0], los[1]), np.maximum(his[0], his[1])
+    assert seen_slots.all() and seen_nodes[1:].all() and not seen_nodes[0]
+    assert int(child[0, 0]) == 1                                          # pre-order: the left child of the root follows it
