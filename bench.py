@@ -465,7 +465,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # poses from host memory and lands its RF frames in pinned host memory, but the PCIe copy of step k
     # overlaps the simulation of step k+1 (separate copy stream, ring of 3 pinned buffers)
     from mcray_tracing_b200 import stream as mstream
-    fs = mstream.FrameStreamer(sim, depth=3, frames_per_submit=F, seed=seed)
+    e2e_sub = max(1, min(int(args.e2e_sub_batches), F))
+    fs = mstream.FrameStreamer(sim, depth=3, frames_per_submit=F, seed=seed, sub_batches=e2e_sub, frame_stride=stride)
 
     def stream_steps(n_steps: int, k0: int) -> float:
         submitted, chk = 0, 0.0
@@ -705,7 +706,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "segments_per_step": float(segs_all.item()), "march_steps_per_step_per_gpu": march_per_step,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(F * 24 + 16), "d2h_bytes_per_step": int(d2h_bytes),
                     "timing": "wall clock around K steps through stream.FrameStreamer (mcrt_simulate_async + pinned ring of 3 buffers): "
-                              "per step poses host->device and RF frames device->pinned host, the copy of step k overlapping step k+1",
+                              "per step poses host->device and RF frames device->pinned host, the copy of step k overlapping step k+1"
+                              + (f"; every step is submitted as {e2e_sub} consecutive calls whose copies start as soon as each is computed" if e2e_sub > 1 else ""),
+                    "sub_batches_per_step": e2e_sub,
                     "synchronous_call_value": e2e_sync_value,
                     "synchronous_call_timing": "wall clock around K blocking mcrt_simulate calls with pinned host buffers (no overlap)",
                     "roofline": {"bound": "pcie_d2h", "ceiling_gbs_per_gpu": d2h_gbs_per_gpu, "achieved_gbs_per_gpu": e2e_gbs_per_gpu,
@@ -753,6 +756,7 @@ def main():
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "none"],
                     help="N > 1: peer-memory deposit over NVLink (default), NCCL send/recv gather, or none (diagnostic: no exchange at all, "
                          "the line is marked invalid_for_scaling)")
+    ap.add_argument("--e2e-sub-batches", type=int, default=2, help="e2e leg: calls per step of the streaming driver (stream.FrameStreamer sub_batches)")
     ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE", help="development A/B: mcrt_set_option before the run (recorded in config.options)")
     ap.add_argument("--contiguous", action="store_true", help="N > 1: contiguous pose blocks per rank instead of the round-robin deal")
     args = ap.parse_args()

@@ -7,6 +7,10 @@ copied into a ring of PINNED host buffers on a second (copy) stream that waits o
 frame k+1 is being traced while frame k is still travelling over PCIe; `get()` only waits for the event
 of the frame it returns.
 The pipeline depth bounds the latency: a frame is at most `depth` submissions behind.
+With `sub_batches` > 1 a submission is simulated as that many consecutive calls and every part starts its
+PCIe copy as soon as it is computed, while the next part is being simulated: the copy that nothing can
+overlap (the last one of a run) shrinks to one part.  Frames are pure functions of (pose, seed, frame
+index), so the split does not change them.
 """
 from __future__ import annotations
 
@@ -20,11 +24,16 @@ from . import api
 
 class FrameStreamer:
     def __init__(self, sim: api.Simulator, depth: int = 3, frames_per_submit: int = 1, scan: bool = False, seed: int = 0,
-                 device: int | None = None):
+                 device: int | None = None, sub_batches: int = 1, frame_stride: int = 1):
         if depth < 2:
             raise ValueError("depth must be >= 2 (one frame in flight while one is read)")
         self.sim = sim
         self.n = int(frames_per_submit)
+        if not 1 <= int(sub_batches) <= self.n:
+            raise ValueError("sub_batches must be in [1, frames_per_submit]")
+        # part boundaries (as even as possible); frame_stride = the context's "frame_stride" option (pose i of a call is frame first + i * stride)
+        self._parts = [(k * self.n // int(sub_batches), (k + 1) * self.n // int(sub_batches)) for k in range(int(sub_batches))]
+        self.frame_stride = int(frame_stride)
         self.scan = bool(scan)
         self.seed = int(seed)
         self.dev = torch.device("cuda", sim.info.device if device is None else device)
@@ -56,14 +65,16 @@ class FrameStreamer:
             raise RuntimeError("pipeline full: call get() before submitting more frames")
         s = self._free.popleft()
         slot = self._slots[s]
-        self.sim.simulate_device(P, slot["rf_dev"].data_ptr(), seed=self.seed, first_frame=self._frame,
-                                 scan_ptr=slot["scan_dev"].data_ptr() if self.scan else None, stream=self.stream.cuda_stream, sync=False)
-        slot["computed"].record(self.stream)
+        for a, b in self._parts:
+            self.sim.simulate_device(P[a:b], slot["rf_dev"][a:].data_ptr(), seed=self.seed, first_frame=self._frame + a * self.frame_stride,
+                                     scan_ptr=slot["scan_dev"][a:].data_ptr() if self.scan else None, stream=self.stream.cuda_stream, sync=False)
+            slot["computed"].record(self.stream)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(slot["computed"])
+                slot["rf_host"][a:b].copy_(slot["rf_dev"][a:b], non_blocking=True)
+                if self.scan:
+                    slot["scan_host"][a:b].copy_(slot["scan_dev"][a:b], non_blocking=True)
         with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(slot["computed"])
-            slot["rf_host"].copy_(slot["rf_dev"], non_blocking=True)
-            if self.scan:
-                slot["scan_host"].copy_(slot["scan_dev"], non_blocking=True)
             slot["done"].record(self.copy_stream)
         self._frame += self.n
         self._ticket += 1

@@ -255,9 +255,17 @@ def test_streaming_driver_matches_batched_call(api, assets_dirs):
         got, got_scan, tickets = [], [], []
         fs = stream.FrameStreamer(sim, depth=3, frames_per_submit=2, scan=True, seed=3)
         fs.run(stream.sweep_pose_stream(poses, 2), lambda t, rf, sc: (tickets.append(t), got.append(rf.copy()), got_scan.append(sc.copy())))
+        # the same with every submission of 7 poses simulated as 3 consecutive calls (sizes 2, 2, 3) whose copies start as soon as each
+        # part is computed: the split must not show in the result
+        got3, got3_scan = [], []
+        fs3 = stream.FrameStreamer(sim, depth=2, frames_per_submit=7, scan=True, seed=3, sub_batches=3)
+        fs3.run(stream.sweep_pose_stream(poses, 7), lambda t, rf, sc: (got3.append(rf.copy()), got3_scan.append(sc.copy())))
+        with pytest.raises(ValueError):
+            stream.FrameStreamer(sim, depth=2, frames_per_submit=2, sub_batches=3)
     assert tickets == list(range(1, 8))
     assert np.array_equal(np.concatenate(got), ref)
     assert np.array_equal(np.concatenate(got_scan), ref_scan)
+    assert np.array_equal(np.concatenate(got3), ref) and np.array_equal(np.concatenate(got3_scan), ref_scan)
 
 
 def test_entry_points_on_different_streams_are_ordered(api, assets_dirs):
