@@ -361,6 +361,9 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate(const Sce
 #ifndef MCRT_WIN_EDGE_SKIP
 #define MCRT_WIN_EDGE_SKIP 1       // a lane whose next unrolled block starts beyond the window waits for the next window at once (see the checked-step loop)
 #endif
+#ifndef MCRT_WIN_TAIL_BLOCK
+#define MCRT_WIN_TAIL_BLOCK 2      // > 0: segment tails of at least this many steps are taken as one masked unrolled block (see the kernel)
+#endif
 #define MCRT_WIN_ROWS (MCRT_WIN_RING - MCRT_WIN_UNROLL)
 #define MCRT_WIN_SLOT(row) ((row) & (MCRT_WIN_RING - 1))
 
@@ -620,6 +623,47 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
                 n_safe -= MCRT_WIN_UNROLL; remaining -= MCRT_WIN_UNROLL;
                 my_steps += MCRT_WIN_UNROLL;
             }
+#if MCRT_WIN_TAIL_BLOCK
+            // ---- tail block: the last m < MCRT_WIN_UNROLL steps of a segment that ends by its step budget (remaining == n_safe), taken like an
+            // unrolled block -- all volume loads in flight together, rows row0 + u under the same guard -- instead of m checked steps with an
+            // exposed load each.  The warp pays for the LONGEST tail among its lanes, so up to seven serial checked steps become one block.  The
+            // steps beyond m are computed and dropped: indices wrap inside the volume, and the march state (point, time, intensity) is dead once
+            // the segment has ended -- the closing echo uses end_micros and the next segment reloads everything.
+            if (n_safe >= MCRT_WIN_TAIL_BLOCK && n_safe < MCRT_WIN_UNROLL && remaining == n_safe && FMADIV && fma_ok) {
+                const double rowd0 = time_elapsed * inv_row_period;
+                const int row0 = __double2int_rd(rowd0);
+                const double f0 = rowd0 - (double)row0;
+                if (fast_rows && f0 >= 1e-6 && f0 <= block_safe_hi && row0 < wend && row0 + MCRT_WIN_UNROLL <= rows && row0 >= base && row0 >= cur_row) {
+                    const int m = n_safe;
+                    uint32_t idx[MCRT_WIN_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < MCRT_WIN_UNROLL; u++) { idx[u] = voxel_linear_fma(point, vres, inv_vres); point = v_add(point, delta_step); }
+                    float2 vox[MCRT_WIN_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < MCRT_WIN_UNROLL; u++) vox[u] = __ldg(&volume[idx[u]]);
+                    float echo[MCRT_WIN_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < MCRT_WIN_UNROLL; u++) {
+                        const float scattering = vox[u].y >= m_mu1 ? vox[u].x * m_sigma + m_mu0 : 0.0f;
+                        echo[u] = intensity * scattering;
+                        intensity *= decay;
+                    }
+                    add_row(echo[0], row0);
+                    for (int r = written > base ? written : base; r < row0; r++) my_col[MCRT_WIN_SLOT(r) * stride] = 0.0f;   // gap (time jumped ahead)
+#pragma unroll
+                    for (int u = 1; u < MCRT_WIN_UNROLL; u++) {
+                        if (u < m) {
+                            my_col[MCRT_WIN_SLOT(row0 + u - 1) * stride] = cur_acc;
+                            cur_acc = echo[u];
+                        }
+                    }
+                    written = row0 + m - 1;
+                    cur_row = row0 + m - 1;
+                    my_steps += m;
+                    remaining = 0; n_safe = 0;
+                }
+            }
+#endif
             // ---- single checked steps: window edges, guard bands, the tail of the segment ----
             bool seg_done = false;
             while (true) {
