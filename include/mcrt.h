@@ -296,7 +296,7 @@ int mcrt_host_tables(const mcrt_params* params, mcrt_info* info, float* elem_sin
  * n_triangles triangles (9 floats each, mesh-local; world = local + mesh_origin3[mesh]).  nodes16: (n_triangles - 1) x 16 words =
  * {child0 lo.xyz hi.xyz, child1 lo.xyz hi.xyz} as float + {child0, child1, 0, 0} as int32 (child >= 0: node index, pre-order, root 0;
  * child < 0: leaf slot -(1 + 4 * slot)); slot_triangle: the triangle of every leaf slot.  threads <= 0: all host threads; the
- * tree does not depend on it.  Replaces the Bullet btBvhTriangleMeshShape build of scene.cpp:319-330. */
+ * tree does not depend on it.  Replaces the Bullet btBvhTriangleMeshShape build of scene.cpp:309. */
 int mcrt_host_build_sah(const float* tri_local9, const int32_t* tri_mesh, int64_t n_triangles, const float* mesh_origin3, int32_t n_meshes,
                         int32_t threads, float* nodes16, int32_t* slot_triangle, int32_t* max_depth);
 
