@@ -361,6 +361,9 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate(const Sce
 #ifndef MCRT_WIN_EDGE_SKIP
 #define MCRT_WIN_EDGE_SKIP 1       // a lane whose next unrolled block starts beyond the window waits for the next window at once (see the checked-step loop)
 #endif
+#ifndef MCRT_WIN_PIN_COL
+#define MCRT_WIN_PIN_COL 0         // 1: the lane's ring-column address is pinned in a register (compile-time sample count only)
+#endif
 #ifndef MCRT_WIN_TAIL_BLOCK
 #define MCRT_WIN_TAIL_BLOCK 2      // > 0: segment tails of at least this many steps are taken as one masked unrolled block (see the kernel)
 #endif
@@ -469,6 +472,12 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
     int written = 0, cur_row = -1;
     float cur_acc = 0.0f;
     float* const my_col = s_win + t;
+#if MCRT_WIN_PIN_COL
+    // the shared-memory address of the lane's column, held in a register: left to itself the compiler re-derives it from the thread index
+    // (nine instructions) in front of the ring stores of every unrolled block
+    unsigned col_addr = (unsigned)__cvta_generic_to_shared(my_col);
+    asm volatile("" : "+r"(col_addr));
+#endif
 
     for (int base = 0; base < rows; base += MCRT_WIN_ROWS) {
         const int wend = base + MCRT_WIN_ROWS < rows ? base + MCRT_WIN_ROWS : rows;
@@ -593,10 +602,22 @@ __global__ void __launch_bounds__(128, MCRT_ACC_MIN_CTAS) k_accumulate_win(const
                 const bool cont = cur_row + 1 == row0 && written == cur_row && cur_row >= base && slot0 >= 1;
                 const bool fresh = cur_row < 0 && written == row0;
                 if ((cont || fresh) && slot0 + MCRT_WIN_UNROLL <= MCRT_WIN_RING) {
+#if MCRT_WIN_PIN_COL
+                    if (SCT > 0) {
+                        const unsigned dsta = col_addr + (unsigned)slot0 * (unsigned)(36 * 4);
+                        if (cont) asm volatile("st.shared.f32 [%0+-144], %1;" :: "r"(dsta), "f"(cur_acc) : "memory");
+                        static_assert(MCRT_WIN_UNROLL == 8, "seven pinned ring stores");
+#define MCRT_PIN_ST(u) asm volatile("st.shared.f32 [%0+%2], %1;" :: "r"(dsta), "f"(echo[u]), "n"((u) * 144) : "memory");
+                        MCRT_PIN_ST(0) MCRT_PIN_ST(1) MCRT_PIN_ST(2) MCRT_PIN_ST(3) MCRT_PIN_ST(4) MCRT_PIN_ST(5) MCRT_PIN_ST(6)
+#undef MCRT_PIN_ST
+                    } else
+#endif
+                    {
                     float* dst = my_col + slot0 * stride;
                     if (cont) dst[-stride] = cur_acc;
 #pragma unroll
                     for (int u = 0; u < MCRT_WIN_UNROLL - 1; u++) dst[u * stride] = echo[u];
+                    }
                     cur_acc = echo[MCRT_WIN_UNROLL - 1];
                 } else {
                     add_row(echo[0], row0);
