@@ -1127,7 +1127,10 @@ static void ensure_scene_current(mcrt_ctx* c)
     if (!c->scene_dirty) {
         bg_tree_adopt(c, false);
         // after mesh updates the optimiser waits for 8 compute calls on an unchanged scene before it starts again
-        if (!c->bvh_optimised && c->bvh_optimise && c->bvh_builder == 0 && ++c->quiet_calls >= 8) bg_tree_start(c);
+        if (!c->bvh_optimised && c->bvh_optimise && c->bvh_builder == 0) {
+            if (c->quiet_calls < 8) c->quiet_calls++;
+            if (c->quiet_calls >= 8) bg_tree_start(c);
+        }
         return;
     }
     c->quiet_calls = 0;
