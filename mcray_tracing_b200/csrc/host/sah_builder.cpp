@@ -49,37 +49,92 @@ struct Builder {
         while (d > cur && !max_depth.compare_exchange_weak(cur, d, std::memory_order_relaxed)) {}
     }
 
+    // up to `want` spare threads for the caller; give them back with release()
+    int claim(int want)
+    {
+        int got = 0;
+        while (got < want) {
+            if (spare_threads.fetch_sub(1, std::memory_order_relaxed) > 0) got++;
+            else { spare_threads.fetch_add(1, std::memory_order_relaxed); break; }
+        }
+        return got;
+    }
+    void release(int n) { if (n > 0) spare_threads.fetch_add(n, std::memory_order_relaxed); }
+
+    // fn(k, lo, hi) over extra + 1 contiguous chunks of [first, first + count): chunk 0 on the calling thread, the others on their own
+    template <class F>
+    void chunked(int first, int count, int extra, F&& fn)
+    {
+        const int parts = extra + 1;
+        auto cut = [&](int k) { return first + (int)((long long)count * k / parts); };
+        std::vector<std::thread> th;
+        for (int k = 1; k < parts; k++)
+            th.emplace_back([&, k]() { try { fn(k, cut(k), cut(k + 1)); } catch (...) { failed.store(true); } });
+        try { fn(0, cut(0), cut(1)); } catch (...) { failed.store(true); }
+        for (auto& t : th) t.join();
+    }
+
+    static constexpr int NB = 16;              // bins per axis
+    static constexpr int kChunkMin = 65536;    // nodes from this size up bin their triangles in parallel chunks ...
+    static constexpr int kChunkMax = 7;        // ... on at most this many extra threads
+    struct Bins { Box box[3][NB]; int cnt[3][NB]; };
+
     // builds the subtree of order[first, first + count) into nodes[id ...]; returns the child reference of its root:
     // >= 0 internal node index, < 0 leaf -(1 + slot*4)
     int build(int first, int count, int depth, int id, Box* out_box)
     {
+        // Large nodes (the top levels, where a single thread would otherwise walk every triangle of the scene) take their two passes over the
+        // triangles in parallel chunks.  Chunk results are merged with min / max / integer adds only, so the bins -- and the tree -- are the
+        // same for any number of chunks.
+        const int extra = count >= kChunkMin ? claim(kChunkMax) : 0;
         Box bb; bb.reset();
         Box cb; cb.reset();
-        for (int i = first; i < first + count; i++) {
-            const int t = order[i];
-            bb.grow(tri_box[t]);
-            for (int a = 0; a < 3; a++) { cb.lo[a] = std::min(cb.lo[a], cent[3 * (size_t)t + a]); cb.hi[a] = std::max(cb.hi[a], cent[3 * (size_t)t + a]); }
+        {
+            Box pbb[kChunkMax + 1], pcb[kChunkMax + 1];
+            chunked(first, count, extra, [&](int k, int lo, int hi) {
+                Box b1; b1.reset();
+                Box c1; c1.reset();
+                for (int i = lo; i < hi; i++) {
+                    const int t = order[i];
+                    b1.grow(tri_box[t]);
+                    for (int a = 0; a < 3; a++) { c1.lo[a] = std::min(c1.lo[a], cent[3 * (size_t)t + a]); c1.hi[a] = std::max(c1.hi[a], cent[3 * (size_t)t + a]); }
+                }
+                pbb[k] = b1; pcb[k] = c1;
+            });
+            for (int k = 0; k <= extra; k++) { bb.grow(pbb[k]); cb.grow(pcb[k]); }
         }
         *out_box = bb;
-        if (count == 1) return -(1 + first * 4);
-        if (count >= 256 && cancel && cancel->load(std::memory_order_relaxed)) throw std::runtime_error("sah builder: cancelled");
+        if (count == 1) { release(extra); return -(1 + first * 4); }
+        if (count >= 256 && cancel && cancel->load(std::memory_order_relaxed)) { release(extra); throw std::runtime_error("sah builder: cancelled"); }
         note_depth(depth + 1);
         // binned SAH over the centroid bounds
-        const int NB = 16;
+        float scale[3];
+        bool live[3];
+        for (int a = 0; a < 3; a++) { const float ext = cb.hi[a] - cb.lo[a]; live[a] = ext > 0.0f; scale[a] = live[a] ? NB / ext : 0.0f; }
+        Bins own;                                        // chunk 0 (the only one of a small node: no allocation there)
+        std::vector<Bins> others((size_t)extra);
+        chunked(first, count, extra, [&](int k, int lo, int hi) {
+            Bins& bn = k == 0 ? own : others[(size_t)k - 1];
+            for (int a = 0; a < 3; a++) for (int b = 0; b < NB; b++) { bn.box[a][b].reset(); bn.cnt[a][b] = 0; }
+            for (int i = lo; i < hi; i++) {
+                const int t = order[i];
+                for (int a = 0; a < 3; a++) {
+                    if (!live[a]) continue;
+                    int b = (int)((cent[3 * (size_t)t + a] - cb.lo[a]) * scale[a]);
+                    b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+                    bn.box[a][b].grow(tri_box[t]); bn.cnt[a][b]++;
+                }
+            }
+        });
+        release(extra);
+        for (int k = 0; k < extra; k++)
+            for (int a = 0; a < 3; a++) for (int b = 0; b < NB; b++) { own.box[a][b].grow(others[k].box[a][b]); own.cnt[a][b] += others[k].cnt[a][b]; }
         int best_axis = -1, best_bin = -1;
         float best_cost = 3.0e38f;
         for (int a = 0; a < 3; a++) {
-            const float ext = cb.hi[a] - cb.lo[a];
-            if (!(ext > 0.0f)) continue;
-            Box bins[NB]; int cnt[NB];
-            for (int b = 0; b < NB; b++) { bins[b].reset(); cnt[b] = 0; }
-            const float scale = NB / ext;
-            for (int i = first; i < first + count; i++) {
-                const int t = order[i];
-                int b = (int)((cent[3 * (size_t)t + a] - cb.lo[a]) * scale);
-                b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
-                bins[b].grow(tri_box[t]); cnt[b]++;
-            }
+            if (!live[a]) continue;
+            const Box* bins = own.box[a];
+            const int* cnt = own.cnt[a];
             float right_area[NB]; int right_cnt[NB];
             Box acc; acc.reset(); int c = 0;
             for (int b = NB - 1; b >= 1; b--) { acc.grow(bins[b]); c += cnt[b]; right_area[b] = acc.area(); right_cnt[b] = c; }
@@ -93,12 +148,11 @@ struct Builder {
         }
         int mid;
         if (best_axis >= 0 && depth < 40) {      // beyond depth 40 fall back to balanced splits: bounds the stack
-            const float ext = cb.hi[best_axis] - cb.lo[best_axis];
-            const float scale = NB / ext;
+            const float bscale = scale[best_axis];
             const float lo = cb.lo[best_axis];
             // stable: the triangle order inside a leaf range (and with it the tree) does not depend on the library's partition algorithm
             auto it = std::stable_partition(order.begin() + first, order.begin() + first + count, [&](int32_t t) {
-                int b = (int)((cent[3 * (size_t)t + best_axis] - lo) * scale);
+                int b = (int)((cent[3 * (size_t)t + best_axis] - lo) * bscale);
                 b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
                 return b <= best_bin;
             });
