@@ -572,3 +572,23 @@ def test_closest_hit_agrees_with_an_independent_moller_trumbore(O, assets_dirs):
             assert abs(abs(np.dot(f[4:7], n)) - 1.0) < 1e-4 and np.dot(f[4:7], dd) < 0.0
             checked += 1
     assert checked > 200 and missed > 50
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm) runs without a GPU and prints ONE JSON line with the
+    contract's keys: the metric / unit / config of the GPU arm, `impl`, a `cpu_baseline` describing the run and an `e2e` with no copies."""
+    import json
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    b = json.loads(lines[0])
+    assert b["impl"] == "reference" and b["metric"] == "rf_frames_per_s" and b["unit"] == "frames/s" and b["higher_is_better"] is True
+    assert b["n_gpus"] == 1 and b["steps"] == 1 and b["value"] > 0 and b["ms_per_step"] > 0 and b["vs_baseline"] is None
+    assert b["config"]["config"] == "c2" and b["config"]["elements"] == 256 and b["config"]["samples_per_element"] == 16
+    cb = b["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == b["value"] and "sample" in cb
+    e = b["e2e"]
+    assert e["value"] == b["value"] and e["unit"] == b["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
